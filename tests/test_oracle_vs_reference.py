@@ -1,0 +1,177 @@
+"""oracle/port.py against (a) the UNMODIFIED reference functions run here through
+oracle/refimport.py (skipped where /root/reference is absent) and (b) the committed
+vectors those functions produced (tests/golden/ref_vectors.npz, always run)."""
+import numpy as np
+import pytest
+
+from oracle import port, refimport, shims
+from oracle.gen_golden import small_scene
+from tests import goldenio
+
+needs_ref = pytest.mark.skipif(not refimport.available(), reason="/root/reference not present")
+
+
+def _eq(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(a, b, equal_nan=True), np.nanmax(np.abs(a - b))
+
+
+# ------------------------------------------------------------------ committed vectors
+def test_vectors_mpl_and_intensity():
+    v = goldenio.load_ref_vectors()
+    d, a, polys = small_scene(int(v["scene7_seed"][0]))
+    H, W = d.shape
+    masks = np.stack([port.rasterize_polygon(P, (H, W)) for P in polys])
+    assert np.array_equal(np.packbits(masks), v["mpl_masks"])
+    img = d.astype(np.float32)
+    bc, B = port.int_bg_correct(img, "percentile", 1.0, None, True, 4)
+    assert B == v["int_bg_p1_s4"][0]
+    _, B2 = port.int_bg_correct(img, "hist-mode", 1.0, None, True, 4)
+    assert B2 == v["int_bg_hist_s4"][0]
+    rows = port.quantify_per_roi_multi({1: bc, 2: port.int_bg_correct(a.astype(np.float32))[0]},
+                                       polys=polys)
+    keys = list(v["int_rows_keys"])
+    _eq([[r[k] for k in keys] for r in rows], v["int_rows"])
+
+
+def test_vectors_fa():
+    v = goldenio.load_ref_vectors()
+    d, a, polys = small_scene(int(v["scene7_seed"][0]))
+    img = d.astype(np.float32)
+    stats = port.fa_global_stats(img)
+    assert np.array_equal(np.array(stats, dtype=np.float32), v["fa_stats"])
+    cfg = {'alpha': 2.0, 'min_px': 12.5, 'max_px': 400.0, 'close_radius': 1, 'subtract_bg': True}
+    tab = []
+    for i, P in enumerate(polys):
+        crop, mask, rect = port.fa_crop_and_mask(img, P.copy())
+        assert tuple(v[f"fa_rect_{i}"]) == rect
+        assert np.array_equal(np.packbits(mask), v[f"fa_mask_{i}"])
+        res, thr, bw, lab = port.analyze_fa_crop(crop, mask, cfg, stats)
+        assert np.array_equal(np.packbits(bw), v[f"fa_bw_{i}"])
+        assert np.array_equal(lab.astype(np.int32), v[f"fa_lab_{i}"])
+        for ci, cat in enumerate(("OK", "Large", "Small")):
+            for it in res[cat]:
+                tab.append([i, ci, it["label"], it["area"], float(it["mean_int_raw"]),
+                            float(it["mean_int_corr"]), it["int_den_raw"], it["int_den_corr"],
+                            it["centroid"][0], it["centroid"][1], float(thr)])
+    assert len(tab) > 5
+    _eq(tab, v["fa_table"])
+
+
+def test_vectors_fret_n2_mor():
+    v = goldenio.load_ref_vectors()
+    d, a, polys = small_scene(int(v["scene7_seed"][0]))
+    H, W = d.shape
+    p = {"bg_scope": "full", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False,
+         "donor_p": 1.0, "fret_p": 1.0, "clip_neg": True, "eps_percentile": 1.0,
+         "ratio_mode": "Donor/FRET"}
+    out = port.fret_process_pair(d.astype(np.float32), a.astype(np.float32), polys, p)
+    _eq([out["Db"], out["Ab"], out["eps"]], v["fret_scalars"])
+    assert np.array_equal(out["R_full"], v["fret_R"])
+    keys = list(v["fret_rows_keys"])
+    _eq([[r[k] for k in keys] for r in out["rows"]], v["fret_rows"])
+    assert np.array_equal(np.packbits(port.make_inside_rim_mask(out["union"], 5)), v["n2_rim5"])
+    assert np.array_equal(np.packbits(port.annulus_mask_from_poly(polys[0], (H, W), 5, 11)),
+                          v["n2_ann"])
+    _, yy = port.spectral_correct(out["Abc"], out["Dbc"], None, 0.12, 0.05, 1.1)
+    assert np.array_equal(yy, v["n2_spec"])
+    mor = [port.morphology_from_polygon(P, (H, W), 0.223) for P in polys]
+    mk = list(v["mor_keys"])
+    _eq([[m[k] for k in mk] for m in mor], v["mor_rows"])
+
+
+# ------------------------------------------------------------------ live reference
+@needs_ref
+@pytest.mark.parametrize("seed", [11, 12])
+def test_live_fluor_int(seed):
+    F = refimport.load("Fluor_INT")
+    d, a, polys = small_scene(seed, H=160, W=200)
+    rng = np.random.default_rng(seed)
+    img = d.astype(np.float32)
+    scope = rng.random(img.shape) < 0.3
+    for mode in ("percentile", "hist-mode"):
+        for sm in (None, scope):
+            for stride in (1, 4, 7):
+                r_bc, r_B = F.bg_correct(img.copy(), mode, 2.5, sm, True, stride)
+                o_bc, o_B = port.int_bg_correct(img.copy(), mode, 2.5, sm, True, stride)
+                assert r_B == o_B and np.array_equal(r_bc, o_bc)
+    bc = {1: F.bg_correct(img)[0], 2: F.bg_correct(a.astype(np.float32))[0]}
+    assert F.quantify_per_roi_multi(bc, polys=polys) == port.quantify_per_roi_multi(bc, polys=polys)
+    assert F.auto_minmax(bc[1].ravel(), 1, 99) == port.auto_minmax(bc[1].ravel(), 1, 99)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [21, 22])
+def test_live_fa(seed):
+    FA = refimport.load("FA_Analyzer")
+    d, a, polys = small_scene(seed, H=200, W=240, blobs=10)
+    img = d.astype(np.float32)
+    stats = port.fa_global_stats(img)
+    for cfg in ({'alpha': 2.0, 'min_px': 12.5, 'max_px': 300.0, 'close_radius': 1, 'subtract_bg': True},
+                {'alpha': 1.0, 'min_px': 0, 'max_px': 50.0, 'close_radius': 0, 'subtract_bg': False},
+                {'alpha': 3.0, 'min_px': 30.0, 'max_px': 5000.0, 'close_radius': 2, 'subtract_bg': True}):
+        for P in polys:
+            crop, mask, _ = port.fa_crop_and_mask(img, P.copy())
+            r = FA.analyze_fa_crop(crop, mask, cfg, stats)
+            o = port.analyze_fa_crop(crop, mask, cfg, stats)
+            assert r[1] == o[1] and np.array_equal(r[2], o[2]) and np.array_equal(r[3], o[3])
+            for cat in ("OK", "Large", "Small"):
+                assert len(r[0][cat]) == len(o[0][cat])
+                for x, y in zip(r[0][cat], o[0][cat]):
+                    for k in ("label", "area", "centroid", "mean_int_raw", "mean_int_corr",
+                              "int_den_raw", "int_den_corr", "bg_level"):
+                        assert x[k] == y[k] and type(x[k]) is type(y[k]), k
+
+
+@needs_ref
+def test_live_fret_and_nesprin2():
+    FR = refimport.load("fret_ratio_builder")
+    N2 = refimport.load("Nesprin2_FRET_Builder")
+    d, a, polys = small_scene(31, H=160, W=200)
+    D, A = d.astype(np.float32), a.astype(np.float32)
+    H, W = D.shape
+    u = np.zeros((H, W), bool)
+    for P in polys:
+        u |= FR.rasterize_polygon(P, (H, W))
+    for mode in ("percentile", "hist-mode"):
+        for sm in (None, u):
+            r = FR.bg_correct(D.copy(), mode, 1.0, sm, True)
+            o = port.fret_bg_correct(D.copy(), mode, 1.0, sm, True)
+            assert r[1] == o[1] and np.array_equal(r[0], o[0])
+    Dn = D.copy()
+    Dn[D >= 65535] = np.nan
+    for sm in (None, u):
+        r = N2.bg_correct(Dn.copy(), "percentile", 1.0, sm, True)
+        o = port.n2_bg_correct(Dn.copy(), "percentile", 1.0, sm, True)
+        assert r[1] == o[1] and np.array_equal(r[0], o[0], equal_nan=True)
+    assert N2.pick_epsilon(Dn[u], 5.0, 1.0) == port.n2_pick_epsilon(Dn[u], 5.0, 1.0)
+    assert np.array_equal(N2.make_inside_rim_mask(u, 5), port.make_inside_rim_mask(u, 5))
+    assert np.array_equal(N2.annulus_mask_from_poly(polys[0], (H, W), 5, 11),
+                          port.annulus_mask_from_poly(polys[0], (H, W), 5, 11))
+    Rr = FR.quantify_per_roi((D + 5) / (A + 5), polys, extra_imgs={"donor": D, "yfret": A})
+    Ro = port.fret_quantify_per_roi((D + 5) / (A + 5), polys, extra_imgs={"donor": D, "yfret": A})
+    assert Rr == Ro
+
+
+@needs_ref
+def test_live_mor():
+    MOR = refimport.load("MOR_by_ROI")
+    d, a, polys = small_scene(41, H=160, W=200)
+    for P in polys:
+        r = MOR.morphology_from_polygon(P, d.shape, 0.223)
+        o = port.morphology_from_polygon(P, d.shape, 0.223)
+        assert r == o
+
+
+def test_label_numbering_is_raster_order():
+    """shims.label must number components by first pixel in raster order
+    (skimage.measure.label)."""
+    rng = np.random.default_rng(5)
+    for _ in range(5):
+        bw = rng.random((40, 53)) < 0.45
+        lab = shims.label(bw)
+        firsts = [np.flatnonzero(lab.ravel() == k)[0] for k in range(1, lab.max() + 1)]
+        assert firsts == sorted(firsts)
+        # 8-connectivity: diagonal neighbours share a label
+        assert (lab[:-1, :-1][bw[:-1, :-1] & bw[1:, 1:]] == lab[1:, 1:][bw[:-1, :-1] & bw[1:, 1:]]).all()
