@@ -1,0 +1,69 @@
+"""ctypes binding of libipb200.so (C ABI declared in include/ipb200.h).
+
+The product loads exactly one library: ``imageprocess_b200/lib/libipb200.so`` built by
+``__graft_entry__.build()`` with nvcc for sm_100a.  There is no CPU fallback: if the library
+is missing, ``load()`` raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libipb200.so")
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_longlong
+_f = ctypes.c_float
+_d = ctypes.c_double
+
+# name -> argtypes (all return int status unless listed in _RESTYPE)
+_PROTOS = {
+    "ipb_version": [],
+    "ipb_is_emulated": [],
+    "ipb_rasterize_rois": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+}
+_RESTYPE = {"ipb_last_error": ctypes.c_char_p}
+
+
+class IpbError(RuntimeError):
+    pass
+
+
+class Lib:
+    """Thin checked wrapper: ``lib.call('ipb_xxx', *args)`` raises IpbError on status < 0."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise IpbError(
+                f"{path} not found: build the CUDA extension first "
+                "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        self.path = path
+        self.c = ctypes.CDLL(path)
+        self.c.ipb_last_error.restype = ctypes.c_char_p
+        self.c.ipb_last_error.argtypes = []
+        for name, argtypes in _PROTOS.items():
+            fn = getattr(self.c, name)          # AttributeError if the symbol is missing
+            fn.argtypes = argtypes
+            fn.restype = _i
+
+    def call(self, name, *args):
+        rc = getattr(self.c, name)(*args)
+        if rc < 0:
+            msg = self.c.ipb_last_error()
+            raise IpbError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
+        return rc
+
+    def exported(self):
+        return list(_PROTOS) + list(_RESTYPE)
+
+
+_lib = None
+
+
+def load() -> Lib:
+    global _lib
+    if _lib is None:
+        _lib = Lib(LIB_PATH)
+        if _lib.c.ipb_is_emulated():
+            raise IpbError("refusing to run the product on an emulated build")
+    return _lib

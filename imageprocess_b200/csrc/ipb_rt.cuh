@@ -1,0 +1,69 @@
+// ipb_rt.cuh -- launch/runtime abstraction shared by every kernel file.
+//
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a (this is the only build the
+// package loads).  With -DIPB_EMULATE the same kernel sources compile with g++ against
+// tests/emu/cuda_emu.h so that the CPU test tier can run the kernels' logic in the build
+// container (no GPU there); that library lives under tests/ and is never loaded by the
+// product.
+#pragma once
+#include <stdint.h>
+
+#ifdef IPB_EMULATE
+#include "cuda_emu.h"
+#define IPB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    IPB_EMU_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
+#define IPB_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::g_blk->dyn_smem)
+#define IPB_HD static inline
+#else
+#include <cuda_runtime.h>
+#define IPB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define IPB_DYN_SMEM(T, name)                                        \
+    extern __shared__ __align__(16) unsigned char name##_raw_[];     \
+    T* name = reinterpret_cast<T*>(name##_raw_)
+#define IPB_HD __device__ __forceinline__
+#endif
+
+#define IPB_FULL 0xffffffffu
+
+// ---- status codes (mirrored in include/ipb200.h)
+#define IPB_OK 0
+#define IPB_ERR_ARG (-1)
+#define IPB_ERR_CUDA (-2)
+#define IPB_ERR_WORKSPACE (-3)
+#define IPB_ERR_UNSUPPORTED (-4)
+
+void ipb_set_error(const char* fmt, ...);
+int ipb_check_launch(const char* what);
+
+#define IPB_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            ipb_set_error(__VA_ARGS__);        \
+            return IPB_ERR_ARG;                \
+        }                                      \
+    } while (0)
+
+static inline unsigned ipb_div_up(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- warp helpers
+__device__ __forceinline__ unsigned ipb_lane() { return threadIdx.x & 31u; }
+
+template <typename T>
+__device__ __forceinline__ T ipb_warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(IPB_FULL, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T ipb_warp_min(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { T u = __shfl_xor_sync(IPB_FULL, v, o); v = u < v ? u : v; }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T ipb_warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { T u = __shfl_xor_sync(IPB_FULL, v, o); v = u > v ? u : v; }
+    return v;
+}

@@ -1,0 +1,82 @@
+"""Device-memory plumbing.  PyTorch is used only for what the task allows it for: device
+allocations, streams and (in pipeline.py) torch.distributed.  Every buffer handed to the
+C ABI is a raw byte tensor; dtype/shape live in the small DevBuf wrapper."""
+import numpy as np
+
+
+class DevBuf:
+    """A typed view over a flat byte buffer owned by a memory backend."""
+    __slots__ = ("raw", "dtype", "shape", "mem")
+
+    def __init__(self, raw, dtype, shape, mem):
+        self.raw, self.dtype, self.shape, self.mem = raw, np.dtype(dtype), tuple(shape), mem
+
+    @property
+    def ptr(self):
+        return self.mem.raw_ptr(self.raw)
+
+    @property
+    def nbytes(self):
+        return int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+
+    def host(self):
+        return self.mem.to_host(self)
+
+    def zero_(self):
+        self.mem.zero(self)
+        return self
+
+
+class TorchMem:
+    """CUDA memory through torch (caching allocator, current stream)."""
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("imageprocess_b200 needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+
+    # -- allocation
+    def empty(self, shape, dtype):
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        n = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        raw = self.torch.empty(max(n, 16), dtype=self.torch.uint8, device=self.device)
+        return DevBuf(raw, dtype, shape, self)
+
+    def zeros(self, shape, dtype):
+        return self.empty(shape, dtype).zero_()
+
+    def zero(self, buf):
+        buf.raw.zero_()
+
+    def from_host(self, arr, pinned=None):
+        arr = np.ascontiguousarray(arr)
+        buf = self.empty(arr.shape, arr.dtype)
+        if arr.nbytes:
+            src = self.torch.from_numpy(arr.view(np.uint8).reshape(-1))
+            buf.raw[: arr.nbytes].copy_(src, non_blocking=False)
+        return buf
+
+    def wrap_tensor(self, t, dtype=None, shape=None):
+        """Wrap an existing contiguous CUDA tensor (no copy)."""
+        assert t.is_cuda and t.is_contiguous()
+        raw = t.view(self.torch.uint8).reshape(-1)
+        return DevBuf(raw, dtype or np.dtype(str(t.dtype).replace("torch.", "")), shape or tuple(t.shape), self)
+
+    def to_host(self, buf):
+        n = buf.nbytes
+        if n == 0:
+            return np.zeros(buf.shape, dtype=buf.dtype)
+        h = buf.raw[:n].cpu().numpy()
+        return h.view(buf.dtype).reshape(buf.shape).copy()
+
+    def raw_ptr(self, raw):
+        return int(raw.data_ptr())
+
+    @property
+    def stream(self):
+        return int(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        self.torch.cuda.current_stream(self.device).synchronize()

@@ -1,0 +1,51 @@
+"""tests/emu/emu_backend.py -- TEST INFRASTRUCTURE.  numpy-backed memory + the emulated
+library, so the product's host logic (imageprocess_b200/ops.py etc.) can drive the product's
+kernels on the CPU in `pytest -m "not gpu"`.  Never imported by the product."""
+import numpy as np
+
+from imageprocess_b200._lib import Lib
+from imageprocess_b200.device import DevBuf
+from tests.emu import build_emu
+
+
+class NumpyMem:
+    def empty(self, shape, dtype):
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        n = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        raw = np.full(max(n, 16) + 64, 0xA5, dtype=np.uint8)     # poison: catches missing init
+        off = (-raw.ctypes.data) % 64
+        return DevBuf(raw[off:off + max(n, 16)], dtype, shape, self)
+
+    def zeros(self, shape, dtype):
+        return self.empty(shape, dtype).zero_()
+
+    def zero(self, buf):
+        buf.raw[:] = 0
+
+    def from_host(self, arr, pinned=None):
+        arr = np.ascontiguousarray(arr)
+        buf = self.empty(arr.shape, arr.dtype)
+        buf.raw[: arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        return buf
+
+    def to_host(self, buf):
+        return buf.raw[: buf.nbytes].view(buf.dtype).reshape(buf.shape).copy()
+
+    def raw_ptr(self, raw):
+        return int(raw.ctypes.data)
+
+    stream = 0
+
+    def sync(self):
+        pass
+
+
+_lib = None
+
+
+def emu_lib():
+    global _lib
+    if _lib is None:
+        _lib = Lib(build_emu.build())
+        assert _lib.c.ipb_is_emulated() == 1
+    return _lib
