@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: Mpix/s on synthetic 2048x2048 uint16 two-channel
+time-lapse frames (config C4 of SURVEY.md 8(d)), per GPU and over N GPUs, with the HBM
+roofline of the dominant kernel and the reference CPU path timed beside it.
+
+  python bench.py --gpus 1 --steps K --warmup W              our arm (CUDA, this repo)
+  python bench.py --impl reference --steps K --warmup W      the reference's CPU path (oracle
+                                                             port of it)
+For N > 1 the driver launches it under torchrun (one rank per GPU); frames are sharded by
+rank with no data-path collective (weak scaling), only the timing is all-reduced (max).
+
+A "step" is one pass of the complete per-frame hot path (ROI rasterisation, backgrounds,
+FRET ratio image, per-ROI intensity + ratio statistics, FA segmentation) over one batch of
+`--frames` frames per GPU.  Inputs are larger than L2 (frames*16 MiB), so no L2 flush is
+needed between timed iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H = W = 2048
+N_CELLS = 24
+BLOBS = 60
+BYTES_PER_PX = 8.0          # 4 B read (2 x uint16) + 4 B ratio image written
+
+FRET_P = {"bg_scope": "full", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False,
+          "donor_p": 1.0, "fret_p": 1.0, "clip_neg": True, "eps_percentile": 1.0,
+          "ratio_mode": "Donor/FRET"}                       # fret_ratio_builder.py:567-589
+INT_TASK = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4,
+            "percentile": 1.0, "per_channel_p": False, "ch_p_map": {}}   # Fluor_INT defaults
+FA_PARAMS = {"alpha": 2.0, "min_area_um": 1.5, "max_area_um": 30.0, "close_radius": 1,
+             "subtract_bg": True}                           # FA_Analyzer.py:298-304
+FA_PX = 0.112
+
+
+def make_frames(n_frames, seed=1234, n_unique=2):
+    """C4 frames: n_unique synthetic base frames (same cell geometry), the rest derived by a
+    per-frame integer jitter so that every frame holds different pixel data."""
+    from imageprocess_b200 import synth
+    base = []
+    polys = None
+    for u in range(n_unique):
+        d, a, polys_u = synth.fret_frame(seed=seed, H=H, W=W, n_cells=N_CELLS, r_min=80, r_max=160,
+                                         blobs_per_cell=BLOBS, drift=1.0 + 0.2 * (u / max(1, n_unique - 1) - 0.5))
+        polys = polys_u
+        base.append(np.stack([d, a]))
+    rng = np.random.default_rng(seed + 17)
+    out = np.empty((n_frames, 2, H, W), dtype=np.uint16)
+    for t in range(n_frames):
+        b = base[t % n_unique]
+        if t < n_unique:
+            out[t] = b
+        else:
+            j = rng.integers(0, 7, size=(2, H, W), dtype=np.uint16)
+            out[t] = np.minimum(b.astype(np.uint32) + j, 65535).astype(np.uint16)
+    return out, polys
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons = index, [], set()
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in o.strip().split(",")]
+                self.samples.append((float(f[0]), float(f[1])))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=3)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1],
+                "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU reference
+def _ref_frame(args):
+    """One frame through the reference's CPU path (oracle port): FRET + ROI intensity + FA."""
+    planes, polys = args
+    from oracle import port
+    d, a = planes[0], planes[1]
+    D, A = d.astype(np.float32), a.astype(np.float32)
+    port.fret_process_pair(D, A, polys, FRET_P)
+    port.int_process_key({1: D.copy(), 2: A.copy()}, polys, None, INT_TASK)
+    port.fa_batch_rows(D, polys, FA_PARAMS, FA_PX, with_contours=False)
+    return planes.shape[-1] * planes.shape[-2]
+
+
+def cpu_reference(frames, polys, workers):
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if workers <= 1:
+        for f in range(frames.shape[0]):
+            _ref_frame((frames[f], polys))
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            pool.map(_ref_frame, [(frames[f], polys) for f in range(frames.shape[0])])
+    dt = time.perf_counter() - t0
+    return frames.shape[0] * H * W / dt / 1e6, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    workers = min(cores, 8)         # the reference's own pool size: Fluor_INT.py:2211-2216
+    n = workers                     # one frame per worker per step: bounded sample
+    frames, polys = make_frames(max(2, min(n, 2)), n_unique=2)
+    frames = np.concatenate([frames] * ((n + 1) // 2))[:n]
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(frames[:workers], polys, workers)
+    vals = []
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_reference(frames, polys, workers)
+        vals.append(v)
+        t_all += dt
+    value = n * args.steps * H * W / t_all / 1e6
+    line = {"impl": "reference", "metric": "Mpix/s (2048x2048 uint16 2ch FRET+FA+ROI-intensity time-lapse)",
+            "value": value, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "C4-synth 2048x2048x2ch uint16, 24 ROIs, FA blobs",
+                                            "frames_per_step": n},
+            "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": workers, "kind": "port",
+                             "sample": f"{n} frames/step through oracle port (FRET+INT+FA, find_contours skipped), "
+                                       f"multiprocessing pool of {workers}"},
+            "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import imageprocess_b200 as ipb
+    from imageprocess_b200 import timelapse
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    eng = ipb.engine(f"cuda:{local}")
+    F = args.frames
+    frames, polys = make_frames(F, seed=1234 + 1000 * rank)
+    polys_pf = [polys] * F
+    shape = (F, 2, H, W)
+    pinned_np, pinned_t = eng.mem.pinned(shape, np.uint16)
+    pinned_np[...] = frames
+    planes = eng.mem.empty(shape, np.uint16)
+    eng.mem.upload_async(planes, pinned_t)
+    eng.mem.sync()
+    job = timelapse.TimelapseJob(eng, shape, polys_pf, FRET_P, INT_TASK, FA_PARAMS, FA_PX)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d2h = 0
+        for _ in range(steps):
+            d2h = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, d2h
+
+    def step_resident():
+        return job.run(planes)["d2h_bytes"]
+
+    def step_e2e():
+        eng.mem.upload_async(planes, pinned_t)          # H2D of this step's inputs (pinned)
+        return job.run(planes)["d2h_bytes"]             # tables come back D2H inside run()
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    launches0 = eng.launches
+    with ClockSampler(local) as clk:
+        eng.profile_start()
+        ms, d2h = timed(step_resident, args.steps)
+        prof = eng.profile_stop()
+    launches = eng.launches - launches0
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    mpix_total = world * F * args.steps * H * W / 1e6
+    value = mpix_total / (ms / 1e3)
+    e2e_value = mpix_total / (ms_e2e / 1e3)
+    line = {"metric": "Mpix/s (2048x2048 uint16 2ch FRET+FA+ROI-intensity time-lapse)",
+            "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u16/f32", "data": "synthetic",
+            "config": {"workload": "C4-synth 2048x2048x2ch uint16, 24 ROIs, 60 FA blobs/cell",
+                       "frames_per_step_per_gpu": F, "l2": "inputs larger than L2 (no flush needed)",
+                       "stages": job.stages},
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(frames.nbytes),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clk.summary()}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
+        dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
+        kern = {k: {"calls": v[0], "ms": round(v[1], 4), "share": round(v[1] / max(ms, 1e-9), 4)}
+                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        if dom is not None:
+            name, (ncalls, tot_ms) = dom
+            per_launch_ms = tot_ms / max(1, ncalls)
+            alg_bytes = job.algorithmic_bytes(name)
+            achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak,
+                                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                                "launch_ms": per_launch_ms}
+        line["pipeline_roofline"] = {"bytes_per_px": BYTES_PER_PX,
+                                     "achieved_gbs": value / world * 1e6 * BYTES_PER_PX / 1e9,
+                                     "frac_of_peak": value / world * 1e6 * BYTES_PER_PX / 1e9 / peak}
+        line["kernels"] = kern
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            t0 = time.perf_counter()
+            v, dt = cpu_reference(frames[:1], polys, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": 1, "kind": "port",
+                                    "sample": f"1 frame of the same workload through the oracle port "
+                                              f"(FRET+INT+FA, find_contours skipped), {dt:.1f} s"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

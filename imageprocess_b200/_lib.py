@@ -20,7 +20,15 @@ _d = ctypes.c_double
 _PROTOS = {
     "ipb_version": [],
     "ipb_is_emulated": [],
+    "ipb_sizeof": [_i],
     "ipb_rasterize_rois": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "ipb_hist_u16": [_vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
+    "ipb_hist_quantiles": [_vp, _vp, _vp, _i, _vp, _vp],
+    "ipb_scatter_qvalues": [_vp, _vp, _i, _vp, _vp],
+    "ipb_fret_eps": [_vp, _i, _i, _i, _f, _vp, _vp],
+    "ipb_fa_params": [_vp, _vp, _vp, _i, _i64, _f, _vp, _vp],
+    "ipb_fret_pixels": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ipb_region_stats": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
 }
 _RESTYPE = {"ipb_last_error": ctypes.c_char_p}
 

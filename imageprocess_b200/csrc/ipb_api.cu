@@ -11,6 +11,9 @@
 #include "ipb_rt.cuh"
 #include "ipb_exact.cuh"
 #include "ipb_raster.cuh"
+#include "ipb_hist.cuh"
+#include "ipb_roistats.cuh"
+#include "ipb_fret.cuh"
 
 static thread_local char g_ipb_err[512] = "";
 
@@ -84,6 +87,128 @@ int ipb_rasterize_rois(int rule, int n_rois, const double* verts_xy, const int32
                    mask_pool, area, union_bits, union_wpr, frame_h);
     }
     return ipb_check_launch("ipb_k_raster");
+}
+
+// ---------------------------------------------------------------- histograms / quantiles
+int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
+                 int has_masked_stride, const uint32_t* union_bits, int union_wpr,
+                 uint64_t* row_rank_scratch, uint32_t* hist, uint64_t* stats, void* stream)
+{
+    IPB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535, "ipb_hist_u16: n_jobs %d out of range", n_jobs);
+    if (n_jobs == 0) return IPB_OK;
+    IPB_REQUIRE(planes && jobs && hist && stats && H > 0 && W > 0, "ipb_hist_u16: bad argument");
+    IPB_REQUIRE(!has_masked_stride || (union_bits && row_rank_scratch), "ipb_hist_u16: masked stride needs union + scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    IPB_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)IPB_HIST_BINS * n_jobs, st), "memset hist");
+    IPB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(uint64_t) * 4 * (size_t)n_jobs, st), "memset stats");
+    int chunks = (592 + n_jobs - 1) / n_jobs;
+    int max_chunks = H / 32 > 0 ? H / 32 : 1;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    const int rows_per_chunk = (H + chunks - 1) / chunks;
+    chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
+    const size_t smem = sizeof(unsigned) * IPB_HIST_WIN;
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist smem");
+    IPB_LAUNCH(ipb_k_hist_u16, dim3(chunks, n_jobs), dim3(IPB_HIST_THREADS), smem, stream,
+               planes, H, W, (const IpbHistJob*)jobs, rows_per_chunk, union_bits, union_wpr,
+               hist, (unsigned long long*)stats);
+    int rc = ipb_check_launch("ipb_k_hist_u16");
+    if (rc) return rc;
+    if (has_masked_stride) {
+        IPB_LAUNCH(ipb_k_hist_masked_stride, dim3(n_jobs), dim3(256), 0, stream, planes, H, W,
+                   (const IpbHistJob*)jobs, union_bits, union_wpr, (unsigned long long*)row_rank_scratch,
+                   hist, (unsigned long long*)stats);
+        rc = ipb_check_launch("ipb_k_hist_masked_stride");
+    }
+    return rc;
+}
+
+int ipb_hist_quantiles(const uint32_t* hist, const uint64_t* stats, const void* qjobs, int n_q,
+                       void* qout, void* stream)
+{
+    if (n_q <= 0) return IPB_OK;
+    IPB_REQUIRE(hist && stats && qjobs && qout, "ipb_hist_quantiles: null pointer");
+    IPB_LAUNCH(ipb_k_hist_quantiles, dim3(n_q), dim3(256), 0, stream, hist,
+               (const unsigned long long*)stats, (const IpbQJob*)qjobs, (IpbQOut*)qout);
+    return ipb_check_launch("ipb_k_hist_quantiles");
+}
+
+int ipb_scatter_qvalues(const void* qout, const int32_t* dst_idx, int n, float* dst, void* stream)
+{
+    if (n <= 0) return IPB_OK;
+    IPB_REQUIRE(qout && dst_idx && dst, "ipb_scatter_qvalues: null pointer");
+    IPB_LAUNCH(ipb_k_scatter_qvalues, dim3(ipb_div_up(n, 128)), dim3(128), 0, stream,
+               (const IpbQOut*)qout, dst_idx, n, dst);
+    return ipb_check_launch("ipb_k_scatter_qvalues");
+}
+
+int ipb_fret_eps(const void* qout_eps, int n_frames, int denom_slot, int clip_neg, float eps_abs,
+                 float* fparams, void* stream)
+{
+    if (n_frames <= 0) return IPB_OK;
+    IPB_REQUIRE(qout_eps && fparams && (denom_slot == IPB_FP_BD || denom_slot == IPB_FP_BA), "ipb_fret_eps: bad argument");
+    IPB_LAUNCH(ipb_k_fret_eps, dim3(ipb_div_up(n_frames, 128)), dim3(128), 0, stream,
+               (const IpbQOut*)qout_eps, n_frames, denom_slot, clip_neg, eps_abs, fparams);
+    return ipb_check_launch("ipb_k_fret_eps");
+}
+
+int ipb_fa_params(const uint64_t* stats, const int32_t* stat_idx, const void* qout_bg, int n_frames,
+                  int64_t npx, float alpha, float* fa, void* stream)
+{
+    if (n_frames <= 0) return IPB_OK;
+    IPB_REQUIRE(stats && stat_idx && qout_bg && fa && npx > 0, "ipb_fa_params: bad argument");
+    IPB_LAUNCH(ipb_k_fa_params, dim3(ipb_div_up(n_frames, 128)), dim3(128), 0, stream,
+               (const unsigned long long*)stats, stat_idx, (const IpbQOut*)qout_bg, n_frames,
+               (long long)npx, alpha, fa);
+    return ipb_check_launch("ipb_k_fa_params");
+}
+
+// ---------------------------------------------------------------- fused FRET pass
+int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const void* cfg_host,
+                    const float* fparams, const uint32_t* union_bits, int union_wpr,
+                    float* R, float* Ralt, float* Rroi, float* Dcorr, float* Acorr, void* stream)
+{
+    if (n_frames <= 0) return IPB_OK;
+    IPB_REQUIRE(planes && cfg_host && fparams && H > 0 && W > 0, "ipb_fret_pixels: bad argument");
+    IpbFretCfg cfg;
+    memcpy(&cfg, cfg_host, sizeof(cfg));
+    IPB_REQUIRE(cfg.n_ch > 0 && cfg.donor_ch >= 0 && cfg.donor_ch < cfg.n_ch && cfg.acc_ch >= 0 &&
+                cfg.acc_ch < cfg.n_ch && cfg.aonly_ch < cfg.n_ch, "ipb_fret_pixels: bad channel indices");
+    const long long work = (long long)n_frames * H * W / 8;
+    long long blocks = (work + 255) / 256;
+    const long long cap = 148LL * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    IPB_LAUNCH(ipb_k_fret_pixels, dim3((unsigned)blocks), dim3(256), 0, stream, planes, n_frames, H, W,
+               cfg, fparams, union_bits, union_wpr, R, Ralt, Rroi, Dcorr, Acorr);
+    return ipb_check_launch("ipb_k_fret_pixels");
+}
+
+// ---------------------------------------------------------------- region statistics
+int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
+                     const uint32_t* and_bits, int and_wpr, int H, int W, const uint16_t* planes,
+                     const float* images, const float* bvals, void* out, void* stream)
+{
+    if (n_jobs <= 0) return IPB_OK;
+    IPB_REQUIRE(regions && jobs && mask_pool && out && H > 0 && W > 0, "ipb_region_stats: bad argument");
+    IPB_LAUNCH(ipb_k_region_stats, dim3(n_jobs), dim3(IPB_RS_THREADS), 0, stream,
+               (const IpbRegion*)regions, (const IpbStatJob*)jobs, mask_pool, and_bits, and_wpr, H, W,
+               planes, images, bvals, (IpbStatOut*)out);
+    return ipb_check_launch("ipb_k_region_stats");
+}
+
+int ipb_sizeof(int what)
+{
+    switch (what) {
+        case 0: return (int)sizeof(IpbHistJob);
+        case 1: return (int)sizeof(IpbQJob);
+        case 2: return (int)sizeof(IpbQOut);
+        case 3: return (int)sizeof(IpbRegion);
+        case 4: return (int)sizeof(IpbStatJob);
+        case 5: return (int)sizeof(IpbStatOut);
+        case 6: return (int)sizeof(IpbFretCfg);
+        default: return -1;
+    }
 }
 
 }  // extern "C"

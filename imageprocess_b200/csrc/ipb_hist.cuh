@@ -1,0 +1,248 @@
+// ipb_hist.cuh -- exact 65 536-bin integer histograms of uint16 planes and the order
+// statistics / float32 percentiles derived from them.
+//
+// Every background / epsilon / preview percentile of the reference is np.percentile over a
+// float32 copy of uint16 pixels (all, a strided subsample, or the pixels under a mask).  The
+// order statistics of such a sample are integers, so one exact integer histogram per
+// (plane, sampling pattern) reproduces them bit-for-bit; numpy's float32 index/lerp
+// arithmetic is then replayed by ipb_exact.cuh.
+//
+// ipb_k_hist_u16: grid (chunks, jobs); one CTA streams a band of rows with 128-bit loads and
+// counts into a shared-memory window of the low IPB_HIST_WIN bins (fluorescence data lives
+// there); brighter values go straight to global atomics.  The window is flushed with one
+// global atomic per non-empty bin.  Optionally the exact integer moments (sum, sum of
+// squares) of ALL pixels of the plane are accumulated in the same pass (FA global stats).
+#pragma once
+#include "ipb_rt.cuh"
+#include "ipb_exact.cuh"
+
+#define IPB_HIST_BINS 65536
+#define IPB_HIST_WIN 24576
+#define IPB_HIST_THREADS 1024
+
+#define IPB_PAT_FULL 0
+#define IPB_PAT_STRIDE1D 1   // flat index % k == 0      (vals[::k] of the raveled plane)
+#define IPB_PAT_STRIDE2D 2   // y % k == 0 && x % k == 0 (img[::k, ::k])
+#define IPB_PAT_MASKED 3     // pixels under the frame's union bitmask
+#define IPB_PAT_MASKED_STRIDE 4  // every k-th masked pixel in raster order (img[mask][::k])
+
+struct IpbHistJob {
+    int plane;        // index of the uint16 plane (frame * C + channel)
+    int pattern;      // IPB_PAT_*
+    int k;            // stride for the strided patterns
+    int mask_frame;   // frame index into the union bitmask (masked patterns)
+    int moments;      // != 0: also accumulate sum / sumsq of ALL pixels of the plane
+    int pad0, pad1, pad2;
+};
+
+// out_stats[job] = { n_selected, sum_all, sumsq_all, reserved }
+__global__ void __launch_bounds__(IPB_HIST_THREADS)
+ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
+               const IpbHistJob* __restrict__ jobs, int rows_per_chunk,
+               const unsigned* __restrict__ union_bits, int union_wpr,
+               unsigned* __restrict__ hist, unsigned long long* __restrict__ out_stats)
+{
+    IPB_DYN_SMEM(unsigned, sh);
+    const IpbHistJob job = jobs[blockIdx.y];
+    const int y_beg = (int)blockIdx.x * rows_per_chunk;
+    int y_end = y_beg + rows_per_chunk;
+    if (y_end > H) y_end = H;
+    unsigned* gh = hist + (size_t)blockIdx.y * IPB_HIST_BINS;
+    for (int b = threadIdx.x; b < IPB_HIST_WIN; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+
+    const unsigned short* img = planes + (size_t)job.plane * H * W;
+    const unsigned* ubits = (job.pattern == IPB_PAT_MASKED) ? union_bits + (size_t)job.mask_frame * H * union_wpr : nullptr;
+    unsigned long long s1 = 0, s2 = 0, nsel = 0;
+    const int k = job.k > 0 ? job.k : 1;
+    const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0);
+
+#define IPB_HIST_COUNT(v)                                      \
+    do {                                                       \
+        unsigned vv_ = (v);                                    \
+        if (vv_ < IPB_HIST_WIN) atomicAdd(&sh[vv_], 1u);       \
+        else atomicAdd(&gh[vv_], 1u);                          \
+        ++nsel;                                                \
+    } while (0)
+
+    if (y_beg < y_end) {
+        if (vec_ok) {
+            const int vpr = W >> 3;                                   // 8-pixel vectors per row
+            const long long nvec = (long long)(y_end - y_beg) * vpr;
+            for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
+                const int y = y_beg + (int)(i / vpr);
+                const int x0 = ((int)(i % vpr)) << 3;
+                if (job.pattern == IPB_PAT_STRIDE2D && !job.moments && (y % k) != 0) continue;
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + x0));
+                const unsigned w[4] = {q.x, q.y, q.z, q.w};
+                unsigned sel = 0;                                     // bit i: pixel x0+i selected
+                if (job.pattern == IPB_PAT_FULL) sel = 0xffu;
+                else if (job.pattern == IPB_PAT_STRIDE1D) {
+                    long long flat = (long long)y * W + x0;
+                    int first = (int)((k - (flat % k)) % k);
+                    for (int t = first; t < 8; t += k) sel |= 1u << t;
+                } else if (job.pattern == IPB_PAT_STRIDE2D) {
+                    if ((y % k) == 0) {
+                        int first = (k - (x0 % k)) % k;
+                        for (int t = first; t < 8; t += k) sel |= 1u << t;
+                    }
+                } else if (job.pattern == IPB_PAT_MASKED) {
+                    sel = (ubits[(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
+                }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                    if (job.moments) { s1 += v; s2 += (unsigned long long)v * v; }
+                    if ((sel >> t) & 1u) IPB_HIST_COUNT(v);
+                }
+            }
+        } else {
+            const long long npx = (long long)(y_end - y_beg) * W;
+            for (long long i = threadIdx.x; i < npx; i += blockDim.x) {
+                const int y = y_beg + (int)(i / W), x = (int)(i % W);
+                const unsigned v = img[(size_t)y * W + x];
+                if (job.moments) { s1 += v; s2 += (unsigned long long)v * v; }
+                bool sel;
+                if (job.pattern == IPB_PAT_FULL) sel = true;
+                else if (job.pattern == IPB_PAT_STRIDE1D) sel = (((long long)y * W + x) % k) == 0;
+                else if (job.pattern == IPB_PAT_STRIDE2D) sel = (y % k) == 0 && (x % k) == 0;
+                else if (job.pattern == IPB_PAT_MASKED) sel = (ubits[(size_t)y * union_wpr + (x >> 5)] >> (x & 31)) & 1u;
+                else sel = false;
+                if (sel) IPB_HIST_COUNT(v);
+            }
+        }
+    }
+#undef IPB_HIST_COUNT
+    __syncthreads();
+    for (int b = threadIdx.x; b < IPB_HIST_WIN; b += blockDim.x) {
+        const unsigned c = sh[b];
+        if (c) atomicAdd(&gh[b], c);
+    }
+    // block reduction of the three 64-bit counters
+    s1 = ipb_warp_sum(s1); s2 = ipb_warp_sum(s2); nsel = ipb_warp_sum(nsel);
+    __shared__ unsigned long long red[3][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; red[2][warp] = nsel; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        unsigned long long a = lane < nw ? red[0][lane] : 0ull;
+        unsigned long long b = lane < nw ? red[1][lane] : 0ull;
+        unsigned long long c = lane < nw ? red[2][lane] : 0ull;
+        a = ipb_warp_sum(a); b = ipb_warp_sum(b); c = ipb_warp_sum(c);
+        if (lane == 0) {
+            unsigned long long* st = out_stats + (size_t)blockIdx.y * 4;
+            if (c) atomicAdd(&st[0], c);
+            if (a) atomicAdd(&st[1], a);
+            if (b) atomicAdd(&st[2], b);
+        }
+    }
+}
+
+// img[mask][::k]: every k-th masked pixel in raster order.  One CTA per job walks the rows
+// in order with a running rank (exclusive scan of per-row popcounts first).  Rare path
+// (Fluor_INT bg_scope = "roi_union" with bg_stride > 1, reference Fluor_INT.py:465-470).
+__global__ void __launch_bounds__(256)
+ipb_k_hist_masked_stride(const unsigned short* __restrict__ planes, int H, int W,
+                         const IpbHistJob* __restrict__ jobs, const unsigned* __restrict__ union_bits,
+                         int union_wpr, unsigned long long* __restrict__ row_rank /* [jobs][H] scratch */,
+                         unsigned* __restrict__ hist, unsigned long long* __restrict__ out_stats)
+{
+    const IpbHistJob job = jobs[blockIdx.x];
+    if (job.pattern != IPB_PAT_MASKED_STRIDE) return;
+    const unsigned short* img = planes + (size_t)job.plane * H * W;
+    const unsigned* ubits = union_bits + (size_t)job.mask_frame * H * union_wpr;
+    unsigned* gh = hist + (size_t)blockIdx.x * IPB_HIST_BINS;
+    unsigned long long* rr = row_rank + (size_t)blockIdx.x * H;
+    const int k = job.k > 0 ? job.k : 1;
+    // per-row popcounts
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        unsigned c = 0;
+        for (int j = 0; j < union_wpr; ++j) c += __popc(ubits[(size_t)y * union_wpr + j]);
+        rr[y] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                      // H <= 16384: a serial exclusive scan is fine here
+        unsigned long long acc = 0;
+        for (int y = 0; y < H; ++y) { unsigned long long c = rr[y]; rr[y] = acc; acc += c; }
+    }
+    __syncthreads();
+    unsigned long long nsel = 0;
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        unsigned long long rank = rr[y];
+        for (int j = 0; j < union_wpr; ++j) {
+            unsigned m = ubits[(size_t)y * union_wpr + j];
+            while (m) {
+                const int b = __ffs((int)m) - 1;
+                m &= m - 1;
+                if ((rank % (unsigned long long)k) == 0) {
+                    const int x = 32 * j + b;
+                    if (x < W) { atomicAdd(&gh[img[(size_t)y * W + x]], 1u); ++nsel; }
+                }
+                ++rank;
+            }
+        }
+    }
+    if (nsel) atomicAdd(&out_stats[(size_t)blockIdx.x * 4], nsel);
+}
+
+// ---------------------------------------------------------------- order statistics
+struct IpbQJob {
+    int hist;       // histogram index
+    float q32;      // quantile = float32(p) / float32(100), computed by the host like numpy
+    int pad0, pad1;
+};
+struct IpbQOut {
+    int prev, next;        // the two order statistics (raw uint16 values); -1 if n == 0
+    float gamma;           // numpy's interpolation weight
+    float value;           // numpy percentile of the float32 copy of the raw sample
+    unsigned long long n;  // sample size
+};
+
+// one CTA (256 threads) per quantile job; thread t owns bins [256 t, 256 t + 256)
+__global__ void __launch_bounds__(256)
+ipb_k_hist_quantiles(const unsigned* __restrict__ hist, const unsigned long long* __restrict__ stats,
+                     const IpbQJob* __restrict__ qjobs, IpbQOut* __restrict__ out)
+{
+    const IpbQJob qj = qjobs[blockIdx.x];
+    const unsigned* h = hist + (size_t)qj.hist * IPB_HIST_BINS;
+    const unsigned long long n = stats[(size_t)qj.hist * 4];
+    __shared__ unsigned long long part[256];
+    __shared__ int res[2];
+    const int t = threadIdx.x;
+    unsigned long long mine = 0;
+    for (int b = 0; b < 256; ++b) mine += h[t * 256 + b];
+    part[t] = mine;
+    if (t < 2) res[t] = -1;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long acc = 0;
+        for (int i = 0; i < 256; ++i) { unsigned long long c = part[i]; part[i] = acc; acc += c; }
+    }
+    __syncthreads();
+    IpbQIdx qi;
+    qi.prev = 0; qi.next = 0; qi.gamma = 0.f;
+    if (n > 0) {
+        qi = ipb_np_qidx_f32((long long)n, qj.q32);
+        const unsigned long long lo = part[t], hi = lo + mine;
+        const long long want[2] = {qi.prev, qi.next};
+        for (int w = 0; w < 2; ++w) {
+            const unsigned long long kk = (unsigned long long)want[w];
+            if (kk >= lo && kk < hi) {
+                unsigned long long acc = lo;
+                for (int b = 0; b < 256; ++b) {
+                    acc += h[t * 256 + b];
+                    if (kk < acc) { res[w] = t * 256 + b; break; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        IpbQOut o;
+        o.prev = res[0]; o.next = res[1]; o.gamma = qi.gamma; o.n = n;
+        o.value = (n > 0 && res[0] >= 0 && res[1] >= 0)
+                      ? ipb_np_lerp_f32((float)res[0], (float)res[1], qi.gamma) : 0.0f;
+        out[blockIdx.x] = o;
+    }
+}

@@ -6,7 +6,7 @@ import numpy as np
 
 class DevBuf:
     """A typed view over a flat byte buffer owned by a memory backend."""
-    __slots__ = ("raw", "dtype", "shape", "mem")
+    __slots__ = ("raw", "dtype", "shape", "mem", "_keep")
 
     def __init__(self, raw, dtype, shape, mem):
         self.raw, self.dtype, self.shape, self.mem = raw, np.dtype(dtype), tuple(shape), mem
@@ -77,6 +77,19 @@ class TorchMem:
     @property
     def stream(self):
         return int(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def pinned(self, shape, dtype):
+        """Pinned host staging buffer as a numpy array (+ the torch tensor that owns it)."""
+        n = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        t = self.torch.empty(n, dtype=self.torch.uint8, pin_memory=True)
+        return t.numpy().view(dtype).reshape(shape), t
+
+    def upload_async(self, buf, pinned_tensor):
+        """H2D copy of a pinned tensor into an existing DevBuf on the current stream."""
+        buf.raw[: pinned_tensor.numel()].copy_(pinned_tensor, non_blocking=True)
 
     def sync(self):
         self.torch.cuda.current_stream(self.device).synchronize()

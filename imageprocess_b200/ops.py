@@ -35,9 +35,39 @@ class RoiMasks:
         return bits[:, :, :W].astype(bool)
 
 
+# kernels launched by each C-ABI entry point (memsets not counted)
+KERNELS_PER_CALL = {"ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
+                    "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
+                    "ipb_fret_pixels": 1, "ipb_region_stats": 1}
+
+
 class Engine:
     def __init__(self, lib, mem):
         self.lib, self.mem = lib, mem
+        self.launches = 0          # kernels launched through this engine
+        self.prof = None           # name -> list of (start_event, end_event) when profiling
+
+    def call(self, name, *args):
+        """Checked C-ABI call; counts kernel launches and, when profiling is on, brackets the
+        call with CUDA events on the launching stream."""
+        self.launches += KERNELS_PER_CALL.get(name, 1)
+        if self.prof is None:
+            return self.lib.call(name, *args)
+        e0, e1 = self.mem.event(), self.mem.event()
+        e0.record()
+        rc = self.lib.call(name, *args)
+        e1.record()
+        self.prof.setdefault(name, []).append((e0, e1))
+        return rc
+
+    def profile_start(self):
+        self.prof = {}
+
+    def profile_stop(self):
+        """Returns {entry point: (n_calls, total_ms)}; caller must have synchronised."""
+        out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.prof or {}).items()}
+        self.prof = None
+        return out
 
     # ------------------------------------------------------------------ a1 / a2
     def rasterize(self, rule, specs, frame_hw, n_frames=1, want_union=True):
@@ -59,8 +89,142 @@ class Engine:
         area = mem.empty(max(t.n, 1), np.uint32)
         union_wpr = (W + 31) // 32
         union = mem.zeros((n_frames, H, union_wpr), np.uint32) if want_union else None
-        self.lib.call("ipb_rasterize_rois", int(rule), t.n, d["verts"].ptr, d["vert_off"].ptr,
+        self.call("ipb_rasterize_rois", int(rule), t.n, d["verts"].ptr, d["vert_off"].ptr,
                       d["erect"].ptr, d["srect"].ptr, d["org"].ptr, d["frame"].ptr,
                       d["mask_off"].ptr, t.max_rows, t.max_wpr, pool.ptr, area.ptr,
                       union.ptr if union is not None else None, union_wpr, H, mem.stream)
         return RoiMasks(t, d, pool, area, union, union_wpr, (H, W), n_frames, mem)
+
+
+# ---------------------------------------------------------------------- struct mirrors
+PAT_FULL, PAT_STRIDE1D, PAT_STRIDE2D, PAT_MASKED, PAT_MASKED_STRIDE = 0, 1, 2, 3, 4
+SRC_U16, SRC_F32 = 0, 1
+QK_NONE, QK_PCT, QK_MEDIAN = 0, 1, 2
+FP_BD, FP_BA, FP_EPS, FP_BAO, FP_STRIDE = 0, 1, 2, 3, 4
+
+HIST_JOB = np.dtype([("plane", "i4"), ("pattern", "i4"), ("k", "i4"), ("mask_frame", "i4"),
+                     ("moments", "i4"), ("pad", "i4", 3)])
+Q_JOB = np.dtype([("hist", "i4"), ("q32", "f4"), ("pad", "i4", 2)])
+Q_OUT = np.dtype([("prev", "i4"), ("next", "i4"), ("gamma", "f4"), ("value", "f4"), ("n", "u8")])
+REGION = np.dtype([("mask_off", "i8"), ("x0", "i4"), ("y0", "i4"), ("w", "i4"), ("h", "i4"),
+                   ("wpr", "i4"), ("frame", "i4"), ("use_and", "i4"), ("pad0", "i4")])
+STAT_JOB = np.dtype([("region", "i4"), ("src", "i4"), ("plane", "i4"), ("bidx", "i4"),
+                     ("clip_neg", "i4"), ("qkind", "i4", 3), ("q32", "f4", 3), ("pad0", "i4")])
+STAT_OUT = np.dtype([("n", "u8"), ("area", "u8"), ("sum", "f8"), ("ssd", "f8"), ("vmin", "f4"),
+                     ("vmax", "f4"), ("q", "f4", 3), ("pad0", "f4")])
+FRET_CFG = np.dtype([("numer_is_acceptor", "i4"), ("clip_neg", "i4"), ("sat_on", "i4"),
+                     ("sat_thr", "f4"), ("use_spectral", "i4"), ("alpha", "f4"), ("beta", "f4"),
+                     ("g_factor", "f4"), ("clip_on", "i4"), ("clip_max", "f4"), ("donor_ch", "i4"),
+                     ("acc_ch", "i4"), ("aonly_ch", "i4"), ("n_ch", "i4")])
+_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG]
+
+
+def q32_of(p):
+    """numpy.percentile's quantile for a float32 sample: true_divide(p, float32(100))."""
+    return np.float32(np.true_divide(p, np.float32(100)))
+
+
+def check_struct_sizes(lib):
+    for i, dt in enumerate(_SIZEOF):
+        n = lib.c.ipb_sizeof(i)
+        if n != dt.itemsize:
+            raise RuntimeError(f"struct {i}: library says {n} bytes, python mirror {dt.itemsize}")
+
+
+class HistResult:
+    def __init__(self, hist, stats, n_jobs):
+        self.hist, self.stats, self.n_jobs = hist, stats, n_jobs
+
+
+def _engine_hist(self, planes, H, W, jobs, union=None, union_wpr=0):
+    """jobs: structured array HIST_JOB.  Returns HistResult (device)."""
+    mem = self.mem
+    jobs = np.ascontiguousarray(jobs, dtype=HIST_JOB)
+    n = jobs.shape[0]
+    d_jobs = mem.from_host(jobs if n else np.zeros(1, HIST_JOB))
+    hist = mem.empty((max(n, 1), 65536), np.uint32)
+    stats = mem.empty((max(n, 1), 4), np.uint64)
+    has_ms = bool((jobs["pattern"] == PAT_MASKED_STRIDE).any()) if n else False
+    scratch = mem.empty((max(n, 1), H), np.uint64) if has_ms else None
+    self.call("ipb_hist_u16", planes.ptr, H, W, d_jobs.ptr, n, int(has_ms),
+                  union.ptr if union is not None else None, int(union_wpr),
+                  scratch.ptr if scratch is not None else None, hist.ptr, stats.ptr, mem.stream)
+    res = HistResult(hist, stats, n)
+    res._keep = (d_jobs, scratch)
+    return res
+
+
+def _engine_quantiles(self, hres, qjobs):
+    """qjobs: structured array Q_JOB.  Returns device buffer of Q_OUT."""
+    mem = self.mem
+    qjobs = np.ascontiguousarray(qjobs, dtype=Q_JOB)
+    n = qjobs.shape[0]
+    d_q = mem.from_host(qjobs if n else np.zeros(1, Q_JOB))
+    qout = mem.empty(max(n, 1), Q_OUT)
+    self.call("ipb_hist_quantiles", hres.hist.ptr, hres.stats.ptr, d_q.ptr, n, qout.ptr, mem.stream)
+    qout._keep = d_q
+    return qout
+
+
+def _engine_scatter_qvalues(self, qout, dst_idx, dst):
+    idx = self.mem.from_host(np.ascontiguousarray(dst_idx, dtype=np.int32))
+    self.call("ipb_scatter_qvalues", qout.ptr, idx.ptr, int(len(dst_idx)), dst.ptr, self.mem.stream)
+
+
+def _engine_fret_eps(self, qout_eps, n_frames, denom_slot, clip_neg, fparams, eps_abs=5.0):
+    self.call("ipb_fret_eps", qout_eps.ptr, int(n_frames), int(denom_slot), int(bool(clip_neg)),
+                  float(eps_abs), fparams.ptr, self.mem.stream)
+
+
+def _engine_fa_params(self, hres, stat_idx, qout_bg, n_frames, npx, alpha, fa):
+    idx = self.mem.from_host(np.ascontiguousarray(stat_idx, dtype=np.int32))
+    self.call("ipb_fa_params", hres.stats.ptr, idx.ptr, qout_bg.ptr, int(n_frames), int(npx),
+                  float(np.float32(alpha)), fa.ptr, self.mem.stream)
+
+
+def _engine_fret_pixels(self, planes, F, H, W, cfg, fparams, union=None, union_wpr=0, R=None,
+                        Ralt=None, Rroi=None, Dcorr=None, Acorr=None):
+    cfg = np.ascontiguousarray(cfg, dtype=FRET_CFG).reshape(1)
+    p = lambda b: b.ptr if b is not None else None
+    self.call("ipb_fret_pixels", planes.ptr, int(F), int(H), int(W), cfg.ctypes.data, fparams.ptr,
+                  p(union), int(union_wpr), p(R), p(Ralt), p(Rroi), p(Dcorr), p(Acorr), self.mem.stream)
+
+
+def _engine_region_stats(self, regions, jobs, mask_pool, H, W, planes=None, images=None, bvals=None,
+                         and_bits=None, and_wpr=0):
+    """regions: REGION array, jobs: STAT_JOB array.  Returns device buffer of STAT_OUT."""
+    mem = self.mem
+    regions = np.ascontiguousarray(regions, dtype=REGION)
+    jobs = np.ascontiguousarray(jobs, dtype=STAT_JOB)
+    n = jobs.shape[0]
+    d_r = mem.from_host(regions if regions.shape[0] else np.zeros(1, REGION))
+    d_j = mem.from_host(jobs if n else np.zeros(1, STAT_JOB))
+    out = mem.empty(max(n, 1), STAT_OUT)
+    p = lambda b: b.ptr if b is not None else None
+    self.call("ipb_region_stats", d_r.ptr, d_j.ptr, n, mask_pool.ptr, p(and_bits), int(and_wpr),
+                  int(H), int(W), p(planes), p(images), p(bvals), out.ptr, mem.stream)
+    out._keep = (d_r, d_j)
+    return out
+
+
+Engine.hist = _engine_hist
+Engine.quantiles = _engine_quantiles
+Engine.scatter_qvalues = _engine_scatter_qvalues
+Engine.fret_eps = _engine_fret_eps
+Engine.fa_params = _engine_fa_params
+Engine.fret_pixels = _engine_fret_pixels
+Engine.region_stats = _engine_region_stats
+
+
+def regions_from_masks(rm):
+    """REGION rows for every ROI of a RoiMasks (frame coordinates)."""
+    t = rm.table
+    reg = np.zeros(t.n, dtype=REGION)
+    reg["mask_off"] = t.mask_off[:-1]
+    reg["x0"] = t.org[:, 0] + t.srect[:, 0]
+    reg["y0"] = t.org[:, 1] + t.srect[:, 1]
+    reg["w"] = t.srect[:, 2] - t.srect[:, 0]
+    reg["h"] = t.srect[:, 3] - t.srect[:, 1]
+    reg["wpr"] = t.wpr
+    reg["frame"] = t.frame
+    return reg

@@ -1,0 +1,165 @@
+/*
+ * ipb200.h -- C ABI of libipb200.so: the B200-native (sm_100a) per-pixel analysis hot path of
+ * gavyek/ImageProcess.
+ *
+ * The reference has no FFI of its own: its hot path is a set of module-level Python functions
+ * (numpy / scipy / scikit-image / matplotlib.path calls).  This header is the boundary a
+ * maintainer binds instead of those library calls; INTEGRATION.md shows the ctypes stub for
+ * each reference function.  Reference citations below are relative to /root/reference/src/.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types.
+ *   - Every pointer marked [dev] is a caller-owned DEVICE pointer; [host] is host memory.
+ *     The library never allocates, frees or keeps pointers.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - Returns IPB_OK (0) or a negative IPB_ERR_* code; ipb_last_error() gives the
+ *     thread-local message.  No global mutable state: safe from many host threads and from
+ *     one process per GPU.
+ *   - Struct layouts are fixed below and can be checked with ipb_sizeof().
+ */
+#ifndef IPB200_H
+#define IPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPB_OK 0
+#define IPB_ERR_ARG (-1)
+#define IPB_ERR_CUDA (-2)
+#define IPB_ERR_WORKSPACE (-3)
+#define IPB_ERR_UNSUPPORTED (-4)
+
+const char* ipb_last_error(void);
+int ipb_version(void);
+int ipb_is_emulated(void);      /* 1 only in the CPU test build of the same sources */
+int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg */
+
+/* ------------------------------------------------------------------ ROI rasterisation
+ * Replaces rasterize_polygon (INT/Fluor_INT.py:398-403; copies FRET/fret_ratio_builder.py:292,
+ * FRET/Nesprin2_FRET_Builder.py:388, MOR_by_ROI.py:160, roi_channel_cropper.py:286), i.e.
+ * matplotlib.path.Path.contains_points over the whole grid  (rule IPB_RULE_MPL), and
+ * skimage.draw.polygon at INT/FA_Analyzer.py:805,883,1014,1225     (rule IPB_RULE_SK),
+ * for all ROIs of a batch of frames in one launch.  Bit-exact with both libraries.
+ *
+ * Per ROI r (all tables [dev]):
+ *   verts_xy[2*vert_off[r] .. 2*vert_off[r+1])  float64 (x,y) in the ROI's LOCAL grid
+ *   erect[4r..]  (x0,y0,x1,y1) half-open rect where the rule is evaluated
+ *   srect[4r..]  (x0,y0,x1,y1) half-open rect the stored mask covers (contains erect)
+ *   org[2r..]    frame position of local (0,0);  roi_frame[r] frame index
+ *   mask_off[r]  offset (32-bit words) of the ROI's mask in mask_pool; rows of
+ *                ceil((sx1-sx0)/32) words; bit b of word j <-> local x = sx0 + 32 j + b
+ * Outputs: mask_pool, area[r] (pixel count), union_bits (optional; must be zeroed by the
+ * caller): per frame H rows of union_wpr words, bit b of word j <-> frame x = 32 j + b.    */
+#define IPB_RULE_MPL 0
+#define IPB_RULE_SK 1
+int ipb_rasterize_rois(int rule, int n_rois, const double* verts_xy, const int32_t* vert_off,
+                       const int32_t* erect, const int32_t* srect, const int32_t* org,
+                       const int32_t* roi_frame, const int64_t* mask_off, int max_rows, int max_wpr,
+                       uint32_t* mask_pool, uint32_t* area, uint32_t* union_bits, int union_wpr,
+                       int frame_h, void* stream);
+
+/* ------------------------------------------------------------------ histograms / percentiles
+ * Replaces every np.percentile / np.histogram over pixels of a uint16-derived float32 image:
+ * bg_value (INT/Fluor_INT.py:464-485, FRET/fret_ratio_builder.py:314-330,
+ * FRET/Nesprin2_FRET_Builder.py:432-451), FA global stats (INT/FA_Analyzer.py:984-987),
+ * pick_epsilon (fret_ratio_builder.py:338-340).  One exact 65536-bin histogram per job.     */
+#define IPB_PAT_FULL 0           /* all pixels                        vals = img.ravel()      */
+#define IPB_PAT_STRIDE1D 1       /* flat index % k == 0               vals[::k]               */
+#define IPB_PAT_STRIDE2D 2       /* y % k == 0 and x % k == 0         img[::k, ::k]           */
+#define IPB_PAT_MASKED 3         /* pixels under union_bits           img[scope_mask]         */
+#define IPB_PAT_MASKED_STRIDE 4  /* every k-th masked pixel           img[scope_mask][::k]    */
+typedef struct {
+    int32_t plane;        /* plane index into planes[][H][W] (frame * C + channel) */
+    int32_t pattern;      /* IPB_PAT_* */
+    int32_t k;            /* stride of the strided patterns */
+    int32_t mask_frame;   /* frame index into union_bits (masked patterns) */
+    int32_t moments;      /* != 0: also accumulate sum / sum of squares of ALL pixels */
+    int32_t pad[3];
+} ipb_hist_job;
+/* hist: [n_jobs][65536] uint32;  stats: [n_jobs][4] uint64 = {n_selected, sum_all, sumsq_all, 0}
+ * row_rank_scratch: [n_jobs][H] uint64, only for IPB_PAT_MASKED_STRIDE jobs.               */
+int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs /* ipb_hist_job[] dev */,
+                 int n_jobs, int has_masked_stride, const uint32_t* union_bits, int union_wpr,
+                 uint64_t* row_rank_scratch, uint32_t* hist, uint64_t* stats, void* stream);
+
+typedef struct {
+    int32_t hist;         /* histogram (job) index */
+    float q32;            /* float32(p) / float32(100), as numpy computes it */
+    int32_t pad[2];
+} ipb_q_job;
+typedef struct {
+    int32_t prev, next;   /* the two order statistics (raw values); -1 if the sample is empty */
+    float gamma;          /* numpy's interpolation weight */
+    float value;          /* np.percentile of the float32 copy of the sample */
+    uint64_t n;           /* sample size */
+} ipb_q_out;
+int ipb_hist_quantiles(const uint32_t* hist, const uint64_t* stats, const void* qjobs /* dev */,
+                       int n_q, void* qout /* ipb_q_out[] dev */, void* stream);
+/* dst[dst_idx[i]] = qout[i].value (0 for an empty sample)                                  */
+int ipb_scatter_qvalues(const void* qout, const int32_t* dst_idx, int n, float* dst, void* stream);
+/* fparams[f][2] = max(eps_abs, percentile of the bg-corrected denominator)                 */
+int ipb_fret_eps(const void* qout_eps, int n_frames, int denom_slot, int clip_neg, float eps_abs,
+                 float* fparams, void* stream);
+/* fa[f] = {mean, std, bg, mean + alpha*std} in float32 (INT/FA_Analyzer.py:143-144,984-987) */
+int ipb_fa_params(const uint64_t* stats, const int32_t* stat_idx, const void* qout_bg, int n_frames,
+                  int64_t npx, float alpha, float* fa, void* stream);
+
+/* ------------------------------------------------------------------ fused FRET pass
+ * Replaces, per pixel and in one pass: saturation filter (Nesprin2_FRET_Builder.py:1415-1421),
+ * bg_correct (fret_ratio_builder.py:332-336), spectral_correct (Nesprin2 460-468), the
+ * epsilon-regularised ratio and its inverse (fret_ratio_builder.py:474; Nesprin2 1499-1500),
+ * ratio clipping (Nesprin2 1502-1504) and the ROI-masked copy (fret_ratio_builder.py:494-495).
+ * planes: uint16 [F][n_ch][H][W]; fparams: float32 [F][4] = {Bd, Ba, eps, Bao};
+ * outputs float32 [F][H][W], any of them may be NULL.                                      */
+typedef struct {
+    int32_t numer_is_acceptor;    /* 1: "FRET/Donor", 0: "Donor/FRET" */
+    int32_t clip_neg;
+    int32_t sat_on;  float sat_thr;
+    int32_t use_spectral;  float alpha, beta, g_factor;
+    int32_t clip_on; float clip_max;
+    int32_t donor_ch, acc_ch, aonly_ch /* < 0: none */, n_ch;
+} ipb_fret_cfg;
+int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W,
+                    const void* cfg_host /* ipb_fret_cfg, [host] */, const float* fparams,
+                    const uint32_t* union_bits, int union_wpr, float* R, float* Ralt, float* Rroi,
+                    float* Dcorr, float* Acorr, void* stream);
+
+/* ------------------------------------------------------------------ per-region statistics
+ * Replaces quantify_stats / quantify_per_roi_multi (INT/Fluor_INT.py:494-538),
+ * quantify_per_roi (fret_ratio_builder.py:342-362) and the Nesprin2 row statistics
+ * (Nesprin2_FRET_Builder.py:1537-1581): n, sum, sum of squared deviations, min, max and up
+ * to three exact order-statistic results (np.percentile / np.median float32 arithmetic).   */
+#define IPB_SRC_U16 0            /* value = float32(raw) - B, optionally clipped at 0 */
+#define IPB_SRC_F32 1            /* value = float32 image pixel, non-finite dropped */
+#define IPB_QKIND_NONE 0
+#define IPB_QKIND_PCT 1
+#define IPB_QKIND_MEDIAN 2
+typedef struct {
+    int64_t mask_off;             /* word offset of the region's bit rows in mask_pool */
+    int32_t x0, y0, w, h;         /* rect in frame coordinates */
+    int32_t wpr, frame, use_and, pad0;
+} ipb_region;
+typedef struct {
+    int32_t region, src, plane, bidx, clip_neg;
+    int32_t qkind[3];
+    float q32[3];
+    int32_t pad0;
+} ipb_stat_job;
+typedef struct {
+    uint64_t n, area;
+    double sum, ssd;
+    float vmin, vmax;
+    float q[3];
+    float pad0;
+} ipb_stat_out;
+int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
+                     const uint32_t* and_bits, int and_wpr, int H, int W, const uint16_t* planes,
+                     const float* images, const float* bvals, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPB200_H */

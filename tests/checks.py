@@ -1,0 +1,204 @@
+"""Shared check bodies: every function takes an Engine and compares the product's kernels
+with the oracle.  tests/test_emu_kernels.py runs them on the CPU through the emulated build of
+the same kernel sources; tests/test_gpu_kernels.py runs them on the B200 through libipb200.so
+(the parity tests proper)."""
+import math
+
+import numpy as np
+
+from imageprocess_b200 import geometry as geo
+from imageprocess_b200 import pipeline
+from oracle import port, shims
+from oracle.gen_golden import small_scene
+from tests import goldenio
+
+REL = 1e-5   # north_star tolerance on float outputs (means / std / sums)
+
+def _check_mpl(eng, polys, H, W):
+    specs = [geo.mpl_spec(P, (W, H)) for P in polys]
+    rm = eng.rasterize(geo.RULE_MPL, specs, (H, W), 1, want_union=True)
+    area = rm.area.host()
+    union = np.zeros((H, W), bool)
+    for i, P in enumerate(polys):
+        want = port.rasterize_polygon(P, (H, W))
+        x0, y0, x1, y1 = specs[i].srect
+        got = np.zeros((H, W), bool)
+        got[y0:y1, x0:x1] = rm.mask_host(i)
+        assert int((got ^ want).sum()) == 0, i
+        assert int(area[i]) == int(want.sum())
+        union |= want
+    assert np.array_equal(rm.union_host()[0], union)
+
+
+def check_mpl_small_scene(eng):
+    d, a, polys = small_scene(7)
+    _check_mpl(eng, polys, *d.shape)
+
+
+def check_mpl_random_polygons(eng):
+    rng = np.random.default_rng(3)
+    H, W = 70, 150
+    polys = []
+    for k in range(12):
+        n = int(rng.integers(3, 12))
+        P = rng.uniform(-10, 160, (n, 2))
+        P[:, 1] = rng.uniform(-10, 80, n)
+        if k % 3 == 0:
+            P = np.round(P * 2) / 2        # .5 grid: vertices on pixel centres / edges
+        if k % 4 == 1:
+            P = np.round(P)                # integer vertices: ties with pixel centres
+        polys.append(P)
+    polys.append(np.array([[5.0, 5.0], [140.0, 5.0], [140.0, 60.0], [5.0, 60.0]]))   # long flat edges
+    polys.append(np.array([[0.0, 10.0], [149.0, 10.5], [149.0, 12.0], [0.0, 11.0]]))  # long shallow edges
+    polys.append(np.array([[10.0, 10.0], [20.0, 10.0], [20.0, 20.0], [10.0, 20.0], [10.0, 10.0]]))  # closed
+    _check_mpl(eng, polys, H, W)
+
+
+def check_sk_crops_match_oracle(eng):
+    d, a, polys = small_scene(7)
+    img = d.astype(np.float32)
+    specs, wants = [], []
+    for P in polys:
+        spec, rect = geo.fa_spec(P, img.shape)
+        crop, mask, rect2 = port.fa_crop_and_mask(img, P.copy())
+        assert rect == rect2
+        specs.append(spec)
+        wants.append(mask)
+    rm = eng.rasterize(geo.RULE_SK, specs, img.shape, 1, want_union=True)
+    area = rm.area.host()
+    for i, want in enumerate(wants):
+        assert np.array_equal(rm.mask_host(i), want), i
+        assert int(area[i]) == int(want.sum())
+
+
+def check_sk_random_polygons(eng):
+    rng = np.random.default_rng(9)
+    H, W = 60, 90
+    specs, wants = [], []
+    for k in range(14):
+        n = int(rng.integers(3, 10))
+        P = np.stack([rng.uniform(-8, 98, n), rng.uniform(-8, 68, n)], axis=1)
+        if k % 2 == 0:
+            P = np.round(P * 2) / 2
+        if k % 5 == 1:
+            P = np.round(P)
+        specs.append(geo.sk_spec(P[:, 1], P[:, 0], (H, W)))
+        m = np.zeros((H, W), bool)
+        rr, cc = shims.polygon(P[:, 1], P[:, 0], (H, W))
+        m[rr, cc] = True
+        wants.append(m)
+    rm = eng.rasterize(geo.RULE_SK, specs, (H, W), 1, want_union=False)
+    for i, want in enumerate(wants):
+        assert int((rm.mask_host(i) ^ want).sum()) == 0, i
+
+
+def check_fa_fixture_polygons_sk(eng):
+    """The FA sample's 62-540 vertex ROI polygons (2200x3200) -- one of them, both rules."""
+    shape, polys = goldenio.load_fa_rois()["e2/S02"]
+    H, W = shape["height"], shape["width"]
+    P = polys[0]
+    spec, rect = geo.fa_spec(P, (H, W))
+    rm = eng.rasterize(geo.RULE_SK, [spec], (H, W), 1, want_union=False)
+    pc = P.copy()
+    pc[:, 0] -= rect[0]
+    pc[:, 1] -= rect[2]
+    h, w = rect[3] - rect[2], rect[1] - rect[0]
+    want = np.zeros((h, w), bool)
+    rr, cc = shims.polygon(pc[:, 1], pc[:, 0], (h, w))
+    want[rr, cc] = True
+    assert int((rm.mask_host(0) ^ want).sum()) == 0
+
+
+def close(a, b, rel=REL):
+    if isinstance(a, float) and math.isnan(a):
+        return isinstance(b, float) and math.isnan(b)
+    return abs(a - b) <= rel * max(abs(a), abs(b), 1e-30)
+
+
+EXACT_INT = ("median", "p5", "p95", "vmin", "vmax", "npx")
+
+
+def check_int_rows(got_rows, want_rows, chs):
+    assert len(got_rows) == len(want_rows)
+    for g, w in zip(got_rows, want_rows):
+        assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"]
+        for ch in chs:
+            for k in EXACT_INT:
+                assert g[f"ch{ch}_{k}"] == w[f"ch{ch}_{k}"], (ch, k, g[f"ch{ch}_{k}"], w[f"ch{ch}_{k}"])
+            for k in ("mean", "std", "vsum"):
+                assert close(g[f"ch{ch}_{k}"], w[f"ch{ch}_{k}"]), (ch, k)
+
+
+def check_intensity_batch(eng, scope, stride, mode):
+    frames = [small_scene(s, H=96, W=128, n_cells=2) for s in (5, 6)]
+    planes = np.stack([np.stack([d, a]) for d, a, _ in frames])          # [F][2][H][W]
+    F, C, H, W = planes.shape
+    task = {"bg_scope": scope, "bg_mode": mode, "clip_neg": True, "bg_stride": stride,
+            "percentile": 2.0, "per_channel_p": True, "ch_p_map": {2: 7.5}}
+    dplanes = eng.mem.from_host(planes)
+    rows, bg_used, _ = pipeline.intensity_batch(eng, dplanes, (F, C, H, W),
+                                                [fr[2] for fr in frames], task, ch_names=[1, 2])
+    for f, (d, a, polys) in enumerate(frames):
+        raw = {1: d.astype(np.float32), 2: a.astype(np.float32)}
+        want, want_bg, _ = port.int_process_key(raw, polys, None, task)
+        for ch in (1, 2):
+            assert bg_used[f][ch]["bg"] == want_bg[ch]["bg"], (f, ch)
+        check_int_rows(rows[f], want, (1, 2))
+
+
+def check_fret_batch(eng, ratio_mode, scope, clip):
+    frames = [small_scene(s, H=96, W=128, n_cells=2) for s in (8, 9)]
+    planes = np.stack([np.stack([d, a]) for d, a, _ in frames])
+    F, C, H, W = planes.shape
+    p = {"bg_scope": scope, "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": True,
+         "donor_p": 1.5, "fret_p": 3.0, "clip_neg": clip, "eps_percentile": 2.0,
+         "ratio_mode": ratio_mode}
+    out = pipeline.fret_batch(eng, eng.mem.from_host(planes), (F, C, H, W), [fr[2] for fr in frames],
+                              p, want_roi_image=True)
+    fp = out["fparams"].host()
+    R = out["R"].host()
+    Rroi = out["R_roi"].host()
+    for f, (d, a, polys) in enumerate(frames):
+        want = port.fret_process_pair(d.astype(np.float32), a.astype(np.float32), polys, p)
+        assert fp[f, 0] == np.float32(want["Db"]) and fp[f, 1] == np.float32(want["Ab"])
+        assert fp[f, 2] == np.float32(want["eps"])
+        assert np.array_equal(R[f], want["R_full"], equal_nan=True)             # bit-exact ratio image
+        assert np.array_equal(Rroi[f], want["R_roi"], equal_nan=True)
+        assert len(out["rows_per_frame"][f]) == len(want["rows"])
+        for g, w in zip(out["rows_per_frame"][f], want["rows"]):
+            assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"]
+            for k in ("ratio_median", "ratio_p5", "ratio_p95", "donor_median", "yfret_median"):
+                assert g[k] == w[k], (k, g[k], w[k])
+            for k in ("ratio_mean", "ratio_std", "donor_mean", "yfret_mean"):
+                assert close(g[k], w[k]), (k, g[k], w[k])
+
+
+def check_intensity_golden(eng, exp):
+    """The reference's own shipped golden: 1536x2048 ch2+ch3, 18 / 11 ROIs,
+    settings recorded in the CSV (percentile p=1, scope full, clip, stride 4)."""
+    imgs, polys, rows, _ = goldenio.load_intensity(exp)
+    planes = np.stack([imgs[2], imgs[3]])[None]
+    F, C, H, W = planes.shape
+    task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4,
+            "percentile": 1.0, "per_channel_p": False, "ch_p_map": {}}
+    got, bg_used, _ = pipeline.intensity_batch(eng, eng.mem.from_host(planes), (F, C, H, W), [polys],
+                                               task, ch_names=[2, 3])
+    assert len(got[0]) == len(rows)
+    for ch in (2, 3):
+        assert bg_used[0][ch]["bg"] == float(rows[0][f"ch{ch}_bg"])
+    for g, e in zip(got[0], rows):
+        assert g["roi"] == int(e["roi"]) and g["area_px"] == int(e["area_px"])
+        for ch in (2, 3):
+            for k in ("median", "p5", "p95", "vmin", "vmax"):
+                assert g[f"ch{ch}_{k}"] == float(e[f"ch{ch}_{k}"]), (ch, k)
+            assert g[f"ch{ch}_npx"] == int(e[f"ch{ch}_npx"])
+            for k in ("mean", "std", "vsum"):
+                assert close(g[f"ch{ch}_{k}"], float(e[f"ch{ch}_{k}"])), (ch, k)
+
+
+INTENSITY_CASES = [("full", 4, "percentile"), ("full", 1, "percentile"), ("roi_union", 1, "percentile"),
+                   ("roi_union", 3, "percentile"), ("full", 4, "hist-mode")]
+FRET_CASES = [("Donor/FRET", "full", True), ("FRET/Donor", "roi_union", True),
+              ("FRET/Donor", "full", False)]
+RASTER_CHECKS = [check_mpl_small_scene, check_mpl_random_polygons, check_sk_crops_match_oracle,
+                 check_sk_random_polygons, check_fa_fixture_polygons_sk]

@@ -1,0 +1,28 @@
+"""CPU tier: the product's kernel sources built with the CUDA emulator (tests/emu) and
+driven by the product's host code, checked against the oracle.  Logic only -- the parity
+tests proper are tests/test_gpu_kernels.py on the B200."""
+import pytest
+
+from imageprocess_b200.ops import Engine
+from tests import checks
+from tests.emu.emu_backend import NumpyMem, emu_lib
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return Engine(emu_lib(), NumpyMem())
+
+
+@pytest.mark.parametrize("fn", checks.RASTER_CHECKS, ids=lambda f: f.__name__)
+def test_raster(eng, fn):
+    fn(eng)
+
+
+@pytest.mark.parametrize("scope,stride,mode", checks.INTENSITY_CASES)
+def test_intensity_batch(eng, scope, stride, mode):
+    checks.check_intensity_batch(eng, scope, stride, mode)
+
+
+@pytest.mark.parametrize("ratio_mode,scope,clip", checks.FRET_CASES)
+def test_fret_batch(eng, ratio_mode, scope, clip):
+    checks.check_fret_batch(eng, ratio_mode, scope, clip)
