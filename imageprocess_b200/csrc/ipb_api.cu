@@ -14,6 +14,7 @@
 #include "ipb_hist.cuh"
 #include "ipb_roistats.cuh"
 #include "ipb_fret.cuh"
+#include "ipb_fa.cuh"
 
 static thread_local char g_ipb_err[512] = "";
 
@@ -197,6 +198,66 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const ui
     return ipb_check_launch("ipb_k_region_stats");
 }
 
+// ---------------------------------------------------------------- focal-adhesion chain
+int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_rows,
+                   const uint16_t* planes, int H, int W, const float* fa_params,
+                   const uint32_t* roi_mask, double min_size, int close_radius,
+                   uint32_t* bw_a, uint32_t* bw_b, int32_t* L, uint32_t* csize, uint32_t* rootbits,
+                   int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
+                   uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
+                   int32_t* labels, void* stream)
+{
+    if (n_crops <= 0) return IPB_OK;
+    IPB_REQUIRE(n_crops <= 65535, "ipb_fa_segment: n_crops %d out of range", n_crops);
+    IPB_REQUIRE(crops && planes && fa_params && roi_mask && bw_a && bw_b && L && csize && rootbits &&
+                row_roots && row_base && crop_count && bw_final && comp_off && comps,
+                "ipb_fa_segment: null pointer");
+    IPB_REQUIRE(close_radius >= 0 && close_radius <= 5, "ipb_fa_segment: close_radius %d not in 0..5", close_radius);
+    IPB_REQUIRE(max_rows > 0 && total_rows > 0 && comp_cap > 0, "ipb_fa_segment: bad sizes");
+    const IpbCrop* cr = (const IpbCrop*)crops;
+    const dim3 grid(ipb_div_up(max_rows, IPB_FA_ROWS), (unsigned)n_crops), block(IPB_FA_THREADS);
+    int rc;
+    IPB_LAUNCH(ipb_k_fa_threshold, grid, block, 0, stream, cr, planes, H, W, fa_params, roi_mask, bw_a);
+    if ((rc = ipb_check_launch("ipb_k_fa_threshold"))) return rc;
+    uint32_t* cur = bw_a;
+    uint32_t* other = bw_b;
+    if (min_size > 0) {
+        IPB_LAUNCH(ipb_k_ccl_init, grid, block, 0, stream, cr, (const unsigned*)cur, L, csize);
+        IPB_LAUNCH(ipb_k_ccl_merge<4>, grid, block, 0, stream, cr, (const unsigned*)cur, L);
+        IPB_LAUNCH(ipb_k_ccl_flatten_size, grid, block, 0, stream, cr, (const unsigned*)cur, L, csize);
+        IPB_LAUNCH(ipb_k_fa_size_filter, grid, block, 0, stream, cr, (const unsigned*)cur, (const int*)L,
+                   (const unsigned*)csize, min_size, other);
+        if ((rc = ipb_check_launch("ipb_fa small-object removal"))) return rc;
+        uint32_t* t = cur; cur = other; other = t;
+    }
+    IpbDisk disk;
+    memset(&disk, 0, sizeof(disk));
+    disk.r = close_radius;
+    for (int dy = -close_radius; dy <= close_radius; ++dy) {
+        int k = 0;
+        while ((k + 1) * (k + 1) + dy * dy <= close_radius * close_radius) ++k;
+        disk.halfw[dy + close_radius] = k;
+    }
+    if (close_radius > 0) {
+        IPB_LAUNCH(ipb_k_bits_morph<0>, grid, block, 0, stream, cr, (const unsigned*)cur, disk, other);
+        IPB_LAUNCH(ipb_k_bits_morph<1>, grid, block, 0, stream, cr, (const unsigned*)other, disk, bw_final);
+    } else {
+        IPB_LAUNCH(ipb_k_bits_morph<0>, grid, block, 0, stream, cr, (const unsigned*)cur, disk, bw_final);
+    }
+    if ((rc = ipb_check_launch("ipb_k_bits_morph"))) return rc;
+    IPB_CUDA_TRY(cudaMemsetAsync(row_roots, 0, sizeof(int32_t) * (size_t)total_rows, (cudaStream_t)stream), "memset row_roots");
+    IPB_LAUNCH(ipb_k_ccl_init, grid, block, 0, stream, cr, (const unsigned*)bw_final, L, (unsigned*)nullptr);
+    IPB_LAUNCH(ipb_k_ccl_merge<8>, grid, block, 0, stream, cr, (const unsigned*)bw_final, L);
+    IPB_LAUNCH(ipb_k_ccl_flatten_roots, grid, block, 0, stream, cr, (const unsigned*)bw_final, L, rootbits, row_roots);
+    IPB_LAUNCH(ipb_k_fa_row_scan, dim3(n_crops), dim3(256), 0, stream, cr, (const int*)row_roots, row_base, crop_count);
+    IPB_LAUNCH(ipb_k_fa_crop_scan, dim3(1), dim3(256), 0, stream, (const int*)crop_count, n_crops, comp_off);
+    IPB_LAUNCH(ipb_k_fa_zero_comps, dim3(296), dim3(256), 0, stream, (const int*)comp_off, n_crops, comp_cap, (IpbComp*)comps);
+    IPB_LAUNCH(ipb_k_fa_props, grid, block, 0, stream, cr, (const unsigned*)bw_final, (const int*)L,
+               (const unsigned*)rootbits, (const int*)row_base, (const int*)comp_off, comp_cap, planes, H, W,
+               (IpbComp*)comps, labels);
+    return ipb_check_launch("ipb_fa labelling");
+}
+
 int ipb_sizeof(int what)
 {
     switch (what) {
@@ -207,6 +268,8 @@ int ipb_sizeof(int what)
         case 4: return (int)sizeof(IpbStatJob);
         case 5: return (int)sizeof(IpbStatOut);
         case 6: return (int)sizeof(IpbFretCfg);
+        case 7: return (int)sizeof(IpbCrop);
+        case 8: return (int)sizeof(IpbComp);
         default: return -1;
     }
 }

@@ -36,7 +36,7 @@ class RoiMasks:
 
 
 # kernels launched by each C-ABI entry point (memsets not counted)
-KERNELS_PER_CALL = {"ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
+KERNELS_PER_CALL = {"ipb_fa_segment": 14, "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
                     "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
                     "ipb_fret_pixels": 1, "ipb_region_stats": 1}
 
@@ -116,7 +116,10 @@ FRET_CFG = np.dtype([("numer_is_acceptor", "i4"), ("clip_neg", "i4"), ("sat_on",
                      ("sat_thr", "f4"), ("use_spectral", "i4"), ("alpha", "f4"), ("beta", "f4"),
                      ("g_factor", "f4"), ("clip_on", "i4"), ("clip_max", "f4"), ("donor_ch", "i4"),
                      ("acc_ch", "i4"), ("aonly_ch", "i4"), ("n_ch", "i4")])
-_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG]
+CROP = np.dtype([("bit_off", "i8"), ("pix_off", "i8"), ("row_off", "i8"), ("ox", "i4"), ("oy", "i4"),
+                 ("w", "i4"), ("h", "i4"), ("wpr", "i4"), ("plane", "i4"), ("frame", "i4"), ("pad0", "i4")])
+COMP = np.dtype([("sum_i", "u8"), ("sum_y", "u8"), ("sum_x", "u8"), ("area", "u4"), ("crop", "i4")])
+_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG, CROP, COMP]
 
 
 def q32_of(p):
@@ -228,3 +231,67 @@ def regions_from_masks(rm):
     reg["wpr"] = t.wpr
     reg["frame"] = t.frame
     return reg
+
+
+class FaResult:
+    """Device-resident result of Engine.fa_segment()."""
+
+    def __init__(self, crops, bw, comp_off, comps, labels, cap, keep):
+        self.crops, self.bw, self.comp_off, self.comps, self.labels, self.cap = crops, bw, comp_off, comps, labels, cap
+        self._keep = keep
+
+    def bw_host(self, i):
+        c = self.crops[i]
+        words = self.bw.host()[c["bit_off"]: c["bit_off"] + c["h"] * c["wpr"]].reshape(c["h"], c["wpr"])
+        bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little")
+        return bits[:, :c["w"]].astype(bool)
+
+    def labels_host(self, i):
+        c = self.crops[i]
+        return self.labels.host()[c["pix_off"]: c["pix_off"] + c["h"] * c["w"]].reshape(c["h"], c["w"])
+
+
+def crops_from_masks(rm, planes_of_roi):
+    """CROP rows for every (skimage-rule, full-crop) ROI of a RoiMasks."""
+    t = rm.table
+    cr = np.zeros(t.n, dtype=CROP)
+    w = (t.srect[:, 2] - t.srect[:, 0]).astype(np.int64)
+    h = (t.srect[:, 3] - t.srect[:, 1]).astype(np.int64)
+    cr["bit_off"] = t.mask_off[:-1]
+    cr["pix_off"][1:] = np.cumsum(w * h)[:-1]
+    cr["row_off"][1:] = np.cumsum(h)[:-1]
+    cr["ox"] = t.org[:, 0] + t.srect[:, 0]
+    cr["oy"] = t.org[:, 1] + t.srect[:, 1]
+    cr["w"], cr["h"], cr["wpr"] = w, h, t.wpr
+    cr["plane"] = planes_of_roi
+    cr["frame"] = t.frame
+    return cr, int((w * h).sum()), int(h.sum())
+
+
+def _engine_fa_segment(self, rm, crops, total_px, total_rows, planes, H, W, fa_params, min_size,
+                       close_radius, want_labels=False, comp_cap=None):
+    mem = self.mem
+    n = crops.shape[0]
+    d_crops = mem.from_host(crops if n else np.zeros(1, CROP))
+    words = max(rm.table.total_words, 1)
+    bw_a, bw_b, bw_f, rootbits = (mem.empty(words, np.uint32) for _ in range(4))
+    L = mem.empty(max(total_px, 1), np.int32)
+    csize = mem.empty(max(total_px, 1), np.uint32)
+    row_roots = mem.empty(max(total_rows, 1), np.int32)
+    row_base = mem.empty(max(total_rows, 1), np.int32)
+    crop_count = mem.empty(max(n, 1), np.int32)
+    comp_off = mem.zeros(n + 1, np.int32)
+    if comp_cap is None:   # rigorous bound on 8-connected components of an h x w image
+        comp_cap = int(sum(((int(c["h"]) + 1) // 2) * ((int(c["w"]) + 1) // 2) for c in crops)) or 1
+    comps = mem.empty(comp_cap, COMP)
+    labels = mem.empty(max(total_px, 1), np.int32) if want_labels else None
+    self.call("ipb_fa_segment", d_crops.ptr, n, int(crops["h"].max()) if n else 0, int(total_rows),
+              planes.ptr, int(H), int(W), fa_params.ptr, rm.pool.ptr, float(min_size), int(close_radius),
+              bw_a.ptr, bw_b.ptr, L.ptr, csize.ptr, rootbits.ptr, row_roots.ptr, row_base.ptr,
+              crop_count.ptr, bw_f.ptr, comp_off.ptr, comps.ptr, int(comp_cap),
+              labels.ptr if labels is not None else None, mem.stream)
+    return FaResult(crops, bw_f, comp_off, comps, labels, comp_cap,
+                    (d_crops, bw_a, bw_b, rootbits, L, csize, row_roots, row_base, crop_count))
+
+
+Engine.fa_segment = _engine_fa_segment

@@ -238,3 +238,113 @@ def fret_batch(eng, planes, shape, polys_per_frame, p, donor_ch=0, acc_ch=1, wan
                 row[f"{name}_median"] = float(oo["q"][1]) if nn else math.nan
             rows_per_frame[f].append(row)
     return {"rows_per_frame": rows_per_frame, "fparams": fparams, "R": R, "R_roi": Rroi, "masks": rm}
+
+
+# ====================================================================== focal adhesions
+FA_CATS = ("OK", "Large", "Small")
+
+
+def fa_um_to_px_config(params, px_size):
+    """FA_Analyzer.py:527-535."""
+    return {"alpha": params["alpha"], "min_px": params["min_area_um"] / (px_size ** 2),
+            "max_px": params["max_area_um"] / (px_size ** 2),
+            "close_radius": params["close_radius"], "subtract_bg": params.get("subtract_bg", True)}
+
+
+def fa_batch(eng, planes, shape, polys_per_frame, params, px_size, channel=0, save_ok_only=True,
+             want_labels=False, config=None):
+    """FA_Analyzer batch body for F frames (reference src/INT/FA_Analyzer.py:984-1039):
+    global stats -> per-ROI crop + skimage mask -> analyze_fa_crop -> CSV rows.
+
+    Returns dict(rows_per_frame, stats (host [F][4] = mean, std, bg, thr), result (FaResult),
+    items_per_crop, d2h_bytes)."""
+    F, C, H, W = shape
+    config = config or fa_um_to_px_config(params, px_size)
+    specs, owner, rects = [], [], []
+    for f, polys in enumerate(polys_per_frame):
+        for i, P in enumerate(polys or []):
+            spec, rect = geo.fa_spec(P, (H, W), frame=f)
+            if spec is None:
+                continue                      # empty crop: reference returns empty results
+            specs.append(spec)
+            owner.append((f, i + 1))
+            rects.append(rect)
+    rm = eng.rasterize(geo.RULE_SK, specs, (H, W), F, want_union=False)
+    # global stats: exact moments of the whole plane + percentile(img[::10, ::10], 1.0)
+    jobs = np.zeros(F, dtype=HIST_JOB)
+    jobs["plane"] = np.arange(F) * C + channel
+    jobs["pattern"] = PAT_STRIDE2D
+    jobs["k"] = 10
+    jobs["moments"] = 1
+    hres = eng.hist(planes, H, W, jobs)
+    qj = np.zeros(F, dtype=Q_JOB)
+    qj["hist"] = np.arange(F)
+    qj["q32"] = q32_of(1.0)
+    qout = eng.quantiles(hres, qj)
+    fa_params = eng.mem.empty((F, 4), np.float32)
+    eng.fa_params(hres, np.arange(F), qout, F, H * W, config["alpha"], fa_params)
+    rows_per_frame = [[] for _ in range(F)]
+    if not specs:
+        return {"rows_per_frame": rows_per_frame, "stats": fa_params.host(), "result": None,
+                "items_per_crop": [], "d2h_bytes": 16 * F}
+    crops, total_px, total_rows = ops.crops_from_masks(rm, np.array([f * C + channel for f, _ in owner]))
+    res = eng.fa_segment(rm, crops, total_px, total_rows, planes, H, W, fa_params,
+                         config["min_px"] if config["min_px"] > 0 else 0.0,
+                         int(config["close_radius"]) if config["close_radius"] > 0 else 0,
+                         want_labels=want_labels)
+    comp_off = res.comp_off.host()
+    total = int(comp_off[-1])
+    if total > res.cap:
+        raise RuntimeError("fa_segment: component table overflow")
+    comps = res.comps.host()[:total]
+    stats = fa_params.host()
+    items_per_crop = fa_items(comps, comp_off, owner, stats, config)
+    for k, (f, cell_id) in enumerate(owner):
+        th_val = np.float32(stats[f, 3])
+        for cat in FA_CATS:
+            if save_ok_only and cat != "OK":
+                continue
+            for it in items_per_crop[k][cat]:
+                rows_per_frame[f].append({
+                    "Cell_ID": cell_id, "Category": cat, "Area_px": it["area"],
+                    "Area_um2": it["area"] * (px_size ** 2),
+                    "Mean_Intensity_Raw": it["mean_int_raw"], "Mean_Intensity_Corr": it["mean_int_corr"],
+                    "Int_Density_Raw": it["int_den_raw"], "Int_Density_Corr": it["int_den_corr"],
+                    "Background_Level": it["bg_level"], "Used_Alpha": params["alpha"],
+                    "Global_Threshold": th_val, "Min_Area_Setting": params["min_area_um"],
+                    "Max_Area_Setting": params["max_area_um"],
+                    "Close_Radius_Setting": params["close_radius"],
+                    "Subtract_BG_Setting": params.get("subtract_bg", True)})
+    return {"rows_per_frame": rows_per_frame, "stats": stats, "result": res,
+            "items_per_crop": items_per_crop, "owner": owner, "rects": rects,
+            "d2h_bytes": int(comps.nbytes + comp_off.nbytes + stats.nbytes)}
+
+
+def fa_items(comps, comp_off, owner, stats, config):
+    """Per-adhesion dicts in the reference's format (FA_Analyzer.py:166-193) from the exact
+    integer component table.  dtypes follow the reference: area np.float64, mean np.float32,
+    integrated densities float64, centroid float64 (row, col) in crop coordinates."""
+    out = []
+    min_px, max_px = config["min_px"], config["max_px"]
+    subtract_bg = config.get("subtract_bg", True)
+    for k, (f, _) in enumerate(owner):
+        res = {"OK": [], "Large": [], "Small": []}
+        bg_val = np.float32(stats[f, 2])
+        seg = comps[comp_off[k]: comp_off[k + 1]]
+        for lab, c in enumerate(seg, 1):
+            area = np.float64(c["area"])
+            mean_raw = np.float32(float(c["sum_i"]) / float(c["area"]))
+            category = "OK"
+            if area < min_px:
+                category = "Small"
+            elif area > max_px:
+                category = "Large"
+            mean_corr = max(0, mean_raw - bg_val) if subtract_bg else mean_raw
+            res[category].append({
+                "label": lab, "area": area, "contour": None,
+                "centroid": (float(c["sum_y"]) / float(c["area"]), float(c["sum_x"]) / float(c["area"])),
+                "mean_int_raw": mean_raw, "mean_int_corr": mean_corr,
+                "int_den_raw": mean_raw * area, "int_den_corr": mean_corr * area,
+                "bg_level": bg_val})
+        out.append(res)
+    return out

@@ -49,4 +49,5 @@ class TimelapseJob:
             "ipb_fret_pixels": 8 * px,                  # 2 x uint16 in, float32 ratio out
             "ipb_region_stats": 4 * roi_px * 3,         # one value per ROI pixel per job
             "ipb_rasterize_rois": roi_px // 8 + 1,      # bit masks written
+            "ipb_fa_segment": 2 * roi_px,               # crop pixels of the FA channel read once
         }.get(entry, 0)

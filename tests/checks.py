@@ -202,3 +202,64 @@ FRET_CASES = [("Donor/FRET", "full", True), ("FRET/Donor", "roi_union", True),
               ("FRET/Donor", "full", False)]
 RASTER_CHECKS = [check_mpl_small_scene, check_mpl_random_polygons, check_sk_crops_match_oracle,
                  check_sk_random_polygons, check_fa_fixture_polygons_sk]
+
+
+FA_CASES = [
+    {"alpha": 2.0, "min_area_um": 12.5 * 0.112 ** 2, "max_area_um": 300.0 * 0.112 ** 2, "close_radius": 1, "subtract_bg": True},
+    {"alpha": 1.0, "min_area_um": 0.0, "max_area_um": 50.0 * 0.112 ** 2, "close_radius": 0, "subtract_bg": False},
+    {"alpha": 3.0, "min_area_um": 30.0 * 0.112 ** 2, "max_area_um": 5000.0 * 0.112 ** 2, "close_radius": 2, "subtract_bg": True},
+    {"alpha": 1.5, "min_area_um": 5.0 * 0.112 ** 2, "max_area_um": 5000.0 * 0.112 ** 2, "close_radius": 5, "subtract_bg": True},
+]
+
+
+def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168):
+    """FA chain vs the oracle's analyze_fa_crop: bw mask, label image, counts, areas and
+    categories bit-exact; float32 mean within REL; CSV rows in the reference's order.
+    Thresholds come from exact integer moments; if numpy's pairwise float32 mean/std gives a
+    different float32 threshold AND an integer lies between the two, the frame is compared
+    with the oracle fed OUR stats (north_star: flips limited to pixels within fp32 eps of the
+    threshold); the count of such frames is returned."""
+    px = 0.112
+    frames = [small_scene(s, H=H, W=W, n_cells=2, blobs=10) for s in seeds]
+    planes = np.stack([np.stack([d, a]) for d, a, _ in frames])
+    F, C = planes.shape[:2]
+    out = pipeline.fa_batch(eng, eng.mem.from_host(planes), (F, C, H, W), [fr[2] for fr in frames],
+                            params, px, channel=0, save_ok_only=False, want_labels=True)
+    cfg = pipeline.fa_um_to_px_config(params, px)
+    straddles = 0
+    k = 0
+    for f, (d, a, polys) in enumerate(frames):
+        img = d.astype(np.float32)
+        ref_stats = port.fa_global_stats(img)
+        got = out["stats"][f]
+        assert got[2] == ref_stats[2]                                   # bg percentile: exact
+        assert close(float(got[0]), float(ref_stats[0]), 1e-6) and close(float(got[1]), float(ref_stats[1]), 1e-6)
+        thr_ref = ref_stats[0] + cfg["alpha"] * ref_stats[1]
+        stats = ref_stats
+        if np.float32(got[3]) != thr_ref:
+            lo, hi = sorted((float(got[3]), float(thr_ref)))
+            if math.floor(hi) > math.floor(lo) or lo == math.floor(lo):
+                straddles += 1
+            stats = (np.float32(got[0]), np.float32(got[1]), ref_stats[2])
+            assert np.float32(got[3]) == stats[0] + cfg["alpha"] * stats[1]
+        want_rows = []
+        for i, P in enumerate(polys):
+            crop, mask, rect = port.fa_crop_and_mask(img, P.copy())
+            assert out["rects"][k] == rect and out["owner"][k] == (f, i + 1)
+            res, thr, bw, lab = port.analyze_fa_crop(crop, mask, cfg, stats, with_contours=False)
+            assert np.array_equal(out["result"].bw_host(k), bw), (f, i)
+            assert np.array_equal(out["result"].labels_host(k), lab), (f, i)
+            for cat in ("OK", "Large", "Small"):
+                g_items, w_items = out["items_per_crop"][k][cat], res[cat]
+                assert len(g_items) == len(w_items), (f, i, cat)
+                for g, w in zip(g_items, w_items):
+                    assert g["label"] == w["label"] and g["area"] == w["area"]
+                    assert type(g["area"]) is type(w["area"]) and type(g["mean_int_raw"]) is type(w["mean_int_raw"])
+                    assert g["centroid"] == w["centroid"]
+                    assert close(float(g["mean_int_raw"]), float(w["mean_int_raw"]))
+                    assert close(float(g["mean_int_corr"]), float(w["mean_int_corr"]), 1e-4)
+                    assert close(float(g["int_den_raw"]), float(w["int_den_raw"]))
+                    assert g["bg_level"] == w["bg_level"]
+            k += 1
+    assert k == len(out["owner"])
+    return straddles

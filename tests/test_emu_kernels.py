@@ -26,3 +26,13 @@ def test_intensity_batch(eng, scope, stride, mode):
 @pytest.mark.parametrize("ratio_mode,scope,clip", checks.FRET_CASES)
 def test_fret_batch(eng, ratio_mode, scope, clip):
     checks.check_fret_batch(eng, ratio_mode, scope, clip)
+
+
+@pytest.mark.parametrize("params", checks.FA_CASES, ids=lambda p: f"a{p['alpha']}_r{p['close_radius']}")
+def test_fa_batch(eng, params):
+    checks.check_fa_batch(eng, params)
+
+
+@pytest.mark.parametrize("exp", ["e1_P0", "e2_P1"])
+def test_intensity_golden(eng, exp):
+    checks.check_intensity_golden(eng, exp)
