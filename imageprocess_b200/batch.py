@@ -1,0 +1,652 @@
+"""FrameBatchJob: the fused per-frame hot path for a batch of F frames resident in HBM
+(BASELINE.json config C4).
+
+One ``run()`` = geometry tables built with vectorised numpy -> ONE pinned H2D copy of all
+tables -> ~25 kernel launches on the current stream with no host synchronisation in
+between -> ONE D2H copy of the packed result tables (+ a second, exact-size copy of the
+per-adhesion table).  Device workspace is allocated once and reused across steps.
+
+Stages (any subset):
+  "fret"  fret_ratio_builder.process_one_stage numeric body (reference
+          src/FRET/fret_ratio_builder.py:454-474,493-507): backgrounds, epsilon, ratio image,
+          per-ROI ratio / donor / acceptor statistics
+  "int"   Fluor_INT._process_key_task numeric body (src/INT/Fluor_INT.py:839-870):
+          background per channel, per-ROI 9 statistics per channel
+  "fa"    FA_Analyzer batch body (src/INT/FA_Analyzer.py:984-1039): global stats, per-cell
+          crop + skimage mask, analyze_fa_crop, per-adhesion table
+Results are numpy structured tables; ``rows_*`` helpers turn them into the reference's row
+dicts for the unchanged pandas writers.
+"""
+import math
+
+import numpy as np
+
+from . import geometry as geo
+from . import ops
+from .ops import (COMP, CROP, FP_BA, FP_BD, FP_STRIDE, FRET_CFG, HIST_JOB, PAT_FULL, PAT_MASKED,
+                  PAT_MASKED_STRIDE, PAT_STRIDE1D, PAT_STRIDE2D, Q_JOB, Q_OUT, QK_MEDIAN, QK_PCT,
+                  REGION, SRC_F32, SRC_U16, STAT_JOB, STAT_OUT, q32_of)
+
+_ALIGN = 256
+
+
+def _al(n):
+    return (int(n) + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class _Arena:
+    """Named sections inside one byte buffer (host pinned or device)."""
+
+    def __init__(self):
+        self.sections, self.size = {}, 0
+
+    def add(self, name, dtype, shape):
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        self.sections[name] = (self.size, np.dtype(dtype), shape, nbytes)
+        self.size = _al(self.size + max(nbytes, 1))
+
+    def view(self, base_np, name):
+        off, dt, shape, nbytes = self.sections[name]
+        return base_np[off: off + nbytes].view(dt).reshape(shape)
+
+    def ptr(self, base_ptr, name):
+        return base_ptr + self.sections[name][0]
+
+
+class BatchResult:
+    """Host tables of one run() (numpy) + handles of the device-resident images."""
+    pass
+
+
+class FrameBatchJob:
+    def __init__(self, eng, shape, stages=("fret", "int", "fa"), fret_p=None, int_task=None,
+                 fa_params=None, fa_px=0.112, donor_ch=0, acc_ch=1, fa_ch=0, int_channels=None,
+                 want_roi_image=False, want_labels=False, fa_config=None, fa_save_ok_only=True):
+        self.eng, self.mem = eng, eng.mem
+        self.F, self.C, self.H, self.W = (int(s) for s in shape)
+        self.stages = tuple(s for s in ("fret", "int", "fa") if s in stages)
+        self.fret_p, self.int_task, self.fa_user = fret_p, int_task, fa_params
+        self.fa_px, self.fa_save_ok_only = fa_px, fa_save_ok_only
+        self.fa_cfg = fa_config or (fa_um_to_px_config(fa_params, fa_px) if fa_params else None)
+        self.donor_ch, self.acc_ch, self.fa_ch = donor_ch, acc_ch, fa_ch
+        self.int_ch = list(int_channels) if int_channels is not None else list(range(self.C))
+        self.want_roi_image, self.want_labels = want_roi_image, want_labels
+        self._bufs = {}
+        self._pin = None
+        self.n_roi_px = 0
+        self.union_wpr = (self.W + 31) // 32
+        if "fret" in self.stages:
+            assert fret_p is not None
+        if "int" in self.stages:
+            assert int_task is not None
+        if "fa" in self.stages:
+            assert self.fa_cfg is not None
+
+    # ------------------------------------------------------------------ buffers
+    def _dev(self, name, nbytes):
+        b = self._bufs.get(name)
+        if b is None or b.nbytes < nbytes:
+            b = self.mem.empty(int(nbytes * 1.25) + 256, np.uint8)
+            self._bufs[name] = b
+        return b
+
+    def _pinned(self, name, nbytes):
+        p = self._bufs.get(name)
+        if p is None or p[0].nbytes < nbytes:
+            p = self.mem.pinned(int(nbytes * 1.25) + 256, np.uint8)
+            self._bufs[name] = p
+        return p
+
+    # ------------------------------------------------------------------ the step
+    def run(self, planes, polys_per_frame):
+        eng, mem, F, C, H, W = self.eng, self.mem, self.F, self.C, self.H, self.W
+        st = self.stages
+        need_mpl = ("fret" in st) or ("int" in st)
+        verts, off, frame, roi = geo.flatten_polys(polys_per_frame)
+        NR = off.shape[0] - 1
+        cnt = np.diff(off)
+        res = BatchResult()
+        res.frame, res.roi, res.n_rois = frame, roi, NR
+        stream = mem.stream
+
+        # ---- geometry (host, vectorised)
+        T = _Arena()                       # uploaded tables
+        if need_mpl:
+            m_rect = geo.mpl_tables(verts, off, W, H)
+            m_wpr, m_rows, m_moff = geo._mask_layout(m_rect)
+        if "fa" in st:
+            fa = geo.fa_tables(verts, off, W, H)
+            f_wpr, f_rows, f_moff = geo._mask_layout(fa["srect"])
+            fw = (fa["srect"][:, 2]).astype(np.int64)
+            fh = (fa["srect"][:, 3]).astype(np.int64)
+            res.fa_rect = fa["crop_rect"]
+        T.add("vert_off", np.int32, NR + 1)
+        T.add("frame", np.int32, max(NR, 1))
+        if need_mpl:
+            T.add("m_verts", np.float64, (max(verts.shape[0], 1), 2))
+            T.add("m_rect", np.int32, (max(NR, 1), 4))
+            T.add("m_org", np.int32, (max(NR, 1), 2))
+            T.add("m_moff", np.int64, NR + 1)
+            T.add("regions", REGION, max(NR, 1))
+        if "fa" in st:
+            T.add("f_verts", np.float64, (max(verts.shape[0], 1), 2))
+            T.add("f_erect", np.int32, (max(NR, 1), 4))
+            T.add("f_srect", np.int32, (max(NR, 1), 4))
+            T.add("f_org", np.int32, (max(NR, 1), 2))
+            T.add("f_moff", np.int64, NR + 1)
+            T.add("crops", CROP, max(NR, 1))
+
+        # ---- job tables
+        has_rois = np.zeros(F, dtype=bool)
+        has_rois[frame] = True
+        hist_jobs = []
+        hidx = {}
+        if "fret" in st:
+            p = self.fret_p
+            masked = (p["bg_scope"] == "roi_union")
+            for key, ch in (("fret_d", self.donor_ch), ("fret_a", self.acc_ch)):
+                j = np.zeros(F, dtype=HIST_JOB)
+                j["plane"] = np.arange(F) * C + ch
+                j["mask_frame"] = np.arange(F)
+                j["pattern"] = np.where(masked & has_rois, PAT_MASKED, PAT_FULL)
+                hidx[key] = sum(x.shape[0] for x in hist_jobs)
+                hist_jobs.append(j)
+        if "int" in st:
+            t = self.int_task
+            stride = int(t["bg_stride"]) if t.get("bg_stride") else 1
+            masked = (t["bg_scope"] == "roi_union")
+            for ci, ch in enumerate(self.int_ch):
+                j = np.zeros(F, dtype=HIST_JOB)
+                j["plane"] = np.arange(F) * C + ch
+                j["mask_frame"] = np.arange(F)
+                j["k"] = stride
+                if stride > 1:
+                    j["pattern"] = np.where(masked & has_rois, PAT_MASKED_STRIDE, PAT_STRIDE1D)
+                else:
+                    j["pattern"] = np.where(masked & has_rois, PAT_MASKED, PAT_FULL)
+                hidx[("int", ci)] = sum(x.shape[0] for x in hist_jobs)
+                hist_jobs.append(j)
+        if "fa" in st:
+            j = np.zeros(F, dtype=HIST_JOB)
+            j["plane"] = np.arange(F) * C + self.fa_ch
+            j["pattern"], j["k"], j["moments"] = PAT_STRIDE2D, 10, 1
+            hidx["fa"] = sum(x.shape[0] for x in hist_jobs)
+            hist_jobs.append(j)
+        hist_jobs = np.concatenate(hist_jobs) if hist_jobs else np.zeros(0, dtype=HIST_JOB)
+        NH = hist_jobs.shape[0]
+        has_ms = bool((hist_jobs["pattern"] == PAT_MASKED_STRIDE).any())
+
+        # params layout (float32): [fret F*4 | int F*Ci | fa F*4]
+        Ci = len(self.int_ch)
+        P_FRET, P_INT, P_FA = 0, F * FP_STRIDE, F * FP_STRIDE + F * Ci
+        NP = P_FA + F * 4
+        qjobs, qdst = [], []
+        qidx = {}
+
+        def add_q(key, h0, q32, dst):
+            q = np.zeros(F, dtype=Q_JOB)
+            q["hist"] = h0 + np.arange(F)
+            q["q32"] = q32
+            qidx[key] = sum(x.shape[0] for x in qjobs)
+            qjobs.append(q)
+            qdst.append(np.asarray(dst, dtype=np.int32))
+
+        host_bg = {}
+        if "fret" in st:
+            p = self.fret_p
+            per_ch = bool(p["per_channel_p"])
+            d_p = float(p["donor_p"]) if per_ch else float(p["percentile"])
+            a_p = float(p["fret_p"]) if per_ch else float(p["percentile"])
+            numer_is_acc = p["ratio_mode"] == "FRET/Donor"
+            pct = p["bg_mode"] == "percentile"
+            neg = np.full(F, -1)
+            add_q("fret_d", hidx["fret_d"], q32_of(d_p), P_FRET + np.arange(F) * FP_STRIDE + FP_BD if pct else neg)
+            add_q("fret_a", hidx["fret_a"], q32_of(a_p), P_FRET + np.arange(F) * FP_STRIDE + FP_BA if pct else neg)
+            add_q("fret_eps", hidx["fret_d"] if numer_is_acc else hidx["fret_a"], q32_of(p["eps_percentile"]), neg)
+            if p["bg_mode"] == "hist-mode":
+                host_bg["fret"] = (d_p, a_p)
+        if "int" in st:
+            t = self.int_task
+            p_glob = float(t["percentile"])
+            self._int_p = [float(t["ch_p_map"].get(self._ch_name(ci), p_glob)) if t.get("per_channel_p") else p_glob
+                           for ci in range(Ci)]
+            pct = t["bg_mode"] == "percentile"
+            for ci in range(Ci):
+                add_q(("int", ci), hidx[("int", ci)], q32_of(self._int_p[ci]),
+                      P_INT + np.arange(F) * Ci + ci if pct else np.full(F, -1))
+            if t["bg_mode"] == "hist-mode":
+                host_bg["int"] = True
+        if "fa" in st:
+            add_q("fa", hidx["fa"], q32_of(1.0), np.full(F, -1))
+        qjobs = np.concatenate(qjobs) if qjobs else np.zeros(0, dtype=Q_JOB)
+        qdst = np.concatenate(qdst) if qdst else np.zeros(0, dtype=np.int32)
+        NQ = qjobs.shape[0]
+
+        # region-stat jobs: per ROI  [fret: R, donor, acceptor][int: one per channel]
+        per_roi_jobs = (3 if "fret" in st else 0) + (Ci if "int" in st else 0)
+        sj = np.zeros((NR, per_roi_jobs), dtype=STAT_JOB)
+        col = 0
+        rr = np.arange(NR)
+        if "fret" in st and NR:
+            clipn = int(bool(self.fret_p["clip_neg"]))
+            s = sj[:, col]
+            s["region"], s["src"], s["plane"], s["bidx"] = rr, SRC_F32, frame, -1
+            s["qkind"] = (QK_PCT, QK_MEDIAN, QK_PCT)
+            s["q32"] = (q32_of(5), 0.0, q32_of(95))
+            for k, (ch, slot) in enumerate(((self.donor_ch, FP_BD), (self.acc_ch, FP_BA)), 1):
+                s = sj[:, col + k]
+                s["region"], s["src"], s["plane"] = rr, SRC_U16, frame * C + ch
+                s["bidx"] = P_FRET + frame * FP_STRIDE + slot
+                s["clip_neg"] = clipn
+                s["qkind"] = (0, QK_MEDIAN, 0)
+            col += 3
+        if "int" in st and NR:
+            clipn = int(bool(self.int_task["clip_neg"]))
+            for ci, ch in enumerate(self.int_ch):
+                s = sj[:, col + ci]
+                s["region"], s["src"], s["plane"] = rr, SRC_U16, frame * C + ch
+                s["bidx"] = P_INT + frame * Ci + ci
+                s["clip_neg"] = clipn
+                s["qkind"] = (QK_PCT, QK_MEDIAN, QK_PCT)
+                s["q32"] = (q32_of(5), 0.0, q32_of(95))
+        sj = np.ascontiguousarray(sj).reshape(-1)
+        NS = sj.shape[0]
+
+        T.add("hist_jobs", HIST_JOB, max(NH, 1))
+        T.add("qjobs", Q_JOB, max(NQ, 1))
+        T.add("qdst", np.int32, max(NQ, 1))
+        T.add("stat_jobs", STAT_JOB, max(NS, 1))
+        T.add("fa_stat_idx", np.int32, F)
+
+        # ---- fill pinned table buffer, single H2D
+        pin_np, pin_t = self._pinned("pin_tables", T.size)
+        V = lambda name: T.view(pin_np, name)
+        V("vert_off")[:] = off.astype(np.int32)
+        if NR:
+            V("frame")[:NR] = frame
+        if need_mpl:
+            V("m_verts")[: verts.shape[0]] = verts
+            V("m_rect")[:NR] = m_rect
+            V("m_org")[:NR] = 0
+            V("m_moff")[:] = m_moff
+            reg = V("regions")
+            if NR:
+                r = reg[:NR]
+                r["mask_off"] = m_moff[:-1]
+                r["x0"], r["y0"] = m_rect[:, 0], m_rect[:, 1]
+                r["w"], r["h"] = m_rect[:, 2] - m_rect[:, 0], m_rect[:, 3] - m_rect[:, 1]
+                r["wpr"], r["frame"], r["use_and"], r["pad0"] = m_wpr, frame, 0, 0
+        if "fa" in st:
+            V("f_verts")[: verts.shape[0]] = fa["local_verts"]
+            V("f_erect")[:NR] = fa["erect"]
+            V("f_srect")[:NR] = fa["srect"]
+            V("f_org")[:NR] = fa["org"]
+            V("f_moff")[:] = f_moff
+            pix_off = np.zeros(NR + 1, dtype=np.int64)
+            row_off = np.zeros(NR + 1, dtype=np.int64)
+            np.cumsum(fw * fh, out=pix_off[1:])
+            np.cumsum(fh, out=row_off[1:])
+            if NR:
+                c = V("crops")[:NR]
+                c["bit_off"], c["pix_off"], c["row_off"] = f_moff[:-1], pix_off[:-1], row_off[:-1]
+                c["ox"], c["oy"] = fa["org"][:, 0], fa["org"][:, 1]
+                c["w"], c["h"], c["wpr"] = fw, fh, f_wpr
+                c["plane"], c["frame"], c["pad0"] = frame * C + self.fa_ch, frame, 0
+            res.fa_crops = V("crops")[:NR].copy()
+            total_px, total_rows = int(pix_off[-1]), int(row_off[-1])
+            comp_cap = int((((fh + 1) // 2) * ((fw + 1) // 2)).sum()) or 1
+        if NH:
+            V("hist_jobs")[:NH] = hist_jobs
+        if NQ:
+            V("qjobs")[:NQ] = qjobs
+            V("qdst")[:NQ] = qdst
+        if NS:
+            V("stat_jobs")[:NS] = sj
+        if "fa" in st:
+            V("fa_stat_idx")[:] = hidx["fa"] + np.arange(F)
+        d_tab = self._dev("d_tables", T.size)
+        mem.upload_async(d_tab, pin_t, T.size)
+        tp = lambda name: T.ptr(d_tab.ptr, name)
+
+        # ---- device output arena (one D2H at the end)
+        O = _Arena()
+        O.add("params", np.float32, max(NP, 1))
+        O.add("m_area", np.uint32, max(NR, 1))
+        O.add("f_area", np.uint32, max(NR, 1))
+        O.add("stat_out", STAT_OUT, max(NS, 1))
+        O.add("comp_off", np.int32, NR + 1)
+        d_out = self._dev("d_out", O.size)
+        op = lambda name: O.ptr(d_out.ptr, name)
+        lib_call = eng.call
+
+        # ---- rasterise
+        if need_mpl:
+            m_pool = self._dev("m_pool", 4 * max(int(m_moff[-1]), 1))
+            d_union = self._dev("union", 4 * F * H * self.union_wpr)
+            mem.zero_bytes(d_union, 4 * F * H * self.union_wpr)
+            lib_call("ipb_rasterize_rois", geo.RULE_MPL, NR, tp("m_verts"), tp("vert_off"), tp("m_rect"),
+                     tp("m_rect"), tp("m_org"), tp("frame"), tp("m_moff"),
+                     int(m_rows.max()) if NR else 0, int(m_wpr.max()) if NR else 0, m_pool.ptr,
+                     op("m_area"), d_union.ptr, self.union_wpr, H, stream)
+            union_ptr = d_union.ptr
+        else:
+            union_ptr = None
+        if "fa" in st:
+            f_pool = self._dev("f_pool", 4 * max(int(f_moff[-1]), 1))
+            lib_call("ipb_rasterize_rois", geo.RULE_SK, NR, tp("f_verts"), tp("vert_off"), tp("f_erect"),
+                     tp("f_srect"), tp("f_org"), tp("frame"), tp("f_moff"),
+                     int(f_rows.max()) if NR else 0, int(f_wpr.max()) if NR else 0, f_pool.ptr,
+                     op("f_area"), None, self.union_wpr, H, stream)
+
+        # ---- histograms -> percentiles -> per-frame scalars
+        d_hist = self._dev("hist", 4 * 65536 * max(NH, 1))
+        d_hstat = self._dev("hstat", 8 * 4 * max(NH, 1))
+        d_scr = self._dev("rank_scratch", 8 * max(NH, 1) * H) if has_ms else None
+        d_qout = self._dev("qout", Q_OUT.itemsize * max(NQ, 1))
+        mem.zero_bytes(d_out, O.sections["params"][3], O.sections["params"][0])
+        if NH:
+            lib_call("ipb_hist_u16", planes.ptr, H, W, tp("hist_jobs"), NH, int(has_ms), union_ptr,
+                     self.union_wpr, d_scr.ptr if d_scr is not None else None, d_hist.ptr, d_hstat.ptr, stream)
+            lib_call("ipb_hist_quantiles", d_hist.ptr, d_hstat.ptr, tp("qjobs"), NQ, d_qout.ptr, stream)
+            lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), stream)
+        if host_bg:
+            self._host_hist_mode(host_bg, d_hist, hidx, d_out, O, NH, P_FRET, P_INT, Ci)
+        if "fret" in st:
+            den_slot = FP_BD if numer_is_acc else FP_BA
+            lib_call("ipb_fret_eps", d_qout.ptr + Q_OUT.itemsize * qidx["fret_eps"], F, den_slot,
+                     int(bool(self.fret_p["clip_neg"])), 5.0, op("params") + 4 * P_FRET, stream)
+        if "fa" in st:
+            lib_call("ipb_fa_params", d_hstat.ptr, tp("fa_stat_idx"), d_qout.ptr + Q_OUT.itemsize * qidx["fa"],
+                     F, H * W, float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, stream)
+
+        # ---- fused FRET pass
+        if "fret" in st:
+            d_R = self._dev("R", 4 * F * H * W)
+            d_Rroi = self._dev("Rroi", 4 * F * H * W) if self.want_roi_image else None
+            cfg = fret_cfg(self.fret_p, C, self.donor_ch, self.acc_ch)
+            lib_call("ipb_fret_pixels", planes.ptr, F, H, W, cfg.ctypes.data, op("params") + 4 * P_FRET,
+                     union_ptr, self.union_wpr, d_R.ptr, None,
+                     d_Rroi.ptr if d_Rroi is not None else None, None, None, stream)
+            res.R = ops_view(d_R, np.float32, (F, H, W), mem)
+            res.R_roi = ops_view(d_Rroi, np.float32, (F, H, W), mem) if d_Rroi is not None else None
+
+        # ---- per-ROI statistics (all stages in one launch)
+        if NS:
+            lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), NS, m_pool.ptr, None, 0, H, W,
+                     planes.ptr, d_R.ptr if "fret" in st else None, op("params"), op("stat_out"), stream)
+
+        # ---- focal adhesions
+        if "fa" in st and NR and total_px > 0:
+            words = max(int(f_moff[-1]), 1)
+            bwA, bwB, bwF, rootb = (self._dev(n, 4 * words) for n in ("bwA", "bwB", "bwF", "rootbits"))
+            d_L = self._dev("L", 4 * total_px)
+            d_cs = self._dev("csize", 4 * total_px)
+            d_rr = self._dev("row_roots", 4 * total_rows)
+            d_rb = self._dev("row_base", 4 * total_rows)
+            d_cc = self._dev("crop_count", 4 * NR)
+            d_comps = self._dev("comps", COMP.itemsize * comp_cap)
+            d_lab = self._dev("labels", 4 * total_px) if self.want_labels else None
+            cfgf = self.fa_cfg
+            lib_call("ipb_fa_segment", tp("crops"), NR, int(fh.max()), total_rows, planes.ptr, H, W,
+                     op("params") + 4 * P_FA, f_pool.ptr,
+                     float(cfgf["min_px"]) if cfgf["min_px"] > 0 else 0.0,
+                     int(cfgf["close_radius"]) if cfgf["close_radius"] > 0 else 0,
+                     bwA.ptr, bwB.ptr, d_L.ptr, d_cs.ptr, rootb.ptr, d_rr.ptr, d_rb.ptr, d_cc.ptr,
+                     bwF.ptr, op("comp_off"), d_comps.ptr, comp_cap,
+                     d_lab.ptr if d_lab is not None else None, stream)
+            res.fa_bw = ops_view(bwF, np.uint32, (words,), mem)
+            res.fa_labels = ops_view(d_lab, np.int32, (total_px,), mem) if d_lab is not None else None
+            fa_ran = True
+        else:
+            fa_ran = False
+            if "fa" in st:
+                mem.zero_bytes(d_out, O.sections["comp_off"][3], O.sections["comp_off"][0])
+
+        # ---- results: one packed D2H (+ exact-size adhesion table)
+        pout_np, pout_t = self._pinned("pin_out", O.size)
+        mem.download_async(pout_t, d_out, O.size)
+        mem.sync()
+        OV = lambda name: O.view(pout_np, name)
+        params = OV("params")[:NP].copy()
+        res.d2h_bytes = O.size
+        if "fret" in st:
+            res.fret_params = params[P_FRET: P_FRET + F * FP_STRIDE].reshape(F, FP_STRIDE)
+        if "int" in st:
+            res.int_bg = params[P_INT: P_INT + F * Ci].reshape(F, Ci)
+            res.int_p = list(self._int_p)
+        if "fa" in st:
+            res.fa_stats = params[P_FA: P_FA + F * 4].reshape(F, 4)
+        if need_mpl:
+            res.area = OV("m_area")[:NR].copy()
+            self.n_roi_px = int(res.area.sum())
+        so = OV("stat_out")[:NS].copy().reshape(NR, per_roi_jobs) if NS else np.zeros((NR, 0), dtype=STAT_OUT)
+        col = 0
+        if "fret" in st:
+            res.fret_stat = so[:, col: col + 3]
+            col += 3
+        if "int" in st:
+            res.int_stat = so[:, col: col + Ci]
+        if "fa" in st:
+            comp_off = OV("comp_off")[: NR + 1].copy()
+            res.fa_comp_off = comp_off
+            total = int(comp_off[-1]) if fa_ran else 0
+            if fa_ran and total > comp_cap:
+                raise RuntimeError("fa_segment: component table overflow")
+            if total:
+                nb = COMP.itemsize * total
+                pc_np, pc_t = self._pinned("pin_comps", nb)
+                mem.download_async(pc_t, d_comps, nb)
+                mem.sync()
+                res.fa_comps = pc_np[:nb].view(COMP).copy()
+                res.d2h_bytes += nb
+            else:
+                res.fa_comps = np.zeros(0, dtype=COMP)
+        return res
+
+    def _ch_name(self, ci):
+        names = getattr(self, "ch_names", None)
+        return names[ci] if names else self.int_ch[ci] + 1
+
+    def _host_hist_mode(self, host_bg, d_hist, hidx, d_out, O, NH, P_FRET, P_INT, Ci):
+        """'hist-mode' background (non-default GUI option): the 2048-bin np.histogram level is
+        derived on the host from the exact device histogram (<= 65536 distinct values)."""
+        mem, F = self.mem, self.F
+        mem.sync()
+        hh = ops_view(d_hist, np.uint32, (NH, 65536), mem).host()
+        off, _, _, nbytes = O.sections["params"]
+        params = ops_view(d_out, np.uint8, (d_out.nbytes,), mem).host()[off: off + nbytes].view(np.float32).copy()
+        if "fret" in host_bg:
+            d_p, a_p = host_bg["fret"]
+            for f in range(F):
+                for key, slot, pp in (("fret_d", FP_BD, d_p), ("fret_a", FP_BA, a_p)):
+                    lvl = hist_mode_level(hh[hidx[key] + f], pp)
+                    params[P_FRET + f * FP_STRIDE + slot] = 0.0 if lvl is None else lvl
+        if "int" in host_bg:
+            for f in range(F):
+                for ci in range(Ci):
+                    lvl = hist_mode_level(hh[hidx[("int", ci)] + f], self._int_p[ci])
+                    params[P_INT + f * Ci + ci] = 0.0 if lvl is None else lvl
+        tmp = mem.from_host(params)
+        mem.copy_bytes(d_out, off, tmp, 0, nbytes)
+
+    def algorithmic_bytes(self, entry):
+        """Compulsory bytes one launch of `entry` moves (DESIGN.md 'Kernels')."""
+        F, C, H, W = self.F, self.C, self.H, self.W
+        px = F * H * W
+        roi_px = self.n_roi_px or 0
+        n_hist = (2 if "fret" in self.stages else 0) + (len(self.int_ch) if "int" in self.stages else 0) + \
+                 (1 if "fa" in self.stages else 0)
+        return {
+            "ipb_hist_u16": 2 * px * n_hist,             # each sampled plane read once per job
+            "ipb_fret_pixels": 8 * px,                   # 2 x uint16 in, float32 ratio out
+            "ipb_region_stats": 4 * roi_px * 3 + 2 * roi_px * len(self.int_ch),
+            "ipb_rasterize_rois": roi_px // 8 + 1,       # bit masks written
+            "ipb_fa_segment": 2 * roi_px,                # crop pixels of the FA channel read once
+        }.get(entry, 0)
+
+
+def ops_view(buf, dtype, shape, mem):
+    from .device import DevBuf
+    return DevBuf(buf.raw, dtype, shape, mem)
+
+
+def fret_cfg(p, n_ch=2, donor_ch=0, acc_ch=1):
+    cfg = np.zeros(1, dtype=FRET_CFG)
+    cfg["numer_is_acceptor"] = int(p["ratio_mode"] == "FRET/Donor")
+    cfg["clip_neg"] = int(bool(p["clip_neg"]))
+    cfg["g_factor"] = 1.0
+    cfg["donor_ch"], cfg["acc_ch"], cfg["aonly_ch"], cfg["n_ch"] = donor_ch, acc_ch, -1, n_ch
+    return cfg
+
+
+def fa_um_to_px_config(params, px_size):
+    """FA_Analyzer.py:527-535."""
+    return {"alpha": params["alpha"], "min_px": params["min_area_um"] / (px_size ** 2),
+            "max_px": params["max_area_um"] / (px_size ** 2),
+            "close_radius": params["close_radius"], "subtract_bg": params.get("subtract_bg", True)}
+
+
+def hist_mode_level(counts, p):
+    """'hist-mode' background (reference Fluor_INT.py:474-483) from an exact integer
+    histogram: np.histogram of the distinct values weighted by their counts places every
+    value in the same bin as np.histogram of the full sample (same float32 edges)."""
+    vals = np.flatnonzero(counts)
+    if vals.size == 0:
+        return 0.0
+    w = counts[vals].astype(np.float64)
+    hist, bins = np.histogram(vals.astype(np.float32), bins=2048, weights=w)
+    if hist.sum() <= 0:
+        return None
+    cdf = np.cumsum(hist).astype(float)
+    cdf /= cdf[-1]
+    idx = int(np.searchsorted(cdf, float(p) / 100.0, side="left"))
+    if idx >= len(bins) - 1:
+        return float(bins[-1])
+    return float(0.5 * (bins[idx] + bins[idx + 1]))
+
+
+# ====================================================================== tables -> reference rows
+def _f32(x):
+    return float(np.float32(x))
+
+
+def _mean_std(o):
+    n = int(o["n"])
+    if n == 0:
+        return 0, math.nan, math.nan
+    mean = float(o["sum"]) / n
+    return n, _f32(mean), _f32(math.sqrt(max(float(o["ssd"]) / n, 0.0)))
+
+
+def rows_intensity(res, F, ch_names):
+    """Per-frame lists of the dicts quantify_per_roi_multi returns (Fluor_INT.py:509-538)."""
+    out = [[] for _ in range(F)]
+    for r in range(res.n_rois):
+        row = {"roi": int(res.roi[r]), "area_px": int(res.area[r])}
+        for ci, ch in enumerate(ch_names):
+            o = res.int_stat[r, ci]
+            n, mean, std = _mean_std(o)
+            if n == 0:
+                st = dict(mean=math.nan, median=math.nan, std=math.nan, p5=math.nan, p95=math.nan,
+                          vmin=math.nan, vmax=math.nan, vsum=math.nan, npx=0)
+            else:
+                st = dict(mean=mean, median=float(o["q"][1]), std=std, p5=float(o["q"][0]),
+                          p95=float(o["q"][2]), vmin=float(o["vmin"]), vmax=float(o["vmax"]),
+                          vsum=_f32(o["sum"]), npx=n)
+            for k, v in st.items():
+                row[f"ch{ch}_{k}"] = v
+        out[int(res.frame[r])].append(row)
+    return out
+
+
+def rows_fret(res, F):
+    """Per-frame lists of the dicts quantify_per_roi returns (fret_ratio_builder.py:342-362)."""
+    out = [[] for _ in range(F)]
+    for r in range(res.n_rois):
+        o = res.fret_stat[r, 0]
+        n, mean, std = _mean_std(o)
+        row = {"roi": int(res.roi[r]), "area_px": int(res.area[r])}
+        if n == 0:
+            row.update({f"ratio_{k}": math.nan for k in ("mean", "median", "std", "p5", "p95")})
+        else:
+            row.update({"ratio_mean": mean, "ratio_median": float(o["q"][1]), "ratio_std": std,
+                        "ratio_p5": float(o["q"][0]), "ratio_p95": float(o["q"][2])})
+        for name, oo in (("donor", res.fret_stat[r, 1]), ("yfret", res.fret_stat[r, 2])):
+            nn, mm, _ = _mean_std(oo)
+            row[f"{name}_mean"] = mm if nn else math.nan
+            row[f"{name}_median"] = float(oo["q"][1]) if nn else math.nan
+        out[int(res.frame[r])].append(row)
+    return out
+
+
+FA_CATS = ("OK", "Large", "Small")
+
+
+def fa_table(res, cfg):
+    """Vectorised per-adhesion table with the reference's dtypes (FA_Analyzer.py:166-193):
+    area float64, mean float32, integrated densities float64, centroid float64."""
+    comps, off = res.fa_comps, res.fa_comp_off
+    n = comps.shape[0]
+    crop = np.repeat(np.arange(res.n_rois), np.diff(off)) if n else np.zeros(0, dtype=np.int64)
+    label = (np.arange(n) - off[crop] + 1) if n else np.zeros(0, dtype=np.int64)
+    area = comps["area"].astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean_raw = (comps["sum_i"].astype(np.float64) / area).astype(np.float32)
+        cy = comps["sum_y"].astype(np.float64) / area
+        cx = comps["sum_x"].astype(np.float64) / area
+    frame = res.frame[crop] if n else np.zeros(0, dtype=np.int32)
+    bg = res.fa_stats[frame, 2].astype(np.float32) if n else np.zeros(0, dtype=np.float32)
+    if cfg.get("subtract_bg", True):
+        mean_corr = np.maximum(np.float32(0), mean_raw - bg)
+    else:
+        mean_corr = mean_raw
+    cat = np.zeros(n, dtype=np.int8)                         # 0 OK, 1 Large, 2 Small
+    cat[area > cfg["max_px"]] = 1
+    cat[area < cfg["min_px"]] = 2
+    return {"crop": crop, "frame": frame, "cell_id": res.roi[crop] if n else np.zeros(0, np.int32),
+            "label": label, "cat": cat, "area": area, "mean_raw": mean_raw, "mean_corr": mean_corr,
+            "int_den_raw": mean_raw.astype(np.float64) * area, "int_den_corr": mean_corr.astype(np.float64) * area,
+            "cy": cy, "cx": cx, "bg": bg, "thr": res.fa_stats[frame, 3].astype(np.float32) if n else bg}
+
+
+def fa_items(res, cfg):
+    """Per-crop results dicts in analyze_fa_crop's format (FA_Analyzer.py:164-193)."""
+    t = fa_table(res, cfg)
+    out = [{"OK": [], "Large": [], "Small": []} for _ in range(res.n_rois)]
+    for i in range(t["label"].shape[0]):
+        mean_raw, mean_corr, area = t["mean_raw"][i], t["mean_corr"][i], t["area"][i]
+        if cfg.get("subtract_bg", True) and not (mean_raw - t["bg"][i] > 0):
+            mean_corr = 0                        # python max(0, x) keeps the int 0
+        out[int(t["crop"][i])][FA_CATS[t["cat"][i]]].append({
+            "label": int(t["label"][i]), "area": area, "contour": None,
+            "centroid": (float(t["cy"][i]), float(t["cx"][i])), "mean_int_raw": mean_raw,
+            "mean_int_corr": mean_corr, "int_den_raw": mean_raw * area, "int_den_corr": mean_corr * area,
+            "bg_level": t["bg"][i]})
+    return out
+
+
+def rows_fa(res, cfg, user_params, px_size, F, save_ok_only=True):
+    """Per-frame CSV row dicts in the reference's order (FA_Analyzer.py:1019-1039): per cell,
+    categories OK / Large / Small, labels ascending."""
+    t = fa_table(res, cfg)
+    out = [[] for _ in range(F)]
+    n = t["label"].shape[0]
+    if n == 0:
+        return out
+    order = np.lexsort((t["label"], t["cat"], t["crop"]))
+    for i in order:
+        cat = FA_CATS[t["cat"][i]]
+        if save_ok_only and cat != "OK":
+            continue
+        area = t["area"][i]
+        out[int(t["frame"][i])].append({
+            "Cell_ID": int(t["cell_id"][i]), "Category": cat, "Area_px": area,
+            "Area_um2": area * (px_size ** 2), "Mean_Intensity_Raw": t["mean_raw"][i],
+            "Mean_Intensity_Corr": t["mean_corr"][i], "Int_Density_Raw": t["int_den_raw"][i],
+            "Int_Density_Corr": t["int_den_corr"][i], "Background_Level": t["bg"][i],
+            "Used_Alpha": user_params["alpha"], "Global_Threshold": t["thr"][i],
+            "Min_Area_Setting": user_params["min_area_um"], "Max_Area_Setting": user_params["max_area_um"],
+            "Close_Radius_Setting": user_params["close_radius"],
+            "Subtract_BG_Setting": user_params.get("subtract_bg", True)})
+    return out

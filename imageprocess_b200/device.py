@@ -87,9 +87,21 @@ class TorchMem:
         t = self.torch.empty(n, dtype=self.torch.uint8, pin_memory=True)
         return t.numpy().view(dtype).reshape(shape), t
 
-    def upload_async(self, buf, pinned_tensor):
+    def upload_async(self, buf, pinned_tensor, nbytes=None):
         """H2D copy of a pinned tensor into an existing DevBuf on the current stream."""
-        buf.raw[: pinned_tensor.numel()].copy_(pinned_tensor, non_blocking=True)
+        n = pinned_tensor.numel() if nbytes is None else int(nbytes)
+        buf.raw[:n].copy_(pinned_tensor[:n], non_blocking=True)
+
+    def download_async(self, pinned_tensor, buf, nbytes):
+        """D2H copy into a pinned tensor on the current stream (caller syncs)."""
+        n = int(nbytes)
+        pinned_tensor[:n].copy_(buf.raw[:n], non_blocking=True)
+
+    def zero_bytes(self, buf, nbytes, offset=0):
+        buf.raw[int(offset): int(offset) + int(nbytes)].zero_()
+
+    def copy_bytes(self, dst, dst_off, src, src_off, nbytes):
+        dst.raw[int(dst_off): int(dst_off) + int(nbytes)].copy_(src.raw[int(src_off): int(src_off) + int(nbytes)])
 
     def sync(self):
         self.torch.cuda.current_stream(self.device).synchronize()

@@ -129,3 +129,101 @@ class RoiTable:
         self.max_rows = int(sh.max()) if n else 0
         self.max_wpr = int(self.wpr.max()) if n else 0
         self.total_words = int(self.mask_off[-1])
+
+
+# ---------------------------------------------------------------------- vectorised batch tables
+class BatchGeometry:
+    """All ROI tables of a batch of frames, built with vectorised numpy (no per-polygon
+    Python loop).  Results are identical to mpl_spec / fa_spec applied per polygon."""
+    pass
+
+
+def flatten_polys(polys_per_frame):
+    """-> verts (V,2) f64, off (N+1,) int64, frame (N,) int32, roi (N,) int32 (1-based)."""
+    polys, frame, roi = [], [], []
+    for f, pl in enumerate(polys_per_frame):
+        for i, P in enumerate(pl or ()):
+            polys.append(np.asarray(P, dtype=np.float64).reshape(-1, 2))
+            frame.append(f)
+            roi.append(i + 1)
+    n = len(polys)
+    cnt = np.fromiter((p.shape[0] for p in polys), dtype=np.int64, count=n)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(cnt, out=off[1:])
+    verts = np.concatenate(polys, axis=0) if n else np.zeros((0, 2), dtype=np.float64)
+    return verts, off, np.asarray(frame, dtype=np.int32), np.asarray(roi, dtype=np.int32)
+
+
+def _seg_minmax(a, off):
+    if off.shape[0] <= 1:
+        z = np.zeros(0, dtype=np.float64)
+        return z, z
+    idx = off[:-1]
+    return np.minimum.reduceat(a, idx), np.maximum.reduceat(a, idx)
+
+
+def _mask_layout(srect):
+    sw = (srect[:, 2] - srect[:, 0]).astype(np.int64)
+    sh = (srect[:, 3] - srect[:, 1]).astype(np.int64)
+    wpr = (sw + 31) // 32
+    mask_off = np.zeros(srect.shape[0] + 1, dtype=np.int64)
+    np.cumsum(wpr * sh, out=mask_off[1:])
+    return wpr.astype(np.int32), sh.astype(np.int32), mask_off
+
+
+def mpl_tables(verts, off, W, H):
+    """Vectorised mpl_spec: erect == srect == vertex bbox padded by one pixel in x, clipped."""
+    n = off.shape[0] - 1
+    cnt = np.diff(off)
+    xmin, xmax = _seg_minmax(verts[:, 0], off)
+    ymin, ymax = _seg_minmax(verts[:, 1], off)
+    ok = (cnt >= 3) & np.isfinite(xmin) & np.isfinite(xmax) & np.isfinite(ymin) & np.isfinite(ymax)
+    big = 1 << 30
+    def cl(v, hi):
+        return np.clip(np.where(ok, v, 0.0), -big, big).astype(np.int64).clip(0, hi)
+    x0 = cl(np.floor(xmin) - 1, W)
+    y0 = cl(np.floor(ymin), H)
+    x1 = np.maximum(cl(np.ceil(xmax) + 2, W), x0)
+    y1 = np.maximum(cl(np.ceil(ymax) + 1, H), y0)
+    rect = np.stack([x0, y0, x1, y1], axis=1).astype(np.int32)
+    rect[~ok] = 0
+    return rect
+
+
+def fa_tables(verts, off, W, H, pad=5):
+    """Vectorised fa_spec: crop rects (FA_Analyzer.py:998-1003), crop-local vertices and the
+    skimage loop ranges.  Returns dict(local_verts, erect, srect, org, crop_rect)."""
+    n = off.shape[0] - 1
+    cnt = np.diff(off)
+    xmin, xmax = _seg_minmax(verts[:, 0], off)
+    ymin, ymax = _seg_minmax(verts[:, 1], off)
+    fin = np.isfinite(xmin) & np.isfinite(xmax) & np.isfinite(ymin) & np.isfinite(ymax) & (cnt >= 1)
+    sx = lambda v: np.where(fin, v, 0.0)
+    x_min = np.maximum(0, np.floor(sx(xmin)).astype(np.int64) - pad)
+    x_max = np.minimum(W, np.ceil(sx(xmax)).astype(np.int64) + pad)
+    y_min = np.maximum(0, np.floor(sx(ymin)).astype(np.int64) - pad)
+    y_max = np.minimum(H, np.ceil(sx(ymax)).astype(np.int64) + pad)
+    ok = fin & (x_min < x_max) & (y_min < y_max)
+    w = np.where(ok, x_max - x_min, 0)
+    h = np.where(ok, y_max - y_min, 0)
+    local = verts.copy()
+    local[:, 0] -= np.repeat(x_min, cnt)
+    local[:, 1] -= np.repeat(y_min, cnt)
+    cmin, cmax = _seg_minmax(local[:, 0], off)
+    rmin, rmax = _seg_minmax(local[:, 1], off)
+    z = lambda v: np.where(ok, v, 0.0)
+    minr = np.maximum(0.0, z(rmin)).astype(np.int64)
+    maxr = np.minimum(h - 1, np.ceil(z(rmax)).astype(np.int64))
+    minc = np.maximum(0.0, z(cmin)).astype(np.int64)
+    maxc = np.minimum(w - 1, np.ceil(z(cmax)).astype(np.int64))
+    ex0 = np.clip(minc, 0, w)
+    ey0 = np.clip(minr, 0, h)
+    ex1 = np.maximum(np.clip(maxc + 1, 0, w), ex0)
+    ey1 = np.maximum(np.clip(maxr + 1, 0, h), ey0)
+    erect = np.stack([ex0, ey0, ex1, ey1], axis=1).astype(np.int32)
+    erect[~ok] = 0
+    srect = np.stack([np.zeros(n, np.int64), np.zeros(n, np.int64), w, h], axis=1).astype(np.int32)
+    org = np.stack([np.where(ok, x_min, 0), np.where(ok, y_min, 0)], axis=1).astype(np.int32)
+    crop_rect = np.stack([x_min, x_max, y_min, y_max], axis=1)
+    return {"local_verts": local, "erect": erect, "srect": srect, "org": org,
+            "crop_rect": crop_rect, "ok": ok}

@@ -155,7 +155,7 @@ def check_fret_batch(eng, ratio_mode, scope, clip):
          "ratio_mode": ratio_mode}
     out = pipeline.fret_batch(eng, eng.mem.from_host(planes), (F, C, H, W), [fr[2] for fr in frames],
                               p, want_roi_image=True)
-    fp = out["fparams"].host()
+    fp = out["fparams"]
     R = out["R"].host()
     Rroi = out["R_roi"].host()
     for f, (d, a, polys) in enumerate(frames):

@@ -36,6 +36,27 @@ class NumpyMem:
 
     stream = 0
 
+    def pinned(self, shape, dtype):
+        n = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        t = np.zeros(n, dtype=np.uint8)
+        return t.view(dtype).reshape(shape), t
+
+    def upload_async(self, buf, pinned_tensor, nbytes=None):
+        n = pinned_tensor.size if nbytes is None else int(nbytes)
+        buf.raw[:n] = pinned_tensor[:n]
+
+    def download_async(self, pinned_tensor, buf, nbytes):
+        pinned_tensor[: int(nbytes)] = buf.raw[: int(nbytes)]
+
+    def zero_bytes(self, buf, nbytes, offset=0):
+        buf.raw[int(offset): int(offset) + int(nbytes)] = 0
+
+    def copy_bytes(self, dst, dst_off, src, src_off, nbytes):
+        dst.raw[int(dst_off): int(dst_off) + int(nbytes)] = src.raw[int(src_off): int(src_off) + int(nbytes)]
+
+    def event(self):
+        raise NotImplementedError
+
     def sync(self):
         pass
 
