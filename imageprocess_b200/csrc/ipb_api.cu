@@ -192,9 +192,11 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const ui
 {
     if (n_jobs <= 0) return IPB_OK;
     IPB_REQUIRE(regions && jobs && mask_pool && out && H > 0 && W > 0, "ipb_region_stats: bad argument");
-    IPB_LAUNCH(ipb_k_region_stats, dim3(n_jobs), dim3(IPB_RS_THREADS), 0, stream,
+    const int smem = IPB_RS_SMEM_BYTES;
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_region_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "region_stats smem");
+    IPB_LAUNCH(ipb_k_region_stats, dim3(n_jobs), dim3(IPB_RS_THREADS), (size_t)smem, stream,
                (const IpbRegion*)regions, (const IpbStatJob*)jobs, mask_pool, and_bits, and_wpr, H, W,
-               planes, images, bvals, (IpbStatOut*)out);
+               planes, images, bvals, (IpbStatOut*)out, smem);
     return ipb_check_launch("ipb_k_region_stats");
 }
 

@@ -11,10 +11,17 @@
 //                selected on the integer key v and transformed afterwards: exact.
 //   IPB_SRC_F32  value = a float32 image pixel (ratio image); non-finite values are
 //                dropped like the reference's np.isfinite filter; key = ordered-uint32.
-// One CTA per job: pass A gets n, sum, min/max key; then a radix select with 10-bit digits
-// over (key - kmin), i.e. only as many passes as the region's own key range needs (1-2 for
-// uint16 data, <= 4 for floats), resolving all requested ranks (p5 / median / p95 -> up to 6
-// ranks) in the same passes with one shared-memory histogram per distinct prefix.
+//
+// One CTA (1024 threads, one per SM) per job:
+//   gather   warps walk the region's mask words, 4 words per iteration so that 4 coalesced
+//            pixel loads per lane are in flight (lane b <-> bit b); valid values are
+//            compacted as keys into shared memory (ballot/popc positions), while n, sum and
+//            the key range are accumulated.  Regions that do not fit in shared memory keep
+//            the same code path but re-walk global memory in every pass.
+//   select   radix select with 8-bit digits over (key - kmin): only as many passes as the
+//            region's own key range needs, all requested ranks (p5 / median / p95 -> up to 6)
+//            resolved together with one 256-bin histogram per distinct prefix.  The first
+//            pass also accumulates the squared deviations from the float64 mean.
 // numpy's float32 percentile / median arithmetic is replayed from ipb_exact.cuh.
 #pragma once
 #include "ipb_rt.cuh"
@@ -22,11 +29,13 @@
 
 #define IPB_SRC_U16 0
 #define IPB_SRC_F32 1
-#define IPB_RS_THREADS 256
+#define IPB_RS_THREADS 1024
 #define IPB_RS_MAXQ 3
 #define IPB_RS_MAXR (2 * IPB_RS_MAXQ)
-#define IPB_RS_DIGIT 10
+#define IPB_RS_DIGIT 8
 #define IPB_RS_BINS (1 << IPB_RS_DIGIT)
+#define IPB_RS_UNROLL 4
+#define IPB_RS_SMEM_BYTES (200 * 1024)      // dynamic shared memory for the key store
 
 #define IPB_QKIND_NONE 0
 #define IPB_QKIND_PCT 1      // np.percentile(vals, p): q32 = f32(p)/f32(100)
@@ -74,36 +83,76 @@ __device__ __forceinline__ float ipb_rs_transform(const IpbRsCtx& c, unsigned v)
     if (c.clip && t < 0.0f) t = 0.0f;
     return t;
 }
+__device__ __forceinline__ float ipb_rs_value(const IpbRsCtx& c, unsigned key) {
+    return c.src == IPB_SRC_U16 ? ipb_rs_transform(c, key) : ipb_key_f32(key);
+}
 
-// Calls f(key, value) for every measured pixel of the region; returns via `area` the number
-// of region pixels seen by this thread.
-template <typename F>
-__device__ __forceinline__ void ipb_rs_foreach(const IpbRsCtx& c, unsigned long long& area, F f) {
-    const long long nwords = (long long)c.h * c.wpr;
-    for (long long wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
-        const int r = (int)(wi / c.wpr), j = (int)(wi % c.wpr);
-        unsigned m = c.mask[wi];
-        if (!m) continue;
-        const int y = c.y0 + r, xb = c.x0 + 32 * j;
-        if (c.androw0) {
-            const unsigned* ar = c.androw0 + (size_t)y * c.and_wpr;
-            const int k = xb >> 5, s = xb & 31;
-            unsigned lo = ar[k] >> s;
-            if (s && k + 1 < c.and_wpr) lo |= ar[k + 1] << (32 - s);
-            m &= lo;
-        }
-        while (m) {
-            const int b = __ffs((int)m) - 1;
-            m &= m - 1;
-            const int x = xb + b;
-            ++area;
-            if (c.src == IPB_SRC_U16) {
-                const unsigned v = c.u16[(size_t)y * c.W + x];
-                f(v, ipb_rs_transform(c, v));
-            } else {
-                const float v = c.f32[(size_t)y * c.W + x];
-                if (isfinite(v)) f(ipb_f32_key(v), v);
+// One warp-iteration of the region walk: IPB_RS_UNROLL consecutive mask words starting at
+// word w0; lane b owns bit b.  Fills m[u] (warp-uniform word after the AND mask), and for
+// this lane key[u] and ok[u] (pixel belongs to the region and is measured).
+__device__ __forceinline__ void ipb_rs_load_group(const IpbRsCtx& c, long long w0, long long nwords, int lane,
+                                                  unsigned (&m)[IPB_RS_UNROLL], unsigned (&key)[IPB_RS_UNROLL],
+                                                  bool (&ok)[IPB_RS_UNROLL], unsigned& region_px) {
+    int yy[IPB_RS_UNROLL], xx[IPB_RS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < IPB_RS_UNROLL; ++u) {
+        const long long wi = w0 + u;
+        m[u] = 0u;
+        yy[u] = 0; xx[u] = 0;
+        if (wi < nwords) {
+            const int r = (int)(wi / c.wpr), j = (int)(wi - (long long)r * c.wpr);
+            unsigned mw = c.mask[wi];
+            const int y = c.y0 + r, xb = c.x0 + 32 * j;
+            if (mw && c.androw0) {
+                const unsigned* ar = c.androw0 + (size_t)y * c.and_wpr;
+                const int k = xb >> 5, s = xb & 31;
+                unsigned lo = ar[k] >> s;
+                if (s && k + 1 < c.and_wpr) lo |= ar[k + 1] << (32 - s);
+                mw &= lo;
             }
+            m[u] = mw;
+            yy[u] = y; xx[u] = xb + lane;
+        }
+    }
+    unsigned raw[IPB_RS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < IPB_RS_UNROLL; ++u) {
+        ok[u] = (m[u] >> lane) & 1u;
+        raw[u] = 0u;
+        if (ok[u]) {
+            const size_t p = (size_t)yy[u] * c.W + xx[u];
+            raw[u] = (c.src == IPB_SRC_U16) ? (unsigned)c.u16[p] : __float_as_uint(c.f32[p]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < IPB_RS_UNROLL; ++u) {
+        region_px += ok[u] ? 1u : 0u;
+        if (c.src == IPB_SRC_U16) key[u] = raw[u];
+        else {
+            const float v = __uint_as_float(raw[u]);
+            if (ok[u] && !isfinite(v)) ok[u] = false;
+            key[u] = ipb_f32_key(v);
+        }
+    }
+}
+
+// f(key) for every measured value: from the shared-memory key store when it holds the whole
+// region, else by re-walking global memory.
+template <typename F>
+__device__ __forceinline__ void ipb_rs_foreach_key(const IpbRsCtx& c, bool in_smem, unsigned long long n,
+                                                   const unsigned* k32, const unsigned short* k16, F f) {
+    if (in_smem) {
+        if (c.src == IPB_SRC_U16) for (unsigned i = threadIdx.x; i < n; i += blockDim.x) f((unsigned)k16[i]);
+        else for (unsigned i = threadIdx.x; i < n; i += blockDim.x) f(k32[i]);
+    } else {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const long long nwords = (long long)c.h * c.wpr;
+        for (long long w0 = (long long)warp * IPB_RS_UNROLL; w0 < nwords; w0 += (long long)nwarps * IPB_RS_UNROLL) {
+            unsigned m[IPB_RS_UNROLL], key[IPB_RS_UNROLL], dummy = 0;
+            bool ok[IPB_RS_UNROLL];
+            ipb_rs_load_group(c, w0, nwords, lane, m, key, ok, dummy);
+#pragma unroll
+            for (int u = 0; u < IPB_RS_UNROLL; ++u) if (ok[u]) f(key[u]);
         }
     }
 }
@@ -131,27 +180,14 @@ __device__ __forceinline__ unsigned long long ipb_block_sum_u64(unsigned long lo
     return t;
 }
 
-// exclusive block scan of one u64 per thread (blockDim.x <= 1024); `sm` holds >= 32 entries
-__device__ __forceinline__ unsigned long long ipb_block_excl_scan_u64(unsigned long long v, unsigned long long* sm) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
-    __syncthreads();
-    if (lane == 31) sm[warp] = incl;
-    __syncthreads();
-    unsigned long long base = 0;
-    for (int i = 0; i < warp; ++i) base += sm[i];
-    return base + incl - v;
-}
-
-__global__ void __launch_bounds__(IPB_RS_THREADS)
+__global__ void __launch_bounds__(IPB_RS_THREADS, 1)
 ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __restrict__ jobs,
                    const unsigned* __restrict__ mask_pool, const unsigned* __restrict__ and_bits,
                    int and_wpr, int H, int W,
                    const unsigned short* __restrict__ planes, const float* __restrict__ images,
-                   const float* __restrict__ bvals, IpbStatOut* __restrict__ out)
+                   const float* __restrict__ bvals, IpbStatOut* __restrict__ out, int smem_bytes)
 {
+    IPB_DYN_SMEM(unsigned, keystore);
     __shared__ unsigned hist[IPB_RS_MAXR][IPB_RS_BINS];
     __shared__ double red_d[32];
     __shared__ unsigned long long red_u[32];
@@ -161,7 +197,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     __shared__ int r_group[IPB_RS_MAXR];
     __shared__ unsigned g_prefix[IPB_RS_MAXR];
     __shared__ int g_n;
-    __shared__ unsigned long long part[IPB_RS_THREADS];
+    __shared__ unsigned n_stored;
 
     const IpbStatJob job = jobs[blockIdx.x];
     const IpbRegion rg = regions[job.region];
@@ -177,18 +213,46 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     c.clip = job.clip_neg;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = (blockDim.x + 31) >> 5;
+    unsigned* k32 = keystore;
+    unsigned short* k16 = reinterpret_cast<unsigned short*>(keystore);
+    const unsigned cap = (unsigned)(smem_bytes / (job.src == IPB_SRC_U16 ? 2 : 4));
+    if (tid == 0) n_stored = 0u;
+    __syncthreads();
 
-    // ---- pass A: n, area, sum, key range
-    unsigned long long n_t = 0, area_t = 0;
+    // ---- gather: n, area, sum, key range; keys compacted into shared memory while they fit
+    unsigned long long n_t = 0;
+    unsigned area_t = 0;
     double s_t = 0.0;
     unsigned kmin_t = 0xffffffffu, kmax_t = 0u;
-    ipb_rs_foreach(c, area_t, [&](unsigned key, float val) {
-        ++n_t; s_t += (double)val;
-        kmin_t = key < kmin_t ? key : kmin_t;
-        kmax_t = key > kmax_t ? key : kmax_t;
-    });
+    {
+        const long long nwords = (long long)c.h * c.wpr;
+        for (long long w0 = (long long)warp * IPB_RS_UNROLL; w0 < nwords; w0 += (long long)nwarps * IPB_RS_UNROLL) {
+            unsigned m[IPB_RS_UNROLL], key[IPB_RS_UNROLL];
+            bool ok[IPB_RS_UNROLL];
+            ipb_rs_load_group(c, w0, nwords, lane, m, key, ok, area_t);
+            unsigned vm[IPB_RS_UNROLL], tot = 0;
+#pragma unroll
+            for (int u = 0; u < IPB_RS_UNROLL; ++u) { vm[u] = __ballot_sync(IPB_FULL, ok[u]); tot += __popc(vm[u]); }
+            if (tot == 0) continue;                                  // warp-uniform
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&n_stored, tot);
+            base = __shfl_sync(IPB_FULL, base, 0);
+#pragma unroll
+            for (int u = 0; u < IPB_RS_UNROLL; ++u) {
+                if (ok[u]) {
+                    const unsigned pos = base + __popc(vm[u] & ((1u << lane) - 1u));
+                    if (pos < cap) { if (job.src == IPB_SRC_U16) k16[pos] = (unsigned short)key[u]; else k32[pos] = key[u]; }
+                    ++n_t;
+                    s_t += (double)ipb_rs_value(c, key[u]);
+                    kmin_t = key[u] < kmin_t ? key[u] : kmin_t;
+                    kmax_t = key[u] > kmax_t ? key[u] : kmax_t;
+                }
+                base += __popc(vm[u]);
+            }
+        }
+    }
     const unsigned long long n = ipb_block_sum_u64(n_t, red_u);
-    const unsigned long long area = ipb_block_sum_u64(area_t, red_u);
+    const unsigned long long area = ipb_block_sum_u64((unsigned long long)area_t, red_u);
     const double sum = ipb_block_sum_d(s_t, red_d);
     kmin_t = ipb_warp_min(kmin_t); kmax_t = ipb_warp_max(kmax_t);
     __syncthreads();
@@ -196,6 +260,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     __syncthreads();
     unsigned kmin = 0xffffffffu, kmax = 0u;
     for (int i = 0; i < nwarps; ++i) { kmin = red_k[0][i] < kmin ? red_k[0][i] : kmin; kmax = red_k[1][i] > kmax ? red_k[1][i] : kmax; }
+    const bool in_smem = n <= (unsigned long long)cap;
 
     IpbStatOut o;
     o.n = n; o.area = area; o.sum = sum; o.ssd = 0.0; o.pad0 = 0.f;
@@ -238,45 +303,45 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     bool first = true;
     do {
         const int shift = shift_prev > IPB_RS_DIGIT ? shift_prev - IPB_RS_DIGIT : 0;
-        const unsigned dmask = (shift_prev - shift) >= 32 ? 0xffffffffu : ((1u << (shift_prev - shift)) - 1u);
+        const unsigned dmask = (1u << (shift_prev - shift)) - 1u;
         const int ng = g_n;
         for (int i = tid; i < ng * IPB_RS_BINS; i += blockDim.x) (&hist[0][0])[i] = 0u;
         __syncthreads();
-        unsigned long long dummy = 0;
-        ipb_rs_foreach(c, dummy, [&](unsigned key, float val) {
+        ipb_rs_foreach_key(c, in_smem, n, k32, k16, [&](unsigned key) {
             const unsigned kp = key - kmin;
-            if (first) { const double d = (double)val - mean; ssd_t += d * d; }
+            if (first) { const double d = (double)ipb_rs_value(c, key) - mean; ssd_t += d * d; }
             const unsigned hi = shift_prev >= 32 ? 0u : (kp >> shift_prev);
             const unsigned dg = (kp >> shift) & dmask;
             for (int g = 0; g < ng; ++g)
                 if (first || hi == g_prefix[g]) atomicAdd(&hist[g][dg], 1u);
         });
         __syncthreads();
-        // locate every rank inside its group's histogram (block-wide scan per group)
-        unsigned long long kk_l[IPB_RS_MAXR];
-        int grp_l[IPB_RS_MAXR];
-        for (int r = 0; r < IPB_RS_MAXR; ++r) { kk_l[r] = r_rank[r]; grp_l[r] = r_group[r]; }
-        __syncthreads();
-        for (int g = 0; g < ng; ++g) {
-            const int per = IPB_RS_BINS / IPB_RS_THREADS;        // 4 bins per thread
-            unsigned long long mine = 0;
-            for (int b = 0; b < per; ++b) mine += hist[g][tid * per + b];
-            const unsigned long long lo = ipb_block_excl_scan_u64(mine, part), hi = lo + mine;
+        // locate every rank inside its group's histogram: warp g scans group g (256 bins)
+        if (warp < ng) {
+            const int g = warp;
+            unsigned cnt[IPB_RS_BINS / 32], mine = 0;
+#pragma unroll
+            for (int b = 0; b < IPB_RS_BINS / 32; ++b) { cnt[b] = hist[g][lane * (IPB_RS_BINS / 32) + b]; mine += cnt[b]; }
+            unsigned long long incl = mine;
+#pragma unroll
+            for (int o2 = 1; o2 < 32; o2 <<= 1) { unsigned long long t = __shfl_up_sync(IPB_FULL, incl, o2); if (lane >= o2) incl += t; }
+            const unsigned long long lo = incl - mine, hi = incl;
             for (int r = 0; r < nr; ++r) {
-                if (grp_l[r] != g) continue;
-                const unsigned long long kk = kk_l[r];
+                if (r_group[r] != g) continue;
+                const unsigned long long kk = r_rank[r];
+                __syncwarp();
                 if (kk >= lo && kk < hi) {
                     unsigned long long acc = lo;
-                    for (int b = 0; b < per; ++b) {
-                        const unsigned cnt = hist[g][tid * per + b];
-                        if (kk < acc + cnt) {
-                            r_prefix[r] = (g_prefix[g] << (shift_prev - shift)) | (unsigned)(tid * per + b);
+#pragma unroll
+                    for (int b = 0; b < IPB_RS_BINS / 32; ++b) {
+                        if (kk >= acc && kk < acc + cnt[b]) {
+                            r_prefix[r] = (g_prefix[g] << (shift_prev - shift)) | (unsigned)(lane * (IPB_RS_BINS / 32) + b);
                             r_rank[r] = kk - acc;
-                            break;
                         }
-                        acc += cnt;
+                        acc += cnt[b];
                     }
                 }
+                __syncwarp();
             }
         }
         __syncthreads();
@@ -299,12 +364,9 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     if (tid == 0) {
         o.ssd = ssd;
         float rv[IPB_RS_MAXR];
-        for (int r = 0; r < IPB_RS_MAXR; ++r) {
-            const unsigned key = kmin + r_prefix[r];
-            rv[r] = (job.src == IPB_SRC_U16) ? ipb_rs_transform(c, key) : ipb_key_f32(key);
-        }
-        o.vmin = (job.src == IPB_SRC_U16) ? ipb_rs_transform(c, kmin) : ipb_key_f32(kmin);
-        o.vmax = (job.src == IPB_SRC_U16) ? ipb_rs_transform(c, kmax) : ipb_key_f32(kmax);
+        for (int r = 0; r < IPB_RS_MAXR; ++r) rv[r] = ipb_rs_value(c, kmin + r_prefix[r]);
+        o.vmin = ipb_rs_value(c, kmin);
+        o.vmax = ipb_rs_value(c, kmax);
         for (int i = 0; i < IPB_RS_MAXQ; ++i) {
             if (job.qkind[i] == IPB_QKIND_PCT) o.q[i] = ipb_np_lerp_f32(rv[2 * i], rv[2 * i + 1], qi[i].gamma);
             else if (job.qkind[i] == IPB_QKIND_MEDIAN)

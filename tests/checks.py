@@ -263,3 +263,48 @@ def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168):
             k += 1
     assert k == len(out["owner"])
     return straddles
+
+
+def check_region_stats_streaming(eng):
+    """Regions larger than the shared-memory key store (re-walk path) + NaN filtering."""
+    from imageprocess_b200 import ops
+    rng = np.random.default_rng(17)
+    H, W = 420, 440
+    img = rng.integers(0, 60000, (1, H, W)).astype(np.uint16)
+    fimg = (rng.normal(1.0, 0.3, (1, H, W))).astype(np.float32)
+    fimg[0, rng.random((H, W)) < 0.01] = np.nan
+    fimg[0, rng.random((H, W)) < 0.005] = np.inf
+    polys = [np.array([[3.0, 2.0], [430.0, 4.0], [436.0, 415.0], [5.0, 410.0]]),
+             np.array([[50.0, 50.0], [200.0, 60.0], [190.0, 300.0], [40.0, 280.0]])]
+    specs = [geo.mpl_spec(P, (W, H)) for P in polys]
+    rm = eng.rasterize(geo.RULE_MPL, specs, (H, W), 1, want_union=False)
+    reg = ops.regions_from_masks(rm)
+    B = np.float32(1234.5)
+    jobs = np.zeros(4, dtype=ops.STAT_JOB)
+    for r in range(2):
+        jobs[2 * r] = (r, ops.SRC_U16, 0, 0, 1, (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
+                       (ops.q32_of(5), 0.0, ops.q32_of(95)), 0)
+        jobs[2 * r + 1] = (r, ops.SRC_F32, 0, -1, 0, (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
+                           (ops.q32_of(2.5), 0.0, ops.q32_of(99)), 0)
+    out = eng.region_stats(reg, jobs, rm.pool, H, W, planes=eng.mem.from_host(img),
+                           images=eng.mem.from_host(fimg), bvals=eng.mem.from_host(np.array([B]))).host()
+    for r, P in enumerate(polys):
+        m = port.rasterize_polygon(P, (H, W))
+        v = img[0].astype(np.float32) - B
+        v[v < 0] = 0
+        vals = v[m]
+        o = out[2 * r]
+        assert int(o["n"]) == vals.size == int(o["area"])
+        assert o["q"][0] == np.percentile(vals, 5) and o["q"][1] == np.median(vals) and o["q"][2] == np.percentile(vals, 95)
+        assert o["vmin"] == vals.min() and o["vmax"] == vals.max()
+        assert close(float(o["sum"]), float(vals.astype(np.float64).sum()), 1e-9)
+        fv = fimg[0][m]
+        fv = fv[np.isfinite(fv)]
+        o = out[2 * r + 1]
+        assert int(o["n"]) == fv.size and int(o["area"]) == int(m.sum())
+        assert o["q"][0] == np.percentile(fv, 2.5) and o["q"][1] == np.median(fv) and o["q"][2] == np.percentile(fv, 99)
+        assert o["vmin"] == fv.min() and o["vmax"] == fv.max()
+        assert close(math.sqrt(float(o["ssd"]) / fv.size), float(fv.astype(np.float64).std()), 1e-9)
+
+
+RASTER_CHECKS.append(check_region_stats_streaming)
