@@ -18,10 +18,12 @@
 //            compacted as keys into shared memory (ballot/popc positions), while n, sum and
 //            the key range are accumulated.  Regions that do not fit in shared memory keep
 //            the same code path but re-walk global memory in every pass.
-//   select   radix select with 8-bit digits over (key - kmin): only as many passes as the
-//            region's own key range needs, all requested ranks (p5 / median / p95 -> up to 6)
-//            resolved together with one 256-bin histogram per distinct prefix.  The first
-//            pass also accumulates the squared deviations from the float64 mean.
+//   select   pass 1 is ONE wide histogram over the top bits of (key - kmin) using all shared
+//            memory the key store left free (up to 32768 bins): for uint16 data this resolves
+//            every rank at once.  If low bits remain (float keys), the handful of keys that
+//            share a wanted prefix are compacted into a small list and ranked by counting;
+//            pathological tie-heavy regions fall back to 8-bit digit passes with one
+//            histogram per distinct prefix.
 // numpy's float32 percentile / median arithmetic is replayed from ipb_exact.cuh.
 #pragma once
 #include "ipb_rt.cuh"
@@ -87,42 +89,36 @@ __device__ __forceinline__ float ipb_rs_value(const IpbRsCtx& c, unsigned key) {
     return c.src == IPB_SRC_U16 ? ipb_rs_transform(c, key) : ipb_key_f32(key);
 }
 
-// One warp-iteration of the region walk: IPB_RS_UNROLL consecutive mask words starting at
-// word w0; lane b owns bit b.  Fills m[u] (warp-uniform word after the AND mask), and for
-// this lane key[u] and ok[u] (pixel belongs to the region and is measured).
-__device__ __forceinline__ void ipb_rs_load_group(const IpbRsCtx& c, long long w0, long long nwords, int lane,
-                                                  unsigned (&m)[IPB_RS_UNROLL], unsigned (&key)[IPB_RS_UNROLL],
-                                                  bool (&ok)[IPB_RS_UNROLL], unsigned& region_px) {
-    int yy[IPB_RS_UNROLL], xx[IPB_RS_UNROLL];
+// One warp-iteration of the region walk: up to IPB_RS_UNROLL consecutive mask words of row
+// r starting at word j0; lane b owns bit b.  Fills for this lane key[u] and ok[u] (pixel
+// belongs to the region and is measured) and counts region pixels.
+__device__ __forceinline__ void ipb_rs_load_group(const IpbRsCtx& c, int r, int j0, int lane,
+                                                  unsigned (&key)[IPB_RS_UNROLL], bool (&ok)[IPB_RS_UNROLL],
+                                                  unsigned& region_px) {
+    const unsigned* mrow = c.mask + (size_t)r * c.wpr;
+    const int y = c.y0 + r;
+    unsigned m[IPB_RS_UNROLL];
 #pragma unroll
-    for (int u = 0; u < IPB_RS_UNROLL; ++u) {
-        const long long wi = w0 + u;
-        m[u] = 0u;
-        yy[u] = 0; xx[u] = 0;
-        if (wi < nwords) {
-            const int r = (int)(wi / c.wpr), j = (int)(wi - (long long)r * c.wpr);
-            unsigned mw = c.mask[wi];
-            const int y = c.y0 + r, xb = c.x0 + 32 * j;
-            if (mw && c.androw0) {
-                const unsigned* ar = c.androw0 + (size_t)y * c.and_wpr;
-                const int k = xb >> 5, s = xb & 31;
+    for (int u = 0; u < IPB_RS_UNROLL; ++u) m[u] = (j0 + u < c.wpr) ? mrow[j0 + u] : 0u;
+    if (c.androw0) {
+        const unsigned* ar = c.androw0 + (size_t)y * c.and_wpr;
+#pragma unroll
+        for (int u = 0; u < IPB_RS_UNROLL; ++u) {
+            if (m[u]) {
+                const int xb = c.x0 + 32 * (j0 + u), k = xb >> 5, s = xb & 31;
                 unsigned lo = ar[k] >> s;
                 if (s && k + 1 < c.and_wpr) lo |= ar[k + 1] << (32 - s);
-                mw &= lo;
+                m[u] &= lo;
             }
-            m[u] = mw;
-            yy[u] = y; xx[u] = xb + lane;
         }
     }
+    const size_t p0 = (size_t)y * c.W + (c.x0 + 32 * j0 + lane);
     unsigned raw[IPB_RS_UNROLL];
 #pragma unroll
     for (int u = 0; u < IPB_RS_UNROLL; ++u) {
         ok[u] = (m[u] >> lane) & 1u;
         raw[u] = 0u;
-        if (ok[u]) {
-            const size_t p = (size_t)yy[u] * c.W + xx[u];
-            raw[u] = (c.src == IPB_SRC_U16) ? (unsigned)c.u16[p] : __float_as_uint(c.f32[p]);
-        }
+        if (ok[u]) raw[u] = (c.src == IPB_SRC_U16) ? (unsigned)c.u16[p0 + 32 * u] : __float_as_uint(c.f32[p0 + 32 * u]);
     }
 #pragma unroll
     for (int u = 0; u < IPB_RS_UNROLL; ++u) {
@@ -139,21 +135,21 @@ __device__ __forceinline__ void ipb_rs_load_group(const IpbRsCtx& c, long long w
 // f(key) for every measured value: from the shared-memory key store when it holds the whole
 // region, else by re-walking global memory.
 template <typename F>
-__device__ __forceinline__ void ipb_rs_foreach_key(const IpbRsCtx& c, bool in_smem, unsigned long long n,
+__device__ __forceinline__ void ipb_rs_foreach_key(const IpbRsCtx& c, bool in_smem, unsigned n,
                                                    const unsigned* k32, const unsigned short* k16, F f) {
     if (in_smem) {
         if (c.src == IPB_SRC_U16) for (unsigned i = threadIdx.x; i < n; i += blockDim.x) f((unsigned)k16[i]);
         else for (unsigned i = threadIdx.x; i < n; i += blockDim.x) f(k32[i]);
     } else {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        const long long nwords = (long long)c.h * c.wpr;
-        for (long long w0 = (long long)warp * IPB_RS_UNROLL; w0 < nwords; w0 += (long long)nwarps * IPB_RS_UNROLL) {
-            unsigned m[IPB_RS_UNROLL], key[IPB_RS_UNROLL], dummy = 0;
-            bool ok[IPB_RS_UNROLL];
-            ipb_rs_load_group(c, w0, nwords, lane, m, key, ok, dummy);
+        for (int r = warp; r < c.h; r += nwarps)
+            for (int j0 = 0; j0 < c.wpr; j0 += IPB_RS_UNROLL) {
+                unsigned key[IPB_RS_UNROLL], dummy = 0;
+                bool ok[IPB_RS_UNROLL];
+                ipb_rs_load_group(c, r, j0, lane, key, ok, dummy);
 #pragma unroll
-            for (int u = 0; u < IPB_RS_UNROLL; ++u) if (ok[u]) f(key[u]);
-        }
+                for (int u = 0; u < IPB_RS_UNROLL; ++u) if (ok[u]) f(key[u]);
+            }
     }
 }
 
@@ -179,6 +175,22 @@ __device__ __forceinline__ unsigned long long ipb_block_sum_u64(unsigned long lo
     for (int i = 0; i < nw; ++i) t += red[i];
     return t;
 }
+// exclusive block scan (blockDim.x <= 1024); `sm` holds >= 32 entries
+__device__ __forceinline__ unsigned long long ipb_block_excl_scan_u64(unsigned long long v, unsigned long long* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();
+    if (lane == 31) sm[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int i = 0; i < warp; ++i) base += sm[i];
+    return base + incl - v;
+}
+
+#define IPB_RS_LISTCAP 2048
+#define IPB_RS_RESERVE (16 * 1024)     // bytes of the dynamic store always left to the histogram
 
 __global__ void __launch_bounds__(IPB_RS_THREADS, 1)
 ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __restrict__ jobs,
@@ -188,7 +200,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
                    const float* __restrict__ bvals, IpbStatOut* __restrict__ out, int smem_bytes)
 {
     IPB_DYN_SMEM(unsigned, keystore);
-    __shared__ unsigned hist[IPB_RS_MAXR][IPB_RS_BINS];
+    __shared__ unsigned ghist[IPB_RS_MAXR][IPB_RS_BINS];   // generic (fallback) per-group histograms
     __shared__ double red_d[32];
     __shared__ unsigned long long red_u[32];
     __shared__ unsigned red_k[2][32];
@@ -197,7 +209,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     __shared__ int r_group[IPB_RS_MAXR];
     __shared__ unsigned g_prefix[IPB_RS_MAXR];
     __shared__ int g_n;
-    __shared__ unsigned n_stored;
+    __shared__ unsigned n_stored, list_n;
 
     const IpbStatJob job = jobs[blockIdx.x];
     const IpbRegion rg = regions[job.region];
@@ -215,21 +227,20 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     const int nwarps = (blockDim.x + 31) >> 5;
     unsigned* k32 = keystore;
     unsigned short* k16 = reinterpret_cast<unsigned short*>(keystore);
-    const unsigned cap = (unsigned)(smem_bytes / (job.src == IPB_SRC_U16 ? 2 : 4));
-    if (tid == 0) n_stored = 0u;
+    const int keysize = job.src == IPB_SRC_U16 ? 2 : 4;
+    const unsigned cap = (unsigned)((smem_bytes - IPB_RS_RESERVE) / keysize);
+    if (tid == 0) { n_stored = 0u; list_n = 0u; }
     __syncthreads();
 
-    // ---- gather: n, area, sum, key range; keys compacted into shared memory while they fit
-    unsigned long long n_t = 0;
-    unsigned area_t = 0;
-    double s_t = 0.0;
+    // ---- gather: n, area, sum, sum of squares, key range; keys compacted into shared memory
+    unsigned n_t = 0, area_t = 0;
+    double s_t = 0.0, s2_t = 0.0;
     unsigned kmin_t = 0xffffffffu, kmax_t = 0u;
-    {
-        const long long nwords = (long long)c.h * c.wpr;
-        for (long long w0 = (long long)warp * IPB_RS_UNROLL; w0 < nwords; w0 += (long long)nwarps * IPB_RS_UNROLL) {
-            unsigned m[IPB_RS_UNROLL], key[IPB_RS_UNROLL];
+    for (int r = warp; r < c.h; r += nwarps) {
+        for (int j0 = 0; j0 < c.wpr; j0 += IPB_RS_UNROLL) {
+            unsigned key[IPB_RS_UNROLL];
             bool ok[IPB_RS_UNROLL];
-            ipb_rs_load_group(c, w0, nwords, lane, m, key, ok, area_t);
+            ipb_rs_load_group(c, r, j0, lane, key, ok, area_t);
             unsigned vm[IPB_RS_UNROLL], tot = 0;
 #pragma unroll
             for (int u = 0; u < IPB_RS_UNROLL; ++u) { vm[u] = __ballot_sync(IPB_FULL, ok[u]); tot += __popc(vm[u]); }
@@ -243,7 +254,8 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
                     const unsigned pos = base + __popc(vm[u] & ((1u << lane) - 1u));
                     if (pos < cap) { if (job.src == IPB_SRC_U16) k16[pos] = (unsigned short)key[u]; else k32[pos] = key[u]; }
                     ++n_t;
-                    s_t += (double)ipb_rs_value(c, key[u]);
+                    const double v = (double)ipb_rs_value(c, key[u]);
+                    s_t += v; s2_t += v * v;
                     kmin_t = key[u] < kmin_t ? key[u] : kmin_t;
                     kmax_t = key[u] > kmax_t ? key[u] : kmax_t;
                 }
@@ -251,9 +263,10 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
             }
         }
     }
-    const unsigned long long n = ipb_block_sum_u64(n_t, red_u);
+    const unsigned long long n = ipb_block_sum_u64((unsigned long long)n_t, red_u);
     const unsigned long long area = ipb_block_sum_u64((unsigned long long)area_t, red_u);
     const double sum = ipb_block_sum_d(s_t, red_d);
+    const double sumsq = ipb_block_sum_d(s2_t, red_d);
     kmin_t = ipb_warp_min(kmin_t); kmax_t = ipb_warp_max(kmax_t);
     __syncthreads();
     if (lane == 0) { red_k[0][warp] = kmin_t; red_k[1][warp] = kmax_t; }
@@ -271,7 +284,10 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         if (tid == 0) out[blockIdx.x] = o;
         return;
     }
-    const double mean = sum / (double)n;
+    {
+        double ssd = sumsq - sum * (sum / (double)n);
+        o.ssd = ssd > 0.0 ? ssd : 0.0;
+    }
 
     // ---- ranks wanted
     IpbQIdx qi[IPB_RS_MAXQ];
@@ -295,57 +311,47 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     }
     __syncthreads();
 
-    // ---- radix select over key' = key - kmin
+    // ---- pass 1: one wide histogram (as many bins as the free part of the store allows)
+    const unsigned nn = (unsigned)(in_smem ? n : 0);
     const unsigned range = kmax - kmin;
     const int bits = range ? (32 - __clz((int)range)) : 0;
-    int shift_prev = bits;                   // bits below this are unresolved
-    double ssd_t = 0.0;
-    bool first = true;
-    do {
-        const int shift = shift_prev > IPB_RS_DIGIT ? shift_prev - IPB_RS_DIGIT : 0;
-        const unsigned dmask = (1u << (shift_prev - shift)) - 1u;
-        const int ng = g_n;
-        for (int i = tid; i < ng * IPB_RS_BINS; i += blockDim.x) (&hist[0][0])[i] = 0u;
-        __syncthreads();
-        ipb_rs_foreach_key(c, in_smem, n, k32, k16, [&](unsigned key) {
-            const unsigned kp = key - kmin;
-            if (first) { const double d = (double)ipb_rs_value(c, key) - mean; ssd_t += d * d; }
-            const unsigned hi = shift_prev >= 32 ? 0u : (kp >> shift_prev);
-            const unsigned dg = (kp >> shift) & dmask;
-            for (int g = 0; g < ng; ++g)
-                if (first || hi == g_prefix[g]) atomicAdd(&hist[g][dg], 1u);
-        });
-        __syncthreads();
-        // locate every rank inside its group's histogram: warp g scans group g (256 bins)
-        if (warp < ng) {
-            const int g = warp;
-            unsigned cnt[IPB_RS_BINS / 32], mine = 0;
-#pragma unroll
-            for (int b = 0; b < IPB_RS_BINS / 32; ++b) { cnt[b] = hist[g][lane * (IPB_RS_BINS / 32) + b]; mine += cnt[b]; }
-            unsigned long long incl = mine;
-#pragma unroll
-            for (int o2 = 1; o2 < 32; o2 <<= 1) { unsigned long long t = __shfl_up_sync(IPB_FULL, incl, o2); if (lane >= o2) incl += t; }
-            const unsigned long long lo = incl - mine, hi = incl;
-            for (int r = 0; r < nr; ++r) {
-                if (r_group[r] != g) continue;
-                const unsigned long long kk = r_rank[r];
-                __syncwarp();
-                if (kk >= lo && kk < hi) {
-                    unsigned long long acc = lo;
-#pragma unroll
-                    for (int b = 0; b < IPB_RS_BINS / 32; ++b) {
-                        if (kk >= acc && kk < acc + cnt[b]) {
-                            r_prefix[r] = (g_prefix[g] << (shift_prev - shift)) | (unsigned)(lane * (IPB_RS_BINS / 32) + b);
-                            r_rank[r] = kk - acc;
-                        }
-                        acc += cnt[b];
-                    }
+    const unsigned key_words = in_smem ? (unsigned)(((size_t)n * keysize + 3) / 4) : 0u;
+    unsigned* whist = keystore + key_words;
+    const unsigned hb_cap = (unsigned)(smem_bytes / 4) - key_words;        // >= RESERVE/4 = 4096
+    int d1 = 31 - __clz((int)hb_cap);
+    if (d1 > 15) d1 = 15;
+    if (d1 > bits) d1 = bits;
+    const int rb = bits - d1;                                               // bits left after pass 1
+    const unsigned nb = 1u << d1;
+    for (unsigned i = tid; i < nb; i += blockDim.x) whist[i] = 0u;
+    __syncthreads();
+    ipb_rs_foreach_key(c, in_smem, nn, k32, k16, [&](unsigned key) { atomicAdd(&whist[(key - kmin) >> rb], 1u); });
+    __syncthreads();
+    {
+        unsigned long long kk_l[IPB_RS_MAXR];
+        for (int r = 0; r < IPB_RS_MAXR; ++r) kk_l[r] = r_rank[r];
+        const unsigned per = (nb + blockDim.x - 1) / blockDim.x;
+        const unsigned b0 = tid * per;
+        unsigned long long mine = 0;
+        for (unsigned b = b0; b < b0 + per && b < nb; ++b) mine += whist[b];
+        const unsigned long long lo = ipb_block_excl_scan_u64(mine, red_u), hi = lo + mine;
+        for (int r = 0; r < nr; ++r) {
+            const unsigned long long kk = kk_l[r];
+            if (kk >= lo && kk < hi) {
+                unsigned long long acc = lo;
+                for (unsigned b = b0; b < b0 + per && b < nb; ++b) {
+                    const unsigned cnt = whist[b];
+                    if (kk < acc + cnt) { r_prefix[r] = b; r_rank[r] = kk - acc; break; }
+                    acc += cnt;
                 }
-                __syncwarp();
             }
         }
         __syncthreads();
-        if (tid == 0) {                                            // regroup by distinct prefix
+    }
+
+    if (rb > 0) {
+        // ---- regroup, then compact the few keys that share a wanted prefix
+        if (tid == 0) {
             int m = 0;
             for (int r = 0; r < nr; ++r) {
                 int gg = -1;
@@ -356,13 +362,106 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
             g_n = m > 0 ? m : 1;
         }
         __syncthreads();
-        shift_prev = shift;
-        first = false;
-    } while (shift_prev > 0);
+        const int ng = g_n;
+        unsigned gp[IPB_RS_MAXR];
+        for (int g = 0; g < IPB_RS_MAXR; ++g) gp[g] = g < ng ? g_prefix[g] : 0xffffffffu;
+        unsigned* list = whist;                                  // the wide histogram is no longer needed
+        const unsigned lowmask = (rb >= 32) ? 0xffffffffu : ((1u << rb) - 1u);
+        const bool packable = rb <= 28;
+        __syncthreads();
+        if (packable) {
+            ipb_rs_foreach_key(c, in_smem, nn, k32, k16, [&](unsigned key) {
+                const unsigned kp = key - kmin, hi = kp >> rb;
+#pragma unroll
+                for (int g = 0; g < IPB_RS_MAXR; ++g) {
+                    if (hi == gp[g]) {
+                        const unsigned idx = atomicAdd(&list_n, 1u);
+                        if (idx < IPB_RS_LISTCAP) list[idx] = ((unsigned)g << 28) | (kp & lowmask);
+                    }
+                }
+            });
+        }
+        __syncthreads();
+        const unsigned m = list_n;
+        if (packable && m <= IPB_RS_LISTCAP) {
+            // exact rank by counting inside the tiny candidate list
+            for (int r = 0; r < nr; ++r) {
+                const unsigned g = (unsigned)r_group[r];
+                const unsigned long long want = r_rank[r];
+                for (unsigned e = tid; e < m; e += blockDim.x) {
+                    const unsigned ve = list[e];
+                    if ((ve >> 28) != g) continue;
+                    unsigned long long less = 0;
+                    for (unsigned f = 0; f < m; ++f) {
+                        const unsigned vf = list[f];
+                        less += ((vf >> 28) == g && (vf < ve || (vf == ve && f < e))) ? 1u : 0u;
+                    }
+                    if (less == want) r_prefix[r] = (gp[g] << rb) | (ve & lowmask);     // full key'
+                }
+            }
+            __syncthreads();
+        } else {
+            // ---- generic fallback: 8-bit digit passes with one histogram per distinct prefix
+            int shift_prev = rb;
+            do {
+                const int shift = shift_prev > IPB_RS_DIGIT ? shift_prev - IPB_RS_DIGIT : 0;
+                const unsigned dmask = (1u << (shift_prev - shift)) - 1u;
+                const int ngc = g_n;
+                for (int i = tid; i < ngc * IPB_RS_BINS; i += blockDim.x) (&ghist[0][0])[i] = 0u;
+                __syncthreads();
+                ipb_rs_foreach_key(c, in_smem, nn, k32, k16, [&](unsigned key) {
+                    const unsigned kp = key - kmin;
+                    const unsigned hi = shift_prev >= 32 ? 0u : (kp >> shift_prev);
+                    const unsigned dg = (kp >> shift) & dmask;
+                    for (int g = 0; g < ngc; ++g)
+                        if (hi == g_prefix[g]) atomicAdd(&ghist[g][dg], 1u);
+                });
+                __syncthreads();
+                if (warp < ngc) {
+                    const int g = warp;
+                    unsigned cnt[IPB_RS_BINS / 32], mine = 0;
+#pragma unroll
+                    for (int b = 0; b < IPB_RS_BINS / 32; ++b) { cnt[b] = ghist[g][lane * (IPB_RS_BINS / 32) + b]; mine += cnt[b]; }
+                    unsigned long long incl = mine;
+#pragma unroll
+                    for (int o2 = 1; o2 < 32; o2 <<= 1) { unsigned long long t = __shfl_up_sync(IPB_FULL, incl, o2); if (lane >= o2) incl += t; }
+                    const unsigned long long lo = incl - mine, hi = incl;
+                    for (int r = 0; r < nr; ++r) {
+                        if (r_group[r] != g) continue;
+                        const unsigned long long kk = r_rank[r];
+                        __syncwarp();
+                        if (kk >= lo && kk < hi) {
+                            unsigned long long acc = lo;
+#pragma unroll
+                            for (int b = 0; b < IPB_RS_BINS / 32; ++b) {
+                                if (kk >= acc && kk < acc + cnt[b]) {
+                                    r_prefix[r] = (g_prefix[g] << (shift_prev - shift)) | (unsigned)(lane * (IPB_RS_BINS / 32) + b);
+                                    r_rank[r] = kk - acc;
+                                }
+                                acc += cnt[b];
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int mm = 0;
+                    for (int r = 0; r < nr; ++r) {
+                        int gg = -1;
+                        for (int t = 0; t < mm; ++t) if (g_prefix[t] == r_prefix[r]) { gg = t; break; }
+                        if (gg < 0) { g_prefix[mm] = r_prefix[r]; gg = mm++; }
+                        r_group[r] = gg;
+                    }
+                    g_n = mm > 0 ? mm : 1;
+                }
+                __syncthreads();
+                shift_prev = shift;
+            } while (shift_prev > 0);
+        }
+    }
 
-    const double ssd = ipb_block_sum_d(ssd_t, red_d);
     if (tid == 0) {
-        o.ssd = ssd;
         float rv[IPB_RS_MAXR];
         for (int r = 0; r < IPB_RS_MAXR; ++r) rv[r] = ipb_rs_value(c, kmin + r_prefix[r]);
         o.vmin = ipb_rs_value(c, kmin);

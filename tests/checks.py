@@ -308,3 +308,30 @@ def check_region_stats_streaming(eng):
 
 
 RASTER_CHECKS.append(check_region_stats_streaming)
+
+
+def check_region_stats_ties(eng):
+    """Tie-heavy float data with a wide key range: candidate list overflows -> digit passes."""
+    from imageprocess_b200 import ops
+    rng = np.random.default_rng(23)
+    H, W = 96, 128
+    fimg = np.full((1, H, W), 1.0, dtype=np.float32)
+    r = rng.random((H, W))
+    fimg[0, r < 0.3] = np.float32(1.0000001)
+    fimg[0, r < 0.05] = 1e6
+    fimg[0, r < 0.02] = -3.5
+    fimg[0, r < 0.01] = 1e-6
+    P = np.array([[2.0, 2.0], [125.0, 3.0], [124.0, 93.0], [3.0, 92.0]])
+    rm = eng.rasterize(geo.RULE_MPL, [geo.mpl_spec(P, (W, H))], (H, W), 1, want_union=False)
+    reg = ops.regions_from_masks(rm)
+    jobs = np.zeros(1, dtype=ops.STAT_JOB)
+    jobs[0] = (0, ops.SRC_F32, 0, -1, 0, (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
+               (ops.q32_of(4), 0.0, ops.q32_of(80)), 0)
+    o = eng.region_stats(reg, jobs, rm.pool, H, W, images=eng.mem.from_host(fimg)).host()[0]
+    fv = fimg[0][port.rasterize_polygon(P, (H, W))]
+    assert int(o["n"]) == fv.size
+    assert o["q"][0] == np.percentile(fv, 4) and o["q"][1] == np.median(fv) and o["q"][2] == np.percentile(fv, 80)
+    assert o["vmin"] == fv.min() and o["vmax"] == fv.max()
+
+
+RASTER_CHECKS.append(check_region_stats_ties)
