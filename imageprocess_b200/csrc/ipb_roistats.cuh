@@ -37,7 +37,7 @@
 #define IPB_RS_DIGIT 8
 #define IPB_RS_BINS (1 << IPB_RS_DIGIT)
 #define IPB_RS_UNROLL 4
-#define IPB_RS_SMEM_BYTES (200 * 1024)      // dynamic shared memory for the key store
+#define IPB_RS_SMEM_BYTES (212 * 1024)      // dynamic shared memory for the key store
 
 #define IPB_QKIND_NONE 0
 #define IPB_QKIND_PCT 1      // np.percentile(vals, p): q32 = f32(p)/f32(100)
@@ -189,7 +189,7 @@ __device__ __forceinline__ unsigned long long ipb_block_excl_scan_u64(unsigned l
     return base + incl - v;
 }
 
-#define IPB_RS_LISTCAP 2048
+#define IPB_RS_LISTCAP 4096
 #define IPB_RS_RESERVE (16 * 1024)     // bytes of the dynamic store always left to the histogram
 
 __global__ void __launch_bounds__(IPB_RS_THREADS, 1)
@@ -384,20 +384,33 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         __syncthreads();
         const unsigned m = list_n;
         if (packable && m <= IPB_RS_LISTCAP) {
-            // exact rank by counting inside the tiny candidate list
-            for (int r = 0; r < nr; ++r) {
-                const unsigned g = (unsigned)r_group[r];
-                const unsigned long long want = r_rank[r];
-                for (unsigned e = tid; e < m; e += blockDim.x) {
-                    const unsigned ve = list[e];
-                    if ((ve >> 28) != g) continue;
-                    unsigned long long less = 0;
-                    for (unsigned f = 0; f < m; ++f) {
-                        const unsigned vf = list[f];
-                        less += ((vf >> 28) == g && (vf < ve || (vf == ve && f < e))) ? 1u : 0u;
+            // sort the candidate list (group in the top 4 bits, low key bits below): bitonic
+            // sort in shared memory, then rank r is a direct index into its group's segment
+            unsigned P = 1;
+            while (P < m) P <<= 1;
+            for (unsigned i = m + tid; i < P; i += blockDim.x) list[i] = 0xffffffffu;
+            __syncthreads();
+            for (unsigned k = 2; k <= P; k <<= 1) {
+                for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                    for (unsigned i = tid; i < P; i += blockDim.x) {
+                        const unsigned ixj = i ^ j;
+                        if (ixj > i) {
+                            const unsigned a = list[i], b = list[ixj];
+                            const bool up = (i & k) == 0;
+                            if ((a > b) == up) { list[i] = b; list[ixj] = a; }
+                        }
                     }
-                    if (less == want) r_prefix[r] = (gp[g] << rb) | (ve & lowmask);     // full key'
+                    __syncthreads();
                 }
+            }
+            if (tid < nr) {
+                const int r = tid;
+                const unsigned g = (unsigned)r_group[r];
+                // first index of group g: binary search for (g << 28)
+                unsigned lo = 0, hi = m;
+                while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (list[mid] < (g << 28)) lo = mid + 1; else hi = mid; }
+                const unsigned ve = list[lo + (unsigned)r_rank[r]];
+                r_prefix[r] = (gp[g] << rb) | (ve & lowmask);                    // full key'
             }
             __syncthreads();
         } else {
