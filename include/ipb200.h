@@ -35,7 +35,7 @@ extern "C" {
 const char* ipb_last_error(void);
 int ipb_version(void);
 int ipb_is_emulated(void);      /* 1 only in the CPU test build of the same sources */
-int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg */
+int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg 7 Crop 8 Comp */
 
 /* ------------------------------------------------------------------ ROI rasterisation
  * Replaces rasterize_polygon (INT/Fluor_INT.py:398-403; copies FRET/fret_ratio_builder.py:292,
@@ -158,6 +158,39 @@ typedef struct {
 int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
                      const uint32_t* and_bits, int and_wpr, int H, int W, const uint16_t* planes,
                      const float* images, const float* bvals, void* out, void* stream);
+
+/* ------------------------------------------------------------------ focal-adhesion chain
+ * Replaces analyze_fa_crop (INT/FA_Analyzer.py:123-195) for a ragged batch of crops in one
+ * call: bw = (crop > thr) & mask (146-147); remove_small_objects, 4-connectivity, float
+ * min_size (151); binary_closing with disk(close_radius) (155-156); label, 8-connectivity,
+ * raster-order numbering (158); regionprops area / intensity sum / centroid sums (159-186).
+ * Crop-border semantics and per-crop label numbering are the reference's.
+ *   crops        ipb_crop[n_crops] [dev]; bit rows of a crop live at bit_off in every bit pool
+ *   fa_params    float32 [F][4] = {mean, std, bg, thr} from ipb_fa_params
+ *   roi_mask     the IPB_RULE_SK mask pool (same layout as the crops' bit rows)
+ *   min_size     <= 0: no small-object removal;  close_radius 0..5 (0: no closing)
+ *   bw_a, bw_b, rootbits, bw_final  uint32 pools of the mask pool's size (scratch / result)
+ *   L, csize     int32 / uint32 [total_px] scratch;  row_roots, row_base int32 [total_rows]
+ *   crop_count   int32 [n_crops];  comp_off int32 [n_crops + 1] (exclusive scan, result)
+ *   comps        ipb_comp[comp_cap] result table: components of crop c are rows
+ *                comp_off[c] .. comp_off[c+1], label k <-> row comp_off[c] + k - 1
+ *   labels       optional int32 [total_px] label maps (crop-local, 0 background)           */
+typedef struct {
+    int64_t bit_off, pix_off, row_off;
+    int32_t ox, oy, w, h, wpr, plane, frame, pad0;
+} ipb_crop;
+typedef struct {
+    uint64_t sum_i, sum_y, sum_x;
+    uint32_t area;
+    int32_t crop;
+} ipb_comp;
+int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_rows,
+                   const uint16_t* planes, int H, int W, const float* fa_params,
+                   const uint32_t* roi_mask, double min_size, int close_radius,
+                   uint32_t* bw_a, uint32_t* bw_b, int32_t* L, uint32_t* csize, uint32_t* rootbits,
+                   int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
+                   uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
+                   int32_t* labels, void* stream);
 
 #ifdef __cplusplus
 }
