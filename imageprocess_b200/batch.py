@@ -17,6 +17,7 @@ Stages (any subset):
 Results are numpy structured tables; ``rows_*`` helpers turn them into the reference's row
 dicts for the unchanged pandas writers.
 """
+import hashlib
 import math
 
 import numpy as np
@@ -54,6 +55,20 @@ class _Arena:
         return base_ptr + self.sections[name][0]
 
 
+class _Plan:
+    """Host tables + sizes of one batch layout (see FrameBatchJob._plan_for)."""
+    pass
+
+
+def _digest(polys):
+    h = hashlib.blake2b(digest_size=16)
+    for P in polys:
+        a = np.ascontiguousarray(np.asarray(P, dtype=np.float64))
+        h.update(str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.digest()
+
+
 class BatchResult:
     """Host tables of one run() (numpy) + handles of the device-resident images."""
     pass
@@ -73,6 +88,7 @@ class FrameBatchJob:
         self.int_ch = list(int_channels) if int_channels is not None else list(range(self.C))
         self.want_roi_image, self.want_labels = want_roi_image, want_labels
         self._bufs = {}
+        self._plans = {}
         self._pin = None
         self.n_roi_px = 0
         self.union_wpr = (self.W + 31) // 32
@@ -98,57 +114,103 @@ class FrameBatchJob:
             self._bufs[name] = p
         return p
 
-    # ------------------------------------------------------------------ the step
-    def run(self, planes, polys_per_frame):
-        eng, mem, F, C, H, W = self.eng, self.mem, self.F, self.C, self.H, self.W
-        st = self.stages
-        need_mpl = ("fret" in st) or ("int" in st)
-        verts, off, frame, roi = geo.flatten_polys(polys_per_frame)
-        NR = off.shape[0] - 1
-        cnt = np.diff(off)
-        res = BatchResult()
-        res.frame, res.roi, res.n_rois = frame, roi, NR
-        stream = mem.stream
+    # ------------------------------------------------------------------ plan (host tables)
+    def _plan_for(self, polys_per_frame):
+        """Host-side tables for one batch.  Frames that carry the same ROI set (a time-lapse
+        stage read with one ROI JSON, reference Fluor_INT.py:333-346) share one rasterised
+        mask per ROI: the unique sets are found by object identity first, by content digest
+        otherwise.  Plans are cached by content, so a steady time-lapse pays for the numpy
+        table building once; every step still uploads the tables and runs every kernel."""
+        F = self.F
+        if len(polys_per_frame) != F:
+            raise ValueError(f"polys_per_frame has {len(polys_per_frame)} entries for {F} frames")
+        set_of_frame = np.zeros(F, dtype=np.int32)
+        usets, digests, by_id, by_dg = [], [], {}, {}
+        for f, pl in enumerate(polys_per_frame):
+            pl = pl if pl is not None else ()
+            s = by_id.get(id(pl))
+            if s is None:
+                dg = _digest(pl)
+                s = by_dg.get(dg)
+                if s is None:
+                    s = len(usets)
+                    usets.append(pl)
+                    digests.append(dg)
+                    by_dg[dg] = s
+                by_id[id(pl)] = s
+            set_of_frame[f] = s
+        key = (set_of_frame.tobytes(), tuple(digests))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._build_plan(set_of_frame, usets)
+            if len(self._plans) >= 4:
+                self._plans.pop(next(iter(self._plans)))
+            self._plans[key] = plan
+        return plan
 
-        # ---- geometry (host, vectorised)
-        T = _Arena()                       # uploaded tables
+    def _build_plan(self, set_of_frame, usets):
+        F, C, H, W = self.F, self.C, self.H, self.W
+        st = self.stages
+        pl = _Plan()
+        need_mpl = pl.need_mpl = ("fret" in st) or ("int" in st)
+        S = pl.S = max(len(usets), 1)
+        verts, off, uset, uroi = geo.flatten_polys(usets)
+        NU = pl.NU = off.shape[0] - 1
+        ucnt = np.bincount(uset, minlength=S).astype(np.int64)
+        ustart = np.concatenate([[0], np.cumsum(ucnt)])[:-1]
+        cnt_f = ucnt[set_of_frame]
+        NR = pl.NR = int(cnt_f.sum())
+        frame = np.repeat(np.arange(F, dtype=np.int32), cnt_f)
+        inst_off = np.concatenate([[0], np.cumsum(cnt_f)])
+        uidx = (ustart[set_of_frame[frame]] + (np.arange(NR) - inst_off[frame])).astype(np.int64)
+        pl.frame, pl.roi, pl.uidx = frame, uroi[uidx].astype(np.int32), uidx
+        pl.set_of_frame = set_of_frame
+
+        T = pl.T = _Arena()                       # uploaded tables
         if need_mpl:
             m_rect = geo.mpl_tables(verts, off, W, H)
             m_wpr, m_rows, m_moff = geo._mask_layout(m_rect)
+            pl.m_words = max(int(m_moff[-1]), 1)
+            pl.m_max_rows = int(m_rows.max()) if NU else 0
+            pl.m_max_wpr = int(m_wpr.max()) if NU else 0
         if "fa" in st:
             fa = geo.fa_tables(verts, off, W, H)
             f_wpr, f_rows, f_moff = geo._mask_layout(fa["srect"])
-            fw = (fa["srect"][:, 2]).astype(np.int64)
-            fh = (fa["srect"][:, 3]).astype(np.int64)
-            res.fa_rect = fa["crop_rect"]
-        T.add("vert_off", np.int32, NR + 1)
-        T.add("frame", np.int32, max(NR, 1))
+            pl.f_words = max(int(f_moff[-1]), 1)
+            pl.f_max_rows = int(f_rows.max()) if NU else 0
+            pl.f_max_wpr = int(f_wpr.max()) if NU else 0
+            fw = fa["srect"][:, 2].astype(np.int64)[uidx]
+            fh = fa["srect"][:, 3].astype(np.int64)[uidx]
+            iw = f_wpr.astype(np.int64)[uidx]
+            pl.fa_rect = fa["crop_rect"][uidx]
+        T.add("vert_off", np.int32, NU + 1)
+        T.add("uset", np.int32, max(NU, 1))
+        T.add("union_idx", np.int32, F)
         if need_mpl:
             T.add("m_verts", np.float64, (max(verts.shape[0], 1), 2))
-            T.add("m_rect", np.int32, (max(NR, 1), 4))
-            T.add("m_org", np.int32, (max(NR, 1), 2))
-            T.add("m_moff", np.int64, NR + 1)
+            T.add("m_rect", np.int32, (max(NU, 1), 4))
+            T.add("m_org", np.int32, (max(NU, 1), 2))
+            T.add("m_moff", np.int64, NU + 1)
             T.add("regions", REGION, max(NR, 1))
         if "fa" in st:
             T.add("f_verts", np.float64, (max(verts.shape[0], 1), 2))
-            T.add("f_erect", np.int32, (max(NR, 1), 4))
-            T.add("f_srect", np.int32, (max(NR, 1), 4))
-            T.add("f_org", np.int32, (max(NR, 1), 2))
-            T.add("f_moff", np.int64, NR + 1)
+            T.add("f_erect", np.int32, (max(NU, 1), 4))
+            T.add("f_srect", np.int32, (max(NU, 1), 4))
+            T.add("f_org", np.int32, (max(NU, 1), 2))
+            T.add("f_moff", np.int64, NU + 1)
             T.add("crops", CROP, max(NR, 1))
 
-        # ---- job tables
-        has_rois = np.zeros(F, dtype=bool)
-        has_rois[frame] = True
+        # ---- histogram / quantile job tables
+        has_rois = cnt_f > 0
         hist_jobs = []
-        hidx = {}
+        hidx = pl.hidx = {}
         if "fret" in st:
             p = self.fret_p
             masked = (p["bg_scope"] == "roi_union")
             for key, ch in (("fret_d", self.donor_ch), ("fret_a", self.acc_ch)):
                 j = np.zeros(F, dtype=HIST_JOB)
                 j["plane"] = np.arange(F) * C + ch
-                j["mask_frame"] = np.arange(F)
+                j["mask_frame"] = set_of_frame
                 j["pattern"] = np.where(masked & has_rois, PAT_MASKED, PAT_FULL)
                 hidx[key] = sum(x.shape[0] for x in hist_jobs)
                 hist_jobs.append(j)
@@ -159,7 +221,7 @@ class FrameBatchJob:
             for ci, ch in enumerate(self.int_ch):
                 j = np.zeros(F, dtype=HIST_JOB)
                 j["plane"] = np.arange(F) * C + ch
-                j["mask_frame"] = np.arange(F)
+                j["mask_frame"] = set_of_frame
                 j["k"] = stride
                 if stride > 1:
                     j["pattern"] = np.where(masked & has_rois, PAT_MASKED_STRIDE, PAT_STRIDE1D)
@@ -174,15 +236,16 @@ class FrameBatchJob:
             hidx["fa"] = sum(x.shape[0] for x in hist_jobs)
             hist_jobs.append(j)
         hist_jobs = np.concatenate(hist_jobs) if hist_jobs else np.zeros(0, dtype=HIST_JOB)
-        NH = hist_jobs.shape[0]
-        has_ms = bool((hist_jobs["pattern"] == PAT_MASKED_STRIDE).any())
+        NH = pl.NH = hist_jobs.shape[0]
+        pl.has_ms = bool((hist_jobs["pattern"] == PAT_MASKED_STRIDE).any())
 
         # params layout (float32): [fret F*4 | int F*Ci | fa F*4]
-        Ci = len(self.int_ch)
+        Ci = pl.Ci = len(self.int_ch)
         P_FRET, P_INT, P_FA = 0, F * FP_STRIDE, F * FP_STRIDE + F * Ci
-        NP = P_FA + F * 4
+        pl.P_FRET, pl.P_INT, pl.P_FA = P_FRET, P_INT, P_FA
+        NP = pl.NP = P_FA + F * 4
         qjobs, qdst = [], []
-        qidx = {}
+        qidx = pl.qidx = {}
 
         def add_q(key, h0, q32, dst):
             q = np.zeros(F, dtype=Q_JOB)
@@ -192,18 +255,18 @@ class FrameBatchJob:
             qjobs.append(q)
             qdst.append(np.asarray(dst, dtype=np.int32))
 
-        host_bg = {}
+        host_bg = pl.host_bg = {}
         if "fret" in st:
             p = self.fret_p
             per_ch = bool(p["per_channel_p"])
             d_p = float(p["donor_p"]) if per_ch else float(p["percentile"])
             a_p = float(p["fret_p"]) if per_ch else float(p["percentile"])
-            numer_is_acc = p["ratio_mode"] == "FRET/Donor"
+            pl.numer_is_acc = p["ratio_mode"] == "FRET/Donor"
             pct = p["bg_mode"] == "percentile"
             neg = np.full(F, -1)
             add_q("fret_d", hidx["fret_d"], q32_of(d_p), P_FRET + np.arange(F) * FP_STRIDE + FP_BD if pct else neg)
             add_q("fret_a", hidx["fret_a"], q32_of(a_p), P_FRET + np.arange(F) * FP_STRIDE + FP_BA if pct else neg)
-            add_q("fret_eps", hidx["fret_d"] if numer_is_acc else hidx["fret_a"], q32_of(p["eps_percentile"]), neg)
+            add_q("fret_eps", hidx["fret_d"] if pl.numer_is_acc else hidx["fret_a"], q32_of(p["eps_percentile"]), neg)
             if p["bg_mode"] == "hist-mode":
                 host_bg["fret"] = (d_p, a_p)
         if "int" in st:
@@ -221,37 +284,51 @@ class FrameBatchJob:
             add_q("fa", hidx["fa"], q32_of(1.0), np.full(F, -1))
         qjobs = np.concatenate(qjobs) if qjobs else np.zeros(0, dtype=Q_JOB)
         qdst = np.concatenate(qdst) if qdst else np.zeros(0, dtype=np.int32)
-        NQ = qjobs.shape[0]
+        NQ = pl.NQ = qjobs.shape[0]
 
-        # region-stat jobs: per ROI  [fret: R, donor, acceptor][int: one per channel]
-        per_roi_jobs = (3 if "fret" in st else 0) + (Ci if "int" in st else 0)
-        sj = np.zeros((NR, per_roi_jobs), dtype=STAT_JOB)
-        col = 0
-        rr = np.arange(NR)
-        if "fret" in st and NR:
+        # ---- region-stat jobs.  Output rows per ROI: [fret: R, donor, acceptor][int: one per
+        # channel].  uint16 views of the same channel (FRET builder + Fluor_INT backgrounds)
+        # share one job; every job template is laid out contiguously: uint16 first, then float.
+        rpr = pl.rpr = (3 if "fret" in st else 0) + (Ci if "int" in st else 0)
+        pl.int_col0 = 3 if "fret" in st else 0
+        q3 = ((QK_PCT, QK_MEDIAN, QK_PCT), (q32_of(5), 0.0, q32_of(95)))
+        qmed = ((0, QK_MEDIAN, 0), (0.0, 0.0, 0.0))
+        views = {}                                   # channel -> list of (bidx array, clip, slot, qspec)
+        if "fret" in st:
             clipn = int(bool(self.fret_p["clip_neg"]))
-            s = sj[:, col]
-            s["region"], s["src"], s["plane"], s["bidx"] = rr, SRC_F32, frame, -1
-            s["qkind"] = (QK_PCT, QK_MEDIAN, QK_PCT)
-            s["q32"] = (q32_of(5), 0.0, q32_of(95))
-            for k, (ch, slot) in enumerate(((self.donor_ch, FP_BD), (self.acc_ch, FP_BA)), 1):
-                s = sj[:, col + k]
-                s["region"], s["src"], s["plane"] = rr, SRC_U16, frame * C + ch
-                s["bidx"] = P_FRET + frame * FP_STRIDE + slot
-                s["clip_neg"] = clipn
-                s["qkind"] = (0, QK_MEDIAN, 0)
-            col += 3
-        if "int" in st and NR:
+            for ch, slot, out_slot in ((self.donor_ch, FP_BD, 1), (self.acc_ch, FP_BA, 2)):
+                views.setdefault(ch, []).append((P_FRET + frame * FP_STRIDE + slot, clipn, out_slot, qmed))
+        if "int" in st:
             clipn = int(bool(self.int_task["clip_neg"]))
             for ci, ch in enumerate(self.int_ch):
-                s = sj[:, col + ci]
-                s["region"], s["src"], s["plane"] = rr, SRC_U16, frame * C + ch
-                s["bidx"] = P_INT + frame * Ci + ci
-                s["clip_neg"] = clipn
-                s["qkind"] = (QK_PCT, QK_MEDIAN, QK_PCT)
-                s["q32"] = (q32_of(5), 0.0, q32_of(95))
-        sj = np.ascontiguousarray(sj).reshape(-1)
-        NS = sj.shape[0]
+                views.setdefault(ch, []).append((P_INT + frame * Ci + ci, clipn, pl.int_col0 + ci, q3))
+        rr = np.arange(NR)
+        u16_tmpl = []
+        for ch, vl in views.items():
+            while vl:
+                take, vl = vl[:2], vl[2:]
+                s = np.zeros(NR, dtype=STAT_JOB)
+                s["region"], s["src"], s["plane"], s["n_views"] = rr, SRC_U16, frame * C + ch, len(take)
+                qs = q3 if any(v[3] is q3 for v in take) else qmed
+                s["qkind"], s["q32"] = qs
+                for v, (bidx, clipn, out_slot, _) in enumerate(take):
+                    s["bidx"][:, v] = bidx
+                    s["clip_neg"][:, v] = clipn
+                    s["out"][:, v] = rr * rpr + out_slot
+                u16_tmpl.append(s)
+        f32_tmpl = []
+        if "fret" in st:
+            s = np.zeros(NR, dtype=STAT_JOB)
+            s["region"], s["src"], s["plane"], s["n_views"] = rr, SRC_F32, frame, 1
+            s["bidx"] = -1
+            s["qkind"], s["q32"] = q3
+            s["out"][:, 0] = rr * rpr
+            f32_tmpl.append(s)
+        pl.n_u16 = NR * len(u16_tmpl)
+        pl.n_f32 = NR * len(f32_tmpl)
+        sj = np.concatenate(u16_tmpl + f32_tmpl) if (u16_tmpl or f32_tmpl) and NR else np.zeros(0, dtype=STAT_JOB)
+        NS = pl.NS = sj.shape[0]
+        pl.n_out = NR * rpr
 
         T.add("hist_jobs", HIST_JOB, max(NH, 1))
         T.add("qjobs", Q_JOB, max(NQ, 1))
@@ -259,43 +336,50 @@ class FrameBatchJob:
         T.add("stat_jobs", STAT_JOB, max(NS, 1))
         T.add("fa_stat_idx", np.int32, F)
 
-        # ---- fill pinned table buffer, single H2D
-        pin_np, pin_t = self._pinned("pin_tables", T.size)
-        V = lambda name: T.view(pin_np, name)
+        # ---- fill the pinned table buffer (uploaded with one H2D copy every step)
+        pl.pin_np, pl.pin_t = self.mem.pinned(T.size, np.uint8)
+        V = lambda name: T.view(pl.pin_np, name)
         V("vert_off")[:] = off.astype(np.int32)
-        if NR:
-            V("frame")[:NR] = frame
+        if NU:
+            V("uset")[:NU] = uset
+        V("union_idx")[:] = set_of_frame
         if need_mpl:
             V("m_verts")[: verts.shape[0]] = verts
-            V("m_rect")[:NR] = m_rect
-            V("m_org")[:NR] = 0
+            V("m_rect")[:NU] = m_rect
+            V("m_org")[:NU] = 0
             V("m_moff")[:] = m_moff
-            reg = V("regions")
             if NR:
-                r = reg[:NR]
-                r["mask_off"] = m_moff[:-1]
-                r["x0"], r["y0"] = m_rect[:, 0], m_rect[:, 1]
-                r["w"], r["h"] = m_rect[:, 2] - m_rect[:, 0], m_rect[:, 3] - m_rect[:, 1]
-                r["wpr"], r["frame"], r["use_and"], r["pad0"] = m_wpr, frame, 0, 0
+                r = V("regions")[:NR]
+                mr = m_rect[uidx]
+                r["mask_off"] = m_moff[:-1][uidx]
+                r["x0"], r["y0"] = mr[:, 0], mr[:, 1]
+                r["w"], r["h"] = mr[:, 2] - mr[:, 0], mr[:, 3] - mr[:, 1]
+                r["wpr"], r["frame"], r["use_and"], r["and_plane"] = m_wpr[uidx], frame, 0, 0
         if "fa" in st:
             V("f_verts")[: verts.shape[0]] = fa["local_verts"]
-            V("f_erect")[:NR] = fa["erect"]
-            V("f_srect")[:NR] = fa["srect"]
-            V("f_org")[:NR] = fa["org"]
+            V("f_erect")[:NU] = fa["erect"]
+            V("f_srect")[:NU] = fa["srect"]
+            V("f_org")[:NU] = fa["org"]
             V("f_moff")[:] = f_moff
+            bit_off = np.zeros(NR + 1, dtype=np.int64)
             pix_off = np.zeros(NR + 1, dtype=np.int64)
             row_off = np.zeros(NR + 1, dtype=np.int64)
+            np.cumsum(iw * fh, out=bit_off[1:])
             np.cumsum(fw * fh, out=pix_off[1:])
             np.cumsum(fh, out=row_off[1:])
             if NR:
                 c = V("crops")[:NR]
-                c["bit_off"], c["pix_off"], c["row_off"] = f_moff[:-1], pix_off[:-1], row_off[:-1]
-                c["ox"], c["oy"] = fa["org"][:, 0], fa["org"][:, 1]
-                c["w"], c["h"], c["wpr"] = fw, fh, f_wpr
+                c["bit_off"], c["pix_off"], c["row_off"] = bit_off[:-1], pix_off[:-1], row_off[:-1]
+                c["mask_off"] = f_moff[:-1][uidx]
+                org = fa["org"][uidx]
+                c["ox"], c["oy"] = org[:, 0], org[:, 1]
+                c["w"], c["h"], c["wpr"] = fw, fh, iw
                 c["plane"], c["frame"], c["pad0"] = frame * C + self.fa_ch, frame, 0
-            res.fa_crops = V("crops")[:NR].copy()
-            total_px, total_rows = int(pix_off[-1]), int(row_off[-1])
-            comp_cap = int((((fh + 1) // 2) * ((fw + 1) // 2)).sum()) or 1
+            pl.fa_crops = V("crops")[:NR].copy()
+            pl.fa_words = max(int(bit_off[-1]), 1)
+            pl.total_px, pl.total_rows = int(pix_off[-1]), int(row_off[-1])
+            pl.fa_max_h = int(fh.max()) if NR else 0
+            pl.comp_cap = int((((fh + 1) // 2) * ((fw + 1) // 2)).sum()) or 1
         if NH:
             V("hist_jobs")[:NH] = hist_jobs
         if NQ:
@@ -305,103 +389,120 @@ class FrameBatchJob:
             V("stat_jobs")[:NS] = sj
         if "fa" in st:
             V("fa_stat_idx")[:] = hidx["fa"] + np.arange(F)
-        d_tab = self._dev("d_tables", T.size)
-        mem.upload_async(d_tab, pin_t, T.size)
-        tp = lambda name: T.ptr(d_tab.ptr, name)
 
         # ---- device output arena (one D2H at the end)
-        O = _Arena()
+        O = pl.O = _Arena()
         O.add("params", np.float32, max(NP, 1))
-        O.add("m_area", np.uint32, max(NR, 1))
-        O.add("f_area", np.uint32, max(NR, 1))
-        O.add("stat_out", STAT_OUT, max(NS, 1))
+        O.add("m_area", np.uint32, max(NU, 1))
+        O.add("f_area", np.uint32, max(NU, 1))
+        O.add("stat_out", STAT_OUT, max(pl.n_out, 1))
         O.add("comp_off", np.int32, NR + 1)
-        d_out = self._dev("d_out", O.size)
-        op = lambda name: O.ptr(d_out.ptr, name)
+        return pl
+
+    # ------------------------------------------------------------------ the step
+    def run(self, planes, polys_per_frame):
+        eng, mem, F, C, H, W = self.eng, self.mem, self.F, self.C, self.H, self.W
+        st = self.stages
+        pl = self._plan_for(polys_per_frame)
+        T, O, NR, NU, NH, NQ, NS = pl.T, pl.O, pl.NR, pl.NU, pl.NH, pl.NQ, pl.NS
+        P_FRET, P_INT, P_FA, Ci, NP = pl.P_FRET, pl.P_INT, pl.P_FA, pl.Ci, pl.NP
+        res = BatchResult()
+        res.frame, res.roi, res.n_rois = pl.frame, pl.roi, NR
+        stream = mem.stream
         lib_call = eng.call
 
-        # ---- rasterise
-        if need_mpl:
-            m_pool = self._dev("m_pool", 4 * max(int(m_moff[-1]), 1))
-            d_union = self._dev("union", 4 * F * H * self.union_wpr)
-            mem.zero_bytes(d_union, 4 * F * H * self.union_wpr)
-            lib_call("ipb_rasterize_rois", geo.RULE_MPL, NR, tp("m_verts"), tp("vert_off"), tp("m_rect"),
-                     tp("m_rect"), tp("m_org"), tp("frame"), tp("m_moff"),
-                     int(m_rows.max()) if NR else 0, int(m_wpr.max()) if NR else 0, m_pool.ptr,
-                     op("m_area"), d_union.ptr, self.union_wpr, H, stream)
+        d_tab = self._dev("d_tables", T.size)
+        mem.upload_async(d_tab, pl.pin_t, T.size)
+        tp = lambda name: T.ptr(d_tab.ptr, name)
+        d_out = self._dev("d_out", O.size)
+        op = lambda name: O.ptr(d_out.ptr, name)
+
+        # ---- rasterise every unique ROI once
+        if pl.need_mpl:
+            m_pool = self._dev("m_pool", 4 * pl.m_words)
+            d_union = self._dev("union", 4 * pl.S * H * self.union_wpr)
+            mem.zero_bytes(d_union, 4 * pl.S * H * self.union_wpr)
+            lib_call("ipb_rasterize_rois", geo.RULE_MPL, NU, tp("m_verts"), tp("vert_off"), tp("m_rect"),
+                     tp("m_rect"), tp("m_org"), tp("uset"), tp("m_moff"), pl.m_max_rows, pl.m_max_wpr,
+                     m_pool.ptr, op("m_area"), d_union.ptr, self.union_wpr, H, stream)
             union_ptr = d_union.ptr
         else:
             union_ptr = None
         if "fa" in st:
-            f_pool = self._dev("f_pool", 4 * max(int(f_moff[-1]), 1))
-            lib_call("ipb_rasterize_rois", geo.RULE_SK, NR, tp("f_verts"), tp("vert_off"), tp("f_erect"),
-                     tp("f_srect"), tp("f_org"), tp("frame"), tp("f_moff"),
-                     int(f_rows.max()) if NR else 0, int(f_wpr.max()) if NR else 0, f_pool.ptr,
-                     op("f_area"), None, self.union_wpr, H, stream)
+            f_pool = self._dev("f_pool", 4 * pl.f_words)
+            lib_call("ipb_rasterize_rois", geo.RULE_SK, NU, tp("f_verts"), tp("vert_off"), tp("f_erect"),
+                     tp("f_srect"), tp("f_org"), tp("uset"), tp("f_moff"), pl.f_max_rows, pl.f_max_wpr,
+                     f_pool.ptr, op("f_area"), None, self.union_wpr, H, stream)
 
         # ---- histograms -> percentiles -> per-frame scalars
         d_hist = self._dev("hist", 4 * 65536 * max(NH, 1))
         d_hstat = self._dev("hstat", 8 * 4 * max(NH, 1))
-        d_scr = self._dev("rank_scratch", 8 * max(NH, 1) * H) if has_ms else None
+        d_scr = self._dev("rank_scratch", 8 * max(NH, 1) * H) if pl.has_ms else None
         d_qout = self._dev("qout", Q_OUT.itemsize * max(NQ, 1))
         mem.zero_bytes(d_out, O.sections["params"][3], O.sections["params"][0])
         if NH:
-            lib_call("ipb_hist_u16", planes.ptr, H, W, tp("hist_jobs"), NH, int(has_ms), union_ptr,
+            lib_call("ipb_hist_u16", planes.ptr, H, W, tp("hist_jobs"), NH, int(pl.has_ms), union_ptr,
                      self.union_wpr, d_scr.ptr if d_scr is not None else None, d_hist.ptr, d_hstat.ptr, stream)
             lib_call("ipb_hist_quantiles", d_hist.ptr, d_hstat.ptr, tp("qjobs"), NQ, d_qout.ptr, stream)
             lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), stream)
-        if host_bg:
-            self._host_hist_mode(host_bg, d_hist, hidx, d_out, O, NH, P_FRET, P_INT, Ci)
+        if pl.host_bg:
+            self._host_hist_mode(pl.host_bg, d_hist, pl.hidx, d_out, O, NH, P_FRET, P_INT, Ci)
         if "fret" in st:
-            den_slot = FP_BD if numer_is_acc else FP_BA
-            lib_call("ipb_fret_eps", d_qout.ptr + Q_OUT.itemsize * qidx["fret_eps"], F, den_slot,
+            den_slot = FP_BD if pl.numer_is_acc else FP_BA
+            lib_call("ipb_fret_eps", d_qout.ptr + Q_OUT.itemsize * pl.qidx["fret_eps"], F, den_slot,
                      int(bool(self.fret_p["clip_neg"])), 5.0, op("params") + 4 * P_FRET, stream)
         if "fa" in st:
-            lib_call("ipb_fa_params", d_hstat.ptr, tp("fa_stat_idx"), d_qout.ptr + Q_OUT.itemsize * qidx["fa"],
+            lib_call("ipb_fa_params", d_hstat.ptr, tp("fa_stat_idx"), d_qout.ptr + Q_OUT.itemsize * pl.qidx["fa"],
                      F, H * W, float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, stream)
 
         # ---- fused FRET pass
+        d_R = None
         if "fret" in st:
             d_R = self._dev("R", 4 * F * H * W)
             d_Rroi = self._dev("Rroi", 4 * F * H * W) if self.want_roi_image else None
             cfg = fret_cfg(self.fret_p, C, self.donor_ch, self.acc_ch)
             lib_call("ipb_fret_pixels", planes.ptr, F, H, W, cfg.ctypes.data, op("params") + 4 * P_FRET,
-                     union_ptr, self.union_wpr, d_R.ptr, None,
+                     union_ptr, self.union_wpr, tp("union_idx"), d_R.ptr, None,
                      d_Rroi.ptr if d_Rroi is not None else None, None, None, stream)
             res.R = ops_view(d_R, np.float32, (F, H, W), mem)
             res.R_roi = ops_view(d_Rroi, np.float32, (F, H, W), mem) if d_Rroi is not None else None
 
-        # ---- per-ROI statistics (all stages in one launch)
-        if NS:
-            lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), NS, m_pool.ptr, None, 0, H, W,
-                     planes.ptr, d_R.ptr if "fret" in st else None, op("params"), op("stat_out"), stream)
+        # ---- per-ROI statistics: the float (ratio) jobs first, they are the long ones
+        if pl.n_f32:
+            lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs") + STAT_JOB.itemsize * pl.n_u16, pl.n_f32,
+                     SRC_F32, m_pool.ptr, None, 0, H, W, planes.ptr, d_R.ptr, op("params"), op("stat_out"), stream)
+        if pl.n_u16:
+            lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, None, 0,
+                     H, W, planes.ptr, None, op("params"), op("stat_out"), stream)
 
         # ---- focal adhesions
-        if "fa" in st and NR and total_px > 0:
-            words = max(int(f_moff[-1]), 1)
+        if "fa" in st and NR and pl.total_px > 0:
+            words = pl.fa_words
             bwA, bwB, bwF, rootb = (self._dev(n, 4 * words) for n in ("bwA", "bwB", "bwF", "rootbits"))
-            d_L = self._dev("L", 4 * total_px)
-            d_cs = self._dev("csize", 4 * total_px)
-            d_rr = self._dev("row_roots", 4 * total_rows)
-            d_rb = self._dev("row_base", 4 * total_rows)
+            d_L = self._dev("L", 4 * pl.total_px)
+            d_cs = self._dev("csize", 4 * pl.total_px)
+            d_rr = self._dev("row_roots", 4 * pl.total_rows)
+            d_rb = self._dev("row_base", 4 * pl.total_rows)
             d_cc = self._dev("crop_count", 4 * NR)
-            d_comps = self._dev("comps", COMP.itemsize * comp_cap)
-            d_lab = self._dev("labels", 4 * total_px) if self.want_labels else None
+            d_comps = self._dev("comps", COMP.itemsize * pl.comp_cap)
+            d_lab = self._dev("labels", 4 * pl.total_px) if self.want_labels else None
             cfgf = self.fa_cfg
-            lib_call("ipb_fa_segment", tp("crops"), NR, int(fh.max()), total_rows, planes.ptr, H, W,
+            lib_call("ipb_fa_segment", tp("crops"), NR, pl.fa_max_h, pl.total_rows, planes.ptr, H, W,
                      op("params") + 4 * P_FA, f_pool.ptr,
                      float(cfgf["min_px"]) if cfgf["min_px"] > 0 else 0.0,
                      int(cfgf["close_radius"]) if cfgf["close_radius"] > 0 else 0,
                      bwA.ptr, bwB.ptr, d_L.ptr, d_cs.ptr, rootb.ptr, d_rr.ptr, d_rb.ptr, d_cc.ptr,
-                     bwF.ptr, op("comp_off"), d_comps.ptr, comp_cap,
+                     bwF.ptr, op("comp_off"), d_comps.ptr, pl.comp_cap,
                      d_lab.ptr if d_lab is not None else None, stream)
             res.fa_bw = ops_view(bwF, np.uint32, (words,), mem)
-            res.fa_labels = ops_view(d_lab, np.int32, (total_px,), mem) if d_lab is not None else None
+            res.fa_labels = ops_view(d_lab, np.int32, (pl.total_px,), mem) if d_lab is not None else None
             fa_ran = True
         else:
             fa_ran = False
             if "fa" in st:
                 mem.zero_bytes(d_out, O.sections["comp_off"][3], O.sections["comp_off"][0])
+        if "fa" in st:
+            res.fa_rect, res.fa_crops = pl.fa_rect, pl.fa_crops
 
         # ---- results: one packed D2H (+ exact-size adhesion table)
         pout_np, pout_t = self._pinned("pin_out", O.size)
@@ -417,21 +518,19 @@ class FrameBatchJob:
             res.int_p = list(self._int_p)
         if "fa" in st:
             res.fa_stats = params[P_FA: P_FA + F * 4].reshape(F, 4)
-        if need_mpl:
-            res.area = OV("m_area")[:NR].copy()
+        if pl.need_mpl:
+            res.area = OV("m_area")[:NU].copy()[pl.uidx] if NR else np.zeros(0, np.uint32)
             self.n_roi_px = int(res.area.sum())
-        so = OV("stat_out")[:NS].copy().reshape(NR, per_roi_jobs) if NS else np.zeros((NR, 0), dtype=STAT_OUT)
-        col = 0
+        so = OV("stat_out")[:pl.n_out].copy().reshape(NR, pl.rpr) if pl.n_out else np.zeros((NR, 0), dtype=STAT_OUT)
         if "fret" in st:
-            res.fret_stat = so[:, col: col + 3]
-            col += 3
+            res.fret_stat = so[:, 0:3]
         if "int" in st:
-            res.int_stat = so[:, col: col + Ci]
+            res.int_stat = so[:, pl.int_col0: pl.int_col0 + Ci]
         if "fa" in st:
             comp_off = OV("comp_off")[: NR + 1].copy()
             res.fa_comp_off = comp_off
             total = int(comp_off[-1]) if fa_ran else 0
-            if fa_ran and total > comp_cap:
+            if fa_ran and total > pl.comp_cap:
                 raise RuntimeError("fa_segment: component table overflow")
             if total:
                 nb = COMP.itemsize * total
@@ -480,7 +579,10 @@ class FrameBatchJob:
         return {
             "ipb_hist_u16": 2 * px * n_hist,             # each sampled plane read once per job
             "ipb_fret_pixels": 8 * px,                   # 2 x uint16 in, float32 ratio out
-            "ipb_region_stats": 4 * roi_px * 3 + 2 * roi_px * len(self.int_ch),
+            # ratio job: float32 under the mask; one uint16 job per measured channel
+            "ipb_region_stats": (4 * roi_px if "fret" in self.stages else 0) + 2 * roi_px * len(
+                set(([self.donor_ch, self.acc_ch] if "fret" in self.stages else []) +
+                    (list(self.int_ch) if "int" in self.stages else []))),
             "ipb_rasterize_rois": roi_px // 8 + 1,       # bit masks written
             "ipb_fa_segment": 2 * roi_px,                # crop pixels of the FA channel read once
         }.get(entry, 0)

@@ -43,6 +43,19 @@ int ipb_check_launch(const char* what) {
         }                                                                 \
     } while (0)
 
+template <int SRC>
+static int ipb_launch_region_stats(const void* regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
+                                   const uint32_t* and_bits, int and_wpr, int H, int W, const uint16_t* planes,
+                                   const float* images, const float* bvals, void* out, void* stream)
+{
+    const int smem = IPB_RS_SMEM_BYTES;
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_region_stats<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "region_stats smem");
+    IPB_LAUNCH(ipb_k_region_stats<SRC>, dim3(n_jobs), dim3(IPB_RS_THREADS), (size_t)smem, stream,
+               (const IpbRegion*)regions, (const IpbStatJob*)jobs, mask_pool, and_bits, and_wpr, H, W,
+               planes, images, bvals, (IpbStatOut*)out, smem);
+    return ipb_check_launch("ipb_k_region_stats");
+}
+
 extern "C" {
 
 const char* ipb_last_error(void) { return g_ipb_err; }
@@ -167,7 +180,8 @@ int ipb_fa_params(const uint64_t* stats, const int32_t* stat_idx, const void* qo
 // ---------------------------------------------------------------- fused FRET pass
 int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const void* cfg_host,
                     const float* fparams, const uint32_t* union_bits, int union_wpr,
-                    float* R, float* Ralt, float* Rroi, float* Dcorr, float* Acorr, void* stream)
+                    const int32_t* union_idx, float* R, float* Ralt, float* Rroi, float* Dcorr,
+                    float* Acorr, void* stream)
 {
     if (n_frames <= 0) return IPB_OK;
     IPB_REQUIRE(planes && cfg_host && fparams && H > 0 && W > 0, "ipb_fret_pixels: bad argument");
@@ -181,23 +195,34 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const vo
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     IPB_LAUNCH(ipb_k_fret_pixels, dim3((unsigned)blocks), dim3(256), 0, stream, planes, n_frames, H, W,
-               cfg, fparams, union_bits, union_wpr, R, Ralt, Rroi, Dcorr, Acorr);
+               cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr);
     return ipb_check_launch("ipb_k_fret_pixels");
 }
 
 // ---------------------------------------------------------------- region statistics
-int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
-                     const uint32_t* and_bits, int and_wpr, int H, int W, const uint16_t* planes,
-                     const float* images, const float* bvals, void* out, void* stream)
+int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int uniform_src,
+                     const uint32_t* mask_pool, const uint32_t* and_bits, int and_wpr, int H, int W,
+                     const uint16_t* planes, const float* images, const float* bvals, void* out,
+                     void* stream)
 {
     if (n_jobs <= 0) return IPB_OK;
     IPB_REQUIRE(regions && jobs && mask_pool && out && H > 0 && W > 0, "ipb_region_stats: bad argument");
-    const int smem = IPB_RS_SMEM_BYTES;
-    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_region_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "region_stats smem");
-    IPB_LAUNCH(ipb_k_region_stats, dim3(n_jobs), dim3(IPB_RS_THREADS), (size_t)smem, stream,
-               (const IpbRegion*)regions, (const IpbStatJob*)jobs, mask_pool, and_bits, and_wpr, H, W,
-               planes, images, bvals, (IpbStatOut*)out, smem);
-    return ipb_check_launch("ipb_k_region_stats");
+    IPB_REQUIRE(uniform_src >= -1 && uniform_src <= 1, "ipb_region_stats: bad uniform_src %d", uniform_src);
+    int rc = IPB_OK;
+    // uniform_src = -1: the job list may mix sources; each instantiation skips the other's jobs
+    // (a source whose buffer is NULL is not launched at all)
+    if (uniform_src == IPB_SRC_U16 || (uniform_src < 0 && planes)) {
+        IPB_REQUIRE(planes, "ipb_region_stats: uint16 jobs need planes");
+        rc = ipb_launch_region_stats<IPB_SRC_U16>(regions, jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
+                                                  planes, images, bvals, out, stream);
+        if (rc) return rc;
+    }
+    if (uniform_src == IPB_SRC_F32 || (uniform_src < 0 && images)) {
+        IPB_REQUIRE(images, "ipb_region_stats: float32 jobs need images");
+        rc = ipb_launch_region_stats<IPB_SRC_F32>(regions, jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
+                                                  planes, images, bvals, out, stream);
+    }
+    return rc;
 }
 
 // ---------------------------------------------------------------- focal-adhesion chain

@@ -29,6 +29,7 @@ struct IpbCrop {
     long long bit_off;   // word offset of the crop's bit rows (all bit pools share it)
     long long pix_off;   // element offset of the crop's per-pixel arrays (labels)
     long long row_off;   // element offset of the crop's per-row arrays
+    long long mask_off;  // word offset of the crop's ROI mask rows in the (shared) roi_mask pool
     int ox, oy;          // frame position of crop pixel (0,0)
     int w, h;
     int wpr;             // words per bit row
@@ -146,7 +147,7 @@ ipb_k_fa_threshold(const IpbCrop* __restrict__ crops, const unsigned short* __re
         const unsigned word = __ballot_sync(IPB_FULL, on);
         if (lane == 0) {
             const size_t wi = (size_t)c.bit_off + (size_t)y * c.wpr + j;
-            bw[wi] = word & roi_mask[wi];
+            bw[wi] = word & roi_mask[(size_t)c.mask_off + (size_t)y * c.wpr + j];
         }
     }
 }

@@ -77,6 +77,7 @@ __device__ __forceinline__ IpbFretPx ipb_fret_px(const IpbFretCfg& cfg, const fl
 __global__ void __launch_bounds__(256)
 ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W, IpbFretCfg cfg,
                   const float* __restrict__ fparams, const unsigned* __restrict__ union_bits, int union_wpr,
+                  const int* __restrict__ union_idx /* frame -> union plane; null: identity */,
                   float* __restrict__ R, float* __restrict__ Ralt, float* __restrict__ Rroi,
                   float* __restrict__ Dcorr, float* __restrict__ Acorr)
 {
@@ -100,7 +101,8 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
             unsigned ub = 0xffu;
             if (Rroi) {
                 const int y = (int)(p0 / W), x0 = (int)(p0 % W);
-                ub = union_bits ? ((union_bits[((size_t)f * H + y) * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu) : 0u;
+                const int uf = union_idx ? union_idx[f] : f;
+                ub = union_bits ? ((union_bits[((size_t)uf * H + y) * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu) : 0u;
             }
             float r[8], ra[8], rr[8], dc[8], ac[8];
 #pragma unroll
@@ -136,7 +138,8 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
             if (Acorr) Acorr[i] = o.acorr;
             if (Rroi) {
                 const int y = (int)(p / W), x = (int)(p % W);
-                const bool in = union_bits && ((union_bits[((size_t)f * H + y) * union_wpr + (x >> 5)] >> (x & 31)) & 1u);
+                const int uf = union_idx ? union_idx[f] : f;
+                const bool in = union_bits && ((union_bits[((size_t)uf * H + y) * union_wpr + (x >> 5)] >> (x & 31)) & 1u);
                 Rroi[i] = in ? o.R : fnan;
             }
         }

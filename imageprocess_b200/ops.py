@@ -107,16 +107,18 @@ HIST_JOB = np.dtype([("plane", "i4"), ("pattern", "i4"), ("k", "i4"), ("mask_fra
 Q_JOB = np.dtype([("hist", "i4"), ("q32", "f4"), ("pad", "i4", 2)])
 Q_OUT = np.dtype([("prev", "i4"), ("next", "i4"), ("gamma", "f4"), ("value", "f4"), ("n", "u8")])
 REGION = np.dtype([("mask_off", "i8"), ("x0", "i4"), ("y0", "i4"), ("w", "i4"), ("h", "i4"),
-                   ("wpr", "i4"), ("frame", "i4"), ("use_and", "i4"), ("pad0", "i4")])
-STAT_JOB = np.dtype([("region", "i4"), ("src", "i4"), ("plane", "i4"), ("bidx", "i4"),
-                     ("clip_neg", "i4"), ("qkind", "i4", 3), ("q32", "f4", 3), ("pad0", "i4")])
+                   ("wpr", "i4"), ("frame", "i4"), ("use_and", "i4"), ("and_plane", "i4")])
+STAT_JOB = np.dtype([("region", "i4"), ("src", "i4"), ("plane", "i4"), ("n_views", "i4"),
+                     ("bidx", "i4", 2), ("clip_neg", "i4", 2), ("qkind", "i4", 3), ("q32", "f4", 3),
+                     ("out", "i4", 2)])
 STAT_OUT = np.dtype([("n", "u8"), ("area", "u8"), ("sum", "f8"), ("ssd", "f8"), ("vmin", "f4"),
                      ("vmax", "f4"), ("q", "f4", 3), ("pad0", "f4")])
 FRET_CFG = np.dtype([("numer_is_acceptor", "i4"), ("clip_neg", "i4"), ("sat_on", "i4"),
                      ("sat_thr", "f4"), ("use_spectral", "i4"), ("alpha", "f4"), ("beta", "f4"),
                      ("g_factor", "f4"), ("clip_on", "i4"), ("clip_max", "f4"), ("donor_ch", "i4"),
                      ("acc_ch", "i4"), ("aonly_ch", "i4"), ("n_ch", "i4")])
-CROP = np.dtype([("bit_off", "i8"), ("pix_off", "i8"), ("row_off", "i8"), ("ox", "i4"), ("oy", "i4"),
+CROP = np.dtype([("bit_off", "i8"), ("pix_off", "i8"), ("row_off", "i8"), ("mask_off", "i8"),
+                 ("ox", "i4"), ("oy", "i4"),
                  ("w", "i4"), ("h", "i4"), ("wpr", "i4"), ("plane", "i4"), ("frame", "i4"), ("pad0", "i4")])
 COMP = np.dtype([("sum_i", "u8"), ("sum_y", "u8"), ("sum_x", "u8"), ("area", "u4"), ("crop", "i4")])
 _SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG, CROP, COMP]
@@ -186,25 +188,35 @@ def _engine_fa_params(self, hres, stat_idx, qout_bg, n_frames, npx, alpha, fa):
 
 
 def _engine_fret_pixels(self, planes, F, H, W, cfg, fparams, union=None, union_wpr=0, R=None,
-                        Ralt=None, Rroi=None, Dcorr=None, Acorr=None):
+                        Ralt=None, Rroi=None, Dcorr=None, Acorr=None, union_idx=None):
     cfg = np.ascontiguousarray(cfg, dtype=FRET_CFG).reshape(1)
     p = lambda b: b.ptr if b is not None else None
     self.call("ipb_fret_pixels", planes.ptr, int(F), int(H), int(W), cfg.ctypes.data, fparams.ptr,
-                  p(union), int(union_wpr), p(R), p(Ralt), p(Rroi), p(Dcorr), p(Acorr), self.mem.stream)
+                  p(union), int(union_wpr), p(union_idx), p(R), p(Ralt), p(Rroi), p(Dcorr), p(Acorr),
+                  self.mem.stream)
 
 
 def _engine_region_stats(self, regions, jobs, mask_pool, H, W, planes=None, images=None, bvals=None,
                          and_bits=None, and_wpr=0):
-    """regions: REGION array, jobs: STAT_JOB array.  Returns device buffer of STAT_OUT."""
+    """regions: REGION array, jobs: STAT_JOB array (output rows are assigned here when left
+    zero: one row per view, in job order).  Returns device buffer of STAT_OUT."""
     mem = self.mem
     regions = np.ascontiguousarray(regions, dtype=REGION)
-    jobs = np.ascontiguousarray(jobs, dtype=STAT_JOB)
+    jobs = np.ascontiguousarray(jobs, dtype=STAT_JOB).copy()
     n = jobs.shape[0]
+    jobs["n_views"] = np.maximum(jobs["n_views"], 1)
+    if n and not jobs["out"].any():
+        first = np.concatenate([[0], np.cumsum(jobs["n_views"])[:-1]])
+        jobs["out"][:, 0] = first
+        jobs["out"][:, 1] = first + 1
+    n_out = int(jobs["n_views"].sum()) if n else 0
+    srcs = np.unique(jobs["src"]) if n else np.zeros(0, np.int32)
+    uniform = int(srcs[0]) if srcs.size == 1 else -1
     d_r = mem.from_host(regions if regions.shape[0] else np.zeros(1, REGION))
     d_j = mem.from_host(jobs if n else np.zeros(1, STAT_JOB))
-    out = mem.empty(max(n, 1), STAT_OUT)
+    out = mem.empty(max(n_out, 1), STAT_OUT)
     p = lambda b: b.ptr if b is not None else None
-    self.call("ipb_region_stats", d_r.ptr, d_j.ptr, n, mask_pool.ptr, p(and_bits), int(and_wpr),
+    self.call("ipb_region_stats", d_r.ptr, d_j.ptr, n, uniform, mask_pool.ptr, p(and_bits), int(and_wpr),
                   int(H), int(W), p(planes), p(images), p(bvals), out.ptr, mem.stream)
     out._keep = (d_r, d_j)
     return out
@@ -258,6 +270,7 @@ def crops_from_masks(rm, planes_of_roi):
     w = (t.srect[:, 2] - t.srect[:, 0]).astype(np.int64)
     h = (t.srect[:, 3] - t.srect[:, 1]).astype(np.int64)
     cr["bit_off"] = t.mask_off[:-1]
+    cr["mask_off"] = t.mask_off[:-1]
     cr["pix_off"][1:] = np.cumsum(w * h)[:-1]
     cr["row_off"][1:] = np.cumsum(h)[:-1]
     cr["ox"] = t.org[:, 0] + t.srect[:, 0]

@@ -124,14 +124,18 @@ typedef struct {
 } ipb_fret_cfg;
 int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W,
                     const void* cfg_host /* ipb_fret_cfg, [host] */, const float* fparams,
-                    const uint32_t* union_bits, int union_wpr, float* R, float* Ralt, float* Rroi,
-                    float* Dcorr, float* Acorr, void* stream);
+                    const uint32_t* union_bits, int union_wpr,
+                    const int32_t* union_idx /* [F] frame -> union plane, NULL: identity */,
+                    float* R, float* Ralt, float* Rroi, float* Dcorr, float* Acorr, void* stream);
 
 /* ------------------------------------------------------------------ per-region statistics
  * Replaces quantify_stats / quantify_per_roi_multi (INT/Fluor_INT.py:494-538),
  * quantify_per_roi (fret_ratio_builder.py:342-362) and the Nesprin2 row statistics
  * (Nesprin2_FRET_Builder.py:1537-1581): n, sum, sum of squared deviations, min, max and up
- * to three exact order-statistic results (np.percentile / np.median float32 arithmetic).   */
+ * to three exact order-statistic results (np.percentile / np.median float32 arithmetic).
+ * A uint16 job may carry up to two VIEWS (background B, clip) of the same pixels: the order
+ * statistics of value = float32(raw) - B are selected once on the raw integer keys and each
+ * view gets its own output row.                                                            */
 #define IPB_SRC_U16 0            /* value = float32(raw) - B, optionally clipped at 0 */
 #define IPB_SRC_F32 1            /* value = float32 image pixel, non-finite dropped */
 #define IPB_QKIND_NONE 0
@@ -140,13 +144,17 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W,
 typedef struct {
     int64_t mask_off;             /* word offset of the region's bit rows in mask_pool */
     int32_t x0, y0, w, h;         /* rect in frame coordinates */
-    int32_t wpr, frame, use_and, pad0;
+    int32_t wpr, frame, use_and;
+    int32_t and_plane;            /* use_and != 0: AND with bit plane and_bits[and_plane][H][and_wpr] */
 } ipb_region;
 typedef struct {
-    int32_t region, src, plane, bidx, clip_neg;
+    int32_t region, src, plane;
+    int32_t n_views;              /* uint16: 1..2, float32: 1 */
+    int32_t bidx[2];              /* per view: index into bvals, < 0: B = 0 */
+    int32_t clip_neg[2];
     int32_t qkind[3];
     float q32[3];
-    int32_t pad0;
+    int32_t out[2];               /* view v writes output row out[v] */
 } ipb_stat_job;
 typedef struct {
     uint64_t n, area;
@@ -155,9 +163,12 @@ typedef struct {
     float q[3];
     float pad0;
 } ipb_stat_out;
-int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
-                     const uint32_t* and_bits, int and_wpr, int H, int W, const uint16_t* planes,
-                     const float* images, const float* bvals, void* out, void* stream);
+/* uniform_src: IPB_SRC_U16 / IPB_SRC_F32 when every job has that source (one launch), -1 for
+ * a mixed list (one launch per source, each skipping the other's jobs).                    */
+int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int uniform_src,
+                     const uint32_t* mask_pool, const uint32_t* and_bits, int and_wpr, int H, int W,
+                     const uint16_t* planes, const float* images, const float* bvals, void* out,
+                     void* stream);
 
 /* ------------------------------------------------------------------ focal-adhesion chain
  * Replaces analyze_fa_crop (INT/FA_Analyzer.py:123-195) for a ragged batch of crops in one
@@ -167,7 +178,7 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const ui
  * Crop-border semantics and per-crop label numbering are the reference's.
  *   crops        ipb_crop[n_crops] [dev]; bit rows of a crop live at bit_off in every bit pool
  *   fa_params    float32 [F][4] = {mean, std, bg, thr} from ipb_fa_params
- *   roi_mask     the IPB_RULE_SK mask pool (same layout as the crops' bit rows)
+ *   roi_mask     the IPB_RULE_SK mask pool (rows of wpr words at ipb_crop.mask_off)
  *   min_size     <= 0: no small-object removal;  close_radius 0..5 (0: no closing)
  *   bw_a, bw_b, rootbits, bw_final  uint32 pools of the mask pool's size (scratch / result)
  *   L, csize     int32 / uint32 [total_px] scratch;  row_roots, row_base int32 [total_rows]
@@ -177,6 +188,8 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, const ui
  *   labels       optional int32 [total_px] label maps (crop-local, 0 background)           */
 typedef struct {
     int64_t bit_off, pix_off, row_off;
+    int64_t mask_off;     /* word offset of the crop's ROI mask rows in roi_mask (crops of
+                             different frames may share one rasterised mask) */
     int32_t ox, oy, w, h, wpr, plane, frame, pad0;
 } ipb_crop;
 typedef struct {

@@ -264,10 +264,13 @@ def fa_um_to_px_config(params, px_size):
 
 
 def fa_batch_rows(img, rois, params, px_size, s_tag="S01", save_ok_only=True,
-                  with_contours=True):
-    """Per-file body of _run_batch_process, INT/FA_Analyzer.py:984-1039."""
+                  with_contours=True, stats=None):
+    """Per-file body of _run_batch_process, INT/FA_Analyzer.py:984-1039.  `stats` overrides
+    the global (mean, std, bg) tuple -- used by parity tests when the float32 threshold built
+    from exact integer moments differs from numpy's pairwise float32 one by an ulp."""
     config = fa_um_to_px_config(params, px_size)
-    stats = fa_global_stats(img)
+    if stats is None:
+        stats = fa_global_stats(img)
     rows = []
     for i, roi_poly in enumerate(rois):
         roi_poly = np.array(roi_poly, dtype=float)

@@ -282,10 +282,10 @@ def check_region_stats_streaming(eng):
     B = np.float32(1234.5)
     jobs = np.zeros(4, dtype=ops.STAT_JOB)
     for r in range(2):
-        jobs[2 * r] = (r, ops.SRC_U16, 0, 0, 1, (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
-                       (ops.q32_of(5), 0.0, ops.q32_of(95)), 0)
-        jobs[2 * r + 1] = (r, ops.SRC_F32, 0, -1, 0, (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
-                           (ops.q32_of(2.5), 0.0, ops.q32_of(99)), 0)
+        jobs[2 * r] = (r, ops.SRC_U16, 0, 1, (0, -1), (1, 0), (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
+                       (ops.q32_of(5), 0.0, ops.q32_of(95)), (0, 0))
+        jobs[2 * r + 1] = (r, ops.SRC_F32, 0, 1, (-1, -1), (0, 0), (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
+                           (ops.q32_of(2.5), 0.0, ops.q32_of(99)), (0, 0))
     out = eng.region_stats(reg, jobs, rm.pool, H, W, planes=eng.mem.from_host(img),
                            images=eng.mem.from_host(fimg), bvals=eng.mem.from_host(np.array([B]))).host()
     for r, P in enumerate(polys):
@@ -325,8 +325,8 @@ def check_region_stats_ties(eng):
     rm = eng.rasterize(geo.RULE_MPL, [geo.mpl_spec(P, (W, H))], (H, W), 1, want_union=False)
     reg = ops.regions_from_masks(rm)
     jobs = np.zeros(1, dtype=ops.STAT_JOB)
-    jobs[0] = (0, ops.SRC_F32, 0, -1, 0, (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
-               (ops.q32_of(4), 0.0, ops.q32_of(80)), 0)
+    jobs[0] = (0, ops.SRC_F32, 0, 1, (-1, -1), (0, 0), (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
+               (ops.q32_of(4), 0.0, ops.q32_of(80)), (0, 0))
     o = eng.region_stats(reg, jobs, rm.pool, H, W, images=eng.mem.from_host(fimg)).host()[0]
     fv = fimg[0][port.rasterize_polygon(P, (H, W))]
     assert int(o["n"]) == fv.size
@@ -335,3 +335,96 @@ def check_region_stats_ties(eng):
 
 
 RASTER_CHECKS.append(check_region_stats_ties)
+
+
+def check_combined_batch_shared_rois(eng):
+    """All three stages in ONE FrameBatchJob (merged uint16 views, shared unique-ROI masks):
+    frames 0 and 2 use the same ROI list object, frame 3 an equal copy, frame 1 another set;
+    pixel data differ everywhere.  Every stage is compared per frame with the oracle."""
+    from imageprocess_b200 import batch
+    rng = np.random.default_rng(5)
+    H, W = 96, 128
+    d0, a0, polysA = small_scene(31, H=H, W=W, n_cells=2, blobs=8)
+    d1, a1, polysB = small_scene(32, H=H, W=W, n_cells=2, blobs=8)
+    def jit(x):
+        return np.minimum(x.astype(np.int64) + rng.integers(0, 40, x.shape), 65535).astype(np.uint16)
+    frames = [(d0, a0, polysA), (d1, a1, polysB), (jit(d0), jit(a0), polysA),
+              (jit(d0), jit(a0), [P.copy() for P in polysA])]
+    planes = np.stack([np.stack([d, a]) for d, a, _ in frames])
+    F, C = planes.shape[:2]
+    fret_p = {"bg_scope": "roi_union", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False,
+              "donor_p": 1.0, "fret_p": 1.0, "clip_neg": True, "eps_percentile": 1.0, "ratio_mode": "FRET/Donor"}
+    task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4,
+            "percentile": 2.0, "per_channel_p": False, "ch_p_map": {}}
+    fa_params = FA_CASES[0]
+    px = 0.112
+    job = batch.FrameBatchJob(eng, (F, C, H, W), stages=("fret", "int", "fa"), fret_p=fret_p, int_task=task,
+                              fa_params=fa_params, fa_px=px, want_roi_image=True)
+    polys_pf = [fr[2] for fr in frames]
+    for rep in range(2):                                   # second run goes through the cached plan
+        res = job.run(eng.mem.from_host(planes), polys_pf)
+        assert len(job._plans) == 1
+        rows_i = batch.rows_intensity(res, F, [1, 2])
+        rows_f = batch.rows_fret(res, F)
+        rows_a = batch.rows_fa(res, job.fa_cfg, fa_params, px, F, save_ok_only=False)
+        R = res.R.host()
+        Rroi = res.R_roi.host()
+        for f, (d, a, polys) in enumerate(frames):
+            D, A = d.astype(np.float32), a.astype(np.float32)
+            want = port.fret_process_pair(D, A, polys, fret_p)
+            assert np.array_equal(R[f], want["R_full"], equal_nan=True)
+            assert np.array_equal(Rroi[f], want["R_roi"], equal_nan=True)
+            assert len(rows_f[f]) == len(want["rows"])
+            for g, w in zip(rows_f[f], want["rows"]):
+                assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"]
+                for k in ("ratio_median", "ratio_p5", "ratio_p95", "donor_median", "yfret_median"):
+                    assert g[k] == w[k], (f, k, g[k], w[k])
+                for k in ("ratio_mean", "ratio_std", "donor_mean", "yfret_mean"):
+                    assert close(g[k], w[k]), (f, k, g[k], w[k])
+            wrows, wbg, _ = port.int_process_key({1: D.copy(), 2: A.copy()}, polys, None, task)
+            assert res.int_bg[f, 0] == wbg[1]["bg"] and res.int_bg[f, 1] == wbg[2]["bg"]
+            check_int_rows(rows_i[f], wrows, (1, 2))
+            stats = port.fa_global_stats(D)
+            got = res.fa_stats[f]
+            if np.float32(got[3]) != stats[0] + job.fa_cfg["alpha"] * stats[1]:
+                stats = (np.float32(got[0]), np.float32(got[1]), stats[2])
+            wfa = port.fa_batch_rows(D, polys, fa_params, px, save_ok_only=False, with_contours=False, stats=stats)
+            assert len(rows_a[f]) == len(wfa), (f, len(rows_a[f]), len(wfa))
+            for g, w in zip(rows_a[f], wfa):
+                assert g["Cell_ID"] == w["Cell_ID"] and g["Category"] == w["Category"]
+                assert g["Area_px"] == w["Area_px"]
+                assert close(float(g["Mean_Intensity_Raw"]), float(w["Mean_Intensity_Raw"]))
+
+
+def check_region_stats_two_views(eng):
+    """One uint16 job carrying two (B, clip) views == two single-view jobs, coarse and exact bins."""
+    from imageprocess_b200 import ops
+    rng = np.random.default_rng(41)
+    H, W = 200, 260
+    for hi in (9000, 65536):                       # exact histogram bins / coarse bins (range >= 2^15)
+        img = rng.integers(0, hi, (1, H, W)).astype(np.uint16)
+        P = np.array([[3.0, 2.0], [250.0, 4.0], [255.0, 190.0], [5.0, 195.0]])
+        rm = eng.rasterize(geo.RULE_MPL, [geo.mpl_spec(P, (W, H))], (H, W), 1, want_union=False)
+        reg = ops.regions_from_masks(rm)
+        Bs = np.array([1234.5, 77.0], dtype=np.float32)
+        jobs = np.zeros(1, dtype=ops.STAT_JOB)
+        jobs[0] = (0, ops.SRC_U16, 0, 2, (0, 1), (1, 0), (ops.QK_PCT, ops.QK_MEDIAN, ops.QK_PCT),
+                   (ops.q32_of(5), 0.0, ops.q32_of(95)), (0, 0))
+        out = eng.region_stats(reg, jobs, rm.pool, H, W, planes=eng.mem.from_host(img),
+                               bvals=eng.mem.from_host(Bs)).host()
+        m = port.rasterize_polygon(P, (H, W))
+        for v, (B, clip) in enumerate(((Bs[0], True), (Bs[1], False))):
+            vals = img[0].astype(np.float32) - B
+            if clip:
+                vals[vals < 0] = 0
+            vals = vals[m]
+            o = out[v]
+            assert int(o["n"]) == vals.size
+            assert o["q"][0] == np.percentile(vals, 5) and o["q"][1] == np.median(vals) and o["q"][2] == np.percentile(vals, 95)
+            assert o["vmin"] == vals.min() and o["vmax"] == vals.max()
+            assert close(float(o["sum"]), float(vals.astype(np.float64).sum()), 1e-12)
+            assert close(math.sqrt(float(o["ssd"]) / vals.size), float(vals.astype(np.float64).std()), 1e-9)
+
+
+RASTER_CHECKS.append(check_region_stats_two_views)
+RASTER_CHECKS.append(check_combined_batch_shared_rois)
