@@ -11,26 +11,31 @@
 //                selected on the integer key v and transformed afterwards: exact.  Because
 //                the key set does not depend on B, one job can carry several VIEWS
 //                (B, clip) of the same pixels -- e.g. the FRET builder's and Fluor_INT's
-//                background levels of one channel -- and all views share the gather and the
+//                background levels of one channel -- and all views share the walk and the
 //                selection; each view gets its own output row.
 //   IPB_SRC_F32  value = a float32 image pixel (ratio image); non-finite values are
 //                dropped like the reference's np.isfinite filter; key = ordered-uint32.
 //
-// One CTA (1024 threads, one per SM) per job:
-//   gather   warps walk the region's mask words, 4 words per iteration so that 4 coalesced
-//            pixel loads per lane are in flight (lane b <-> bit b); valid values are
-//            compacted as keys into shared memory (ballot/popc positions) while n and the
-//            key range are accumulated.  Regions that do not fit in shared memory keep the
-//            same code path but re-walk global memory in every pass.
-//   select   pass 1 is ONE wide histogram over the top bits of (key - kmin) using all shared
-//            memory the key store left free (up to 32768 bins): for uint16 data this resolves
-//            every rank at once AND gives the exact per-view sums (sum of count*T(bin)), so
-//            the uint16 path does no per-pixel floating point at all.  The histogram is
-//            scanned warp-cooperatively (lanes read consecutive bins: no bank conflicts).
-//            If low bits remain (float keys), the handful of keys that share a wanted prefix
-//            are compacted into a small list which is ranked by counting (<= 512 entries) or
-//            a bitonic sort; pathological tie-heavy regions fall back to 8-bit digit passes
-//            with one histogram per distinct prefix.
+// One CTA (1024 threads, one per SM) per job.
+//   walk     the region's mask words are taken 1024 at a time: every thread fetches one
+//            word (+ the AND plane), a block scan of the popcounts gives every word its
+//            output position, and the words, positions and pixel offsets are parked in
+//            shared memory.  Each warp then owns 32 consecutive words and issues the
+//            coalesced pixel loads of 8 words back to back (lane b <-> bit b), so 8
+//            independent loads per lane are in flight instead of a mask->pixel chain.
+//   uint16, n <= 65535 (every ROI of the C1-C4 workloads): the walk counts straight into a
+//            FULL-RANGE 65536-bin histogram of packed 16-bit counters (128 KB of shared
+//            memory, no key store, no dependence on the value range -- saturated pixels
+//            cost nothing).  One warp-cooperative pass over the bins then yields n, min,
+//            max, every rank and the exact per-view sums (sum of count * T(bin)); a second
+//            one the squared deviations.  No per-pixel floating point at all.
+//   float32 (and uint16 regions with more pixels): keys are compacted into shared memory;
+//            pass 1 is ONE wide histogram over the top bits of (key - kmin) using all shared
+//            memory the key store left free; the few keys that share a wanted bin are
+//            compacted into a candidate list, and the remaining low bits are resolved by
+//            8-bit digit passes over that short list (over all keys if the list overflows).
+//            Regions that do not fit in shared memory keep the same code path but re-walk
+//            global memory in every pass.
 // numpy's float32 percentile / median arithmetic is replayed from ipb_exact.cuh.
 #pragma once
 #include "ipb_rt.cuh"
@@ -44,8 +49,13 @@
 #define IPB_RS_MAXV 2
 #define IPB_RS_DIGIT 8
 #define IPB_RS_BINS (1 << IPB_RS_DIGIT)
-#define IPB_RS_UNROLL 4
-#define IPB_RS_SMEM_BYTES (212 * 1024)      // dynamic shared memory for the key store
+#define IPB_RS_BATCH 8                      // pixel loads in flight per lane
+#define IPB_RS_SMEM_BYTES (212 * 1024)      // dynamic shared memory: key store + histogram
+#define IPB_RS_LISTCAP 4096
+// bytes of the dynamic store always left to the histogram / candidate list + digit histograms
+#define IPB_RS_RESERVE ((IPB_RS_LISTCAP + IPB_RS_MAXR * IPB_RS_BINS) * 4)
+#define IPB_RS_SENTINEL 0xffffffffu         // key slot of a dropped (non-finite) float pixel
+#define IPB_RS_PACKED_MAX 65535u            // packed 16-bit counters are exact up to this many pixels
 
 #define IPB_QKIND_NONE 0
 #define IPB_QKIND_PCT 1      // np.percentile(vals, p): q32 = f32(p)/f32(100)
@@ -88,75 +98,87 @@ struct IpbRsCtx {
     const unsigned short* u16; const float* f32; int W;
 };
 
+struct IpbRsWalkSh {          // shared staging of one 1024-word chunk of the walk
+    unsigned mw[IPB_RS_THREADS];    // mask word
+    unsigned mb[IPB_RS_THREADS];    // output position of the word's first pixel
+    unsigned mp[IPB_RS_THREADS];    // plane offset of the word's bit 0
+    unsigned wt[32];                // per-warp popcount totals
+};
+
 __device__ __forceinline__ float ipb_rs_transform(float B, int clip, unsigned v) {
     float t = __fsub_rn((float)v, B);
     if (clip && t < 0.0f) t = 0.0f;
     return t;
 }
 
-// One warp-iteration of the region walk: up to IPB_RS_UNROLL consecutive mask words of row
-// r starting at word j0; lane b owns bit b.  Fills for this lane key[u] and ok[u] (pixel
-// belongs to the region and is measured) and counts region pixels.
-template <int SRC>
-__device__ __forceinline__ void ipb_rs_load_group(const IpbRsCtx& c, int r, int j0, int lane,
-                                                  unsigned (&key)[IPB_RS_UNROLL], bool (&ok)[IPB_RS_UNROLL],
-                                                  unsigned& region_px) {
-    const unsigned* mrow = c.mask + (size_t)r * c.wpr;
-    const int y = c.y0 + r;
-    unsigned m[IPB_RS_UNROLL];
-#pragma unroll
-    for (int u = 0; u < IPB_RS_UNROLL; ++u) m[u] = (j0 + u < c.wpr) ? mrow[j0 + u] : 0u;
-    if (c.androw0) {
-        const unsigned* ar = c.androw0 + (size_t)y * c.and_wpr;
-#pragma unroll
-        for (int u = 0; u < IPB_RS_UNROLL; ++u) {
-            if (m[u]) {
-                const int xb = c.x0 + 32 * (j0 + u), k = xb >> 5, s = xb & 31;
-                unsigned lo = ar[k] >> s;
-                if (s && k + 1 < c.and_wpr) lo |= ar[k + 1] << (32 - s);
-                m[u] &= lo;
-            }
-        }
+// mask word `wi` (row r, word j) of the region, ANDed with the AND plane when there is one
+__device__ __forceinline__ unsigned ipb_rs_mask_word(const IpbRsCtx& c, unsigned wi, unsigned r, unsigned j) {
+    unsigned m = c.mask[wi];
+    if (c.androw0 && m) {
+        const unsigned* ar = c.androw0 + (size_t)(c.y0 + (int)r) * c.and_wpr;
+        const int xb = c.x0 + 32 * (int)j, k = xb >> 5, s = xb & 31;
+        unsigned lo = ar[k] >> s;
+        if (s && k + 1 < c.and_wpr) lo |= ar[k + 1] << (32 - s);
+        m &= lo;
     }
-    const size_t p0 = (size_t)y * c.W + (c.x0 + 32 * j0 + lane);
-    unsigned raw[IPB_RS_UNROLL];
-#pragma unroll
-    for (int u = 0; u < IPB_RS_UNROLL; ++u) {
-        ok[u] = (m[u] >> lane) & 1u;
-        raw[u] = 0u;
-        if (ok[u]) raw[u] = (SRC == IPB_SRC_U16) ? (unsigned)c.u16[p0 + 32 * u] : __float_as_uint(c.f32[p0 + 32 * u]);
-    }
-#pragma unroll
-    for (int u = 0; u < IPB_RS_UNROLL; ++u) {
-        region_px += ok[u] ? 1u : 0u;
-        if (SRC == IPB_SRC_U16) key[u] = raw[u];
-        else {
-            const float v = __uint_as_float(raw[u]);
-            if (ok[u] && !isfinite(v)) ok[u] = false;
-            key[u] = ipb_f32_key(v);
-        }
-    }
+    return m;
 }
 
-// f(key) for every measured value: from the shared-memory key store when it holds the whole
-// region, else by re-walking global memory.
-template <int SRC, typename F>
-__device__ __forceinline__ void ipb_rs_foreach_key(const IpbRsCtx& c, bool in_smem, unsigned n,
-                                                   const unsigned* k32, const unsigned short* k16, F f) {
-    if (in_smem) {
-        if (SRC == IPB_SRC_U16) for (unsigned i = threadIdx.x; i < n; i += blockDim.x) f((unsigned)k16[i]);
-        else for (unsigned i = threadIdx.x; i < n; i += blockDim.x) f(k32[i]);
-    } else {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        for (int r = warp; r < c.h; r += nwarps)
-            for (int j0 = 0; j0 < c.wpr; j0 += IPB_RS_UNROLL) {
-                unsigned key[IPB_RS_UNROLL], dummy = 0;
-                bool ok[IPB_RS_UNROLL];
-                ipb_rs_load_group<SRC>(c, r, j0, lane, key, ok, dummy);
+// Walks the region: f(raw, pos) for every region pixel, raw = the uint16 value or the
+// float32 bit pattern, pos = the pixel's raster-order index inside the region (only when
+// NEED_POS).  Returns the number of region pixels.  All threads of the CTA must call it.
+template <int SRC, bool NEED_POS, typename F>
+__device__ __forceinline__ unsigned ipb_rs_walk(const IpbRsCtx& c, IpbRsWalkSh& sh, F f) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned nwords = (unsigned)c.h * (unsigned)c.wpr;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned run = 0;
+    for (unsigned c0 = 0; c0 < nwords; c0 += IPB_RS_THREADS) {
+        const unsigned wi = c0 + (unsigned)tid;
+        unsigned m = 0, p = 0;
+        if (wi < nwords) {
+            const unsigned r = wi / (unsigned)c.wpr, j = wi - r * (unsigned)c.wpr;
+            m = ipb_rs_mask_word(c, wi, r, j);
+            p = (unsigned)(c.y0 + (int)r) * (unsigned)c.W + (unsigned)(c.x0 + 32 * (int)j);
+        }
+        unsigned base = 0;
+        if (NEED_POS) {
+            const unsigned cnt = (unsigned)__popc(m);
+            unsigned incl = cnt;
 #pragma unroll
-                for (int u = 0; u < IPB_RS_UNROLL; ++u) if (ok[u]) f(key[u]);
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) sh.wt[warp] = incl;
+            __syncthreads();
+            unsigned before = 0, total = 0;
+            for (int i = 0; i < (IPB_RS_THREADS >> 5); ++i) { const unsigned t = sh.wt[i]; total += t; if (i < warp) before += t; }
+            base = run + before + incl - cnt;
+            run += total;
+        }
+        sh.mw[tid] = m; sh.mb[tid] = base; sh.mp[tid] = p;
+        __syncthreads();
+#pragma unroll 1
+        for (int k = 0; k < 32; k += IPB_RS_BATCH) {
+            unsigned word[IPB_RS_BATCH], raw[IPB_RS_BATCH], any = 0;
+#pragma unroll
+            for (int u = 0; u < IPB_RS_BATCH; ++u) { word[u] = sh.mw[warp * 32 + k + u]; any |= word[u]; }
+            if (!any) continue;                                              // warp-uniform
+#pragma unroll
+            for (int u = 0; u < IPB_RS_BATCH; ++u) {
+                raw[u] = 0u;
+                if ((word[u] >> lane) & 1u) {
+                    const size_t a = (size_t)sh.mp[warp * 32 + k + u] + (size_t)lane;
+                    raw[u] = (SRC == IPB_SRC_U16) ? (unsigned)c.u16[a] : __float_as_uint(c.f32[a]);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < IPB_RS_BATCH; ++u)
+                if ((word[u] >> lane) & 1u)
+                    f(raw[u], NEED_POS ? sh.mb[warp * 32 + k + u] + (unsigned)__popc(word[u] & lt) : 0u);
+        }
+        __syncthreads();
     }
+    if (!NEED_POS) return 0u;
+    return run;
 }
 
 __device__ __forceinline__ double ipb_block_sum_d(double v, double* red) {
@@ -182,9 +204,84 @@ __device__ __forceinline__ unsigned long long ipb_block_sum_u64(unsigned long lo
     return t;
 }
 
-#define IPB_RS_LISTCAP 4096
-#define IPB_RS_COUNTSORT 512           // candidate lists up to this size are ranked by counting
-#define IPB_RS_RESERVE (16 * 1024)     // bytes of the dynamic store always left to the histogram
+// f(key) for every measured key: from the shared-memory key store when it holds the whole
+// region (slots of dropped pixels hold the sentinel), else by re-walking global memory.
+template <int SRC, typename F>
+__device__ __forceinline__ void ipb_rs_foreach_key(const IpbRsCtx& c, IpbRsWalkSh& sh, bool in_smem, unsigned n_slots,
+                                                   const unsigned* k32, const unsigned short* k16, F f) {
+    if (in_smem) {
+        if (SRC == IPB_SRC_U16) for (unsigned i = threadIdx.x; i < n_slots; i += blockDim.x) f((unsigned)k16[i]);
+        else for (unsigned i = threadIdx.x; i < n_slots; i += blockDim.x) { const unsigned k = k32[i]; if (k != IPB_RS_SENTINEL) f(k); }
+    } else {
+        ipb_rs_walk<SRC, false>(c, sh, [&](unsigned raw, unsigned) {
+            if (SRC == IPB_SRC_U16) f(raw);
+            else { const float v = __uint_as_float(raw); if (isfinite(v)) f(ipb_f32_key(v)); }
+        });
+    }
+}
+
+// Shared rank bookkeeping of the selection passes
+struct IpbRsSel {
+    unsigned long long rank[IPB_RS_MAXR];   // remaining rank inside its group
+    unsigned prefix[IPB_RS_MAXR];           // key' bits resolved so far
+    int group[IPB_RS_MAXR];
+    unsigned gprefix[IPB_RS_MAXR];
+    int gn;
+};
+
+// thread 0: distinct prefixes -> groups
+__device__ __forceinline__ void ipb_rs_regroup(IpbRsSel& s, int nr) {
+    int m = 0;
+    for (int r = 0; r < nr; ++r) {
+        int gg = -1;
+        for (int t = 0; t < m; ++t) if (s.gprefix[t] == s.prefix[r]) { gg = t; break; }
+        if (gg < 0) { s.gprefix[m] = s.prefix[r]; gg = m++; }
+        s.group[r] = gg;
+    }
+    s.gn = m > 0 ? m : 1;
+}
+
+// Warp-cooperative scan of `nrows` rows of 32 counters: finds, for every wanted rank, the
+// counter that holds it.  value(i) = counter i (0 beyond the end).  hit(r, i, rank_inside).
+template <typename V, typename HIT>
+__device__ __forceinline__ void ipb_rs_locate(unsigned nrows, const unsigned long long* want, int nr,
+                                              unsigned long long* red_u, V value, HIT hit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned rpw = (nrows + (unsigned)nwarps - 1u) / (unsigned)nwarps;
+    const unsigned row0 = (unsigned)warp * rpw;
+    unsigned row1 = row0 + rpw;
+    if (row1 > nrows) row1 = nrows;
+    unsigned long long band = 0;
+    for (unsigned row = row0; row < row1; ++row) band += value((row << 5) + (unsigned)lane);
+    band = ipb_warp_sum(band);
+    __syncthreads();
+    if (lane == 0) red_u[warp] = band;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int i = 0; i < warp; ++i) base += red_u[i];
+    bool mine = false;
+    for (int r = 0; r < nr; ++r) mine = mine || (want[r] >= base && want[r] < base + band);
+    if (mine) {                                                            // warp-uniform
+        unsigned long long run = base;
+        for (unsigned row = row0; row < row1; ++row) {
+            const unsigned i = (row << 5) + (unsigned)lane;
+            const unsigned v = value(i);
+            unsigned incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+            const unsigned rowtot = __shfl_sync(IPB_FULL, incl, 31);
+            for (int r = 0; r < nr; ++r) {
+                const unsigned long long kk = want[r];
+                if (kk >= run && kk < run + rowtot) {
+                    const unsigned off = (unsigned)(kk - run);
+                    if (off >= incl - v && off < incl) hit(r, i, off - (incl - v));
+                }
+            }
+            run += rowtot;
+        }
+    }
+    __syncthreads();
+}
 
 template <int SRC>
 __global__ void __launch_bounds__(IPB_RS_THREADS, 1)
@@ -195,16 +292,12 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
                    const float* __restrict__ bvals, IpbStatOut* __restrict__ out, int smem_bytes)
 {
     IPB_DYN_SMEM(unsigned, keystore);
-    __shared__ unsigned ghist[IPB_RS_MAXR][IPB_RS_BINS];   // generic (fallback) per-group histograms
+    __shared__ IpbRsWalkSh wsh;
     __shared__ double red_d[32];
     __shared__ unsigned long long red_u[32];
     __shared__ unsigned red_k[2][32];
-    __shared__ unsigned long long r_rank[IPB_RS_MAXR];   // remaining rank inside its group
-    __shared__ unsigned r_prefix[IPB_RS_MAXR];           // key' bits resolved so far (>> shift)
-    __shared__ int r_group[IPB_RS_MAXR];
-    __shared__ unsigned g_prefix[IPB_RS_MAXR];
-    __shared__ int g_n;
-    __shared__ unsigned n_stored, list_n;
+    __shared__ IpbRsSel sel;
+    __shared__ unsigned list_n;
 
     const IpbStatJob job = jobs[blockIdx.x];
     if (job.src != SRC) return;                          // mixed job lists: the other instantiation takes it
@@ -226,296 +319,281 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = (blockDim.x + 31) >> 5;
-    unsigned* k32 = keystore;
-    unsigned short* k16 = reinterpret_cast<unsigned short*>(keystore);
-    const int keysize = SRC == IPB_SRC_U16 ? 2 : 4;
-    const unsigned cap = (unsigned)((smem_bytes - IPB_RS_RESERVE) / keysize);
-    if (tid == 0) { n_stored = 0u; list_n = 0u; }
-    __syncthreads();
-
-    // ---- gather: n, area, key range (F32: also sum); keys compacted into shared memory
-    unsigned n_t = 0, area_t = 0;
-    double s_t = 0.0, s2_t = 0.0;
-    unsigned kmin_t = 0xffffffffu, kmax_t = 0u;
-    for (int r = warp; r < c.h; r += nwarps) {
-        for (int j0 = 0; j0 < c.wpr; j0 += IPB_RS_UNROLL) {
-            unsigned key[IPB_RS_UNROLL];
-            bool ok[IPB_RS_UNROLL];
-            ipb_rs_load_group<SRC>(c, r, j0, lane, key, ok, area_t);
-            unsigned vm[IPB_RS_UNROLL], tot = 0;
-#pragma unroll
-            for (int u = 0; u < IPB_RS_UNROLL; ++u) { vm[u] = __ballot_sync(IPB_FULL, ok[u]); tot += __popc(vm[u]); }
-            if (tot == 0) continue;                                  // warp-uniform
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&n_stored, tot);
-            base = __shfl_sync(IPB_FULL, base, 0);
-#pragma unroll
-            for (int u = 0; u < IPB_RS_UNROLL; ++u) {
-                if (ok[u]) {
-                    const unsigned pos = base + __popc(vm[u] & ((1u << lane) - 1u));
-                    if (pos < cap) { if (SRC == IPB_SRC_U16) k16[pos] = (unsigned short)key[u]; else k32[pos] = key[u]; }
-                    ++n_t;
-                    if (SRC == IPB_SRC_F32) { const double v = (double)ipb_key_f32(key[u]); s_t += v; s2_t += v * v; }
-                    kmin_t = key[u] < kmin_t ? key[u] : kmin_t;
-                    kmax_t = key[u] > kmax_t ? key[u] : kmax_t;
-                }
-                base += __popc(vm[u]);
-            }
-        }
-    }
-    const unsigned long long n = ipb_block_sum_u64((unsigned long long)n_t, red_u);
-    const unsigned long long area = ipb_block_sum_u64((unsigned long long)area_t, red_u);
-    kmin_t = ipb_warp_min(kmin_t); kmax_t = ipb_warp_max(kmax_t);
-    __syncthreads();
-    if (lane == 0) { red_k[0][warp] = kmin_t; red_k[1][warp] = kmax_t; }
-    __syncthreads();
-    unsigned kmin = 0xffffffffu, kmax = 0u;
-    for (int i = 0; i < nwarps; ++i) { kmin = red_k[0][i] < kmin ? red_k[0][i] : kmin; kmax = red_k[1][i] > kmax ? red_k[1][i] : kmax; }
-    const bool in_smem = n <= (unsigned long long)cap;
-
     const float fnan = __uint_as_float(0x7fc00000u);
-    if (n == 0) {
-        if (tid < nv) {
-            IpbStatOut o;
-            o.n = 0; o.area = area; o.sum = 0.0; o.ssd = 0.0; o.pad0 = 0.f;
-            o.vmin = fnan; o.vmax = fnan;
-            for (int i = 0; i < IPB_RS_MAXQ; ++i) o.q[i] = fnan;
-            out[job.out[tid]] = o;
+    const unsigned nwords = (unsigned)c.h * (unsigned)c.wpr;
+
+    // ---- region size (mask popcount): `area`, and the choice of the uint16 strategy
+    unsigned long long area;
+    {
+        unsigned cnt = 0;
+        for (unsigned wi = tid; wi < nwords; wi += blockDim.x) {
+            const unsigned r = wi / (unsigned)c.wpr, j = wi - r * (unsigned)c.wpr;
+            cnt += (unsigned)__popc(ipb_rs_mask_word(c, wi, r, j));
         }
-        return;
+        area = ipb_block_sum_u64((unsigned long long)cnt, red_u);
     }
 
-    // ---- ranks wanted
+    unsigned long long n = 0;
+    unsigned kmin = 0xffffffffu, kmax = 0u;     // key range of the sample
+    unsigned kbase = 0u;                        // sel.prefix is relative to this key
     IpbQIdx qi[IPB_RS_MAXQ];
     int nr = 0;
-    for (int i = 0; i < IPB_RS_MAXQ; ++i) {
-        qi[i].prev = qi[i].next = 0; qi[i].gamma = 0.f;
-        if (job.qkind[i] == IPB_QKIND_PCT) qi[i] = ipb_np_qidx_f32((long long)n, job.q32[i]);
-        else if (job.qkind[i] == IPB_QKIND_MEDIAN) {
-            if (n & 1ull) qi[i].prev = qi[i].next = (long long)(n >> 1);
-            else { qi[i].prev = (long long)(n >> 1) - 1; qi[i].next = (long long)(n >> 1); }
-        }
-        if (job.qkind[i] != IPB_QKIND_NONE) nr = 2 * (i + 1);
-    }
-    if (tid == 0) {
-        for (int i = 0; i < IPB_RS_MAXQ; ++i) {
-            r_rank[2 * i] = (unsigned long long)qi[i].prev; r_rank[2 * i + 1] = (unsigned long long)qi[i].next;
-            r_prefix[2 * i] = r_prefix[2 * i + 1] = 0u;
-            r_group[2 * i] = r_group[2 * i + 1] = 0;
-        }
-        g_prefix[0] = 0u; g_n = 1;
-    }
-    __syncthreads();
-
-    // ---- pass 1: one wide histogram (as many bins as the free part of the store allows)
-    const unsigned nn = (unsigned)(in_smem ? n : 0);
-    const unsigned range = kmax - kmin;
-    const int bits = range ? (32 - __clz((int)range)) : 0;
-    const unsigned key_words = in_smem ? (unsigned)(((size_t)n * keysize + 3) / 4) : 0u;
-    unsigned* whist = keystore + key_words;
-    const unsigned hb_cap = (unsigned)(smem_bytes / 4) - key_words;        // >= RESERVE/4 = 4096
-    int d1 = 31 - __clz((int)hb_cap);
-    if (d1 > 15) d1 = 15;
-    if (d1 > bits) d1 = bits;
-    const int rb = bits - d1;                                               // bits left after pass 1
-    const unsigned nb = 1u << d1;
-    for (unsigned i = tid; i < nb; i += blockDim.x) whist[i] = 0u;
-    __syncthreads();
-    ipb_rs_foreach_key<SRC>(c, in_smem, nn, k32, k16, [&](unsigned key) { atomicAdd(&whist[(key - kmin) >> rb], 1u); });
-    __syncthreads();
-    {
-        // warp-cooperative scan: warp w owns a contiguous band of 32-bin rows; lanes read
-        // consecutive bins (conflict-free).  Only the bands that contain a wanted rank are
-        // scanned row by row.
-        unsigned long long kk_l[IPB_RS_MAXR];
-        for (int r = 0; r < IPB_RS_MAXR; ++r) kk_l[r] = r_rank[r];
-        const unsigned rows = (nb + 31u) >> 5;
-        const unsigned rpw = (rows + (unsigned)nwarps - 1u) / (unsigned)nwarps;
-        const unsigned row0 = (unsigned)warp * rpw;
-        unsigned row1 = row0 + rpw;
-        if (row1 > rows) row1 = rows;
-        unsigned long long band = 0;
-        for (unsigned row = row0; row < row1; ++row) {
-            const unsigned b = (row << 5) + (unsigned)lane;
-            if (b < nb) band += whist[b];
-        }
-        band = ipb_warp_sum(band);
-        __syncthreads();
-        if (lane == 0) red_u[warp] = band;
-        __syncthreads();
-        unsigned long long base = 0;
-        for (int i = 0; i < warp; ++i) base += red_u[i];
-        bool mine = false;
-        for (int r = 0; r < nr; ++r) mine = mine || (kk_l[r] >= base && kk_l[r] < base + band);
-        if (mine) {                                                        // warp-uniform
-            unsigned long long run = base;
-            for (unsigned row = row0; row < row1; ++row) {
-                const unsigned b = (row << 5) + (unsigned)lane;
-                const unsigned v = b < nb ? whist[b] : 0u;
-                unsigned incl = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
-                const unsigned rowtot = __shfl_sync(IPB_FULL, incl, 31);
-                for (int r = 0; r < nr; ++r) {
-                    const unsigned long long kk = kk_l[r];
-                    if (kk >= run && kk < run + rowtot) {
-                        const unsigned off = (unsigned)(kk - run);
-                        if (off >= incl - v && off < incl) { r_prefix[r] = b; r_rank[r] = (unsigned long long)(off - (incl - v)); }
-                    }
-                }
-                run += rowtot;
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- sums.  U16: per view from the exact histogram (or the keys when bins are coarse);
-    //      F32: sum from the gather, squared deviations from the stored keys.
     double v_sum[IPB_RS_MAXV], v_ssd[IPB_RS_MAXV];
-    if (SRC == IPB_SRC_U16) {
-        for (int v = 0; v < nv; ++v) {
-            const float B = vB[v]; const int clip = vclip[v];
-            double s = 0.0;
-            if (rb == 0) { for (unsigned b = tid; b < nb; b += blockDim.x) { const unsigned cnt = whist[b]; if (cnt) s += (double)cnt * (double)ipb_rs_transform(B, clip, kmin + b); } }
-            else ipb_rs_foreach_key<SRC>(c, in_smem, nn, k32, k16, [&](unsigned key) { s += (double)ipb_rs_transform(B, clip, key); });
-            const double sum = ipb_block_sum_d(s, red_d);
-            const double mean = sum / (double)n;
-            double q = 0.0;
-            if (rb == 0) { for (unsigned b = tid; b < nb; b += blockDim.x) { const unsigned cnt = whist[b]; if (cnt) { const double d = (double)ipb_rs_transform(B, clip, kmin + b) - mean; q += (double)cnt * d * d; } } }
-            else ipb_rs_foreach_key<SRC>(c, in_smem, nn, k32, k16, [&](unsigned key) { const double d = (double)ipb_rs_transform(B, clip, key) - mean; q += d * d; });
-            v_sum[v] = sum;
-            v_ssd[v] = ipb_block_sum_d(q, red_d);
-        }
-    } else {
-        const double sum = ipb_block_sum_d(s_t, red_d);
-        double ssd;
-        if (in_smem) {
-            const double mean = sum / (double)n;
-            double q = 0.0;
-            for (unsigned i = tid; i < nn; i += blockDim.x) { const double d = (double)ipb_key_f32(k32[i]) - mean; q += d * d; }
-            ssd = ipb_block_sum_d(q, red_d);
-        } else {
-            const double sumsq = ipb_block_sum_d(s2_t, red_d);
-            ssd = sumsq - sum * (sum / (double)n);
-            if (!(ssd > 0.0)) ssd = 0.0;
-        }
-        v_sum[0] = sum; v_ssd[0] = ssd;
-    }
-
-    if (rb > 0 && nr > 0) {
-        // ---- regroup, then compact the few keys that share a wanted prefix
-        if (tid == 0) {
-            int m = 0;
-            for (int r = 0; r < nr; ++r) {
-                int gg = -1;
-                for (int t = 0; t < m; ++t) if (g_prefix[t] == r_prefix[r]) { gg = t; break; }
-                if (gg < 0) { g_prefix[m] = r_prefix[r]; gg = m++; }
-                r_group[r] = gg;
-            }
-            g_n = m > 0 ? m : 1;
-        }
-        __syncthreads();
-        const int ng = g_n;
-        unsigned gp[IPB_RS_MAXR];
-        for (int g = 0; g < IPB_RS_MAXR; ++g) gp[g] = g < ng ? g_prefix[g] : 0xffffffffu;
-        unsigned* list = whist;                                  // the wide histogram is no longer needed
-        const unsigned lowmask = (rb >= 32) ? 0xffffffffu : ((1u << rb) - 1u);
-        const bool packable = rb <= 28;
-        __syncthreads();
-        if (packable) {
-            ipb_rs_foreach_key<SRC>(c, in_smem, nn, k32, k16, [&](unsigned key) {
-                const unsigned kp = key - kmin, hi = kp >> rb;
 #pragma unroll
-                for (int g = 0; g < IPB_RS_MAXR; ++g) {
-                    if (hi == gp[g]) {
-                        const unsigned idx = atomicAdd(&list_n, 1u);
-                        if (idx < IPB_RS_LISTCAP) list[idx] = ((unsigned)g << 28) | (kp & lowmask);
-                    }
+    for (int v = 0; v < IPB_RS_MAXV; ++v) { v_sum[v] = 0.0; v_ssd[v] = 0.0; }
+    for (int i = 0; i < IPB_RS_MAXQ; ++i) { qi[i].prev = qi[i].next = 0; qi[i].gamma = 0.f; }
+
+    // ranks wanted for a sample of nn_ values -> sel (thread 0 writes, everyone syncs)
+    auto setup_ranks = [&](unsigned long long nn_) {
+        nr = 0;
+        for (int i = 0; i < IPB_RS_MAXQ; ++i) {
+            if (job.qkind[i] == IPB_QKIND_PCT) qi[i] = ipb_np_qidx_f32((long long)nn_, job.q32[i]);
+            else if (job.qkind[i] == IPB_QKIND_MEDIAN) {
+                if (nn_ & 1ull) qi[i].prev = qi[i].next = (long long)(nn_ >> 1);
+                else { qi[i].prev = (long long)(nn_ >> 1) - 1; qi[i].next = (long long)(nn_ >> 1); }
+            }
+            if (job.qkind[i] != IPB_QKIND_NONE) nr = 2 * (i + 1);
+        }
+        if (tid == 0) {
+            for (int i = 0; i < IPB_RS_MAXQ; ++i) {
+                sel.rank[2 * i] = (unsigned long long)qi[i].prev; sel.rank[2 * i + 1] = (unsigned long long)qi[i].next;
+                sel.prefix[2 * i] = sel.prefix[2 * i + 1] = 0u;
+                sel.group[2 * i] = sel.group[2 * i + 1] = 0;
+            }
+            sel.gprefix[0] = 0u; sel.gn = 1;
+        }
+        __syncthreads();
+    };
+    // block-wide min / max of per-thread key bounds
+    auto block_minmax = [&](unsigned lo_t, unsigned hi_t) {
+        lo_t = ipb_warp_min(lo_t); hi_t = ipb_warp_max(hi_t);
+        __syncthreads();
+        if (lane == 0) { red_k[0][warp] = lo_t; red_k[1][warp] = hi_t; }
+        __syncthreads();
+        for (int i = 0; i < nwarps; ++i) { kmin = red_k[0][i] < kmin ? red_k[0][i] : kmin; kmax = red_k[1][i] > kmax ? red_k[1][i] : kmax; }
+    };
+
+    if (SRC == IPB_SRC_U16 && area > 0 && area <= (unsigned long long)IPB_RS_PACKED_MAX) {
+        // ================= uint16 fast path: full-range histogram of packed 16-bit counters
+        unsigned* h16 = keystore;                                  // 32768 words = 65536 counters
+        for (unsigned i = tid; i < 32768u; i += blockDim.x) h16[i] = 0u;
+        __syncthreads();
+        ipb_rs_walk<SRC, false>(c, wsh, [&](unsigned raw, unsigned) { atomicAdd(&h16[raw >> 1], 1u << ((raw & 1u) << 4)); });
+        n = area;
+        setup_ranks(n);
+        // pass A: key range and per-view sums
+        unsigned lo_t = 0xffffffffu, hi_t = 0u;
+        double s[IPB_RS_MAXV];
+#pragma unroll
+        for (int v = 0; v < IPB_RS_MAXV; ++v) s[v] = 0.0;
+        for (unsigned i = tid; i < 32768u; i += blockDim.x) {
+            const unsigned w = h16[i];
+            if (!w) continue;
+            const unsigned lo = w & 0xffffu, hi = w >> 16, k0 = 2u * i;
+            const unsigned first = lo ? k0 : k0 + 1u, last = hi ? k0 + 1u : k0;
+            lo_t = first < lo_t ? first : lo_t;
+            hi_t = last > hi_t ? last : hi_t;
+#pragma unroll
+            for (int v = 0; v < IPB_RS_MAXV; ++v)
+                if (v < nv) s[v] += (double)lo * (double)ipb_rs_transform(vB[v], vclip[v], k0) +
+                                    (double)hi * (double)ipb_rs_transform(vB[v], vclip[v], k0 + 1u);
+        }
+        block_minmax(lo_t, hi_t);
+        for (int v = 0; v < nv; ++v) v_sum[v] = ipb_block_sum_d(s[v], red_d);
+        // pass B: squared deviations from the exact mean
+        double q[IPB_RS_MAXV], mean[IPB_RS_MAXV];
+#pragma unroll
+        for (int v = 0; v < IPB_RS_MAXV; ++v) { q[v] = 0.0; mean[v] = v_sum[v] / (double)n; }
+        for (unsigned i = tid; i < 32768u; i += blockDim.x) {
+            const unsigned w = h16[i];
+            if (!w) continue;
+            const unsigned lo = w & 0xffffu, hi = w >> 16, k0 = 2u * i;
+#pragma unroll
+            for (int v = 0; v < IPB_RS_MAXV; ++v)
+                if (v < nv) {
+                    const double d0 = (double)ipb_rs_transform(vB[v], vclip[v], k0) - mean[v];
+                    const double d1 = (double)ipb_rs_transform(vB[v], vclip[v], k0 + 1u) - mean[v];
+                    q[v] += (double)lo * d0 * d0 + (double)hi * d1 * d1;
+                }
+        }
+        for (int v = 0; v < nv; ++v) v_ssd[v] = ipb_block_sum_d(q[v], red_d);
+        // ranks: the word first, then the low / high counter inside the word
+        unsigned long long want[IPB_RS_MAXR];
+        for (int r = 0; r < IPB_RS_MAXR; ++r) want[r] = sel.rank[r];
+        ipb_rs_locate(1024u, want, nr, red_u,
+                      [&](unsigned i) { const unsigned w = h16[i]; return (w & 0xffffu) + (w >> 16); },
+                      [&](int r, unsigned i, unsigned inside) { sel.prefix[r] = 2u * i + (inside >= (h16[i] & 0xffffu) ? 1u : 0u); });
+        kbase = 0u;                                                // prefixes are absolute keys
+    } else {
+        // ================= keyed path (float32; uint16 regions above 65535 px)
+        unsigned* k32 = keystore;
+        unsigned short* k16 = reinterpret_cast<unsigned short*>(keystore);
+        const int keysize = SRC == IPB_SRC_U16 ? 2 : 4;
+        const unsigned cap = (unsigned)((smem_bytes - IPB_RS_RESERVE) / keysize);
+        const bool in_smem = area <= (unsigned long long)cap;
+        unsigned n_t = 0, lo_t = 0xffffffffu, hi_t = 0u;
+        double s_t = 0.0, s2_t = 0.0;
+        if (area > 0) {
+            ipb_rs_walk<SRC, true>(c, wsh, [&](unsigned raw, unsigned pos) {
+                unsigned key;
+                if (SRC == IPB_SRC_U16) key = raw;
+                else {
+                    const float v = __uint_as_float(raw);
+                    if (isfinite(v)) { key = ipb_f32_key(v); const double d = (double)v; s_t += d; s2_t += d * d; }
+                    else key = IPB_RS_SENTINEL;
+                }
+                if (in_smem) { if (SRC == IPB_SRC_U16) k16[pos] = (unsigned short)key; else k32[pos] = key; }
+                if (SRC == IPB_SRC_U16 || key != IPB_RS_SENTINEL) {
+                    ++n_t;
+                    lo_t = key < lo_t ? key : lo_t;
+                    hi_t = key > hi_t ? key : hi_t;
                 }
             });
         }
-        __syncthreads();
-        const unsigned m = list_n;
-        if (packable && m <= IPB_RS_LISTCAP) {
-            // order the candidate list (group in the top 4 bits, low key bits below); rank r is
-            // then a direct index into its group's segment
-            unsigned* sorted = list;
-            if (m <= IPB_RS_COUNTSORT) {
-                // small list: every thread places one element by counting (stable on index)
-                sorted = list + IPB_RS_LISTCAP / 2;
-                if ((unsigned)tid < m) {
-                    const unsigned a = list[tid];
-                    unsigned pos = 0;
-                    for (unsigned j = 0; j < m; ++j) { const unsigned b = list[j]; pos += (b < a || (b == a && j < (unsigned)tid)) ? 1u : 0u; }
-                    sorted[pos] = a;
-                }
-                __syncthreads();
-            } else {
-                unsigned P = 1;
-                while (P < m) P <<= 1;
-                for (unsigned i = m + tid; i < P; i += blockDim.x) list[i] = 0xffffffffu;
-                __syncthreads();
-                for (unsigned k = 2; k <= P; k <<= 1) {
-                    for (unsigned j = k >> 1; j > 0; j >>= 1) {
-                        for (unsigned i = tid; i < P; i += blockDim.x) {
-                            const unsigned ixj = i ^ j;
-                            if (ixj > i) {
-                                const unsigned a = list[i], b = list[ixj];
-                                const bool up = (i & k) == 0;
-                                if ((a > b) == up) { list[i] = b; list[ixj] = a; }
-                            }
-                        }
-                        __syncthreads();
-                    }
-                }
+        n = ipb_block_sum_u64((unsigned long long)n_t, red_u);
+        if (n == 0) {
+            if (tid < nv) {
+                IpbStatOut o;
+                o.n = 0; o.area = area; o.sum = 0.0; o.ssd = 0.0; o.pad0 = 0.f;
+                o.vmin = fnan; o.vmax = fnan;
+                for (int i = 0; i < IPB_RS_MAXQ; ++i) o.q[i] = fnan;
+                out[job.out[tid]] = o;
             }
-            if (tid < nr) {
-                const int r = tid;
-                const unsigned g = (unsigned)r_group[r];
-                // first index of group g: binary search for (g << 28)
-                unsigned lo = 0, hi = m;
-                while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (sorted[mid] < (g << 28)) lo = mid + 1; else hi = mid; }
-                const unsigned ve = sorted[lo + (unsigned)r_rank[r]];
-                r_prefix[r] = (gp[g] << rb) | (ve & lowmask);                    // full key'
+            return;
+        }
+        block_minmax(lo_t, hi_t);
+        setup_ranks(n);
+        kbase = kmin;
+
+        // ---- pass 1: one wide histogram (as many bins as the free part of the store allows)
+        const unsigned n_slots = in_smem ? (unsigned)area : 0u;
+        const unsigned range = kmax - kmin;
+        const int bits = range ? (32 - __clz((int)range)) : 0;
+        const unsigned key_words = in_smem ? (unsigned)(((size_t)area * keysize + 3) / 4) : 0u;
+        unsigned* whist = keystore + key_words;
+        const unsigned hb_cap = (unsigned)(smem_bytes / 4) - key_words;        // >= RESERVE/4 words
+        int d1 = 31 - __clz((int)hb_cap);
+        if (d1 > 15) d1 = 15;
+        if (d1 > bits) d1 = bits;
+        const int rb = bits - d1;                                               // bits left after pass 1
+        const unsigned nb = 1u << d1;
+        for (unsigned i = tid; i < nb; i += blockDim.x) whist[i] = 0u;
+        __syncthreads();
+        ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) { atomicAdd(&whist[(key - kmin) >> rb], 1u); });
+        __syncthreads();
+        {
+            unsigned long long want[IPB_RS_MAXR];
+            for (int r = 0; r < IPB_RS_MAXR; ++r) want[r] = sel.rank[r];
+            ipb_rs_locate((nb + 31u) >> 5, want, nr, red_u,
+                          [&](unsigned i) { return i < nb ? whist[i] : 0u; },
+                          [&](int r, unsigned i, unsigned inside) { sel.prefix[r] = i; sel.rank[r] = (unsigned long long)inside; });
+        }
+
+        // ---- sums.  uint16: per view from the exact histogram (or the keys when bins are
+        //      coarse); float32: sum from the walk, squared deviations from the stored keys.
+        if (SRC == IPB_SRC_U16) {
+            for (int v = 0; v < nv; ++v) {
+                const float B = vB[v]; const int clip = vclip[v];
+                double s = 0.0;
+                if (rb == 0) { for (unsigned b = tid; b < nb; b += blockDim.x) { const unsigned cnt = whist[b]; if (cnt) s += (double)cnt * (double)ipb_rs_transform(B, clip, kmin + b); } }
+                else ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) { s += (double)ipb_rs_transform(B, clip, key); });
+                const double sum = ipb_block_sum_d(s, red_d);
+                const double mean = sum / (double)n;
+                double q = 0.0;
+                if (rb == 0) { for (unsigned b = tid; b < nb; b += blockDim.x) { const unsigned cnt = whist[b]; if (cnt) { const double d = (double)ipb_rs_transform(B, clip, kmin + b) - mean; q += (double)cnt * d * d; } } }
+                else ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) { const double d = (double)ipb_rs_transform(B, clip, key) - mean; q += d * d; });
+                v_sum[v] = sum;
+                v_ssd[v] = ipb_block_sum_d(q, red_d);
+            }
+        } else {
+            const double sum = ipb_block_sum_d(s_t, red_d);
+            double ssd;
+            if (in_smem) {
+                const double mean = sum / (double)n;
+                double q = 0.0;
+                for (unsigned i = tid; i < n_slots; i += blockDim.x) {
+                    const unsigned k = k32[i];
+                    if (k != IPB_RS_SENTINEL) { const double d = (double)ipb_key_f32(k) - mean; q += d * d; }
+                }
+                ssd = ipb_block_sum_d(q, red_d);
+            } else {
+                const double sumsq = ipb_block_sum_d(s2_t, red_d);
+                ssd = sumsq - sum * (sum / (double)n);
+            }
+            v_sum[0] = sum; v_ssd[0] = ssd;
+        }
+
+        if (rb > 0 && nr > 0) {
+            // ---- candidates: the few keys that share a wanted pass-1 bin
+            if (tid == 0) { ipb_rs_regroup(sel, nr); list_n = 0u; }
+            __syncthreads();
+            const int ng0 = sel.gn;
+            unsigned gp0[IPB_RS_MAXR];
+            for (int g = 0; g < IPB_RS_MAXR; ++g) gp0[g] = g < ng0 ? sel.gprefix[g] : 0xffffffffu;
+            unsigned* list = whist;                              // the wide histogram is no longer needed
+            unsigned* ghist = whist + IPB_RS_LISTCAP;            // [group][256] digit histograms
+            const unsigned lowmask = (rb >= 32) ? 0xffffffffu : ((1u << rb) - 1u);
+            const bool packable = rb <= 28;
+            __syncthreads();
+            if (packable) {
+                ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) {
+                    const unsigned kp = key - kmin, hi = kp >> rb;
+#pragma unroll
+                    for (int g = 0; g < IPB_RS_MAXR; ++g) {
+                        if (hi == gp0[g]) {
+                            const unsigned idx = atomicAdd(&list_n, 1u);
+                            if (idx < IPB_RS_LISTCAP) list[idx] = ((unsigned)g << 28) | (kp & lowmask);
+                        }
+                    }
+                });
             }
             __syncthreads();
-        } else {
-            // ---- generic fallback: 8-bit digit passes with one histogram per distinct prefix
+            const unsigned m = list_n;
+            const bool use_list = packable && m <= IPB_RS_LISTCAP;
+            // ---- 8-bit digit passes over the candidates (or over every key), one histogram
+            //      per distinct prefix, until all bits are resolved
             int shift_prev = rb;
             do {
                 const int shift = shift_prev > IPB_RS_DIGIT ? shift_prev - IPB_RS_DIGIT : 0;
                 const unsigned dmask = (1u << (shift_prev - shift)) - 1u;
-                const int ngc = g_n;
-                for (int i = tid; i < ngc * IPB_RS_BINS; i += blockDim.x) (&ghist[0][0])[i] = 0u;
+                const int ngc = sel.gn;
+                for (int i = tid; i < ngc * IPB_RS_BINS; i += blockDim.x) ghist[i] = 0u;
                 __syncthreads();
-                ipb_rs_foreach_key<SRC>(c, in_smem, nn, k32, k16, [&](unsigned key) {
-                    const unsigned kp = key - kmin;
+                auto count = [&](unsigned kp) {
                     const unsigned hi = shift_prev >= 32 ? 0u : (kp >> shift_prev);
                     const unsigned dg = (kp >> shift) & dmask;
                     for (int g = 0; g < ngc; ++g)
-                        if (hi == g_prefix[g]) atomicAdd(&ghist[g][dg], 1u);
-                });
+                        if (hi == sel.gprefix[g]) atomicAdd(&ghist[g * IPB_RS_BINS + dg], 1u);
+                };
+                if (use_list) {
+                    for (unsigned i = tid; i < m; i += blockDim.x) {
+                        const unsigned e = list[i];
+                        count((gp0[e >> 28] << rb) | (e & lowmask));
+                    }
+                } else {
+                    ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) { count(key - kmin); });
+                }
                 __syncthreads();
                 if (warp < ngc) {
                     const int g = warp;
                     unsigned cnt[IPB_RS_BINS / 32], mine = 0;
 #pragma unroll
-                    for (int b = 0; b < IPB_RS_BINS / 32; ++b) { cnt[b] = ghist[g][lane * (IPB_RS_BINS / 32) + b]; mine += cnt[b]; }
+                    for (int b = 0; b < IPB_RS_BINS / 32; ++b) { cnt[b] = ghist[g * IPB_RS_BINS + lane * (IPB_RS_BINS / 32) + b]; mine += cnt[b]; }
                     unsigned long long incl = mine;
 #pragma unroll
                     for (int o2 = 1; o2 < 32; o2 <<= 1) { unsigned long long t = __shfl_up_sync(IPB_FULL, incl, o2); if (lane >= o2) incl += t; }
                     const unsigned long long lo = incl - mine, hi = incl;
                     for (int r = 0; r < nr; ++r) {
-                        if (r_group[r] != g) continue;
-                        const unsigned long long kk = r_rank[r];
+                        if (sel.group[r] != g) continue;
+                        const unsigned long long kk = sel.rank[r];
                         __syncwarp();
                         if (kk >= lo && kk < hi) {
                             unsigned long long acc = lo;
 #pragma unroll
                             for (int b = 0; b < IPB_RS_BINS / 32; ++b) {
                                 if (kk >= acc && kk < acc + cnt[b]) {
-                                    r_prefix[r] = (g_prefix[g] << (shift_prev - shift)) | (unsigned)(lane * (IPB_RS_BINS / 32) + b);
-                                    r_rank[r] = kk - acc;
+                                    sel.prefix[r] = (sel.gprefix[g] << (shift_prev - shift)) | (unsigned)(lane * (IPB_RS_BINS / 32) + b);
+                                    sel.rank[r] = kk - acc;
                                 }
                                 acc += cnt[b];
                             }
@@ -524,16 +602,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
                     }
                 }
                 __syncthreads();
-                if (tid == 0) {
-                    int mm = 0;
-                    for (int r = 0; r < nr; ++r) {
-                        int gg = -1;
-                        for (int t = 0; t < mm; ++t) if (g_prefix[t] == r_prefix[r]) { gg = t; break; }
-                        if (gg < 0) { g_prefix[mm] = r_prefix[r]; gg = mm++; }
-                        r_group[r] = gg;
-                    }
-                    g_n = mm > 0 ? mm : 1;
-                }
+                if (tid == 0) ipb_rs_regroup(sel, nr);
                 __syncthreads();
                 shift_prev = shift;
             } while (shift_prev > 0);
@@ -547,7 +616,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         o.n = n; o.area = area; o.sum = v_sum[v]; o.ssd = v_ssd[v] > 0.0 ? v_ssd[v] : 0.0; o.pad0 = 0.f;
         float rv[IPB_RS_MAXR];
         for (int r = 0; r < IPB_RS_MAXR; ++r) {
-            const unsigned key = kmin + r_prefix[r];
+            const unsigned key = kbase + sel.prefix[r];
             rv[r] = (SRC == IPB_SRC_U16) ? ipb_rs_transform(B, clip, key) : ipb_key_f32(key);
         }
         o.vmin = (SRC == IPB_SRC_U16) ? ipb_rs_transform(B, clip, kmin) : ipb_key_f32(kmin);
