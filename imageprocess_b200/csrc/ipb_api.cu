@@ -15,6 +15,7 @@
 #include "ipb_roistats.cuh"
 #include "ipb_fret.cuh"
 #include "ipb_fa.cuh"
+#include "ipb_morph.cuh"
 
 static thread_local char g_ipb_err[512] = "";
 
@@ -207,7 +208,7 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int unif
 {
     if (n_jobs <= 0) return IPB_OK;
     IPB_REQUIRE(regions && jobs && mask_pool && out && H > 0 && W > 0, "ipb_region_stats: bad argument");
-    IPB_REQUIRE(uniform_src >= -1 && uniform_src <= 1, "ipb_region_stats: bad uniform_src %d", uniform_src);
+    IPB_REQUIRE(uniform_src >= -1 && uniform_src <= IPB_SRC_RATIO, "ipb_region_stats: bad uniform_src %d", uniform_src);
     int rc = IPB_OK;
     // uniform_src = -1: the job list may mix sources; each instantiation skips the other's jobs
     // (a source whose buffer is NULL is not launched at all)
@@ -221,6 +222,12 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int unif
         IPB_REQUIRE(images, "ipb_region_stats: float32 jobs need images");
         rc = ipb_launch_region_stats<IPB_SRC_F32>(regions, jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
                                                   planes, images, bvals, out, stream);
+        if (rc) return rc;
+    }
+    if (uniform_src == IPB_SRC_RATIO || (uniform_src < 0 && images && bvals)) {
+        IPB_REQUIRE(images && bvals, "ipb_region_stats: ratio jobs need images and parameters");
+        rc = ipb_launch_region_stats<IPB_SRC_RATIO>(regions, jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
+                                                    planes, images, bvals, out, stream);
     }
     return rc;
 }
@@ -285,6 +292,78 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
     return ipb_check_launch("ipb_fa labelling");
 }
 
+// ---------------------------------------------------------------- morphology / moments / previews
+int ipb_region_dilate(const void* regions, int n_regions, int max_w, int max_h, const uint32_t* in_pool,
+                      int invert, const uint8_t* gmax_host, int R, uint8_t* g_scratch, const int64_t* g_off,
+                      const uint32_t* and_pool, const uint32_t* andnot_pool, uint32_t* out_pool, void* stream)
+{
+    if (n_regions <= 0 || max_w <= 0 || max_h <= 0) return IPB_OK;
+    IPB_REQUIRE(n_regions <= 65535, "ipb_region_dilate: n_regions %d out of range", n_regions);
+    IPB_REQUIRE(regions && in_pool && gmax_host && g_scratch && g_off && out_pool, "ipb_region_dilate: null pointer");
+    IPB_REQUIRE(R >= 0 && R <= IPB_MORPH_MAXR, "ipb_region_dilate: radius %d not in 0..%d", R, IPB_MORPH_MAXR);
+    IpbSpan span;
+    memset(&span, 0, sizeof(span));
+    span.R = R;
+    for (int i = 0; i <= R; ++i) {
+        IPB_REQUIRE(gmax_host[i] <= IPB_MORPH_MAXR, "ipb_region_dilate: gmax[%d] too large", i);
+        span.gmax[i] = gmax_host[i];
+    }
+    IPB_LAUNCH(ipb_k_morph_coldist, dim3(ipb_div_up(max_w, 128), (unsigned)n_regions), dim3(128), 0, stream,
+               (const IpbRegion*)regions, in_pool, invert, (const long long*)g_off, g_scratch);
+    int rc = ipb_check_launch("ipb_k_morph_coldist");
+    if (rc) return rc;
+    IPB_LAUNCH(ipb_k_morph_rowtest, dim3(ipb_div_up(max_h, 8), (unsigned)n_regions), dim3(256), 0, stream,
+               (const IpbRegion*)regions, (const long long*)g_off, (const unsigned char*)g_scratch, span,
+               and_pool, andnot_pool, out_pool);
+    return ipb_check_launch("ipb_k_morph_rowtest");
+}
+
+int ipb_region_moments(const void* regions, int n_regions, const uint32_t* mask_pool, uint64_t* out, void* stream)
+{
+    if (n_regions <= 0) return IPB_OK;
+    IPB_REQUIRE(regions && mask_pool && out, "ipb_region_moments: null pointer");
+    IPB_LAUNCH(ipb_k_region_moments, dim3(n_regions), dim3(256), 0, stream, (const IpbRegion*)regions, mask_pool,
+               (unsigned long long*)out);
+    return ipb_check_launch("ipb_k_region_moments");
+}
+
+int ipb_preview_u16(const float* images, int64_t px_per_image, int n_images, const float* lohi,
+                    uint16_t* out, void* stream)
+{
+    if (n_images <= 0 || px_per_image <= 0) return IPB_OK;
+    IPB_REQUIRE(images && lohi && out, "ipb_preview_u16: null pointer");
+    long long blocks = (px_per_image * n_images + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    IPB_LAUNCH(ipb_k_preview_u16, dim3((unsigned)blocks), dim3(256), 0, stream, images, (long long)px_per_image,
+               n_images, lohi, out);
+    return ipb_check_launch("ipb_k_preview_u16");
+}
+
+int ipb_crop_normalize(const void* jobs, int n_jobs, int64_t max_px, const uint16_t* planes, int H, int W,
+                       const float* params, float inv_gamma, const void* regions, const uint32_t* mask_pool,
+                       float* out_norm, uint16_t* out16, void* stream)
+{
+    if (n_jobs <= 0 || max_px <= 0) return IPB_OK;
+    IPB_REQUIRE(n_jobs <= 65535, "ipb_crop_normalize: n_jobs %d out of range", n_jobs);
+    IPB_REQUIRE(jobs && planes && params && (out_norm || out16), "ipb_crop_normalize: null pointer");
+    long long bx = (max_px + 255) / 256;
+    if (bx > 64) bx = 64;
+    IPB_LAUNCH(ipb_k_crop_normalize, dim3((unsigned)bx, (unsigned)n_jobs), dim3(256), 0, stream,
+               (const IpbCropJob*)jobs, planes, H, W, params, inv_gamma, (const IpbRegion*)regions, mask_pool,
+               out_norm, out16);
+    return ipb_check_launch("ipb_k_crop_normalize");
+}
+
+int ipb_eps_from_stat(const void* stat_out, const int32_t* row_of_frame, int n_frames, float eps_abs,
+                      float* fparams, void* stream)
+{
+    if (n_frames <= 0) return IPB_OK;
+    IPB_REQUIRE(stat_out && row_of_frame && fparams, "ipb_eps_from_stat: null pointer");
+    IPB_LAUNCH(ipb_k_eps_from_stat, dim3(ipb_div_up(n_frames, 128)), dim3(128), 0, stream,
+               (const IpbStatOut*)stat_out, row_of_frame, n_frames, eps_abs, fparams);
+    return ipb_check_launch("ipb_k_eps_from_stat");
+}
+
 int ipb_sizeof(int what)
 {
     switch (what) {
@@ -297,6 +376,7 @@ int ipb_sizeof(int what)
         case 6: return (int)sizeof(IpbFretCfg);
         case 7: return (int)sizeof(IpbCrop);
         case 8: return (int)sizeof(IpbComp);
+        case 9: return (int)sizeof(IpbCropJob);
         default: return -1;
     }
 }

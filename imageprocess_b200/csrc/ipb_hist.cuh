@@ -32,7 +32,10 @@ struct IpbHistJob {
     int k;            // stride for the strided patterns
     int mask_frame;   // frame index into the union bitmask (masked patterns)
     int moments;      // != 0: also accumulate sum / sumsq of ALL pixels of the plane
-    int pad0, pad1, pad2;
+    int excl_plane1;  // 1 + index of a second plane for the saturation filter, 0 = none
+    int sat_min;      // > 0: drop pixels whose value, or the second plane's, is >= sat_min
+                      //      (Nesprin2 saturation -> NaN -> np.isfinite filter, 1415-1421,435)
+    int pad2;
 };
 
 // out_stats[job] = { n_selected, sum_all, sumsq_all, reserved }
@@ -52,10 +55,12 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
     __syncthreads();
 
     const unsigned short* img = planes + (size_t)job.plane * H * W;
+    const unsigned sat_min = job.sat_min > 0 ? (unsigned)job.sat_min : 0xffffffffu;
+    const unsigned short* img2 = (job.sat_min > 0 && job.excl_plane1 > 0) ? planes + (size_t)(job.excl_plane1 - 1) * H * W : nullptr;
     const unsigned* ubits = (job.pattern == IPB_PAT_MASKED) ? union_bits + (size_t)job.mask_frame * H * union_wpr : nullptr;
     unsigned long long s1 = 0, s2 = 0, nsel = 0;
     const int k = job.k > 0 ? job.k : 1;
-    const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0);
+    const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0) && ((((size_t)img2) & 15) == 0);
 
 #define IPB_HIST_COUNT(v)                                      \
     do {                                                       \
@@ -75,6 +80,9 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
                 if (job.pattern == IPB_PAT_STRIDE2D && !job.moments && (y % k) != 0) continue;
                 const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + x0));
                 const unsigned w[4] = {q.x, q.y, q.z, q.w};
+                uint4 q2 = make_uint4(0, 0, 0, 0);
+                if (img2) q2 = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + x0));
+                const unsigned w2[4] = {q2.x, q2.y, q2.z, q2.w};
                 unsigned sel = 0;                                     // bit i: pixel x0+i selected
                 if (job.pattern == IPB_PAT_FULL) sel = 0xffu;
                 else if (job.pattern == IPB_PAT_STRIDE1D) {
@@ -92,8 +100,9 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                    const unsigned o = (t & 1) ? (w2[t >> 1] >> 16) : (w2[t >> 1] & 0xffffu);
                     if (job.moments) { s1 += v; s2 += (unsigned long long)v * v; }
-                    if ((sel >> t) & 1u) IPB_HIST_COUNT(v);
+                    if (((sel >> t) & 1u) && v < sat_min && o < sat_min) IPB_HIST_COUNT(v);
                 }
             }
         } else {
@@ -108,7 +117,8 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
                 else if (job.pattern == IPB_PAT_STRIDE2D) sel = (y % k) == 0 && (x % k) == 0;
                 else if (job.pattern == IPB_PAT_MASKED) sel = (ubits[(size_t)y * union_wpr + (x >> 5)] >> (x & 31)) & 1u;
                 else sel = false;
-                if (sel) IPB_HIST_COUNT(v);
+                if (sel && img2 && (unsigned)img2[(size_t)y * W + x] >= sat_min) sel = false;
+                if (sel && v < sat_min) IPB_HIST_COUNT(v);
             }
         }
     }

@@ -15,6 +15,12 @@
 //                selection; each view gets its own output row.
 //   IPB_SRC_F32  value = a float32 image pixel (ratio image); non-finite values are
 //                dropped like the reference's np.isfinite filter; key = ordered-uint32.
+//   IPB_SRC_RATIO value = (eff(N - bg_n) + eps) / (eff(D - bg_d) + eps), eff = max(., 0) when
+//                clip_neg, NaN above clip_max: the per-ROI ratio Nesprin2 re-derives after its
+//                annulus background (Nesprin2_FRET_Builder.py:1528-1535) from the corrected
+//                channel images N = images[plane], D = images[clip_neg[0]]; the six float
+//                parameters {bg_n, bg_d, eps, clip_neg, clip_on, clip_max} sit at
+//                bvals[bidx[0]].  Otherwise handled like IPB_SRC_F32.
 //
 // One CTA (1024 threads, one per SM) per job.
 //   walk     the region's mask words are taken 1024 at a time: every thread fetches one
@@ -43,6 +49,7 @@
 
 #define IPB_SRC_U16 0
 #define IPB_SRC_F32 1
+#define IPB_SRC_RATIO 2     // float32 ratio re-derived per pixel from two float32 images (Nesprin2 annulus)
 #define IPB_RS_THREADS 1024
 #define IPB_RS_MAXQ 3
 #define IPB_RS_MAXR (2 * IPB_RS_MAXQ)
@@ -96,7 +103,19 @@ struct IpbRsCtx {
     const unsigned* mask; const unsigned* androw0; int and_wpr;
     int x0, y0, w, h, wpr;
     const unsigned short* u16; const float* f32; int W;
+    const float* f32b; float rp[6];      // IPB_SRC_RATIO: second image and its parameters
 };
+
+// np.maximum(x, 0.0) semantics (NaN propagates)
+__device__ __forceinline__ float ipb_np_max0(float x) { return (x != x) ? x : (x > 0.0f ? x : 0.0f); }
+
+__device__ __forceinline__ float ipb_rs_ratio(const IpbRsCtx& c, float nv, float dv) {
+    float n = __fsub_rn(nv, c.rp[0]), d = __fsub_rn(dv, c.rp[1]);
+    if (c.rp[3] != 0.0f) { n = ipb_np_max0(n); d = ipb_np_max0(d); }
+    float r = __fdiv_rn(__fadd_rn(n, c.rp[2]), __fadd_rn(d, c.rp[2]));
+    if (c.rp[4] != 0.0f && r > c.rp[5]) r = __uint_as_float(0x7fc00000u);
+    return r;
+}
 
 struct IpbRsWalkSh {          // shared staging of one 1024-word chunk of the walk
     unsigned mw[IPB_RS_THREADS];    // mask word
@@ -167,7 +186,9 @@ __device__ __forceinline__ unsigned ipb_rs_walk(const IpbRsCtx& c, IpbRsWalkSh& 
                 raw[u] = 0u;
                 if ((word[u] >> lane) & 1u) {
                     const size_t a = (size_t)sh.mp[warp * 32 + k + u] + (size_t)lane;
-                    raw[u] = (SRC == IPB_SRC_U16) ? (unsigned)c.u16[a] : __float_as_uint(c.f32[a]);
+                    if (SRC == IPB_SRC_U16) raw[u] = (unsigned)c.u16[a];
+                    else if (SRC == IPB_SRC_F32) raw[u] = __float_as_uint(c.f32[a]);
+                    else raw[u] = __float_as_uint(ipb_rs_ratio(c, c.f32[a], c.f32b[a]));
                 }
             }
 #pragma unroll
@@ -310,6 +331,13 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     c.W = W;
     c.u16 = planes ? planes + (size_t)job.plane * H * W : nullptr;
     c.f32 = images ? images + (size_t)job.plane * H * W : nullptr;
+    c.f32b = nullptr;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) c.rp[i] = 0.0f;
+    if (SRC == IPB_SRC_RATIO) {
+        c.f32b = images + (size_t)job.clip_neg[0] * H * W;
+        if (bvals && job.bidx[0] >= 0) { for (int i = 0; i < 6; ++i) c.rp[i] = bvals[job.bidx[0] + i]; }
+    }
     const int nv = (SRC == IPB_SRC_U16) ? (job.n_views < 1 ? 1 : (job.n_views > IPB_RS_MAXV ? IPB_RS_MAXV : job.n_views)) : 1;
     float vB[IPB_RS_MAXV]; int vclip[IPB_RS_MAXV];
 #pragma unroll

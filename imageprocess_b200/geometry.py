@@ -32,9 +32,10 @@ def _clip_rect(x0, y0, x1, y1, w, h):
     return (x0, y0, x1, y1)
 
 
-def mpl_spec(poly, grid_wh, org=(0, 0), frame=0, store_full=False):
+def mpl_spec(poly, grid_wh, org=(0, 0), frame=0, store_full=False, pad=0):
     """Spec for rasterize_polygon(poly, (h, w)) -- reference Fluor_INT.py:398-403.  The rule
-    is evaluated on the vertex bbox padded by one pixel; outside it no pixel can be inside."""
+    is evaluated on the vertex bbox padded by one pixel; outside it no pixel can be inside.
+    pad > 0 stores the mask in a rect grown by `pad` pixels (room for later dilations)."""
     P = np.ascontiguousarray(np.asarray(poly, dtype=np.float64))
     w, h = int(grid_wh[0]), int(grid_wh[1])
     if P.ndim != 2 or P.shape[0] < 3 or not np.isfinite(P).all():
@@ -44,7 +45,12 @@ def mpl_spec(poly, grid_wh, org=(0, 0), frame=0, store_full=False):
     ymin, ymax = P[:, 1].min(), P[:, 1].max()
     e = _clip_rect(math.floor(xmin) - 1, math.floor(ymin), math.ceil(xmax) + 2,
                    math.ceil(ymax) + 1, w, h)
-    return RoiSpec(P, (w, h), org, frame, e, (0, 0, w, h) if store_full else e)
+    sr = e
+    if store_full:
+        sr = (0, 0, w, h)
+    elif pad > 0 and e[2] > e[0] and e[3] > e[1]:
+        sr = _clip_rect(e[0] - pad, e[1] - pad, e[2] + pad, e[3] + pad, w, h)
+    return RoiSpec(P, (w, h), org, frame, e, sr)
 
 
 def sk_spec(r, c, shape_hw, org=(0, 0), frame=0):

@@ -4,6 +4,8 @@
 and torch-backed memory.  (The CPU test tier injects the emulated build of the same kernel
 sources and a numpy memory backend; see tests/emu/.)
 """
+import math
+
 import numpy as np
 
 from . import geometry as geo
@@ -38,7 +40,7 @@ class RoiMasks:
 # kernels launched by each C-ABI entry point (memsets not counted)
 KERNELS_PER_CALL = {"ipb_fa_segment": 14, "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
                     "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
-                    "ipb_fret_pixels": 1, "ipb_region_stats": 1}
+                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_region_dilate": 2}
 
 
 class Engine:
@@ -98,12 +100,12 @@ class Engine:
 
 # ---------------------------------------------------------------------- struct mirrors
 PAT_FULL, PAT_STRIDE1D, PAT_STRIDE2D, PAT_MASKED, PAT_MASKED_STRIDE = 0, 1, 2, 3, 4
-SRC_U16, SRC_F32 = 0, 1
+SRC_U16, SRC_F32, SRC_RATIO = 0, 1, 2
 QK_NONE, QK_PCT, QK_MEDIAN = 0, 1, 2
 FP_BD, FP_BA, FP_EPS, FP_BAO, FP_STRIDE = 0, 1, 2, 3, 4
 
 HIST_JOB = np.dtype([("plane", "i4"), ("pattern", "i4"), ("k", "i4"), ("mask_frame", "i4"),
-                     ("moments", "i4"), ("pad", "i4", 3)])
+                     ("moments", "i4"), ("excl_plane1", "i4"), ("sat_min", "i4"), ("pad", "i4")])
 Q_JOB = np.dtype([("hist", "i4"), ("q32", "f4"), ("pad", "i4", 2)])
 Q_OUT = np.dtype([("prev", "i4"), ("next", "i4"), ("gamma", "f4"), ("value", "f4"), ("n", "u8")])
 REGION = np.dtype([("mask_off", "i8"), ("x0", "i4"), ("y0", "i4"), ("w", "i4"), ("h", "i4"),
@@ -121,7 +123,9 @@ CROP = np.dtype([("bit_off", "i8"), ("pix_off", "i8"), ("row_off", "i8"), ("mask
                  ("ox", "i4"), ("oy", "i4"),
                  ("w", "i4"), ("h", "i4"), ("wpr", "i4"), ("plane", "i4"), ("frame", "i4"), ("pad0", "i4")])
 COMP = np.dtype([("sum_i", "u8"), ("sum_y", "u8"), ("sum_x", "u8"), ("area", "u4"), ("crop", "i4")])
-_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG, CROP, COMP]
+CROP_JOB = np.dtype([("plane", "i4"), ("x0", "i4"), ("y0", "i4"), ("w", "i4"), ("h", "i4"), ("region", "i4"),
+                     ("out_off", "i8")])
+_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG, CROP, COMP, CROP_JOB]
 
 
 def q32_of(p):
@@ -308,3 +312,77 @@ def _engine_fa_segment(self, rm, crops, total_px, total_rows, planes, H, W, fa_p
 
 
 Engine.fa_segment = _engine_fa_segment
+
+
+# ---------------------------------------------------------------------- morphology / moments / previews
+def ball_gmax(d2max):
+    """gmax table of the Euclidean ball dx^2 + dy^2 <= d2max (integers)."""
+    R = int(math.isqrt(int(d2max)))
+    return np.array([math.isqrt(int(d2max) - dx * dx) for dx in range(R + 1)], dtype=np.uint8), R
+
+
+def square_gmax(p):
+    return np.full(int(p) + 1, int(p), dtype=np.uint8), int(p)
+
+
+def rim_d2max(rim_px):
+    """Largest integer d2 with sqrt(d2) <= rim_px as numpy evaluates `dist_in <= rim_px` on the
+    float64 EDT (reference Nesprin2_FRET_Builder.py:412-413); rim_px may be fractional."""
+    r = float(rim_px)
+    d2 = int(math.floor(r * r)) + 2
+    while d2 > 0 and not (math.sqrt(d2) <= r):
+        d2 -= 1
+    return d2
+
+
+def _engine_region_dilate(self, regions, in_pool, gmax, R, invert=False, and_pool=None, andnot_pool=None,
+                          out_pool=None, d_regions=None):
+    """Dilates every region mask (REGION rows; all pools share mask_off).  Returns the out pool."""
+    mem = self.mem
+    regions = np.ascontiguousarray(regions, dtype=REGION)
+    n = regions.shape[0]
+    if out_pool is None:
+        out_pool = mem.empty(in_pool.shape, np.uint32)
+    if n == 0:
+        return out_pool
+    w = regions["w"].astype(np.int64)
+    h = regions["h"].astype(np.int64)
+    g_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(w * h, out=g_off[1:])
+    d_r = d_regions if d_regions is not None else mem.from_host(regions)
+    d_goff = mem.from_host(g_off)
+    g = mem.empty(max(int(g_off[-1]), 1), np.uint8)
+    gm = np.ascontiguousarray(gmax, dtype=np.uint8)
+    p = lambda b: b.ptr if b is not None else None
+    self.call("ipb_region_dilate", d_r.ptr, n, int(w.max()), int(h.max()), in_pool.ptr, int(bool(invert)),
+              gm.ctypes.data, int(R), g.ptr, d_goff.ptr, p(and_pool), p(andnot_pool), out_pool.ptr, mem.stream)
+    out_pool._keep = (d_r, d_goff, g)
+    return out_pool
+
+
+def _engine_region_moments(self, regions, mask_pool):
+    """Exact integer sums per region: columns n, sx, sy, sxx, syy, sxy (uint64, frame coords)."""
+    mem = self.mem
+    regions = np.ascontiguousarray(regions, dtype=REGION)
+    n = regions.shape[0]
+    out = mem.empty((max(n, 1), 6), np.uint64)
+    if n:
+        d_r = mem.from_host(regions)
+        self.call("ipb_region_moments", d_r.ptr, n, mask_pool.ptr, out.ptr, mem.stream)
+        out._keep = d_r
+    return out.host()[:n]
+
+
+def _engine_preview_u16(self, images, px_per_image, n_images, lohi):
+    """images: device float32 [n_images][px]; lohi: host float32 [n_images][3] = lo, hi, den."""
+    mem = self.mem
+    out = mem.empty((n_images, px_per_image), np.uint16)
+    d_l = mem.from_host(np.ascontiguousarray(lohi, dtype=np.float32).reshape(-1))
+    self.call("ipb_preview_u16", images.ptr, int(px_per_image), int(n_images), d_l.ptr, out.ptr, mem.stream)
+    out._keep = d_l
+    return out
+
+
+Engine.region_dilate = _engine_region_dilate
+Engine.region_moments = _engine_region_moments
+Engine.preview_u16 = _engine_preview_u16

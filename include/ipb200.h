@@ -35,7 +35,7 @@ extern "C" {
 const char* ipb_last_error(void);
 int ipb_version(void);
 int ipb_is_emulated(void);      /* 1 only in the CPU test build of the same sources */
-int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg 7 Crop 8 Comp */
+int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg 7 Crop 8 Comp 9 CropJob */
 
 /* ------------------------------------------------------------------ ROI rasterisation
  * Replaces rasterize_polygon (INT/Fluor_INT.py:398-403; copies FRET/fret_ratio_builder.py:292,
@@ -77,7 +77,10 @@ typedef struct {
     int32_t k;            /* stride of the strided patterns */
     int32_t mask_frame;   /* frame index into union_bits (masked patterns) */
     int32_t moments;      /* != 0: also accumulate sum / sum of squares of ALL pixels */
-    int32_t pad[3];
+    int32_t excl_plane1;  /* 1 + index of a second plane for the saturation filter, 0 = none */
+    int32_t sat_min;      /* > 0: drop pixels whose value (or the second plane's) is >= sat_min:
+                             Nesprin2 saturation filter (Nesprin2_FRET_Builder.py:1415-1421) */
+    int32_t pad;
 } ipb_hist_job;
 /* hist: [n_jobs][65536] uint32;  stats: [n_jobs][4] uint64 = {n_selected, sum_all, sumsq_all, 0}
  * row_rank_scratch: [n_jobs][H] uint64, only for IPB_PAT_MASKED_STRIDE jobs.               */
@@ -138,6 +141,10 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W,
  * view gets its own output row.                                                            */
 #define IPB_SRC_U16 0            /* value = float32(raw) - B, optionally clipped at 0 */
 #define IPB_SRC_F32 1            /* value = float32 image pixel, non-finite dropped */
+#define IPB_SRC_RATIO 2          /* value = (eff(N-bg_n)+eps)/(eff(D-bg_d)+eps), N = images[plane],
+                                    D = images[clip_neg[0]], six float32 parameters {bg_n, bg_d, eps,
+                                    clip_neg, clip_on, clip_max} at bvals[bidx[0]]: the per-ROI ratio
+                                    after Nesprin2's annulus background (Nesprin2_FRET_Builder.py:1528-1535) */
 #define IPB_QKIND_NONE 0
 #define IPB_QKIND_PCT 1
 #define IPB_QKIND_MEDIAN 2
@@ -163,7 +170,7 @@ typedef struct {
     float q[3];
     float pad0;
 } ipb_stat_out;
-/* uniform_src: IPB_SRC_U16 / IPB_SRC_F32 when every job has that source (one launch), -1 for
+/* uniform_src: IPB_SRC_* when every job has that source (one launch), -1 for
  * a mixed list (one launch per source, each skipping the other's jobs).                    */
 int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int uniform_src,
                      const uint32_t* mask_pool, const uint32_t* and_bits, int and_wpr, int H, int W,
@@ -204,6 +211,38 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
                    uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
                    int32_t* labels, void* stream);
+
+/* ------------------------------------------------------------------ morphology, moments, previews
+ * ipb_region_dilate: dilation of region masks (ipb_region layout, all pools share mask_off)
+ * by a symmetric row-convex structuring element  gmax[|dx|] = largest |dy| covered at
+ * horizontal offset dx  (dx = 0..R, R <= 254; [host] table):
+ *   Euclidean ball dx^2+dy^2 <= d2max, source = ~mask (invert = 1), and_pool = mask:
+ *     make_inside_rim_mask, 0 < EDT <= rim_px (FRET/Nesprin2_FRET_Builder.py:409-414), exact;
+ *   full square gmax[dx] = p: scipy binary_dilation with ones((2p+1,2p+1)), outside = 0
+ *     (annulus_mask_from_poly, Nesprin2_FRET_Builder.py:416-427; ring = outer & ~inner via
+ *     andnot_pool).
+ * g_scratch: uint8, w*h bytes per region at g_off[region] ([dev] int64 offsets).
+ * out = dilate(src) & and_pool & ~andnot_pool (NULL pools are skipped).                     */
+int ipb_region_dilate(const void* regions, int n_regions, int max_w, int max_h, const uint32_t* in_pool,
+                      int invert, const uint8_t* gmax_host, int R, uint8_t* g_scratch, const int64_t* g_off,
+                      const uint32_t* and_pool, const uint32_t* andnot_pool, uint32_t* out_pool, void* stream);
+/* out[r][6] = {n, sum x, sum y, sum x^2, sum y^2, sum xy} of the set pixels (frame coordinates):
+ * morphology_from_polygon / second_moments (MOR_by_ROI.py:193-241).                         */
+int ipb_region_moments(const void* regions, int n_regions, const uint32_t* mask_pool, uint64_t* out, void* stream);
+/* 16-bit preview (INT/Fluor_INT.py:930-943, FRET/fret_ratio_builder.py:479-483):
+ * out = uint16(((clip(img, lo, hi) - lo) / den) * 65535), lohi[k] = {lo, hi, den} per image. */
+int ipb_preview_u16(const float* images, int64_t px_per_image, int n_images, const float* lohi,
+                    uint16_t* out, void* stream);
+/* ROI cropper chain (roi_channel_cropper.py:923-953): clip((crop-lo)/(hi-lo),0,1) * mask,
+ * ** inv_gamma, float32 and/or uint16 crops.  params[k] = {lo, hi-lo}.                      */
+typedef struct { int32_t plane, x0, y0, w, h, region; int64_t out_off; } ipb_crop_job;
+int ipb_crop_normalize(const void* jobs, int n_jobs, int64_t max_px, const uint16_t* planes, int H, int W,
+                       const float* params, float inv_gamma, const void* regions, const uint32_t* mask_pool,
+                       float* out_norm, uint16_t* out16, void* stream);
+/* fparams[f][2] = max(eps_abs, q[0] of float32 stat row row_of_frame[f]) (Nesprin2 pick_epsilon
+ * on a spectrally corrected denominator, Nesprin2_FRET_Builder.py:470-476,1484-1486).       */
+int ipb_eps_from_stat(const void* stat_out, const int32_t* row_of_frame, int n_frames, float eps_abs,
+                      float* fparams, void* stream);
 
 #ifdef __cplusplus
 }

@@ -428,3 +428,169 @@ def check_region_stats_two_views(eng):
 
 RASTER_CHECKS.append(check_region_stats_two_views)
 RASTER_CHECKS.append(check_combined_batch_shared_rois)
+
+
+# ====================================================================== Nesprin2 / morphology
+def check_rim_mask(eng):
+    """Inner rim 0 < EDT <= rim_px via ball dilation == scipy's exact EDT (oracle), several radii
+    including a fractional one; frame borders; holes."""
+    from imageprocess_b200 import ops
+    from imageprocess_b200.nesprin2 import bits_to_bool
+    rng = np.random.default_rng(3)
+    H, W = 90, 140
+    polys = [np.array([[5.0, 4.0], [60.0, 8.0], [70.0, 50.0], [30.0, 80.0], [2.0, 60.0]]),
+             np.array([[80.0, -5.0], [150.0, 20.0], [120.0, 95.0], [85.0, 60.0]]),        # crosses the border
+             np.array([[40.5, 30.5], [55.5, 30.5], [55.5, 45.5], [40.5, 45.5]])]
+    specs = [geo.mpl_spec(P, (W, H)) for P in polys]
+    rm = eng.rasterize(geo.RULE_MPL, specs, (H, W), 1, want_union=True)
+    union = rm.union_host()[0]
+    wpr = (W + 31) // 32
+    ureg = np.zeros(1, dtype=ops.REGION)
+    ureg["w"], ureg["h"], ureg["wpr"] = W, H, wpr
+    for rim_px in (1, 2, 5, 9, 3.7):
+        gm, R = ops.ball_gmax(ops.rim_d2max(rim_px))
+        rim = eng.region_dilate(ureg, rm.union, gm, R, invert=True, and_pool=rm.union)
+        got = bits_to_bool(rim.host().reshape(1, H, wpr), H, W)[0]
+        want = port.make_inside_rim_mask(union, rim_px)
+        assert np.array_equal(got, want), rim_px
+
+
+def check_square_dilation(eng):
+    """Per-ROI annulus = dilate(roi, (2o+1)^2) & ~dilate(roi, (2i+1)^2) == scipy binary_dilation."""
+    from imageprocess_b200 import ops
+    H, W = 80, 120
+    polys = [np.array([[20.0, 20.0], [50.0, 22.0], [48.0, 55.0], [18.0, 50.0]]),
+             np.array([[100.0, 5.0], [118.0, 6.0], [117.0, 30.0], [95.0, 28.0]])]          # near the border
+    for inner, outer in ((1, 2), (3, 7), (5, 11)):
+        specs = [geo.mpl_spec(P, (W, H), pad=outer) for P in polys]
+        rm = eng.rasterize(geo.RULE_MPL, specs, (H, W), 1, want_union=False)
+        reg = ops.regions_from_masks(rm)
+        gi, Ri = ops.square_gmax(inner)
+        go, Ro = ops.square_gmax(outer)
+        inn = eng.region_dilate(reg, rm.pool, gi, Ri)
+        ring = eng.region_dilate(reg, rm.pool, go, Ro, andnot_pool=inn)
+        pool = ring.host()
+        for i, P in enumerate(polys):
+            want = port.annulus_mask_from_poly(P, (H, W), inner, outer)
+            t = rm.table
+            rows, wpr_i = int(t.rows[i]), int(t.wpr[i])
+            words = pool[t.mask_off[i]: t.mask_off[i] + rows * wpr_i].reshape(rows, wpr_i)
+            bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little")
+            x0, y0, x1, y1 = t.srect[i]
+            got = np.zeros((H, W), bool)
+            got[y0:y1, x0:x1] = bits[:, : x1 - x0].astype(bool)
+            assert np.array_equal(got, want), (inner, outer, i)
+
+
+N2_BASE = {"px_um": 0.223, "rim_um": 1.12, "annulus_on": False, "ann_in_um": 1.2, "ann_out_um": 2.5,
+           "bg_scope": "full", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False,
+           "donor_p": 1.0, "fret_p": 1.0, "clip_neg": True, "eps_percentile": 1.0,
+           "ratio_mode": "FRET/Donor", "use_spectral": False, "alpha": 0.0, "beta": 0.0, "g_factor": 1.0,
+           "sat_filter_on": True, "sat_threshold": 65535.0, "clip_ratio_on": True, "clip_ratio_max": 20.0}
+N2_CASES = [
+    {},
+    {"use_spectral": True, "alpha": 0.12, "beta": 0.05, "g_factor": 1.1, "aonly": True},
+    {"ratio_mode": "Donor/FRET", "use_spectral": True, "alpha": 0.2, "g_factor": 0.9, "bg_scope": "roi_union",
+     "per_channel_p": True, "donor_p": 2.0, "fret_p": 3.5, "eps_percentile": 4.0},
+    {"annulus_on": True, "clip_neg": False, "sat_threshold": 30000.0, "clip_ratio_max": 3.0},
+    {"ratio_mode": "Donor/FRET", "annulus_on": True, "ann_in_um": 0.5, "ann_out_um": 1.4, "sat_filter_on": False,
+     "clip_ratio_on": False, "rim_um": 0.5},
+]
+
+
+def check_nesprin2_batch(eng, case):
+    from imageprocess_b200 import nesprin2
+    from imageprocess_b200.nesprin2 import bits_to_bool
+    p = dict(N2_BASE)
+    p.update({k: v for k, v in case.items() if k != "aonly"})
+    rng = np.random.default_rng(77)
+    frames = [small_scene(s, H=96, W=128, n_cells=2) for s in (11, 12)]
+    planes = []
+    for d, a, _ in frames:
+        d, a = d.copy(), a.copy()
+        hot = rng.random(d.shape) < 0.002                                # saturated pixels
+        d[hot] = 65535
+        a[rng.random(d.shape) < 0.002] = 65535
+        ao = (0.3 * a + rng.poisson(50, d.shape)).astype(np.uint16)
+        planes.append(np.stack([d, a, ao]))
+    planes = np.stack(planes)
+    F, C, H, W = planes.shape
+    aonly_ch = 2 if case.get("aonly") else None
+    out = nesprin2.nesprin2_batch(eng, eng.mem.from_host(planes), (F, C, H, W), [fr[2] for fr in frames], p,
+                                  donor_ch=0, acc_ch=1, aonly_ch=aonly_ch)
+    imgs = out["images"].host()
+    wpr = (W + 31) // 32
+    rim = bits_to_bool(out["rim"].host().reshape(F, H, wpr), H, W)
+    for f, (_, _, polys) in enumerate(frames):
+        D, A = planes[f, 0].astype(np.float32), planes[f, 1].astype(np.float32)
+        Ao = planes[f, 2].astype(np.float32) if aonly_ch is not None else None
+        want = port.n2_process_pair(D, A, polys, p, Aonly=Ao)
+        assert np.float32(out["eps"][f]) == np.float32(want["eps"]), (f, out["eps"][f], want["eps"])
+        assert np.array_equal(imgs[0, f], want["R_full"], equal_nan=True)
+        assert np.array_equal(imgs[1, f], want["R_alt"], equal_nan=True)
+        assert np.array_equal(imgs[2, f], want["Dcorr"], equal_nan=True)
+        assert np.array_equal(imgs[3, f], want["Acorr"], equal_nan=True)
+        assert np.array_equal(rim[f], want["rim_mask"])
+        assert len(out["rows_per_frame"][f]) == len(want["rows"])
+        for g, w in zip(out["rows_per_frame"][f], want["rows"]):
+            assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"], (g["area_px"], w["area_px"])
+            for k in ("ratio_median", "ratio_p5", "ratio_p95"):
+                assert (g[k] == w[k]) or (math.isnan(g[k]) and math.isnan(w[k])), (f, k, g[k], w[k])
+            for k in ("ratio_mean", "ratio_std", "ratio_FoverD_mean", "ratio_DoverF_mean", "donor_mean", "fret_mean"):
+                assert close(g[k], w[k]), (f, k, g[k], w[k])
+
+
+def check_region_moments(eng):
+    """Exact integer moments -> area, centroid, covariance of MOR_by_ROI.second_moments."""
+    from imageprocess_b200 import roi_ops
+    H, W = 150, 200
+    rng = np.random.default_rng(12)
+    polys = [np.array([[20.0, 30.0], [120.0, 25.0], [150.0, 90.0], [60.0, 130.0], [15.0, 80.0]]),
+             np.array([[160.5, 10.5], [190.5, 12.5], [185.5, 60.5]]),
+             rng.uniform(0, 140, (9, 2))]
+    for px_um in (0.112, 1.0):
+        got = roi_ops.morphology_batch(eng, polys, (H, W), px_um)
+        for P, g in zip(polys, got):
+            w = port.morphology_from_polygon(P, (H, W), px_um)
+            assert g.keys() == w.keys()
+            assert g["area_px"] == w["area_px"] and type(g["area_px"]) is type(w["area_px"])
+            for k in w:
+                if k == "area_px":
+                    continue
+                gv, wv = float(g[k]), float(w[k])
+                if k == "orientation_deg" and not math.isnan(wv):       # eigenvector sign is arbitrary
+                    dd = abs(gv - wv) % 180.0
+                    assert min(dd, 180.0 - dd) < 1e-6, (k, gv, wv)
+                else:
+                    assert close(gv, wv, 1e-9) or abs(gv - wv) < 1e-9, (k, gv, wv)
+
+
+def check_preview_and_crop(eng):
+    """16-bit previews of float32 images and the ROI cropper's normalise / mask / gamma chain."""
+    from imageprocess_b200 import roi_ops
+    rng = np.random.default_rng(8)
+    d, a, polys = small_scene(15, H=120, W=160, n_cells=2)
+    img = (d.astype(np.float32) - np.float32(97.0))
+    img[img < 0] = 0
+    R = (a.astype(np.float32) + 5) / (d.astype(np.float32) + 5)
+    R[rng.random(R.shape) < 0.01] = np.nan
+    got = roi_ops.preview_u16_batch(eng, np.stack([img, R]), 1.0, 99.0)
+    for k, src in enumerate((img, R)):
+        want = port.preview_u16(src, 1.0, 99.0)
+        assert np.array_equal(got[k], want), k
+    for gamma, low, high, mo in ((1.0, 1.0, 1.0, True), (2.2, 0.5, 2.0, True), (0.7, 0.0, 0.0, False)):
+        outs = roi_ops.cropper_batch(eng, d, polys, low, high, gamma, mask_outside=mo)
+        for P, g in zip(polys, outs):
+            w = port.cropper_normalize(d.astype(np.float32), d, P, low, high, gamma, mask_outside=mo)
+            assert (g is None) == (w is None)
+            if w is None:
+                continue
+            assert g["rect"] == w["rect"]
+            assert np.array_equal(g["mask"], w["mask"])
+            assert np.array_equal(g["raw_out"], w["raw_out"])
+            assert np.allclose(g["norm_gamma"], w["norm_gamma"], rtol=2e-6, atol=1e-7)
+            diff = np.abs(g["out16"].astype(np.int64) - w["out16"].astype(np.int64))
+            assert diff.max() <= (0 if gamma == 1.0 else 1), (gamma, diff.max())
+
+
+RASTER_CHECKS += [check_rim_mask, check_square_dilation, check_region_moments, check_preview_and_crop]

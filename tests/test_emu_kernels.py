@@ -36,3 +36,8 @@ def test_fa_batch(eng, params):
 @pytest.mark.parametrize("exp", ["e1_P0", "e2_P1"])
 def test_intensity_golden(eng, exp):
     checks.check_intensity_golden(eng, exp)
+
+
+@pytest.mark.parametrize("case", checks.N2_CASES, ids=lambda c: "_".join(sorted(c)) or "default")
+def test_nesprin2_batch(eng, case):
+    checks.check_nesprin2_batch(eng, case)

@@ -36,3 +36,8 @@ def test_intensity_golden(eng, exp):
 @pytest.mark.parametrize("params", checks.FA_CASES, ids=lambda p: f"a{p['alpha']}_r{p['close_radius']}")
 def test_fa_batch(eng, params):
     checks.check_fa_batch(eng, params)
+
+
+@pytest.mark.parametrize("case", checks.N2_CASES, ids=lambda c: "_".join(sorted(c)) or "default")
+def test_nesprin2_batch(eng, case):
+    checks.check_nesprin2_batch(eng, case)
