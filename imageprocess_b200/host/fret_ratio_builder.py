@@ -1,0 +1,114 @@
+"""Mirror of src/FRET/fret_ratio_builder.py's stage worker:
+
+    process_one_stage(stage_key, pairs_for_stage, p, paths) -> (stage_key, rows, logs)   :429-552
+
+All (stage, time) pairs of the stage that share an image shape go through ONE
+batch.FrameBatchJob("fret") (rasterisation, backgrounds, epsilon, ratio image, per-ROI tables);
+ratio TIFFs and their 16-bit previews are produced from the device-resident ratio images.
+PNG rendering (matplotlib) is outside the device path and is skipped with a log line.
+"""
+import os
+
+import numpy as np
+
+from .. import batch, roi_ops
+from . import common
+from ._fretnames import build_pairs_by_channel, load_roi_polys, parse_tokens  # noqa: F401
+from .common import ensure_dir, list_tifs
+
+LANG_CURRENT = "en"
+
+DEFAULT_P = {"timelapse": False, "donor_ch": 1, "fret_ch": 2, "ratio_mode": "FRET/Donor", "bg_scope": "full",
+             "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False, "donor_p": 1.0, "fret_p": 1.0,
+             "clip_neg": True, "eps_percentile": 1.0, "out_xls": True, "out_tif": True, "out_png": False,
+             "save_full": False, "save_crop": False, "mask_outside": True}
+
+
+def _engine():
+    import imageprocess_b200 as ipb
+    return ipb.engine()
+
+
+def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per_batch=32):
+    eng = eng or _engine()
+    logs = [f"[Stage {stage_key}] start"]
+    RES_ROOT, RAT32, RAT16, RROI32, RROI16, PNG_FULL, PNG_CROP = paths
+    timelapse = bool(p["timelapse"])
+    out_tif = bool(p["out_tif"])
+    suffix = "FoverD" if p["ratio_mode"] == "FRET/Donor" else "DoverF"
+    per_ch = bool(p["per_channel_p"])
+    d_p = float(p["donor_p"]) if per_ch else float(p["percentile"])
+    a_p = float(p["fret_p"]) if per_ch else float(p["percentile"])
+    items = []
+    for (s, t_code), dpath, apath in pairs_for_stage:
+        stid = f"{s}_{t_code}" if (timelapse and t_code is not None) else s
+        logs.append(f"  - Processing: {stid}")
+        D = common.as_u16_plane(common.read_image_raw(dpath), f"{stid} donor")
+        A = common.as_u16_plane(common.read_image_raw(apath), f"{stid} fret")
+        polys = load_roi_polys(p["roi_dir"], s, t_code, timelapse=timelapse)
+        if not polys:
+            logs.append(f"    [Warn] ROI missing: {stid}.json ? skip ROI-based outputs")
+        items.append((s, t_code, stid, np.stack([D, A]), polys))
+    rows_stage = []
+    by_shape = {}
+    for it in items:
+        by_shape.setdefault(it[3].shape, []).append(it)
+    for shape, group in by_shape.items():
+        for b0 in range(0, len(group), frames_per_batch):
+            chunk = group[b0: b0 + frames_per_batch]
+            planes = np.stack([it[3] for it in chunk])
+            F = planes.shape[0]
+            job = batch.FrameBatchJob(eng, planes.shape, stages=("fret",), fret_p=p, want_roi_image=out_tif)
+            res = job.run(eng.mem.from_host(planes), [it[4] or [] for it in chunk])
+            rows_pf = batch.rows_fret(res, F)
+            if out_tif:
+                R = res.R.host()
+                prev = roi_ops.preview_u16_batch(eng, res.R, 1.0, 99.0)
+                Rroi = res.R_roi.host()
+                prev_roi = roi_ops.preview_u16_batch(eng, res.R_roi, 1.0, 99.0)
+            for f, (s, t_code, stid, _, polys) in enumerate(chunk):
+                if out_tif:
+                    common.write_tiff(os.path.join(RAT32, f"{stid}_ratio_{suffix}.tif"), R[f])
+                    pv = prev[f] if prev[f] is not None else np.zeros(R[f].shape, np.uint16)
+                    common.write_tiff(os.path.join(RAT16, f"{stid}_ratio_{suffix}_preview.tif"), pv)
+                if not polys:
+                    continue
+                if out_tif:
+                    common.write_tiff(os.path.join(RROI32, f"{stid}_ratio_{suffix}.tif"), Rroi[f])
+                    pv = prev_roi[f] if prev_roi[f] is not None else np.zeros(R[f].shape, np.uint16)
+                    common.write_tiff(os.path.join(RROI16, f"{stid}_ratio_{suffix}_preview.tif"), pv)
+                eps = float(res.fret_params[f, 2])
+                for r in rows_pf[f]:
+                    r.update({"stage": s, "time": (t_code if timelapse else None), "eps": eps, "p": p["percentile"],
+                              "donor_p": d_p, "fret_p": a_p, "ratio_mode": p["ratio_mode"],
+                              "bg_scope": p["bg_scope"], "bg_mode": p["bg_mode"], "clip_neg": p["clip_neg"],
+                              "eps_p": p["eps_percentile"]})
+                rows_stage.extend(rows_pf[f])
+    if p.get("out_png"):
+        logs.append("  [SKIP-PNG] figure rendering is host matplotlib code outside the device path")
+    logs.append(f"[Stage {stage_key}] end (total {len(pairs_for_stage)} time/files)")
+    return stage_key, rows_stage, logs
+
+
+def run_headless(img_dir, roi_dir, out_root=None, p=None, eng=None, log=print):
+    """_pipeline_thread without Tk (fret_ratio_builder.py:892-1011): pair files, group by stage,
+    process, write RES/xls/fret_ratio_perROI.csv."""
+    p = {**DEFAULT_P, **(p or {}), "img_dir": img_dir, "roi_dir": roi_dir}
+    res_root = ensure_dir(out_root or os.path.join(img_dir, "RES"))
+    tif = os.path.join(res_root, "TIF")
+    paths = (res_root,) + tuple(ensure_dir(os.path.join(tif, d)) if p["out_tif"] else None
+                                for d in ("ratio32", "ratio16_preview", "ratio32_roi", "ratio16_roi_preview")) + (None, None)
+    pairs, _ = build_pairs_by_channel(list_tifs(img_dir), bool(p["timelapse"]), int(p["donor_ch"]), int(p["fret_ch"]))
+    stages = {}
+    for pr in pairs:
+        stages.setdefault(pr[0][0], []).append(pr)
+    rows_all = []
+    for stage_key, prs in stages.items():
+        _, rows, logs = process_one_stage(stage_key, prs, p, paths, eng=eng)
+        rows_all.extend(rows)
+        for line in logs:
+            log(line)
+    if rows_all and p["out_xls"]:
+        common.write_rows_csv(os.path.join(ensure_dir(os.path.join(res_root, "xls")), "fret_ratio_perROI.csv"), rows_all,
+                              columns=["stage", "time", "roi", "area_px"])
+    return rows_all
