@@ -89,6 +89,7 @@ class FrameBatchJob:
         self.want_roi_image, self.want_labels = want_roi_image, want_labels
         self._bufs = {}
         self._plans = {}
+        self.window_misses = 0
         self._pin = None
         self.n_roi_px = 0
         self.union_wpr = (self.W + 31) // 32
@@ -330,7 +331,10 @@ class FrameBatchJob:
         NS = pl.NS = sj.shape[0]
         pl.n_out = NR * rpr
 
+        passes = ops.plane_passes(hist_jobs)
+        pl.n_passes = passes.shape[0]
         T.add("hist_jobs", HIST_JOB, max(NH, 1))
+        T.add("passes", ops.PLANE_PASS, max(pl.n_passes, 1))
         T.add("qjobs", Q_JOB, max(NQ, 1))
         T.add("qdst", np.int32, max(NQ, 1))
         T.add("stat_jobs", STAT_JOB, max(NS, 1))
@@ -382,6 +386,7 @@ class FrameBatchJob:
             pl.comp_cap = int((((fh + 1) // 2) * ((fw + 1) // 2)).sum()) or 1
         if NH:
             V("hist_jobs")[:NH] = hist_jobs
+            V("passes")[: pl.n_passes] = passes
         if NQ:
             V("qjobs")[:NQ] = qjobs
             V("qdst")[:NQ] = qdst
@@ -397,10 +402,13 @@ class FrameBatchJob:
         O.add("f_area", np.uint32, max(NU, 1))
         O.add("stat_out", STAT_OUT, max(pl.n_out, 1))
         O.add("comp_off", np.int32, NR + 1)
+        O.add("miss", np.uint32, 1)
         return pl
 
     # ------------------------------------------------------------------ the step
-    def run(self, planes, polys_per_frame):
+    def run(self, planes, polys_per_frame, full_hist=False):
+        """One step.  full_hist = True forces exact full-range histograms instead of the
+        sample-selected windows (used automatically if a window ever misses a rank)."""
         eng, mem, F, C, H, W = self.eng, self.mem, self.F, self.C, self.H, self.W
         st = self.stages
         pl = self._plan_for(polys_per_frame)
@@ -440,7 +448,20 @@ class FrameBatchJob:
         d_scr = self._dev("rank_scratch", 8 * max(NH, 1) * H) if pl.has_ms else None
         d_qout = self._dev("qout", Q_OUT.itemsize * max(NQ, 1))
         mem.zero_bytes(d_out, O.sections["params"][3], O.sections["params"][0])
-        if NH:
+        mem.zero_bytes(d_out, O.sections["miss"][3], O.sections["miss"][0])
+        use_select = NH and not full_hist and not pl.host_bg
+        if use_select:
+            d_hs = self._dev("hist_sample", 4 * 65536 * NH)
+            d_hw = self._dev("hist_win", 4 * 4096 * NH)
+            d_win = self._dev("hist_winrange", ops.HIST_WIN.itemsize * NH)
+            d_cnt = self._dev("hist_cnt", 8 * 4 * NH)
+            d_hss = self._dev("hstat_sample", 8 * 4 * NH)
+            lib_call("ipb_hist_select", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, tp("qjobs"), NQ,
+                     int(pl.has_ms), union_ptr, self.union_wpr, d_scr.ptr if d_scr is not None else None,
+                     d_hs.ptr, d_hist.ptr, d_hw.ptr, d_win.ptr, d_cnt.ptr, d_hss.ptr, d_hstat.ptr, d_qout.ptr,
+                     op("miss"), stream)
+            lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), stream)
+        elif NH:
             lib_call("ipb_hist_u16", planes.ptr, H, W, tp("hist_jobs"), NH, int(pl.has_ms), union_ptr,
                      self.union_wpr, d_scr.ptr if d_scr is not None else None, d_hist.ptr, d_hstat.ptr, stream)
             lib_call("ipb_hist_quantiles", d_hist.ptr, d_hstat.ptr, tp("qjobs"), NQ, d_qout.ptr, stream)
@@ -509,6 +530,9 @@ class FrameBatchJob:
         mem.download_async(pout_t, d_out, O.size)
         mem.sync()
         OV = lambda name: O.view(pout_np, name)
+        if int(OV("miss")[0]) != 0:                        # a sampled window missed a wanted rank: exact rerun
+            self.window_misses += 1
+            return self.run(planes, polys_per_frame, full_hist=True)
         params = OV("params")[:NP].copy()
         res.d2h_bytes = O.size
         if "fret" in st:

@@ -126,7 +126,7 @@ int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs, int n_j
     IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist smem");
     IPB_LAUNCH(ipb_k_hist_u16, dim3(chunks, n_jobs), dim3(IPB_HIST_THREADS), smem, stream,
                planes, H, W, (const IpbHistJob*)jobs, rows_per_chunk, union_bits, union_wpr,
-               hist, (unsigned long long*)stats);
+               hist, (unsigned long long*)stats, 0, (const IpbHistWin*)nullptr);
     int rc = ipb_check_launch("ipb_k_hist_u16");
     if (rc) return rc;
     if (has_masked_stride) {
@@ -134,6 +134,83 @@ int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs, int n_j
                    (const IpbHistJob*)jobs, union_bits, union_wpr, (unsigned long long*)row_rank_scratch,
                    hist, (unsigned long long*)stats);
         rc = ipb_check_launch("ipb_k_hist_masked_stride");
+    }
+    return rc;
+}
+
+// one launch of the full-range histogram kernel over all jobs (sampled, or restricted to the
+// jobs the selection path marked FULL)
+static int ipb_launch_hist_full(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
+                                const uint32_t* union_bits, int union_wpr, uint32_t* hist, uint64_t* stats,
+                                int sample, const IpbHistWin* only_full, void* stream)
+{
+    int chunks = (592 + n_jobs - 1) / n_jobs;
+    int max_chunks = H / 32 > 0 ? H / 32 : 1;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    const int rows_per_chunk = (H + chunks - 1) / chunks;
+    chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
+    const size_t smem = sizeof(unsigned) * IPB_HIST_WIN;
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist smem");
+    IPB_LAUNCH(ipb_k_hist_u16, dim3(chunks, n_jobs), dim3(IPB_HIST_THREADS), smem, stream,
+               planes, H, W, (const IpbHistJob*)jobs, rows_per_chunk, union_bits, union_wpr,
+               hist, (unsigned long long*)stats, sample, only_full);
+    return ipb_check_launch("ipb_k_hist_u16");
+}
+
+int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
+                    const void* passes, int n_passes, const void* qjobs, int n_q, int has_masked_stride,
+                    const uint32_t* union_bits, int union_wpr, uint64_t* row_rank_scratch,
+                    uint32_t* hist_sample, uint32_t* hist_full, uint32_t* hist_win, void* win,
+                    uint64_t* cnt, uint64_t* stats_sample, uint64_t* stats, void* qout, uint32_t* miss,
+                    void* stream)
+{
+    IPB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535 && n_passes >= 0 && n_passes <= 65535, "ipb_hist_select: job count out of range");
+    if (n_jobs == 0) return IPB_OK;
+    IPB_REQUIRE(planes && jobs && passes && hist_sample && hist_full && hist_win && win && cnt && stats_sample &&
+                stats && miss && H > 0 && W > 0, "ipb_hist_select: bad argument");
+    IPB_REQUIRE(n_q == 0 || (qjobs && qout), "ipb_hist_select: quantile jobs without buffers");
+    IPB_REQUIRE(!has_masked_stride || (union_bits && row_rank_scratch), "ipb_hist_select: masked stride needs union + scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nj = (size_t)n_jobs;
+    IPB_CUDA_TRY(cudaMemsetAsync(hist_sample, 0, sizeof(uint32_t) * IPB_HIST_BINS * nj, st), "memset sample hist");
+    IPB_CUDA_TRY(cudaMemsetAsync(hist_full, 0, sizeof(uint32_t) * IPB_HIST_BINS * nj, st), "memset full hist");
+    IPB_CUDA_TRY(cudaMemsetAsync(hist_win, 0, sizeof(uint32_t) * IPB_HSEL_WIN * nj, st), "memset window hist");
+    IPB_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(uint64_t) * 4 * nj, st), "memset cnt");
+    IPB_CUDA_TRY(cudaMemsetAsync(stats_sample, 0, sizeof(uint64_t) * 4 * nj, st), "memset stats_sample");
+    IPB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(uint64_t) * 4 * nj, st), "memset stats");
+    int rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist_sample, stats_sample, 1, nullptr, stream);
+    if (rc) return rc;
+    IPB_LAUNCH(ipb_k_hist_windows, dim3(n_jobs), dim3(256), 0, stream, hist_sample, (const unsigned long long*)stats_sample,
+               (const IpbHistJob*)jobs, (const IpbQJob*)qjobs, n_q, (IpbHistWin*)win);
+    if ((rc = ipb_check_launch("ipb_k_hist_windows"))) return rc;
+    if (n_passes > 0) {
+        int chunks = (148 * 3 + n_passes - 1) / n_passes;
+        int max_chunks = H / 8 > 0 ? H / 8 : 1;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        const int rows_per_chunk = (H + chunks - 1) / chunks;
+        chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
+        const size_t smem = sizeof(unsigned) * IPB_HSEL_WIN * IPB_HSEL_MAXJ;
+        IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist tail smem");
+        IPB_LAUNCH(ipb_k_hist_tail, dim3(chunks, n_passes), dim3(IPB_HSEL_THREADS), smem, stream, planes, H, W,
+                   (const IpbPlanePass*)passes, (const IpbHistJob*)jobs, (const IpbHistWin*)win, rows_per_chunk,
+                   union_bits, union_wpr, hist_win, (unsigned long long*)cnt, (unsigned long long*)stats);
+        if ((rc = ipb_check_launch("ipb_k_hist_tail"))) return rc;
+    }
+    rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist_full, stats, 0, (const IpbHistWin*)win, stream);
+    if (rc) return rc;
+    if (has_masked_stride) {
+        IPB_LAUNCH(ipb_k_hist_masked_stride, dim3(n_jobs), dim3(256), 0, stream, planes, H, W,
+                   (const IpbHistJob*)jobs, union_bits, union_wpr, (unsigned long long*)row_rank_scratch,
+                   hist_full, (unsigned long long*)stats);
+        if ((rc = ipb_check_launch("ipb_k_hist_masked_stride"))) return rc;
+    }
+    if (n_q > 0) {
+        IPB_LAUNCH(ipb_k_hist_select_q, dim3(n_q), dim3(256), 0, stream, (const IpbQJob*)qjobs, (const IpbHistWin*)win,
+                   (const unsigned long long*)cnt, hist_win, hist_full, (const unsigned long long*)stats,
+                   (IpbQOut*)qout, miss);
+        rc = ipb_check_launch("ipb_k_hist_select_q");
     }
     return rc;
 }
@@ -377,6 +454,8 @@ int ipb_sizeof(int what)
         case 7: return (int)sizeof(IpbCrop);
         case 8: return (int)sizeof(IpbComp);
         case 9: return (int)sizeof(IpbCropJob);
+        case 10: return (int)sizeof(IpbPlanePass);
+        case 11: return (int)sizeof(IpbHistWin);
         default: return -1;
     }
 }

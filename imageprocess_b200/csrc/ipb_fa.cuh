@@ -23,7 +23,7 @@
 #include "ipb_rt.cuh"
 
 #define IPB_FA_THREADS 256
-#define IPB_FA_ROWS 8          // rows of one crop handled by one CTA
+#define IPB_FA_ROWS 32         // rows of one crop handled by one CTA (~1-2 words per thread)
 
 struct IpbCrop {
     long long bit_off;   // word offset of the crop's bit rows (all bit pools share it)
@@ -139,15 +139,31 @@ ipb_k_fa_threshold(const IpbCrop* __restrict__ crops, const unsigned short* __re
     if (nrow > IPB_FA_ROWS) nrow = IPB_FA_ROWS;
     const float thr = fa_params[(size_t)c.frame * 4 + 3];
     const unsigned short* img = planes + (size_t)c.plane * H * W;
-    for (int i = warp; i < nrow * c.wpr; i += nwarps) {
-        const int y = y_beg + i / c.wpr, j = i % c.wpr;
-        const int x = 32 * j + lane;
-        bool on = false;
-        if (x < c.w) on = (float)img[(size_t)(c.oy + y) * W + (c.ox + x)] > thr;
-        const unsigned word = __ballot_sync(IPB_FULL, on);
-        if (lane == 0) {
-            const size_t wi = (size_t)c.bit_off + (size_t)y * c.wpr + j;
-            bw[wi] = word & roi_mask[(size_t)c.mask_off + (size_t)y * c.wpr + j];
+    const int nitems = nrow * c.wpr;
+    // 4 words per warp-iteration: four independent coalesced pixel loads in flight per lane
+    for (int i0 = warp * 4; i0 < nitems; i0 += nwarps * 4) {
+        unsigned short px[4];
+        bool in[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            in[u] = false;
+            px[u] = 0;
+            if (i < nitems) {
+                const int y = y_beg + i / c.wpr, j = i % c.wpr, x = 32 * j + lane;
+                in[u] = x < c.w;
+                if (in[u]) px[u] = img[(size_t)(c.oy + y) * W + (c.ox + x)];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            const unsigned word = __ballot_sync(IPB_FULL, in[u] && (float)px[u] > thr);
+            if (lane == 0 && i < nitems) {
+                const int y = y_beg + i / c.wpr, j = i % c.wpr;
+                const size_t wi = (size_t)c.bit_off + (size_t)y * c.wpr + j;
+                bw[wi] = word & roi_mask[(size_t)c.mask_off + (size_t)y * c.wpr + j];
+            }
         }
     }
 }

@@ -40,7 +40,7 @@ class RoiMasks:
 # kernels launched by each C-ABI entry point (memsets not counted)
 KERNELS_PER_CALL = {"ipb_fa_segment": 14, "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
                     "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
-                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_region_dilate": 2}
+                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_region_dilate": 2, "ipb_hist_select": 5}
 
 
 class Engine:
@@ -125,7 +125,25 @@ CROP = np.dtype([("bit_off", "i8"), ("pix_off", "i8"), ("row_off", "i8"), ("mask
 COMP = np.dtype([("sum_i", "u8"), ("sum_y", "u8"), ("sum_x", "u8"), ("area", "u4"), ("crop", "i4")])
 CROP_JOB = np.dtype([("plane", "i4"), ("x0", "i4"), ("y0", "i4"), ("w", "i4"), ("h", "i4"), ("region", "i4"),
                      ("out_off", "i8")])
-_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG, CROP, COMP, CROP_JOB]
+PLANE_PASS = np.dtype([("plane", "i4"), ("excl_plane1", "i4"), ("sat_min", "i4"), ("n_jobs", "i4"), ("job", "i4", 4)])
+HIST_WIN = np.dtype([("wlo", "i4"), ("whi", "i4"), ("mode", "i4"), ("pad", "i4")])
+_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG, CROP, COMP, CROP_JOB, PLANE_PASS, HIST_WIN]
+
+
+def plane_passes(hist_jobs):
+    """Groups histogram jobs that read the same plane (and saturation partner) into passes of
+    up to four jobs for ipb_hist_select's single read of each plane."""
+    groups = {}
+    for j, hj in enumerate(hist_jobs):
+        groups.setdefault((int(hj["plane"]), int(hj["excl_plane1"]), int(hj["sat_min"])), []).append(j)
+    out = []
+    for (plane, excl, sat), js in groups.items():
+        for i in range(0, len(js), 4):
+            pp = np.zeros(1, dtype=PLANE_PASS)[0]
+            pp["plane"], pp["excl_plane1"], pp["sat_min"], pp["n_jobs"] = plane, excl, sat, len(js[i: i + 4])
+            pp["job"][: len(js[i: i + 4])] = js[i: i + 4]
+            out.append(pp)
+    return np.array(out, dtype=PLANE_PASS) if out else np.zeros(0, dtype=PLANE_PASS)
 
 
 def q32_of(p):

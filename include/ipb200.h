@@ -35,7 +35,7 @@ extern "C" {
 const char* ipb_last_error(void);
 int ipb_version(void);
 int ipb_is_emulated(void);      /* 1 only in the CPU test build of the same sources */
-int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg 7 Crop 8 Comp 9 CropJob */
+int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg 7 Crop 8 Comp 9 CropJob 10 PlanePass 11 HistWin */
 
 /* ------------------------------------------------------------------ ROI rasterisation
  * Replaces rasterize_polygon (INT/Fluor_INT.py:398-403; copies FRET/fret_ratio_builder.py:292,
@@ -87,6 +87,26 @@ typedef struct {
 int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs /* ipb_hist_job[] dev */,
                  int n_jobs, int has_masked_stride, const uint32_t* union_bits, int union_wpr,
                  uint64_t* row_rank_scratch, uint32_t* hist, uint64_t* stats, void* stream);
+
+/* Selection by sampling: the same percentiles as ipb_hist_u16 + ipb_hist_quantiles, exact, with
+ * ~16x fewer shared-memory atomics.  A hashed 1/16 sample of every job fixes a value window that
+ * holds the wanted ranks with overwhelming probability; ONE further read of each plane (passes:
+ * up to 4 jobs that share a plane and its saturation partner) counts pixels below / above the
+ * window and histograms those inside; sparse patterns, tiny samples and wide windows take the
+ * exact full-range histogram.  *miss (zeroed by the caller) counts quantiles whose rank fell
+ * outside the window: the caller must then repeat with ipb_hist_u16 (never seen in practice;
+ * the margin is 6 sigma of the sample rank).  Buffers: hist_sample / hist_full
+ * uint32 [n_jobs][65536], hist_win uint32 [n_jobs][4096], win ipb_hist_win[n_jobs],
+ * cnt / stats_sample / stats uint64 [n_jobs][4] (stats as in ipb_hist_u16).                   */
+typedef struct { int32_t plane, excl_plane1, sat_min, n_jobs; int32_t job[4]; } ipb_plane_pass;
+typedef struct { int32_t wlo, whi, mode, pad; } ipb_hist_win;
+int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
+                    const void* passes /* ipb_plane_pass[] dev */, int n_passes,
+                    const void* qjobs /* ipb_q_job[] dev */, int n_q, int has_masked_stride,
+                    const uint32_t* union_bits, int union_wpr, uint64_t* row_rank_scratch,
+                    uint32_t* hist_sample, uint32_t* hist_full, uint32_t* hist_win, void* win,
+                    uint64_t* cnt, uint64_t* stats_sample, uint64_t* stats, void* qout /* ipb_q_out[n_q] */,
+                    uint32_t* miss, void* stream);
 
 typedef struct {
     int32_t hist;         /* histogram (job) index */

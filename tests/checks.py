@@ -594,3 +594,42 @@ def check_preview_and_crop(eng):
 
 
 RASTER_CHECKS += [check_rim_mask, check_square_dilation, check_region_moments, check_preview_and_crop]
+
+
+def _hist_sampled(y, xv):
+    """numpy twin of ipb_hist_sampled (csrc/ipb_hist.cuh): the hashed 1/16 sample of 8-px groups."""
+    h = (y.astype(np.uint64) * 0x9E3779B1 + xv.astype(np.uint64) * 0x85EBCA77) & 0xFFFFFFFF
+    h ^= h >> 15
+    h = (h * 0x2C1B3C6D) & 0xFFFFFFFF
+    h ^= h >> 12
+    return (h & 15) == 0
+
+
+def check_hist_select_paths(eng):
+    """Backgrounds through ipb_hist_select: windowed selection on ordinary data is exact; data
+    built so that the hashed sample misleads the window makes the step report a miss and repeat
+    itself with full histograms -- still exact."""
+    from imageprocess_b200 import batch
+    rng = np.random.default_rng(2)
+    H, W = 256, 512
+    yy, xv = np.meshgrid(np.arange(H), np.arange(W // 8), indexing="ij")
+    sampled = np.repeat(_hist_sampled(yy, xv), 8, axis=1)
+    assert 0.04 < sampled.mean() < 0.09
+    normal = rng.poisson(400, (H, W)).astype(np.uint16)
+    tricky = rng.integers(1000, 2000, (H, W)).astype(np.uint16)
+    tricky[(~sampled) & (rng.random((H, W)) < 0.3)] = 50000          # invisible to the sample
+    for img, want_miss in ((normal, 0), (tricky, 1)):
+        planes = np.stack([img, img[::-1].copy()])[None]
+        for p, stride in ((1.0, 4), (50.0, 1)):
+            task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": stride,
+                    "percentile": p, "per_channel_p": False, "ch_p_map": {}}
+            job = batch.FrameBatchJob(eng, planes.shape, stages=("int",), int_task=task)
+            res = job.run(eng.mem.from_host(planes), [[]])
+            for ci in range(2):
+                want = port.int_bg_value(planes[0, ci].astype(np.float32), "percentile", p, None, stride)
+                assert float(res.int_bg[0, ci]) == want, (p, stride, ci)
+            if p == 50.0:
+                assert job.window_misses == want_miss, (job.window_misses, want_miss)
+
+
+RASTER_CHECKS.append(check_hist_select_paths)
