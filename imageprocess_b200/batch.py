@@ -19,6 +19,7 @@ dicts for the unchanged pandas writers.
 """
 import hashlib
 import math
+import os
 
 import numpy as np
 
@@ -77,7 +78,7 @@ class BatchResult:
 class FrameBatchJob:
     def __init__(self, eng, shape, stages=("fret", "int", "fa"), fret_p=None, int_task=None,
                  fa_params=None, fa_px=0.112, donor_ch=0, acc_ch=1, fa_ch=0, int_channels=None,
-                 want_roi_image=False, want_labels=False, fa_config=None, fa_save_ok_only=True):
+                 want_roi_image=False, want_labels=False, fa_config=None, fa_save_ok_only=True, hist_select=None):
         self.eng, self.mem = eng, eng.mem
         self.F, self.C, self.H, self.W = (int(s) for s in shape)
         self.stages = tuple(s for s in ("fret", "int", "fa") if s in stages)
@@ -90,6 +91,9 @@ class FrameBatchJob:
         self._bufs = {}
         self._plans = {}
         self.window_misses = 0
+        # percentiles by sampling (ipb_hist_select) instead of full histograms: exact either way;
+        # off by default until its tail pass beats the full-histogram kernel
+        self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "0"))) if hist_select is None else bool(hist_select)
         self._pin = None
         self.n_roi_px = 0
         self.union_wpr = (self.W + 31) // 32
@@ -449,7 +453,7 @@ class FrameBatchJob:
         d_qout = self._dev("qout", Q_OUT.itemsize * max(NQ, 1))
         mem.zero_bytes(d_out, O.sections["params"][3], O.sections["params"][0])
         mem.zero_bytes(d_out, O.sections["miss"][3], O.sections["miss"][0])
-        use_select = NH and not full_hist and not pl.host_bg
+        use_select = NH and self.hist_select and not full_hist and not pl.host_bg
         if use_select:
             d_hs = self._dev("hist_sample", 4 * 65536 * NH)
             d_hw = self._dev("hist_win", 4 * 4096 * NH)

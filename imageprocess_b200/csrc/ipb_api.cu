@@ -267,12 +267,14 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const vo
     memcpy(&cfg, cfg_host, sizeof(cfg));
     IPB_REQUIRE(cfg.n_ch > 0 && cfg.donor_ch >= 0 && cfg.donor_ch < cfg.n_ch && cfg.acc_ch >= 0 &&
                 cfg.acc_ch < cfg.n_ch && cfg.aonly_ch < cfg.n_ch, "ipb_fret_pixels: bad channel indices");
-    const long long work = (long long)n_frames * H * W / 8;
+    IPB_REQUIRE(n_frames <= 65535, "ipb_fret_pixels: n_frames %d out of range", n_frames);
+    const long long work = (long long)H * W / 8;                      // per frame
     long long blocks = (work + 255) / 256;
-    const long long cap = 148LL * 8 * 4;
+    long long cap = (148LL * 8 * 4 + n_frames - 1) / n_frames;        // ~32 CTAs per SM over the whole grid
+    if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    IPB_LAUNCH(ipb_k_fret_pixels, dim3((unsigned)blocks), dim3(256), 0, stream, planes, n_frames, H, W,
+    IPB_LAUNCH(ipb_k_fret_pixels, dim3((unsigned)blocks, (unsigned)n_frames), dim3(256), 0, stream, planes, n_frames, H, W,
                cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr);
     return ipb_check_launch("ipb_k_fret_pixels");
 }

@@ -84,11 +84,12 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
     const long long plane_px = (long long)H * W;
     const float fnan = __uint_as_float(0x7fc00000u);
     if ((W & 7) == 0) {
-        const long long vpf = plane_px >> 3, nvec = vpf * F;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-             i += (long long)gridDim.x * blockDim.x) {
-            const int f = (int)(i / vpf);
-            const long long p0 = (i % vpf) << 3;
+        // grid = (chunks, frames): indices inside a frame are walked without 64-bit divisions
+        const long long vpf = plane_px >> 3;
+        const int f = blockIdx.y;
+        for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < vpf;
+             iv += (long long)gridDim.x * blockDim.x) {
+            const long long p0 = iv << 3;
             const unsigned short* base = planes + (size_t)f * cfg.n_ch * plane_px;
             const uint4 dq = __ldg(reinterpret_cast<const uint4*>(base + (size_t)cfg.donor_ch * plane_px + p0));
             const uint4 aq = __ldg(reinterpret_cast<const uint4*>(base + (size_t)cfg.acc_ch * plane_px + p0));
@@ -100,7 +101,7 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
             const float* fp = fparams + (size_t)f * IPB_FP_STRIDE;
             unsigned ub = 0xffu;
             if (Rroi) {
-                const int y = (int)(p0 / W), x0 = (int)(p0 % W);
+                const int y = (int)((unsigned long long)p0 / (unsigned)W), x0 = (int)(p0 - (long long)y * W);
                 const int uf = union_idx ? union_idx[f] : f;
                 ub = union_bits ? ((union_bits[((size_t)uf * H + y) * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu) : 0u;
             }
@@ -122,11 +123,10 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
             if (Acorr) { reinterpret_cast<float4*>(Acorr + o0)[0] = make_float4(ac[0], ac[1], ac[2], ac[3]); reinterpret_cast<float4*>(Acorr + o0)[1] = make_float4(ac[4], ac[5], ac[6], ac[7]); }
         }
     } else {
-        const long long npx = plane_px * F;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx;
-             i += (long long)gridDim.x * blockDim.x) {
-            const int f = (int)(i / plane_px);
-            const long long p = i % plane_px;
+        const int f = blockIdx.y;
+        for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < plane_px;
+             p += (long long)gridDim.x * blockDim.x) {
+            const long long i = (long long)f * plane_px + p;
             const unsigned short* base = planes + (size_t)f * cfg.n_ch * plane_px;
             const unsigned dv = base[(size_t)cfg.donor_ch * plane_px + p];
             const unsigned av = base[(size_t)cfg.acc_ch * plane_px + p];

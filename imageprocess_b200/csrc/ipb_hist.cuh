@@ -15,6 +15,7 @@
 #pragma once
 #include "ipb_rt.cuh"
 #include "ipb_exact.cuh"
+#include "ipb_scan.cuh"
 
 #define IPB_HIST_BINS 65536
 #define IPB_HIST_WIN 24576
@@ -47,10 +48,12 @@ struct IpbHistJob {
 struct IpbHistWin { int wlo, whi, mode, pad; };     // window [wlo, whi)
 struct IpbPlanePass { int plane, excl_plane1, sat_min, n_jobs; int job[IPB_HSEL_MAXJ]; };
 
-// deterministic 1/16 sample of the 8-pixel groups (hash of the group's row and column index:
-// no row / column periodicity of the image can line up with it)
+// deterministic 1/16 sample of 256-pixel row segments (32 consecutive 8-pixel groups = the
+// groups one warp reads together, so a sampled warp is fully active): hash of the segment's
+// row and column index -- no row / column periodicity of the image can line up with it.
+// Pixels of a segment are correlated, which ipb_k_hist_windows' margin accounts for.
 __device__ __forceinline__ bool ipb_hist_sampled(unsigned y, unsigned xv) {
-    unsigned h = y * 0x9E3779B1u + xv * 0x85EBCA77u;
+    unsigned h = y * 0x9E3779B1u + (xv >> 5) * 0x85EBCA77u;
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
     return (h & 15u) == 0u;
 }
@@ -80,6 +83,7 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
     const unsigned short* img2 = (job.sat_min > 0 && job.excl_plane1 > 0) ? planes + (size_t)(job.excl_plane1 - 1) * H * W : nullptr;
     const unsigned* ubits = (job.pattern == IPB_PAT_MASKED) ? union_bits + (size_t)job.mask_frame * H * union_wpr : nullptr;
     unsigned long long s1 = 0, s2 = 0, nsel = 0;
+    unsigned nsel32 = 0;                       // per-thread count of the vector path (<= 2^27 pixels per thread)
     const int k = job.k > 0 ? job.k : 1;
     const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0) && ((((size_t)img2) & 15) == 0);
 
@@ -94,22 +98,19 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
     if (y_beg < y_end) {
         if (vec_ok) {
             const int vpr = W >> 3;                                   // 8-pixel vectors per row
-            const long long nvec = (long long)(y_end - y_beg) * vpr;
-            for (long long i = threadIdx.x; i < nvec; i += blockDim.x) {
-                const int y = y_beg + (int)(i / vpr);
-                const int x0 = ((int)(i % vpr)) << 3;
-                if (job.pattern == IPB_PAT_STRIDE2D && !job.moments && (y % k) != 0) continue;
-                if (sample && !ipb_hist_sampled((unsigned)y, (unsigned)(x0 >> 3))) continue;
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + x0));
+            // (row, vector) walk without a division per iteration
+            const int dy = (int)blockDim.x / vpr, dx = (int)blockDim.x % vpr;
+            int y = y_beg + (int)threadIdx.x / vpr, xv = (int)threadIdx.x % vpr;
+            // one 8-pixel group: selection mask, then counting
+            auto process = [&](int y, int x0, const uint4& q, const uint4& q2) {
                 const unsigned w[4] = {q.x, q.y, q.z, q.w};
-                uint4 q2 = make_uint4(0, 0, 0, 0);
-                if (img2) q2 = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + x0));
                 const unsigned w2[4] = {q2.x, q2.y, q2.z, q2.w};
                 unsigned sel = 0;                                     // bit i: pixel x0+i selected
                 if (job.pattern == IPB_PAT_FULL) sel = 0xffu;
                 else if (job.pattern == IPB_PAT_STRIDE1D) {
-                    long long flat = (long long)y * W + x0;
-                    int first = (int)((k - (flat % k)) % k);
+                    const unsigned long long flat = (unsigned long long)y * W + x0;
+                    const unsigned fm = flat < 0xffffffffull ? (unsigned)flat % (unsigned)k : (unsigned)(flat % (unsigned long long)k);
+                    int first = (int)(((unsigned)k - fm) % (unsigned)k);
                     for (int t = first; t < 8; t += k) sel |= 1u << t;
                 } else if (job.pattern == IPB_PAT_STRIDE2D) {
                     if ((y % k) == 0) {
@@ -119,18 +120,64 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
                 } else if (job.pattern == IPB_PAT_MASKED) {
                     sel = (ubits[(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
                 }
+                if (job.moments) {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
-                    const unsigned o = (t & 1) ? (w2[t >> 1] >> 16) : (w2[t >> 1] & 0xffffu);
-                    if (job.moments) { s1 += v; s2 += (unsigned long long)v * v; }
-                    if (((sel >> t) & 1u) && v < sat_min && o < sat_min) IPB_HIST_COUNT(v);
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned a = w[j] & 0xffffu, b = w[j] >> 16;
+                        s1 += a + b;
+                        s2 += (unsigned long long)a * a + (unsigned long long)b * b;
+                    }
                 }
+                if (img2 || job.sat_min > 0) {                        // saturation filter (rare)
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                        const unsigned o = (t & 1) ? (w2[t >> 1] >> 16) : (w2[t >> 1] & 0xffffu);
+                        if (!(v < sat_min && o < sat_min)) sel &= ~(1u << t);
+                    }
+                }
+                nsel32 += (unsigned)__popc(sel);
+                if (sel == 0xffu) {                                   // the common case: no tests per pixel
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                        if (v < IPB_HIST_WIN) atomicAdd(&sh[v], 1u); else atomicAdd(&gh[v], 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                        if ((sel >> t) & 1u) { if (v < IPB_HIST_WIN) atomicAdd(&sh[v], 1u); else atomicAdd(&gh[v], 1u); }
+                    }
+                }
+            };
+            // 4 groups per trip: their (up to 8) 128-bit loads are issued before any counting,
+            // so every thread keeps several loads in flight
+            while (y < y_end) {
+                int ys[4], xs[4];
+                bool ok[4];
+                uint4 q[4], q2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ys[u] = y; xs[u] = xv << 3;
+                    ok[u] = y < y_end;
+                    if (ok[u] && job.pattern == IPB_PAT_STRIDE2D && !job.moments && (y % k) != 0) ok[u] = false;
+                    if (ok[u] && sample && !ipb_hist_sampled((unsigned)y, (unsigned)xv)) ok[u] = false;
+                    q[u] = make_uint4(0, 0, 0, 0); q2[u] = make_uint4(0, 0, 0, 0);
+                    if (ok[u]) {
+                        q[u] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + xs[u]));
+                        if (img2) q2[u] = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + xs[u]));
+                    }
+                    xv += dx; y += dy;
+                    if (xv >= vpr) { xv -= vpr; ++y; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (ok[u]) process(ys[u], xs[u], q[u], q2[u]);
             }
         } else {
-            const long long npx = (long long)(y_end - y_beg) * W;
-            for (long long i = threadIdx.x; i < npx; i += blockDim.x) {
-                const int y = y_beg + (int)(i / W), x = (int)(i % W);
+            const int dy = (int)blockDim.x / W, dx = (int)blockDim.x % W;
+            int y = y_beg + (int)threadIdx.x / W, x = (int)threadIdx.x % W;
+            for (; y < y_end; x += dx, y += dy, y += (x >= W) ? 1 : 0, x -= (x >= W) ? W : 0) {
                 if (sample && !ipb_hist_sampled((unsigned)y, (unsigned)(x >> 3))) continue;
                 const unsigned v = img[(size_t)y * W + x];
                 if (job.moments) { s1 += v; s2 += (unsigned long long)v * v; }
@@ -152,6 +199,7 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
         if (c) atomicAdd(&gh[b], c);
     }
     // block reduction of the three 64-bit counters
+    nsel += nsel32;
     s1 = ipb_warp_sum(s1); s2 = ipb_warp_sum(s2); nsel = ipb_warp_sum(nsel);
     __shared__ unsigned long long red[3][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,7 +280,8 @@ struct IpbQOut {
     unsigned long long n;  // sample size
 };
 
-// one CTA (256 threads) per quantile job; thread t owns bins [256 t, 256 t + 256)
+// one CTA (256 threads) per quantile job; warps scan contiguous bands of the histogram with
+// coalesced reads (ipb_locate_ranks)
 __global__ void __launch_bounds__(256)
 ipb_k_hist_quantiles(const unsigned* __restrict__ hist, const unsigned long long* __restrict__ stats,
                      const IpbQJob* __restrict__ qjobs, IpbQOut* __restrict__ out)
@@ -240,38 +289,19 @@ ipb_k_hist_quantiles(const unsigned* __restrict__ hist, const unsigned long long
     const IpbQJob qj = qjobs[blockIdx.x];
     const unsigned* h = hist + (size_t)qj.hist * IPB_HIST_BINS;
     const unsigned long long n = stats[(size_t)qj.hist * 4];
-    __shared__ unsigned long long part[256];
+    __shared__ unsigned long long red_u[32];
     __shared__ int res[2];
-    const int t = threadIdx.x;
-    unsigned long long mine = 0;
-    for (int b = 0; b < 256; ++b) mine += h[t * 256 + b];
-    part[t] = mine;
-    if (t < 2) res[t] = -1;
-    __syncthreads();
-    if (t == 0) {
-        unsigned long long acc = 0;
-        for (int i = 0; i < 256; ++i) { unsigned long long c = part[i]; part[i] = acc; acc += c; }
-    }
-    __syncthreads();
+    if (threadIdx.x < 2) res[threadIdx.x] = -1;
     IpbQIdx qi;
     qi.prev = 0; qi.next = 0; qi.gamma = 0.f;
-    if (n > 0) {
+    if (n > 0) {                                              // block-uniform
         qi = ipb_np_qidx_f32((long long)n, qj.q32);
-        const unsigned long long lo = part[t], hi = lo + mine;
-        const long long want[2] = {qi.prev, qi.next};
-        for (int w = 0; w < 2; ++w) {
-            const unsigned long long kk = (unsigned long long)want[w];
-            if (kk >= lo && kk < hi) {
-                unsigned long long acc = lo;
-                for (int b = 0; b < 256; ++b) {
-                    acc += h[t * 256 + b];
-                    if (kk < acc) { res[w] = t * 256 + b; break; }
-                }
-            }
-        }
+        const unsigned long long want[2] = {(unsigned long long)qi.prev, (unsigned long long)qi.next};
+        ipb_locate_ranks(IPB_HIST_BINS / 32, want, 2, red_u, [&](unsigned i) { return h[i]; },
+                         [&](int r, unsigned i, unsigned) { res[r] = (int)i; });
     }
     __syncthreads();
-    if (t == 0) {
+    if (threadIdx.x == 0) {
         IpbQOut o;
         o.prev = res[0]; o.next = res[1]; o.gamma = qi.gamma; o.n = n;
         o.value = (n > 0 && res[0] >= 0 && res[1] >= 0)
@@ -303,65 +333,47 @@ ipb_k_hist_windows(const unsigned* __restrict__ hs /* sample histograms */,
     const int job = blockIdx.x, t = threadIdx.x;
     const unsigned* h = hs + (size_t)job * IPB_HIST_BINS;
     const unsigned long long ns = stats_s[(size_t)job * 4];
-    __shared__ unsigned long long part[256];
-    __shared__ long long want[2];
+    __shared__ unsigned long long red_u[32];
+    __shared__ int want[2];
     __shared__ int res[2];
     __shared__ int any_q;
-    if (t == 0) {
-        // rank range over every quantile wanted from this job
-        long long lo = 0x7fffffffffffffffll, hi = -1;
-        int any = 0;
-        for (int i = 0; i < n_q; ++i) {
-            if (qjobs[i].hist != job) continue;
-            any = 1;
-            if (ns == 0) continue;
-            const double q = (double)qjobs[i].q32;
-            const double r = q * (double)(ns - 1);
-            const double d = 6.0 * sqrt(fmax(q * (1.0 - q), 0.0) * (double)ns) + 8.0;
-            long long a = (long long)floor(r - d), b = (long long)ceil(r + d) + 1;
-            if (a < 0) a = 0;
-            if (b > (long long)ns - 1) b = (long long)ns - 1;
-            lo = a < lo ? a : lo;
-            hi = b > hi ? b : hi;
-        }
-        want[0] = lo; want[1] = hi; any_q = any;
-        res[0] = res[1] = -1;
-    }
-    unsigned long long mine = 0;
-    for (int b = 0; b < 256; ++b) mine += h[t * 256 + b];
-    part[t] = mine;
+    if (t == 0) { want[0] = 0x7fffffff; want[1] = -1; any_q = 0; res[0] = res[1] = -1; }
     __syncthreads();
-    if (t == 0) {
-        unsigned long long acc = 0;
-        for (int i = 0; i < 256; ++i) { unsigned long long c = part[i]; part[i] = acc; acc += c; }
+    const bool countable = ns > 0 && ns < 0x7fffffffull;
+    // rank range over every quantile wanted from this job
+    for (int i = t; i < n_q; i += blockDim.x) {
+        if (qjobs[i].hist != job) continue;
+        atomicOr(&any_q, 1);
+        if (!countable) continue;
+        const double q = (double)qjobs[i].q32;
+        const double r = q * (double)(ns - 1);
+        // 6 sigma of the sample rank, widened 9x for the clustered (256-px segment) sample
+        const double d = 54.0 * sqrt(fmax(q * (1.0 - q), 0.0) * (double)ns) + 64.0;
+        double a = floor(r - d), b = ceil(r + d) + 1.0;
+        if (a < 0.0) a = 0.0;
+        if (b > (double)(ns - 1)) b = (double)(ns - 1);
+        atomicMin(&want[0], (int)a);
+        atomicMax(&want[1], (int)b);
     }
     __syncthreads();
     const int pattern = jobs[job].pattern;
     const bool sparse = pattern == IPB_PAT_STRIDE2D || pattern == IPB_PAT_MASKED_STRIDE;
-    if (any_q && ns >= 256 && !sparse) {
-        const unsigned long long lo = part[t], hi = lo + mine;
-        for (int w = 0; w < 2; ++w) {
-            const unsigned long long kk = (unsigned long long)want[w];
-            if (kk >= lo && kk < hi) {
-                unsigned long long acc = lo;
-                for (int b = 0; b < 256; ++b) {
-                    acc += h[t * 256 + b];
-                    if (kk < acc) { res[w] = t * 256 + b; break; }
-                }
-            }
-        }
+    if (any_q && ns >= 256 && countable && !sparse) {         // block-uniform
+        const unsigned long long wv[2] = {(unsigned long long)want[0], (unsigned long long)want[1]};
+        ipb_locate_ranks(IPB_HIST_BINS / 32, wv, 2, red_u, [&](unsigned i) { return h[i]; },
+                         [&](int r, unsigned i, unsigned) { res[r] = (int)i; });
     }
     __syncthreads();
     if (t == 0) {
         IpbHistWin o;
         o.pad = 0;
         if (!any_q) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_NONE; }
-        else if (ns < 256 || sparse || res[0] < 0 || res[1] < 0) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_FULL; }
+        else if (ns < 256 || !countable || sparse || res[0] < 0 || res[1] < 0) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_FULL; }
         else {
             // a window that starts / ends at the sample's extreme rank is opened to the end of
             // the value range: the true extremes may lie beyond the sample's
             o.wlo = want[0] == 0 ? 0 : res[0];
-            o.whi = want[1] >= (long long)ns - 1 ? IPB_HIST_BINS : res[1] + 1;
+            o.whi = want[1] >= (int)ns - 1 ? IPB_HIST_BINS : res[1] + 1;
             o.mode = (o.whi - o.wlo <= IPB_HSEL_WIN) ? IPB_HSEL_WINDOWED : IPB_HSEL_FULL;
         }
         win[job] = o;
@@ -372,7 +384,7 @@ ipb_k_hist_windows(const unsigned* __restrict__ hs /* sample histograms */,
 // cnt[job] = { below, inside, above, 0 }; moments (sum, sumsq of ALL pixels) -> stats[job][1..2],
 // n_selected -> stats[job][0].
 #define IPB_HSEL_THREADS 512
-__global__ void __launch_bounds__(IPB_HSEL_THREADS)
+__global__ void __launch_bounds__(IPB_HSEL_THREADS, 2)
 ipb_k_hist_tail(const unsigned short* __restrict__ planes, int H, int W,
                 const IpbPlanePass* __restrict__ passes, const IpbHistJob* __restrict__ jobs,
                 const IpbHistWin* __restrict__ win, int rows_per_chunk,
@@ -385,18 +397,25 @@ ipb_k_hist_tail(const unsigned short* __restrict__ planes, int H, int W,
     const int y_beg = (int)blockIdx.x * rows_per_chunk;
     int y_end = y_beg + rows_per_chunk;
     if (y_end > H) y_end = H;
-    IpbHistJob jb[IPB_HSEL_MAXJ];
-    IpbHistWin wn[IPB_HSEL_MAXJ];
+    // per job only what the inner loop needs (registers): pattern (-1 = not windowed), stride, window
+    int pat[IPB_HSEL_MAXJ], kk[IPB_HSEL_MAXJ];
+    unsigned wlo[IPB_HSEL_MAXJ], whi[IPB_HSEL_MAXJ];
     const unsigned* ub[IPB_HSEL_MAXJ];
-    bool need = false;
+    bool need = false, moments = false;
 #pragma unroll
     for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+        pat[u] = -1; kk[u] = 1; wlo[u] = 0; whi[u] = 0; ub[u] = nullptr;
         if (u < pp.n_jobs) {
-            jb[u] = jobs[pp.job[u]];
-            wn[u] = win[pp.job[u]];
-            ub[u] = (jb[u].pattern == IPB_PAT_MASKED) ? union_bits + (size_t)jb[u].mask_frame * H * union_wpr : nullptr;
-            need = need || wn[u].mode == IPB_HSEL_WINDOWED || jb[u].moments;
-        } else { jb[u].pattern = -1; jb[u].moments = 0; jb[u].k = 1; wn[u].mode = IPB_HSEL_NONE; wn[u].wlo = wn[u].whi = 0; ub[u] = nullptr; }
+            const IpbHistJob j = jobs[pp.job[u]];
+            const IpbHistWin w = win[pp.job[u]];
+            moments = moments || j.moments != 0;
+            if (w.mode == IPB_HSEL_WINDOWED) {
+                pat[u] = j.pattern; kk[u] = j.k > 0 ? j.k : 1;
+                wlo[u] = (unsigned)w.wlo; whi[u] = (unsigned)w.whi;
+                ub[u] = (j.pattern == IPB_PAT_MASKED) ? union_bits + (size_t)j.mask_frame * H * union_wpr : nullptr;
+            }
+            need = need || w.mode == IPB_HSEL_WINDOWED || j.moments;
+        }
     }
     if (!need || y_beg >= y_end) return;
     for (int b = threadIdx.x; b < pp.n_jobs * IPB_HSEL_WIN; b += blockDim.x) sh[b] = 0;
@@ -406,59 +425,123 @@ ipb_k_hist_tail(const unsigned short* __restrict__ planes, int H, int W,
     const unsigned short* img2 = (pp.sat_min > 0 && pp.excl_plane1 > 0) ? planes + (size_t)(pp.excl_plane1 - 1) * H * W : nullptr;
     unsigned below[IPB_HSEL_MAXJ], inside[IPB_HSEL_MAXJ], above[IPB_HSEL_MAXJ];
     unsigned long long s1 = 0, s2 = 0;
-    bool moments = false;
 #pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) { below[u] = inside[u] = above[u] = 0; moments = moments || jb[u].moments; }
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) { below[u] = inside[u] = above[u] = 0; }
     const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0) && ((((size_t)img2) & 15) == 0);
     const int step = vec_ok ? 8 : 1;
     const int upr = vec_ok ? (W >> 3) : W;                            // units (vectors or pixels) per row
-    const long long nunits = (long long)(y_end - y_beg) * upr;
-    for (long long i = threadIdx.x; i < nunits; i += blockDim.x) {
-        const int y = y_beg + (int)(i / upr);
-        const int x0 = ((int)(i % upr)) * step;
-        unsigned w[4] = {0, 0, 0, 0}, w2[4] = {0, 0, 0, 0};
-        if (vec_ok) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + x0));
-            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
-            if (img2) {
-                const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + x0));
-                w2[0] = q2.x; w2[1] = q2.y; w2[2] = q2.z; w2[3] = q2.w;
-            }
-        } else {
-            w[0] = img[(size_t)y * W + x0];
-            if (img2) w2[0] = img2[(size_t)y * W + x0];
-        }
-        unsigned sel[IPB_HSEL_MAXJ];
+    const int dy = (int)blockDim.x / upr, dx = (int)blockDim.x % upr;
+    int y = y_beg + (int)threadIdx.x / upr, xu = (int)threadIdx.x % upr;
+    unsigned whi_all = 0;                      // pixels >= whi_all are "above" for every windowed job
+#pragma unroll
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) if (pat[u] >= 0 && whi[u] > whi_all) whi_all = whi[u];
+
+    // selection masks of one unit (8-pixel group or single pixel) for every windowed job
+    auto select = [&](int y, int x0, unsigned (&sel)[IPB_HSEL_MAXJ]) {
 #pragma unroll
         for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
             sel[u] = 0;
-            if (wn[u].mode != IPB_HSEL_WINDOWED) continue;
-            const int k = jb[u].k > 0 ? jb[u].k : 1;
-            if (jb[u].pattern == IPB_PAT_FULL) sel[u] = 0xffu;
-            else if (jb[u].pattern == IPB_PAT_STRIDE1D) {
-                const long long flat = (long long)y * W + x0;
-                const int first = (int)((k - (flat % k)) % k);
+            if (pat[u] < 0) continue;
+            const int k = kk[u];
+            if (pat[u] == IPB_PAT_FULL) sel[u] = 0xffu;
+            else if (pat[u] == IPB_PAT_STRIDE1D) {
+                const unsigned long long flat = (unsigned long long)y * W + x0;
+                const unsigned fm = flat < 0xffffffffull ? (unsigned)flat % (unsigned)k : (unsigned)(flat % (unsigned long long)k);
+                const int first = (int)(((unsigned)k - fm) % (unsigned)k);
                 for (int t = first; t < step; t += k) sel[u] |= 1u << t;
-            } else if (jb[u].pattern == IPB_PAT_MASKED) {
+            } else if (pat[u] == IPB_PAT_MASKED) {
                 sel[u] = (ub[u][(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
             }
             if (!vec_ok) sel[u] &= 1u;
         }
+    };
+    // exact classification of one pixel for every job that selects it
+    auto classify = [&](unsigned v, int t, const unsigned (&sel)[IPB_HSEL_MAXJ]) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            if (t >= step) break;
-            const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
-            const unsigned o = (t & 1) ? (w2[t >> 1] >> 16) : (w2[t >> 1] & 0xffffu);
-            if (moments) { s1 += v; s2 += (unsigned long long)v * v; }
-            const bool keep = v < sat_min && o < sat_min;
+        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+            if ((sel[u] >> t) & 1u) {
+                if (v < wlo[u]) ++below[u];
+                else if (v >= whi[u]) ++above[u];
+                else { ++inside[u]; atomicAdd(&sh[u * IPB_HSEL_WIN + (v - wlo[u])], 1u); }
+            }
+        }
+    };
+    if (vec_ok) {
+        // the common pixel is above every window (low percentiles): one vector minimum decides
+        // that for all eight pixels; only pixels below whi_all are classified one by one
+        auto process = [&](int y, int x0, const uint4& q, const uint4& q2) {
+            const unsigned w0 = q.x, w1 = q.y, w2 = q.z, w3 = q.w;
+            unsigned sel[IPB_HSEL_MAXJ];
+            select(y, x0, sel);
+            if (moments) {
+                const unsigned wv[4] = {w0, w1, w2, w3};
 #pragma unroll
-            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-                if (((sel[u] >> t) & 1u) && keep) {
-                    if (v < (unsigned)wn[u].wlo) ++below[u];
-                    else if (v >= (unsigned)wn[u].whi) ++above[u];
-                    else { ++inside[u]; atomicAdd(&sh[u * IPB_HSEL_WIN + (int)v - wn[u].wlo], 1u); }
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned a = wv[j] & 0xffffu, b = wv[j] >> 16;
+                    s1 += a + b;
+                    s2 += (unsigned long long)a * a + (unsigned long long)b * b;
                 }
             }
+            unsigned keep = 0xffu;
+            if (pp.sat_min > 0) {
+                const unsigned wv[4] = {w0, w1, w2, w3}, ov[4] = {q2.x, q2.y, q2.z, q2.w};
+                keep = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const unsigned v = (t & 1) ? (wv[t >> 1] >> 16) : (wv[t >> 1] & 0xffffu);
+                    const unsigned o = (t & 1) ? (ov[t >> 1] >> 16) : (ov[t >> 1] & 0xffffu);
+                    keep |= (v < sat_min && o < sat_min) ? (1u << t) : 0u;
+                }
+            }
+            const unsigned m01 = umin(umin(w0 & 0xffffu, w0 >> 16), umin(w1 & 0xffffu, w1 >> 16));
+            const unsigned m23 = umin(umin(w2 & 0xffffu, w2 >> 16), umin(w3 & 0xffffu, w3 >> 16));
+            unsigned low = 0;
+            if (umin(m01, m23) < whi_all) {
+                const unsigned wv[4] = {w0, w1, w2, w3};
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const unsigned v = (t & 1) ? (wv[t >> 1] >> 16) : (wv[t >> 1] & 0xffffu);
+                    low |= (v < whi_all) ? (1u << t) : 0u;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) above[u] += (unsigned)__popc(sel[u] & keep & ~low);
+            unsigned todo = low & keep;
+            while (todo) {
+                const int t = __ffs((int)todo) - 1;
+                todo &= todo - 1;
+                const unsigned word = t < 4 ? (t < 2 ? w0 : w1) : (t < 6 ? w2 : w3);
+                classify((t & 1) ? (word >> 16) : (word & 0xffffu), t, sel);
+            }
+        };
+        while (y < y_end) {
+            int ys[2], xs[2];
+            bool ok[2];
+            uint4 q[2], q2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                ys[u] = y; xs[u] = xu << 3;
+                ok[u] = y < y_end;
+                q[u] = make_uint4(0, 0, 0, 0); q2[u] = make_uint4(0, 0, 0, 0);
+                if (ok[u]) {
+                    q[u] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + xs[u]));
+                    if (img2) q2[u] = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + xs[u]));
+                }
+                xu += dx; y += dy;
+                if (xu >= upr) { xu -= upr; ++y; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) if (ok[u]) process(ys[u], xs[u], q[u], q2[u]);
+        }
+    } else {
+        for (; y < y_end; xu += dx, y += dy, y += (xu >= upr) ? 1 : 0, xu -= (xu >= upr) ? upr : 0) {
+            const unsigned v = img[(size_t)y * W + xu];
+            const unsigned o = img2 ? (unsigned)img2[(size_t)y * W + xu] : 0u;
+            if (moments) { s1 += v; s2 += (unsigned long long)v * v; }
+            if (!(v < sat_min && o < sat_min)) continue;
+            unsigned sel[IPB_HSEL_MAXJ];
+            select(y, xu, sel);
+            classify(v, 0, sel);
         }
     }
     __syncthreads();
@@ -512,35 +595,20 @@ ipb_k_hist_select_q(const IpbQJob* __restrict__ qjobs, const IpbHistWin* __restr
     const int per = windowed ? IPB_HSEL_WIN / 256 : IPB_HIST_BINS / 256;
     const unsigned long long base = windowed ? cnt[(size_t)qj.hist * 4] : 0ull;
     const int v0 = windowed ? wn.wlo : 0;
-    __shared__ unsigned long long part[256];
+    __shared__ unsigned long long red_u[32];
     __shared__ int res[2];
     const int t = threadIdx.x;
-    unsigned long long mine = 0;
-    for (int b = 0; b < per; ++b) mine += h[t * per + b];
-    part[t] = mine;
     if (t < 2) res[t] = -1;
-    __syncthreads();
-    if (t == 0) {
-        unsigned long long acc = base;
-        for (int i = 0; i < 256; ++i) { unsigned long long c = part[i]; part[i] = acc; acc += c; }
-    }
-    __syncthreads();
     IpbQIdx qi;
     qi.prev = 0; qi.next = 0; qi.gamma = 0.f;
-    if (n > 0) {
+    if (n > 0) {                                              // block-uniform
         qi = ipb_np_qidx_f32((long long)n, qj.q32);
-        const unsigned long long lo = part[t], hi = lo + mine;
-        const long long want[2] = {qi.prev, qi.next};
-        for (int w = 0; w < 2; ++w) {
-            const unsigned long long kk = (unsigned long long)want[w];
-            if (kk >= lo && kk < hi) {
-                unsigned long long acc = lo;
-                for (int b = 0; b < per; ++b) {
-                    acc += h[t * per + b];
-                    if (kk < acc) { res[w] = v0 + t * per + b; break; }
-                }
-            }
-        }
+        // ranks relative to the first counter of the scanned histogram; a rank below the window
+        // (prev < base) wraps to a huge value and is never found -> reported as a miss
+        const unsigned long long want[2] = {(unsigned long long)qi.prev - base, (unsigned long long)qi.next - base};
+        const unsigned nbins = (unsigned)(per * 256);
+        ipb_locate_ranks(nbins / 32, want, 2, red_u, [&](unsigned i) { return h[i]; },
+                         [&](int r, unsigned i, unsigned) { res[r] = v0 + (int)i; });
     }
     __syncthreads();
     if (t == 0) {

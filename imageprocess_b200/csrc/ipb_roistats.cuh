@@ -46,6 +46,7 @@
 #pragma once
 #include "ipb_rt.cuh"
 #include "ipb_exact.cuh"
+#include "ipb_scan.cuh"
 
 #define IPB_SRC_U16 0
 #define IPB_SRC_F32 1
@@ -262,48 +263,6 @@ __device__ __forceinline__ void ipb_rs_regroup(IpbRsSel& s, int nr) {
     s.gn = m > 0 ? m : 1;
 }
 
-// Warp-cooperative scan of `nrows` rows of 32 counters: finds, for every wanted rank, the
-// counter that holds it.  value(i) = counter i (0 beyond the end).  hit(r, i, rank_inside).
-template <typename V, typename HIT>
-__device__ __forceinline__ void ipb_rs_locate(unsigned nrows, const unsigned long long* want, int nr,
-                                              unsigned long long* red_u, V value, HIT hit) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const unsigned rpw = (nrows + (unsigned)nwarps - 1u) / (unsigned)nwarps;
-    const unsigned row0 = (unsigned)warp * rpw;
-    unsigned row1 = row0 + rpw;
-    if (row1 > nrows) row1 = nrows;
-    unsigned long long band = 0;
-    for (unsigned row = row0; row < row1; ++row) band += value((row << 5) + (unsigned)lane);
-    band = ipb_warp_sum(band);
-    __syncthreads();
-    if (lane == 0) red_u[warp] = band;
-    __syncthreads();
-    unsigned long long base = 0;
-    for (int i = 0; i < warp; ++i) base += red_u[i];
-    bool mine = false;
-    for (int r = 0; r < nr; ++r) mine = mine || (want[r] >= base && want[r] < base + band);
-    if (mine) {                                                            // warp-uniform
-        unsigned long long run = base;
-        for (unsigned row = row0; row < row1; ++row) {
-            const unsigned i = (row << 5) + (unsigned)lane;
-            const unsigned v = value(i);
-            unsigned incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
-            const unsigned rowtot = __shfl_sync(IPB_FULL, incl, 31);
-            for (int r = 0; r < nr; ++r) {
-                const unsigned long long kk = want[r];
-                if (kk >= run && kk < run + rowtot) {
-                    const unsigned off = (unsigned)(kk - run);
-                    if (off >= incl - v && off < incl) hit(r, i, off - (incl - v));
-                }
-            }
-            run += rowtot;
-        }
-    }
-    __syncthreads();
-}
-
 template <int SRC>
 __global__ void __launch_bounds__(IPB_RS_THREADS, 1)
 ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __restrict__ jobs,
@@ -448,7 +407,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         // ranks: the word first, then the low / high counter inside the word
         unsigned long long want[IPB_RS_MAXR];
         for (int r = 0; r < IPB_RS_MAXR; ++r) want[r] = sel.rank[r];
-        ipb_rs_locate(1024u, want, nr, red_u,
+        ipb_locate_ranks(1024u, want, nr, red_u,
                       [&](unsigned i) { const unsigned w = h16[i]; return (w & 0xffffu) + (w >> 16); },
                       [&](int r, unsigned i, unsigned inside) { sel.prefix[r] = 2u * i + (inside >= (h16[i] & 0xffffu) ? 1u : 0u); });
         kbase = 0u;                                                // prefixes are absolute keys
@@ -512,7 +471,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         {
             unsigned long long want[IPB_RS_MAXR];
             for (int r = 0; r < IPB_RS_MAXR; ++r) want[r] = sel.rank[r];
-            ipb_rs_locate((nb + 31u) >> 5, want, nr, red_u,
+            ipb_locate_ranks((nb + 31u) >> 5, want, nr, red_u,
                           [&](unsigned i) { return i < nb ? whist[i] : 0u; },
                           [&](int r, unsigned i, unsigned inside) { sel.prefix[r] = i; sel.rank[r] = (unsigned long long)inside; });
         }

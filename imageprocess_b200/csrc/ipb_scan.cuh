@@ -1,0 +1,47 @@
+// ipb_scan.cuh -- block-wide rank location in a histogram, shared by the percentile kernels.
+#pragma once
+#include "ipb_rt.cuh"
+
+// Warp-cooperative scan of `nrows` rows of 32 counters: finds, for every wanted rank, the
+// counter that holds it.  value(i) = counter i (0 beyond the end).  hit(r, i, rank_inside).
+template <typename V, typename HIT>
+__device__ __forceinline__ void ipb_locate_ranks(unsigned nrows, const unsigned long long* want, int nr,
+                                              unsigned long long* red_u, V value, HIT hit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned rpw = (nrows + (unsigned)nwarps - 1u) / (unsigned)nwarps;
+    const unsigned row0 = (unsigned)warp * rpw;
+    unsigned row1 = row0 + rpw;
+    if (row1 > nrows) row1 = nrows;
+    unsigned long long band = 0;
+#pragma unroll 8
+    for (unsigned row = row0; row < row1; ++row) band += value((row << 5) + (unsigned)lane);   // independent loads
+    band = ipb_warp_sum(band);
+    __syncthreads();
+    if (lane == 0) red_u[warp] = band;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int i = 0; i < warp; ++i) base += red_u[i];
+    bool mine = false;
+    for (int r = 0; r < nr; ++r) mine = mine || (want[r] >= base && want[r] < base + band);
+    if (mine) {                                                            // warp-uniform
+        unsigned long long run = base;
+        for (unsigned row = row0; row < row1; ++row) {
+            const unsigned i = (row << 5) + (unsigned)lane;
+            const unsigned v = value(i);
+            unsigned incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+            const unsigned rowtot = __shfl_sync(IPB_FULL, incl, 31);
+            for (int r = 0; r < nr; ++r) {
+                const unsigned long long kk = want[r];
+                if (kk >= run && kk < run + rowtot) {
+                    const unsigned off = (unsigned)(kk - run);
+                    if (off >= incl - v && off < incl) hit(r, i, off - (incl - v));
+                }
+            }
+            run += rowtot;
+        }
+    }
+    __syncthreads();
+}
+
