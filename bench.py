@@ -194,9 +194,17 @@ def run_ours(args):
     job = batch.FrameBatchJob(eng, shape, stages=("fret", "int", "fa"), fret_p=FRET_P, int_task=INT_TASK,
                               fa_params=FA_PARAMS, fa_px=FA_PX)
 
-    def run_step():
-        res = job.run(planes, polys_pf)
-        batch.fa_table(res, job.fa_cfg)          # per-adhesion table with the reference's dtypes
+    tab_dev = torch.device(f"cuda:{local}")
+
+    def consume(res):
+        """Host side of one step: per-adhesion table with the reference's dtypes; with N > 1 ranks
+        the small row tables are gathered to rank 0 (the only collective on this path)."""
+        batch.fa_table(res, job.fa_cfg)
+        if dist is not None:
+            from imageprocess_b200 import parallel
+            parallel.gather_tables(res.fret_stat.reshape(-1), dist, tab_dev)
+            parallel.gather_tables(res.int_stat.reshape(-1), dist, tab_dev)
+            parallel.gather_tables(res.fa_comps, dist, tab_dev)
         return res.d2h_bytes
 
     def barrier():
@@ -205,13 +213,11 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(loop, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        d2h = 0
-        for _ in range(steps):
-            d2h = fn()
+        d2h = loop(steps)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -222,25 +228,58 @@ def run_ours(args):
         barrier()
         return ms, d2h
 
-    def step_resident():
-        return run_step()
+    def loop_resident(steps):
+        """Steps over HBM-resident frames; step k+1 is submitted before step k's tables are
+        unpacked, as consecutive batches of a time-lapse are in the product."""
+        prev, d2h = None, 0
+        for _ in range(steps):
+            tk = job.submit(planes, polys_pf)
+            if prev is not None:
+                d2h = consume(job.collect(prev))
+            prev = tk
+        return consume(job.collect(prev))
 
-    def step_e2e():
-        eng.mem.upload_async(planes, pinned_t)          # H2D of this step's inputs (pinned)
-        return run_step()                               # tables come back D2H inside run()
+    # end-to-end: host frames in pinned memory, H2D of step k+1 on a copy stream while step k computes
+    planes_b = [planes, eng.mem.empty(shape, np.uint16)]
+    copy_stream = torch.cuda.Stream(device=tab_dev)
 
-    for _ in range(args.warmup):
-        step_resident()
+    def loop_e2e(steps):
+        main = torch.cuda.current_stream(tab_dev)
+        up = [None, None]          # upload-finished events per buffer
+        done = [None, None]        # compute-finished events per buffer
+        def upload(k):
+            b = k & 1
+            with torch.cuda.stream(copy_stream):
+                if done[b] is not None:
+                    copy_stream.wait_event(done[b])
+                eng.mem.upload_async(planes_b[b], pinned_t)
+                up[b] = torch.cuda.Event()
+                up[b].record(copy_stream)
+        upload(0)
+        prev, d2h = None, 0
+        for k in range(steps):
+            if k + 1 < steps:
+                upload(k + 1)
+            b = k & 1
+            main.wait_event(up[b])
+            tk = job.submit(planes_b[b], polys_pf)
+            done[b] = torch.cuda.Event()
+            done[b].record(main)
+            if prev is not None:
+                d2h = consume(job.collect(prev))
+            prev = tk
+        return consume(job.collect(prev))
+
+    loop_resident(args.warmup)
     torch.cuda.synchronize()
     launches0 = eng.launches
     with ClockSampler(local) as clk:
         eng.profile_start()
-        ms, d2h = timed(step_resident, args.steps)
+        ms, d2h = timed(loop_resident, args.steps)
         prof = eng.profile_stop()
     launches = eng.launches - launches0
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    loop_e2e(min(args.warmup, 2))
+    ms_e2e, _ = timed(loop_e2e, args.steps)
 
     mpix_total = world * F * args.steps * H * W / 1e6
     value = mpix_total / (ms / 1e3)
@@ -267,14 +306,21 @@ def run_ours(args):
         kern = {k: {"calls": v[0], "ms": round(v[1], 4), "share": round(v[1] / max(ms, 1e-9), 4)}
                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
         if dom is not None:
+            # the entry point with the largest share of the step; bytes and time are both taken
+            # per step (an entry point may be called more than once per step)
             name, (ncalls, tot_ms) = dom
-            per_launch_ms = tot_ms / max(1, ncalls)
+            per_step_ms = tot_ms / max(1, args.steps)
             alg_bytes = job.algorithmic_bytes(name)
-            achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9
+            achieved = alg_bytes / (per_step_ms / 1e3) / 1e9
+            traffic = None
+            try:                   # dram bytes per step from the committed ncu --set full capture
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(name)
+            except Exception:
+                pass
             line["roofline"] = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak,
-                                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                                "launch_ms": per_launch_ms}
+                                "launch_ms": per_step_ms, "calls_per_step": ncalls / max(1, args.steps)}
         line["pipeline_roofline"] = {"bytes_per_px": BYTES_PER_PX,
                                      "achieved_gbs": value / world * 1e6 * BYTES_PER_PX / 1e9,
                                      "frac_of_peak": value / world * 1e6 * BYTES_PER_PX / 1e9 / peak}

@@ -70,6 +70,11 @@ def _digest(polys):
     return h.digest()
 
 
+class _Ticket:
+    """A submitted, not yet collected step."""
+    pass
+
+
 class BatchResult:
     """Host tables of one run() (numpy) + handles of the device-resident images."""
     pass
@@ -91,6 +96,7 @@ class FrameBatchJob:
         self._bufs = {}
         self._plans = {}
         self.window_misses = 0
+        self._slot = 0
         # percentiles by sampling (ipb_hist_select) instead of full histograms: exact either way;
         # off by default until its tail pass beats the full-histogram kernel
         self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "0"))) if hist_select is None else bool(hist_select)
@@ -410,9 +416,12 @@ class FrameBatchJob:
         return pl
 
     # ------------------------------------------------------------------ the step
-    def run(self, planes, polys_per_frame, full_hist=False):
-        """One step.  full_hist = True forces exact full-range histograms instead of the
-        sample-selected windows (used automatically if a window ever misses a rank)."""
+    def submit(self, planes, polys_per_frame, full_hist=False):
+        """Enqueues one step on the current stream and returns a ticket for collect(); nothing
+        here waits for the device, so consecutive steps of a time-lapse overlap the host's table
+        unpacking with the device's next batch (outputs are double-buffered: collect a ticket
+        before submitting the step after next).  full_hist = True forces exact full-range
+        histograms instead of sample-selected windows (automatic after a window miss)."""
         eng, mem, F, C, H, W = self.eng, self.mem, self.F, self.C, self.H, self.W
         st = self.stages
         pl = self._plan_for(polys_per_frame)
@@ -529,14 +538,36 @@ class FrameBatchJob:
         if "fa" in st:
             res.fa_rect, res.fa_crops = pl.fa_rect, pl.fa_crops
 
-        # ---- results: one packed D2H (+ exact-size adhesion table)
-        pout_np, pout_t = self._pinned("pin_out", O.size)
+        # ---- results: one packed D2H (+ a first slice of the adhesion table), then an event;
+        #      the host reads them in collect() while the device may already run the next step
+        slot = self._slot
+        self._slot ^= 1
+        pout_np, pout_t = self._pinned(f"pin_out{slot}", O.size)
         mem.download_async(pout_t, d_out, O.size)
-        mem.sync()
-        OV = lambda name: O.view(pout_np, name)
+        tk = _Ticket()
+        tk.pl, tk.res, tk.pout_np, tk.fa_ran = pl, res, pout_np, fa_ran
+        tk.planes, tk.polys, tk.full_hist = planes, polys_per_frame, full_hist
+        tk.d_comps, tk.pc_np, tk.pc_rows = None, None, 0
+        if fa_ran:
+            tk.d_comps = d_comps
+            tk.pc_rows = min(pl.comp_cap, max(4096, 128 * NR))       # usual batches fit; collect() fetches the rest
+            tk.pc_np, pc_t = self._pinned(f"pin_comps{slot}", COMP.itemsize * tk.pc_rows)
+            mem.download_async(pc_t, d_comps, COMP.itemsize * tk.pc_rows)
+        tk.event = mem.event()
+        tk.event.record()
+        return tk
+
+    def collect(self, tk):
+        """Waits for a submitted step and unpacks its host tables."""
+        mem, F, st = self.mem, self.F, self.stages
+        pl, res, O = tk.pl, tk.res, tk.pl.O
+        NR, NU, NP, Ci = pl.NR, pl.NU, pl.NP, pl.Ci
+        P_FRET, P_INT, P_FA = pl.P_FRET, pl.P_INT, pl.P_FA
+        tk.event.synchronize()
+        OV = lambda name: O.view(tk.pout_np, name)
         if int(OV("miss")[0]) != 0:                        # a sampled window missed a wanted rank: exact rerun
             self.window_misses += 1
-            return self.run(planes, polys_per_frame, full_hist=True)
+            return self.run(tk.planes, tk.polys, full_hist=True)
         params = OV("params")[:NP].copy()
         res.d2h_bytes = O.size
         if "fret" in st:
@@ -557,19 +588,26 @@ class FrameBatchJob:
         if "fa" in st:
             comp_off = OV("comp_off")[: NR + 1].copy()
             res.fa_comp_off = comp_off
-            total = int(comp_off[-1]) if fa_ran else 0
-            if fa_ran and total > pl.comp_cap:
+            total = int(comp_off[-1]) if tk.fa_ran else 0
+            if tk.fa_ran and total > pl.comp_cap:
                 raise RuntimeError("fa_segment: component table overflow")
             if total:
-                nb = COMP.itemsize * total
-                pc_np, pc_t = self._pinned("pin_comps", nb)
-                mem.download_async(pc_t, d_comps, nb)
-                mem.sync()
-                res.fa_comps = pc_np[:nb].view(COMP).copy()
-                res.d2h_bytes += nb
+                if total <= tk.pc_rows:
+                    res.fa_comps = tk.pc_np[: COMP.itemsize * total].view(COMP).copy()
+                else:                                       # more adhesions than the pre-fetched slice
+                    nb = COMP.itemsize * total
+                    pc_np, pc_t = self._pinned("pin_comps_all", nb)
+                    mem.download_async(pc_t, tk.d_comps, nb)
+                    mem.sync()
+                    res.fa_comps = pc_np[:nb].view(COMP).copy()
+                res.d2h_bytes += COMP.itemsize * total
             else:
                 res.fa_comps = np.zeros(0, dtype=COMP)
         return res
+
+    def run(self, planes, polys_per_frame, full_hist=False):
+        """One synchronous step: submit + collect."""
+        return self.collect(self.submit(planes, polys_per_frame, full_hist))
 
     def _ch_name(self, ci):
         names = getattr(self, "ch_names", None)
