@@ -97,6 +97,7 @@ class FrameBatchJob:
         self._plans = {}
         self.window_misses = 0
         self._slot = 0
+        self.fa_path = 0            # ipb_fa_segment path: 0 auto, 1 one CTA per crop, 2 one kernel per phase
         # percentiles by sampling (ipb_hist_select) instead of full histograms: exact either way;
         # off by default until its tail pass beats the full-histogram kernel
         self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "0"))) if hist_select is None else bool(hist_select)
@@ -527,7 +528,7 @@ class FrameBatchJob:
                      int(cfgf["close_radius"]) if cfgf["close_radius"] > 0 else 0,
                      bwA.ptr, bwB.ptr, d_L.ptr, d_cs.ptr, rootb.ptr, d_rr.ptr, d_rb.ptr, d_cc.ptr,
                      bwF.ptr, op("comp_off"), d_comps.ptr, pl.comp_cap,
-                     d_lab.ptr if d_lab is not None else None, stream)
+                     d_lab.ptr if d_lab is not None else None, int(self.fa_path), stream)
             res.fa_bw = ops_view(bwF, np.uint32, (words,), mem)
             res.fa_labels = ops_view(d_lab, np.int32, (pl.total_px,), mem) if d_lab is not None else None
             fa_ran = True

@@ -274,8 +274,12 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const vo
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    IPB_LAUNCH(ipb_k_fret_pixels, dim3((unsigned)blocks, (unsigned)n_frames), dim3(256), 0, stream, planes, n_frames, H, W,
-               cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr);
+    if (Ralt)
+        IPB_LAUNCH(ipb_k_fret_pixels<true>, dim3((unsigned)blocks, (unsigned)n_frames), dim3(256), 0, stream, planes, n_frames, H, W,
+                   cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr);
+    else
+        IPB_LAUNCH(ipb_k_fret_pixels<false>, dim3((unsigned)blocks, (unsigned)n_frames), dim3(256), 0, stream, planes, n_frames, H, W,
+                   cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr);
     return ipb_check_launch("ipb_k_fret_pixels");
 }
 
@@ -318,9 +322,10 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    uint32_t* bw_a, uint32_t* bw_b, int32_t* L, uint32_t* csize, uint32_t* rootbits,
                    int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
                    uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
-                   int32_t* labels, void* stream)
+                   int32_t* labels, int path, void* stream)
 {
     if (n_crops <= 0) return IPB_OK;
+    IPB_REQUIRE(path >= 0 && path <= 2, "ipb_fa_segment: path %d not in 0..2", path);
     IPB_REQUIRE(n_crops <= 65535, "ipb_fa_segment: n_crops %d out of range", n_crops);
     IPB_REQUIRE(crops && planes && fa_params && roi_mask && bw_a && bw_b && L && csize && rootbits &&
                 row_roots && row_base && crop_count && bw_final && comp_off && comps,
@@ -330,19 +335,6 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
     const IpbCrop* cr = (const IpbCrop*)crops;
     const dim3 grid(ipb_div_up(max_rows, IPB_FA_ROWS), (unsigned)n_crops), block(IPB_FA_THREADS);
     int rc;
-    IPB_LAUNCH(ipb_k_fa_threshold, grid, block, 0, stream, cr, planes, H, W, fa_params, roi_mask, bw_a);
-    if ((rc = ipb_check_launch("ipb_k_fa_threshold"))) return rc;
-    uint32_t* cur = bw_a;
-    uint32_t* other = bw_b;
-    if (min_size > 0) {
-        IPB_LAUNCH(ipb_k_ccl_init, grid, block, 0, stream, cr, (const unsigned*)cur, L, csize);
-        IPB_LAUNCH(ipb_k_ccl_merge<4>, grid, block, 0, stream, cr, (const unsigned*)cur, L);
-        IPB_LAUNCH(ipb_k_ccl_flatten_size, grid, block, 0, stream, cr, (const unsigned*)cur, L, csize);
-        IPB_LAUNCH(ipb_k_fa_size_filter, grid, block, 0, stream, cr, (const unsigned*)cur, (const int*)L,
-                   (const unsigned*)csize, min_size, other);
-        if ((rc = ipb_check_launch("ipb_fa small-object removal"))) return rc;
-        uint32_t* t = cur; cur = other; other = t;
-    }
     IpbDisk disk;
     memset(&disk, 0, sizeof(disk));
     disk.r = close_radius;
@@ -351,18 +343,41 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
         while ((k + 1) * (k + 1) + dy * dy <= close_radius * close_radius) ++k;
         disk.halfw[dy + close_radius] = k;
     }
-    if (close_radius > 0) {
-        IPB_LAUNCH(ipb_k_bits_morph<0>, grid, block, 0, stream, cr, (const unsigned*)cur, disk, other);
-        IPB_LAUNCH(ipb_k_bits_morph<1>, grid, block, 0, stream, cr, (const unsigned*)other, disk, bw_final);
+    // many small crops (cell ROIs): one CTA per crop runs the whole chain; few / huge crops
+    // (the mosaic): one kernel per phase, each crop spread over the chip
+    const bool fused = path == 1 || (path == 0 && n_crops >= 64 && max_rows <= 1024);
+    if (fused) {
+        IPB_LAUNCH(ipb_k_fa_fused, dim3(n_crops), dim3(IPB_FA_FUSED_THREADS), 0, stream, cr, planes, H, W, fa_params,
+                   roi_mask, min_size, disk, bw_a, bw_b, L, csize, rootbits, row_roots, row_base, crop_count, bw_final);
+        if ((rc = ipb_check_launch("ipb_k_fa_fused"))) return rc;
     } else {
-        IPB_LAUNCH(ipb_k_bits_morph<0>, grid, block, 0, stream, cr, (const unsigned*)cur, disk, bw_final);
+        IPB_LAUNCH(ipb_k_fa_threshold, grid, block, 0, stream, cr, planes, H, W, fa_params, roi_mask, bw_a);
+        if ((rc = ipb_check_launch("ipb_k_fa_threshold"))) return rc;
+        uint32_t* cur = bw_a;
+        uint32_t* other = bw_b;
+        if (min_size > 0) {
+            IPB_LAUNCH(ipb_k_ccl_init, grid, block, 0, stream, cr, (const unsigned*)cur, L, csize);
+            IPB_LAUNCH(ipb_k_ccl_merge<4>, grid, block, 0, stream, cr, (const unsigned*)cur, L);
+            IPB_LAUNCH(ipb_k_ccl_flatten_size, grid, block, 0, stream, cr, (const unsigned*)cur, L, csize);
+            IPB_LAUNCH(ipb_k_fa_size_filter, grid, block, 0, stream, cr, (const unsigned*)cur, (const int*)L,
+                       (const unsigned*)csize, min_size, other);
+            if ((rc = ipb_check_launch("ipb_fa small-object removal"))) return rc;
+            uint32_t* t = cur; cur = other; other = t;
+        }
+        if (close_radius > 0) {
+            IPB_LAUNCH(ipb_k_bits_morph<0>, grid, block, 0, stream, cr, (const unsigned*)cur, disk, other);
+            IPB_LAUNCH(ipb_k_bits_morph<1>, grid, block, 0, stream, cr, (const unsigned*)other, disk, bw_final);
+        } else {
+            IPB_LAUNCH(ipb_k_bits_morph<0>, grid, block, 0, stream, cr, (const unsigned*)cur, disk, bw_final);
+        }
+        if ((rc = ipb_check_launch("ipb_k_bits_morph"))) return rc;
+        IPB_CUDA_TRY(cudaMemsetAsync(row_roots, 0, sizeof(int32_t) * (size_t)total_rows, (cudaStream_t)stream), "memset row_roots");
+        IPB_LAUNCH(ipb_k_ccl_init, grid, block, 0, stream, cr, (const unsigned*)bw_final, L, (unsigned*)nullptr);
+        IPB_LAUNCH(ipb_k_ccl_merge<8>, grid, block, 0, stream, cr, (const unsigned*)bw_final, L);
+        IPB_LAUNCH(ipb_k_ccl_flatten_roots, grid, block, 0, stream, cr, (const unsigned*)bw_final, L, rootbits, row_roots);
+        IPB_LAUNCH(ipb_k_fa_row_scan, dim3(n_crops), dim3(256), 0, stream, cr, (const int*)row_roots, row_base, crop_count);
+        if ((rc = ipb_check_launch("ipb_fa labelling"))) return rc;
     }
-    if ((rc = ipb_check_launch("ipb_k_bits_morph"))) return rc;
-    IPB_CUDA_TRY(cudaMemsetAsync(row_roots, 0, sizeof(int32_t) * (size_t)total_rows, (cudaStream_t)stream), "memset row_roots");
-    IPB_LAUNCH(ipb_k_ccl_init, grid, block, 0, stream, cr, (const unsigned*)bw_final, L, (unsigned*)nullptr);
-    IPB_LAUNCH(ipb_k_ccl_merge<8>, grid, block, 0, stream, cr, (const unsigned*)bw_final, L);
-    IPB_LAUNCH(ipb_k_ccl_flatten_roots, grid, block, 0, stream, cr, (const unsigned*)bw_final, L, rootbits, row_roots);
-    IPB_LAUNCH(ipb_k_fa_row_scan, dim3(n_crops), dim3(256), 0, stream, cr, (const int*)row_roots, row_base, crop_count);
     IPB_LAUNCH(ipb_k_fa_crop_scan, dim3(1), dim3(256), 0, stream, (const int*)crop_count, n_crops, comp_off);
     IPB_LAUNCH(ipb_k_fa_zero_comps, dim3(296), dim3(256), 0, stream, (const int*)comp_off, n_crops, comp_cap, (IpbComp*)comps);
     IPB_LAUNCH(ipb_k_fa_props, grid, block, 0, stream, cr, (const unsigned*)bw_final, (const int*)L,

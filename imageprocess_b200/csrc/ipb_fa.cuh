@@ -113,68 +113,66 @@ __device__ __forceinline__ void ipb_uf_union(int* L, int a, int b) {
     }
 }
 
+// every word (y, j) of the row band [fa_y0, fa_y0 + fa_nrow) of a crop, spread over the CTA
 #define IPB_FA_FOREACH_WORD(crop, ...)                                                         \
     {                                                                                          \
-        const int y_beg_ = (int)blockIdx.x * IPB_FA_ROWS;                                      \
-        int nrow_ = (crop).h - y_beg_;                                                         \
-        if (nrow_ > IPB_FA_ROWS) nrow_ = IPB_FA_ROWS;                                          \
-        for (int i_ = threadIdx.x; i_ < nrow_ * (crop).wpr; i_ += blockDim.x) {                \
-            const int y = y_beg_ + i_ / (crop).wpr, j = i_ % (crop).wpr;                       \
+        for (int i_ = threadIdx.x; i_ < fa_nrow * (crop).wpr; i_ += blockDim.x) {              \
+            const int y = fa_y0 + i_ / (crop).wpr, j = i_ % (crop).wpr;                        \
             __VA_ARGS__                                                                        \
         }                                                                                      \
     }
+// the band of one CTA of the multi-kernel path: IPB_FA_ROWS rows starting at blockIdx.x * IPB_FA_ROWS
+#define IPB_FA_BAND(crop)                                                                      \
+    const int fa_y0 = (int)blockIdx.x * IPB_FA_ROWS;                                           \
+    if (fa_y0 >= (crop).h) return;                                                             \
+    const int fa_nrow = (crop).h - fa_y0 > IPB_FA_ROWS ? IPB_FA_ROWS : (crop).h - fa_y0;
 
 // ---------------------------------------------------------------- 1. threshold & mask
-// warp per word: lane b reads pixel 32 j + b (coalesced 64 B), ballot -> word.
+// a warp owns a row at a time; lane b reads pixel 32 j + b of four consecutive words (four
+// independent coalesced 64-byte loads in flight), ballot -> word.
+__device__ __forceinline__ void ipb_k_fa_threshold_phase(const IpbCrop& c, int fa_y0, int fa_nrow,
+                                                         const unsigned short* planes, int H, int W, const float* fa_params,
+                                                         const unsigned* roi_mask, unsigned* bw)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const float thr = fa_params[(size_t)c.frame * 4 + 3];
+    const unsigned short* img = planes + (size_t)c.plane * H * W;
+    for (int r = warp; r < fa_nrow; r += nwarps) {
+        const int y = fa_y0 + r;
+        const unsigned short* irow = img + (size_t)(c.oy + y) * W + c.ox;
+        const size_t w0 = (size_t)c.bit_off + (size_t)y * c.wpr, m0 = (size_t)c.mask_off + (size_t)y * c.wpr;
+        for (int j0 = 0; j0 < c.wpr; j0 += 4) {
+            unsigned short px[4];
+            bool in[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int x = 32 * (j0 + u) + lane;
+                in[u] = (j0 + u < c.wpr) && x < c.w;
+                px[u] = 0;
+                if (in[u]) px[u] = irow[x];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned word = __ballot_sync(IPB_FULL, in[u] && (float)px[u] > thr);
+                if (lane == 0 && j0 + u < c.wpr) bw[w0 + j0 + u] = word & roi_mask[m0 + j0 + u];
+            }
+        }
+    }
+}
 __global__ void __launch_bounds__(IPB_FA_THREADS)
 ipb_k_fa_threshold(const IpbCrop* __restrict__ crops, const unsigned short* __restrict__ planes,
                    int H, int W, const float* __restrict__ fa_params /* [F][4], [3] = thr */,
                    const unsigned* __restrict__ roi_mask, unsigned* __restrict__ bw)
 {
     const IpbCrop c = crops[blockIdx.y];
-    const int y_beg = (int)blockIdx.x * IPB_FA_ROWS;
-    if (y_beg >= c.h) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    int nrow = c.h - y_beg;
-    if (nrow > IPB_FA_ROWS) nrow = IPB_FA_ROWS;
-    const float thr = fa_params[(size_t)c.frame * 4 + 3];
-    const unsigned short* img = planes + (size_t)c.plane * H * W;
-    const int nitems = nrow * c.wpr;
-    // 4 words per warp-iteration: four independent coalesced pixel loads in flight per lane
-    for (int i0 = warp * 4; i0 < nitems; i0 += nwarps * 4) {
-        unsigned short px[4];
-        bool in[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u;
-            in[u] = false;
-            px[u] = 0;
-            if (i < nitems) {
-                const int y = y_beg + i / c.wpr, j = i % c.wpr, x = 32 * j + lane;
-                in[u] = x < c.w;
-                if (in[u]) px[u] = img[(size_t)(c.oy + y) * W + (c.ox + x)];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u;
-            const unsigned word = __ballot_sync(IPB_FULL, in[u] && (float)px[u] > thr);
-            if (lane == 0 && i < nitems) {
-                const int y = y_beg + i / c.wpr, j = i % c.wpr;
-                const size_t wi = (size_t)c.bit_off + (size_t)y * c.wpr + j;
-                bw[wi] = word & roi_mask[(size_t)c.mask_off + (size_t)y * c.wpr + j];
-            }
-        }
-    }
+    IPB_FA_BAND(c);
+    ipb_k_fa_threshold_phase(c, fa_y0, fa_nrow, planes, H, W, fa_params, roi_mask, bw);
 }
 
 // ---------------------------------------------------------------- 2. CCL
-__global__ void __launch_bounds__(IPB_FA_THREADS)
-ipb_k_ccl_init(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits,
-               int* __restrict__ L, unsigned* __restrict__ csize)
+__device__ __forceinline__ void ipb_k_ccl_init_phase(const IpbCrop& c, int fa_y0, int fa_nrow, const unsigned* bits,
+               int* L, unsigned* csize)
 {
-    const IpbCrop c = crops[blockIdx.y];
-    if ((int)blockIdx.x * IPB_FA_ROWS >= c.h) return;
     IPB_FA_FOREACH_WORD(c, {
         const unsigned* row = bits + c.bit_off + (size_t)y * c.wpr;
         unsigned s = ipb_bits_starts(row, j);
@@ -187,14 +185,19 @@ ipb_k_ccl_init(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ b
         }
     })
 }
+__global__ void __launch_bounds__(IPB_FA_THREADS)
+ipb_k_ccl_init(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits,
+               int* __restrict__ L, unsigned* __restrict__ csize)
+{
+    const IpbCrop c = crops[blockIdx.y];
+    IPB_FA_BAND(c);
+    ipb_k_ccl_init_phase(c, fa_y0, fa_nrow, bits, L, csize);
+}
 
 // unite every run starting in this word with the runs of the previous row it touches
 template <int CONN>
-__global__ void __launch_bounds__(IPB_FA_THREADS)
-ipb_k_ccl_merge(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits, int* __restrict__ L)
+__device__ __forceinline__ void ipb_k_ccl_merge_phase(const IpbCrop& c, int fa_y0, int fa_nrow, const unsigned* bits, int* L)
 {
-    const IpbCrop c = crops[blockIdx.y];
-    if ((int)blockIdx.x * IPB_FA_ROWS >= c.h) return;
     int* Lc = L + c.pix_off;
     IPB_FA_FOREACH_WORD(c, {
         if (y > 0) {
@@ -220,14 +223,19 @@ ipb_k_ccl_merge(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ 
         }
     })
 }
-
-// L[start] = root ; component size accumulated per run (4-conn pass: remove_small_objects)
+template <int CONN>
 __global__ void __launch_bounds__(IPB_FA_THREADS)
-ipb_k_ccl_flatten_size(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits,
-                       int* __restrict__ L, unsigned* __restrict__ csize)
+ipb_k_ccl_merge(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits, int* __restrict__ L)
 {
     const IpbCrop c = crops[blockIdx.y];
-    if ((int)blockIdx.x * IPB_FA_ROWS >= c.h) return;
+    IPB_FA_BAND(c);
+    ipb_k_ccl_merge_phase<CONN>(c, fa_y0, fa_nrow, bits, L);
+}
+
+// L[start] = root ; component size accumulated per run (4-conn pass: remove_small_objects)
+__device__ __forceinline__ void ipb_k_ccl_flatten_size_phase(const IpbCrop& c, int fa_y0, int fa_nrow, const unsigned* bits,
+                       int* L, unsigned* csize)
+{
     int* Lc = L + c.pix_off;
     IPB_FA_FOREACH_WORD(c, {
         const unsigned* row = bits + c.bit_off + (size_t)y * c.wpr;
@@ -243,15 +251,20 @@ ipb_k_ccl_flatten_size(const IpbCrop* __restrict__ crops, const unsigned* __rest
         }
     })
 }
-
-// keep a pixel iff its component has size >= min_size (skimage: sizes < min_size removed)
 __global__ void __launch_bounds__(IPB_FA_THREADS)
-ipb_k_fa_size_filter(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits,
-                     const int* __restrict__ L, const unsigned* __restrict__ csize, double min_size,
-                     unsigned* __restrict__ out)
+ipb_k_ccl_flatten_size(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits,
+                       int* __restrict__ L, unsigned* __restrict__ csize)
 {
     const IpbCrop c = crops[blockIdx.y];
-    if ((int)blockIdx.x * IPB_FA_ROWS >= c.h) return;
+    IPB_FA_BAND(c);
+    ipb_k_ccl_flatten_size_phase(c, fa_y0, fa_nrow, bits, L, csize);
+}
+
+// keep a pixel iff its component has size >= min_size (skimage: sizes < min_size removed)
+__device__ __forceinline__ void ipb_k_fa_size_filter_phase(const IpbCrop& c, int fa_y0, int fa_nrow, const unsigned* bits,
+                     const int* L, const unsigned* csize, double min_size,
+                     unsigned* out)
+{
     IPB_FA_FOREACH_WORD(c, {
         const unsigned* row = bits + c.bit_off + (size_t)y * c.wpr;
         const unsigned wv = row[j];
@@ -273,6 +286,15 @@ ipb_k_fa_size_filter(const IpbCrop* __restrict__ crops, const unsigned* __restri
         out[(size_t)c.bit_off + (size_t)y * c.wpr + j] = keep;
     })
 }
+__global__ void __launch_bounds__(IPB_FA_THREADS)
+ipb_k_fa_size_filter(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits,
+                     const int* __restrict__ L, const unsigned* __restrict__ csize, double min_size,
+                     unsigned* __restrict__ out)
+{
+    const IpbCrop c = crops[blockIdx.y];
+    IPB_FA_BAND(c);
+    ipb_k_fa_size_filter_phase(c, fa_y0, fa_nrow, bits, L, csize, min_size, out);
+}
 
 // ---------------------------------------------------------------- 3. morphology with disk(r)
 // OP = 0 dilation (outside = 0), OP = 1 erosion (outside = 1): scipy.ndimage semantics used by
@@ -287,12 +309,9 @@ __device__ __forceinline__ unsigned ipb_row_word(const unsigned* bits, const Ipb
 }
 
 template <int OP>
-__global__ void __launch_bounds__(IPB_FA_THREADS)
-ipb_k_bits_morph(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ in, IpbDisk disk,
-                 unsigned* __restrict__ out)
+__device__ __forceinline__ void ipb_k_bits_morph_phase(const IpbCrop& c, int fa_y0, int fa_nrow, const unsigned* in, IpbDisk disk,
+                 unsigned* out)
 {
-    const IpbCrop c = crops[blockIdx.y];
-    if ((int)blockIdx.x * IPB_FA_ROWS >= c.h) return;
     const unsigned outside = OP ? 0xffffffffu : 0u;
     IPB_FA_FOREACH_WORD(c, {
         unsigned acc = OP ? 0xffffffffu : 0u;
@@ -313,15 +332,21 @@ ipb_k_bits_morph(const IpbCrop* __restrict__ crops, const unsigned* __restrict__
         out[(size_t)c.bit_off + (size_t)y * c.wpr + j] = acc;
     })
 }
+template <int OP>
+__global__ void __launch_bounds__(IPB_FA_THREADS)
+ipb_k_bits_morph(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ in, IpbDisk disk,
+                 unsigned* __restrict__ out)
+{
+    const IpbCrop c = crops[blockIdx.y];
+    IPB_FA_BAND(c);
+    ipb_k_bits_morph_phase<OP>(c, fa_y0, fa_nrow, in, disk, out);
+}
 
 // ---------------------------------------------------------------- 4. labels & regionprops
 // L[start] = root ; root bits ; roots per row
-__global__ void __launch_bounds__(IPB_FA_THREADS)
-ipb_k_ccl_flatten_roots(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits,
-                        int* __restrict__ L, unsigned* __restrict__ rootbits, int* __restrict__ row_roots)
+__device__ __forceinline__ void ipb_k_ccl_flatten_roots_phase(const IpbCrop& c, int fa_y0, int fa_nrow, const unsigned* bits,
+                        int* L, unsigned* rootbits, int* row_roots)
 {
-    const IpbCrop c = crops[blockIdx.y];
-    if ((int)blockIdx.x * IPB_FA_ROWS >= c.h) return;
     int* Lc = L + c.pix_off;
     IPB_FA_FOREACH_WORD(c, {
         const unsigned* row = bits + c.bit_off + (size_t)y * c.wpr;
@@ -338,6 +363,14 @@ ipb_k_ccl_flatten_roots(const IpbCrop* __restrict__ crops, const unsigned* __res
         rootbits[(size_t)c.bit_off + (size_t)y * c.wpr + j] = rb;
         if (rb) atomicAdd(&row_roots[c.row_off + y], __popc(rb));
     })
+}
+__global__ void __launch_bounds__(IPB_FA_THREADS)
+ipb_k_ccl_flatten_roots(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ bits,
+                        int* __restrict__ L, unsigned* __restrict__ rootbits, int* __restrict__ row_roots)
+{
+    const IpbCrop c = crops[blockIdx.y];
+    IPB_FA_BAND(c);
+    ipb_k_ccl_flatten_roots_phase(c, fa_y0, fa_nrow, bits, L, rootbits, row_roots);
 }
 
 // per crop: exclusive scan of roots per row -> row_base ; crop_count[crop] = total
@@ -366,6 +399,76 @@ ipb_k_fa_row_scan(const IpbCrop* __restrict__ crops, const int* __restrict__ row
         if (threadIdx.x == 255) carry = base + incl;
         __syncthreads();
     }
+    if (threadIdx.x == 0) crop_count[blockIdx.x] = carry;
+}
+
+// ---------------------------------------------------------------- fused per-crop chain
+// One CTA per crop runs every phase up to the per-row root counts back to back (phases are
+// separated by __syncthreads; the union-find works through global memory, which the barrier
+// makes visible inside the CTA).  Used when the batch has many small crops (cell ROIs); big
+// single crops (the 8192^2 mosaic) take the multi-kernel path, which spreads one crop over
+// the whole chip.
+#define IPB_FA_FUSED_THREADS 512
+__global__ void __launch_bounds__(IPB_FA_FUSED_THREADS)
+ipb_k_fa_fused(const IpbCrop* __restrict__ crops, const unsigned short* __restrict__ planes, int H, int W,
+               const float* __restrict__ fa_params, const unsigned* __restrict__ roi_mask,
+               double min_size, IpbDisk disk, unsigned* bw_a, unsigned* bw_b, int* L, unsigned* csize,
+               unsigned* rootbits, int* row_roots, int* row_base, int* crop_count, unsigned* bw_final)
+{
+    const IpbCrop c = crops[blockIdx.x];
+    const int fa_y0 = 0, fa_nrow = c.h;
+    __shared__ int wsum[IPB_FA_FUSED_THREADS / 32];
+    __shared__ int carry;
+    ipb_k_fa_threshold_phase(c, fa_y0, fa_nrow, planes, H, W, fa_params, roi_mask, bw_a);
+    __syncthreads();
+    unsigned* cur = bw_a;
+    unsigned* other = bw_b;
+    if (min_size > 0) {
+        ipb_k_ccl_init_phase(c, fa_y0, fa_nrow, cur, L, csize);
+        __syncthreads();
+        ipb_k_ccl_merge_phase<4>(c, fa_y0, fa_nrow, cur, L);
+        __syncthreads();
+        ipb_k_ccl_flatten_size_phase(c, fa_y0, fa_nrow, cur, L, csize);
+        __syncthreads();
+        ipb_k_fa_size_filter_phase(c, fa_y0, fa_nrow, cur, L, csize, min_size, other);
+        __syncthreads();
+        unsigned* t = cur; cur = other; other = t;
+    }
+    if (disk.r > 0) {
+        ipb_k_bits_morph_phase<0>(c, fa_y0, fa_nrow, cur, disk, other);
+        __syncthreads();
+        ipb_k_bits_morph_phase<1>(c, fa_y0, fa_nrow, other, disk, bw_final);
+    } else {
+        ipb_k_bits_morph_phase<0>(c, fa_y0, fa_nrow, cur, disk, bw_final);
+    }
+    for (int y = threadIdx.x; y < c.h; y += blockDim.x) row_roots[c.row_off + y] = 0;
+    __syncthreads();
+    ipb_k_ccl_init_phase(c, fa_y0, fa_nrow, bw_final, L, (unsigned*)nullptr);
+    __syncthreads();
+    ipb_k_ccl_merge_phase<8>(c, fa_y0, fa_nrow, bw_final, L);
+    __syncthreads();
+    ipb_k_ccl_flatten_roots_phase(c, fa_y0, fa_nrow, bw_final, L, rootbits, row_roots);
+    __syncthreads();
+    // exclusive scan of roots per row -> row_base ; crop_count[crop] = total
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int y0 = 0; y0 < c.h; y0 += blockDim.x) {
+        const int y = y0 + threadIdx.x;
+        const int v = y < c.h ? row_roots[c.row_off + y] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int base = carry;
+        for (int i = 0; i < warp; ++i) base += wsum[i];
+        if (y < c.h) row_base[c.row_off + y] = base + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = base + incl;
+        __syncthreads();
+    }
+    (void)nw;
     if (threadIdx.x == 0) crop_count[blockIdx.x] = carry;
 }
 
@@ -436,7 +539,7 @@ ipb_k_fa_props(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ b
                IpbComp* __restrict__ comps, int* __restrict__ labels /* nullable */)
 {
     const IpbCrop c = crops[blockIdx.y];
-    if ((int)blockIdx.x * IPB_FA_ROWS >= c.h) return;
+    IPB_FA_BAND(c);
     const unsigned short* img = planes + (size_t)c.plane * H * W;
     IPB_FA_FOREACH_WORD(c, {
         const unsigned* row = bits + c.bit_off + (size_t)y * c.wpr;

@@ -42,6 +42,7 @@ __device__ __forceinline__ float ipb_bgsub(float v, float B, int clip_neg) {
 
 struct IpbFretPx { float R, Ralt, dcorr, acorr; };
 
+template <bool WANT_ALT>
 __device__ __forceinline__ IpbFretPx ipb_fret_px(const IpbFretCfg& cfg, const float* fp,
                                                  unsigned dv, unsigned av, unsigned aov) {
     const float fnan = __uint_as_float(0x7fc00000u);
@@ -63,10 +64,10 @@ __device__ __forceinline__ IpbFretPx ipb_fret_px(const IpbFretCfg& cfg, const fl
     const float denom = cfg.numer_is_acceptor ? dbc : acorr;
     IpbFretPx o;
     o.R = __fdiv_rn(__fadd_rn(numer, eps), __fadd_rn(denom, eps));
-    o.Ralt = __fdiv_rn(__fadd_rn(denom, eps), __fadd_rn(numer, eps));
+    o.Ralt = WANT_ALT ? __fdiv_rn(__fadd_rn(denom, eps), __fadd_rn(numer, eps)) : 0.0f;
     if (cfg.clip_on) {
         if (o.R > cfg.clip_max) o.R = fnan;
-        if (o.Ralt > cfg.clip_max) o.Ralt = fnan;
+        if (WANT_ALT && o.Ralt > cfg.clip_max) o.Ralt = fnan;
     }
     o.dcorr = dbc; o.acorr = acorr;
     return o;
@@ -74,6 +75,7 @@ __device__ __forceinline__ IpbFretPx ipb_fret_px(const IpbFretCfg& cfg, const fl
 
 // planes: uint16 [F][n_ch][H][W].  Outputs (any may be null): R, Ralt, Rroi, Dcorr, Acorr,
 // each float32 [F][H][W].  Requires W % 8 == 0 for the vector path (scalar path otherwise).
+template <bool WANT_ALT>
 __global__ void __launch_bounds__(256)
 ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W, IpbFretCfg cfg,
                   const float* __restrict__ fparams, const unsigned* __restrict__ union_bits, int union_wpr,
@@ -84,43 +86,60 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
     const long long plane_px = (long long)H * W;
     const float fnan = __uint_as_float(0x7fc00000u);
     if ((W & 7) == 0) {
-        // grid = (chunks, frames): indices inside a frame are walked without 64-bit divisions
+        // grid = (chunks, frames): indices inside a frame are walked without 64-bit divisions;
+        // two 8-pixel groups per trip, all of their 128-bit loads issued before the arithmetic
         const long long vpf = plane_px >> 3;
         const int f = blockIdx.y;
-        for (long long iv = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv < vpf;
-             iv += (long long)gridDim.x * blockDim.x) {
-            const long long p0 = iv << 3;
-            const unsigned short* base = planes + (size_t)f * cfg.n_ch * plane_px;
-            const uint4 dq = __ldg(reinterpret_cast<const uint4*>(base + (size_t)cfg.donor_ch * plane_px + p0));
-            const uint4 aq = __ldg(reinterpret_cast<const uint4*>(base + (size_t)cfg.acc_ch * plane_px + p0));
-            uint4 oq = make_uint4(0, 0, 0, 0);
-            if (cfg.use_spectral && cfg.aonly_ch >= 0)
-                oq = __ldg(reinterpret_cast<const uint4*>(base + (size_t)cfg.aonly_ch * plane_px + p0));
-            const unsigned dw[4] = {dq.x, dq.y, dq.z, dq.w}, aw[4] = {aq.x, aq.y, aq.z, aq.w},
-                           ow[4] = {oq.x, oq.y, oq.z, oq.w};
-            const float* fp = fparams + (size_t)f * IPB_FP_STRIDE;
-            unsigned ub = 0xffu;
-            if (Rroi) {
-                const int y = (int)((unsigned long long)p0 / (unsigned)W), x0 = (int)(p0 - (long long)y * W);
-                const int uf = union_idx ? union_idx[f] : f;
-                ub = union_bits ? ((union_bits[((size_t)uf * H + y) * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu) : 0u;
-            }
-            float r[8], ra[8], rr[8], dc[8], ac[8];
+        const unsigned short* base = planes + (size_t)f * cfg.n_ch * plane_px;
+        const unsigned short* dptr = base + (size_t)cfg.donor_ch * plane_px;
+        const unsigned short* aptr = base + (size_t)cfg.acc_ch * plane_px;
+        const bool have_ao = cfg.use_spectral && cfg.aonly_ch >= 0;
+        const unsigned short* optr = have_ao ? base + (size_t)cfg.aonly_ch * plane_px : nullptr;
+        const float* fp = fparams + (size_t)f * IPB_FP_STRIDE;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long iv0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; iv0 < vpf; iv0 += 2 * stride) {
+            uint4 dq[2], aq[2], oq[2];
+            bool ok[2];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const unsigned dv = (t & 1) ? (dw[t >> 1] >> 16) : (dw[t >> 1] & 0xffffu);
-                const unsigned av = (t & 1) ? (aw[t >> 1] >> 16) : (aw[t >> 1] & 0xffffu);
-                const unsigned ov = (t & 1) ? (ow[t >> 1] >> 16) : (ow[t >> 1] & 0xffffu);
-                const IpbFretPx o = ipb_fret_px(cfg, fp, dv, av, ov);
-                r[t] = o.R; ra[t] = o.Ralt; dc[t] = o.dcorr; ac[t] = o.acorr;
-                rr[t] = ((ub >> t) & 1u) ? o.R : fnan;
+            for (int g = 0; g < 2; ++g) {
+                const long long iv = iv0 + g * stride;
+                ok[g] = iv < vpf;
+                dq[g] = aq[g] = oq[g] = make_uint4(0, 0, 0, 0);
+                if (ok[g]) {
+                    dq[g] = __ldg(reinterpret_cast<const uint4*>(dptr + (iv << 3)));
+                    aq[g] = __ldg(reinterpret_cast<const uint4*>(aptr + (iv << 3)));
+                    if (have_ao) oq[g] = __ldg(reinterpret_cast<const uint4*>(optr + (iv << 3)));
+                }
             }
-            const size_t o0 = (size_t)f * plane_px + p0;
-            if (R)     { reinterpret_cast<float4*>(R + o0)[0] = make_float4(r[0], r[1], r[2], r[3]);         reinterpret_cast<float4*>(R + o0)[1] = make_float4(r[4], r[5], r[6], r[7]); }
-            if (Ralt)  { reinterpret_cast<float4*>(Ralt + o0)[0] = make_float4(ra[0], ra[1], ra[2], ra[3]);  reinterpret_cast<float4*>(Ralt + o0)[1] = make_float4(ra[4], ra[5], ra[6], ra[7]); }
-            if (Rroi)  { reinterpret_cast<float4*>(Rroi + o0)[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);  reinterpret_cast<float4*>(Rroi + o0)[1] = make_float4(rr[4], rr[5], rr[6], rr[7]); }
-            if (Dcorr) { reinterpret_cast<float4*>(Dcorr + o0)[0] = make_float4(dc[0], dc[1], dc[2], dc[3]); reinterpret_cast<float4*>(Dcorr + o0)[1] = make_float4(dc[4], dc[5], dc[6], dc[7]); }
-            if (Acorr) { reinterpret_cast<float4*>(Acorr + o0)[0] = make_float4(ac[0], ac[1], ac[2], ac[3]); reinterpret_cast<float4*>(Acorr + o0)[1] = make_float4(ac[4], ac[5], ac[6], ac[7]); }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (!ok[g]) continue;
+                const long long p0 = (iv0 + g * stride) << 3;
+                const unsigned dw[4] = {dq[g].x, dq[g].y, dq[g].z, dq[g].w}, aw[4] = {aq[g].x, aq[g].y, aq[g].z, aq[g].w},
+                               ow[4] = {oq[g].x, oq[g].y, oq[g].z, oq[g].w};
+                unsigned ub = 0xffu;
+                if (Rroi) {
+                    const int y = (int)((unsigned long long)p0 / (unsigned)W), x0 = (int)(p0 - (long long)y * W);
+                    const int uf = union_idx ? union_idx[f] : f;
+                    ub = union_bits ? ((union_bits[((size_t)uf * H + y) * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu) : 0u;
+                }
+                float r[8], ra[8], rr[8], dc[8], ac[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const unsigned dv = (t & 1) ? (dw[t >> 1] >> 16) : (dw[t >> 1] & 0xffffu);
+                    const unsigned av = (t & 1) ? (aw[t >> 1] >> 16) : (aw[t >> 1] & 0xffffu);
+                    const unsigned ov = (t & 1) ? (ow[t >> 1] >> 16) : (ow[t >> 1] & 0xffffu);
+                    const IpbFretPx o = ipb_fret_px<WANT_ALT>(cfg, fp, dv, av, ov);
+                    r[t] = o.R; ra[t] = o.Ralt; dc[t] = o.dcorr; ac[t] = o.acorr;
+                    rr[t] = ((ub >> t) & 1u) ? o.R : fnan;
+                }
+                const size_t o0 = (size_t)f * plane_px + p0;
+                if (R)     { reinterpret_cast<float4*>(R + o0)[0] = make_float4(r[0], r[1], r[2], r[3]);         reinterpret_cast<float4*>(R + o0)[1] = make_float4(r[4], r[5], r[6], r[7]); }
+                if (WANT_ALT && Ralt) { reinterpret_cast<float4*>(Ralt + o0)[0] = make_float4(ra[0], ra[1], ra[2], ra[3]);  reinterpret_cast<float4*>(Ralt + o0)[1] = make_float4(ra[4], ra[5], ra[6], ra[7]); }
+                if (Rroi)  { reinterpret_cast<float4*>(Rroi + o0)[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);  reinterpret_cast<float4*>(Rroi + o0)[1] = make_float4(rr[4], rr[5], rr[6], rr[7]); }
+                if (Dcorr) { reinterpret_cast<float4*>(Dcorr + o0)[0] = make_float4(dc[0], dc[1], dc[2], dc[3]); reinterpret_cast<float4*>(Dcorr + o0)[1] = make_float4(dc[4], dc[5], dc[6], dc[7]); }
+                if (Acorr) { reinterpret_cast<float4*>(Acorr + o0)[0] = make_float4(ac[0], ac[1], ac[2], ac[3]); reinterpret_cast<float4*>(Acorr + o0)[1] = make_float4(ac[4], ac[5], ac[6], ac[7]); }
+            }
         }
     } else {
         const int f = blockIdx.y;
@@ -131,9 +150,9 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
             const unsigned dv = base[(size_t)cfg.donor_ch * plane_px + p];
             const unsigned av = base[(size_t)cfg.acc_ch * plane_px + p];
             const unsigned ov = (cfg.use_spectral && cfg.aonly_ch >= 0) ? base[(size_t)cfg.aonly_ch * plane_px + p] : 0u;
-            const IpbFretPx o = ipb_fret_px(cfg, fparams + (size_t)f * IPB_FP_STRIDE, dv, av, ov);
+            const IpbFretPx o = ipb_fret_px<WANT_ALT>(cfg, fparams + (size_t)f * IPB_FP_STRIDE, dv, av, ov);
             if (R) R[i] = o.R;
-            if (Ralt) Ralt[i] = o.Ralt;
+            if (WANT_ALT && Ralt) Ralt[i] = o.Ralt;
             if (Dcorr) Dcorr[i] = o.dcorr;
             if (Acorr) Acorr[i] = o.acorr;
             if (Rroi) {

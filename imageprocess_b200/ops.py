@@ -38,7 +38,8 @@ class RoiMasks:
 
 
 # kernels launched by each C-ABI entry point (memsets not counted)
-KERNELS_PER_CALL = {"ipb_fa_segment": 14, "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
+KERNELS_PER_CALL = {"ipb_fa_segment": 4,   # fused per-crop path (14 on the one-kernel-per-phase path)
+                     "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
                     "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
                     "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_region_dilate": 2, "ipb_hist_select": 5}
 
@@ -324,7 +325,7 @@ def _engine_fa_segment(self, rm, crops, total_px, total_rows, planes, H, W, fa_p
               planes.ptr, int(H), int(W), fa_params.ptr, rm.pool.ptr, float(min_size), int(close_radius),
               bw_a.ptr, bw_b.ptr, L.ptr, csize.ptr, rootbits.ptr, row_roots.ptr, row_base.ptr,
               crop_count.ptr, bw_f.ptr, comp_off.ptr, comps.ptr, int(comp_cap),
-              labels.ptr if labels is not None else None, mem.stream)
+              labels.ptr if labels is not None else None, 0, mem.stream)
     return FaResult(crops, bw_f, comp_off, comps, labels, comp_cap,
                     (d_crops, bw_a, bw_b, rootbits, L, csize, row_roots, row_base, crop_count))
 

@@ -49,12 +49,13 @@ class _FaView:
 
 
 def fa_batch(eng, planes, shape, polys_per_frame, params, px_size, channel=0, save_ok_only=True,
-             want_labels=False, config=None):
+             want_labels=False, config=None, fa_path=0):
     """FA_Analyzer batch body for F frames (reference src/INT/FA_Analyzer.py:984-1039)."""
     F = shape[0]
     cfg = config or fa_um_to_px_config(params, px_size)
     job = batch.FrameBatchJob(eng, shape, stages=("fa",), fa_params=params, fa_px=px_size, fa_ch=channel,
                               want_labels=want_labels, fa_config=cfg)
+    job.fa_path = fa_path
     res = job.run(planes, polys_per_frame)
     owner = [(int(f), int(r)) for f, r in zip(res.frame, res.roi)]
     rects = [tuple(int(v) for v in rc) for rc in res.fa_rect]

@@ -212,7 +212,9 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int unif
  *   crop_count   int32 [n_crops];  comp_off int32 [n_crops + 1] (exclusive scan, result)
  *   comps        ipb_comp[comp_cap] result table: components of crop c are rows
  *                comp_off[c] .. comp_off[c+1], label k <-> row comp_off[c] + k - 1
- *   labels       optional int32 [total_px] label maps (crop-local, 0 background)           */
+ *   labels       optional int32 [total_px] label maps (crop-local, 0 background)
+ *   path         0: many small crops (cell ROIs) run one CTA per crop through the whole chain,
+ *                few / huge crops (stitched mosaic) one kernel per phase over the whole chip   */
 typedef struct {
     int64_t bit_off, pix_off, row_off;
     int64_t mask_off;     /* word offset of the crop's ROI mask rows in roi_mask (crops of
@@ -230,7 +232,8 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    uint32_t* bw_a, uint32_t* bw_b, int32_t* L, uint32_t* csize, uint32_t* rootbits,
                    int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
                    uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
-                   int32_t* labels, void* stream);
+                   int32_t* labels, int path /* 0 auto, 1 one CTA per crop, 2 one kernel per phase */,
+                   void* stream);
 
 /* ------------------------------------------------------------------ morphology, moments, previews
  * ipb_region_dilate: dilation of region masks (ipb_region layout, all pools share mask_off)

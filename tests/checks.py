@@ -212,7 +212,7 @@ FA_CASES = [
 ]
 
 
-def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168):
+def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168, fa_path=0):
     """FA chain vs the oracle's analyze_fa_crop: bw mask, label image, counts, areas and
     categories bit-exact; float32 mean within REL; CSV rows in the reference's order.
     Thresholds come from exact integer moments; if numpy's pairwise float32 mean/std gives a
@@ -224,7 +224,7 @@ def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168):
     planes = np.stack([np.stack([d, a]) for d, a, _ in frames])
     F, C = planes.shape[:2]
     out = pipeline.fa_batch(eng, eng.mem.from_host(planes), (F, C, H, W), [fr[2] for fr in frames],
-                            params, px, channel=0, save_ok_only=False, want_labels=True)
+                            params, px, channel=0, save_ok_only=False, want_labels=True, fa_path=fa_path)
     cfg = pipeline.fa_um_to_px_config(params, px)
     straddles = 0
     k = 0
