@@ -141,11 +141,14 @@ def run_reference(args):
     oracle.build()
     cores = os.cpu_count() or 1
     workers = min(cores, 8)         # the reference's own pool size: Fluor_INT.py:2211-2216
-    n = workers                     # one frame per worker per step: bounded sample
+    # bounded sample: one frame per worker per step; with many timed steps half of that, so that
+    # the whole run stays within a few minutes (a frame costs ~20 s of one core)
+    n = workers if args.steps <= 3 else max(2, workers // 2)
+    workers = min(workers, n)
     frames, polys = make_frames(max(2, min(n, 2)), n_unique=2)
     frames = np.concatenate([frames] * ((n + 1) // 2))[:n]
     for _ in range(min(args.warmup, 1)):
-        cpu_reference(frames[:workers], polys, workers)
+        cpu_reference(frames[:1], polys, 1)
     vals = []
     t_all = 0.0
     for _ in range(args.steps):

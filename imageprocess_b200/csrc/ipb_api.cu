@@ -220,7 +220,7 @@ int ipb_hist_quantiles(const uint32_t* hist, const uint64_t* stats, const void* 
 {
     if (n_q <= 0) return IPB_OK;
     IPB_REQUIRE(hist && stats && qjobs && qout, "ipb_hist_quantiles: null pointer");
-    IPB_LAUNCH(ipb_k_hist_quantiles, dim3(n_q), dim3(256), 0, stream, hist,
+    IPB_LAUNCH(ipb_k_hist_quantiles, dim3(n_q), dim3(1024), 0, stream, hist,
                (const unsigned long long*)stats, (const IpbQJob*)qjobs, (IpbQOut*)qout);
     return ipb_check_launch("ipb_k_hist_quantiles");
 }

@@ -282,7 +282,7 @@ struct IpbQOut {
 
 // one CTA (256 threads) per quantile job; warps scan contiguous bands of the histogram with
 // coalesced reads (ipb_locate_ranks)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 ipb_k_hist_quantiles(const unsigned* __restrict__ hist, const unsigned long long* __restrict__ stats,
                      const IpbQJob* __restrict__ qjobs, IpbQOut* __restrict__ out)
 {

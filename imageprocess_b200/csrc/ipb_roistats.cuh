@@ -407,7 +407,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         // ranks: the word first, then the low / high counter inside the word
         unsigned long long want[IPB_RS_MAXR];
         for (int r = 0; r < IPB_RS_MAXR; ++r) want[r] = sel.rank[r];
-        ipb_locate_ranks(1024u, want, nr, red_u,
+        ipb_locate_ranks_smem(32768u, 32768u / IPB_RS_THREADS, want, nr, red_u,
                       [&](unsigned i) { const unsigned w = h16[i]; return (w & 0xffffu) + (w >> 16); },
                       [&](int r, unsigned i, unsigned inside) { sel.prefix[r] = 2u * i + (inside >= (h16[i] & 0xffffu) ? 1u : 0u); });
         kbase = 0u;                                                // prefixes are absolute keys
@@ -471,8 +471,8 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         {
             unsigned long long want[IPB_RS_MAXR];
             for (int r = 0; r < IPB_RS_MAXR; ++r) want[r] = sel.rank[r];
-            ipb_locate_ranks((nb + 31u) >> 5, want, nr, red_u,
-                          [&](unsigned i) { return i < nb ? whist[i] : 0u; },
+            ipb_locate_ranks_smem(nb, (nb + IPB_RS_THREADS - 1u) / IPB_RS_THREADS, want, nr, red_u,
+                          [&](unsigned i) { return whist[i]; },
                           [&](int r, unsigned i, unsigned inside) { sel.prefix[r] = i; sel.rank[r] = (unsigned long long)inside; });
         }
 

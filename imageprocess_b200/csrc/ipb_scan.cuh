@@ -45,3 +45,46 @@ __device__ __forceinline__ void ipb_locate_ranks(unsigned nrows, const unsigned 
     __syncthreads();
 }
 
+
+// Same task for counters that live in SHARED memory (or registers behind `value`): every thread
+// owns `per` consecutive counters and sums them with a rotated start (thread t begins at
+// counter (t mod per) of its chunk, so the lanes of a warp hit different banks), a block scan
+// of the per-thread sums follows, and only the threads whose chunk holds a wanted rank walk
+// their chunk in order.  All threads work in parallel; no warp walks a long serial chain.
+// `per` = counters per thread (nbins <= per * blockDim.x); scan32 = >= 32 words of shared scratch.
+template <typename V, typename HIT>
+__device__ __forceinline__ void ipb_locate_ranks_smem(unsigned nbins, unsigned per, const unsigned long long* want,
+                                                      int nr, unsigned long long* scan32, V value, HIT hit) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const unsigned c0 = (unsigned)tid * per;
+    unsigned long long mine = 0;
+    const unsigned rot = per ? (unsigned)tid % per : 0u;
+    for (unsigned i = 0; i < per; ++i) {
+        unsigned k = i + rot;
+        if (k >= per) k -= per;
+        const unsigned b = c0 + k;
+        if (b < nbins) mine += value(b);
+    }
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();
+    if (lane == 31) scan32[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int i = 0; i < warp && i < nwarps; ++i) base += scan32[i];
+    const unsigned long long lo = base + incl - mine, hi = base + incl;
+    for (int r = 0; r < nr; ++r) {
+        const unsigned long long kk = want[r];
+        if (kk >= lo && kk < hi) {
+            unsigned long long acc = lo;
+            for (unsigned i = 0; i < per; ++i) {
+                const unsigned b = c0 + i;
+                const unsigned v = b < nbins ? value(b) : 0u;
+                if (kk < acc + v) { hit(r, b, (unsigned)(kk - acc)); break; }
+                acc += v;
+            }
+        }
+    }
+    __syncthreads();
+}
