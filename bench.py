@@ -92,12 +92,14 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._t.start()
+        if self.index is not None:
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=3)
+        if self.index is not None:
+            self._t.join(timeout=3)
 
     def summary(self):
         if not self.samples:
@@ -199,15 +201,15 @@ def run_ours(args):
 
     tab_dev = torch.device(f"cuda:{local}")
 
+    job.dist = dist                     # N > 1: every step all-gathers its packed row tables (NCCL)
+
     def consume(res):
-        """Host side of one step: per-adhesion table with the reference's dtypes; with N > 1 ranks
-        the small row tables are gathered to rank 0 (the only collective on this path)."""
+        """Host side of one step: per-adhesion table with the reference's dtypes; on rank 0 of an
+        N-rank job also the other ranks' gathered tables (their adhesion counts are read here)."""
         batch.fa_table(res, job.fa_cfg)
-        if dist is not None:
-            from imageprocess_b200 import parallel
-            parallel.gather_tables(res.fret_stat.reshape(-1), dist, tab_dev)
-            parallel.gather_tables(res.int_stat.reshape(-1), dist, tab_dev)
-            parallel.gather_tables(res.fa_comps, dist, tab_dev)
+        if res.gathered is not None:
+            for arena, comps in res.gathered:
+                int(job._plans[next(iter(job._plans))].O.view(arena, "comp_off")[-1])
         return res.d2h_bytes
 
     def barrier():
@@ -276,7 +278,7 @@ def run_ours(args):
     loop_resident(args.warmup)
     torch.cuda.synchronize()
     launches0 = eng.launches
-    with ClockSampler(local) as clk:
+    with ClockSampler(local if rank == 0 else None) as clk:      # one sampler per job, on rank 0's GPU
         eng.profile_start()
         ms, d2h = timed(loop_resident, args.steps)
         prof = eng.profile_stop()

@@ -97,6 +97,9 @@ class FrameBatchJob:
         self._plans = {}
         self.window_misses = 0
         self._slot = 0
+        self.dist = None            # torch.distributed module when the job is one rank of N (see parallel.py)
+        self.gather_dst = 0
+        self._gather_cap = None     # bytes every rank contributes to the per-step all-gather
         self.fa_path = 0            # ipb_fa_segment path: 0 auto, 1 one CTA per crop, 2 one kernel per phase
         # percentiles by sampling (ipb_hist_select) instead of full histograms: exact either way;
         # off by default until its tail pass beats the full-histogram kernel
@@ -551,9 +554,39 @@ class FrameBatchJob:
         tk.d_comps, tk.pc_np, tk.pc_rows = None, None, 0
         if fa_ran:
             tk.d_comps = d_comps
-            tk.pc_rows = min(pl.comp_cap, max(4096, 128 * NR))       # usual batches fit; collect() fetches the rest
+            tk.pc_rows = min(pl.comp_cap, max(4096, 96 * NR))        # usual batches fit; collect() fetches the rest
             tk.pc_np, pc_t = self._pinned(f"pin_comps{slot}", COMP.itemsize * tk.pc_rows)
             mem.download_async(pc_t, d_comps, COMP.itemsize * tk.pc_rows)
+        # N > 1 ranks: the packed tables of every rank go to all ranks with ONE NCCL all-gather per
+        # step (KBs..MBs over NVLink); rank `gather_dst` also brings the gathered blob to the host
+        tk.gather_np = None
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            # every rank sends the same number of bytes: a capacity agreed once per job (max over
+            # ranks of 1.25x the first step's need + 64 KiB).  Segment = 32-byte header {arena bytes,
+            # adhesion rows sent}, the table arena, the first adhesion rows.  Rows that do not fit
+            # are not sent; the receiver sees that from comp_off and reports it.
+            world = self.dist.get_world_size()
+            comps_b = COMP.itemsize * tk.pc_rows if fa_ran else 0
+            need = 32 + _al(O.size) + _al(comps_b)
+            if self._gather_cap is None:
+                self._gather_cap = _al(mem.all_reduce_max(need + need // 4 + (1 << 16), self.dist))
+            cap = self._gather_cap
+            if 32 + _al(O.size) > cap:
+                raise RuntimeError("table arena larger than the agreed gather capacity; pass gather_cap_bytes")
+            rows_sent = min(tk.pc_rows if fa_ran else 0, (cap - 32 - _al(O.size)) // COMP.itemsize)
+            hdr_np, hdr_t = self._pinned(f"pin_ghdr{slot}", 32)
+            hdr_np[:32].view(np.int64)[:] = (O.size, rows_sent, 0, 0)
+            d_stage = self._dev("gather_stage", cap)
+            mem.upload_async(d_stage, hdr_t, 32)
+            mem.copy_bytes(d_stage, 32, d_out, 0, O.size)
+            if rows_sent:
+                mem.copy_bytes(d_stage, 32 + _al(O.size), d_comps, 0, COMP.itemsize * rows_sent)
+            d_all = self._dev("gather_all", cap * world)
+            mem.all_gather_bytes(d_all, d_stage, cap, self.dist)
+            if self.dist.get_rank() == self.gather_dst:
+                g_np, g_t = self._pinned(f"pin_gather{slot}", cap * world)
+                mem.download_async(g_t, d_all, cap * world)
+                tk.gather_np, tk.gather_pack = g_np, cap
         tk.event = mem.event()
         tk.event.record()
         return tk
@@ -604,6 +637,16 @@ class FrameBatchJob:
                 res.d2h_bytes += COMP.itemsize * total
             else:
                 res.fa_comps = np.zeros(0, dtype=COMP)
+        # gathered[r] = (packed table arena, adhesion rows) of rank r, on the destination rank only
+        res.gathered = None
+        if tk.gather_np is not None:
+            world = self.dist.get_world_size()
+            blobs = tk.gather_np[: world * tk.gather_pack].reshape(world, tk.gather_pack)
+            res.gathered = []
+            for r in range(world):
+                arena_b, rows = (int(v) for v in blobs[r, :16].view(np.int64))
+                a0 = 32 + _al(arena_b)
+                res.gathered.append((blobs[r, 32: 32 + arena_b], blobs[r, a0: a0 + COMP.itemsize * rows].view(COMP)))
         return res
 
     def run(self, planes, polys_per_frame, full_hist=False):

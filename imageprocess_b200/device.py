@@ -105,3 +105,15 @@ class TorchMem:
 
     def sync(self):
         self.torch.cuda.current_stream(self.device).synchronize()
+
+    def all_reduce_max(self, value, dist):
+        """max over ranks of a Python int (one small collective + host read; used once per job)."""
+        t = self.torch.tensor([int(value)], dtype=self.torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
+
+    def all_gather_bytes(self, dst, src, nbytes, dist):
+        """dst[r * nbytes : (r + 1) * nbytes] = rank r's src[:nbytes] (NCCL all-gather, enqueued
+        asynchronously with respect to the host, ordered after the current stream's work)."""
+        n = int(nbytes)
+        dist.all_gather_into_tensor(dst.raw[: n * dist.get_world_size()], src.raw[:n])

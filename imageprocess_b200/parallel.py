@@ -16,30 +16,47 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_tables(table, dist=None, device=None, dst=0):
-    """Gathers one numpy structured (or plain) 1-D table per rank to `dst`.  Returns the list of
-    per-rank tables on `dst` (rank order == frame order for contiguous shards), None elsewhere.
-    Two collectives: row counts, then the padded byte tables."""
-    table = np.ascontiguousarray(table)
+def gather_many(tables, dist=None, device=None, dst=0):
+    """Gathers a LIST of numpy 1-D tables per rank to `dst` with two collectives in total: the
+    byte sizes of every table of every rank, then one padded byte blob per rank.  Returns, on
+    `dst`, a list (one entry per table) of per-rank arrays in rank order (== frame order for
+    contiguous shards); None on the other ranks."""
+    tables = [np.ascontiguousarray(t) for t in tables]
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
-        return [table]
+        return [[t] for t in tables]
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = device if device is not None else torch.device("cpu")
-    n = torch.tensor([table.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
-    row = table.dtype.itemsize
-    cap = max(max(counts), 1) * row
-    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
-    if table.shape[0]:
-        buf[: table.nbytes] = torch.from_numpy(table.view(np.uint8).reshape(-1).copy()).to(dev)
-    bufs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(bufs, buf)
+    sizes = torch.tensor([t.nbytes for t in tables], dtype=torch.int64, device=dev)
+    all_sizes = torch.zeros(world * len(tables), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes)
+    all_sizes = all_sizes.cpu().numpy().reshape(world, len(tables))
+    cap = max(int(all_sizes.sum(axis=1).max()), 16)
+    blob = np.zeros(cap, dtype=np.uint8)
+    off = 0
+    for t in tables:
+        blob[off: off + t.nbytes] = t.view(np.uint8).reshape(-1)
+        off += t.nbytes
+    mine = torch.from_numpy(blob).to(dev, non_blocking=True)
+    everyone = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(everyone, mine)
     if rank != dst:
         return None
-    return [b[: c * row].cpu().numpy().view(table.dtype).copy() for b, c in zip(bufs, counts)]
+    host = everyone.cpu().numpy().reshape(world, cap)
+    out = [[] for _ in tables]
+    for r in range(world):
+        off = 0
+        for k, t in enumerate(tables):
+            nb = int(all_sizes[r, k])
+            out[k].append(host[r, off: off + nb].view(t.dtype).copy())
+            off += nb
+    return out
+
+
+def gather_tables(table, dist=None, device=None, dst=0):
+    """One table per rank -> list of per-rank tables on `dst`, None elsewhere."""
+    res = gather_many([table], dist, device, dst)
+    return None if res is None else res[0]
 
 
 def rows_to_table(rows, columns):

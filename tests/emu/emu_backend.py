@@ -70,6 +70,18 @@ class NumpyMem:
     def sync(self):
         pass
 
+    def all_reduce_max(self, value, dist):
+        import torch
+        t = torch.tensor([int(value)], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
+
+    def all_gather_bytes(self, dst, src, nbytes, dist):
+        import torch
+        n = int(nbytes)
+        out = torch.from_numpy(dst.raw[: n * dist.get_world_size()])
+        dist.all_gather_into_tensor(out, torch.from_numpy(src.raw[:n].copy()))
+
 
 _lib = None
 

@@ -67,3 +67,70 @@ def test_two_rank_gather_gloo():
     assert [int(r["area_px"]) for r in merged] == [100 * f + roi for f, roi in want]
     flat = [row for t in tabs for row in t]
     assert [r[1] for r in flat] == list(range(n_frames)) and [r[0] for r in flat] == [7 * i for i in range(n_frames)]
+
+
+def _job_worker(rank, world, port, q):
+    try:
+        _job_worker_body(rank, world, port, q)
+    except Exception as e:                                   # surface the failure instead of a queue timeout
+        q.put(f"rank {rank}: {type(e).__name__}: {e}")
+        raise
+
+
+def _job_worker_body(rank, world, port, q):
+    """Each rank runs the product's FrameBatchJob (kernels in the emulated build) on its block of
+    frames; every step all-gathers the packed tables; rank 0 checks what it received."""
+    import torch.distributed as dist
+    from imageprocess_b200 import batch
+    from imageprocess_b200.ops import Engine
+    from oracle.gen_golden import small_scene
+    from tests.emu.emu_backend import NumpyMem, emu_lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = Engine(emu_lib(), NumpyMem())
+    scenes = [small_scene(s, H=96, W=128, n_cells=2, blobs=4) for s in (51, 52, 53, 54)]
+    fa_params = {"alpha": 2.0, "min_area_um": 0.05, "max_area_um": 5.0, "close_radius": 1, "subtract_bg": True}
+    task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4, "percentile": 1.0,
+            "per_channel_p": False, "ch_p_map": {}}
+
+    def run_block(r, with_dist):
+        lo, hi = parallel.shard_range(len(scenes), r, world)
+        planes = np.stack([np.stack([d, a]) for d, a, _ in scenes[lo:hi]])
+        job = batch.FrameBatchJob(eng, planes.shape, stages=("int", "fa"), int_task=task, fa_params=fa_params, fa_px=0.112)
+        job.dist = dist if with_dist else None
+        return job, job.run(eng.mem.from_host(planes), [sc[2] for sc in scenes[lo:hi]])
+
+    job, res = run_block(rank, True)
+    ok = True
+    if rank == 0:
+        assert res.gathered is not None and len(res.gathered) == world
+        for r in range(world):
+            jr, want = run_block(r, False)                    # what rank r must have produced
+            O = jr._plans[next(iter(jr._plans))].O
+            arena, comps = res.gathered[r]
+            ok &= np.array_equal(O.view(arena, "comp_off")[: want.n_rois + 1], want.fa_comp_off)
+            n = int(want.fa_comp_off[-1])
+            ok &= np.array_equal(comps[:n], want.fa_comps)
+            so = O.view(arena, "stat_out")[: want.int_stat.size].reshape(want.int_stat.shape)
+            ok &= bool((so["n"] == want.int_stat["n"]).all() and (so["q"] == want.int_stat["q"]).all())
+        q.put(bool(ok))
+    else:
+        assert res.gathered is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_job_all_gather_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_job_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    assert got is True, got
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
