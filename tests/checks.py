@@ -124,7 +124,9 @@ def check_int_rows(got_rows, want_rows, chs):
         assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"]
         for ch in chs:
             for k in EXACT_INT:
-                assert g[f"ch{ch}_{k}"] == w[f"ch{ch}_{k}"], (ch, k, g[f"ch{ch}_{k}"], w[f"ch{ch}_{k}"])
+                gv, wv = g[f"ch{ch}_{k}"], w[f"ch{ch}_{k}"]
+                both_nan = isinstance(gv, float) and isinstance(wv, float) and math.isnan(gv) and math.isnan(wv)
+                assert gv == wv or both_nan, (ch, k, gv, wv)
             for k in ("mean", "std", "vsum"):
                 assert close(g[f"ch{ch}_{k}"], w[f"ch{ch}_{k}"]), (ch, k)
 
@@ -634,3 +636,84 @@ def check_hist_select_paths(eng):
 
 
 RASTER_CHECKS.append(check_hist_select_paths)
+
+
+def check_edge_cases(eng):
+    """Ragged / degenerate inputs through all three stages against the oracle: odd image sizes
+    (scalar code paths), frames without ROIs, ROIs partly or wholly outside the frame,
+    overlapping ROIs, a zero-area polygon, a constant image, a fully saturated channel."""
+    from imageprocess_b200 import batch
+    rng = np.random.default_rng(77)
+    H, W = 61, 83                                           # W % 8 != 0, W % 32 != 0
+    base = rng.poisson(300, (H, W)).astype(np.uint16)
+    blob = np.zeros((H, W), np.uint16)
+    blob[20:35, 30:52] = 4000
+    blob[40:50, 5:20] = 2500
+    frames_px = [
+        np.stack([base + blob, (base * 0.7).astype(np.uint16) + blob // 2]),
+        np.stack([np.full((H, W), 1234, np.uint16), base]),                       # constant donor: std 0
+        np.stack([np.full((H, W), 65535, np.uint16), base + blob]),              # saturated donor
+        np.stack([base[::-1].copy(), base.T[:H, :W].copy() if base.T.shape[0] >= H and base.T.shape[1] >= W else base]),
+    ]
+    planes = np.stack(frames_px)
+    polys = [
+        [np.array([[25.0, 15.0], [60.0, 18.0], [58.0, 40.0], [27.0, 38.0]]),       # inside
+         np.array([[50.0, 30.0], [95.0, 28.0], [90.0, 70.0], [48.0, 55.0]]),       # crosses right / bottom border
+         np.array([[-30.0, -20.0], [-5.0, -20.0], [-5.0, -2.0]]),                  # wholly outside
+         np.array([[40.0, 20.0], [70.0, 22.0], [66.0, 45.0], [38.0, 44.0]]),       # overlaps ROI 1
+         np.array([[10.0, 10.0], [20.0, 10.0], [30.0, 10.0]])],                    # zero area (collinear)
+        [],                                                                         # no ROI at all
+        [np.array([[2.5, 2.5], [80.5, 3.5], [79.5, 58.5], [3.5, 57.5]])],
+        [np.array([[0.0, 0.0], [82.0, 0.0], [82.0, 60.0], [0.0, 60.0]]),           # the whole frame, on pixel centres
+         np.array([[5.0, 5.0], [6.0, 5.0]])],                                       # < 3 points: dropped upstream
+    ]
+    polys = [[P for P in pl if P.shape[0] >= 3] for pl in polys]                    # Fluor_INT.py:419-422
+    F, C = planes.shape[:2]
+    fret_p = {"bg_scope": "roi_union", "bg_mode": "percentile", "percentile": 5.0, "per_channel_p": False,
+              "donor_p": 1.0, "fret_p": 1.0, "clip_neg": True, "eps_percentile": 3.0, "ratio_mode": "Donor/FRET"}
+    task = {"bg_scope": "roi_union", "bg_mode": "percentile", "clip_neg": False, "bg_stride": 3,
+            "percentile": 10.0, "per_channel_p": False, "ch_p_map": {}}
+    fa_params = {"alpha": 1.5, "min_area_um": 0.2, "max_area_um": 2.0, "close_radius": 2, "subtract_bg": True}
+    px = 0.112
+    job = batch.FrameBatchJob(eng, planes.shape, stages=("fret", "int"), fret_p=fret_p, int_task=task,
+                              want_roi_image=True)
+    res = job.run(eng.mem.from_host(planes), polys)
+    rows_i = batch.rows_intensity(res, F, [1, 2])
+    rows_f = batch.rows_fret(res, F)
+    # FA: an ROI wholly outside the frame gives the reference an empty crop on which
+    # skimage.draw.polygon raises (FA_Analyzer.py:1008-1014) -- not a result to reproduce
+    polys_fa = [[P for P in pl if P[:, 0].max() >= 0] for pl in polys]
+    jfa = batch.FrameBatchJob(eng, planes.shape, stages=("fa",), fa_params=fa_params, fa_px=px, want_labels=True)
+    rfa = jfa.run(eng.mem.from_host(planes), polys_fa)
+    rows_a = batch.rows_fa(rfa, jfa.fa_cfg, fa_params, px, F, save_ok_only=False)
+    R = res.R.host()
+    for f in range(F):
+        D, A = planes[f, 0].astype(np.float32), planes[f, 1].astype(np.float32)
+        with np.errstate(all="ignore"):
+            want = port.fret_process_pair(D, A, polys[f], fret_p)
+        assert np.array_equal(R[f], want["R_full"], equal_nan=True), f
+        assert len(rows_f[f]) == len(want["rows"])
+        for g, w in zip(rows_f[f], want["rows"]):
+            assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"], (f, g["roi"])
+            for k in ("ratio_median", "ratio_p5", "ratio_p95", "donor_median"):
+                assert g[k] == w[k] or (math.isnan(g[k]) and math.isnan(w[k])), (f, k, g[k], w[k])
+            assert close(g["ratio_mean"], w["ratio_mean"]), (f, g["ratio_mean"], w["ratio_mean"])
+        if polys[f]:
+            with np.errstate(all="ignore"):
+                wrows, wbg, _ = port.int_process_key({1: D.copy(), 2: A.copy()}, polys[f], None, task)
+            assert res.int_bg[f, 0] == wbg[1]["bg"] and res.int_bg[f, 1] == wbg[2]["bg"], f
+            check_int_rows(rows_i[f], wrows, (1, 2))
+        else:
+            assert rows_i[f] == []
+        stats = port.fa_global_stats(D)
+        got = rfa.fa_stats[f]
+        assert got[2] == stats[2]
+        if np.float32(got[3]) != stats[0] + jfa.fa_cfg["alpha"] * stats[1]:
+            stats = (np.float32(got[0]), np.float32(got[1]), stats[2])
+        wfa = port.fa_batch_rows(D, polys_fa[f], fa_params, px, save_ok_only=False, with_contours=False, stats=stats)
+        assert len(rows_a[f]) == len(wfa), (f, len(rows_a[f]), len(wfa))
+        for g, w in zip(rows_a[f], wfa):
+            assert g["Cell_ID"] == w["Cell_ID"] and g["Category"] == w["Category"] and g["Area_px"] == w["Area_px"]
+
+
+RASTER_CHECKS.append(check_edge_cases)
