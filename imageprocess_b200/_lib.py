@@ -82,6 +82,12 @@ _lib = None
 def load() -> Lib:
     global _lib
     if _lib is None:
+        from . import build
+        if os.path.isdir(build.CSRC):                      # source tree present: the library must match it
+            have = open(build.HASH).read().strip() if os.path.exists(build.HASH) else None
+            if os.path.exists(LIB_PATH) and have != build.source_digest():
+                raise IpbError(f"{LIB_PATH} was built from different kernel sources: rebuild it "
+                               "(python -c 'import __graft_entry__ as g; g.build()')")
         _lib = Lib(LIB_PATH)
         if _lib.c.ipb_is_emulated():
             raise IpbError("refusing to run the product on an emulated build")
