@@ -38,6 +38,7 @@ _PROTOS.update({
     "ipb_preview_u16": [_vp, _i64, _i, _vp, _vp, _vp],
     "ipb_crop_normalize": [_vp, _i, _i64, _vp, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp],
     "ipb_eps_from_stat": [_vp, _vp, _i, _f, _vp, _vp],
+    "ipb_hist_planes": [_vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "ipb_hist_select": [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                         _vp, _vp, _vp, _vp],
 })

@@ -479,8 +479,8 @@ class FrameBatchJob:
                      op("miss"), stream)
             lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), stream)
         elif NH:
-            lib_call("ipb_hist_u16", planes.ptr, H, W, tp("hist_jobs"), NH, int(pl.has_ms), union_ptr,
-                     self.union_wpr, d_scr.ptr if d_scr is not None else None, d_hist.ptr, d_hstat.ptr, stream)
+            lib_call("ipb_hist_planes", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, int(pl.has_ms),
+                     union_ptr, self.union_wpr, d_scr.ptr if d_scr is not None else None, d_hist.ptr, d_hstat.ptr, stream)
             lib_call("ipb_hist_quantiles", d_hist.ptr, d_hstat.ptr, tp("qjobs"), NQ, d_qout.ptr, stream)
             lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), stream)
         if pl.host_bg:
@@ -653,6 +653,17 @@ class FrameBatchJob:
         """One synchronous step: submit + collect."""
         return self.collect(self.submit(planes, polys_per_frame, full_hist))
 
+    def _n_hist_planes(self):
+        """Distinct uint16 planes per frame that the histogram stage reads."""
+        chs = set()
+        if "fret" in self.stages:
+            chs |= {self.donor_ch, self.acc_ch}
+        if "int" in self.stages:
+            chs |= set(self.int_ch)
+        if "fa" in self.stages:
+            chs.add(self.fa_ch)
+        return len(chs)
+
     def _ch_name(self, ci):
         names = getattr(self, "ch_names", None)
         return names[ci] if names else self.int_ch[ci] + 1
@@ -687,7 +698,7 @@ class FrameBatchJob:
         n_hist = (2 if "fret" in self.stages else 0) + (len(self.int_ch) if "int" in self.stages else 0) + \
                  (1 if "fa" in self.stages else 0)
         return {
-            "ipb_hist_u16": 2 * px * n_hist,             # each sampled plane read once per job
+            "ipb_hist_planes": 2 * px * self._n_hist_planes(),   # every sampled plane read once per launch
             "ipb_fret_pixels": 8 * px,                   # 2 x uint16 in, float32 ratio out
             # ratio job: float32 under the mask; one uint16 job per measured channel
             "ipb_region_stats": (4 * roi_px if "fret" in self.stages else 0) + 2 * roi_px * len(

@@ -215,6 +215,41 @@ int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int 
     return rc;
 }
 
+int ipb_hist_planes(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
+                    const void* passes, int n_passes, int has_masked_stride, const uint32_t* union_bits,
+                    int union_wpr, uint64_t* row_rank_scratch, uint32_t* hist, uint64_t* stats, void* stream)
+{
+    IPB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535 && n_passes >= 0 && n_passes <= 65535, "ipb_hist_planes: job count out of range");
+    if (n_jobs == 0) return IPB_OK;
+    IPB_REQUIRE(planes && jobs && passes && hist && stats && H > 0 && W > 0, "ipb_hist_planes: bad argument");
+    IPB_REQUIRE(!has_masked_stride || (union_bits && row_rank_scratch), "ipb_hist_planes: masked stride needs union + scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    IPB_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)IPB_HIST_BINS * n_jobs, st), "memset hist");
+    IPB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(uint64_t) * 4 * (size_t)n_jobs, st), "memset stats");
+    int rc = IPB_OK;
+    if (n_passes > 0) {
+        int chunks = (296 + n_passes - 1) / n_passes;
+        int max_chunks = H / 32 > 0 ? H / 32 : 1;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        const int rows_per_chunk = (H + chunks - 1) / chunks;
+        chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
+        const size_t smem = sizeof(unsigned) * IPB_HIST_WIN;
+        IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist planes smem");
+        IPB_LAUNCH(ipb_k_hist_planes, dim3(chunks, n_passes), dim3(IPB_HIST_THREADS), smem, stream, planes, H, W,
+                   (const IpbPlanePass*)passes, (const IpbHistJob*)jobs, rows_per_chunk, union_bits, union_wpr,
+                   hist, (unsigned long long*)stats);
+        if ((rc = ipb_check_launch("ipb_k_hist_planes"))) return rc;
+    }
+    if (has_masked_stride) {
+        IPB_LAUNCH(ipb_k_hist_masked_stride, dim3(n_jobs), dim3(256), 0, stream, planes, H, W,
+                   (const IpbHistJob*)jobs, union_bits, union_wpr, (unsigned long long*)row_rank_scratch,
+                   hist, (unsigned long long*)stats);
+        rc = ipb_check_launch("ipb_k_hist_masked_stride");
+    }
+    return rc;
+}
+
 int ipb_hist_quantiles(const uint32_t* hist, const uint64_t* stats, const void* qjobs, int n_q,
                        void* qout, void* stream)
 {

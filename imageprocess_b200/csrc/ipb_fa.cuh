@@ -96,10 +96,17 @@ __device__ __forceinline__ int ipb_uf_load(const int* L, int i) {
     return __ldcg(L + i);          // L2 (coherent) read: parents only ever decrease
 #endif
 }
-__device__ __forceinline__ int ipb_uf_find(const int* L, int i) {
-    int p = ipb_uf_load(L, i);
-    while (p != i) { i = p; p = ipb_uf_load(L, i); }
-    return i;
+// find with path halving: every visited node is re-pointed at its grandparent (atomicMin, so
+// parents only ever decrease and concurrent unions stay correct); later finds walk short paths
+__device__ __forceinline__ int ipb_uf_find(int* L, int i) {
+    while (true) {
+        const int p = ipb_uf_load(L, i);
+        if (p == i) return i;
+        const int gp = ipb_uf_load(L, p);
+        if (gp == p) return p;
+        atomicMin(&L[i], gp);
+        i = gp;
+    }
 }
 __device__ __forceinline__ void ipb_uf_union(int* L, int a, int b) {
     while (true) {

@@ -620,3 +620,235 @@ ipb_k_hist_select_q(const IpbQJob* __restrict__ qjobs, const IpbHistWin* __restr
         out[blockIdx.x] = o;
     }
 }
+
+// ================================================================ fused full histograms per plane
+// ipb_k_hist_planes: the exact 65 536-bin histograms of EVERY job that samples a plane from ONE
+// read of that plane (ipb_hist_planes; passes built like ipb_hist_select's).  A time-lapse frame
+// typically has a full / masked job (FRET background + epsilon), a flat-stride job (Fluor_INT
+// background on vals[::k]) and the FA job (moments of all pixels + a sparse [::k, ::k] sample) on
+// the same channel: three reads of the plane become one, and the per-8-pixel bookkeeping is paid
+// once.  Dense jobs share the shared-memory window (IPB_HIST_WIN / n_dense bins each, brighter
+// values go to L2 atomics); sparse [::k, ::k] jobs count straight into global memory.  A
+// flat-stride job next to a FULL job selects a subset of its pixels: those pixels are counted
+// once, in the stride job's window, and that window is added to both histograms at the end --
+// the kernel is bound by shared-memory atomics (~2 per clock per SM), so every atomic saved counts.
+__global__ void __launch_bounds__(IPB_HIST_THREADS)
+ipb_k_hist_planes(const unsigned short* __restrict__ planes, int H, int W,
+                  const IpbPlanePass* __restrict__ passes, const IpbHistJob* __restrict__ jobs, int rows_per_chunk,
+                  const unsigned* __restrict__ union_bits, int union_wpr,
+                  unsigned* __restrict__ hist, unsigned long long* __restrict__ out_stats)
+{
+    IPB_DYN_SMEM(unsigned, sh);
+    const IpbPlanePass pp = passes[blockIdx.y];
+    const int y_beg = (int)blockIdx.x * rows_per_chunk;
+    int y_end = y_beg + rows_per_chunk;
+    if (y_end > H) y_end = H;
+    if (y_beg >= y_end) return;
+    int pat[IPB_HSEL_MAXJ], kk[IPB_HSEL_MAXJ], wbase[IPB_HSEL_MAXJ];
+    unsigned pat16[IPB_HSEL_MAXJ];                     // bits at multiples of k (flat-stride selection)
+    unsigned* gh[IPB_HSEL_MAXJ];
+    const unsigned* ub[IPB_HSEL_MAXJ];
+    bool moments = false;
+    int n_dense = 0;
+#pragma unroll
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+        pat[u] = -1; kk[u] = 1; wbase[u] = -1; gh[u] = nullptr; ub[u] = nullptr; pat16[u] = 0;
+        if (u < pp.n_jobs) {
+            const IpbHistJob j = jobs[pp.job[u]];
+            pat[u] = j.pattern == IPB_PAT_MASKED_STRIDE ? -1 : j.pattern;     // masked-stride: its own kernel
+            kk[u] = j.k > 0 ? j.k : 1;
+            gh[u] = hist + (size_t)pp.job[u] * IPB_HIST_BINS;
+            ub[u] = (j.pattern == IPB_PAT_MASKED) ? union_bits + (size_t)j.mask_frame * H * union_wpr : nullptr;
+            moments = moments || j.moments != 0;
+            for (int t = 0; t < 16; t += kk[u]) pat16[u] |= 1u << t;
+            if (pat[u] == IPB_PAT_FULL || pat[u] == IPB_PAT_MASKED || pat[u] == IPB_PAT_STRIDE1D) ++n_dense;
+        }
+    }
+    const int win = n_dense ? IPB_HIST_WIN / n_dense : 0;
+    {
+        int d = 0;
+#pragma unroll
+        for (int u = 0; u < IPB_HSEL_MAXJ; ++u)
+            if (pat[u] == IPB_PAT_FULL || pat[u] == IPB_PAT_MASKED || pat[u] == IPB_PAT_STRIDE1D) wbase[u] = (d++) * win;
+    }
+    int pair_full = -1, pair_sub = -1;               // FULL job + flat-stride job: subset counting
+#pragma unroll
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+        if (pat[u] == IPB_PAT_FULL && pair_full < 0) pair_full = u;
+        if (pat[u] == IPB_PAT_STRIDE1D && pair_sub < 0) pair_sub = u;
+    }
+    if (pair_full < 0 || pair_sub < 0) { pair_full = -1; pair_sub = -1; }
+    for (int b = threadIdx.x; b < n_dense * win; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    const unsigned short* img = planes + (size_t)pp.plane * H * W;
+    const unsigned sat_min = pp.sat_min > 0 ? (unsigned)pp.sat_min : 0xffffffffu;
+    const unsigned short* img2 = (pp.sat_min > 0 && pp.excl_plane1 > 0) ? planes + (size_t)(pp.excl_plane1 - 1) * H * W : nullptr;
+    unsigned nsel[IPB_HSEL_MAXJ];
+#pragma unroll
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) nsel[u] = 0;
+    unsigned long long s1 = 0, s2 = 0;
+    const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0) && ((((size_t)img2) & 15) == 0);
+    const int step = vec_ok ? 8 : 1;
+    const int upr = vec_ok ? (W >> 3) : W;
+    const int dy = (int)blockDim.x / upr, dx = (int)blockDim.x % upr;
+    int y = y_beg + (int)threadIdx.x / upr, xu = (int)threadIdx.x % upr;
+
+    // one unit (8-pixel group, or one pixel when the row length is not a multiple of 8)
+    auto process = [&](int y, int x0, const unsigned (&w)[4], const unsigned (&w2)[4]) {
+        if (moments) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j * 2 >= step) break;
+                const unsigned a = w[j] & 0xffffu, b = step == 1 ? 0u : (w[j] >> 16);
+                s1 += a + b;
+                s2 += (unsigned long long)a * a + (unsigned long long)b * b;
+            }
+        }
+        unsigned keep = step == 8 ? 0xffu : 1u;
+        if (pp.sat_min > 0) {
+            keep = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (t >= step) break;
+                const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                const unsigned o = (t & 1) ? (w2[t >> 1] >> 16) : (w2[t >> 1] & 0xffffu);
+                keep |= (v < sat_min && o < sat_min) ? (1u << t) : 0u;
+            }
+        }
+        unsigned sel_sub = 0;                            // pixels the paired flat-stride job selects
+        if (pair_sub >= 0) {
+#pragma unroll
+            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+                if (u != pair_sub) continue;
+                const unsigned k = (unsigned)kk[u];
+                const unsigned long long flat = (unsigned long long)y * W + x0;
+                const unsigned fm = (k & (k - 1u)) == 0u ? (unsigned)flat & (k - 1u)
+                                    : (flat < 0xffffffffull ? (unsigned)flat % k : (unsigned)(flat % (unsigned long long)k));
+                const unsigned first = fm ? k - fm : 0u;
+                sel_sub = (first < 8u ? (pat16[u] << first) & 0xffu : 0u) & keep;
+                nsel[u] += (unsigned)__popc(sel_sub);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+            if (pat[u] < 0 || u == pair_sub) continue;
+            if (u == pair_full) {                         // every kept pixel once: stride pixels in the stride job's window
+                nsel[u] += (unsigned)__popc(keep);
+                const int bf = wbase[u], bs = wbase[pair_sub >= 0 ? pair_sub : 0];
+                unsigned* gs = gh[pair_sub >= 0 ? pair_sub : 0];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (t >= step) break;
+                    if (!((keep >> t) & 1u)) continue;
+                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                    const bool sub = (sel_sub >> t) & 1u;
+                    if (v < (unsigned)win) atomicAdd(&sh[(sub ? bs : bf) + v], 1u);
+                    else { atomicAdd(&gh[u][v], 1u); if (sub) atomicAdd(&gs[v], 1u); }
+                }
+                continue;
+            }
+            unsigned sel = 0;
+            const unsigned k = (unsigned)kk[u];
+            if (pat[u] == IPB_PAT_FULL) sel = 0xffu;
+            else if (pat[u] == IPB_PAT_STRIDE1D) {
+                const unsigned long long flat = (unsigned long long)y * W + x0;
+                const unsigned fm = (k & (k - 1u)) == 0u ? (unsigned)flat & (k - 1u)
+                                    : (flat < 0xffffffffull ? (unsigned)flat % k : (unsigned)(flat % (unsigned long long)k));
+                const unsigned first = fm ? k - fm : 0u;
+                sel = first < 8u ? (pat16[u] << first) & 0xffu : 0u;
+            } else if (pat[u] == IPB_PAT_STRIDE2D) {
+                if ((unsigned)y % k == 0u) {
+                    const unsigned xm = (unsigned)x0 % k;
+                    const unsigned first = xm ? k - xm : 0u;
+                    sel = first < 8u ? (pat16[u] << first) & 0xffu : 0u;
+                }
+            } else if (pat[u] == IPB_PAT_MASKED) {
+                sel = (ub[u][(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
+            }
+            sel &= keep;
+            if (!sel) continue;
+            nsel[u] += (unsigned)__popc(sel);
+            const int base = wbase[u];
+            if (sel == 0xffu && base >= 0) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                    if (v < (unsigned)win) atomicAdd(&sh[base + v], 1u); else atomicAdd(&gh[u][v], 1u);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (t >= step) break;
+                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                    if ((sel >> t) & 1u) {
+                        if (base >= 0 && v < (unsigned)win) atomicAdd(&sh[base + v], 1u); else atomicAdd(&gh[u][v], 1u);
+                    }
+                }
+            }
+        }
+    };
+    if (vec_ok) {
+        while (y < y_end) {
+            int ys[4], xs[4];
+            bool ok[4];
+            uint4 q[4], q2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ys[u] = y; xs[u] = xu << 3;
+                ok[u] = y < y_end;
+                q[u] = make_uint4(0, 0, 0, 0); q2[u] = make_uint4(0, 0, 0, 0);
+                if (ok[u]) {
+                    q[u] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + xs[u]));
+                    if (img2) q2[u] = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + xs[u]));
+                }
+                xu += dx; y += dy;
+                if (xu >= upr) { xu -= upr; ++y; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                const unsigned w[4] = {q[u].x, q[u].y, q[u].z, q[u].w}, w2[4] = {q2[u].x, q2[u].y, q2[u].z, q2[u].w};
+                process(ys[u], xs[u], w, w2);
+            }
+        }
+    } else {
+        for (; y < y_end; xu += dx, y += dy, y += (xu >= upr) ? 1 : 0, xu -= (xu >= upr) ? upr : 0) {
+            const unsigned w[4] = {img[(size_t)y * W + xu], 0u, 0u, 0u};
+            const unsigned w2[4] = {img2 ? (unsigned)img2[(size_t)y * W + xu] : 0u, 0u, 0u, 0u};
+            process(y, xu, w, w2);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_dense * win; b += blockDim.x) {
+        const unsigned c = sh[b];
+        if (c) {
+            const int d = b / win;                       // d-th dense job of the pass
+            int u = 0, seen = -1;
+#pragma unroll
+            for (int q = 0; q < IPB_HSEL_MAXJ; ++q) if (wbase[q] >= 0 && ++seen == d) u = q;
+            atomicAdd(&gh[u][b - d * win], c);
+            if (u == pair_sub) atomicAdd(&gh[pair_full][b - d * win], c);      // subset pixels belong to both
+        }
+    }
+    // per job: selected-pixel count; moments of the plane (all pixels) to every job that asked
+    __shared__ unsigned long long acc[IPB_HSEL_MAXJ + 2];
+    if (threadIdx.x < IPB_HSEL_MAXJ + 2) acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+        const unsigned long long a = ipb_warp_sum((unsigned long long)nsel[u]);
+        if (lane == 0 && a) atomicAdd(&acc[u], a);
+    }
+    s1 = ipb_warp_sum(s1); s2 = ipb_warp_sum(s2);
+    if (lane == 0) { if (s1) atomicAdd(&acc[IPB_HSEL_MAXJ], s1); if (s2) atomicAdd(&acc[IPB_HSEL_MAXJ + 1], s2); }
+    __syncthreads();
+    if (threadIdx.x < pp.n_jobs) {
+        const int u = threadIdx.x, j = pp.job[u];
+        if (acc[u]) atomicAdd(&out_stats[(size_t)j * 4], acc[u]);
+        if (jobs[j].moments) {
+            if (acc[IPB_HSEL_MAXJ]) atomicAdd(&out_stats[(size_t)j * 4 + 1], acc[IPB_HSEL_MAXJ]);
+            if (acc[IPB_HSEL_MAXJ + 1]) atomicAdd(&out_stats[(size_t)j * 4 + 2], acc[IPB_HSEL_MAXJ + 1]);
+        }
+    }
+}

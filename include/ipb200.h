@@ -88,6 +88,12 @@ int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs /* ipb_h
                  int n_jobs, int has_masked_stride, const uint32_t* union_bits, int union_wpr,
                  uint64_t* row_rank_scratch, uint32_t* hist, uint64_t* stats, void* stream);
 
+/* Same histograms and stats as ipb_hist_u16, from ONE read of each plane for all the jobs that
+ * sample it (passes: ipb_plane_pass[], up to 4 jobs sharing a plane and saturation partner).   */
+int ipb_hist_planes(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
+                    const void* passes, int n_passes, int has_masked_stride, const uint32_t* union_bits,
+                    int union_wpr, uint64_t* row_rank_scratch, uint32_t* hist, uint64_t* stats, void* stream);
+
 /* Selection by sampling: the same percentiles as ipb_hist_u16 + ipb_hist_quantiles, exact, with
  * ~16x fewer shared-memory atomics.  A hashed 1/16 sample of every job fixes a value window that
  * holds the wanted ranks with overwhelming probability; ONE further read of each plane (passes:

@@ -360,43 +360,45 @@ def check_combined_batch_shared_rois(eng):
             "percentile": 2.0, "per_channel_p": False, "ch_p_map": {}}
     fa_params = FA_CASES[0]
     px = 0.112
-    job = batch.FrameBatchJob(eng, (F, C, H, W), stages=("fret", "int", "fa"), fret_p=fret_p, int_task=task,
-                              fa_params=fa_params, fa_px=px, want_roi_image=True)
-    polys_pf = [fr[2] for fr in frames]
-    for rep in range(2):                                   # second run goes through the cached plan
-        job.hist_select = bool(rep)                        # ... and through percentiles by sampling
-        res = job.run(eng.mem.from_host(planes), polys_pf)
-        assert len(job._plans) == 1
-        rows_i = batch.rows_intensity(res, F, [1, 2])
-        rows_f = batch.rows_fret(res, F)
-        rows_a = batch.rows_fa(res, job.fa_cfg, fa_params, px, F, save_ok_only=False)
-        R = res.R.host()
-        Rroi = res.R_roi.host()
-        for f, (d, a, polys) in enumerate(frames):
-            D, A = d.astype(np.float32), a.astype(np.float32)
-            want = port.fret_process_pair(D, A, polys, fret_p)
-            assert np.array_equal(R[f], want["R_full"], equal_nan=True)
-            assert np.array_equal(Rroi[f], want["R_roi"], equal_nan=True)
-            assert len(rows_f[f]) == len(want["rows"])
-            for g, w in zip(rows_f[f], want["rows"]):
-                assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"]
-                for k in ("ratio_median", "ratio_p5", "ratio_p95", "donor_median", "yfret_median"):
-                    assert g[k] == w[k], (f, k, g[k], w[k])
-                for k in ("ratio_mean", "ratio_std", "donor_mean", "yfret_mean"):
-                    assert close(g[k], w[k]), (f, k, g[k], w[k])
-            wrows, wbg, _ = port.int_process_key({1: D.copy(), 2: A.copy()}, polys, None, task)
-            assert res.int_bg[f, 0] == wbg[1]["bg"] and res.int_bg[f, 1] == wbg[2]["bg"]
-            check_int_rows(rows_i[f], wrows, (1, 2))
-            stats = port.fa_global_stats(D)
-            got = res.fa_stats[f]
-            if np.float32(got[3]) != stats[0] + job.fa_cfg["alpha"] * stats[1]:
-                stats = (np.float32(got[0]), np.float32(got[1]), stats[2])
-            wfa = port.fa_batch_rows(D, polys, fa_params, px, save_ok_only=False, with_contours=False, stats=stats)
-            assert len(rows_a[f]) == len(wfa), (f, len(rows_a[f]), len(wfa))
-            for g, w in zip(rows_a[f], wfa):
-                assert g["Cell_ID"] == w["Cell_ID"] and g["Category"] == w["Category"]
-                assert g["Area_px"] == w["Area_px"]
-                assert close(float(g["Mean_Intensity_Raw"]), float(w["Mean_Intensity_Raw"]))
+    for fret_scope in ("roi_union", "full"):           # "full": FULL + flat-stride jobs share a plane pass
+        fret_p = dict(fret_p, bg_scope=fret_scope)
+        job = batch.FrameBatchJob(eng, (F, C, H, W), stages=("fret", "int", "fa"), fret_p=fret_p, int_task=task,
+                                  fa_params=fa_params, fa_px=px, want_roi_image=True)
+        polys_pf = [fr[2] for fr in frames]
+        for rep in range(2):                                   # second run goes through the cached plan
+            job.hist_select = bool(rep)                        # ... and through percentiles by sampling
+            res = job.run(eng.mem.from_host(planes), polys_pf)
+            assert len(job._plans) == 1
+            rows_i = batch.rows_intensity(res, F, [1, 2])
+            rows_f = batch.rows_fret(res, F)
+            rows_a = batch.rows_fa(res, job.fa_cfg, fa_params, px, F, save_ok_only=False)
+            R = res.R.host()
+            Rroi = res.R_roi.host()
+            for f, (d, a, polys) in enumerate(frames):
+                D, A = d.astype(np.float32), a.astype(np.float32)
+                want = port.fret_process_pair(D, A, polys, fret_p)
+                assert np.array_equal(R[f], want["R_full"], equal_nan=True)
+                assert np.array_equal(Rroi[f], want["R_roi"], equal_nan=True)
+                assert len(rows_f[f]) == len(want["rows"])
+                for g, w in zip(rows_f[f], want["rows"]):
+                    assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"]
+                    for k in ("ratio_median", "ratio_p5", "ratio_p95", "donor_median", "yfret_median"):
+                        assert g[k] == w[k], (f, k, g[k], w[k])
+                    for k in ("ratio_mean", "ratio_std", "donor_mean", "yfret_mean"):
+                        assert close(g[k], w[k]), (f, k, g[k], w[k])
+                wrows, wbg, _ = port.int_process_key({1: D.copy(), 2: A.copy()}, polys, None, task)
+                assert res.int_bg[f, 0] == wbg[1]["bg"] and res.int_bg[f, 1] == wbg[2]["bg"]
+                check_int_rows(rows_i[f], wrows, (1, 2))
+                stats = port.fa_global_stats(D)
+                got = res.fa_stats[f]
+                if np.float32(got[3]) != stats[0] + job.fa_cfg["alpha"] * stats[1]:
+                    stats = (np.float32(got[0]), np.float32(got[1]), stats[2])
+                wfa = port.fa_batch_rows(D, polys, fa_params, px, save_ok_only=False, with_contours=False, stats=stats)
+                assert len(rows_a[f]) == len(wfa), (f, len(rows_a[f]), len(wfa))
+                for g, w in zip(rows_a[f], wfa):
+                    assert g["Cell_ID"] == w["Cell_ID"] and g["Category"] == w["Category"]
+                    assert g["Area_px"] == w["Area_px"]
+                    assert close(float(g["Mean_Intensity_Raw"]), float(w["Mean_Intensity_Raw"]))
 
 
 def check_region_stats_two_views(eng):
