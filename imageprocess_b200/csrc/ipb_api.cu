@@ -105,6 +105,10 @@ int ipb_rasterize_rois(int rule, int n_rois, const double* verts_xy, const int32
 }
 
 // ---------------------------------------------------------------- histograms / quantiles
+static int ipb_launch_hist_full(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
+                                const uint32_t* union_bits, int union_wpr, uint32_t* hist, uint64_t* stats,
+                                int sample, const IpbHistWin* only_full, void* stream);
+
 int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
                  int has_masked_stride, const uint32_t* union_bits, int union_wpr,
                  uint64_t* row_rank_scratch, uint32_t* hist, uint64_t* stats, void* stream)
@@ -116,18 +120,7 @@ int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs, int n_j
     cudaStream_t st = (cudaStream_t)stream;
     IPB_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)IPB_HIST_BINS * n_jobs, st), "memset hist");
     IPB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(uint64_t) * 4 * (size_t)n_jobs, st), "memset stats");
-    int chunks = (592 + n_jobs - 1) / n_jobs;
-    int max_chunks = H / 32 > 0 ? H / 32 : 1;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
-    const int rows_per_chunk = (H + chunks - 1) / chunks;
-    chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
-    const size_t smem = sizeof(unsigned) * IPB_HIST_WIN;
-    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist smem");
-    IPB_LAUNCH(ipb_k_hist_u16, dim3(chunks, n_jobs), dim3(IPB_HIST_THREADS), smem, stream,
-               planes, H, W, (const IpbHistJob*)jobs, rows_per_chunk, union_bits, union_wpr,
-               hist, (unsigned long long*)stats, 0, (const IpbHistWin*)nullptr);
-    int rc = ipb_check_launch("ipb_k_hist_u16");
+    int rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist, stats, 0, nullptr, stream);
     if (rc) return rc;
     if (has_masked_stride) {
         IPB_LAUNCH(ipb_k_hist_masked_stride, dim3(n_jobs), dim3(256), 0, stream, planes, H, W,
@@ -144,8 +137,8 @@ static int ipb_launch_hist_full(const uint16_t* planes, int H, int W, const void
                                 const uint32_t* union_bits, int union_wpr, uint32_t* hist, uint64_t* stats,
                                 int sample, const IpbHistWin* only_full, void* stream)
 {
-    int chunks = (592 + n_jobs - 1) / n_jobs;
-    int max_chunks = H / 32 > 0 ? H / 32 : 1;
+    int chunks = (296 * 6 + n_jobs - 1) / n_jobs;       // ~6 waves of the 296 resident CTAs
+    int max_chunks = H / 16 > 0 ? H / 16 : 1;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     const int rows_per_chunk = (H + chunks - 1) / chunks;
@@ -228,8 +221,10 @@ int ipb_hist_planes(const uint16_t* planes, int H, int W, const void* jobs, int 
     IPB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(uint64_t) * 4 * (size_t)n_jobs, st), "memset stats");
     int rc = IPB_OK;
     if (n_passes > 0) {
-        int chunks = (296 + n_passes - 1) / n_passes;
-        int max_chunks = H / 32 > 0 ? H / 32 : 1;
+        // 2 CTAs of 1024 threads per SM = 296 resident CTAs; ~6 waves keep the last, partly filled
+        // wave short against the whole launch
+        int chunks = (296 * 6 + n_passes - 1) / n_passes;
+        int max_chunks = H / 16 > 0 ? H / 16 : 1;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;
         const int rows_per_chunk = (H + chunks - 1) / chunks;
