@@ -473,10 +473,13 @@ class FrameBatchJob:
             d_win = self._dev("hist_winrange", ops.HIST_WIN.itemsize * NH)
             d_cnt = self._dev("hist_cnt", 8 * 4 * NH)
             d_hss = self._dev("hstat_sample", 8 * 4 * NH)
+            list_cap = max(4096, (H * W) // 4)                 # low pixels per plane pass (windowed mode: <= ~12 %)
+            d_list = self._dev("hist_list", 4 * list_cap * max(pl.n_passes, 1))
+            d_listn = self._dev("hist_list_n", 4 * max(pl.n_passes, 1))
             lib_call("ipb_hist_select", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, tp("qjobs"), NQ,
                      int(pl.has_ms), union_ptr, self.union_wpr, d_scr.ptr if d_scr is not None else None,
-                     d_hs.ptr, d_hist.ptr, d_hw.ptr, d_win.ptr, d_cnt.ptr, d_hss.ptr, d_hstat.ptr, d_qout.ptr,
-                     op("miss"), stream)
+                     d_hs.ptr, d_hist.ptr, d_hw.ptr, d_win.ptr, d_cnt.ptr, d_hss.ptr, d_hstat.ptr, d_list.ptr, list_cap,
+                     d_listn.ptr, d_qout.ptr, op("miss"), stream)
             lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), stream)
         elif NH:
             lib_call("ipb_hist_planes", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, int(pl.has_ms),

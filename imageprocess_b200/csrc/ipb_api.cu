@@ -155,13 +155,14 @@ int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int 
                     const void* passes, int n_passes, const void* qjobs, int n_q, int has_masked_stride,
                     const uint32_t* union_bits, int union_wpr, uint64_t* row_rank_scratch,
                     uint32_t* hist_sample, uint32_t* hist_full, uint32_t* hist_win, void* win,
-                    uint64_t* cnt, uint64_t* stats_sample, uint64_t* stats, void* qout, uint32_t* miss,
-                    void* stream)
+                    uint64_t* cnt, uint64_t* stats_sample, uint64_t* stats, uint32_t* list, int64_t list_cap,
+                    uint32_t* list_n, void* qout, uint32_t* miss, void* stream)
 {
     IPB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535 && n_passes >= 0 && n_passes <= 65535, "ipb_hist_select: job count out of range");
     if (n_jobs == 0) return IPB_OK;
     IPB_REQUIRE(planes && jobs && passes && hist_sample && hist_full && hist_win && win && cnt && stats_sample &&
-                stats && miss && H > 0 && W > 0, "ipb_hist_select: bad argument");
+                stats && list && list_n && miss && H > 0 && W > 0, "ipb_hist_select: bad argument");
+    IPB_REQUIRE(list_cap > 0 && list_cap < 0x7fffffffLL, "ipb_hist_select: bad list capacity");
     IPB_REQUIRE(n_q == 0 || (qjobs && qout), "ipb_hist_select: quantile jobs without buffers");
     IPB_REQUIRE(!has_masked_stride || (union_bits && row_rank_scratch), "ipb_hist_select: masked stride needs union + scratch");
     cudaStream_t st = (cudaStream_t)stream;
@@ -172,24 +173,30 @@ int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int 
     IPB_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(uint64_t) * 4 * nj, st), "memset cnt");
     IPB_CUDA_TRY(cudaMemsetAsync(stats_sample, 0, sizeof(uint64_t) * 4 * nj, st), "memset stats_sample");
     IPB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(uint64_t) * 4 * nj, st), "memset stats");
+    IPB_CUDA_TRY(cudaMemsetAsync(list_n, 0, sizeof(uint32_t) * (size_t)(n_passes > 0 ? n_passes : 1), st), "memset list_n");
     int rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist_sample, stats_sample, 1, nullptr, stream);
     if (rc) return rc;
     IPB_LAUNCH(ipb_k_hist_windows, dim3(n_jobs), dim3(256), 0, stream, hist_sample, (const unsigned long long*)stats_sample,
                (const IpbHistJob*)jobs, (const IpbQJob*)qjobs, n_q, (IpbHistWin*)win);
     if ((rc = ipb_check_launch("ipb_k_hist_windows"))) return rc;
     if (n_passes > 0) {
-        int chunks = (148 * 3 + n_passes - 1) / n_passes;
+        int chunks = (148 * 4 * 4 + n_passes - 1) / n_passes;
         int max_chunks = H / 8 > 0 ? H / 8 : 1;
         if (chunks > max_chunks) chunks = max_chunks;
         if (chunks < 1) chunks = 1;
         const int rows_per_chunk = (H + chunks - 1) / chunks;
         chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
-        const size_t smem = sizeof(unsigned) * IPB_HSEL_WIN * IPB_HSEL_MAXJ;
-        IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist tail smem");
-        IPB_LAUNCH(ipb_k_hist_tail, dim3(chunks, n_passes), dim3(IPB_HSEL_THREADS), smem, stream, planes, H, W,
+        IPB_LAUNCH(ipb_k_hist_tail, dim3(chunks, n_passes), dim3(IPB_HSEL_THREADS), 0, stream, planes, H, W,
                    (const IpbPlanePass*)passes, (const IpbHistJob*)jobs, (const IpbHistWin*)win, rows_per_chunk,
-                   union_bits, union_wpr, hist_win, (unsigned long long*)cnt, (unsigned long long*)stats);
+                   union_bits, union_wpr, hist_full, list, (unsigned)list_cap, list_n, (unsigned long long*)stats, miss);
         if ((rc = ipb_check_launch("ipb_k_hist_tail"))) return rc;
+        const size_t smem = sizeof(unsigned) * IPB_HSEL_WIN * IPB_HSEL_MAXJ;
+        IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist classify smem");
+        int cchunks = (148 * 3 + n_passes - 1) / n_passes;
+        if (cchunks < 1) cchunks = 1;
+        IPB_LAUNCH(ipb_k_hist_classify, dim3(cchunks, n_passes), dim3(256), smem, stream, (const IpbPlanePass*)passes,
+                   (const IpbHistWin*)win, list, (unsigned)list_cap, list_n, hist_win, (unsigned long long*)cnt, miss);
+        if ((rc = ipb_check_launch("ipb_k_hist_classify"))) return rc;
     }
     rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist_full, stats, 0, (const IpbHistWin*)win, stream);
     if (rc) return rc;

@@ -45,6 +45,8 @@ struct IpbHistJob {
 #define IPB_HSEL_WINDOWED 0
 #define IPB_HSEL_FULL 1          // exact full-range histogram instead (sparse patterns, wide windows)
 #define IPB_HSEL_NONE 2          // no order statistic wanted from this job
+#define IPB_HSEL_SPARSE 3        // [::k, ::k] sample: counted straight into the full histogram by the tail pass
+#define IPB_HSEL_LOWFRAC 0.12    // windowed selection only when at most this fraction lies below the window's end
 struct IpbHistWin { int wlo, whi, mode, pad; };     // window [wlo, whi)
 struct IpbPlanePass { int plane, excl_plane1, sat_min, n_jobs; int job[IPB_HSEL_MAXJ]; };
 
@@ -368,180 +370,311 @@ ipb_k_hist_windows(const unsigned* __restrict__ hs /* sample histograms */,
         IpbHistWin o;
         o.pad = 0;
         if (!any_q) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_NONE; }
-        else if (ns < 256 || !countable || sparse || res[0] < 0 || res[1] < 0) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_FULL; }
+        else if (pattern == IPB_PAT_STRIDE2D) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_SPARSE; }
+        else if (ns < 256 || !countable || sparse || res[0] < 0 || res[1] < 0 ||
+                 (double)want[1] > IPB_HSEL_LOWFRAC * (double)ns) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_FULL; }
         else {
             // a window that starts / ends at the sample's extreme rank is opened to the end of
             // the value range: the true extremes may lie beyond the sample's
-            o.wlo = want[0] == 0 ? 0 : res[0];
-            o.whi = want[1] >= (int)ns - 1 ? IPB_HIST_BINS : res[1] + 1;
+            // the tail pass lists every pixel below the window's end, so the window may start at 0:
+            // a rank can then never fall below it
+            o.wlo = 0;
+            o.whi = res[1] + 1;
             o.mode = (o.whi - o.wlo <= IPB_HSEL_WIN) ? IPB_HSEL_WINDOWED : IPB_HSEL_FULL;
         }
         win[job] = o;
     }
 }
 
-// tail pass: grid (chunks, plane passes), 512 threads; shared = n_jobs windows of 4096 bins.
-// cnt[job] = { below, inside, above, 0 }; moments (sum, sumsq of ALL pixels) -> stats[job][1..2],
-// n_selected -> stats[job][0].
+// tail pass: grid (chunks, plane passes).  Per job: number of selected pixels -> stats[job][0];
+// moments of the plane -> stats[job][1..2]; sparse [::k, ::k] jobs are counted straight into
+// their full histogram.  Every selected pixel BELOW the largest window end of the pass is appended
+// (value | selection bits << 16) to the pass's list; all the others are "above" for every job and
+// need nothing more.  The common 8-pixel group is decided by one vector minimum.
 #define IPB_HSEL_THREADS 512
+#define IPB_HSEL_WBUF 128         // low pixels staged per warp before one global append
 __global__ void __launch_bounds__(IPB_HSEL_THREADS, 2)
 ipb_k_hist_tail(const unsigned short* __restrict__ planes, int H, int W,
                 const IpbPlanePass* __restrict__ passes, const IpbHistJob* __restrict__ jobs,
                 const IpbHistWin* __restrict__ win, int rows_per_chunk,
                 const unsigned* __restrict__ union_bits, int union_wpr,
-                unsigned* __restrict__ hw /* [jobs][IPB_HSEL_WIN] */,
-                unsigned long long* __restrict__ cnt, unsigned long long* __restrict__ stats)
+                unsigned* __restrict__ hist_full, unsigned* __restrict__ list, unsigned list_cap,
+                unsigned* __restrict__ list_n, unsigned long long* __restrict__ stats, unsigned* __restrict__ miss)
 {
-    IPB_DYN_SMEM(unsigned, sh);
     const IpbPlanePass pp = passes[blockIdx.y];
     const int y_beg = (int)blockIdx.x * rows_per_chunk;
     int y_end = y_beg + rows_per_chunk;
     if (y_end > H) y_end = H;
-    // per job only what the inner loop needs (registers): pattern (-1 = not windowed), stride, window
-    int pat[IPB_HSEL_MAXJ], kk[IPB_HSEL_MAXJ];
-    unsigned wlo[IPB_HSEL_MAXJ], whi[IPB_HSEL_MAXJ];
+    if (y_beg >= y_end) return;
+    int pat[IPB_HSEL_MAXJ], kk[IPB_HSEL_MAXJ], mode[IPB_HSEL_MAXJ];
+    unsigned pat16[IPB_HSEL_MAXJ];
+    unsigned* gh[IPB_HSEL_MAXJ];
     const unsigned* ub[IPB_HSEL_MAXJ];
-    bool need = false, moments = false;
+    bool moments = false;
+    unsigned whi_all = 0;
 #pragma unroll
     for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        pat[u] = -1; kk[u] = 1; wlo[u] = 0; whi[u] = 0; ub[u] = nullptr;
+        pat[u] = -1; kk[u] = 1; mode[u] = IPB_HSEL_NONE; pat16[u] = 0; gh[u] = nullptr; ub[u] = nullptr;
         if (u < pp.n_jobs) {
             const IpbHistJob j = jobs[pp.job[u]];
             const IpbHistWin w = win[pp.job[u]];
             moments = moments || j.moments != 0;
-            if (w.mode == IPB_HSEL_WINDOWED) {
-                pat[u] = j.pattern; kk[u] = j.k > 0 ? j.k : 1;
-                wlo[u] = (unsigned)w.wlo; whi[u] = (unsigned)w.whi;
+            if (w.mode == IPB_HSEL_WINDOWED || w.mode == IPB_HSEL_SPARSE) {
+                pat[u] = j.pattern; kk[u] = j.k > 0 ? j.k : 1; mode[u] = w.mode;
+                gh[u] = hist_full + (size_t)pp.job[u] * IPB_HIST_BINS;
                 ub[u] = (j.pattern == IPB_PAT_MASKED) ? union_bits + (size_t)j.mask_frame * H * union_wpr : nullptr;
+                for (int t = 0; t < 16; t += kk[u]) pat16[u] |= 1u << t;
+                if (w.mode == IPB_HSEL_WINDOWED && (unsigned)w.whi > whi_all) whi_all = (unsigned)w.whi;
             }
-            need = need || w.mode == IPB_HSEL_WINDOWED || j.moments;
         }
     }
-    if (!need || y_beg >= y_end) return;
-    for (int b = threadIdx.x; b < pp.n_jobs * IPB_HSEL_WIN; b += blockDim.x) sh[b] = 0;
-    __syncthreads();
+    {
+        bool need = moments;
+#pragma unroll
+        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) need = need || pat[u] >= 0;
+        if (!need) return;
+    }
+    unsigned* lst = list + (size_t)blockIdx.y * list_cap;
+    unsigned* lst_n = list_n + blockIdx.y;
     const unsigned short* img = planes + (size_t)pp.plane * H * W;
     const unsigned sat_min = pp.sat_min > 0 ? (unsigned)pp.sat_min : 0xffffffffu;
     const unsigned short* img2 = (pp.sat_min > 0 && pp.excl_plane1 > 0) ? planes + (size_t)(pp.excl_plane1 - 1) * H * W : nullptr;
-    unsigned below[IPB_HSEL_MAXJ], inside[IPB_HSEL_MAXJ], above[IPB_HSEL_MAXJ];
-    unsigned long long s1 = 0, s2 = 0;
+    unsigned nsel[IPB_HSEL_MAXJ];
 #pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) { below[u] = inside[u] = above[u] = 0; }
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) nsel[u] = 0;
+    unsigned long long s1 = 0, s2 = 0;
     const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0) && ((((size_t)img2) & 15) == 0);
     const int step = vec_ok ? 8 : 1;
-    const int upr = vec_ok ? (W >> 3) : W;                            // units (vectors or pixels) per row
+    const int upr = vec_ok ? (W >> 3) : W;
     const int dy = (int)blockDim.x / upr, dx = (int)blockDim.x % upr;
     int y = y_beg + (int)threadIdx.x / upr, xu = (int)threadIdx.x % upr;
-    unsigned whi_all = 0;                      // pixels >= whi_all are "above" for every windowed job
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) if (pat[u] >= 0 && whi[u] > whi_all) whi_all = whi[u];
+    const int lane = threadIdx.x & 31;
+    __shared__ unsigned wbuf_all[IPB_HSEL_THREADS / 32][IPB_HSEL_WBUF];
+    unsigned* wbuf = wbuf_all[threadIdx.x >> 5];
+    unsigned wcount = 0;                                   // entries staged by this warp (warp-uniform)
+    auto flush = [&]() {
+        if (wcount == 0) return;
+        __syncwarp();
+        unsigned g = 0;
+        if (lane == 0) g = atomicAdd(lst_n, wcount);
+        g = __shfl_sync(IPB_FULL, g, 0);
+        for (unsigned i = lane; i < wcount; i += 32) if (g + i < list_cap) lst[g + i] = wbuf[i];
+        __syncwarp();
+        wcount = 0;
+    };
 
-    // selection masks of one unit (8-pixel group or single pixel) for every windowed job
-    auto select = [&](int y, int x0, unsigned (&sel)[IPB_HSEL_MAXJ]) {
+    auto process = [&](bool ok, int y, int x0, const unsigned (&w)[4], const unsigned (&w2)[4]) {
+        unsigned low = 0, selj[IPB_HSEL_MAXJ];
 #pragma unroll
-        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-            sel[u] = 0;
-            if (pat[u] < 0) continue;
-            const int k = kk[u];
-            if (pat[u] == IPB_PAT_FULL) sel[u] = 0xffu;
-            else if (pat[u] == IPB_PAT_STRIDE1D) {
-                const unsigned long long flat = (unsigned long long)y * W + x0;
-                const unsigned fm = flat < 0xffffffffull ? (unsigned)flat % (unsigned)k : (unsigned)(flat % (unsigned long long)k);
-                const int first = (int)(((unsigned)k - fm) % (unsigned)k);
-                for (int t = first; t < step; t += k) sel[u] |= 1u << t;
-            } else if (pat[u] == IPB_PAT_MASKED) {
-                sel[u] = (ub[u][(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
-            }
-            if (!vec_ok) sel[u] &= 1u;
-        }
-    };
-    // exact classification of one pixel for every job that selects it
-    auto classify = [&](unsigned v, int t, const unsigned (&sel)[IPB_HSEL_MAXJ]) {
-#pragma unroll
-        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-            if ((sel[u] >> t) & 1u) {
-                if (v < wlo[u]) ++below[u];
-                else if (v >= whi[u]) ++above[u];
-                else { ++inside[u]; atomicAdd(&sh[u * IPB_HSEL_WIN + (v - wlo[u])], 1u); }
-            }
-        }
-    };
-    if (vec_ok) {
-        // the common pixel is above every window (low percentiles): one vector minimum decides
-        // that for all eight pixels; only pixels below whi_all are classified one by one
-        auto process = [&](int y, int x0, const uint4& q, const uint4& q2) {
-            const unsigned w0 = q.x, w1 = q.y, w2 = q.z, w3 = q.w;
-            unsigned sel[IPB_HSEL_MAXJ];
-            select(y, x0, sel);
+        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) selj[u] = 0;
+        if (ok) {
             if (moments) {
-                const unsigned wv[4] = {w0, w1, w2, w3};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const unsigned a = wv[j] & 0xffffu, b = wv[j] >> 16;
+                    if (j * 2 >= step) break;
+                    const unsigned a = w[j] & 0xffffu, b = step == 1 ? 0u : (w[j] >> 16);
                     s1 += a + b;
                     s2 += (unsigned long long)a * a + (unsigned long long)b * b;
                 }
             }
-            unsigned keep = 0xffu;
+            unsigned keep = step == 8 ? 0xffu : 1u;
             if (pp.sat_min > 0) {
-                const unsigned wv[4] = {w0, w1, w2, w3}, ov[4] = {q2.x, q2.y, q2.z, q2.w};
                 keep = 0;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    const unsigned v = (t & 1) ? (wv[t >> 1] >> 16) : (wv[t >> 1] & 0xffffu);
-                    const unsigned o = (t & 1) ? (ov[t >> 1] >> 16) : (ov[t >> 1] & 0xffffu);
+                    if (t >= step) break;
+                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                    const unsigned o = (t & 1) ? (w2[t >> 1] >> 16) : (w2[t >> 1] & 0xffffu);
                     keep |= (v < sat_min && o < sat_min) ? (1u << t) : 0u;
                 }
             }
-            const unsigned m01 = umin(umin(w0 & 0xffffu, w0 >> 16), umin(w1 & 0xffffu, w1 >> 16));
-            const unsigned m23 = umin(umin(w2 & 0xffffu, w2 >> 16), umin(w3 & 0xffffu, w3 >> 16));
-            unsigned low = 0;
-            if (umin(m01, m23) < whi_all) {
-                const unsigned wv[4] = {w0, w1, w2, w3};
+            unsigned vmin = w[0] & 0xffffu;
+            if (step == 8) {
+                const unsigned m01 = umin(umin(w[0] & 0xffffu, w[0] >> 16), umin(w[1] & 0xffffu, w[1] >> 16));
+                const unsigned m23 = umin(umin(w[2] & 0xffffu, w[2] >> 16), umin(w[3] & 0xffffu, w[3] >> 16));
+                vmin = umin(m01, m23);
+            }
+            if (vmin < whi_all) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    const unsigned v = (t & 1) ? (wv[t >> 1] >> 16) : (wv[t >> 1] & 0xffffu);
+                    if (t >= step) break;
+                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
                     low |= (v < whi_all) ? (1u << t) : 0u;
                 }
+                low &= keep;
             }
+            unsigned anysel = 0;
 #pragma unroll
-            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) above[u] += (unsigned)__popc(sel[u] & keep & ~low);
-            unsigned todo = low & keep;
-            while (todo) {
-                const int t = __ffs((int)todo) - 1;
-                todo &= todo - 1;
-                const unsigned word = t < 4 ? (t < 2 ? w0 : w1) : (t < 6 ? w2 : w3);
-                classify((t & 1) ? (word >> 16) : (word & 0xffffu), t, sel);
-            }
-        };
-        while (y < y_end) {
-            int ys[2], xs[2];
-            bool ok[2];
-            uint4 q[2], q2[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                ys[u] = y; xs[u] = xu << 3;
-                ok[u] = y < y_end;
-                q[u] = make_uint4(0, 0, 0, 0); q2[u] = make_uint4(0, 0, 0, 0);
-                if (ok[u]) {
-                    q[u] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + xs[u]));
-                    if (img2) q2[u] = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + xs[u]));
+            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+                if (pat[u] < 0) continue;
+                unsigned sel = 0;
+                const unsigned k = (unsigned)kk[u];
+                if (pat[u] == IPB_PAT_FULL) sel = 0xffu;
+                else if (pat[u] == IPB_PAT_STRIDE1D) {
+                    const unsigned long long flat = (unsigned long long)y * W + x0;
+                    const unsigned fm = (k & (k - 1u)) == 0u ? (unsigned)flat & (k - 1u)
+                                        : (flat < 0xffffffffull ? (unsigned)flat % k : (unsigned)(flat % (unsigned long long)k));
+                    const unsigned first = fm ? k - fm : 0u;
+                    sel = first < 8u ? (pat16[u] << first) & 0xffu : 0u;
+                } else if (pat[u] == IPB_PAT_STRIDE2D) {
+                    if ((unsigned)y % k == 0u) {
+                        const unsigned xm = (unsigned)x0 % k;
+                        const unsigned first = xm ? k - xm : 0u;
+                        sel = first < 8u ? (pat16[u] << first) & 0xffu : 0u;
+                    }
+                } else if (pat[u] == IPB_PAT_MASKED) {
+                    sel = (ub[u][(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
                 }
-                xu += dx; y += dy;
-                if (xu >= upr) { xu -= upr; ++y; }
+                sel &= keep;
+                if (step == 1) sel &= 1u;
+                nsel[u] += (unsigned)__popc(sel);
+                if (mode[u] == IPB_HSEL_SPARSE) {               // few pixels: straight to the full histogram
+                    unsigned todo = sel;
+                    while (todo) {
+                        const int t = __ffs((int)todo) - 1;
+                        todo &= todo - 1;
+                        const unsigned word = t < 4 ? (t < 2 ? w[0] : w[1]) : (t < 6 ? w[2] : w[3]);
+                        atomicAdd(&gh[u][(t & 1) ? (word >> 16) : (word & 0xffffu)], 1u);
+                    }
+                } else {
+                    anysel |= sel;
+                    selj[u] = sel;
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) if (ok[u]) process(ys[u], xs[u], q[u], q2[u]);
+            low &= anysel;
         }
-    } else {
-        for (; y < y_end; xu += dx, y += dy, y += (xu >= upr) ? 1 : 0, xu -= (xu >= upr) ? upr : 0) {
-            const unsigned v = img[(size_t)y * W + xu];
-            const unsigned o = img2 ? (unsigned)img2[(size_t)y * W + xu] : 0u;
-            if (moments) { s1 += v; s2 += (unsigned long long)v * v; }
-            if (!(v < sat_min && o < sat_min)) continue;
-            unsigned sel[IPB_HSEL_MAXJ];
-            select(y, xu, sel);
-            classify(v, 0, sel);
+        // append this warp's low pixels.  They are staged in a per-warp shared buffer (positions
+        // from a warp scan, no atomics) and go to the pass's global list 128 at a time with ONE
+        // global atomic per flush; a trip with more than 64 of them writes through directly.
+        const unsigned cnt = (unsigned)__popc(low);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+        const unsigned total = __shfl_sync(IPB_FULL, incl, 31);
+        if (total == 0) return;                                   // warp-uniform
+        const bool direct = total > 64u;
+        if (!direct && wcount + total > IPB_HSEL_WBUF) flush();
+        unsigned base;
+        if (direct) {
+            base = 0;
+            if (lane == 31) base = atomicAdd(lst_n, total);
+            base = __shfl_sync(IPB_FULL, base, 31) + incl - cnt;
+        } else {
+            base = wcount + incl - cnt;
+            wcount += total;
+        }
+        unsigned todo = low;
+        while (todo) {
+            const int t = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const unsigned word = t < 4 ? (t < 2 ? w[0] : w[1]) : (t < 6 ? w[2] : w[3]);
+            const unsigned v = (t & 1) ? (word >> 16) : (word & 0xffffu);
+            unsigned sb = 0;                                      // which jobs selected this pixel
+#pragma unroll
+            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) sb |= ((selj[u] >> t) & 1u) << u;
+            if (direct) { if (base < list_cap) lst[base] = v | (sb << 16); }
+            else wbuf[base] = v | (sb << 16);
+            ++base;
+        }
+    };
+    // trips are warp-uniform (every lane of a warp runs the same number of them), the scans need that
+    const int units_band = (y_end - y_beg) * upr;
+    const int trips = (units_band + (int)blockDim.x - 1) / (int)blockDim.x;
+    for (int trip = 0; trip < trips; trip += 2) {             // two units per trip: both loads issued first
+        bool ok[2];
+        int ys[2], xs[2];
+        unsigned w[2][4], w2[2][4];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            ok[g] = (trip + g < trips) && y < y_end;
+            ys[g] = y; xs[g] = xu * step;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { w[g][j] = 0; w2[g][j] = 0; }
+            if (ok[g]) {
+                if (vec_ok) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + xs[g]));
+                    w[g][0] = q.x; w[g][1] = q.y; w[g][2] = q.z; w[g][3] = q.w;
+                    if (img2) {
+                        const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + xs[g]));
+                        w2[g][0] = q2.x; w2[g][1] = q2.y; w2[g][2] = q2.z; w2[g][3] = q2.w;
+                    }
+                } else {
+                    w[g][0] = img[(size_t)y * W + xs[g]];
+                    if (img2) w2[g][0] = img2[(size_t)y * W + xs[g]];
+                }
+            }
+            xu += dx; y += dy;
+            if (xu >= upr) { xu -= upr; ++y; }
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) if (trip + g < trips) process(ok[g], ys[g], xs[g], w[g], w2[g]);
+    }
+    flush();
+    // per job: selected-pixel count; moments of the plane (all pixels) to every job that asked
+    __shared__ unsigned long long acc[IPB_HSEL_MAXJ + 2];
+    if (threadIdx.x < IPB_HSEL_MAXJ + 2) acc[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+        const unsigned long long a = ipb_warp_sum((unsigned long long)nsel[u]);
+        if (lane == 0 && a) atomicAdd(&acc[u], a);
+    }
+    s1 = ipb_warp_sum(s1); s2 = ipb_warp_sum(s2);
+    if (lane == 0) { if (s1) atomicAdd(&acc[IPB_HSEL_MAXJ], s1); if (s2) atomicAdd(&acc[IPB_HSEL_MAXJ + 1], s2); }
+    __syncthreads();
+    if (threadIdx.x < pp.n_jobs) {
+        const int u = threadIdx.x, j = pp.job[u];
+        if (acc[u]) atomicAdd(&stats[(size_t)j * 4], acc[u]);
+        if (jobs[j].moments) {
+            if (acc[IPB_HSEL_MAXJ]) atomicAdd(&stats[(size_t)j * 4 + 1], acc[IPB_HSEL_MAXJ]);
+            if (acc[IPB_HSEL_MAXJ + 1]) atomicAdd(&stats[(size_t)j * 4 + 2], acc[IPB_HSEL_MAXJ + 1]);
+        }
+    }
+    (void)miss;                                            // list overflow is reported by the classify pass
+}
+
+// classify pass: grid (chunks, plane passes), 256 threads.  Every list entry is placed, per job
+// that selected it, below the job's window or into its 4096-bin window histogram.
+// cnt[job] = { below, inside, 0, 0 }.
+__global__ void __launch_bounds__(256)
+ipb_k_hist_classify(const IpbPlanePass* __restrict__ passes, const IpbHistWin* __restrict__ win,
+                    const unsigned* __restrict__ list, unsigned list_cap, const unsigned* __restrict__ list_n,
+                    unsigned* __restrict__ hw, unsigned long long* __restrict__ cnt, unsigned* __restrict__ miss)
+{
+    IPB_DYN_SMEM(unsigned, sh);
+    const IpbPlanePass pp = passes[blockIdx.y];
+    const unsigned n_all = list_n[blockIdx.y];
+    if (n_all > list_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(miss, 1u); return; }   // list overflow
+    const unsigned per = (n_all + gridDim.x - 1) / gridDim.x;
+    const unsigned i0 = blockIdx.x * per;
+    unsigned i1 = i0 + per;
+    if (i1 > n_all) i1 = n_all;
+    if (i0 >= i1) return;
+    unsigned wlo[IPB_HSEL_MAXJ], whi[IPB_HSEL_MAXJ];
+    bool on[IPB_HSEL_MAXJ];
+#pragma unroll
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+        on[u] = false; wlo[u] = whi[u] = 0;
+        if (u < pp.n_jobs) {
+            const IpbHistWin w = win[pp.job[u]];
+            on[u] = w.mode == IPB_HSEL_WINDOWED;
+            wlo[u] = (unsigned)w.wlo; whi[u] = (unsigned)w.whi;
+        }
+    }
+    for (int b = threadIdx.x; b < pp.n_jobs * IPB_HSEL_WIN; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    const unsigned* lst = list + (size_t)blockIdx.y * list_cap;
+    unsigned below[IPB_HSEL_MAXJ], inside[IPB_HSEL_MAXJ];
+#pragma unroll
+    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) below[u] = inside[u] = 0;
+    for (unsigned i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const unsigned e = lst[i], v = e & 0xffffu, sb = e >> 16;
+#pragma unroll
+        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
+            if (on[u] && ((sb >> u) & 1u)) {
+                if (v < wlo[u]) ++below[u];
+                else if (v < whi[u]) { ++inside[u]; atomicAdd(&sh[u * IPB_HSEL_WIN + (v - wlo[u])], 1u); }
+            }
         }
     }
     __syncthreads();
@@ -549,33 +682,14 @@ ipb_k_hist_tail(const unsigned short* __restrict__ planes, int H, int W,
         const unsigned c = sh[b];
         if (c) atomicAdd(&hw[(size_t)pp.job[b / IPB_HSEL_WIN] * IPB_HSEL_WIN + (b % IPB_HSEL_WIN)], c);
     }
-    // block reduction: per job three counters (+ the two moment sums)
-    __shared__ unsigned long long red[16];
-    __shared__ unsigned long long acc[3 * IPB_HSEL_MAXJ + 2];
-    if (threadIdx.x < 3 * IPB_HSEL_MAXJ + 2) acc[threadIdx.x] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        unsigned long long a = ipb_warp_sum((unsigned long long)below[u]);
-        unsigned long long b = ipb_warp_sum((unsigned long long)inside[u]);
-        unsigned long long c = ipb_warp_sum((unsigned long long)above[u]);
-        if (lane == 0) { if (a) atomicAdd(&acc[3 * u], a); if (b) atomicAdd(&acc[3 * u + 1], b); if (c) atomicAdd(&acc[3 * u + 2], c); }
-    }
-    s1 = ipb_warp_sum(s1); s2 = ipb_warp_sum(s2);
-    if (lane == 0) { if (s1) atomicAdd(&acc[3 * IPB_HSEL_MAXJ], s1); if (s2) atomicAdd(&acc[3 * IPB_HSEL_MAXJ + 1], s2); }
-    (void)red;
-    __syncthreads();
-    if (threadIdx.x < pp.n_jobs) {
-        const int u = threadIdx.x, j = pp.job[u];
-        const unsigned long long a = acc[3 * u], b = acc[3 * u + 1], c = acc[3 * u + 2];
-        if (a) atomicAdd(&cnt[(size_t)j * 4], a);
-        if (b) atomicAdd(&cnt[(size_t)j * 4 + 1], b);
-        if (c) atomicAdd(&cnt[(size_t)j * 4 + 2], c);
-        if (a + b + c) atomicAdd(&stats[(size_t)j * 4], a + b + c);
-        if (jobs[j].moments) {
-            if (acc[3 * IPB_HSEL_MAXJ]) atomicAdd(&stats[(size_t)j * 4 + 1], acc[3 * IPB_HSEL_MAXJ]);
-            if (acc[3 * IPB_HSEL_MAXJ + 1]) atomicAdd(&stats[(size_t)j * 4 + 2], acc[3 * IPB_HSEL_MAXJ + 1]);
+        const unsigned long long a = ipb_warp_sum((unsigned long long)below[u]);
+        const unsigned long long b = ipb_warp_sum((unsigned long long)inside[u]);
+        if (lane == 0 && u < pp.n_jobs) {
+            if (a) atomicAdd(&cnt[(size_t)pp.job[u] * 4], a);
+            if (b) atomicAdd(&cnt[(size_t)pp.job[u] * 4 + 1], b);
         }
     }
 }
@@ -632,6 +746,11 @@ ipb_k_hist_select_q(const IpbQJob* __restrict__ qjobs, const IpbHistWin* __restr
 // flat-stride job next to a FULL job selects a subset of its pixels: those pixels are counted
 // once, in the stride job's window, and that window is added to both histograms at the end --
 // the kernel is bound by shared-memory atomics (~2 per clock per SM), so every atomic saved counts.
+// n % k for n < 2^32 / k with magic = ceil(2^32 / k): one multiply-high instead of a division
+__device__ __forceinline__ unsigned ipb_fastmod(unsigned n, unsigned k, unsigned magic) {
+    return n - __umulhi(n, magic) * k;
+}
+
 __global__ void __launch_bounds__(IPB_HIST_THREADS)
 ipb_k_hist_planes(const unsigned short* __restrict__ planes, int H, int W,
                   const IpbPlanePass* __restrict__ passes, const IpbHistJob* __restrict__ jobs, int rows_per_chunk,
@@ -644,48 +763,45 @@ ipb_k_hist_planes(const unsigned short* __restrict__ planes, int H, int W,
     int y_end = y_beg + rows_per_chunk;
     if (y_end > H) y_end = H;
     if (y_beg >= y_end) return;
-    int pat[IPB_HSEL_MAXJ], kk[IPB_HSEL_MAXJ], wbase[IPB_HSEL_MAXJ];
-    unsigned pat16[IPB_HSEL_MAXJ];                     // bits at multiples of k (flat-stride selection)
-    unsigned* gh[IPB_HSEL_MAXJ];
-    const unsigned* ub[IPB_HSEL_MAXJ];
+    // The jobs of a pass are sorted into fixed roles held in scalars (no indexed register arrays
+    // in the pixel loop):  F = a FULL job, S = a flat-stride job (subset of F when both exist: its
+    // pixels are counted once, in S's window, which is added to both histograms at the flush),
+    // M = a masked job, P = a sparse [::k, ::k] job.  A second job of a role takes the generic slot G.
+    int jF = -1, jS = -1, jM = -1, jP = -1, jG = -1, patG = -1;
+    unsigned kS = 1, kP = 1, kG = 1;
     bool moments = false;
-    int n_dense = 0;
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        pat[u] = -1; kk[u] = 1; wbase[u] = -1; gh[u] = nullptr; ub[u] = nullptr; pat16[u] = 0;
-        if (u < pp.n_jobs) {
-            const IpbHistJob j = jobs[pp.job[u]];
-            pat[u] = j.pattern == IPB_PAT_MASKED_STRIDE ? -1 : j.pattern;     // masked-stride: its own kernel
-            kk[u] = j.k > 0 ? j.k : 1;
-            gh[u] = hist + (size_t)pp.job[u] * IPB_HIST_BINS;
-            ub[u] = (j.pattern == IPB_PAT_MASKED) ? union_bits + (size_t)j.mask_frame * H * union_wpr : nullptr;
-            moments = moments || j.moments != 0;
-            for (int t = 0; t < 16; t += kk[u]) pat16[u] |= 1u << t;
-            if (pat[u] == IPB_PAT_FULL || pat[u] == IPB_PAT_MASKED || pat[u] == IPB_PAT_STRIDE1D) ++n_dense;
-        }
+    for (int u = 0; u < pp.n_jobs; ++u) {
+        const IpbHistJob j = jobs[pp.job[u]];
+        moments = moments || j.moments != 0;
+        const unsigned k = j.k > 0 ? (unsigned)j.k : 1u;
+        if (j.pattern == IPB_PAT_FULL && jF < 0) jF = u;
+        else if (j.pattern == IPB_PAT_STRIDE1D && jS < 0) { jS = u; kS = k; }
+        else if (j.pattern == IPB_PAT_MASKED && jM < 0) jM = u;
+        else if (j.pattern == IPB_PAT_STRIDE2D && jP < 0) { jP = u; kP = k; }
+        else if (j.pattern != IPB_PAT_MASKED_STRIDE && jG < 0) { jG = u; patG = j.pattern; kG = k; }
+        // IPB_PAT_MASKED_STRIDE has its own kernel; a third job of one role cannot occur (<= 4 jobs, 5 roles)
     }
-    const int win = n_dense ? IPB_HIST_WIN / n_dense : 0;
-    {
-        int d = 0;
-#pragma unroll
-        for (int u = 0; u < IPB_HSEL_MAXJ; ++u)
-            if (pat[u] == IPB_PAT_FULL || pat[u] == IPB_PAT_MASKED || pat[u] == IPB_PAT_STRIDE1D) wbase[u] = (d++) * win;
-    }
-    int pair_full = -1, pair_sub = -1;               // FULL job + flat-stride job: subset counting
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        if (pat[u] == IPB_PAT_FULL && pair_full < 0) pair_full = u;
-        if (pat[u] == IPB_PAT_STRIDE1D && pair_sub < 0) pair_sub = u;
-    }
-    if (pair_full < 0 || pair_sub < 0) { pair_full = -1; pair_sub = -1; }
-    for (int b = threadIdx.x; b < n_dense * win; b += blockDim.x) sh[b] = 0;
+    const int n_dense = (jF >= 0) + (jS >= 0) + (jM >= 0) + (jG >= 0 && patG != IPB_PAT_STRIDE2D);
+    const unsigned win = n_dense ? (unsigned)(IPB_HIST_WIN / n_dense) : 0u;
+    int d = 0;
+    const int bF = jF >= 0 ? (d++) * (int)win : 0, bS = jS >= 0 ? (d++) * (int)win : 0, bM = jM >= 0 ? (d++) * (int)win : 0;
+    const int bG = (jG >= 0 && patG != IPB_PAT_STRIDE2D) ? (d++) * (int)win : -1;
+    auto ghist = [&](int slot) { return hist + (size_t)pp.job[slot < 0 ? 0 : slot] * IPB_HIST_BINS; };
+    unsigned* gF = ghist(jF); unsigned* gS = ghist(jS); unsigned* gM = ghist(jM); unsigned* gP = ghist(jP); unsigned* gG = ghist(jG);
+    const unsigned* ubM = jM >= 0 ? union_bits + (size_t)jobs[pp.job[jM]].mask_frame * H * union_wpr : nullptr;
+    const unsigned* ubG = (jG >= 0 && patG == IPB_PAT_MASKED) ? union_bits + (size_t)jobs[pp.job[jG]].mask_frame * H * union_wpr : nullptr;
+    unsigned p16S = 0, p16P = 0, p16G = 0;
+    for (unsigned t = 0; t < 16; t += kS) p16S |= 1u << t;
+    for (unsigned t = 0; t < 16; t += kP) p16P |= 1u << t;
+    for (unsigned t = 0; t < 16; t += kG) p16G |= 1u << t;
+    const unsigned mgP = (unsigned)((0x100000000ull + kP - 1) / kP), mgG = (unsigned)((0x100000000ull + kG - 1) / kG);
+    const bool pairFS = jF >= 0 && jS >= 0;
+    for (int b = threadIdx.x; b < n_dense * (int)win; b += blockDim.x) sh[b] = 0;
     __syncthreads();
     const unsigned short* img = planes + (size_t)pp.plane * H * W;
     const unsigned sat_min = pp.sat_min > 0 ? (unsigned)pp.sat_min : 0xffffffffu;
     const unsigned short* img2 = (pp.sat_min > 0 && pp.excl_plane1 > 0) ? planes + (size_t)(pp.excl_plane1 - 1) * H * W : nullptr;
-    unsigned nsel[IPB_HSEL_MAXJ];
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) nsel[u] = 0;
+    unsigned nF = 0, nS = 0, nM = 0, nP = 0, nG = 0;
     unsigned long long s1 = 0, s2 = 0;
     const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0) && ((((size_t)img2) & 15) == 0);
     const int step = vec_ok ? 8 : 1;
@@ -693,16 +809,49 @@ ipb_k_hist_planes(const unsigned short* __restrict__ planes, int H, int W,
     const int dy = (int)blockDim.x / upr, dx = (int)blockDim.x % upr;
     int y = y_beg + (int)threadIdx.x / upr, xu = (int)threadIdx.x % upr;
 
+    // flat-stride selection of one unit: bits of the pixels with flat index % k == 0
+    auto stride1d = [&](int y, int x0, unsigned k, unsigned p16) -> unsigned {
+        const unsigned long long flat = (unsigned long long)y * W + x0;
+        const unsigned fm = (k & (k - 1u)) == 0u ? (unsigned)flat & (k - 1u)
+                            : (flat < 0xffffffffull ? (unsigned)flat % k : (unsigned)(flat % (unsigned long long)k));
+        const unsigned first = fm ? k - fm : 0u;
+        return first < 8u ? (p16 << first) & 0xffu : 0u;
+    };
+    auto stride2d = [&](int y, int x0, unsigned k, unsigned p16, unsigned magic) -> unsigned {
+        if (ipb_fastmod((unsigned)y, k, magic) != 0u) return 0u;
+        const unsigned xm = ipb_fastmod((unsigned)x0, k, magic);
+        const unsigned first = xm ? k - xm : 0u;
+        return first < 8u ? (p16 << first) & 0xffu : 0u;
+    };
+    // count the selected pixels of one unit into a dense job's window / global histogram
+    auto count_dense = [&](unsigned sel, int base, unsigned* g, const unsigned (&w)[4]) {
+        if (sel == 0xffu) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
+                if (v < win) atomicAdd(&sh[base + v], 1u); else atomicAdd(&g[v], 1u);
+            }
+        } else {
+            while (sel) {
+                const int t = __ffs((int)sel) - 1;
+                sel &= sel - 1;
+                const unsigned word = t < 4 ? (t < 2 ? w[0] : w[1]) : (t < 6 ? w[2] : w[3]);
+                const unsigned v = (t & 1) ? (word >> 16) : (word & 0xffffu);
+                if (v < win) atomicAdd(&sh[base + v], 1u); else atomicAdd(&g[v], 1u);
+            }
+        }
+    };
     // one unit (8-pixel group, or one pixel when the row length is not a multiple of 8)
     auto process = [&](int y, int x0, const unsigned (&w)[4], const unsigned (&w2)[4]) {
         if (moments) {
+            if (step == 8) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j * 2 >= step) break;
-                const unsigned a = w[j] & 0xffffu, b = step == 1 ? 0u : (w[j] >> 16);
-                s1 += a + b;
-                s2 += (unsigned long long)a * a + (unsigned long long)b * b;
-            }
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned a = w[j] & 0xffffu, b = w[j] >> 16;
+                    s1 += a + b;
+                    s2 += (unsigned long long)a * a + (unsigned long long)b * b;
+                }
+            } else { const unsigned a = w[0] & 0xffffu; s1 += a; s2 += (unsigned long long)a * a; }
         }
         unsigned keep = step == 8 ? 0xffu : 1u;
         if (pp.sat_min > 0) {
@@ -715,74 +864,62 @@ ipb_k_hist_planes(const unsigned short* __restrict__ planes, int H, int W,
                 keep |= (v < sat_min && o < sat_min) ? (1u << t) : 0u;
             }
         }
-        unsigned sel_sub = 0;                            // pixels the paired flat-stride job selects
-        if (pair_sub >= 0) {
-#pragma unroll
-            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-                if (u != pair_sub) continue;
-                const unsigned k = (unsigned)kk[u];
-                const unsigned long long flat = (unsigned long long)y * W + x0;
-                const unsigned fm = (k & (k - 1u)) == 0u ? (unsigned)flat & (k - 1u)
-                                    : (flat < 0xffffffffull ? (unsigned)flat % k : (unsigned)(flat % (unsigned long long)k));
-                const unsigned first = fm ? k - fm : 0u;
-                sel_sub = (first < 8u ? (pat16[u] << first) & 0xffu : 0u) & keep;
-                nsel[u] += (unsigned)__popc(sel_sub);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-            if (pat[u] < 0 || u == pair_sub) continue;
-            if (u == pair_full) {                         // every kept pixel once: stride pixels in the stride job's window
-                nsel[u] += (unsigned)__popc(keep);
-                const int bf = wbase[u], bs = wbase[pair_sub >= 0 ? pair_sub : 0];
-                unsigned* gs = gh[pair_sub >= 0 ? pair_sub : 0];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    if (t >= step) break;
-                    if (!((keep >> t) & 1u)) continue;
-                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
-                    const bool sub = (sel_sub >> t) & 1u;
-                    if (v < (unsigned)win) atomicAdd(&sh[(sub ? bs : bf) + v], 1u);
-                    else { atomicAdd(&gh[u][v], 1u); if (sub) atomicAdd(&gs[v], 1u); }
-                }
-                continue;
-            }
-            unsigned sel = 0;
-            const unsigned k = (unsigned)kk[u];
-            if (pat[u] == IPB_PAT_FULL) sel = 0xffu;
-            else if (pat[u] == IPB_PAT_STRIDE1D) {
-                const unsigned long long flat = (unsigned long long)y * W + x0;
-                const unsigned fm = (k & (k - 1u)) == 0u ? (unsigned)flat & (k - 1u)
-                                    : (flat < 0xffffffffull ? (unsigned)flat % k : (unsigned)(flat % (unsigned long long)k));
-                const unsigned first = fm ? k - fm : 0u;
-                sel = first < 8u ? (pat16[u] << first) & 0xffu : 0u;
-            } else if (pat[u] == IPB_PAT_STRIDE2D) {
-                if ((unsigned)y % k == 0u) {
-                    const unsigned xm = (unsigned)x0 % k;
-                    const unsigned first = xm ? k - xm : 0u;
-                    sel = first < 8u ? (pat16[u] << first) & 0xffu : 0u;
-                }
-            } else if (pat[u] == IPB_PAT_MASKED) {
-                sel = (ub[u][(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
-            }
-            sel &= keep;
-            if (!sel) continue;
-            nsel[u] += (unsigned)__popc(sel);
-            const int base = wbase[u];
-            if (sel == 0xffu && base >= 0) {
+        const unsigned selS = jS >= 0 ? stride1d(y, x0, kS, p16S) & keep : 0u;
+        if (pairFS) {                                  // every kept pixel once; S's pixels in S's window
+            nF += (unsigned)__popc(keep); nS += (unsigned)__popc(selS);
+            if (keep == 0xffu) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
-                    if (v < (unsigned)win) atomicAdd(&sh[base + v], 1u); else atomicAdd(&gh[u][v], 1u);
+                    const bool sub = (selS >> t) & 1u;
+                    if (v < win) atomicAdd(&sh[(sub ? bS : bF) + (int)v], 1u);
+                    else { atomicAdd(&gF[v], 1u); if (sub) atomicAdd(&gS[v], 1u); }
                 }
             } else {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    if (t >= step) break;
-                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
-                    if ((sel >> t) & 1u) {
-                        if (base >= 0 && v < (unsigned)win) atomicAdd(&sh[base + v], 1u); else atomicAdd(&gh[u][v], 1u);
-                    }
+                unsigned todo = keep;
+                while (todo) {
+                    const int t = __ffs((int)todo) - 1;
+                    todo &= todo - 1;
+                    const unsigned word = t < 4 ? (t < 2 ? w[0] : w[1]) : (t < 6 ? w[2] : w[3]);
+                    const unsigned v = (t & 1) ? (word >> 16) : (word & 0xffffu);
+                    const bool sub = (selS >> t) & 1u;
+                    if (v < win) atomicAdd(&sh[(sub ? bS : bF) + (int)v], 1u);
+                    else { atomicAdd(&gF[v], 1u); if (sub) atomicAdd(&gS[v], 1u); }
+                }
+            }
+        } else {
+            if (jF >= 0) { nF += (unsigned)__popc(keep); count_dense(keep, bF, gF, w); }
+            if (jS >= 0 && selS) { nS += (unsigned)__popc(selS); count_dense(selS, bS, gS, w); }
+        }
+        if (jM >= 0) {
+            const unsigned sel = ((ubM[(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu) & keep;
+            if (sel) { nM += (unsigned)__popc(sel); count_dense(sel, bM, gM, w); }
+        }
+        if (jP >= 0) {
+            unsigned sel = stride2d(y, x0, kP, p16P, mgP) & keep;
+            nP += (unsigned)__popc(sel);
+            while (sel) {                              // sparse: straight to the global histogram
+                const int t = __ffs((int)sel) - 1;
+                sel &= sel - 1;
+                const unsigned word = t < 4 ? (t < 2 ? w[0] : w[1]) : (t < 6 ? w[2] : w[3]);
+                atomicAdd(&gP[(t & 1) ? (word >> 16) : (word & 0xffffu)], 1u);
+            }
+        }
+        if (jG >= 0) {
+            unsigned sel = 0;
+            if (patG == IPB_PAT_FULL) sel = 0xffu;
+            else if (patG == IPB_PAT_STRIDE1D) sel = stride1d(y, x0, kG, p16G);
+            else if (patG == IPB_PAT_STRIDE2D) sel = stride2d(y, x0, kG, p16G, mgG);
+            else if (patG == IPB_PAT_MASKED) sel = (ubG[(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
+            sel &= keep;
+            if (sel) {
+                nG += (unsigned)__popc(sel);
+                if (bG >= 0) count_dense(sel, bG, gG, w);
+                else while (sel) {
+                    const int t = __ffs((int)sel) - 1;
+                    sel &= sel - 1;
+                    const unsigned word = t < 4 ? (t < 2 ? w[0] : w[1]) : (t < 6 ? w[2] : w[3]);
+                    atomicAdd(&gG[(t & 1) ? (word >> 16) : (word & 0xffffu)], 1u);
                 }
             }
         }
@@ -819,36 +956,45 @@ ipb_k_hist_planes(const unsigned short* __restrict__ planes, int H, int W,
         }
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < n_dense * win; b += blockDim.x) {
+    // flush the windows (S's window also belongs to F when they are paired)
+    for (int b = threadIdx.x; b < n_dense * (int)win; b += blockDim.x) {
         const unsigned c = sh[b];
-        if (c) {
-            const int d = b / win;                       // d-th dense job of the pass
-            int u = 0, seen = -1;
-#pragma unroll
-            for (int q = 0; q < IPB_HSEL_MAXJ; ++q) if (wbase[q] >= 0 && ++seen == d) u = q;
-            atomicAdd(&gh[u][b - d * win], c);
-            if (u == pair_sub) atomicAdd(&gh[pair_full][b - d * win], c);      // subset pixels belong to both
-        }
+        if (!c) continue;
+        const int dd = b / (int)win, v = b - dd * (int)win;
+        const int base = dd * (int)win;
+        if (jF >= 0 && base == bF) atomicAdd(&gF[v], c);
+        else if (jS >= 0 && base == bS) { atomicAdd(&gS[v], c); if (pairFS) atomicAdd(&gF[v], c); }
+        else if (jM >= 0 && base == bM) atomicAdd(&gM[v], c);
+        else atomicAdd(&gG[v], c);
     }
     // per job: selected-pixel count; moments of the plane (all pixels) to every job that asked
-    __shared__ unsigned long long acc[IPB_HSEL_MAXJ + 2];
-    if (threadIdx.x < IPB_HSEL_MAXJ + 2) acc[threadIdx.x] = 0;
+    __shared__ unsigned long long acc[7];
+    if (threadIdx.x < 7) acc[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        const unsigned long long a = ipb_warp_sum((unsigned long long)nsel[u]);
-        if (lane == 0 && a) atomicAdd(&acc[u], a);
-    }
-    s1 = ipb_warp_sum(s1); s2 = ipb_warp_sum(s2);
-    if (lane == 0) { if (s1) atomicAdd(&acc[IPB_HSEL_MAXJ], s1); if (s2) atomicAdd(&acc[IPB_HSEL_MAXJ + 1], s2); }
-    __syncthreads();
-    if (threadIdx.x < pp.n_jobs) {
-        const int u = threadIdx.x, j = pp.job[u];
-        if (acc[u]) atomicAdd(&out_stats[(size_t)j * 4], acc[u]);
-        if (jobs[j].moments) {
-            if (acc[IPB_HSEL_MAXJ]) atomicAdd(&out_stats[(size_t)j * 4 + 1], acc[IPB_HSEL_MAXJ]);
-            if (acc[IPB_HSEL_MAXJ + 1]) atomicAdd(&out_stats[(size_t)j * 4 + 2], acc[IPB_HSEL_MAXJ + 1]);
+    {
+        const unsigned long long a0 = ipb_warp_sum((unsigned long long)nF), a1 = ipb_warp_sum((unsigned long long)nS),
+                                 a2 = ipb_warp_sum((unsigned long long)nM), a3 = ipb_warp_sum((unsigned long long)nP),
+                                 a4 = ipb_warp_sum((unsigned long long)nG);
+        s1 = ipb_warp_sum(s1); s2 = ipb_warp_sum(s2);
+        if (lane == 0) {
+            if (a0) atomicAdd(&acc[0], a0);
+            if (a1) atomicAdd(&acc[1], a1);
+            if (a2) atomicAdd(&acc[2], a2);
+            if (a3) atomicAdd(&acc[3], a3);
+            if (a4) atomicAdd(&acc[4], a4);
+            if (s1) atomicAdd(&acc[5], s1);
+            if (s2) atomicAdd(&acc[6], s2);
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        const int slot = threadIdx.x == 0 ? jF : threadIdx.x == 1 ? jS : threadIdx.x == 2 ? jM : threadIdx.x == 3 ? jP : jG;
+        if (slot >= 0 && acc[threadIdx.x]) atomicAdd(&out_stats[(size_t)pp.job[slot] * 4], acc[threadIdx.x]);
+    }
+    if (threadIdx.x < pp.n_jobs && jobs[pp.job[threadIdx.x]].moments) {
+        const int j = pp.job[threadIdx.x];
+        if (acc[5]) atomicAdd(&out_stats[(size_t)j * 4 + 1], acc[5]);
+        if (acc[6]) atomicAdd(&out_stats[(size_t)j * 4 + 2], acc[6]);
     }
 }

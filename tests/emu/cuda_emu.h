@@ -297,6 +297,7 @@ using std::isfinite;
 using std::isnan;
 using std::max;
 using std::min;
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
 
