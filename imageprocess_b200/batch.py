@@ -214,6 +214,7 @@ class FrameBatchJob:
             T.add("f_org", np.int32, (max(NU, 1), 2))
             T.add("f_moff", np.int64, NU + 1)
             T.add("crops", CROP, max(NR, 1))
+            T.add("crop_order", np.int32, max(NR, 1))
 
         # ---- histogram / quantile job tables
         has_rois = cnt_f > 0
@@ -341,6 +342,14 @@ class FrameBatchJob:
             f32_tmpl.append(s)
         pl.n_u16 = NR * len(u16_tmpl)
         pl.n_f32 = NR * len(f32_tmpl)
+        if NR and need_mpl:
+            # longest jobs first (one CTA per job, scheduled in index order): the last wave of a
+            # launch then holds the small regions.  Every view names its own output row, so the
+            # job order is free.
+            mr = m_rect[uidx]
+            big_first = np.argsort(-((mr[:, 2] - mr[:, 0]).astype(np.int64) * (mr[:, 3] - mr[:, 1])), kind="stable")
+            u16_tmpl = [np.concatenate(u16_tmpl)[np.argsort(np.tile(np.argsort(big_first, kind="stable"), len(u16_tmpl)), kind="stable")]] if u16_tmpl else []
+            f32_tmpl = [t[big_first] for t in f32_tmpl]
         sj = np.concatenate(u16_tmpl + f32_tmpl) if (u16_tmpl or f32_tmpl) and NR else np.zeros(0, dtype=STAT_JOB)
         NS = pl.NS = sj.shape[0]
         pl.n_out = NR * rpr
@@ -394,6 +403,7 @@ class FrameBatchJob:
                 c["w"], c["h"], c["wpr"] = fw, fh, iw
                 c["plane"], c["frame"], c["pad0"] = frame * C + self.fa_ch, frame, 0
             pl.fa_crops = V("crops")[:NR].copy()
+            V("crop_order")[:NR] = np.argsort(-(fw * fh), kind="stable")       # biggest crops start first
             pl.fa_words = max(int(bit_off[-1]), 1)
             pl.total_px, pl.total_rows = int(pix_off[-1]), int(row_off[-1])
             pl.fa_max_h = int(fh.max()) if NR else 0
@@ -534,7 +544,7 @@ class FrameBatchJob:
                      int(cfgf["close_radius"]) if cfgf["close_radius"] > 0 else 0,
                      bwA.ptr, bwB.ptr, d_L.ptr, d_cs.ptr, rootb.ptr, d_rr.ptr, d_rb.ptr, d_cc.ptr,
                      bwF.ptr, op("comp_off"), d_comps.ptr, pl.comp_cap,
-                     d_lab.ptr if d_lab is not None else None, int(self.fa_path), stream)
+                     d_lab.ptr if d_lab is not None else None, int(self.fa_path), tp("crop_order"), stream)
             res.fa_bw = ops_view(bwF, np.uint32, (words,), mem)
             res.fa_labels = ops_view(d_lab, np.int32, (pl.total_px,), mem) if d_lab is not None else None
             fa_ran = True

@@ -359,7 +359,7 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    uint32_t* bw_a, uint32_t* bw_b, int32_t* L, uint32_t* csize, uint32_t* rootbits,
                    int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
                    uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
-                   int32_t* labels, int path, void* stream)
+                   int32_t* labels, int path, const int32_t* crop_order, void* stream)
 {
     if (n_crops <= 0) return IPB_OK;
     IPB_REQUIRE(path >= 0 && path <= 2, "ipb_fa_segment: path %d not in 0..2", path);
@@ -385,7 +385,7 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
     const bool fused = path == 1 || (path == 0 && n_crops >= 64 && max_rows <= 1024);
     if (fused) {
         IPB_LAUNCH(ipb_k_fa_fused, dim3(n_crops), dim3(IPB_FA_FUSED_THREADS), 0, stream, cr, planes, H, W, fa_params,
-                   roi_mask, min_size, disk, bw_a, bw_b, L, csize, rootbits, row_roots, row_base, crop_count, bw_final);
+                   roi_mask, min_size, disk, bw_a, bw_b, L, csize, rootbits, row_roots, row_base, crop_count, bw_final, crop_order);
         if ((rc = ipb_check_launch("ipb_k_fa_fused"))) return rc;
     } else {
         IPB_LAUNCH(ipb_k_fa_threshold, grid, block, 0, stream, cr, planes, H, W, fa_params, roi_mask, bw_a);

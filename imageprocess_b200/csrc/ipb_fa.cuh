@@ -420,9 +420,11 @@ __global__ void __launch_bounds__(IPB_FA_FUSED_THREADS)
 ipb_k_fa_fused(const IpbCrop* __restrict__ crops, const unsigned short* __restrict__ planes, int H, int W,
                const float* __restrict__ fa_params, const unsigned* __restrict__ roi_mask,
                double min_size, IpbDisk disk, unsigned* bw_a, unsigned* bw_b, int* L, unsigned* csize,
-               unsigned* rootbits, int* row_roots, int* row_base, int* crop_count, unsigned* bw_final)
+               unsigned* rootbits, int* row_roots, int* row_base, int* crop_count, unsigned* bw_final,
+               const int* __restrict__ order /* nullable: CTA b runs crop order[b] (biggest first) */)
 {
-    const IpbCrop c = crops[blockIdx.x];
+    const int ci = order ? order[blockIdx.x] : (int)blockIdx.x;
+    const IpbCrop c = crops[ci];
     const int fa_y0 = 0, fa_nrow = c.h;
     __shared__ int wsum[IPB_FA_FUSED_THREADS / 32];
     __shared__ int carry;
@@ -476,7 +478,7 @@ ipb_k_fa_fused(const IpbCrop* __restrict__ crops, const unsigned short* __restri
         __syncthreads();
     }
     (void)nw;
-    if (threadIdx.x == 0) crop_count[blockIdx.x] = carry;
+    if (threadIdx.x == 0) crop_count[ci] = carry;
 }
 
 // comp_off = exclusive scan of crop_count (single CTA), comp_off[n] = total

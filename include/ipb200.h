@@ -239,7 +239,7 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
                    uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
                    int32_t* labels, int path /* 0 auto, 1 one CTA per crop, 2 one kernel per phase */,
-                   void* stream);
+                   const int32_t* crop_order /* [dev] optional: crops by decreasing size */, void* stream);
 
 /* ------------------------------------------------------------------ morphology, moments, previews
  * ipb_region_dilate: dilation of region masks (ipb_region layout, all pools share mask_off)
