@@ -368,11 +368,13 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         ipb_rs_walk<SRC, false>(c, wsh, [&](unsigned raw, unsigned) { atomicAdd(&h16[raw >> 1], 1u << ((raw & 1u) << 4)); });
         n = area;
         setup_ranks(n);
-        // pass A: key range and per-view sums
+        // one pass over the bins: key range, per-view sum and sum of squares (the squared
+        // deviations follow as sumsq - sum^2 / n in float64: the terms are counts times values
+        // with at most 17 significant bits, far inside float64's exact-integer range)
         unsigned lo_t = 0xffffffffu, hi_t = 0u;
-        double s[IPB_RS_MAXV];
+        double s[IPB_RS_MAXV], q[IPB_RS_MAXV];
 #pragma unroll
-        for (int v = 0; v < IPB_RS_MAXV; ++v) s[v] = 0.0;
+        for (int v = 0; v < IPB_RS_MAXV; ++v) { s[v] = 0.0; q[v] = 0.0; }
         for (unsigned i = tid; i < 32768u; i += blockDim.x) {
             const unsigned w = h16[i];
             if (!w) continue;
@@ -382,28 +384,20 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
             hi_t = last > hi_t ? last : hi_t;
 #pragma unroll
             for (int v = 0; v < IPB_RS_MAXV; ++v)
-                if (v < nv) s[v] += (double)lo * (double)ipb_rs_transform(vB[v], vclip[v], k0) +
-                                    (double)hi * (double)ipb_rs_transform(vB[v], vclip[v], k0 + 1u);
-        }
-        block_minmax(lo_t, hi_t);
-        for (int v = 0; v < nv; ++v) v_sum[v] = ipb_block_sum_d(s[v], red_d);
-        // pass B: squared deviations from the exact mean
-        double q[IPB_RS_MAXV], mean[IPB_RS_MAXV];
-#pragma unroll
-        for (int v = 0; v < IPB_RS_MAXV; ++v) { q[v] = 0.0; mean[v] = v_sum[v] / (double)n; }
-        for (unsigned i = tid; i < 32768u; i += blockDim.x) {
-            const unsigned w = h16[i];
-            if (!w) continue;
-            const unsigned lo = w & 0xffffu, hi = w >> 16, k0 = 2u * i;
-#pragma unroll
-            for (int v = 0; v < IPB_RS_MAXV; ++v)
                 if (v < nv) {
-                    const double d0 = (double)ipb_rs_transform(vB[v], vclip[v], k0) - mean[v];
-                    const double d1 = (double)ipb_rs_transform(vB[v], vclip[v], k0 + 1u) - mean[v];
-                    q[v] += (double)lo * d0 * d0 + (double)hi * d1 * d1;
+                    const double t0 = (double)ipb_rs_transform(vB[v], vclip[v], k0);
+                    const double t1 = (double)ipb_rs_transform(vB[v], vclip[v], k0 + 1u);
+                    const double c0 = (double)lo * t0, c1 = (double)hi * t1;
+                    s[v] += c0 + c1;
+                    q[v] += c0 * t0 + c1 * t1;
                 }
         }
-        for (int v = 0; v < nv; ++v) v_ssd[v] = ipb_block_sum_d(q[v], red_d);
+        block_minmax(lo_t, hi_t);
+        for (int v = 0; v < nv; ++v) {
+            v_sum[v] = ipb_block_sum_d(s[v], red_d);
+            const double sumsq = ipb_block_sum_d(q[v], red_d);
+            v_ssd[v] = (kmin == kmax) ? 0.0 : sumsq - v_sum[v] * (v_sum[v] / (double)n);   // constant region: exactly 0
+        }
         // ranks: the word first, then the low / high counter inside the word
         unsigned long long want[IPB_RS_MAXR];
         for (int r = 0; r < IPB_RS_MAXR; ++r) want[r] = sel.rank[r];
