@@ -459,8 +459,24 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         const int rb = bits - d1;                                               // bits left after pass 1
         const unsigned nb = 1u << d1;
         for (unsigned i = tid; i < nb; i += blockDim.x) whist[i] = 0u;
+        // float32: the sum is known from the walk, so the squared deviations from the exact mean
+        // ride along with the histogram pass over the stored keys
+        double f_sum = 0.0, f_q = 0.0;
+        if (SRC != IPB_SRC_U16) f_sum = ipb_block_sum_d(s_t, red_d);
+        const double f_mean = f_sum / (double)n;
         __syncthreads();
-        ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) { atomicAdd(&whist[(key - kmin) >> rb], 1u); });
+        if (SRC != IPB_SRC_U16 && in_smem) {
+            for (unsigned i = tid; i < n_slots; i += blockDim.x) {
+                const unsigned k = k32[i];
+                if (k != IPB_RS_SENTINEL) {
+                    atomicAdd(&whist[(k - kmin) >> rb], 1u);
+                    const double d = (double)ipb_key_f32(k) - f_mean;
+                    f_q += d * d;
+                }
+            }
+        } else {
+            ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) { atomicAdd(&whist[(key - kmin) >> rb], 1u); });
+        }
         __syncthreads();
         {
             unsigned long long want[IPB_RS_MAXR];
@@ -487,16 +503,10 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
                 v_ssd[v] = ipb_block_sum_d(q, red_d);
             }
         } else {
-            const double sum = ipb_block_sum_d(s_t, red_d);
+            const double sum = f_sum;
             double ssd;
             if (in_smem) {
-                const double mean = sum / (double)n;
-                double q = 0.0;
-                for (unsigned i = tid; i < n_slots; i += blockDim.x) {
-                    const unsigned k = k32[i];
-                    if (k != IPB_RS_SENTINEL) { const double d = (double)ipb_key_f32(k) - mean; q += d * d; }
-                }
-                ssd = ipb_block_sum_d(q, red_d);
+                ssd = ipb_block_sum_d(f_q, red_d);
             } else {
                 const double sumsq = ipb_block_sum_d(s2_t, red_d);
                 ssd = sumsq - sum * (sum / (double)n);
