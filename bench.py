@@ -279,10 +279,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches0 = eng.launches
     with ClockSampler(local if rank == 0 else None) as clk:      # one sampler per job, on rank 0's GPU
-        eng.profile_start()
         ms, d2h = timed(loop_resident, args.steps)
+        launches = eng.launches - launches0
+        # per-kernel CUDA-event times: the same steps once more with the branches of a step
+        # serialised on one stream (overlapped kernels cannot be timed one by one)
+        job.overlap = False
+        loop_resident(1)
+        eng.profile_start()
+        ms_ser, _ = timed(loop_resident, args.steps)
         prof = eng.profile_stop()
-    launches = eng.launches - launches0
+        job.overlap = True
     loop_e2e(min(args.warmup, 2))
     ms_e2e, _ = timed(loop_e2e, args.steps)
 
@@ -308,7 +314,7 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
         dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
-        kern = {k: {"calls": v[0], "ms": round(v[1], 4), "share": round(v[1] / max(ms, 1e-9), 4)}
+        kern = {k: {"calls": v[0], "ms": round(v[1], 4), "share": round(v[1] / max(ms_ser, 1e-9), 4)}
                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
         if dom is not None:
             # the entry point with the largest share of the step; bytes and time are both taken
@@ -330,6 +336,7 @@ def run_ours(args):
                                      "achieved_gbs": value / world * 1e6 * BYTES_PER_PX / 1e9,
                                      "frac_of_peak": value / world * 1e6 * BYTES_PER_PX / 1e9 / peak}
         line["kernels"] = kern
+        line["ms_per_step_serialized"] = ms_ser / args.steps
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()

@@ -100,6 +100,7 @@ class FrameBatchJob:
         self.dist = None            # torch.distributed module when the job is one rank of N (see parallel.py)
         self.gather_dst = 0
         self._gather_cap = None     # bytes every rank contributes to the per-step all-gather
+        self.overlap = bool(int(os.environ.get("IPB_OVERLAP", "1")))   # branches of a step on side streams
         self.fa_path = 0            # ipb_fa_segment path: 0 auto, 1 one CTA per crop, 2 one kernel per phase
         # percentiles by sampling (ipb_hist_select) instead of full histograms: exact either way;
         # off by default until its tail pass beats the full-histogram kernel
@@ -443,8 +444,11 @@ class FrameBatchJob:
         P_FRET, P_INT, P_FA, Ci, NP = pl.P_FRET, pl.P_INT, pl.P_FA, pl.Ci, pl.NP
         res = BatchResult()
         res.frame, res.roi, res.n_rois = pl.frame, pl.roi, NR
-        stream = mem.stream
         lib_call = eng.call
+        # independent branches of the step (FA chain, uint16 region statistics, FRET pass + ratio
+        # statistics) go to side streams and meet again before the result download
+        import contextlib
+        branch = mem.branch if self.overlap else (lambda i: contextlib.nullcontext())
 
         d_tab = self._dev("d_tables", T.size)
         mem.upload_async(d_tab, pl.pin_t, T.size)
@@ -459,15 +463,16 @@ class FrameBatchJob:
             mem.zero_bytes(d_union, 4 * pl.S * H * self.union_wpr)
             lib_call("ipb_rasterize_rois", geo.RULE_MPL, NU, tp("m_verts"), tp("vert_off"), tp("m_rect"),
                      tp("m_rect"), tp("m_org"), tp("uset"), tp("m_moff"), pl.m_max_rows, pl.m_max_wpr,
-                     m_pool.ptr, op("m_area"), d_union.ptr, self.union_wpr, H, stream)
+                     m_pool.ptr, op("m_area"), d_union.ptr, self.union_wpr, H, mem.stream)
             union_ptr = d_union.ptr
         else:
             union_ptr = None
         if "fa" in st:
             f_pool = self._dev("f_pool", 4 * pl.f_words)
-            lib_call("ipb_rasterize_rois", geo.RULE_SK, NU, tp("f_verts"), tp("vert_off"), tp("f_erect"),
-                     tp("f_srect"), tp("f_org"), tp("uset"), tp("f_moff"), pl.f_max_rows, pl.f_max_wpr,
-                     f_pool.ptr, op("f_area"), None, self.union_wpr, H, stream)
+            with branch(2):
+                lib_call("ipb_rasterize_rois", geo.RULE_SK, NU, tp("f_verts"), tp("vert_off"), tp("f_erect"),
+                         tp("f_srect"), tp("f_org"), tp("uset"), tp("f_moff"), pl.f_max_rows, pl.f_max_wpr,
+                         f_pool.ptr, op("f_area"), None, self.union_wpr, H, mem.stream)
 
         # ---- histograms -> percentiles -> per-frame scalars
         d_hist = self._dev("hist", 4 * 65536 * max(NH, 1))
@@ -489,42 +494,22 @@ class FrameBatchJob:
             lib_call("ipb_hist_select", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, tp("qjobs"), NQ,
                      int(pl.has_ms), union_ptr, self.union_wpr, d_scr.ptr if d_scr is not None else None,
                      d_hs.ptr, d_hist.ptr, d_hw.ptr, d_win.ptr, d_cnt.ptr, d_hss.ptr, d_hstat.ptr, d_list.ptr, list_cap,
-                     d_listn.ptr, d_qout.ptr, op("miss"), stream)
-            lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), stream)
+                     d_listn.ptr, d_qout.ptr, op("miss"), mem.stream)
+            lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), mem.stream)
         elif NH:
             lib_call("ipb_hist_planes", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, int(pl.has_ms),
-                     union_ptr, self.union_wpr, d_scr.ptr if d_scr is not None else None, d_hist.ptr, d_hstat.ptr, stream)
-            lib_call("ipb_hist_quantiles", d_hist.ptr, d_hstat.ptr, tp("qjobs"), NQ, d_qout.ptr, stream)
-            lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), stream)
+                     union_ptr, self.union_wpr, d_scr.ptr if d_scr is not None else None, d_hist.ptr, d_hstat.ptr, mem.stream)
+            lib_call("ipb_hist_quantiles", d_hist.ptr, d_hstat.ptr, tp("qjobs"), NQ, d_qout.ptr, mem.stream)
+            lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), mem.stream)
         if pl.host_bg:
             self._host_hist_mode(pl.host_bg, d_hist, pl.hidx, d_out, O, NH, P_FRET, P_INT, Ci)
         if "fret" in st:
             den_slot = FP_BD if pl.numer_is_acc else FP_BA
             lib_call("ipb_fret_eps", d_qout.ptr + Q_OUT.itemsize * pl.qidx["fret_eps"], F, den_slot,
-                     int(bool(self.fret_p["clip_neg"])), 5.0, op("params") + 4 * P_FRET, stream)
+                     int(bool(self.fret_p["clip_neg"])), 5.0, op("params") + 4 * P_FRET, mem.stream)
         if "fa" in st:
             lib_call("ipb_fa_params", d_hstat.ptr, tp("fa_stat_idx"), d_qout.ptr + Q_OUT.itemsize * pl.qidx["fa"],
-                     F, H * W, float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, stream)
-
-        # ---- fused FRET pass
-        d_R = None
-        if "fret" in st:
-            d_R = self._dev("R", 4 * F * H * W)
-            d_Rroi = self._dev("Rroi", 4 * F * H * W) if self.want_roi_image else None
-            cfg = fret_cfg(self.fret_p, C, self.donor_ch, self.acc_ch)
-            lib_call("ipb_fret_pixels", planes.ptr, F, H, W, cfg.ctypes.data, op("params") + 4 * P_FRET,
-                     union_ptr, self.union_wpr, tp("union_idx"), d_R.ptr, None,
-                     d_Rroi.ptr if d_Rroi is not None else None, None, None, stream)
-            res.R = ops_view(d_R, np.float32, (F, H, W), mem)
-            res.R_roi = ops_view(d_Rroi, np.float32, (F, H, W), mem) if d_Rroi is not None else None
-
-        # ---- per-ROI statistics: the float (ratio) jobs first, they are the long ones
-        if pl.n_f32:
-            lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs") + STAT_JOB.itemsize * pl.n_u16, pl.n_f32,
-                     SRC_F32, m_pool.ptr, None, 0, H, W, planes.ptr, d_R.ptr, op("params"), op("stat_out"), stream)
-        if pl.n_u16:
-            lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, None, 0,
-                     H, W, planes.ptr, None, op("params"), op("stat_out"), stream)
+                     F, H * W, float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, mem.stream)
 
         # ---- focal adhesions
         if "fa" in st and NR and pl.total_px > 0:
@@ -538,13 +523,14 @@ class FrameBatchJob:
             d_comps = self._dev("comps", COMP.itemsize * pl.comp_cap)
             d_lab = self._dev("labels", 4 * pl.total_px) if self.want_labels else None
             cfgf = self.fa_cfg
-            lib_call("ipb_fa_segment", tp("crops"), NR, pl.fa_max_h, pl.total_rows, planes.ptr, H, W,
-                     op("params") + 4 * P_FA, f_pool.ptr,
-                     float(cfgf["min_px"]) if cfgf["min_px"] > 0 else 0.0,
-                     int(cfgf["close_radius"]) if cfgf["close_radius"] > 0 else 0,
-                     bwA.ptr, bwB.ptr, d_L.ptr, d_cs.ptr, rootb.ptr, d_rr.ptr, d_rb.ptr, d_cc.ptr,
-                     bwF.ptr, op("comp_off"), d_comps.ptr, pl.comp_cap,
-                     d_lab.ptr if d_lab is not None else None, int(self.fa_path), tp("crop_order"), stream)
+            with branch(2):
+                lib_call("ipb_fa_segment", tp("crops"), NR, pl.fa_max_h, pl.total_rows, planes.ptr, H, W,
+                         op("params") + 4 * P_FA, f_pool.ptr,
+                         float(cfgf["min_px"]) if cfgf["min_px"] > 0 else 0.0,
+                         int(cfgf["close_radius"]) if cfgf["close_radius"] > 0 else 0,
+                         bwA.ptr, bwB.ptr, d_L.ptr, d_cs.ptr, rootb.ptr, d_rr.ptr, d_rb.ptr, d_cc.ptr,
+                         bwF.ptr, op("comp_off"), d_comps.ptr, pl.comp_cap,
+                         d_lab.ptr if d_lab is not None else None, int(self.fa_path), tp("crop_order"), mem.stream)
             res.fa_bw = ops_view(bwF, np.uint32, (words,), mem)
             res.fa_labels = ops_view(d_lab, np.int32, (pl.total_px,), mem) if d_lab is not None else None
             fa_ran = True
@@ -552,6 +538,29 @@ class FrameBatchJob:
             fa_ran = False
             if "fa" in st:
                 mem.zero_bytes(d_out, O.sections["comp_off"][3], O.sections["comp_off"][0])
+        # ---- uint16 per-ROI statistics (side stream)
+        with branch(1):
+            if pl.n_u16:
+                lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, None, 0,
+                         H, W, planes.ptr, None, op("params"), op("stat_out"), mem.stream)
+
+        # ---- fused FRET pass
+        d_R = None
+        if "fret" in st:
+            d_R = self._dev("R", 4 * F * H * W)
+            d_Rroi = self._dev("Rroi", 4 * F * H * W) if self.want_roi_image else None
+            cfg = fret_cfg(self.fret_p, C, self.donor_ch, self.acc_ch)
+            lib_call("ipb_fret_pixels", planes.ptr, F, H, W, cfg.ctypes.data, op("params") + 4 * P_FRET,
+                     union_ptr, self.union_wpr, tp("union_idx"), d_R.ptr, None,
+                     d_Rroi.ptr if d_Rroi is not None else None, None, None, mem.stream)
+            res.R = ops_view(d_R, np.float32, (F, H, W), mem)
+            res.R_roi = ops_view(d_Rroi, np.float32, (F, H, W), mem) if d_Rroi is not None else None
+
+        # ---- per-ROI statistics: the float (ratio) jobs first, they are the long ones
+        if pl.n_f32:
+            lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs") + STAT_JOB.itemsize * pl.n_u16, pl.n_f32,
+                     SRC_F32, m_pool.ptr, None, 0, H, W, planes.ptr, d_R.ptr, op("params"), op("stat_out"), mem.stream)
+        mem.join()
         if "fa" in st:
             res.fa_rect, res.fa_crops = pl.fa_rect, pl.fa_crops
 

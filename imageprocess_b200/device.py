@@ -27,6 +27,31 @@ class DevBuf:
         return self
 
 
+class _Branch:
+    def __init__(self, mem, idx):
+        self.mem, self.idx = mem, idx
+
+    def __enter__(self):
+        mem, torch = self.mem, self.mem.torch
+        side = mem.__dict__.setdefault("_side", {})
+        if self.idx not in side:
+            side[self.idx] = torch.cuda.Stream(device=mem.device)
+        s = side[self.idx]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(mem.device))
+        s.wait_event(ev)
+        self.ctx = torch.cuda.stream(s)
+        self.ctx.__enter__()
+        self.s = s
+        return self
+
+    def __exit__(self, *a):
+        ev = self.mem.torch.cuda.Event()
+        ev.record(self.s)
+        self.mem.__dict__.setdefault("_pending", []).append(ev)
+        return self.ctx.__exit__(*a)
+
+
 class TorchMem:
     """CUDA memory through torch (caching allocator, current stream)."""
 
@@ -105,6 +130,19 @@ class TorchMem:
 
     def sync(self):
         self.torch.cuda.current_stream(self.device).synchronize()
+
+    # -- side streams: independent branches of one step run concurrently (fork / join by events)
+    def branch(self, idx):
+        """Context manager: work enqueued inside goes to side stream `idx`, ordered after
+        everything enqueued on the current stream so far.  join() makes the current stream
+        wait for every branch opened since the last join()."""
+        return _Branch(self, idx)
+
+    def join(self):
+        cur = self.torch.cuda.current_stream(self.device)
+        for ev in getattr(self, "_pending", []):
+            cur.wait_event(ev)
+        self._pending = []
 
     def all_reduce_max(self, value, dist):
         """max over ranks of a Python int (one small collective + host read; used once per job)."""

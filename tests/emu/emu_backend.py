@@ -70,6 +70,13 @@ class NumpyMem:
     def sync(self):
         pass
 
+    def branch(self, idx):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def join(self):
+        pass
+
     def all_reduce_max(self, value, dist):
         import torch
         t = torch.tensor([int(value)], dtype=torch.int64)
