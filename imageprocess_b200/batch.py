@@ -102,9 +102,10 @@ class FrameBatchJob:
         self._gather_cap = None     # bytes every rank contributes to the per-step all-gather
         self.overlap = bool(int(os.environ.get("IPB_OVERLAP", "1")))   # branches of a step on side streams
         self.fa_path = 0            # ipb_fa_segment path: 0 auto, 1 one CTA per crop, 2 one kernel per phase
-        # percentiles by sampling (ipb_hist_select) instead of full histograms: exact either way;
-        # off by default until its tail pass beats the full-histogram kernel
-        self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "0"))) if hist_select is None else bool(hist_select)
+        # percentiles by sampled windows (ipb_hist_select) instead of full histograms wherever the
+        # plane passes allow it (ops.pq_servable): exact either way
+        self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "1"))) if hist_select is None else bool(hist_select)
+        self.pq_min_px = 1 << 18     # smaller planes take the full histograms (the sample would be most of the plane)
         self._pin = None
         self.n_roi_px = 0
         self.union_wpr = (self.W + 31) // 32
@@ -255,6 +256,7 @@ class FrameBatchJob:
         hist_jobs = np.concatenate(hist_jobs) if hist_jobs else np.zeros(0, dtype=HIST_JOB)
         NH = pl.NH = hist_jobs.shape[0]
         pl.has_ms = bool((hist_jobs["pattern"] == PAT_MASKED_STRIDE).any())
+        pl.pq_ok = False             # set once the plane passes are known
 
         # params layout (float32): [fret F*4 | int F*Ci | fa F*4]
         Ci = pl.Ci = len(self.int_ch)
@@ -357,6 +359,8 @@ class FrameBatchJob:
 
         passes = ops.plane_passes(hist_jobs)
         pl.n_passes = passes.shape[0]
+        pl.pq_ok = bool(pl.n_passes) and self.W % 8 == 0 and self.H * self.W >= self.pq_min_px and \
+            ops.pq_servable(hist_jobs, passes)
         T.add("hist_jobs", HIST_JOB, max(NH, 1))
         T.add("passes", ops.PLANE_PASS, max(pl.n_passes, 1))
         T.add("qjobs", Q_JOB, max(NQ, 1))
@@ -481,20 +485,14 @@ class FrameBatchJob:
         d_qout = self._dev("qout", Q_OUT.itemsize * max(NQ, 1))
         mem.zero_bytes(d_out, O.sections["params"][3], O.sections["params"][0])
         mem.zero_bytes(d_out, O.sections["miss"][3], O.sections["miss"][0])
-        use_select = NH and self.hist_select and not full_hist and not pl.host_bg
+        use_select = NH and self.hist_select and not full_hist and not pl.host_bg and pl.pq_ok
         if use_select:
-            d_hs = self._dev("hist_sample", 4 * 65536 * NH)
-            d_hw = self._dev("hist_win", 4 * 4096 * NH)
+            # percentiles by sampled windows (exact; a window miss repeats the step with full histograms)
+            d_hw = self._dev("hist_win", 4 * ops.PQ_WIN * NH)
             d_win = self._dev("hist_winrange", ops.HIST_WIN.itemsize * NH)
-            d_cnt = self._dev("hist_cnt", 8 * 4 * NH)
-            d_hss = self._dev("hstat_sample", 8 * 4 * NH)
-            list_cap = max(4096, (H * W) // 4)                 # low pixels per plane pass (windowed mode: <= ~12 %)
-            d_list = self._dev("hist_list", 4 * list_cap * max(pl.n_passes, 1))
-            d_listn = self._dev("hist_list_n", 4 * max(pl.n_passes, 1))
+            d_cnt = self._dev("hist_cnt", 8 * NH)
             lib_call("ipb_hist_select", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, tp("qjobs"), NQ,
-                     int(pl.has_ms), union_ptr, self.union_wpr, d_scr.ptr if d_scr is not None else None,
-                     d_hs.ptr, d_hist.ptr, d_hw.ptr, d_win.ptr, d_cnt.ptr, d_hss.ptr, d_hstat.ptr, d_list.ptr, list_cap,
-                     d_listn.ptr, d_qout.ptr, op("miss"), mem.stream)
+                     d_hist.ptr, d_hw.ptr, d_win.ptr, d_cnt.ptr, d_hstat.ptr, d_qout.ptr, op("miss"), mem.stream)
             lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), mem.stream)
         elif NH:
             lib_call("ipb_hist_planes", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, int(pl.has_ms),

@@ -107,7 +107,7 @@ int ipb_rasterize_rois(int rule, int n_rois, const double* verts_xy, const int32
 // ---------------------------------------------------------------- histograms / quantiles
 static int ipb_launch_hist_full(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
                                 const uint32_t* union_bits, int union_wpr, uint32_t* hist, uint64_t* stats,
-                                int sample, const IpbHistWin* only_full, void* stream);
+                                void* stream);
 
 int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
                  int has_masked_stride, const uint32_t* union_bits, int union_wpr,
@@ -120,7 +120,7 @@ int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs, int n_j
     cudaStream_t st = (cudaStream_t)stream;
     IPB_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)IPB_HIST_BINS * n_jobs, st), "memset hist");
     IPB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(uint64_t) * 4 * (size_t)n_jobs, st), "memset stats");
-    int rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist, stats, 0, nullptr, stream);
+    int rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist, stats, stream);
     if (rc) return rc;
     if (has_masked_stride) {
         IPB_LAUNCH(ipb_k_hist_masked_stride, dim3(n_jobs), dim3(256), 0, stream, planes, H, W,
@@ -131,11 +131,10 @@ int ipb_hist_u16(const uint16_t* planes, int H, int W, const void* jobs, int n_j
     return rc;
 }
 
-// one launch of the full-range histogram kernel over all jobs (sampled, or restricted to the
-// jobs the selection path marked FULL)
+// one launch of the full-range histogram kernel over all jobs
 static int ipb_launch_hist_full(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
                                 const uint32_t* union_bits, int union_wpr, uint32_t* hist, uint64_t* stats,
-                                int sample, const IpbHistWin* only_full, void* stream)
+                                void* stream)
 {
     int chunks = (296 * 6 + n_jobs - 1) / n_jobs;       // ~6 waves of the 296 resident CTAs
     int max_chunks = H / 16 > 0 ? H / 16 : 1;
@@ -147,72 +146,48 @@ static int ipb_launch_hist_full(const uint16_t* planes, int H, int W, const void
     IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist smem");
     IPB_LAUNCH(ipb_k_hist_u16, dim3(chunks, n_jobs), dim3(IPB_HIST_THREADS), smem, stream,
                planes, H, W, (const IpbHistJob*)jobs, rows_per_chunk, union_bits, union_wpr,
-               hist, (unsigned long long*)stats, sample, only_full);
+               hist, (unsigned long long*)stats);
     return ipb_check_launch("ipb_k_hist_u16");
 }
 
 int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
-                    const void* passes, int n_passes, const void* qjobs, int n_q, int has_masked_stride,
-                    const uint32_t* union_bits, int union_wpr, uint64_t* row_rank_scratch,
-                    uint32_t* hist_sample, uint32_t* hist_full, uint32_t* hist_win, void* win,
-                    uint64_t* cnt, uint64_t* stats_sample, uint64_t* stats, uint32_t* list, int64_t list_cap,
-                    uint32_t* list_n, void* qout, uint32_t* miss, void* stream)
+                    const void* passes, int n_passes, const void* qjobs, int n_q,
+                    uint32_t* hist_full, uint32_t* hist_win, void* win, uint64_t* cnt, uint64_t* stats,
+                    void* qout, uint32_t* miss, void* stream)
 {
     IPB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535 && n_passes >= 0 && n_passes <= 65535, "ipb_hist_select: job count out of range");
-    if (n_jobs == 0) return IPB_OK;
-    IPB_REQUIRE(planes && jobs && passes && hist_sample && hist_full && hist_win && win && cnt && stats_sample &&
-                stats && list && list_n && miss && H > 0 && W > 0, "ipb_hist_select: bad argument");
-    IPB_REQUIRE(list_cap > 0 && list_cap < 0x7fffffffLL, "ipb_hist_select: bad list capacity");
+    if (n_jobs == 0 || n_passes == 0) return IPB_OK;
+    IPB_REQUIRE(planes && jobs && passes && hist_full && hist_win && win && cnt && stats && miss && H > 0 && W > 0,
+                "ipb_hist_select: bad argument");
     IPB_REQUIRE(n_q == 0 || (qjobs && qout), "ipb_hist_select: quantile jobs without buffers");
-    IPB_REQUIRE(!has_masked_stride || (union_bits && row_rank_scratch), "ipb_hist_select: masked stride needs union + scratch");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t nj = (size_t)n_jobs;
-    IPB_CUDA_TRY(cudaMemsetAsync(hist_sample, 0, sizeof(uint32_t) * IPB_HIST_BINS * nj, st), "memset sample hist");
-    IPB_CUDA_TRY(cudaMemsetAsync(hist_full, 0, sizeof(uint32_t) * IPB_HIST_BINS * nj, st), "memset full hist");
-    IPB_CUDA_TRY(cudaMemsetAsync(hist_win, 0, sizeof(uint32_t) * IPB_HSEL_WIN * nj, st), "memset window hist");
-    IPB_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(uint64_t) * 4 * nj, st), "memset cnt");
-    IPB_CUDA_TRY(cudaMemsetAsync(stats_sample, 0, sizeof(uint64_t) * 4 * nj, st), "memset stats_sample");
-    IPB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(uint64_t) * 4 * nj, st), "memset stats");
-    IPB_CUDA_TRY(cudaMemsetAsync(list_n, 0, sizeof(uint32_t) * (size_t)(n_passes > 0 ? n_passes : 1), st), "memset list_n");
-    int rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist_sample, stats_sample, 1, nullptr, stream);
-    if (rc) return rc;
-    IPB_LAUNCH(ipb_k_hist_windows, dim3(n_jobs), dim3(256), 0, stream, hist_sample, (const unsigned long long*)stats_sample,
-               (const IpbHistJob*)jobs, (const IpbQJob*)qjobs, n_q, (IpbHistWin*)win);
-    if ((rc = ipb_check_launch("ipb_k_hist_windows"))) return rc;
-    if (n_passes > 0) {
-        int chunks = (148 * 4 * 4 + n_passes - 1) / n_passes;
-        int max_chunks = H / 8 > 0 ? H / 8 : 1;
-        if (chunks > max_chunks) chunks = max_chunks;
-        if (chunks < 1) chunks = 1;
-        const int rows_per_chunk = (H + chunks - 1) / chunks;
-        chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
-        IPB_LAUNCH(ipb_k_hist_tail, dim3(chunks, n_passes), dim3(IPB_HSEL_THREADS), 0, stream, planes, H, W,
-                   (const IpbPlanePass*)passes, (const IpbHistJob*)jobs, (const IpbHistWin*)win, rows_per_chunk,
-                   union_bits, union_wpr, hist_full, list, (unsigned)list_cap, list_n, (unsigned long long*)stats, miss);
-        if ((rc = ipb_check_launch("ipb_k_hist_tail"))) return rc;
-        const size_t smem = sizeof(unsigned) * IPB_HSEL_WIN * IPB_HSEL_MAXJ;
-        IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_hist_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "hist classify smem");
-        int cchunks = (148 * 3 + n_passes - 1) / n_passes;
-        if (cchunks < 1) cchunks = 1;
-        IPB_LAUNCH(ipb_k_hist_classify, dim3(cchunks, n_passes), dim3(256), smem, stream, (const IpbPlanePass*)passes,
-                   (const IpbHistWin*)win, list, (unsigned)list_cap, list_n, hist_win, (unsigned long long*)cnt, miss);
-        if ((rc = ipb_check_launch("ipb_k_hist_classify"))) return rc;
-    }
-    rc = ipb_launch_hist_full(planes, H, W, jobs, n_jobs, union_bits, union_wpr, hist_full, stats, 0, (const IpbHistWin*)win, stream);
-    if (rc) return rc;
-    if (has_masked_stride) {
-        IPB_LAUNCH(ipb_k_hist_masked_stride, dim3(n_jobs), dim3(256), 0, stream, planes, H, W,
-                   (const IpbHistJob*)jobs, union_bits, union_wpr, (unsigned long long*)row_rank_scratch,
-                   hist_full, (unsigned long long*)stats);
-        if ((rc = ipb_check_launch("ipb_k_hist_masked_stride"))) return rc;
-    }
+    IPB_REQUIRE((W & 7) == 0 && (((size_t)planes) & 15) == 0, "ipb_hist_select: needs W %% 8 == 0 and 16-byte aligned planes");
+    int rc;
+    const size_t smem = sizeof(unsigned) * IPB_PQ_SBINS;
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_pq_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pq sample smem");
+    IPB_LAUNCH(ipb_k_pq_sample, dim3(n_passes), dim3(1024), smem, stream, planes, H, W, (const IpbPlanePass*)passes,
+               (const IpbHistJob*)jobs, (const IpbQJob*)qjobs, n_q, hist_full, hist_win, (IpbHistWin*)win,
+               (unsigned long long*)cnt, (unsigned long long*)stats);
+    if ((rc = ipb_check_launch("ipb_k_pq_sample"))) return rc;
+    // 4 CTAs of 256 threads per SM = 592 resident CTAs; ~4 waves, at least 4 trips of 4 units per thread
+    const unsigned long long U = ((unsigned long long)H * (unsigned long long)W) >> 3;
+    unsigned long long chunks = (592ull * 4 + n_passes - 1) / n_passes;
+    const unsigned long long min_units = 16ull * IPB_PQ_THREADS;
+    if (chunks * min_units > U) chunks = U / min_units;
+    if (chunks < 1) chunks = 1;
+    const unsigned long long upc = (U + chunks - 1) / chunks;
+    IPB_REQUIRE(upc < 0xffffffffull, "ipb_hist_select: plane too large");
+    chunks = (U + upc - 1) / upc;
+    IPB_LAUNCH(ipb_k_pq_count, dim3((unsigned)chunks, n_passes), dim3(IPB_PQ_THREADS), 0, stream, planes, H, W,
+               (const IpbPlanePass*)passes, (const IpbHistJob*)jobs, (const IpbHistWin*)win, (unsigned)upc,
+               hist_full, hist_win, (unsigned long long*)cnt, (unsigned long long*)stats);
+    if ((rc = ipb_check_launch("ipb_k_pq_count"))) return rc;
     if (n_q > 0) {
-        IPB_LAUNCH(ipb_k_hist_select_q, dim3(n_q), dim3(256), 0, stream, (const IpbQJob*)qjobs, (const IpbHistWin*)win,
+        IPB_LAUNCH(ipb_k_pq_select, dim3(n_q), dim3(256), 0, stream, (const IpbQJob*)qjobs, (const IpbHistWin*)win,
                    (const unsigned long long*)cnt, hist_win, hist_full, (const unsigned long long*)stats,
                    (IpbQOut*)qout, miss);
-        rc = ipb_check_launch("ipb_k_hist_select_q");
+        if ((rc = ipb_check_launch("ipb_k_pq_select"))) return rc;
     }
-    return rc;
+    return IPB_OK;
 }
 
 int ipb_hist_planes(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,

@@ -39,40 +39,20 @@ struct IpbHistJob {
     int pad2;
 };
 
-// ---- selection by sampling (ipb_hist_select): per-job value window derived from a sample
-#define IPB_HSEL_WIN 4096        // window bins per job in the tail pass
+// ---- plane passes: the jobs that read one plane, fused into one read (ipb_hist_planes, ipb_hist_select)
 #define IPB_HSEL_MAXJ 4          // jobs fused into one pass over a plane
-#define IPB_HSEL_WINDOWED 0
-#define IPB_HSEL_FULL 1          // exact full-range histogram instead (sparse patterns, wide windows)
-#define IPB_HSEL_NONE 2          // no order statistic wanted from this job
-#define IPB_HSEL_SPARSE 3        // [::k, ::k] sample: counted straight into the full histogram by the tail pass
-#define IPB_HSEL_LOWFRAC 0.12    // windowed selection only when at most this fraction lies below the window's end
-struct IpbHistWin { int wlo, whi, mode, pad; };     // window [wlo, whi)
+struct IpbHistWin { int wlo, whi, mode, pad; };     // window [wlo, whi); mode IPB_PQ_*
 struct IpbPlanePass { int plane, excl_plane1, sat_min, n_jobs; int job[IPB_HSEL_MAXJ]; };
-
-// deterministic 1/16 sample of 256-pixel row segments (32 consecutive 8-pixel groups = the
-// groups one warp reads together, so a sampled warp is fully active): hash of the segment's
-// row and column index -- no row / column periodicity of the image can line up with it.
-// Pixels of a segment are correlated, which ipb_k_hist_windows' margin accounts for.
-__device__ __forceinline__ bool ipb_hist_sampled(unsigned y, unsigned xv) {
-    unsigned h = y * 0x9E3779B1u + (xv >> 5) * 0x85EBCA77u;
-    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
-    return (h & 15u) == 0u;
-}
 
 // out_stats[job] = { n_selected, sum_all, sumsq_all, reserved }
 __global__ void __launch_bounds__(IPB_HIST_THREADS)
 ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
                const IpbHistJob* __restrict__ jobs, int rows_per_chunk,
                const unsigned* __restrict__ union_bits, int union_wpr,
-               unsigned* __restrict__ hist, unsigned long long* __restrict__ out_stats,
-               int sample /* != 0: only the hash-sampled 1/16 of the 8-pixel groups */,
-               const IpbHistWin* __restrict__ only_full /* non-null: jobs whose mode != FULL are skipped */)
+               unsigned* __restrict__ hist, unsigned long long* __restrict__ out_stats)
 {
     IPB_DYN_SMEM(unsigned, sh);
-    if (only_full && only_full[blockIdx.y].mode != IPB_HSEL_FULL) return;
-    IpbHistJob job = jobs[blockIdx.y];
-    if (sample || only_full) job.moments = 0;        // the selection path takes moments in its tail pass
+    const IpbHistJob job = jobs[blockIdx.y];
     const int y_beg = (int)blockIdx.x * rows_per_chunk;
     int y_end = y_beg + rows_per_chunk;
     if (y_end > H) y_end = H;
@@ -164,7 +144,6 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
                     ys[u] = y; xs[u] = xv << 3;
                     ok[u] = y < y_end;
                     if (ok[u] && job.pattern == IPB_PAT_STRIDE2D && !job.moments && (y % k) != 0) ok[u] = false;
-                    if (ok[u] && sample && !ipb_hist_sampled((unsigned)y, (unsigned)xv)) ok[u] = false;
                     q[u] = make_uint4(0, 0, 0, 0); q2[u] = make_uint4(0, 0, 0, 0);
                     if (ok[u]) {
                         q[u] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + xs[u]));
@@ -180,7 +159,6 @@ ipb_k_hist_u16(const unsigned short* __restrict__ planes, int H, int W,
             const int dy = (int)blockDim.x / W, dx = (int)blockDim.x % W;
             int y = y_beg + (int)threadIdx.x / W, x = (int)threadIdx.x % W;
             for (; y < y_end; x += dx, y += dy, y += (x >= W) ? 1 : 0, x -= (x >= W) ? W : 0) {
-                if (sample && !ipb_hist_sampled((unsigned)y, (unsigned)(x >> 3))) continue;
                 const unsigned v = img[(size_t)y * W + x];
                 if (job.moments) { s1 += v; s2 += (unsigned long long)v * v; }
                 bool sel;
@@ -312,428 +290,7 @@ ipb_k_hist_quantiles(const unsigned* __restrict__ hist, const unsigned long long
     }
 }
 
-// ================================================================ selection by sampling
-// np.percentile needs two order statistics, not the whole distribution.  ipb_hist_select:
-//   1. sample   exact histogram of a hashed 1/16 sample of each job's pixels (ipb_k_hist_u16,
-//               sample = 1): 16x fewer shared-memory atomics, 1/8 of the DRAM sectors.
-//   2. windows  per job, the value window that contains every wanted rank with overwhelming
-//               probability: sample ranks r = q (n_s - 1) -/+ (6 sqrt(q (1-q) n_s) + 8).
-//   3. tail     ONE read of each plane for all jobs that sample it: pixels below / above the
-//               window are only counted, pixels inside go to a 4096-bin shared histogram.
-//   4. fallback sparse patterns, tiny samples and wide windows take the exact full-range
-//               histogram (ipb_k_hist_u16 restricted to those jobs).
-//   5. select   exact ranks inside the window.  A wanted rank outside its window is reported
-//               in *miss (the caller then repeats the step with full histograms), so the
-//               result is exact in every case.
-
-// one CTA (256 threads) per histogram job
-__global__ void __launch_bounds__(256)
-ipb_k_hist_windows(const unsigned* __restrict__ hs /* sample histograms */,
-                   const unsigned long long* __restrict__ stats_s, const IpbHistJob* __restrict__ jobs,
-                   const IpbQJob* __restrict__ qjobs, int n_q, IpbHistWin* __restrict__ win)
-{
-    const int job = blockIdx.x, t = threadIdx.x;
-    const unsigned* h = hs + (size_t)job * IPB_HIST_BINS;
-    const unsigned long long ns = stats_s[(size_t)job * 4];
-    __shared__ unsigned long long red_u[32];
-    __shared__ int want[2];
-    __shared__ int res[2];
-    __shared__ int any_q;
-    if (t == 0) { want[0] = 0x7fffffff; want[1] = -1; any_q = 0; res[0] = res[1] = -1; }
-    __syncthreads();
-    const bool countable = ns > 0 && ns < 0x7fffffffull;
-    // rank range over every quantile wanted from this job
-    for (int i = t; i < n_q; i += blockDim.x) {
-        if (qjobs[i].hist != job) continue;
-        atomicOr(&any_q, 1);
-        if (!countable) continue;
-        const double q = (double)qjobs[i].q32;
-        const double r = q * (double)(ns - 1);
-        // 6 sigma of the sample rank, widened 9x for the clustered (256-px segment) sample
-        const double d = 54.0 * sqrt(fmax(q * (1.0 - q), 0.0) * (double)ns) + 64.0;
-        double a = floor(r - d), b = ceil(r + d) + 1.0;
-        if (a < 0.0) a = 0.0;
-        if (b > (double)(ns - 1)) b = (double)(ns - 1);
-        atomicMin(&want[0], (int)a);
-        atomicMax(&want[1], (int)b);
-    }
-    __syncthreads();
-    const int pattern = jobs[job].pattern;
-    const bool sparse = pattern == IPB_PAT_STRIDE2D || pattern == IPB_PAT_MASKED_STRIDE;
-    if (any_q && ns >= 256 && countable && !sparse) {         // block-uniform
-        const unsigned long long wv[2] = {(unsigned long long)want[0], (unsigned long long)want[1]};
-        ipb_locate_ranks(IPB_HIST_BINS / 32, wv, 2, red_u, [&](unsigned i) { return h[i]; },
-                         [&](int r, unsigned i, unsigned) { res[r] = (int)i; });
-    }
-    __syncthreads();
-    if (t == 0) {
-        IpbHistWin o;
-        o.pad = 0;
-        if (!any_q) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_NONE; }
-        else if (pattern == IPB_PAT_STRIDE2D) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_SPARSE; }
-        else if (ns < 256 || !countable || sparse || res[0] < 0 || res[1] < 0 ||
-                 (double)want[1] > IPB_HSEL_LOWFRAC * (double)ns) { o.wlo = 0; o.whi = 0; o.mode = IPB_HSEL_FULL; }
-        else {
-            // a window that starts / ends at the sample's extreme rank is opened to the end of
-            // the value range: the true extremes may lie beyond the sample's
-            // the tail pass lists every pixel below the window's end, so the window may start at 0:
-            // a rank can then never fall below it
-            o.wlo = 0;
-            o.whi = res[1] + 1;
-            o.mode = (o.whi - o.wlo <= IPB_HSEL_WIN) ? IPB_HSEL_WINDOWED : IPB_HSEL_FULL;
-        }
-        win[job] = o;
-    }
-}
-
-// tail pass: grid (chunks, plane passes).  Per job: number of selected pixels -> stats[job][0];
-// moments of the plane -> stats[job][1..2]; sparse [::k, ::k] jobs are counted straight into
-// their full histogram.  Every selected pixel BELOW the largest window end of the pass is appended
-// (value | selection bits << 16) to the pass's list; all the others are "above" for every job and
-// need nothing more.  The common 8-pixel group is decided by one vector minimum.
-#define IPB_HSEL_THREADS 512
-#define IPB_HSEL_WBUF 128         // low pixels staged per warp before one global append
-__global__ void __launch_bounds__(IPB_HSEL_THREADS, 2)
-ipb_k_hist_tail(const unsigned short* __restrict__ planes, int H, int W,
-                const IpbPlanePass* __restrict__ passes, const IpbHistJob* __restrict__ jobs,
-                const IpbHistWin* __restrict__ win, int rows_per_chunk,
-                const unsigned* __restrict__ union_bits, int union_wpr,
-                unsigned* __restrict__ hist_full, unsigned* __restrict__ list, unsigned list_cap,
-                unsigned* __restrict__ list_n, unsigned long long* __restrict__ stats, unsigned* __restrict__ miss)
-{
-    const IpbPlanePass pp = passes[blockIdx.y];
-    const int y_beg = (int)blockIdx.x * rows_per_chunk;
-    int y_end = y_beg + rows_per_chunk;
-    if (y_end > H) y_end = H;
-    if (y_beg >= y_end) return;
-    int pat[IPB_HSEL_MAXJ], kk[IPB_HSEL_MAXJ], mode[IPB_HSEL_MAXJ];
-    unsigned pat16[IPB_HSEL_MAXJ];
-    unsigned* gh[IPB_HSEL_MAXJ];
-    const unsigned* ub[IPB_HSEL_MAXJ];
-    bool moments = false;
-    unsigned whi_all = 0;
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        pat[u] = -1; kk[u] = 1; mode[u] = IPB_HSEL_NONE; pat16[u] = 0; gh[u] = nullptr; ub[u] = nullptr;
-        if (u < pp.n_jobs) {
-            const IpbHistJob j = jobs[pp.job[u]];
-            const IpbHistWin w = win[pp.job[u]];
-            moments = moments || j.moments != 0;
-            if (w.mode == IPB_HSEL_WINDOWED || w.mode == IPB_HSEL_SPARSE) {
-                pat[u] = j.pattern; kk[u] = j.k > 0 ? j.k : 1; mode[u] = w.mode;
-                gh[u] = hist_full + (size_t)pp.job[u] * IPB_HIST_BINS;
-                ub[u] = (j.pattern == IPB_PAT_MASKED) ? union_bits + (size_t)j.mask_frame * H * union_wpr : nullptr;
-                for (int t = 0; t < 16; t += kk[u]) pat16[u] |= 1u << t;
-                if (w.mode == IPB_HSEL_WINDOWED && (unsigned)w.whi > whi_all) whi_all = (unsigned)w.whi;
-            }
-        }
-    }
-    {
-        bool need = moments;
-#pragma unroll
-        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) need = need || pat[u] >= 0;
-        if (!need) return;
-    }
-    unsigned* lst = list + (size_t)blockIdx.y * list_cap;
-    unsigned* lst_n = list_n + blockIdx.y;
-    const unsigned short* img = planes + (size_t)pp.plane * H * W;
-    const unsigned sat_min = pp.sat_min > 0 ? (unsigned)pp.sat_min : 0xffffffffu;
-    const unsigned short* img2 = (pp.sat_min > 0 && pp.excl_plane1 > 0) ? planes + (size_t)(pp.excl_plane1 - 1) * H * W : nullptr;
-    unsigned nsel[IPB_HSEL_MAXJ];
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) nsel[u] = 0;
-    unsigned long long s1 = 0, s2 = 0;
-    const bool vec_ok = ((W & 7) == 0) && ((((size_t)img) & 15) == 0) && ((((size_t)img2) & 15) == 0);
-    const int step = vec_ok ? 8 : 1;
-    const int upr = vec_ok ? (W >> 3) : W;
-    const int dy = (int)blockDim.x / upr, dx = (int)blockDim.x % upr;
-    int y = y_beg + (int)threadIdx.x / upr, xu = (int)threadIdx.x % upr;
-    const int lane = threadIdx.x & 31;
-    __shared__ unsigned wbuf_all[IPB_HSEL_THREADS / 32][IPB_HSEL_WBUF];
-    unsigned* wbuf = wbuf_all[threadIdx.x >> 5];
-    unsigned wcount = 0;                                   // entries staged by this warp (warp-uniform)
-    auto flush = [&]() {
-        if (wcount == 0) return;
-        __syncwarp();
-        unsigned g = 0;
-        if (lane == 0) g = atomicAdd(lst_n, wcount);
-        g = __shfl_sync(IPB_FULL, g, 0);
-        for (unsigned i = lane; i < wcount; i += 32) if (g + i < list_cap) lst[g + i] = wbuf[i];
-        __syncwarp();
-        wcount = 0;
-    };
-
-    auto process = [&](bool ok, int y, int x0, const unsigned (&w)[4], const unsigned (&w2)[4]) {
-        unsigned low = 0, selj[IPB_HSEL_MAXJ];
-#pragma unroll
-        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) selj[u] = 0;
-        if (ok) {
-            if (moments) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j * 2 >= step) break;
-                    const unsigned a = w[j] & 0xffffu, b = step == 1 ? 0u : (w[j] >> 16);
-                    s1 += a + b;
-                    s2 += (unsigned long long)a * a + (unsigned long long)b * b;
-                }
-            }
-            unsigned keep = step == 8 ? 0xffu : 1u;
-            if (pp.sat_min > 0) {
-                keep = 0;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    if (t >= step) break;
-                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
-                    const unsigned o = (t & 1) ? (w2[t >> 1] >> 16) : (w2[t >> 1] & 0xffffu);
-                    keep |= (v < sat_min && o < sat_min) ? (1u << t) : 0u;
-                }
-            }
-            unsigned vmin = w[0] & 0xffffu;
-            if (step == 8) {
-                const unsigned m01 = umin(umin(w[0] & 0xffffu, w[0] >> 16), umin(w[1] & 0xffffu, w[1] >> 16));
-                const unsigned m23 = umin(umin(w[2] & 0xffffu, w[2] >> 16), umin(w[3] & 0xffffu, w[3] >> 16));
-                vmin = umin(m01, m23);
-            }
-            if (vmin < whi_all) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    if (t >= step) break;
-                    const unsigned v = (t & 1) ? (w[t >> 1] >> 16) : (w[t >> 1] & 0xffffu);
-                    low |= (v < whi_all) ? (1u << t) : 0u;
-                }
-                low &= keep;
-            }
-            unsigned anysel = 0;
-#pragma unroll
-            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-                if (pat[u] < 0) continue;
-                unsigned sel = 0;
-                const unsigned k = (unsigned)kk[u];
-                if (pat[u] == IPB_PAT_FULL) sel = 0xffu;
-                else if (pat[u] == IPB_PAT_STRIDE1D) {
-                    const unsigned long long flat = (unsigned long long)y * W + x0;
-                    const unsigned fm = (k & (k - 1u)) == 0u ? (unsigned)flat & (k - 1u)
-                                        : (flat < 0xffffffffull ? (unsigned)flat % k : (unsigned)(flat % (unsigned long long)k));
-                    const unsigned first = fm ? k - fm : 0u;
-                    sel = first < 8u ? (pat16[u] << first) & 0xffu : 0u;
-                } else if (pat[u] == IPB_PAT_STRIDE2D) {
-                    if ((unsigned)y % k == 0u) {
-                        const unsigned xm = (unsigned)x0 % k;
-                        const unsigned first = xm ? k - xm : 0u;
-                        sel = first < 8u ? (pat16[u] << first) & 0xffu : 0u;
-                    }
-                } else if (pat[u] == IPB_PAT_MASKED) {
-                    sel = (ub[u][(size_t)y * union_wpr + (x0 >> 5)] >> (x0 & 31)) & 0xffu;
-                }
-                sel &= keep;
-                if (step == 1) sel &= 1u;
-                nsel[u] += (unsigned)__popc(sel);
-                if (mode[u] == IPB_HSEL_SPARSE) {               // few pixels: straight to the full histogram
-                    unsigned todo = sel;
-                    while (todo) {
-                        const int t = __ffs((int)todo) - 1;
-                        todo &= todo - 1;
-                        const unsigned word = t < 4 ? (t < 2 ? w[0] : w[1]) : (t < 6 ? w[2] : w[3]);
-                        atomicAdd(&gh[u][(t & 1) ? (word >> 16) : (word & 0xffffu)], 1u);
-                    }
-                } else {
-                    anysel |= sel;
-                    selj[u] = sel;
-                }
-            }
-            low &= anysel;
-        }
-        // append this warp's low pixels.  They are staged in a per-warp shared buffer (positions
-        // from a warp scan, no atomics) and go to the pass's global list 128 at a time with ONE
-        // global atomic per flush; a trip with more than 64 of them writes through directly.
-        const unsigned cnt = (unsigned)__popc(low);
-        unsigned incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
-        const unsigned total = __shfl_sync(IPB_FULL, incl, 31);
-        if (total == 0) return;                                   // warp-uniform
-        const bool direct = total > 64u;
-        if (!direct && wcount + total > IPB_HSEL_WBUF) flush();
-        unsigned base;
-        if (direct) {
-            base = 0;
-            if (lane == 31) base = atomicAdd(lst_n, total);
-            base = __shfl_sync(IPB_FULL, base, 31) + incl - cnt;
-        } else {
-            base = wcount + incl - cnt;
-            wcount += total;
-        }
-        unsigned todo = low;
-        while (todo) {
-            const int t = __ffs((int)todo) - 1;
-            todo &= todo - 1;
-            const unsigned word = t < 4 ? (t < 2 ? w[0] : w[1]) : (t < 6 ? w[2] : w[3]);
-            const unsigned v = (t & 1) ? (word >> 16) : (word & 0xffffu);
-            unsigned sb = 0;                                      // which jobs selected this pixel
-#pragma unroll
-            for (int u = 0; u < IPB_HSEL_MAXJ; ++u) sb |= ((selj[u] >> t) & 1u) << u;
-            if (direct) { if (base < list_cap) lst[base] = v | (sb << 16); }
-            else wbuf[base] = v | (sb << 16);
-            ++base;
-        }
-    };
-    // trips are warp-uniform (every lane of a warp runs the same number of them), the scans need that
-    const int units_band = (y_end - y_beg) * upr;
-    const int trips = (units_band + (int)blockDim.x - 1) / (int)blockDim.x;
-    for (int trip = 0; trip < trips; trip += 2) {             // two units per trip: both loads issued first
-        bool ok[2];
-        int ys[2], xs[2];
-        unsigned w[2][4], w2[2][4];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            ok[g] = (trip + g < trips) && y < y_end;
-            ys[g] = y; xs[g] = xu * step;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { w[g][j] = 0; w2[g][j] = 0; }
-            if (ok[g]) {
-                if (vec_ok) {
-                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + (size_t)y * W + xs[g]));
-                    w[g][0] = q.x; w[g][1] = q.y; w[g][2] = q.z; w[g][3] = q.w;
-                    if (img2) {
-                        const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(img2 + (size_t)y * W + xs[g]));
-                        w2[g][0] = q2.x; w2[g][1] = q2.y; w2[g][2] = q2.z; w2[g][3] = q2.w;
-                    }
-                } else {
-                    w[g][0] = img[(size_t)y * W + xs[g]];
-                    if (img2) w2[g][0] = img2[(size_t)y * W + xs[g]];
-                }
-            }
-            xu += dx; y += dy;
-            if (xu >= upr) { xu -= upr; ++y; }
-        }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) if (trip + g < trips) process(ok[g], ys[g], xs[g], w[g], w2[g]);
-    }
-    flush();
-    // per job: selected-pixel count; moments of the plane (all pixels) to every job that asked
-    __shared__ unsigned long long acc[IPB_HSEL_MAXJ + 2];
-    if (threadIdx.x < IPB_HSEL_MAXJ + 2) acc[threadIdx.x] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        const unsigned long long a = ipb_warp_sum((unsigned long long)nsel[u]);
-        if (lane == 0 && a) atomicAdd(&acc[u], a);
-    }
-    s1 = ipb_warp_sum(s1); s2 = ipb_warp_sum(s2);
-    if (lane == 0) { if (s1) atomicAdd(&acc[IPB_HSEL_MAXJ], s1); if (s2) atomicAdd(&acc[IPB_HSEL_MAXJ + 1], s2); }
-    __syncthreads();
-    if (threadIdx.x < pp.n_jobs) {
-        const int u = threadIdx.x, j = pp.job[u];
-        if (acc[u]) atomicAdd(&stats[(size_t)j * 4], acc[u]);
-        if (jobs[j].moments) {
-            if (acc[IPB_HSEL_MAXJ]) atomicAdd(&stats[(size_t)j * 4 + 1], acc[IPB_HSEL_MAXJ]);
-            if (acc[IPB_HSEL_MAXJ + 1]) atomicAdd(&stats[(size_t)j * 4 + 2], acc[IPB_HSEL_MAXJ + 1]);
-        }
-    }
-    (void)miss;                                            // list overflow is reported by the classify pass
-}
-
-// classify pass: grid (chunks, plane passes), 256 threads.  Every list entry is placed, per job
-// that selected it, below the job's window or into its 4096-bin window histogram.
-// cnt[job] = { below, inside, 0, 0 }.
-__global__ void __launch_bounds__(256)
-ipb_k_hist_classify(const IpbPlanePass* __restrict__ passes, const IpbHistWin* __restrict__ win,
-                    const unsigned* __restrict__ list, unsigned list_cap, const unsigned* __restrict__ list_n,
-                    unsigned* __restrict__ hw, unsigned long long* __restrict__ cnt, unsigned* __restrict__ miss)
-{
-    IPB_DYN_SMEM(unsigned, sh);
-    const IpbPlanePass pp = passes[blockIdx.y];
-    const unsigned n_all = list_n[blockIdx.y];
-    if (n_all > list_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(miss, 1u); return; }   // list overflow
-    const unsigned per = (n_all + gridDim.x - 1) / gridDim.x;
-    const unsigned i0 = blockIdx.x * per;
-    unsigned i1 = i0 + per;
-    if (i1 > n_all) i1 = n_all;
-    if (i0 >= i1) return;
-    unsigned wlo[IPB_HSEL_MAXJ], whi[IPB_HSEL_MAXJ];
-    bool on[IPB_HSEL_MAXJ];
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        on[u] = false; wlo[u] = whi[u] = 0;
-        if (u < pp.n_jobs) {
-            const IpbHistWin w = win[pp.job[u]];
-            on[u] = w.mode == IPB_HSEL_WINDOWED;
-            wlo[u] = (unsigned)w.wlo; whi[u] = (unsigned)w.whi;
-        }
-    }
-    for (int b = threadIdx.x; b < pp.n_jobs * IPB_HSEL_WIN; b += blockDim.x) sh[b] = 0;
-    __syncthreads();
-    const unsigned* lst = list + (size_t)blockIdx.y * list_cap;
-    unsigned below[IPB_HSEL_MAXJ], inside[IPB_HSEL_MAXJ];
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) below[u] = inside[u] = 0;
-    for (unsigned i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        const unsigned e = lst[i], v = e & 0xffffu, sb = e >> 16;
-#pragma unroll
-        for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-            if (on[u] && ((sb >> u) & 1u)) {
-                if (v < wlo[u]) ++below[u];
-                else if (v < whi[u]) { ++inside[u]; atomicAdd(&sh[u * IPB_HSEL_WIN + (v - wlo[u])], 1u); }
-            }
-        }
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < pp.n_jobs * IPB_HSEL_WIN; b += blockDim.x) {
-        const unsigned c = sh[b];
-        if (c) atomicAdd(&hw[(size_t)pp.job[b / IPB_HSEL_WIN] * IPB_HSEL_WIN + (b % IPB_HSEL_WIN)], c);
-    }
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int u = 0; u < IPB_HSEL_MAXJ; ++u) {
-        const unsigned long long a = ipb_warp_sum((unsigned long long)below[u]);
-        const unsigned long long b = ipb_warp_sum((unsigned long long)inside[u]);
-        if (lane == 0 && u < pp.n_jobs) {
-            if (a) atomicAdd(&cnt[(size_t)pp.job[u] * 4], a);
-            if (b) atomicAdd(&cnt[(size_t)pp.job[u] * 4 + 1], b);
-        }
-    }
-}
-
-// one CTA (256 threads) per quantile job
-__global__ void __launch_bounds__(256)
-ipb_k_hist_select_q(const IpbQJob* __restrict__ qjobs, const IpbHistWin* __restrict__ win,
-                    const unsigned long long* __restrict__ cnt, const unsigned* __restrict__ hw,
-                    const unsigned* __restrict__ hf, const unsigned long long* __restrict__ stats,
-                    IpbQOut* __restrict__ out, unsigned* __restrict__ miss)
-{
-    const IpbQJob qj = qjobs[blockIdx.x];
-    const IpbHistWin wn = win[qj.hist];
-    const unsigned long long n = stats[(size_t)qj.hist * 4];
-    const bool windowed = wn.mode == IPB_HSEL_WINDOWED;
-    const unsigned* h = windowed ? hw + (size_t)qj.hist * IPB_HSEL_WIN : hf + (size_t)qj.hist * IPB_HIST_BINS;
-    const int per = windowed ? IPB_HSEL_WIN / 256 : IPB_HIST_BINS / 256;
-    const unsigned long long base = windowed ? cnt[(size_t)qj.hist * 4] : 0ull;
-    const int v0 = windowed ? wn.wlo : 0;
-    __shared__ unsigned long long red_u[32];
-    __shared__ int res[2];
-    const int t = threadIdx.x;
-    if (t < 2) res[t] = -1;
-    IpbQIdx qi;
-    qi.prev = 0; qi.next = 0; qi.gamma = 0.f;
-    if (n > 0) {                                              // block-uniform
-        qi = ipb_np_qidx_f32((long long)n, qj.q32);
-        // ranks relative to the first counter of the scanned histogram; a rank below the window
-        // (prev < base) wraps to a huge value and is never found -> reported as a miss
-        const unsigned long long want[2] = {(unsigned long long)qi.prev - base, (unsigned long long)qi.next - base};
-        const unsigned nbins = (unsigned)(per * 256);
-        ipb_locate_ranks(nbins / 32, want, 2, red_u, [&](unsigned i) { return h[i]; },
-                         [&](int r, unsigned i, unsigned) { res[r] = v0 + (int)i; });
-    }
-    __syncthreads();
-    if (t == 0) {
-        IpbQOut o;
-        o.prev = res[0]; o.next = res[1]; o.gamma = qi.gamma; o.n = n;
-        const bool ok = n > 0 && res[0] >= 0 && res[1] >= 0;
-        o.value = ok ? ipb_np_lerp_f32((float)res[0], (float)res[1], qi.gamma) : 0.0f;
-        if (n > 0 && !ok) atomicAdd(miss, 1u);          // the sample-derived window missed a rank
-        out[blockIdx.x] = o;
-    }
-}
+#include "ipb_pq.cuh"
 
 // ================================================================ fused full histograms per plane
 // ipb_k_hist_planes: the exact 65 536-bin histograms of EVERY job that samples a plane from ONE

@@ -41,7 +41,7 @@ class RoiMasks:
 KERNELS_PER_CALL = {"ipb_fa_segment": 4,   # fused per-crop path (14 on the one-kernel-per-phase path)
                      "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
                     "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
-                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_region_dilate": 2, "ipb_hist_select": 6, "ipb_hist_planes": 1}
+                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_region_dilate": 2, "ipb_hist_select": 3, "ipb_hist_planes": 1}
 
 
 class Engine:
@@ -145,6 +145,33 @@ def plane_passes(hist_jobs):
             pp["job"][: len(js[i: i + 4])] = js[i: i + 4]
             out.append(pp)
     return np.array(out, dtype=PLANE_PASS) if out else np.zeros(0, dtype=PLANE_PASS)
+
+
+PQ_WIN = 2048
+
+
+def pq_servable(hist_jobs, passes):
+    """True when every plane pass can take ipb_hist_select's sampled-window path (mirror of
+    ipb_pq_roles in csrc/ipb_pq.cuh): at most one FULL job, one flat-stride job with k in
+    {2, 4, 8} and one [::k, ::k] job per pass, no masks, no saturation filter."""
+    for pp in passes:
+        if int(pp["sat_min"]) > 0:
+            return False
+        roles = set()
+        for j in pp["job"][: int(pp["n_jobs"])]:
+            hj = hist_jobs[int(j)]
+            if int(hj["sat_min"]) > 0 or int(hj["excl_plane1"]) > 0:
+                return False
+            pat, k = int(hj["pattern"]), int(hj["k"])
+            if pat == PAT_FULL and "F" not in roles:
+                roles.add("F")
+            elif pat == PAT_STRIDE1D and k in (2, 4, 8) and "S" not in roles:
+                roles.add("S")
+            elif pat == PAT_STRIDE2D and k >= 1 and "P" not in roles:
+                roles.add("P")
+            else:
+                return False
+    return True
 
 
 def q32_of(p):

@@ -364,6 +364,7 @@ def check_combined_batch_shared_rois(eng):
         fret_p = dict(fret_p, bg_scope=fret_scope)
         job = batch.FrameBatchJob(eng, (F, C, H, W), stages=("fret", "int", "fa"), fret_p=fret_p, int_task=task,
                                   fa_params=fa_params, fa_px=px, want_roi_image=True)
+        job.pq_min_px = 0                                      # sampled windows even on these small planes
         polys_pf = [fr[2] for fr in frames]
         for rep in range(2):                                   # second run goes through the cached plan
             job.hist_select = bool(rep)                        # ... and through percentiles by sampling
@@ -601,43 +602,72 @@ def check_preview_and_crop(eng):
 RASTER_CHECKS += [check_rim_mask, check_square_dilation, check_region_moments, check_preview_and_crop]
 
 
-def _hist_sampled(y, xv):
-    """numpy twin of ipb_hist_sampled (csrc/ipb_hist.cuh): the hashed 1/16 sample of 8-px groups."""
-    h = (y.astype(np.uint64) * 0x9E3779B1 + (xv.astype(np.uint64) >> 5) * 0x85EBCA77) & 0xFFFFFFFF
+def _pq_sampled_units(plane, n_units):
+    """numpy twin of ipb_k_pq_sample's unit choice (csrc/ipb_pq.cuh): one hashed 8-pixel unit
+    out of every stratum of consecutive units."""
+    nsu = min(8192, n_units)
+    stratum = n_units // nsu
+    i = np.arange(nsu, dtype=np.uint64)
+    h = ((i * 0x9E3779B1) & 0xFFFFFFFF) ^ (((plane + 1) * 0x85EBCA77) & 0xFFFFFFFF)
     h ^= h >> 15
     h = (h * 0x2C1B3C6D) & 0xFFFFFFFF
     h ^= h >> 12
-    return (h & 15) == 0
+    return (i * stratum + ((h * stratum) >> 32)).astype(np.int64)
 
 
 def check_hist_select_paths(eng):
-    """Backgrounds through ipb_hist_select: windowed selection on ordinary data is exact; data
-    built so that the hashed sample misleads the window (most pixels the sample never saw are
-    darker than anything it saw) makes the step report a miss and repeat itself with full
-    histograms -- still exact."""
+    """Backgrounds through ipb_hist_select (sampled windows): exact on ordinary data without a
+    rerun; data built so that the sample misleads the window (most pixels the sample never saw
+    are darker than anything it saw) makes the step report a miss and repeat itself with full
+    histograms -- still exact.  FRET (two quantiles of one FULL job) + Fluor_INT (flat stride)
+    + FA (moments + sparse sample) share the plane passes."""
     from imageprocess_b200 import batch
     rng = np.random.default_rng(2)
     H, W = 512, 1024
-    yy, xv = np.meshgrid(np.arange(H), np.arange(W // 8), indexing="ij")
-    sampled = np.repeat(_hist_sampled(yy, xv), 8, axis=1)
-    assert 0.03 < sampled.mean() < 0.10
-    normal = rng.poisson(400, (H, W)).astype(np.uint16)
-    tricky = rng.integers(1000, 2000, (H, W)).astype(np.uint16)
-    tricky[(~sampled) & (rng.random((H, W)) < 0.6)] = 5              # invisible to the sample: floods the low-pixel list
-    for img, want_miss in ((normal, 0), (tricky, 1)):
-        planes = np.stack([img, img[::-1].copy()])[None]
-        for p, stride in ((1.0, 4), (1.0, 1), (50.0, 1)):
+    normal = [rng.poisson(400, (H, W)).astype(np.uint16) for _ in range(2)]
+    tricky = []
+    for plane in range(2):
+        t = rng.integers(1000, 2000, (H, W)).astype(np.uint16)
+        seen = np.zeros(H * W // 8, dtype=bool)
+        seen[_pq_sampled_units(plane, H * W // 8)] = True
+        seen = np.repeat(seen, 8).reshape(H, W)
+        assert 0.10 < seen.mean() < 0.15
+        t[(~seen) & (rng.random((H, W)) < 0.6)] = 5                  # invisible to the sample
+        tricky.append(t)
+    for imgs, want_miss in ((normal, 0), (tricky, 1)):
+        planes = np.stack(imgs)[None]
+        for p, stride in ((1.0, 4), (1.0, 1), (50.0, 2), (0.0, 8)):
             task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": stride,
                     "percentile": p, "per_channel_p": False, "ch_p_map": {}}
             job = batch.FrameBatchJob(eng, planes.shape, stages=("int",), int_task=task, hist_select=True)
             res = job.run(eng.mem.from_host(planes), [[]])
+            assert job._plans[next(iter(job._plans))].pq_ok
             for ci in range(2):
                 want = port.int_bg_value(planes[0, ci].astype(np.float32), "percentile", p, None, stride)
                 assert float(res.int_bg[0, ci]) == want, (p, stride, ci)
-            # p = 50 never takes the windowed path (too many pixels below the window's end); p = 1
-            # does: with stride 4 the unseen dark pixels still fit the list (exact without a
-            # rerun), with stride 1 on the tricky image the list overflows -> miss -> exact rerun
-            assert job.window_misses == (want_miss if (p, stride) == (1.0, 1) else 0), (p, stride, job.window_misses)
+            # p = 0 (the minimum) and p = 1 on the 4-strided subsample: the lowest wanted sample
+            # rank is the sample's first, so the window opens at 0 and holds the unseen dark
+            # pixels -- exact without a rerun; the other two windows start above them -> miss
+            assert job.window_misses == (want_miss if (p, stride) in ((1.0, 1), (50.0, 2)) else 0), (p, stride, job.window_misses)
+    # all three stages on one frame: FULL + flat stride + sparse jobs and the moments in one pass
+    fret_p = {"bg_scope": "full", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": True,
+              "donor_p": 2.0, "fret_p": 0.5, "clip_neg": True, "eps_percentile": 3.0, "ratio_mode": "FRET/Donor"}
+    task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4,
+            "percentile": 1.0, "per_channel_p": False, "ch_p_map": {}}
+    planes = np.stack(normal)[None]
+    res = {}
+    for sel in (True, False):
+        job = batch.FrameBatchJob(eng, planes.shape, stages=("fret", "int", "fa"), fret_p=fret_p, int_task=task,
+                                  fa_params=FA_CASES[0], fa_px=0.112, hist_select=sel)
+        res[sel] = job.run(eng.mem.from_host(planes), [[]])
+        assert job.window_misses == 0
+        assert job._plans[next(iter(job._plans))].pq_ok
+    assert np.array_equal(res[True].fret_params, res[False].fret_params)
+    assert np.array_equal(res[True].int_bg, res[False].int_bg)
+    assert np.array_equal(res[True].fa_stats, res[False].fa_stats)
+    D = planes[0, 0].astype(np.float32)
+    assert float(res[True].fret_params[0, 0]) == float(np.percentile(D, 2.0))
+    assert float(res[True].fa_stats[0, 2]) == float(np.percentile(D[::10, ::10], 1.0))
 
 
 RASTER_CHECKS.append(check_hist_select_paths)
