@@ -101,7 +101,7 @@ class FrameBatchJob:
         self.gather_dst = 0
         self._gather_cap = None     # bytes every rank contributes to the per-step all-gather
         self.overlap = bool(int(os.environ.get("IPB_OVERLAP", "1")))   # branches of a step on side streams
-        self.fa_path = 0            # ipb_fa_segment path: 0 auto, 1 one CTA per crop, 2 one kernel per phase
+        self.fa_path = 0            # ipb_fa_segment path: 0 auto, 1 one CTA per crop (shared memory), 2 one kernel per phase, 3 one CTA per crop (global memory)
         # percentiles by sampled windows (ipb_hist_select) instead of full histograms wherever the
         # plane passes allow it (ops.pq_servable): exact either way
         self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "1"))) if hist_select is None else bool(hist_select)

@@ -337,7 +337,7 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    int32_t* labels, int path, const int32_t* crop_order, void* stream)
 {
     if (n_crops <= 0) return IPB_OK;
-    IPB_REQUIRE(path >= 0 && path <= 2, "ipb_fa_segment: path %d not in 0..2", path);
+    IPB_REQUIRE(path >= 0 && path <= 3, "ipb_fa_segment: path %d not in 0..3", path);
     IPB_REQUIRE(n_crops <= 65535, "ipb_fa_segment: n_crops %d out of range", n_crops);
     IPB_REQUIRE(crops && planes && fa_params && roi_mask && bw_a && bw_b && L && csize && rootbits &&
                 row_roots && row_base && crop_count && bw_final && comp_off && comps,
@@ -357,10 +357,22 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
     }
     // many small crops (cell ROIs): one CTA per crop runs the whole chain; few / huge crops
     // (the mosaic): one kernel per phase, each crop spread over the chip
-    const bool fused = path == 1 || (path == 0 && n_crops >= 64 && max_rows <= 1024);
+    // many small crops (cell ROIs): one CTA per crop runs the whole chain in shared memory (crops
+    // that do not fit are flagged and taken by the global-memory variant right after); few / huge
+    // crops (the mosaic): one kernel per phase, each crop spread over the chip.  path 3 = the
+    // global-memory per-crop kernel for every crop.
+    const bool fused = path == 1 || path == 3 || (path == 0 && n_crops >= 64 && max_rows <= 1024);
     if (fused) {
+        if (path != 3) {
+            IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_fa_fused_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)IPB_FAS_SMEM_BYTES), "fa smem");
+            IPB_LAUNCH(ipb_k_fa_fused_smem, dim3(n_crops), dim3(IPB_FAS_THREADS), IPB_FAS_SMEM_BYTES, stream, cr, planes, H, W,
+                       fa_params, roi_mask, min_size, disk, L, csize, row_roots, row_base, crop_count, bw_final, labels, crop_order);
+            if ((rc = ipb_check_launch("ipb_k_fa_fused_smem"))) return rc;
+        }
         IPB_LAUNCH(ipb_k_fa_fused, dim3(n_crops), dim3(IPB_FA_FUSED_THREADS), 0, stream, cr, planes, H, W, fa_params,
-                   roi_mask, min_size, disk, bw_a, bw_b, L, csize, rootbits, row_roots, row_base, crop_count, bw_final, crop_order);
+                   roi_mask, min_size, disk, bw_a, bw_b, L, csize, rootbits, row_roots, row_base, crop_count, bw_final, crop_order,
+                   path != 3 ? 1 : 0);
         if ((rc = ipb_check_launch("ipb_k_fa_fused"))) return rc;
     } else {
         IPB_LAUNCH(ipb_k_fa_threshold, grid, block, 0, stream, cr, planes, H, W, fa_params, roi_mask, bw_a);
@@ -392,6 +404,11 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
     }
     IPB_LAUNCH(ipb_k_fa_crop_scan, dim3(1), dim3(256), 0, stream, (const int*)crop_count, n_crops, comp_off);
     IPB_LAUNCH(ipb_k_fa_zero_comps, dim3(296), dim3(256), 0, stream, (const int*)comp_off, n_crops, comp_cap, (IpbComp*)comps);
+    if (fused && path != 3) {
+        IPB_LAUNCH(ipb_k_fa_gather_smem, dim3(8, (unsigned)n_crops), dim3(256), 0, stream, cr, (const int*)L, (const unsigned*)csize,
+                   (const int*)row_roots, (const int*)row_base, (const int*)crop_count, (const int*)comp_off, comp_cap,
+                   (IpbComp*)comps, labels);
+    }
     IPB_LAUNCH(ipb_k_fa_props, grid, block, 0, stream, cr, (const unsigned*)bw_final, (const int*)L,
                (const unsigned*)rootbits, (const int*)row_base, (const int*)comp_off, comp_cap, planes, H, W,
                (IpbComp*)comps, labels);

@@ -349,6 +349,16 @@ ipb_k_bits_morph(const IpbCrop* __restrict__ crops, const unsigned* __restrict__
     ipb_k_bits_morph_phase<OP>(c, fa_y0, fa_nrow, in, disk, out);
 }
 
+struct IpbComp {               // one row of the per-adhesion table (exact integer sums)
+    unsigned long long sum_i;  // sum of raw intensities
+    unsigned long long sum_y;  // sum of row coordinates (crop-local)
+    unsigned long long sum_x;  // sum of column coordinates (crop-local)
+    unsigned area;
+    int crop;
+};
+
+#include "ipb_fa_smem.cuh"
+
 // ---------------------------------------------------------------- 4. labels & regionprops
 // L[start] = root ; root bits ; roots per row
 __device__ __forceinline__ void ipb_k_ccl_flatten_roots_phase(const IpbCrop& c, int fa_y0, int fa_nrow, const unsigned* bits,
@@ -421,9 +431,11 @@ ipb_k_fa_fused(const IpbCrop* __restrict__ crops, const unsigned short* __restri
                const float* __restrict__ fa_params, const unsigned* __restrict__ roi_mask,
                double min_size, IpbDisk disk, unsigned* bw_a, unsigned* bw_b, int* L, unsigned* csize,
                unsigned* rootbits, int* row_roots, int* row_base, int* crop_count, unsigned* bw_final,
-               const int* __restrict__ order /* nullable: CTA b runs crop order[b] (biggest first) */)
+               const int* __restrict__ order /* nullable: CTA b runs crop order[b] (biggest first) */,
+               int only_flagged /* != 0: only crops the shared-memory kernel flagged (crop_count == -1) */)
 {
     const int ci = order ? order[blockIdx.x] : (int)blockIdx.x;
+    if (only_flagged && crop_count[ci] != -1) return;
     const IpbCrop c = crops[ci];
     const int fa_y0 = 0, fa_nrow = c.h;
     __shared__ int wsum[IPB_FA_FUSED_THREADS / 32];
@@ -508,14 +520,6 @@ ipb_k_fa_crop_scan(const int* __restrict__ crop_count, int n, int* __restrict__ 
     if (threadIdx.x == 0) comp_off[n] = carry;
 }
 
-struct IpbComp {               // one row of the per-adhesion table (exact integer sums)
-    unsigned long long sum_i;  // sum of raw intensities
-    unsigned long long sum_y;  // sum of row coordinates (crop-local)
-    unsigned long long sum_x;  // sum of column coordinates (crop-local)
-    unsigned area;
-    int crop;
-};
-
 __global__ void ipb_k_fa_zero_comps(const int* __restrict__ comp_off, int n_crops, int cap, IpbComp* __restrict__ comps)
 {
     int total = comp_off[n_crops];
@@ -549,6 +553,7 @@ ipb_k_fa_props(const IpbCrop* __restrict__ crops, const unsigned* __restrict__ b
 {
     const IpbCrop c = crops[blockIdx.y];
     IPB_FA_BAND(c);
+    if (row_base[c.row_off] == IPB_FAS_MARK) return;   // finished by ipb_k_fa_fused_smem / ipb_k_fa_gather_smem
     const unsigned short* img = planes + (size_t)c.plane * H * W;
     IPB_FA_FOREACH_WORD(c, {
         const unsigned* row = bits + c.bit_off + (size_t)y * c.wpr;

@@ -1,0 +1,310 @@
+// ipb_fa_smem.cuh -- the focal-adhesion chain of one crop entirely in shared memory.
+// Included by ipb_fa.cuh (same phases, same exact semantics as the kernels there).
+//
+// ipb_k_fa_fused walks its union-find and its bit images through L2: ~15 dependent phases of a
+// few global round trips each, ~80 us per cell crop although a crop is only ~2-4 K words of bits.
+// Here ONE CTA keeps everything of its crop on chip:
+//   * the two bit images it ping-pongs between (threshold -> size filter -> dilation -> erosion),
+//   * a compact run index: base[word] = number of run starts before the word (block scan), so a
+//     run's id is base[word] + its rank among the starts of the word; ids follow raster order,
+//   * union-find parents and component sizes over run ids (shared-memory atomicMin / atomicAdd),
+//   * per-component sums (area, intensity, coordinates) accumulated per run.
+// Component ranks (skimage's raster-order label numbers) are a block scan over the root flags of
+// the run ids.  Results leave the CTA as: the final bit rows (bw_final), a staged component table
+// (csize slice: 8 words per adhesion) and a run table (L slice: 2 words per run: y<<16 | x0,
+// len<<16 | rank) from which the optional label map is painted.  A crop that does not fit
+// (> IPB_FAS_MAXWORDS words, > IPB_FAS_MAXRUNS runs, > IPB_FAS_MAXCOMP adhesions, staging larger
+// than its slices) is flagged (crop_count = -1) and taken by ipb_k_fa_fused afterwards.
+#pragma once
+
+#define IPB_FAS_THREADS 512
+#define IPB_FAS_MAXWORDS 4096
+#define IPB_FAS_MAXRUNS 8192
+#define IPB_FAS_MAXCOMP 512
+#define IPB_FAS_MARK (-7)          // row_base[c.row_off]: this crop was finished by the shared-memory kernel
+#define IPB_FAS_SMEM_BYTES (IPB_FAS_MAXWORDS * 4 * 2 + IPB_FAS_MAXWORDS * 2 + IPB_FAS_MAXRUNS * 4 * 2)
+
+__device__ __forceinline__ unsigned ipb_fas_find(unsigned* parent, unsigned i) {
+    volatile unsigned* P = parent;
+    while (true) {
+        const unsigned p = P[i];
+        if (p == i) return i;
+        const unsigned gp = P[p];
+        if (gp == p) return p;
+        atomicMin(&parent[i], gp);          // path halving; parents only ever decrease
+        i = gp;
+    }
+}
+__device__ __forceinline__ void ipb_fas_union(unsigned* parent, unsigned a, unsigned b) {
+    while (true) {
+        a = ipb_fas_find(parent, a);
+        b = ipb_fas_find(parent, b);
+        if (a == b) return;
+        if (a > b) { const unsigned t = a; a = b; b = t; }
+        const unsigned old = atomicMin(&parent[b], a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+// base[word] = run starts before the word (raster order); returns the number of runs.
+// All threads must call it; ends with a barrier.
+__device__ __forceinline__ unsigned ipb_fas_index_runs(const IpbCrop& c, const unsigned* bits, unsigned short* base, unsigned* wsum) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int nwords = c.h * c.wpr;
+    const int per = (nwords + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int w0 = tid * per;
+    unsigned cnt = 0;
+    for (int k = 0; k < per; ++k) {
+        const int wi = w0 + k;
+        if (wi < nwords) { const int y = wi / c.wpr, j = wi - y * c.wpr; cnt += (unsigned)__popc(ipb_bits_starts(bits + (size_t)y * c.wpr, j)); }
+    }
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();                        // wsum may still be read from an earlier call
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, total = 0;
+    for (int i = 0; i < nwarps; ++i) { const unsigned t = wsum[i]; total += t; if (i < warp) before += t; }
+    unsigned run = before + incl - cnt;
+    for (int k = 0; k < per; ++k) {
+        const int wi = w0 + k;
+        if (wi < nwords) {
+            const int y = wi / c.wpr, j = wi - y * c.wpr;
+            base[wi] = (unsigned short)(run < 0xffffu ? run : 0xffffu);
+            run += (unsigned)__popc(ipb_bits_starts(bits + (size_t)y * c.wpr, j));
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+// id of the run that starts at pixel x of row y
+__device__ __forceinline__ unsigned ipb_fas_run_id(const IpbCrop& c, const unsigned* bits, const unsigned short* base, int y, int x) {
+    const int j = x >> 5;
+    const unsigned s = ipb_bits_starts(bits + (size_t)y * c.wpr, j);
+    return (unsigned)base[y * c.wpr + j] + (unsigned)__popc(s & ((1u << (x & 31)) - 1u));
+}
+
+#define IPB_FAS_FOREACH_RUN(c, bits, base, ...)                                                \
+    for (int i_ = threadIdx.x; i_ < (c).h * (c).wpr; i_ += blockDim.x) {                       \
+        const int y = i_ / (c).wpr, j = i_ - y * (c).wpr;                                      \
+        const unsigned* row = (bits) + (size_t)y * (c).wpr;                                    \
+        unsigned s_ = ipb_bits_starts(row, j);                                                 \
+        unsigned id = (base)[i_];                                                              \
+        while (s_) {                                                                           \
+            const int b_ = __ffs((int)s_) - 1;                                                 \
+            s_ &= s_ - 1;                                                                      \
+            const int a = 32 * j + b_;                                                         \
+            const int e = ipb_bits_next_clear(row, a, (c).w);       /* run = [a, e) */         \
+            __VA_ARGS__                                                                        \
+            ++id;                                                                              \
+        }                                                                                      \
+    }
+
+template <int CONN>
+__device__ __forceinline__ void ipb_fas_merge(const IpbCrop& c, const unsigned* bits, const unsigned short* base, unsigned* parent) {
+    IPB_FAS_FOREACH_RUN(c, bits, base, {
+        if (y > 0) {
+            const unsigned* prow = row - c.wpr;
+            int lo = a, hi = e - 1;
+            if (CONN == 8) { lo = a > 0 ? a - 1 : 0; hi = e < c.w ? e : c.w - 1; }
+            int pos = lo;
+            while (pos <= hi) {
+                const int t = ipb_bits_next_set(prow, pos, hi);
+                if (t < 0) break;
+                const int ps = ipb_bits_run_start(prow, t);
+                ipb_fas_union(parent, id, ipb_fas_run_id(c, bits, base, y - 1, ps));
+                pos = ipb_bits_next_clear(prow, t, c.w) + 1;
+            }
+        }
+    })
+}
+
+__global__ void __launch_bounds__(IPB_FAS_THREADS, 2)
+ipb_k_fa_fused_smem(const IpbCrop* __restrict__ crops, const unsigned short* __restrict__ planes, int H, int W,
+                    const float* __restrict__ fa_params, const unsigned* __restrict__ roi_mask,
+                    double min_size, IpbDisk disk, int* __restrict__ L /* run tables */, unsigned* __restrict__ csize /* staged comps */,
+                    int* __restrict__ row_roots, int* __restrict__ row_base, int* __restrict__ crop_count,
+                    unsigned* __restrict__ bw_final, int* __restrict__ labels /* nullable: zeroed here, painted by the gather */,
+                    const int* __restrict__ order)
+{
+    IPB_DYN_SMEM(unsigned, smem);
+    unsigned* A = smem;
+    unsigned* B = A + IPB_FAS_MAXWORDS;
+    unsigned* parent = B + IPB_FAS_MAXWORDS;
+    unsigned* size = parent + IPB_FAS_MAXRUNS;
+    unsigned short* base = reinterpret_cast<unsigned short*>(size + IPB_FAS_MAXRUNS);
+    __shared__ unsigned wsum[IPB_FAS_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int ci = order ? order[blockIdx.x] : (int)blockIdx.x;
+    const IpbCrop c = crops[ci];
+    const int nwords = c.h * c.wpr;
+    const long long npx = (long long)c.w * c.h;
+    if (nwords > IPB_FAS_MAXWORDS || c.w >= 65536 || c.h >= 65536) {              // block-uniform
+        if (tid == 0) crop_count[ci] = -1;
+        return;
+    }
+    IpbCrop cs = c;
+    cs.bit_off = 0;                                         // bit rows live in shared memory from here on
+
+    // ---- 1. threshold & ROI mask -> A
+    ipb_k_fa_threshold_phase(cs, 0, c.h, planes, H, W, fa_params, roi_mask, A);
+    __syncthreads();
+    unsigned* cur = A;
+    unsigned* other = B;
+
+    // ---- 2. remove_small_objects: 4-connected components over run ids, sizes, filter -> other
+    if (min_size > 0) {
+        const unsigned nruns = ipb_fas_index_runs(cs, cur, base, wsum);
+        if (nruns > IPB_FAS_MAXRUNS) { if (tid == 0) crop_count[ci] = -1; return; }
+        for (unsigned i = tid; i < nruns; i += blockDim.x) { parent[i] = i; size[i] = 0u; }
+        __syncthreads();
+        ipb_fas_merge<4>(cs, cur, base, parent);
+        __syncthreads();
+        IPB_FAS_FOREACH_RUN(cs, cur, base, {
+            const unsigned r = ipb_fas_find(parent, id);
+            parent[id] = r;
+            atomicAdd(&size[r], (unsigned)(e - a));
+        })
+        __syncthreads();
+        for (int i = tid; i < nwords; i += blockDim.x) {
+            const int y = i / c.wpr, j = i - y * c.wpr;
+            const unsigned* row = cur + (size_t)y * c.wpr;
+            const unsigned wv = row[j];
+            unsigned keep = 0u, todo = wv;
+            while (todo) {
+                const int b = __ffs((int)todo) - 1;
+                const int x = 32 * j + b;
+                const int a = ipb_bits_run_start(row, x);
+                const unsigned r = parent[ipb_fas_run_id(cs, cur, base, y, a)];      // flattened: the run's root
+                const bool ok = !((double)size[r] < min_size);
+                int e = ipb_bits_next_clear(row, x, c.w);
+                if (e > 32 * j + 32) e = 32 * j + 32;
+                const int nb = e - x;
+                const unsigned seg = (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u)) << b;
+                if (ok) keep |= seg;
+                todo &= ~seg;
+            }
+            other[i] = keep;
+        }
+        __syncthreads();
+        unsigned* t = cur; cur = other; other = t;
+    }
+
+    // ---- 3. binary closing with disk(r): dilation (outside = 0), erosion (outside = 1)
+    if (disk.r > 0) {
+        ipb_k_bits_morph_phase<0>(cs, 0, c.h, cur, disk, other);
+        __syncthreads();
+        ipb_k_bits_morph_phase<1>(cs, 0, c.h, other, disk, cur);
+        __syncthreads();
+    }
+    const unsigned* fin = cur;
+    for (int i = tid; i < nwords; i += blockDim.x) bw_final[(size_t)c.bit_off + i] = fin[i];
+
+    // ---- 4. label: 8-connected components, raster-order ranks
+    const unsigned nruns = ipb_fas_index_runs(cs, fin, base, wsum);
+    if (nruns > IPB_FAS_MAXRUNS || 2ll * nruns > npx) { if (tid == 0) crop_count[ci] = -1; return; }
+    for (unsigned i = tid; i < nruns; i += blockDim.x) parent[i] = i;
+    __syncthreads();
+    ipb_fas_merge<8>(cs, fin, base, parent);
+    __syncthreads();
+    for (unsigned i = tid; i < nruns; i += blockDim.x) {
+        const unsigned r = ipb_fas_find(parent, i);
+        parent[i] = r;
+        size[i] = (r == i) ? 1u : 0u;                       // root flag, turned into the root's rank below
+    }
+    __syncthreads();
+    unsigned nroots;
+    {
+        const unsigned per = (nruns + blockDim.x - 1) / blockDim.x;
+        const unsigned i0 = (unsigned)tid * per;
+        unsigned cnt = 0;
+        for (unsigned k = 0; k < per; ++k) if (i0 + k < nruns) cnt += size[i0 + k];
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int i = 0; i < nwarps; ++i) { const unsigned t = wsum[i]; total += t; if (i < warp) before += t; }
+        unsigned run = before + incl - cnt;
+        for (unsigned k = 0; k < per; ++k) if (i0 + k < nruns) { const unsigned f = size[i0 + k]; size[i0 + k] = run; run += f; }
+        nroots = total;
+        __syncthreads();
+    }
+    if (nroots > IPB_FAS_MAXCOMP || 8ll * nroots > npx) { if (tid == 0) crop_count[ci] = -1; return; }
+
+    // ---- 5. per-adhesion sums (shared accumulators in the bit buffer that is free now) + run table
+    unsigned long long* acc_i = reinterpret_cast<unsigned long long*>(other);        // [MAXCOMP] each: 3 * 4 KB + 2 KB <= 16 KB
+    unsigned long long* acc_y = acc_i + IPB_FAS_MAXCOMP;
+    unsigned long long* acc_x = acc_y + IPB_FAS_MAXCOMP;
+    unsigned* acc_a = reinterpret_cast<unsigned*>(acc_x + IPB_FAS_MAXCOMP);
+    for (unsigned i = tid; i < nroots; i += blockDim.x) { acc_i[i] = 0; acc_y[i] = 0; acc_x[i] = 0; acc_a[i] = 0; }
+    __syncthreads();
+    const unsigned short* img = planes + (size_t)c.plane * H * W;
+    int* Lc = L + c.pix_off;
+    IPB_FAS_FOREACH_RUN(cs, fin, base, {
+        const unsigned rank = size[parent[id]];
+        const unsigned len = (unsigned)(e - a);
+        const unsigned short* irow = img + (size_t)(c.oy + y) * W + c.ox;
+        unsigned long long si = 0;
+        for (int x = a; x < e; ++x) si += irow[x];
+        atomicAdd(&acc_a[rank], len);
+        atomicAdd(&acc_i[rank], si);
+        atomicAdd(&acc_y[rank], (unsigned long long)len * (unsigned long long)y);
+        atomicAdd(&acc_x[rank], (unsigned long long)(a + e - 1) * len / 2ull);
+        Lc[2 * id] = (int)(((unsigned)y << 16) | (unsigned)a);
+        Lc[2 * id + 1] = (int)((len << 16) | rank);
+    })
+    __syncthreads();
+    unsigned* st = csize + c.pix_off;
+    for (unsigned i = tid; i < nroots; i += blockDim.x) {
+        st[8 * i + 0] = (unsigned)acc_i[i]; st[8 * i + 1] = (unsigned)(acc_i[i] >> 32);
+        st[8 * i + 2] = (unsigned)acc_y[i]; st[8 * i + 3] = (unsigned)(acc_y[i] >> 32);
+        st[8 * i + 4] = (unsigned)acc_x[i]; st[8 * i + 5] = (unsigned)(acc_x[i] >> 32);
+        st[8 * i + 6] = acc_a[i]; st[8 * i + 7] = (unsigned)ci;
+    }
+    if (labels) for (long long i = tid; i < npx; i += blockDim.x) labels[c.pix_off + i] = 0;
+    if (tid == 0) {
+        crop_count[ci] = (int)nroots;
+        row_roots[c.row_off] = (int)nruns;
+        row_base[c.row_off] = IPB_FAS_MARK;
+    }
+}
+
+// staged component tables -> the compact table (after the crop scan); optional label map from
+// the run tables.  grid (8, n_crops), 256 threads.  Crops of the global-memory path are skipped.
+__global__ void __launch_bounds__(256)
+ipb_k_fa_gather_smem(const IpbCrop* __restrict__ crops, const int* __restrict__ L, const unsigned* __restrict__ csize,
+                     const int* __restrict__ row_roots, const int* __restrict__ row_base,
+                     const int* __restrict__ crop_count, const int* __restrict__ comp_off, int cap,
+                     IpbComp* __restrict__ comps, int* __restrict__ labels /* nullable, zeroed */)
+{
+    const int ci = blockIdx.y;
+    const IpbCrop c = crops[ci];
+    if (row_base[c.row_off] != IPB_FAS_MARK) return;
+    const int n = crop_count[ci], off = comp_off[ci];
+    const unsigned* st = csize + c.pix_off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (off + i >= cap) break;
+        IpbComp o;
+        o.sum_i = (unsigned long long)st[8 * i] | ((unsigned long long)st[8 * i + 1] << 32);
+        o.sum_y = (unsigned long long)st[8 * i + 2] | ((unsigned long long)st[8 * i + 3] << 32);
+        o.sum_x = (unsigned long long)st[8 * i + 4] | ((unsigned long long)st[8 * i + 5] << 32);
+        o.area = st[8 * i + 6];
+        o.crop = ci;
+        comps[off + i] = o;
+    }
+    if (labels) {
+        const int nruns = row_roots[c.row_off];
+        const int* Lc = L + c.pix_off;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nruns; i += gridDim.x * blockDim.x) {
+            const unsigned p = (unsigned)Lc[2 * i], q = (unsigned)Lc[2 * i + 1];
+            const int y = (int)(p >> 16), a = (int)(p & 0xffffu), len = (int)(q >> 16), rank = (int)(q & 0xffffu);
+            int* lrow = labels + c.pix_off + (size_t)y * c.w + a;
+            for (int k = 0; k < len; ++k) lrow[k] = rank + 1;
+        }
+    }
+}

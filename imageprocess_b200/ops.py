@@ -38,7 +38,7 @@ class RoiMasks:
 
 
 # kernels launched by each C-ABI entry point (memsets not counted)
-KERNELS_PER_CALL = {"ipb_fa_segment": 4,   # fused per-crop path (14 on the one-kernel-per-phase path)
+KERNELS_PER_CALL = {"ipb_fa_segment": 6,   # per-crop shared-memory path (14 on the one-kernel-per-phase path)
                      "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
                     "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
                     "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_region_dilate": 2, "ipb_hist_select": 3, "ipb_hist_planes": 1}

@@ -206,6 +206,23 @@ RASTER_CHECKS = [check_mpl_small_scene, check_mpl_random_polygons, check_sk_crop
                  check_sk_random_polygons, check_fa_fixture_polygons_sk]
 
 
+def check_fa_overflow(eng):
+    """A noisy crop with more adhesions than the shared-memory per-crop kernel stages (512) next
+    to an ordinary one: the first is flagged and finished by the global-memory kernel, the
+    second stays on chip; both bit-exact against the oracle."""
+    rng = np.random.default_rng(77)
+    H, W = 150, 200
+    d = rng.poisson(1000, (H, W)).astype(np.uint16)
+    d[100:140, 120:190] = 400
+    d[110:120, 130:150] = 5000
+    a = rng.poisson(800, (H, W)).astype(np.uint16)
+    big = np.array([[4.5, 3.5], [115.5, 3.5], [115.5, 145.5], [4.5, 145.5]])
+    small = np.array([[121.5, 101.5], [188.5, 101.5], [188.5, 138.5], [121.5, 138.5]])
+    params = {"alpha": 1.0, "min_area_um": 0.0, "max_area_um": 50.0 * 0.112 ** 2, "close_radius": 0, "subtract_bg": False}
+    n = check_fa_batch(eng, params, fa_path=1, frames=[(d, a, [big, small])])
+    return n
+
+
 FA_CASES = [
     {"alpha": 2.0, "min_area_um": 12.5 * 0.112 ** 2, "max_area_um": 300.0 * 0.112 ** 2, "close_radius": 1, "subtract_bg": True},
     {"alpha": 1.0, "min_area_um": 0.0, "max_area_um": 50.0 * 0.112 ** 2, "close_radius": 0, "subtract_bg": False},
@@ -214,7 +231,7 @@ FA_CASES = [
 ]
 
 
-def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168, fa_path=0):
+def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168, fa_path=0, frames=None):
     """FA chain vs the oracle's analyze_fa_crop: bw mask, label image, counts, areas and
     categories bit-exact; float32 mean within REL; CSV rows in the reference's order.
     Thresholds come from exact integer moments; if numpy's pairwise float32 mean/std gives a
@@ -222,9 +239,11 @@ def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168, fa_path=0):
     with the oracle fed OUR stats (north_star: flips limited to pixels within fp32 eps of the
     threshold); the count of such frames is returned."""
     px = 0.112
-    frames = [small_scene(s, H=H, W=W, n_cells=2, blobs=10) for s in seeds]
+    if frames is None:
+        frames = [small_scene(s, H=H, W=W, n_cells=2, blobs=10) for s in seeds]
     planes = np.stack([np.stack([d, a]) for d, a, _ in frames])
     F, C = planes.shape[:2]
+    H, W = planes.shape[2:]
     out = pipeline.fa_batch(eng, eng.mem.from_host(planes), (F, C, H, W), [fr[2] for fr in frames],
                             params, px, channel=0, save_ok_only=False, want_labels=True, fa_path=fa_path)
     cfg = pipeline.fa_um_to_px_config(params, px)
@@ -671,6 +690,7 @@ def check_hist_select_paths(eng):
 
 
 RASTER_CHECKS.append(check_hist_select_paths)
+RASTER_CHECKS.append(check_fa_overflow)
 
 
 def check_edge_cases(eng):

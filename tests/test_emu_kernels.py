@@ -28,7 +28,7 @@ def test_fret_batch(eng, ratio_mode, scope, clip):
     checks.check_fret_batch(eng, ratio_mode, scope, clip)
 
 
-@pytest.mark.parametrize("fa_path", [1, 2], ids=["fused", "phases"])
+@pytest.mark.parametrize("fa_path", [1, 2, 3], ids=["fused-smem", "phases", "fused-global"])
 @pytest.mark.parametrize("params", checks.FA_CASES, ids=lambda p: f"a{p['alpha']}_r{p['close_radius']}")
 def test_fa_batch(eng, params, fa_path):
     checks.check_fa_batch(eng, params, fa_path=fa_path)

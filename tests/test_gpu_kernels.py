@@ -33,7 +33,7 @@ def test_intensity_golden(eng, exp):
     checks.check_intensity_golden(eng, exp)
 
 
-@pytest.mark.parametrize("fa_path", [1, 2], ids=["fused", "phases"])
+@pytest.mark.parametrize("fa_path", [1, 2, 3], ids=["fused-smem", "phases", "fused-global"])
 @pytest.mark.parametrize("params", checks.FA_CASES, ids=lambda p: f"a{p['alpha']}_r{p['close_radius']}")
 def test_fa_batch(eng, params, fa_path):
     checks.check_fa_batch(eng, params, fa_path=fa_path)
