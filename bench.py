@@ -233,12 +233,17 @@ def run_ours(args):
         barrier()
         return ms, d2h
 
+    host = {"submit_s": 0.0, "n": 0}
+
     def loop_resident(steps):
         """Steps over HBM-resident frames; step k+1 is submitted before step k's tables are
         unpacked, as consecutive batches of a time-lapse are in the product."""
         prev, d2h = None, 0
         for _ in range(steps):
+            t0 = time.perf_counter()
             tk = job.submit(planes, polys_pf)
+            host["submit_s"] += time.perf_counter() - t0
+            host["n"] += 1
             if prev is not None:
                 d2h = consume(job.collect(prev))
             prev = tk
@@ -279,7 +284,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches0 = eng.launches
     with ClockSampler(local if rank == 0 else None) as clk:      # one sampler per job, on rank 0's GPU
+        host["submit_s"], host["n"] = 0.0, 0
         ms, d2h = timed(loop_resident, args.steps)
+        host_submit_ms = 1e3 * host["submit_s"] / max(1, host["n"])
         launches = eng.launches - launches0
         # per-kernel CUDA-event times: the same steps once more with the branches of a step
         # serialised on one stream (overlapped kernels cannot be timed one by one)
@@ -337,6 +344,7 @@ def run_ours(args):
                                      "frac_of_peak": value / world * 1e6 * BYTES_PER_PX / 1e9 / peak}
         line["kernels"] = kern
         line["ms_per_step_serialized"] = ms_ser / args.steps
+        line["host_submit_ms_per_step"] = host_submit_ms
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
