@@ -464,10 +464,12 @@ class FrameBatchJob:
         if pl.need_mpl:
             m_pool = self._dev("m_pool", 4 * pl.m_words)
             d_union = self._dev("union", 4 * pl.S * H * self.union_wpr)
-            mem.zero_bytes(d_union, 4 * pl.S * H * self.union_wpr)
-            lib_call("ipb_rasterize_rois", geo.RULE_MPL, NU, tp("m_verts"), tp("vert_off"), tp("m_rect"),
-                     tp("m_rect"), tp("m_org"), tp("uset"), tp("m_moff"), pl.m_max_rows, pl.m_max_wpr,
-                     m_pool.ptr, op("m_area"), d_union.ptr, self.union_wpr, H, mem.stream)
+            # the rasterisers run beside the percentile chain (masked histogram jobs need the union first)
+            with (branch(3) if pl.pq_ok else contextlib.nullcontext()):
+                mem.zero_bytes(d_union, 4 * pl.S * H * self.union_wpr)
+                lib_call("ipb_rasterize_rois", geo.RULE_MPL, NU, tp("m_verts"), tp("vert_off"), tp("m_rect"),
+                         tp("m_rect"), tp("m_org"), tp("uset"), tp("m_moff"), pl.m_max_rows, pl.m_max_wpr,
+                         m_pool.ptr, op("m_area"), d_union.ptr, self.union_wpr, H, mem.stream)
             union_ptr = d_union.ptr
         else:
             union_ptr = None
@@ -492,7 +494,7 @@ class FrameBatchJob:
             d_win = self._dev("hist_winrange", ops.HIST_WIN.itemsize * NH)
             d_cnt = self._dev("hist_cnt", 8 * NH)
             lib_call("ipb_hist_select", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, tp("qjobs"), NQ,
-                     d_hist.ptr, d_hw.ptr, d_win.ptr, d_cnt.ptr, d_hstat.ptr, d_qout.ptr, op("miss"), mem.stream)
+                     d_hw.ptr, d_win.ptr, d_cnt.ptr, d_hstat.ptr, d_qout.ptr, op("miss"), mem.stream)
             lib_call("ipb_scatter_qvalues", d_qout.ptr, tp("qdst"), NQ, op("params"), mem.stream)
         elif NH:
             lib_call("ipb_hist_planes", planes.ptr, H, W, tp("hist_jobs"), NH, tp("passes"), pl.n_passes, int(pl.has_ms),
@@ -508,6 +510,8 @@ class FrameBatchJob:
         if "fa" in st:
             lib_call("ipb_fa_params", d_hstat.ptr, tp("fa_stat_idx"), d_qout.ptr + Q_OUT.itemsize * pl.qidx["fa"],
                      F, H * W, float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, mem.stream)
+
+        mem.join()                                   # masks and per-frame scalars are ready from here on
 
         # ---- focal adhesions
         if "fa" in st and NR and pl.total_px > 0:

@@ -152,12 +152,12 @@ static int ipb_launch_hist_full(const uint16_t* planes, int H, int W, const void
 
 int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
                     const void* passes, int n_passes, const void* qjobs, int n_q,
-                    uint32_t* hist_full, uint32_t* hist_win, void* win, uint64_t* cnt, uint64_t* stats,
+                    uint32_t* hist_win, void* win, uint64_t* cnt, uint64_t* stats,
                     void* qout, uint32_t* miss, void* stream)
 {
     IPB_REQUIRE(n_jobs >= 0 && n_jobs <= 65535 && n_passes >= 0 && n_passes <= 65535, "ipb_hist_select: job count out of range");
     if (n_jobs == 0 || n_passes == 0) return IPB_OK;
-    IPB_REQUIRE(planes && jobs && passes && hist_full && hist_win && win && cnt && stats && miss && H > 0 && W > 0,
+    IPB_REQUIRE(planes && jobs && passes && hist_win && win && cnt && stats && miss && H > 0 && W > 0,
                 "ipb_hist_select: bad argument");
     IPB_REQUIRE(n_q == 0 || (qjobs && qout), "ipb_hist_select: quantile jobs without buffers");
     IPB_REQUIRE((W & 7) == 0 && (((size_t)planes) & 15) == 0, "ipb_hist_select: needs W %% 8 == 0 and 16-byte aligned planes");
@@ -165,7 +165,7 @@ int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int 
     const size_t smem = sizeof(unsigned) * IPB_PQ_SBINS;
     IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_pq_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pq sample smem");
     IPB_LAUNCH(ipb_k_pq_sample, dim3(n_passes), dim3(1024), smem, stream, planes, H, W, (const IpbPlanePass*)passes,
-               (const IpbHistJob*)jobs, (const IpbQJob*)qjobs, n_q, hist_full, hist_win, (IpbHistWin*)win,
+               (const IpbHistJob*)jobs, (const IpbQJob*)qjobs, n_q, hist_win, (IpbHistWin*)win,
                (unsigned long long*)cnt, (unsigned long long*)stats);
     if ((rc = ipb_check_launch("ipb_k_pq_sample"))) return rc;
     // 4 CTAs of 256 threads per SM = 592 resident CTAs; ~4 waves, at least 4 trips of 4 units per thread
@@ -179,11 +179,11 @@ int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int 
     chunks = (U + upc - 1) / upc;
     IPB_LAUNCH(ipb_k_pq_count, dim3((unsigned)chunks, n_passes), dim3(IPB_PQ_THREADS), 0, stream, planes, H, W,
                (const IpbPlanePass*)passes, (const IpbHistJob*)jobs, (const IpbHistWin*)win, (unsigned)upc,
-               hist_full, hist_win, (unsigned long long*)cnt, (unsigned long long*)stats);
+               hist_win, (unsigned long long*)cnt, (unsigned long long*)stats);
     if ((rc = ipb_check_launch("ipb_k_pq_count"))) return rc;
     if (n_q > 0) {
         IPB_LAUNCH(ipb_k_pq_select, dim3(n_q), dim3(256), 0, stream, (const IpbQJob*)qjobs, (const IpbHistWin*)win,
-                   (const unsigned long long*)cnt, hist_win, hist_full, (const unsigned long long*)stats,
+                   (const unsigned long long*)cnt, hist_win, (const unsigned long long*)stats,
                    (IpbQOut*)qout, miss);
         if ((rc = ipb_check_launch("ipb_k_pq_select"))) return rc;
     }

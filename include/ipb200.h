@@ -97,24 +97,23 @@ int ipb_hist_planes(const uint16_t* planes, int H, int W, const void* jobs, int 
 /* Percentiles by sampled windows: the same percentiles as ipb_hist_planes + ipb_hist_quantiles,
  * exact, without the full histograms (a shared-memory atomic per pixel bounds those, not HBM).
  * Per plane pass, a stratified sample of 8-pixel units fixes ONE value window [wlo, whi) that holds
- * every wanted rank with overwhelming probability; one HBM-bound read of the plane counts the
- * pixels below the window in registers and histograms the pixels inside it (2048 bins); the
- * plane's integer moments and a sparse [::k, ::k] job (exact full histogram in hist_full) ride
- * along.  Served roles per pass: one FULL job, one flat-stride job vals[::k] (k in {2, 4, 8}),
+ * every wanted rank with overwhelming probability; one read of the plane counts the pixels below
+ * the window in registers and histograms the pixels inside it (2048 bins); the plane's integer
+ * moments and a sparse [::k, ::k] job (own window from the same sample) ride along.  Served roles per pass: one FULL job, one flat-stride job vals[::k] (k in {2, 4, 8}),
  * one [::k, ::k] job; W % 8 == 0.  *miss (zeroed by the caller) counts quantiles whose rank fell
  * outside the window or whose pass cannot be served: the caller must then repeat with
  * ipb_hist_planes + ipb_hist_quantiles.  Replaces the np.percentile calls of bg_value
  * (Fluor_INT.py:464-485, fret_ratio_builder.py:314-330), pick_epsilon (fret_ratio_builder.py:338)
  * and the FA global statistics (FA_Analyzer.py:984-987).
- * Buffers: hist_full uint32 [n_jobs][65536] (only sparse jobs are written), hist_win uint32
- * [n_jobs][2048], win ipb_hist_win[n_jobs], cnt uint64 [n_jobs], stats uint64 [n_jobs][4]
+ * Buffers: hist_win uint32 [n_jobs][2048], win ipb_hist_win[n_jobs], cnt uint64 [n_jobs],
+ * stats uint64 [n_jobs][4]
  * ({n, sum, sumsq, 0} as in ipb_hist_u16).  No buffer needs clearing by the caller.            */
 typedef struct { int32_t plane, excl_plane1, sat_min, n_jobs; int32_t job[4]; } ipb_plane_pass;
 typedef struct { int32_t wlo, whi, mode, pad; } ipb_hist_win;
 int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int n_jobs,
                     const void* passes /* ipb_plane_pass[] dev */, int n_passes,
                     const void* qjobs /* ipb_q_job[] dev */, int n_q,
-                    uint32_t* hist_full, uint32_t* hist_win, void* win, uint64_t* cnt, uint64_t* stats,
+                    uint32_t* hist_win, void* win, uint64_t* cnt, uint64_t* stats,
                     void* qout /* ipb_q_out[n_q] */, uint32_t* miss, void* stream);
 
 typedef struct {
