@@ -105,6 +105,10 @@ class FrameBatchJob:
         # percentiles by sampled windows (ipb_hist_select) instead of full histograms wherever the
         # plane passes allow it (ops.pq_servable): exact either way
         self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "1"))) if hist_select is None else bool(hist_select)
+        # per-ROI statistics by sampled windows (ipb_region_stats_sw) where the regions allow it; exact
+        # either way (a miss repeats the step with the full-histogram kernels)
+        self.stats_sw = bool(int(os.environ.get("IPB_STATS_SW", "1")))
+        self.rs_ctas = 148 * 4
         self.pq_min_px = 1 << 18     # smaller planes take the full histograms (the sample would be most of the plane)
         self._pin = None
         self.n_roi_px = 0
@@ -257,6 +261,7 @@ class FrameBatchJob:
         NH = pl.NH = hist_jobs.shape[0]
         pl.has_ms = bool((hist_jobs["pattern"] == PAT_MASKED_STRIDE).any())
         pl.pq_ok = False             # set once the plane passes are known
+        pl.rs_sw_ok, pl.rs_stride = False, 0
 
         # params layout (float32): [fret F*4 | int F*Ci | fa F*4]
         Ci = pl.Ci = len(self.int_ch)
@@ -387,6 +392,10 @@ class FrameBatchJob:
                 r["x0"], r["y0"] = mr[:, 0], mr[:, 1]
                 r["w"], r["h"] = mr[:, 2] - mr[:, 0], mr[:, 3] - mr[:, 1]
                 r["wpr"], r["frame"], r["use_and"], r["and_plane"] = m_wpr[uidx], frame, 0, 0
+                # per-ROI statistics by sampled windows (ipb_region_stats_sw): every region must fit a
+                # CTA's scratch slice (rect area bounds the pixel count) and the row-offset table
+                pl.rs_stride = int((r["w"].astype(np.int64) * r["h"]).max())
+                pl.rs_sw_ok = int(r["h"].max()) <= 2048 and pl.rs_stride <= (1 << 18)
         if "fa" in st:
             V("f_verts")[: verts.shape[0]] = fa["local_verts"]
             V("f_erect")[:NU] = fa["erect"]
@@ -512,6 +521,7 @@ class FrameBatchJob:
                      F, H * W, float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, mem.stream)
 
         mem.join()                                   # masks and per-frame scalars are ready from here on
+        use_sw = self.stats_sw and pl.rs_sw_ok and not full_hist
 
         # ---- focal adhesions
         if "fa" in st and NR and pl.total_px > 0:
@@ -542,7 +552,12 @@ class FrameBatchJob:
                 mem.zero_bytes(d_out, O.sections["comp_off"][3], O.sections["comp_off"][0])
         # ---- uint16 per-ROI statistics (side stream)
         with branch(1):
-            if pl.n_u16:
+            if pl.n_u16 and use_sw:
+                d_sc = self._dev("rs_scratch_u16", 4 * pl.rs_stride * self.rs_ctas)
+                lib_call("ipb_region_stats_sw", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, H, W,
+                         planes.ptr, None, op("params"), op("stat_out"), d_sc.ptr, pl.rs_stride, self.rs_ctas,
+                         op("miss"), mem.stream)
+            elif pl.n_u16:
                 lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, None, 0,
                          H, W, planes.ptr, None, op("params"), op("stat_out"), mem.stream)
 
@@ -559,7 +574,12 @@ class FrameBatchJob:
             res.R_roi = ops_view(d_Rroi, np.float32, (F, H, W), mem) if d_Rroi is not None else None
 
         # ---- per-ROI statistics: the float (ratio) jobs first, they are the long ones
-        if pl.n_f32:
+        if pl.n_f32 and use_sw:
+            d_sc = self._dev("rs_scratch_f32", 4 * pl.rs_stride * self.rs_ctas)
+            lib_call("ipb_region_stats_sw", tp("regions"), tp("stat_jobs") + STAT_JOB.itemsize * pl.n_u16, pl.n_f32,
+                     SRC_F32, m_pool.ptr, H, W, None, d_R.ptr, op("params"), op("stat_out"), d_sc.ptr, pl.rs_stride,
+                     self.rs_ctas, op("miss"), mem.stream)
+        elif pl.n_f32:
             lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs") + STAT_JOB.itemsize * pl.n_u16, pl.n_f32,
                      SRC_F32, m_pool.ptr, None, 0, H, W, planes.ptr, d_R.ptr, op("params"), op("stat_out"), mem.stream)
         mem.join()
@@ -721,6 +741,7 @@ class FrameBatchJob:
         roi_px = self.n_roi_px or 0
         n_hist = (2 if "fret" in self.stages else 0) + (len(self.int_ch) if "int" in self.stages else 0) + \
                  (1 if "fa" in self.stages else 0)
+        entry = {"ipb_region_stats_sw": "ipb_region_stats", "ipb_hist_select": "ipb_hist_planes"}.get(entry, entry)
         return {
             "ipb_hist_planes": 2 * px * self._n_hist_planes(),   # every sampled plane read once per launch
             "ipb_fret_pixels": 8 * px,                   # 2 x uint16 in, float32 ratio out

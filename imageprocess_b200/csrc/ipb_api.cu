@@ -296,6 +296,27 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const vo
 }
 
 // ---------------------------------------------------------------- region statistics
+int ipb_region_stats_sw(const void* regions, const void* jobs, int n_jobs, int src, const uint32_t* mask_pool,
+                        int H, int W, const uint16_t* planes, const float* images, const float* bvals, void* out,
+                        uint32_t* scratch, int64_t stride, int n_ctas, uint32_t* miss, void* stream)
+{
+    if (n_jobs <= 0) return IPB_OK;
+    IPB_REQUIRE(src == IPB_SRC_U16 || src == IPB_SRC_F32, "ipb_region_stats_sw: source %d not served", src);
+    IPB_REQUIRE(regions && jobs && mask_pool && out && scratch && miss && stride > 0 && n_ctas > 0 && H > 0 && W > 0,
+                "ipb_region_stats_sw: bad argument");
+    IPB_REQUIRE(src == IPB_SRC_U16 ? planes != nullptr : images != nullptr, "ipb_region_stats_sw: no pixel source");
+    const int grid = n_ctas < n_jobs ? n_ctas : n_jobs;
+    if (src == IPB_SRC_U16)
+        IPB_LAUNCH(ipb_k_region_stats_sw<IPB_SRC_U16>, dim3(grid), dim3(IPB_SW_THREADS), 0, stream, (const IpbRegion*)regions,
+                   (const IpbStatJob*)jobs, n_jobs, mask_pool, H, W, planes, images, bvals, (IpbStatOut*)out, scratch,
+                   (unsigned long long)stride, miss);
+    else
+        IPB_LAUNCH(ipb_k_region_stats_sw<IPB_SRC_F32>, dim3(grid), dim3(IPB_SW_THREADS), 0, stream, (const IpbRegion*)regions,
+                   (const IpbStatJob*)jobs, n_jobs, mask_pool, H, W, planes, images, bvals, (IpbStatOut*)out, scratch,
+                   (unsigned long long)stride, miss);
+    return ipb_check_launch("ipb_k_region_stats_sw");
+}
+
 int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int uniform_src,
                      const uint32_t* mask_pool, const uint32_t* and_bits, int and_wpr, int H, int W,
                      const uint16_t* planes, const float* images, const float* bvals, void* out,

@@ -621,3 +621,5 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         out[job.out[v]] = o;
     }
 }
+
+#include "ipb_roistats_sw.cuh"

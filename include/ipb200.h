@@ -205,6 +205,19 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int unif
                      const uint16_t* planes, const float* images, const float* bvals, void* out,
                      void* stream);
 
+/* The same jobs and outputs as ipb_region_stats for IPB_SRC_U16 / IPB_SRC_F32 regions without an
+ * AND plane, by sampled windows instead of full histograms: persistent 256-thread CTAs (n_ctas of
+ * them, 4 per SM) compact a region's keys into their slice of `scratch` (uint32 [n_ctas][stride],
+ * stride >= the largest region's pixel count), sort a <= 2048-key sample in shared memory, derive
+ * a key window per wanted quantile and resolve the exact ranks with two passes over the keys.
+ * Exact in every case: a job that does not fit (AND plane, > 2048 rows, more pixels than stride, a
+ * rank outside its window) adds to *miss (zeroed by the caller), and the caller repeats the jobs
+ * with ipb_region_stats.  Replaces the per-ROI np.mean / median / std / percentile / min / max
+ * of quantify_stats (Fluor_INT.py:494-507) and quantify_per_roi (fret_ratio_builder.py:342-362). */
+int ipb_region_stats_sw(const void* regions, const void* jobs, int n_jobs, int src, const uint32_t* mask_pool,
+                        int H, int W, const uint16_t* planes, const float* images, const float* bvals,
+                        void* out, uint32_t* scratch, int64_t stride, int n_ctas, uint32_t* miss, void* stream);
+
 /* ------------------------------------------------------------------ focal-adhesion chain
  * Replaces analyze_fa_crop (INT/FA_Analyzer.py:123-195) for a ragged batch of crops in one
  * call: bw = (crop > thr) & mask (146-147); remove_small_objects, 4-connectivity, float
