@@ -103,6 +103,73 @@ __device__ __forceinline__ unsigned ipb_fas_run_id(const IpbCrop& c, const unsig
         }                                                                                      \
     }
 
+// ---- threshold & ROI mask with 128-bit loads.  A warp owns a crop row; lane L reads the aligned
+// 8-pixel unit 4 j0 + L of the frame row (one coalesced 512-byte request covers 7 crop words), turns
+// it into a byte of comparison bits, and lanes 0..6 assemble the crop words from five neighbouring
+// bytes (the crop's left edge is not unit-aligned: shift by ox & 7).  (float)px > thr is evaluated
+// as the equivalent integer test px > floor(thr).
+__device__ __forceinline__ unsigned ipb_fas_unit_bits(const uint4& q, int ithr) {
+    unsigned b = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const unsigned w = t < 4 ? (t < 2 ? q.x : q.y) : (t < 6 ? q.z : q.w);
+        const int v = (int)((t & 1) ? (w >> 16) : (w & 0xffffu));
+        b |= (v > ithr ? 1u : 0u) << t;
+    }
+    return b;
+}
+__device__ __forceinline__ void ipb_fas_threshold(const IpbCrop& c, const unsigned short* __restrict__ planes, int H, int W,
+                                                  const float* __restrict__ fa_params, const unsigned* __restrict__ roi_mask, unsigned* A)
+{
+    const unsigned short* img = planes + (size_t)c.plane * H * W;
+    if ((W & 7) != 0 || (((size_t)img) & 15) != 0) {               // block-uniform: unaligned frames take the scalar phase
+        IpbCrop cs = c;
+        cs.bit_off = 0;
+        ipb_k_fa_threshold_phase(cs, 0, c.h, planes, H, W, fa_params, roi_mask, A);
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const float thr = fa_params[(size_t)c.frame * 4 + 3];
+    int ithr;
+    if (!(thr == thr)) ithr = 65536;                               // NaN: no pixel passes
+    else if (thr < 0.0f) ithr = -1;
+    else if (thr >= 65535.0f) ithr = 65535;
+    else ithr = (int)floorf(thr);
+    const int k0 = c.ox >> 3, s = c.ox & 7;
+    const int nunits = ((c.ox + c.w + 7) >> 3) - k0;
+    const int src = 4 * (lane < 7 ? lane : 0);
+    for (int y = warp; y < c.h; y += nwarps) {
+        const uint4* row = reinterpret_cast<const uint4*>(img + (size_t)(c.oy + y) * W) + k0;
+        const unsigned* mrow = roi_mask + c.mask_off + (size_t)y * c.wpr;
+        for (int j0 = 0; j0 < c.wpr; j0 += 14) {                   // two groups of 7 words, both loads issued first
+            uint4 q[2];
+            bool in[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int unit = 4 * (j0 + 7 * g) + lane;
+                in[g] = (j0 + 7 * g < c.wpr) && unit < nunits;
+                q[g] = make_uint4(0, 0, 0, 0);
+                if (in[g]) q[g] = __ldg(row + unit);
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (j0 + 7 * g >= c.wpr) break;                     // warp-uniform
+                const unsigned byte = in[g] ? ipb_fas_unit_bits(q[g], ithr) : 0u;
+                unsigned long long v = 0;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) v |= (unsigned long long)__shfl_sync(IPB_FULL, byte, src + k) << (8 * k);
+                unsigned word = (unsigned)(v >> s);
+                const int j = j0 + 7 * g + lane;
+                if (lane < 7 && j < c.wpr) {
+                    const int rem = c.w - 32 * j;
+                    if (rem < 32) word &= (1u << rem) - 1u;
+                    A[(size_t)y * c.wpr + j] = word & mrow[j];
+                }
+            }
+        }
+    }
+}
+
 template <int CONN>
 __device__ __forceinline__ void ipb_fas_merge(const IpbCrop& c, const unsigned* bits, const unsigned short* base, unsigned* parent) {
     IPB_FAS_FOREACH_RUN(c, bits, base, {
@@ -150,7 +217,7 @@ ipb_k_fa_fused_smem(const IpbCrop* __restrict__ crops, const unsigned short* __r
     cs.bit_off = 0;                                         // bit rows live in shared memory from here on
 
     // ---- 1. threshold & ROI mask -> A
-    ipb_k_fa_threshold_phase(cs, 0, c.h, planes, H, W, fa_params, roi_mask, A);
+    ipb_fas_threshold(c, planes, H, W, fa_params, roi_mask, A);
     __syncthreads();
     unsigned* cur = A;
     unsigned* other = B;
