@@ -106,8 +106,10 @@ class FrameBatchJob:
         # plane passes allow it (ops.pq_servable): exact either way
         self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "1"))) if hist_select is None else bool(hist_select)
         # per-ROI statistics by sampled windows (ipb_region_stats_sw) where the regions allow it; exact
-        # either way (a miss repeats the step with the full-histogram kernels)
-        self.stats_sw = bool(int(os.environ.get("IPB_STATS_SW", "1")))
+        # either way (a miss repeats the step with the full-histogram kernels).  Measured 3.4x SLOWER
+        # than the histogram kernels on the C4 workload (2.24 vs 0.65 ms per step: ~400 instructions per
+        # pixel in its three passes, profiles/README.md), so it is an option, off by default.
+        self.stats_sw = bool(int(os.environ.get("IPB_STATS_SW", "0")))
         self.rs_ctas = 148 * 4
         self.pq_min_px = 1 << 18     # smaller planes take the full histograms (the sample would be most of the plane)
         self._pin = None

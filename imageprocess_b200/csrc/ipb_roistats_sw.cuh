@@ -25,12 +25,7 @@
 // ipb_k_region_stats, so results are exact in every case.
 #pragma once
 
-#ifdef IPB_EMULATE
-#include <cstdio>
-#define DBG(...) fprintf(stderr, __VA_ARGS__)
-#else
 #define DBG(...)
-#endif
 #define IPB_SW_THREADS 256
 #define IPB_SW_SAMP 2048
 #define IPB_SW_BINS 512
