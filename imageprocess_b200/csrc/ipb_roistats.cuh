@@ -303,27 +303,38 @@ __device__ __forceinline__ void ipb_rs_walk_f32x4(const IpbRsCtx& c, unsigned* s
     }
 }
 
+// block sums: warp partials -> shared memory -> warp 0 folds them with shuffles -> one broadcast
+// value (red: >= 33 entries).  Every thread summing all 32 partials itself cost ~10 % of the
+// uint16 kernel's instructions.
 __device__ __forceinline__ double ipb_block_sum_d(double v, double* red) {
     v = ipb_warp_sum(v);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = (blockDim.x + 31) >> 5;
     __syncthreads();
     if (lane == 0) red[warp] = v;
     __syncthreads();
-    double t = 0.0;
-    const int nw = (blockDim.x + 31) >> 5;
-    for (int i = 0; i < nw; ++i) t += red[i];
-    return t;
+    if (warp == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = ipb_warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
 }
 __device__ __forceinline__ unsigned long long ipb_block_sum_u64(unsigned long long v, unsigned long long* red) {
     v = ipb_warp_sum(v);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = (blockDim.x + 31) >> 5;
     __syncthreads();
     if (lane == 0) red[warp] = v;
     __syncthreads();
-    unsigned long long t = 0;
-    const int nw = (blockDim.x + 31) >> 5;
-    for (int i = 0; i < nw; ++i) t += red[i];
-    return t;
+    if (warp == 0) {
+        unsigned long long t = lane < nw ? red[lane] : 0ull;
+        t = ipb_warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
 }
 
 // f(key) for every measured key: from the shared-memory key store when it holds the whole
@@ -373,9 +384,9 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
 {
     IPB_DYN_SMEM(unsigned, keystore);
     __shared__ IpbRsWalkSh wsh;
-    __shared__ double red_d[32];
-    __shared__ unsigned long long red_u[32];
-    __shared__ unsigned red_k[2][32];
+    __shared__ double red_d[33];
+    __shared__ unsigned long long red_u[33];
+    __shared__ unsigned red_k[2][33];
     __shared__ IpbRsSel sel;
     __shared__ unsigned list_n;
 
@@ -457,7 +468,14 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         __syncthreads();
         if (lane == 0) { red_k[0][warp] = lo_t; red_k[1][warp] = hi_t; }
         __syncthreads();
-        for (int i = 0; i < nwarps; ++i) { kmin = red_k[0][i] < kmin ? red_k[0][i] : kmin; kmax = red_k[1][i] > kmax ? red_k[1][i] : kmax; }
+        if (warp == 0) {
+            unsigned a = lane < nwarps ? red_k[0][lane] : 0xffffffffu, b = lane < nwarps ? red_k[1][lane] : 0u;
+            a = ipb_warp_min(a); b = ipb_warp_max(b);
+            if (lane == 0) { red_k[0][32] = a; red_k[1][32] = b; }
+        }
+        __syncthreads();
+        kmin = red_k[0][32] < kmin ? red_k[0][32] : kmin;
+        kmax = red_k[1][32] > kmax ? red_k[1][32] : kmax;
     };
 
     if (SRC == IPB_SRC_U16 && area > 0 && area <= (unsigned long long)IPB_RS_PACKED_MAX) {

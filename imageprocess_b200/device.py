@@ -138,6 +138,12 @@ class TorchMem:
         wait for every branch opened since the last join()."""
         return _Branch(self, idx)
 
+    def graph(self):
+        """(CUDA graph, capture context): work enqueued inside the context on the current stream
+        (and on branches forked from it) is recorded, not run."""
+        g = self.torch.cuda.CUDAGraph()
+        return g, self.torch.cuda.graph(g, capture_error_mode="thread_local")
+
     def join(self):
         cur = self.torch.cuda.current_stream(self.device)
         for ev in getattr(self, "_pending", []):
