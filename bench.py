@@ -280,6 +280,9 @@ def run_ours(args):
             prev = tk
         return consume(job.collect(prev))
 
+    eng.mem.copy_bytes(planes_b[1], 0, planes, 0, planes.nbytes)
+    for b in planes_b:                  # setup: buffers, plan tables and the CUDA graphs of both input buffers
+        job.prime(b, polys_pf)
     loop_resident(args.warmup)
     torch.cuda.synchronize()
     launches0 = eng.launches

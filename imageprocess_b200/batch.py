@@ -496,6 +496,13 @@ class FrameBatchJob:
         tk.event.record()
         return tk
 
+    def prime(self, planes, polys_per_frame):
+        """Setup for a long run over `planes`' buffer: steps it until both output slots have their
+        CUDA graphs (buffers allocated, kernels loaded, graphs captured), so that the first real
+        step already is one graph launch."""
+        for _ in range(6):
+            self.run(planes, polys_per_frame)
+
     def _enqueue(self, planes, polys_per_frame, full_hist, pl, slot):
         """The stream work of one step (see submit)."""
         eng, mem, F, C, H, W = self.eng, self.mem, self.F, self.C, self.H, self.W
