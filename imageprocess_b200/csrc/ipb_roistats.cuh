@@ -251,16 +251,17 @@ __device__ __forceinline__ void ipb_rs_walk_u16x8(const IpbRsCtx& c, F f) {
 }
 
 // float32 images, same idea with aligned 4-pixel units (one 128-bit load).  The keyed path only
-// needs every region pixel to get ONE slot of the key store, not raster order: a warp reserves the
-// slots of its units with one shared-memory atomic per trip.  f(raw bits, slot).
+// needs every region pixel to get ONE slot of the key store: slots follow the flat unit order
+// (block scan of the per-thread counts once per trip).  f(raw bits, slot).
 template <typename F>
-__device__ __forceinline__ void ipb_rs_walk_f32x4(const IpbRsCtx& c, unsigned* slot_counter, F f) {
+__device__ __forceinline__ void ipb_rs_walk_f32x4(const IpbRsCtx& c, IpbRsWalkSh& sh, F f) {
     const int k0 = c.x0 >> 2, s = c.x0 & 3;
     const unsigned nunits = (unsigned)(((c.x0 + c.w + 3) >> 2) - k0);
     const unsigned total = (unsigned)c.h * nunits;
     const bool fastdiv = (unsigned long long)total * nunits < 0xffffffffull;
     const unsigned magic = (unsigned)((0x100000000ull + nunits - 1) / nunits);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    unsigned run = 0;
     const unsigned trips = (total + 4u * blockDim.x - 1u) / (4u * blockDim.x);          // block-uniform
     for (unsigned trip = 0; trip < trips; ++trip) {
         const unsigned i0 = trip * 4u * blockDim.x + threadIdx.x;
@@ -289,10 +290,15 @@ __device__ __forceinline__ void ipb_rs_walk_f32x4(const IpbRsCtx& c, unsigned* s
         unsigned incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
-        unsigned base = 0;
-        const unsigned wtot = __shfl_sync(IPB_FULL, incl, 31);
-        if (lane == 31 && wtot) base = atomicAdd(slot_counter, wtot);
-        unsigned pos = __shfl_sync(IPB_FULL, base, 31) + incl - cnt;
+        // slots in flat unit order (deterministic: the float64 sums over the key store must not
+        // depend on which warp came first)
+        if (lane == 31) sh.wt[warp] = incl;
+        __syncthreads();
+        unsigned before = 0, tot = 0;
+        for (int i = 0; i < nwarps; ++i) { const unsigned t = sh.wt[i]; tot += t; if (i < warp) before += t; }
+        unsigned pos = run + before + incl - cnt;
+        run += tot;
+        __syncthreads();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (!bits[g]) continue;
@@ -552,9 +558,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
             };
         if (area > 0) {
             if (SRC == IPB_SRC_F32 && !c.androw0 && (W & 3) == 0 && (((size_t)c.f32) & 15) == 0) {   // block-uniform
-                if (tid == 0) list_n = 0u;
-                __syncthreads();
-                ipb_rs_walk_f32x4(c, &list_n, take);
+                ipb_rs_walk_f32x4(c, wsh, take);
             } else {
                 ipb_rs_walk<SRC, true>(c, wsh, take);
             }
