@@ -357,8 +357,14 @@ def run_ours(args):
                                     "sample": f"1 frame of the same workload through the oracle port "
                                               f"(FRET+INT+FA, find_contours skipped), {dt:.1f} s"}
         print(json.dumps(line))
+    # leave without waiting on NCCL / CUDA teardown (a hung shutdown would stall the whole launch):
+    # the line is out, every rank has passed the last barrier
+    sys.stdout.flush()
     if dist is not None:
-        dist.destroy_process_group()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=10)
+        os._exit(0)
 
 
 def main():

@@ -457,9 +457,9 @@ class FrameBatchJob:
         histograms instead of sample-selected windows (automatic after a window miss).
 
         A step whose plan, input buffer and output slot were already seen twice is captured into
-        a CUDA graph (table upload, ~25 launches on four streams, result downloads, the NCCL
-        all-gather of an N-rank job) and replayed from then on: one launch instead of ~60 driver
-        calls from Python."""
+        a CUDA graph (table upload, ~25 launches on four streams, result downloads) and replayed
+        from then on: one launch instead of ~60 driver calls from Python.  The NCCL all-gather of
+        an N-rank job follows eagerly."""
         mem = self.mem
         pl = self._plan_for(polys_per_frame)
         slot = self._slot
@@ -492,6 +492,7 @@ class FrameBatchJob:
             if graphable:
                 self._graphs[key] = (None, (ent[1] if ent else 0) + 1)
             tk = self._enqueue(planes, polys_per_frame, full_hist, pl, slot)
+        self._gather(tk, slot)
         tk.event = mem.event()
         tk.event.record()
         return tk
@@ -655,7 +656,7 @@ class FrameBatchJob:
             mem.download_async(pc_t, d_comps, COMP.itemsize * tk.pc_rows)
         # N > 1 ranks: the packed tables of every rank go to all ranks with ONE NCCL all-gather per
         # step (KBs..MBs over NVLink); rank `gather_dst` also brings the gathered blob to the host
-        tk.gather_np = None
+        tk.gather_np, tk.g_stage = None, None
         if self.dist is not None and self.dist.get_world_size() > 1:
             # every rank sends the same number of bytes: a capacity agreed once per job (max over
             # ranks of 1.25x the first step's need + 64 KiB).  Segment = 32-byte header {arena bytes,
@@ -677,13 +678,23 @@ class FrameBatchJob:
             mem.copy_bytes(d_stage, 32, d_out, 0, O.size)
             if rows_sent:
                 mem.copy_bytes(d_stage, 32 + _al(O.size), d_comps, 0, COMP.itemsize * rows_sent)
-            d_all = self._dev("gather_all", cap * world)
-            mem.all_gather_bytes(d_all, d_stage, cap, self.dist)
-            if self.dist.get_rank() == self.gather_dst:
-                g_np, g_t = self._pinned(f"pin_gather{slot}", cap * world)
-                mem.download_async(g_t, d_all, cap * world)
-                tk.gather_np, tk.gather_pack = g_np, cap
+            tk.g_stage = (d_stage, cap, world)               # the collective itself is issued by _gather()
         return tk
+
+    def _gather(self, tk, slot):
+        """The NCCL all-gather of a step's staged tables and the destination rank's download:
+        always issued eagerly after the step's stream work (a collective inside a replayed CUDA
+        graph left the process group unable to shut down)."""
+        if getattr(tk, "g_stage", None) is None:
+            return
+        mem = self.mem
+        d_stage, cap, world = tk.g_stage
+        d_all = self._dev("gather_all", cap * world)
+        mem.all_gather_bytes(d_all, d_stage, cap, self.dist)
+        if self.dist.get_rank() == self.gather_dst:
+            g_np, g_t = self._pinned(f"pin_gather{slot}", cap * world)
+            mem.download_async(g_t, d_all, cap * world)
+            tk.gather_np, tk.gather_pack = g_np, cap
 
     def collect(self, tk):
         """Waits for a submitted step and unpacks its host tables."""
