@@ -96,6 +96,7 @@ class FrameBatchJob:
         self.want_roi_image, self.want_labels = want_roi_image, want_labels
         self._bufs = {}
         self._plans = {}
+        self._gather_ev = [None, None]   # per output slot: event of the last all-gather that read its staging buffer
         self._graphs = {}           # (plan, input buffer, output slot, full_hist) -> (CUDA graph, ticket template) | (None, times seen)
         self.use_graphs = bool(int(os.environ.get("IPB_GRAPHS", "1")))
         self.window_misses = 0
@@ -464,6 +465,9 @@ class FrameBatchJob:
         pl = self._plan_for(polys_per_frame)
         slot = self._slot
         self._slot ^= 1
+        if self._gather_ev[slot] is not None:                # this slot's staging buffer is free again
+            mem.wait_event(self._gather_ev[slot])
+            self._gather_ev[slot] = None
         key = (id(pl), int(planes.ptr), slot, bool(full_hist))
         graphable = self.use_graphs and hasattr(mem, "graph") and self.eng.prof is None and not pl.host_bg
         ent = self._graphs.get(key) if graphable else None
@@ -656,7 +660,7 @@ class FrameBatchJob:
             mem.download_async(pc_t, d_comps, COMP.itemsize * tk.pc_rows)
         # N > 1 ranks: the packed tables of every rank go to all ranks with ONE NCCL all-gather per
         # step (KBs..MBs over NVLink); rank `gather_dst` also brings the gathered blob to the host
-        tk.gather_np, tk.g_stage = None, None
+        tk.gather_np, tk.g_stage, tk.gather_event = None, None, None
         if self.dist is not None and self.dist.get_world_size() > 1:
             # every rank sends the same number of bytes: a capacity agreed once per job (max over
             # ranks of 1.25x the first step's need + 64 KiB).  Segment = 32-byte header {arena bytes,
@@ -673,7 +677,7 @@ class FrameBatchJob:
             rows_sent = min(tk.pc_rows if fa_ran else 0, (cap - 32 - _al(O.size)) // COMP.itemsize)
             hdr_np, hdr_t = self._pinned(f"pin_ghdr{slot}", 32)
             hdr_np[:32].view(np.int64)[:] = (O.size, rows_sent, 0, 0)
-            d_stage = self._dev("gather_stage", cap)
+            d_stage = self._dev(f"gather_stage{slot}", cap)
             mem.upload_async(d_stage, hdr_t, 32)
             mem.copy_bytes(d_stage, 32, d_out, 0, O.size)
             if rows_sent:
@@ -689,12 +693,17 @@ class FrameBatchJob:
             return
         mem = self.mem
         d_stage, cap, world = tk.g_stage
-        d_all = self._dev("gather_all", cap * world)
-        mem.all_gather_bytes(d_all, d_stage, cap, self.dist)
-        if self.dist.get_rank() == self.gather_dst:
-            g_np, g_t = self._pinned(f"pin_gather{slot}", cap * world)
-            mem.download_async(g_t, d_all, cap * world)
-            tk.gather_np, tk.gather_pack = g_np, cap
+        d_all = self._dev(f"gather_all{slot}", cap * world)
+        # on its own stream: the next step's kernels do not queue behind the collective (which
+        # waits for the slowest rank); staging and receive buffers are per output slot
+        with mem.branch(4, detach=True) as br:
+            mem.all_gather_bytes(d_all, d_stage, cap, self.dist)
+            if self.dist.get_rank() == self.gather_dst:
+                g_np, g_t = self._pinned(f"pin_gather{slot}", cap * world)
+                mem.download_async(g_t, d_all, cap * world)
+                tk.gather_np, tk.gather_pack = g_np, cap
+        tk.gather_event = br.event if br is not None else None
+        self._gather_ev[slot] = tk.gather_event
 
     def collect(self, tk):
         """Waits for a submitted step and unpacks its host tables."""
@@ -703,6 +712,8 @@ class FrameBatchJob:
         NR, NU, NP, Ci = pl.NR, pl.NU, pl.NP, pl.Ci
         P_FRET, P_INT, P_FA = pl.P_FRET, pl.P_INT, pl.P_FA
         tk.event.synchronize()
+        if getattr(tk, "gather_event", None) is not None:
+            tk.gather_event.synchronize()
         OV = lambda name: O.view(tk.pout_np, name)
         if int(OV("miss")[0]) != 0:                        # a sampled window missed a wanted rank: exact rerun
             self.window_misses += 1

@@ -28,8 +28,8 @@ class DevBuf:
 
 
 class _Branch:
-    def __init__(self, mem, idx):
-        self.mem, self.idx = mem, idx
+    def __init__(self, mem, idx, detach=False):
+        self.mem, self.idx, self.detach, self.event = mem, idx, detach, None
 
     def __enter__(self):
         mem, torch = self.mem, self.mem.torch
@@ -48,7 +48,9 @@ class _Branch:
     def __exit__(self, *a):
         ev = self.mem.torch.cuda.Event()
         ev.record(self.s)
-        self.mem.__dict__.setdefault("_pending", []).append(ev)
+        self.event = ev
+        if not self.detach:
+            self.mem.__dict__.setdefault("_pending", []).append(ev)
         return self.ctx.__exit__(*a)
 
 
@@ -132,11 +134,15 @@ class TorchMem:
         self.torch.cuda.current_stream(self.device).synchronize()
 
     # -- side streams: independent branches of one step run concurrently (fork / join by events)
-    def branch(self, idx):
+    def branch(self, idx, detach=False):
         """Context manager: work enqueued inside goes to side stream `idx`, ordered after
         everything enqueued on the current stream so far.  join() makes the current stream
-        wait for every branch opened since the last join()."""
-        return _Branch(self, idx)
+        wait for every branch opened since the last join(); a detached branch is not joined
+        (its .event is the caller's to wait on)."""
+        return _Branch(self, idx, detach)
+
+    def wait_event(self, ev):
+        self.torch.cuda.current_stream(self.device).wait_event(ev)
 
     def graph(self):
         """(CUDA graph, capture context): work enqueued inside the context on the current stream

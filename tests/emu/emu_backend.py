@@ -70,9 +70,12 @@ class NumpyMem:
     def sync(self):
         pass
 
-    def branch(self, idx):
+    def branch(self, idx, detach=False):
         import contextlib
         return contextlib.nullcontext()
+
+    def wait_event(self, ev):
+        pass
 
     def join(self):
         pass
