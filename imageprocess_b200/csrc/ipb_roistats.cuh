@@ -502,10 +502,15 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         double s[IPB_RS_MAXV], q[IPB_RS_MAXV];
 #pragma unroll
         for (int v = 0; v < IPB_RS_MAXV; ++v) { s[v] = 0.0; q[v] = 0.0; }
-        for (unsigned i = tid; i < 32768u; i += blockDim.x) {
+        // every thread owns the 32 consecutive words [32 tid, 32 tid + 32) (rotated start: the lanes
+        // of a warp hit different banks) and keeps their pixel count for the rank location below
+        unsigned mine = 0;
+        for (unsigned ii = 0; ii < 32u; ++ii) {
+            const unsigned i = 32u * (unsigned)tid + ((ii + (unsigned)tid) & 31u);
             const unsigned w = h16[i];
             if (!w) continue;
             const unsigned lo = w & 0xffffu, hi = w >> 16, k0 = 2u * i;
+            mine += lo + hi;
             const unsigned first = lo ? k0 : k0 + 1u, last = hi ? k0 + 1u : k0;
             lo_t = first < lo_t ? first : lo_t;
             hi_t = last > hi_t ? last : hi_t;
@@ -528,7 +533,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         // ranks: the word first, then the low / high counter inside the word
         unsigned long long want[IPB_RS_MAXR];
         for (int r = 0; r < IPB_RS_MAXR; ++r) want[r] = sel.rank[r];
-        ipb_locate_ranks_smem(32768u, 32768u / IPB_RS_THREADS, want, nr, red_u,
+        ipb_locate_ranks_chunks(32768u, 32768u / IPB_RS_THREADS, (unsigned long long)mine, want, nr, red_u,
                       [&](unsigned i) { const unsigned w = h16[i]; return (w & 0xffffu) + (w >> 16); },
                       [&](int r, unsigned i, unsigned inside) { sel.prefix[r] = 2u * i + (inside >= (h16[i] & 0xffffu) ? 1u : 0u); });
         kbase = 0u;                                                // prefixes are absolute keys

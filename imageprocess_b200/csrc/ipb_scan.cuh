@@ -52,19 +52,34 @@ __device__ __forceinline__ void ipb_locate_ranks(unsigned nrows, const unsigned 
 // of the per-thread sums follows, and only the threads whose chunk holds a wanted rank walk
 // their chunk in order.  All threads work in parallel; no warp walks a long serial chain.
 // `per` = counters per thread (nbins <= per * blockDim.x); scan32 = >= 32 words of shared scratch.
+// second half of ipb_locate_ranks_smem for callers that already hold `mine`, the sum of their own
+// chunk [tid * per, tid * per + per) (e.g. from a pass over the bins they had to make anyway)
+template <typename V, typename HIT>
+__device__ __forceinline__ void ipb_locate_ranks_chunks(unsigned nbins, unsigned per, unsigned long long mine,
+                                                        const unsigned long long* want, int nr,
+                                                        unsigned long long* scan32, V value, HIT hit);
+
 template <typename V, typename HIT>
 __device__ __forceinline__ void ipb_locate_ranks_smem(unsigned nbins, unsigned per, const unsigned long long* want,
                                                       int nr, unsigned long long* scan32, V value, HIT hit) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const unsigned c0 = (unsigned)tid * per;
+    const unsigned c0 = (unsigned)threadIdx.x * per;
     unsigned long long mine = 0;
-    const unsigned rot = per ? (unsigned)tid % per : 0u;
+    const unsigned rot = per ? (unsigned)threadIdx.x % per : 0u;
     for (unsigned i = 0; i < per; ++i) {
         unsigned k = i + rot;
         if (k >= per) k -= per;
         const unsigned b = c0 + k;
         if (b < nbins) mine += value(b);
     }
+    ipb_locate_ranks_chunks(nbins, per, mine, want, nr, scan32, value, hit);
+}
+
+template <typename V, typename HIT>
+__device__ __forceinline__ void ipb_locate_ranks_chunks(unsigned nbins, unsigned per, unsigned long long mine,
+                                                        const unsigned long long* want, int nr,
+                                                        unsigned long long* scan32, V value, HIT hit) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const unsigned c0 = (unsigned)tid * per;
     unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(IPB_FULL, incl, o); if (lane >= o) incl += t; }
