@@ -291,12 +291,13 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const vo
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (Ralt)
-        IPB_LAUNCH(ipb_k_fret_pixels<true>, dim3((unsigned)blocks, (unsigned)n_frames), dim3(256), 0, stream, planes, n_frames, H, W,
-                   cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr);
-    else
-        IPB_LAUNCH(ipb_k_fret_pixels<false>, dim3((unsigned)blocks, (unsigned)n_frames), dim3(256), 0, stream, planes, n_frames, H, W,
-                   cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr);
+    const bool plain = !cfg.sat_on && !cfg.use_spectral && !cfg.clip_on;
+#define IPB_FRET_LAUNCH(ALT, PLAIN)                                                                                    \
+    IPB_LAUNCH((ipb_k_fret_pixels<ALT, PLAIN>), dim3((unsigned)blocks, (unsigned)n_frames), dim3(256), 0, stream, planes, \
+               n_frames, H, W, cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr)
+    if (Ralt) { if (plain) IPB_FRET_LAUNCH(true, true); else IPB_FRET_LAUNCH(true, false); }
+    else      { if (plain) IPB_FRET_LAUNCH(false, true); else IPB_FRET_LAUNCH(false, false); }
+#undef IPB_FRET_LAUNCH
     return ipb_check_launch("ipb_k_fret_pixels");
 }
 

@@ -42,16 +42,18 @@ __device__ __forceinline__ float ipb_bgsub(float v, float B, int clip_neg) {
 
 struct IpbFretPx { float R, Ralt, dcorr, acorr; };
 
-template <bool WANT_ALT>
+// PLAIN = no saturation filter, no spectral correction, no ratio clip (the general FRET builder,
+// fret_ratio_builder.py:466-474): those per-pixel tests are compiled out
+template <bool WANT_ALT, bool PLAIN>
 __device__ __forceinline__ IpbFretPx ipb_fret_px(const IpbFretCfg& cfg, const float* fp,
                                                  unsigned dv, unsigned av, unsigned aov) {
     const float fnan = __uint_as_float(0x7fc00000u);
     float d = (float)dv, a = (float)av;
-    if (cfg.sat_on && (d >= cfg.sat_thr || a >= cfg.sat_thr)) { d = fnan; a = fnan; }
+    if (!PLAIN && cfg.sat_on && (d >= cfg.sat_thr || a >= cfg.sat_thr)) { d = fnan; a = fnan; }
     const float dbc = ipb_bgsub(d, fp[IPB_FP_BD], cfg.clip_neg);
     const float abc = ipb_bgsub(a, fp[IPB_FP_BA], cfg.clip_neg);
     float acorr = abc;
-    if (cfg.use_spectral) {
+    if (!PLAIN && cfg.use_spectral) {
         float t = __fsub_rn(abc, __fmul_rn(cfg.alpha, dbc));
         if (cfg.aonly_ch >= 0) {
             const float aobc = ipb_bgsub((float)aov, fp[IPB_FP_BAO], cfg.clip_neg);
@@ -65,7 +67,7 @@ __device__ __forceinline__ IpbFretPx ipb_fret_px(const IpbFretCfg& cfg, const fl
     IpbFretPx o;
     o.R = __fdiv_rn(__fadd_rn(numer, eps), __fadd_rn(denom, eps));
     o.Ralt = WANT_ALT ? __fdiv_rn(__fadd_rn(denom, eps), __fadd_rn(numer, eps)) : 0.0f;
-    if (cfg.clip_on) {
+    if (!PLAIN && cfg.clip_on) {
         if (o.R > cfg.clip_max) o.R = fnan;
         if (WANT_ALT && o.Ralt > cfg.clip_max) o.Ralt = fnan;
     }
@@ -75,7 +77,7 @@ __device__ __forceinline__ IpbFretPx ipb_fret_px(const IpbFretCfg& cfg, const fl
 
 // planes: uint16 [F][n_ch][H][W].  Outputs (any may be null): R, Ralt, Rroi, Dcorr, Acorr,
 // each float32 [F][H][W].  Requires W % 8 == 0 for the vector path (scalar path otherwise).
-template <bool WANT_ALT>
+template <bool WANT_ALT, bool PLAIN>
 __global__ void __launch_bounds__(256)
 ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W, IpbFretCfg cfg,
                   const float* __restrict__ fparams, const unsigned* __restrict__ union_bits, int union_wpr,
@@ -93,7 +95,7 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
         const unsigned short* base = planes + (size_t)f * cfg.n_ch * plane_px;
         const unsigned short* dptr = base + (size_t)cfg.donor_ch * plane_px;
         const unsigned short* aptr = base + (size_t)cfg.acc_ch * plane_px;
-        const bool have_ao = cfg.use_spectral && cfg.aonly_ch >= 0;
+        const bool have_ao = !PLAIN && cfg.use_spectral && cfg.aonly_ch >= 0;
         const unsigned short* optr = have_ao ? base + (size_t)cfg.aonly_ch * plane_px : nullptr;
         const float* fp = fparams + (size_t)f * IPB_FP_STRIDE;
         const long long stride = (long long)gridDim.x * blockDim.x;
@@ -129,7 +131,7 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
                     const unsigned dv = (t & 1) ? (dw[t >> 1] >> 16) : (dw[t >> 1] & 0xffffu);
                     const unsigned av = (t & 1) ? (aw[t >> 1] >> 16) : (aw[t >> 1] & 0xffffu);
                     const unsigned ov = (t & 1) ? (ow[t >> 1] >> 16) : (ow[t >> 1] & 0xffffu);
-                    const IpbFretPx o = ipb_fret_px<WANT_ALT>(cfg, fp, dv, av, ov);
+                    const IpbFretPx o = ipb_fret_px<WANT_ALT, PLAIN>(cfg, fp, dv, av, ov);
                     r[t] = o.R; ra[t] = o.Ralt; dc[t] = o.dcorr; ac[t] = o.acorr;
                     rr[t] = ((ub >> t) & 1u) ? o.R : fnan;
                 }
@@ -150,7 +152,7 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
             const unsigned dv = base[(size_t)cfg.donor_ch * plane_px + p];
             const unsigned av = base[(size_t)cfg.acc_ch * plane_px + p];
             const unsigned ov = (cfg.use_spectral && cfg.aonly_ch >= 0) ? base[(size_t)cfg.aonly_ch * plane_px + p] : 0u;
-            const IpbFretPx o = ipb_fret_px<WANT_ALT>(cfg, fparams + (size_t)f * IPB_FP_STRIDE, dv, av, ov);
+            const IpbFretPx o = ipb_fret_px<WANT_ALT, PLAIN>(cfg, fparams + (size_t)f * IPB_FP_STRIDE, dv, av, ov);
             if (R) R[i] = o.R;
             if (WANT_ALT && Ralt) Ralt[i] = o.Ralt;
             if (Dcorr) Dcorr[i] = o.dcorr;
