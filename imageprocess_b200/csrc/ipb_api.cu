@@ -177,7 +177,7 @@ int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int 
     const unsigned long long upc = (U + chunks - 1) / chunks;
     IPB_REQUIRE(upc < 0xffffffffull, "ipb_hist_select: plane too large");
     chunks = (U + upc - 1) / upc;
-    IPB_LAUNCH(ipb_k_pq_count<true>, dim3((unsigned)chunks, n_passes), dim3(IPB_PQ_THREADS), 0, stream, planes, H, W,
+    IPB_LAUNCH(ipb_k_pq_count, dim3((unsigned)chunks, n_passes), dim3(IPB_PQ_THREADS), 0, stream, planes, H, W,
                (const IpbPlanePass*)passes, (const IpbHistJob*)jobs, (const IpbHistWin*)win, (unsigned)upc,
                hist_win, (unsigned long long*)cnt, (unsigned long long*)stats);
     if ((rc = ipb_check_launch("ipb_k_pq_count"))) return rc;

@@ -253,12 +253,10 @@ __device__ __forceinline__ void ipb_pq_count_unit(const uint4& q, unsigned wlo, 
 // grid (chunks, n_passes), IPB_PQ_THREADS threads; a CTA streams a contiguous band of units with
 // four 128-bit loads in flight per thread.  cnt[job] = pixels below the window; hist_win[job] =
 // the window's bins; stats[job][1..2] = moments of the plane for jobs that asked.
-// EXTRA = passes may want the plane's moments and / or have a sparse job (the FA channel).  One
-// launch of the EXTRA instantiation serves every pass (measured: 188 us per step; one launch per
-// pass kind, each skipping the other's passes, 156 + 68 us -- the plain passes alone stream at
-// 3.9 TB/s, but the two half-empty grids overlap worse than the mixed one).
+// (Measured variants: one instantiation per pass kind -- plain passes alone stream at 3.9 TB/s, but
+// the two half-empty launches took 156 + 68 us against 188 us for this mixed one; a main loop of
+// whole trips without bounds tests behind a per-unit lambda: 231 us.)
 #define IPB_PQ_QCAP 64             // queue entries per warp (at most 31 left over + 32 new)
-template <bool EXTRA>
 __global__ void __launch_bounds__(IPB_PQ_THREADS, 4)
 ipb_k_pq_count(const unsigned short* __restrict__ planes, int H, int W,
                const IpbPlanePass* __restrict__ passes, const IpbHistJob* __restrict__ jobs,
@@ -273,21 +271,20 @@ ipb_k_pq_count(const unsigned short* __restrict__ planes, int H, int W,
     const IpbPlanePass pp = passes[blockIdx.y];
     const IpbPqRoles r = ipb_pq_roles(pp, jobs, W);
     if (!r.ok) return;
-    if (!EXTRA && (r.moments != 0 || r.jP >= 0)) return;    // the plain instantiation serves plain passes only
     const unsigned long long U = ((unsigned long long)H * (unsigned long long)W) >> 3;
     const unsigned long long u_beg = (unsigned long long)blockIdx.x * units_per_chunk;
     if (u_beg >= U) return;
-    const unsigned n_c = (unsigned)(U - u_beg < (unsigned long long)units_per_chunk ? U - u_beg : (unsigned long long)units_per_chunk);
+    unsigned long long u_end = u_beg + units_per_chunk;
+    if (u_end > U) u_end = U;
     const int jw = r.jF >= 0 ? r.jF : r.jS;
     IpbHistWin w; w.wlo = 0; w.whi = 0; w.mode = IPB_PQ_IDLE; w.pad = 0;
     IpbHistWin wP = w;
     if (jw >= 0) w = win[jw];
     if (r.jP >= 0) wP = win[r.jP];
     const bool windowed = w.mode == IPB_PQ_OK;
-    const bool moments = EXTRA && r.moments != 0;
-    const bool sparse = EXTRA && r.jP >= 0 && wP.mode == IPB_PQ_OK;
+    const bool moments = r.moments != 0;
+    const bool sparse = r.jP >= 0 && wP.mode == IPB_PQ_OK;
     if (!windowed && !moments && !sparse) return;
-    // a pass without a usable dense window still streams its plane for the extras: whi = 0 keeps every unit out of the queue
     const unsigned wlo = windowed ? (unsigned)w.wlo : 0u, whi = windowed ? (unsigned)w.whi : 0u;
     const unsigned wloP = sparse ? (unsigned)wP.wlo : 0u, whiP = sparse ? (unsigned)wP.whi : 0u;
     const bool haveF = r.jF >= 0;
@@ -295,7 +292,7 @@ ipb_k_pq_count(const unsigned short* __restrict__ planes, int H, int W,
     if (tid < 5) acc[tid] = 0;
     __syncthreads();
 
-    const uint4* img = reinterpret_cast<const uint4*>(planes + (size_t)pp.plane * H * W) + u_beg;
+    const uint4* img = reinterpret_cast<const uint4*>(planes + (size_t)pp.plane * H * W);
     const unsigned upr = (unsigned)W >> 3;
     // row of a unit: one multiply-high while unit * upr stays below 2^32 (every frame up to 4096^2)
     const bool fastdiv = U * (unsigned long long)upr < 0xffffffffull;
@@ -307,77 +304,68 @@ ipb_k_pq_count(const unsigned short* __restrict__ planes, int H, int W,
     uint4* wq = queue[warp];
     const unsigned lt = (1u << lane) - 1u;
 
-    // one unit: extras, then the queue of units that hold a pixel below whi
-    auto unit = [&](const uint4& q, unsigned rel, bool ok) {
-        if (EXTRA && moments && ok) {
-            const unsigned ws[4] = {q.x, q.y, q.z, q.w};
-            unsigned s = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned a = ws[j] & 0xffffu, b = ws[j] >> 16;
-                s += a + b;
-                s2 += (unsigned long long)a * a;
-                s2 += (unsigned long long)b * b;
-            }
-            s1 += s;
-        }
-        // !ok units were loaded as all-ones: never below whi (<= 32768)
-        const unsigned m = __ballot_sync(IPB_FULL, ipb_pq_min8(q) < whi);
-        if (m) {                                               // warp-uniform
-            if ((m >> lane) & 1u) wq[qn + (unsigned)__popc(m & lt)] = q;
-            qn += (unsigned)__popc(m);
-            __syncwarp();
-            if (qn >= 32u) {
-                const uint4 e = wq[lane];
-                const uint4 rest = wq[32 + lane];
-                __syncwarp();
-                ipb_pq_count_unit(e, wlo, whi, r.pS, haveF, sh, cF, cS);
-                qn -= 32u;
-                if ((unsigned)lane < qn) wq[lane] = rest;
-                __syncwarp();
-            }
-        }
-        if (EXTRA && sparse && ok) {
-            const unsigned long long u = u_beg + rel;
-            const unsigned y = fastdiv ? __umulhi((unsigned)u, mg_upr) : (unsigned)(u / upr);
-            if (y - __umulhi(y, mg_kP) * r.kP == 0u) {                   // y % kP == 0 (y < 2^32 / kP)
-                const unsigned x0 = ((unsigned)(u - (unsigned long long)y * upr)) << 3;
-                const unsigned xm = x0 - __umulhi(x0, mg_kP) * r.kP;
-                unsigned sel = 0;
-                for (unsigned t = xm ? r.kP - xm : 0u; t < 8u; t += r.kP) sel |= 1u << t;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    if (!((sel >> t) & 1u)) continue;
-                    const unsigned v = ipb_pq_px(q, t);
-                    if (v < wloP) ++cP;
-                    else if (v < whiP) atomicAdd(&sh[2 * IPB_PQ_WIN + (int)(v - wloP)], 1u);
-                }
-            }
-        }
-    };
-
-    const unsigned full = n_c - n_c % (4u * IPB_PQ_THREADS);          // whole trips: no bounds tests
-    for (unsigned base = 0; base < full; base += 4u * IPB_PQ_THREADS) {
-        uint4 q[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) q[g] = __ldg(img + base + (unsigned)g * IPB_PQ_THREADS + (unsigned)tid);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) unit(q[g], base + (unsigned)g * IPB_PQ_THREADS + (unsigned)tid, true);
-    }
-    if (full < n_c) {                                                 // block-uniform tail trip
+    for (unsigned long long base = u_beg; base < u_end; base += 4ull * IPB_PQ_THREADS) {      // block-uniform trips
         uint4 q[4];
         bool ok[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            const unsigned rel = full + (unsigned)g * IPB_PQ_THREADS + (unsigned)tid;
-            ok[g] = rel < n_c;
+            const unsigned long long u = base + (unsigned long long)g * IPB_PQ_THREADS + (unsigned)tid;
+            ok[g] = u < u_end;
             q[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            if (ok[g]) q[g] = __ldg(img + rel);
+            if (ok[g]) q[g] = __ldg(img + u);
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) unit(q[g], full + (unsigned)g * IPB_PQ_THREADS + (unsigned)tid, ok[g]);
+        for (int g = 0; g < 4; ++g) {
+            if (moments && ok[g]) {
+                const unsigned ws[4] = {q[g].x, q[g].y, q[g].z, q[g].w};
+                unsigned s = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned a = ws[j] & 0xffffu, b = ws[j] >> 16;
+                    s += a + b;
+                    s2 += (unsigned long long)a * a;
+                    s2 += (unsigned long long)b * b;
+                }
+                s1 += s;
+            }
+            if (windowed) {
+                const bool low = ok[g] && ipb_pq_min8(q[g]) < whi;
+                const unsigned m = __ballot_sync(IPB_FULL, low);
+                if (m) {                                               // warp-uniform
+                    if (low) wq[qn + (unsigned)__popc(m & lt)] = q[g];
+                    qn += (unsigned)__popc(m);
+                    __syncwarp();
+                    if (qn >= 32u) {
+                        const uint4 e = wq[lane];
+                        const uint4 rest = wq[32 + lane];
+                        __syncwarp();
+                        ipb_pq_count_unit(e, wlo, whi, r.pS, haveF, sh, cF, cS);
+                        qn -= 32u;
+                        if ((unsigned)lane < qn) wq[lane] = rest;
+                        __syncwarp();
+                    }
+                }
+            }
+            if (sparse && ok[g]) {
+                const unsigned long long u = base + (unsigned long long)g * IPB_PQ_THREADS + (unsigned)tid;
+                const unsigned y = fastdiv ? __umulhi((unsigned)u, mg_upr) : (unsigned)(u / upr);
+                if (y - __umulhi(y, mg_kP) * r.kP == 0u) {                   // y % kP == 0 (y < 2^32 / kP)
+                    const unsigned x0 = ((unsigned)(u - (unsigned long long)y * upr)) << 3;
+                    const unsigned xm = x0 - __umulhi(x0, mg_kP) * r.kP;
+                    unsigned sel = 0;
+                    for (unsigned t = xm ? r.kP - xm : 0u; t < 8u; t += r.kP) sel |= 1u << t;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (!((sel >> t) & 1u)) continue;
+                        const unsigned v = ipb_pq_px(q[g], t);
+                        if (v < wloP) ++cP;
+                        else if (v < whiP) atomicAdd(&sh[2 * IPB_PQ_WIN + (int)(v - wloP)], 1u);
+                    }
+                }
+            }
+        }
     }
-    if ((unsigned)lane < qn) ipb_pq_count_unit(wq[lane], wlo, whi, r.pS, haveF, sh, cF, cS);
+    if (windowed && (unsigned)lane < qn) ipb_pq_count_unit(wq[lane], wlo, whi, r.pS, haveF, sh, cF, cS);
     __syncthreads();
     // ---- flush: S's window also belongs to F (S is a subset of F)
     if (windowed) {
