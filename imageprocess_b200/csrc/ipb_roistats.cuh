@@ -603,8 +603,12 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
             const bool packable = rb <= 28;
             __syncthreads();
             if (packable) {
+                // most keys share no pass-1 bin with a wanted rank: one bit test on (bin mod 64) rejects them
+                unsigned long long binmask = 0ull;
+                for (int g = 0; g < ng0; ++g) binmask |= 1ull << (gp0[g] & 63u);
                 ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) {
                     const unsigned kp = key - kmin, hi = kp >> rb;
+                    if (!((binmask >> (hi & 63u)) & 1ull)) return;
 #pragma unroll
                     for (int g = 0; g < IPB_RS_MAXR; ++g) {
                         if (hi == gp0[g]) {
