@@ -208,8 +208,8 @@ def run_ours(args):
         N-rank job also the other ranks' gathered tables (their adhesion counts are read here)."""
         batch.fa_table(res, job.fa_cfg)
         if res.gathered is not None:
-            for arena, comps in res.gathered:
-                int(job._plans[next(iter(job._plans))].O.view(arena, "comp_off")[-1])
+            for comp_off in res.gathered_comp_off:          # every rank has its own ROI set / arena layout
+                int(comp_off[-1])
         return res.d2h_bytes
 
     def barrier():

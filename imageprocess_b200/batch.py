@@ -676,7 +676,9 @@ class FrameBatchJob:
                 raise RuntimeError("table arena larger than the agreed gather capacity; pass gather_cap_bytes")
             rows_sent = min(tk.pc_rows if fa_ran else 0, (cap - 32 - _al(O.size)) // COMP.itemsize)
             hdr_np, hdr_t = self._pinned(f"pin_ghdr{slot}", 32)
-            hdr_np[:32].view(np.int64)[:] = (O.size, rows_sent, 0, 0)
+            # ranks may carry different ROI sets, hence different arena layouts: the header names the
+            # section every receiver needs to read the adhesion table (comp_off: offset, entries)
+            hdr_np[:32].view(np.int64)[:] = (O.size, rows_sent, O.sections["comp_off"][0], NR + 1)
             d_stage = self._dev(f"gather_stage{slot}", cap)
             mem.upload_async(d_stage, hdr_t, 32)
             mem.copy_bytes(d_stage, 32, d_out, 0, O.size)
@@ -758,11 +760,13 @@ class FrameBatchJob:
         if tk.gather_np is not None:
             world = self.dist.get_world_size()
             blobs = tk.gather_np[: world * tk.gather_pack].reshape(world, tk.gather_pack)
-            res.gathered = []
+            res.gathered, res.gathered_comp_off = [], []
             for r in range(world):
-                arena_b, rows = (int(v) for v in blobs[r, :16].view(np.int64))
+                arena_b, rows, co_off, co_n = (int(v) for v in blobs[r, :32].view(np.int64))
                 a0 = 32 + _al(arena_b)
-                res.gathered.append((blobs[r, 32: 32 + arena_b], blobs[r, a0: a0 + COMP.itemsize * rows].view(COMP)))
+                arena = blobs[r, 32: 32 + arena_b]
+                res.gathered.append((arena, blobs[r, a0: a0 + COMP.itemsize * rows].view(COMP)))
+                res.gathered_comp_off.append(arena[co_off: co_off + 4 * co_n].view(np.int32))
         return res
 
     def run(self, planes, polys_per_frame, full_hist=False):

@@ -110,6 +110,8 @@ def _job_worker_body(rank, world, port, q):
             O = jr._plans[next(iter(jr._plans))].O
             arena, comps = res.gathered[r]
             ok &= np.array_equal(O.view(arena, "comp_off")[: want.n_rois + 1], want.fa_comp_off)
+            # the header names the section, so a receiver with a different layout can read it too
+            ok &= np.array_equal(res.gathered_comp_off[r], want.fa_comp_off)
             n = int(want.fa_comp_off[-1])
             ok &= np.array_equal(comps[:n], want.fa_comps)
             so = O.view(arena, "stat_out")[: want.int_stat.size].reshape(want.int_stat.shape)
