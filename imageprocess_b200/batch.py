@@ -96,6 +96,7 @@ class FrameBatchJob:
         self.want_roi_image, self.want_labels = want_roi_image, want_labels
         self._bufs = {}
         self._plans = {}
+        self._plan_serial = 0
         self._gather_ev = [None, None]   # per output slot: event of the last all-gather that read its staging buffer
         self._graphs = {}           # (plan, input buffer, output slot, full_hist) -> (CUDA graph, ticket template) | (None, times seen)
         self.use_graphs = bool(int(os.environ.get("IPB_GRAPHS", "1")))
@@ -130,6 +131,8 @@ class FrameBatchJob:
     def _dev(self, name, nbytes):
         b = self._bufs.get(name)
         if b is None or b.nbytes < nbytes:
+            if b is not None:
+                self._graphs.clear()            # captured graphs hold the old buffer's address
             b = self.mem.empty(int(nbytes * 1.25) + 256, np.uint8)
             self._bufs[name] = b
         return b
@@ -137,6 +140,8 @@ class FrameBatchJob:
     def _pinned(self, name, nbytes):
         p = self._bufs.get(name)
         if p is None or p[0].nbytes < nbytes:
+            if p is not None:
+                self._graphs.clear()
             p = self.mem.pinned(int(nbytes * 1.25) + 256, np.uint8)
             self._bufs[name] = p
         return p
@@ -170,8 +175,11 @@ class FrameBatchJob:
         plan = self._plans.get(key)
         if plan is None:
             plan = self._build_plan(set_of_frame, usets)
+            self._plan_serial += 1
+            plan.serial = self._plan_serial      # graphs are keyed by it (an id() can come back after eviction)
             if len(self._plans) >= 4:
-                self._plans.pop(next(iter(self._plans)))
+                old = self._plans.pop(next(iter(self._plans)))
+                self._graphs = {k: v for k, v in self._graphs.items() if k[0] != old.serial}
             self._plans[key] = plan
         return plan
 
@@ -468,7 +476,7 @@ class FrameBatchJob:
         if self._gather_ev[slot] is not None:                # this slot's staging buffer is free again
             mem.wait_event(self._gather_ev[slot])
             self._gather_ev[slot] = None
-        key = (id(pl), int(planes.ptr), slot, bool(full_hist))
+        key = (pl.serial, int(planes.ptr), slot, bool(full_hist))
         graphable = self.use_graphs and hasattr(mem, "graph") and self.eng.prof is None and not pl.host_bg
         ent = self._graphs.get(key) if graphable else None
         if ent is not None and ent[0] is not None:
