@@ -207,7 +207,8 @@ __device__ __forceinline__ unsigned ipb_rs_walk(const IpbRsCtx& c, IpbRsWalkSh& 
 // aligned 8-pixel units.  Every thread takes units (row, unit) of the region's rect in flat order,
 // cuts the unit's 8 mask bits out of the (unaligned) mask row with one funnel shift, and reads the
 // 8 pixels with ONE 128-bit load; four units are in flight per thread.  ~6 instructions per pixel
-// instead of the ~50 of the lane-per-pixel walk (which also serves every other case).  f(value).
+// instead of the ~50 of the lane-per-pixel walk (which also serves every other case).
+// f(value, in_region): called for all 8 pixels of a unit that holds a region pixel.
 template <typename F>
 __device__ __forceinline__ void ipb_rs_walk_u16x8(const IpbRsCtx& c, F f) {
     const int k0 = c.x0 >> 3, s = c.x0 & 7;
@@ -237,14 +238,14 @@ __device__ __forceinline__ void ipb_rs_walk_u16x8(const IpbRsCtx& c, F f) {
                 if (b) q[g] = __ldg(reinterpret_cast<const uint4*>(c.u16 + (size_t)(c.y0 + (int)r) * c.W) + k0 + u);
             }
         }
+        // no per-pixel branch: f(value, 0 / 1) for all 8 pixels of a unit that holds any region pixel
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (!bits[g]) continue;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                if (!((bits[g] >> t) & 1u)) continue;
                 const unsigned w = t < 4 ? (t < 2 ? q[g].x : q[g].y) : (t < 6 ? q[g].z : q[g].w);
-                f((t & 1) ? (w >> 16) : (w & 0xffffu));
+                f((t & 1) ? (w >> 16) : (w & 0xffffu), (bits[g] >> t) & 1u);
             }
         }
     }
@@ -336,6 +337,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     __shared__ unsigned red_k[2][33];
     __shared__ IpbRsSel sel;
     __shared__ unsigned list_n;
+    __shared__ unsigned char gtab[64];
 
     const IpbStatJob job = jobs[blockIdx.x];
     if (job.src != SRC) return;                          // mixed job lists: the other instantiation takes it
@@ -431,7 +433,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
         for (unsigned i = tid; i < 32768u; i += blockDim.x) h16[i] = 0u;
         __syncthreads();
         if (!c.androw0 && (W & 7) == 0 && (((size_t)c.u16) & 15) == 0)                    // block-uniform
-            ipb_rs_walk_u16x8(c, [&](unsigned raw) { atomicAdd(&h16[raw >> 1], 1u << ((raw & 1u) << 4)); });
+            ipb_rs_walk_u16x8(c, [&](unsigned raw, unsigned on) { atomicAdd(&h16[raw >> 1], on << ((raw & 1u) << 4)); });
         else
             ipb_rs_walk<SRC, false>(c, wsh, [&](unsigned raw, unsigned) { atomicAdd(&h16[raw >> 1], 1u << ((raw & 1u) << 4)); });
         n = area;
@@ -603,15 +605,21 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
             const bool packable = rb <= 28;
             __syncthreads();
             if (packable) {
-                // most keys share no pass-1 bin with a wanted rank: one bit test on (bin mod 64) rejects them
-                unsigned long long binmask = 0ull;
-                for (int g = 0; g < ng0; ++g) binmask |= 1ull << (gp0[g] & 63u);
+                // most keys share no pass-1 bin with a wanted rank: gtab[bin mod 64] = the groups whose
+                // bin has that residue (usually none): one shared-memory byte instead of six compares
+                if (tid < 64) {
+                    unsigned mk = 0;
+                    for (int g = 0; g < ng0; ++g) if ((gp0[g] & 63u) == (unsigned)tid) mk |= 1u << g;
+                    gtab[tid] = (unsigned char)mk;
+                }
+                __syncthreads();
                 ipb_rs_foreach_key<SRC>(c, wsh, in_smem, n_slots, k32, k16, [&](unsigned key) {
                     const unsigned kp = key - kmin, hi = kp >> rb;
-                    if (!((binmask >> (hi & 63u)) & 1ull)) return;
-#pragma unroll
-                    for (int g = 0; g < IPB_RS_MAXR; ++g) {
-                        if (hi == gp0[g]) {
+                    unsigned mk = gtab[hi & 63u];
+                    while (mk) {
+                        const int g = __ffs((int)mk) - 1;
+                        mk &= mk - 1u;
+                        if (hi == sel.gprefix[g]) {
                             const unsigned idx = atomicAdd(&list_n, 1u);
                             if (idx < IPB_RS_LISTCAP) list[idx] = ((unsigned)g << 28) | (kp & lowmask);
                         }
