@@ -325,8 +325,9 @@ __device__ __forceinline__ void ipb_k_bits_morph_phase(const IpbCrop& c, int fa_
         for (int dy = -disk.r; dy <= disk.r; ++dy) {
             const int k = disk.halfw[dy + disk.r];
             const unsigned m = ipb_row_word(in, c, y + dy, j, outside);
-            const unsigned l = ipb_row_word(in, c, y + dy, j - 1, outside);
-            const unsigned r = ipb_row_word(in, c, y + dy, j + 1, outside);
+            // the neighbouring words only matter where the disk row is wider than one pixel
+            const unsigned l = k > 0 ? ipb_row_word(in, c, y + dy, j - 1, outside) : 0u;
+            const unsigned r = k > 0 ? ipb_row_word(in, c, y + dy, j + 1, outside) : 0u;
             unsigned v = m;
             for (int sft = 1; sft <= k; ++sft) {
                 const unsigned from_left = (m << sft) | (l >> (32 - sft));     // pixel x - sft

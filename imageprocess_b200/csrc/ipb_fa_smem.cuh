@@ -103,10 +103,10 @@ __device__ __forceinline__ unsigned ipb_fas_run_id(const IpbCrop& c, const unsig
         }                                                                                      \
     }
 
-// ---- threshold & ROI mask with 128-bit loads.  A warp owns a crop row; lane L reads the aligned
-// 8-pixel unit 4 j0 + L of the frame row (one coalesced 512-byte request covers 7 crop words), turns
-// it into a byte of comparison bits, and lanes 0..6 assemble the crop words from five neighbouring
-// bytes (the crop's left edge is not unit-aligned: shift by ox & 7).  (float)px > thr is evaluated
+// ---- threshold & ROI mask with 128-bit loads.  A warp owns a crop row; lane L reads the two aligned
+// 8-pixel units 4 j0 + 2 L, + 1 of the frame row (one pass covers 15 crop words), turns them into 16
+// comparison bits, and lanes 0..14 assemble the crop words from three neighbouring lanes' bits (the
+// crop's left edge is not unit-aligned: shift by ox & 7).  (float)px > thr is evaluated
 // as the equivalent integer test px > floor(thr).
 __device__ __forceinline__ unsigned ipb_fas_unit_bits(const uint4& q, int ithr) {
     unsigned b = 0;
@@ -137,34 +137,27 @@ __device__ __forceinline__ void ipb_fas_threshold(const IpbCrop& c, const unsign
     else ithr = (int)floorf(thr);
     const int k0 = c.ox >> 3, s = c.ox & 7;
     const int nunits = ((c.ox + c.w + 7) >> 3) - k0;
-    const int src = 4 * (lane < 7 ? lane : 0);
+    const int src = 2 * (lane < 15 ? lane : 0);
     for (int y = warp; y < c.h; y += nwarps) {
         const uint4* row = reinterpret_cast<const uint4*>(img + (size_t)(c.oy + y) * W) + k0;
         const unsigned* mrow = roi_mask + c.mask_off + (size_t)y * c.wpr;
-        for (int j0 = 0; j0 < c.wpr; j0 += 14) {                   // two groups of 7 words, both loads issued first
-            uint4 q[2];
-            bool in[2];
+        // a lane takes two adjacent units (16 pixels): one pass of the warp covers 15 crop words
+        for (int j0 = 0; j0 < c.wpr; j0 += 15) {
+            const int unit = 4 * j0 + 2 * lane;
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+            const bool in0 = unit < nunits, in1 = unit + 1 < nunits;
+            if (in0) q0 = __ldg(row + unit);
+            if (in1) q1 = __ldg(row + unit + 1);
+            const unsigned half = (in0 ? ipb_fas_unit_bits(q0, ithr) : 0u) | ((in1 ? ipb_fas_unit_bits(q1, ithr) : 0u) << 8);
+            unsigned long long v = 0;
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int unit = 4 * (j0 + 7 * g) + lane;
-                in[g] = (j0 + 7 * g < c.wpr) && unit < nunits;
-                q[g] = make_uint4(0, 0, 0, 0);
-                if (in[g]) q[g] = __ldg(row + unit);
-            }
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                if (j0 + 7 * g >= c.wpr) break;                     // warp-uniform
-                const unsigned byte = in[g] ? ipb_fas_unit_bits(q[g], ithr) : 0u;
-                unsigned long long v = 0;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) v |= (unsigned long long)__shfl_sync(IPB_FULL, byte, src + k) << (8 * k);
-                unsigned word = (unsigned)(v >> s);
-                const int j = j0 + 7 * g + lane;
-                if (lane < 7 && j < c.wpr) {
-                    const int rem = c.w - 32 * j;
-                    if (rem < 32) word &= (1u << rem) - 1u;
-                    A[(size_t)y * c.wpr + j] = word & mrow[j];
-                }
+            for (int k = 0; k < 3; ++k) v |= (unsigned long long)__shfl_sync(IPB_FULL, half, src + k) << (16 * k);
+            unsigned word = (unsigned)(v >> s);
+            const int j = j0 + lane;
+            if (lane < 15 && j < c.wpr) {
+                const int rem = c.w - 32 * j;
+                if (rem < 32) word &= (1u << rem) - 1u;
+                A[(size_t)y * c.wpr + j] = word & mrow[j];
             }
         }
     }

@@ -222,6 +222,21 @@ def check_fa_overflow(eng):
     return n
 
 
+def check_fa_wide_crop(eng):
+    """A crop wider than one pass of the shared-memory threshold phase (15 words = 480 px), at an
+    odd left edge: the second pass and the unaligned word assembly against the oracle."""
+    rng = np.random.default_rng(5)
+    H, W = 64, 720
+    d = rng.poisson(500, (H, W)).astype(np.uint16)
+    for k in range(40):
+        y, x = int(rng.integers(8, H - 12)), int(rng.integers(20, W - 30))
+        d[y:y + int(rng.integers(2, 6)), x:x + int(rng.integers(3, 14))] += 900
+    a = rng.poisson(300, (H, W)).astype(np.uint16)
+    wide = np.array([[13.5, 4.5], [690.5, 6.5], [701.5, 55.5], [11.5, 57.5]])
+    params = {"alpha": 2.0, "min_area_um": 4.0 * 0.112 ** 2, "max_area_um": 500.0 * 0.112 ** 2, "close_radius": 1, "subtract_bg": True}
+    return check_fa_batch(eng, params, fa_path=1, frames=[(d, a, [wide])])
+
+
 FA_CASES = [
     {"alpha": 2.0, "min_area_um": 12.5 * 0.112 ** 2, "max_area_um": 300.0 * 0.112 ** 2, "close_radius": 1, "subtract_bg": True},
     {"alpha": 1.0, "min_area_um": 0.0, "max_area_um": 50.0 * 0.112 ** 2, "close_radius": 0, "subtract_bg": False},
@@ -782,6 +797,7 @@ def check_hist_select_paths(eng):
 
 RASTER_CHECKS.append(check_hist_select_paths)
 RASTER_CHECKS.append(check_fa_overflow)
+RASTER_CHECKS.append(check_fa_wide_crop)
 
 
 def check_edge_cases(eng):
