@@ -383,6 +383,7 @@ def run_ours(args):
         line["kernels"] = kern
         line["ms_per_step_serialized"] = ms_ser / args.steps
         line["host_submit_ms_per_step"] = host_submit_ms
+        line["window_misses"] = int(job.window_misses)       # steps repeated with full histograms (exact either way)
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()
