@@ -202,7 +202,7 @@ ipb_k_fa_fused_smem(const IpbCrop* __restrict__ crops, const unsigned short* __r
     const IpbCrop c = crops[ci];
     const int nwords = c.h * c.wpr;
     const long long npx = (long long)c.w * c.h;
-    if (nwords > IPB_FAS_MAXWORDS || c.w >= 65536 || c.h >= 65536) {              // block-uniform
+    if (nwords > IPB_FAS_MAXWORDS || c.w > 8192 || c.h >= 65536) {                // block-uniform
         if (tid == 0) crop_count[ci] = -1;
         return;
     }
@@ -296,12 +296,16 @@ ipb_k_fa_fused_smem(const IpbCrop* __restrict__ crops, const unsigned short* __r
     }
     if (nroots > IPB_FAS_MAXCOMP || 8ll * nroots > npx) { if (tid == 0) crop_count[ci] = -1; return; }
 
-    // ---- 5. per-adhesion sums (shared accumulators in the bit buffer that is free now) + run table
-    unsigned long long* acc_i = reinterpret_cast<unsigned long long*>(other);        // [MAXCOMP] each: 3 * 4 KB + 2 KB <= 16 KB
-    unsigned long long* acc_y = acc_i + IPB_FAS_MAXCOMP;
-    unsigned long long* acc_x = acc_y + IPB_FAS_MAXCOMP;
-    unsigned* acc_a = reinterpret_cast<unsigned*>(acc_x + IPB_FAS_MAXCOMP);
-    for (unsigned i = tid; i < nroots; i += blockDim.x) { acc_i[i] = 0; acc_y[i] = 0; acc_x[i] = 0; acc_a[i] = 0; }
+    // ---- 5. per-adhesion sums (shared accumulators in the bit buffer that is free now) + run table.
+    // All accumulators are 32-bit (native shared-memory atomics; 64-bit ones are CAS loops): a run's
+    // intensity sum fits 32 bits (<= 4096 px x 65535) and goes in as two 16-bit halves; the
+    // coordinate sums of a <= 131072-px crop at most 8192 wide stay below 2^30.
+    unsigned* acc_a = other;                                   // [MAXCOMP] each: 5 x 2 KB <= 16 KB
+    unsigned* acc_il = acc_a + IPB_FAS_MAXCOMP;
+    unsigned* acc_ih = acc_il + IPB_FAS_MAXCOMP;
+    unsigned* acc_y = acc_ih + IPB_FAS_MAXCOMP;
+    unsigned* acc_x = acc_y + IPB_FAS_MAXCOMP;
+    for (unsigned i = tid; i < 5u * IPB_FAS_MAXCOMP; i += blockDim.x) acc_a[i] = 0u;
     __syncthreads();
     const unsigned short* img = planes + (size_t)c.plane * H * W;
     int* Lc = L + c.pix_off;
@@ -309,21 +313,23 @@ ipb_k_fa_fused_smem(const IpbCrop* __restrict__ crops, const unsigned short* __r
         const unsigned rank = size[parent[id]];
         const unsigned len = (unsigned)(e - a);
         const unsigned short* irow = img + (size_t)(c.oy + y) * W + c.ox;
-        unsigned long long si = 0;
+        unsigned si = 0;
         for (int x = a; x < e; ++x) si += irow[x];
         atomicAdd(&acc_a[rank], len);
-        atomicAdd(&acc_i[rank], si);
-        atomicAdd(&acc_y[rank], (unsigned long long)len * (unsigned long long)y);
-        atomicAdd(&acc_x[rank], (unsigned long long)(a + e - 1) * len / 2ull);
+        atomicAdd(&acc_il[rank], si & 0xffffu);
+        atomicAdd(&acc_ih[rank], si >> 16);
+        atomicAdd(&acc_y[rank], len * (unsigned)y);
+        atomicAdd(&acc_x[rank], (unsigned)(a + e - 1) * len / 2u);
         Lc[2 * id] = (int)(((unsigned)y << 16) | (unsigned)a);
         Lc[2 * id + 1] = (int)((len << 16) | rank);
     })
     __syncthreads();
     unsigned* st = csize + c.pix_off;
     for (unsigned i = tid; i < nroots; i += blockDim.x) {
-        st[8 * i + 0] = (unsigned)acc_i[i]; st[8 * i + 1] = (unsigned)(acc_i[i] >> 32);
-        st[8 * i + 2] = (unsigned)acc_y[i]; st[8 * i + 3] = (unsigned)(acc_y[i] >> 32);
-        st[8 * i + 4] = (unsigned)acc_x[i]; st[8 * i + 5] = (unsigned)(acc_x[i] >> 32);
+        const unsigned long long si = ((unsigned long long)acc_ih[i] << 16) + acc_il[i];
+        st[8 * i + 0] = (unsigned)si; st[8 * i + 1] = (unsigned)(si >> 32);
+        st[8 * i + 2] = acc_y[i]; st[8 * i + 3] = 0u;
+        st[8 * i + 4] = acc_x[i]; st[8 * i + 5] = 0u;
         st[8 * i + 6] = acc_a[i]; st[8 * i + 7] = (unsigned)ci;
     }
     if (labels) for (long long i = tid; i < npx; i += blockDim.x) labels[c.pix_off + i] = 0;
