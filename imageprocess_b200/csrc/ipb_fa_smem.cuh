@@ -309,20 +309,43 @@ ipb_k_fa_fused_smem(const IpbCrop* __restrict__ crops, const unsigned short* __r
     __syncthreads();
     const unsigned short* img = planes + (size_t)c.plane * H * W;
     int* Lc = L + c.pix_off;
-    IPB_FAS_FOREACH_RUN(cs, fin, base, {
-        const unsigned rank = size[parent[id]];
-        const unsigned len = (unsigned)(e - a);
-        const unsigned short* irow = img + (size_t)(c.oy + y) * W + c.ox;
-        unsigned si = 0;
-        for (int x = a; x < e; ++x) si += irow[x];
-        atomicAdd(&acc_a[rank], len);
-        atomicAdd(&acc_il[rank], si & 0xffffu);
-        atomicAdd(&acc_ih[rank], si >> 16);
-        atomicAdd(&acc_y[rank], len * (unsigned)y);
-        atomicAdd(&acc_x[rank], (unsigned)(a + e - 1) * len / 2u);
-        Lc[2 * id] = (int)(((unsigned)y << 16) | (unsigned)a);
-        Lc[2 * id + 1] = (int)((len << 16) | rank);
-    })
+    // word by word, not run by run: a thread sums at most the 32 pixels of its word's segments, so the
+    // long runs of large adhesions spread over many threads; the run table is only written when the
+    // label map is wanted
+    for (int wi = tid; wi < nwords; wi += blockDim.x) {
+        const int y = wi / c.wpr, j = wi - y * c.wpr;
+        const unsigned* row = fin + (size_t)y * c.wpr;
+        const unsigned wv = row[j];
+        if (!wv) continue;
+        const unsigned starts = ipb_bits_starts(row, j);
+        const unsigned id0 = base[wi];                         // id of the first run that STARTS in this word
+        const unsigned short* irow = img + (size_t)(c.oy + y) * W + c.ox + 32 * j;
+        unsigned todo = wv, k = 0;
+        while (todo) {
+            const int b = __ffs((int)todo) - 1;
+            const unsigned inv = ~wv >> b;                     // bit 0 is clear (the segment starts at b)
+            const int nb = inv ? __ffs((int)inv) - 1 : 32 - b;
+            const unsigned seg = (nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u)) << b;
+            todo &= ~seg;
+            const bool is_start = (starts >> b) & 1u;          // else: the run continues from the previous word (b == 0)
+            const unsigned rid = is_start ? id0 + k : id0 - 1u;
+            k += is_start ? 1u : 0u;
+            const unsigned rank = size[parent[rid]];
+            unsigned si = 0;
+            for (int t = 0; t < nb; ++t) si += irow[b + t];
+            const unsigned len = (unsigned)nb, x0 = (unsigned)(32 * j + b);
+            atomicAdd(&acc_a[rank], len);
+            atomicAdd(&acc_il[rank], si & 0xffffu);
+            atomicAdd(&acc_ih[rank], si >> 16);
+            atomicAdd(&acc_y[rank], len * (unsigned)y);
+            atomicAdd(&acc_x[rank], (2u * x0 + len - 1u) * len / 2u);
+            if (labels && is_start) {
+                const unsigned e = (unsigned)ipb_bits_next_clear(row, (int)x0, c.w);
+                Lc[2 * rid] = (int)(((unsigned)y << 16) | x0);
+                Lc[2 * rid + 1] = (int)(((e - x0) << 16) | rank);
+            }
+        }
+    }
     __syncthreads();
     unsigned* st = csize + c.pix_off;
     for (unsigned i = tid; i < nroots; i += blockDim.x) {
