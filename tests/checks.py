@@ -392,6 +392,44 @@ def check_graph_replay(eng):
 RASTER_CHECKS.append(check_graph_replay)
 
 
+def check_hist_select_distributions(eng):
+    """Percentiles by sampled windows on awkward value distributions -- constant, two-valued,
+    saturated, wide uniform, a bright plane above the 15-bit sample range, a steep ramp -- for
+    several percentiles and strides: the value always equals np.percentile of the float32 copy
+    (directly, or through the full-histogram rerun after a miss)."""
+    from imageprocess_b200 import batch
+    rng = np.random.default_rng(12)
+    H, W = 256, 1024
+    ramp = (np.arange(H * W, dtype=np.int64) * 60000 // (H * W)).reshape(H, W).astype(np.uint16)
+    two = np.where(rng.random((H, W)) < 0.013, 7, 900).astype(np.uint16)
+    planes_list = [
+        np.full((H, W), 1234, np.uint16),
+        two,
+        np.full((H, W), 65535, np.uint16),
+        rng.integers(0, 65536, (H, W)).astype(np.uint16),
+        (rng.poisson(300, (H, W)) + 40000).astype(np.uint16),
+        ramp,
+    ]
+    misses = 0
+    for k in range(0, len(planes_list), 2):
+        planes = np.stack(planes_list[k:k + 2])[None]
+        for p, stride in ((1.0, 4), (0.5, 1), (99.0, 2), (50.0, 8), (100.0, 4)):
+            task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": stride,
+                    "percentile": p, "per_channel_p": False, "ch_p_map": {}}
+            job = batch.FrameBatchJob(eng, planes.shape, stages=("int",), int_task=task, hist_select=True)
+            job.pq_min_px = 0
+            res = job.run(eng.mem.from_host(planes), [[]])
+            assert job._plans[next(iter(job._plans))].pq_ok
+            for ci in range(2):
+                want = port.int_bg_value(planes[0, ci].astype(np.float32), "percentile", p, None, stride)
+                assert float(res.int_bg[0, ci]) == want, (k, p, stride, ci, float(res.int_bg[0, ci]), want)
+            misses += job.window_misses
+    return misses
+
+
+RASTER_CHECKS.append(check_hist_select_distributions)
+
+
 def check_region_stats_streaming(eng):
     """Regions larger than the shared-memory key store (re-walk path) + NaN filtering."""
     from imageprocess_b200 import ops
