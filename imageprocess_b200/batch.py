@@ -19,6 +19,7 @@ dicts for the unchanged pandas writers.
 """
 import hashlib
 import math
+import contextlib
 import copy
 import os
 
@@ -527,7 +528,6 @@ class FrameBatchJob:
         lib_call = eng.call
         # independent branches of the step (FA chain, uint16 region statistics, FRET pass + ratio
         # statistics) go to side streams and meet again before the result download
-        import contextlib
         branch = mem.branch if self.overlap else (lambda i: contextlib.nullcontext())
 
         d_tab = self._dev("d_tables", T.size)

@@ -25,7 +25,6 @@
 // ipb_k_region_stats, so results are exact in every case.
 #pragma once
 
-#define DBG(...)
 #define IPB_SW_THREADS 256
 #define IPB_SW_SAMP 2048
 #define IPB_SW_BINS 512
@@ -263,7 +262,7 @@ ipb_k_region_stats_sw(const IpbRegion* __restrict__ regions, const IpbStatJob* _
                 if (a < 0) { a = 0; klo = 0u; } else klo = sh.samp[a];
                 if (b > (long long)ns_v - 1) { b = (long long)ns_v - 1; khi = IPB_RS_SENTINEL - 1u; } else khi = sh.samp[b];
                 if (b < a) b = a;
-                if (b - a + 2 > IPB_SW_BINS) { sh.missed = 1; DBG("bins job %d i %d a %lld b %lld nsv %u n %llu\n", jb, i, a, b, ns_v, n); }
+                if (b - a + 2 > IPB_SW_BINS) sh.missed = 1;
                 else { sh.wa[i] = (int)a; sh.wT[i] = (int)(b - a); sh.klo[i] = klo; sh.khi[i] = khi; sh.wact[i] = 1; }
             }
             __syncthreads();
@@ -324,7 +323,7 @@ ipb_k_region_stats_sw(const IpbRegion* __restrict__ regions, const IpbStatJob* _
                     }
                     found = __any_sync(IPB_FULL, rr >= incl - mine && rr < incl);
                 }
-                if (!found && lane == 0) { sh.missed = 1; DBG("notfound job %d t %d r %llu below %llu nb %u klo %u khi %u a %d T %d nsv %u n %llu area %u\n", jb, t, r, below, nb, sh.klo[i], sh.khi[i], sh.wa[i], sh.wT[i], sh.ns_v, n, area); }
+                if (!found && lane == 0) sh.missed = 1;
             }
             __syncthreads();
             // next shares prev's bin (the usual case): one list serves both
