@@ -477,7 +477,9 @@ class FrameBatchJob:
         if self._gather_ev[slot] is not None:                # this slot's staging buffer is free again
             mem.wait_event(self._gather_ev[slot])
             self._gather_ev[slot] = None
-        key = (pl.serial, int(planes.ptr), slot, bool(full_hist))
+        # everything the enqueued work depends on besides the (fixed) job parameters
+        key = (pl.serial, int(planes.ptr), slot, bool(full_hist), bool(self.hist_select), bool(self.stats_sw),
+               bool(self.overlap), int(self.fa_path), int(self.pq_min_px), self.dist is not None)
         graphable = self.use_graphs and hasattr(mem, "graph") and self.eng.prof is None and not pl.host_bg
         ent = self._graphs.get(key) if graphable else None
         if ent is not None and ent[0] is not None:
