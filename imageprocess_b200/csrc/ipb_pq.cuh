@@ -240,7 +240,7 @@ ipb_k_pq_sample(const unsigned short* __restrict__ planes, int H, int W,
 __device__ __forceinline__ void ipb_pq_count_unit(const uint4& q, unsigned wlo, unsigned whi, unsigned pS, bool haveF,
                                                   unsigned* sh, unsigned& cF, unsigned& cS) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < 8; ++t) {                     // (a fully predicated variant measured 6 % slower)
         const unsigned v = ipb_pq_px(q, t);
         if (v >= whi) continue;
         const bool inS = (pS >> t) & 1u;

@@ -494,7 +494,7 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
                 if (SRC == IPB_SRC_U16) key = raw;
                 else {
                     const float v = __uint_as_float(raw);
-                    if (isfinite(v)) { key = ipb_f32_key(v); const double d = (double)v; s_t += d; s2_t += d * d; }
+                    if (isfinite(v)) { key = ipb_f32_key(v); const double d = (double)v; s_t += d; if (!in_smem) s2_t += d * d; }
                     else key = IPB_RS_SENTINEL;
                 }
                 if (in_smem) { if (SRC == IPB_SRC_U16) k16[pos] = (unsigned short)key; else k32[pos] = key; }
