@@ -373,6 +373,65 @@ def build_tasks(img_dir, roi_dir, out_root, cfg):
     return tasks, keymap
 
 
+BASE_COLS = ["stage", "time", "roi", "area_px", "bg_mode", "bg_scope", "clip_neg", "bg_stride"]
+
+
+def per_roi_frame(rows_all):
+    """The per_ROI table of save_excel (Fluor_INT.py:728-749): the eight fixed columns, every
+    other column in natural order (ch2_bg, ch2_color, ..., ch10_*), then the four derived index /
+    label columns.  Returns a pandas DataFrame (None when there are no rows)."""
+    import pandas as pd
+    df = pd.DataFrame(rows_all)
+    if df.empty:
+        return None
+    for c in BASE_COLS:
+        if c not in df.columns:
+            df[c] = None
+    dyn = sorted((c for c in df.columns if c not in BASE_COLS), key=common.natural_key)
+    df = df[BASE_COLS + dyn].copy()
+    df["stage_idx"] = [int(re.search(r"S(\d+)", s).group(1)) for s in df["stage"]]
+    if df["time"].notna().any():
+        df["time_idx"] = [int(re.search(r"t(\d+)", tt if isinstance(tt, str) else "t0").group(1)) for tt in df["time"]]
+    else:
+        df["time_idx"] = 0
+    df["roi_lab"] = ["s%dc%d" % (si, r) for si, r in zip(df["stage_idx"], df["roi"])]
+    df["roi_id"] = ["%s_roi%d" % (s, r) for s, r in zip(df["stage"], df["roi"])]
+    return df
+
+
+def save_excel(rows_all, keymap, xls_dir, log=print):
+    """fluor_intensity_perROI.csv (+ .xlsx with the per-channel sheets / time matrices when an
+    Excel engine is installed) exactly as the reference's save_excel lays them out
+    (Fluor_INT.py:728-790)."""
+    df = per_roi_frame(rows_all)
+    if df is None:
+        return None
+    csv_path = os.path.join(xls_dir, "fluor_intensity_perROI.csv")
+    try:
+        import openpyxl  # noqa: F401
+        import pandas as pd
+        xlsx = os.path.join(xls_dir, "fluor_intensity_perROI.xlsx")
+        with pd.ExcelWriter(xlsx, engine="openpyxl") as w:
+            df.to_excel(w, index=False, sheet_name="per_ROI")
+            chans = sorted({int(m.group(1)) for c in df.columns if (m := re.match(r"ch(\d+)_mean", c))})
+            if not any(k[1] is not None for k in keymap):
+                for ch in chans:
+                    keep = [c for c in ["stage", "roi", "roi_id", "area_px"] if c in df.columns] + \
+                           [c for c in df.columns if c.startswith(f"ch{ch}_")]
+                    sub = df[keep].sort_values(["stage", "roi"])
+                    sub.insert(0, "No.", range(1, len(sub) + 1))
+                    sub.to_excel(w, index=False, sheet_name=f"ch{ch}")
+            else:
+                for ch in chans:
+                    for what in ("mean", "median"):
+                        df.pivot(index="time_idx", columns="roi_lab", values=f"ch{ch}_{what}").sort_index() \
+                          .to_excel(w, sheet_name=f"ch{ch}_{what}_matrix")
+    except ImportError:
+        log("[INFO] no Excel engine (openpyxl) installed: wrote the CSV only")
+    df.to_csv(csv_path, index=False)
+    return csv_path
+
+
 def run_headless(img_dir, roi_dir, out_root=None, cfg=None, eng=None, log=print):
     """_run_pipeline without Tk: tasks -> device batches -> RES/xls/fluor_intensity_perROI.csv."""
     out_root = out_root or os.path.join(img_dir, "RES")
@@ -383,7 +442,5 @@ def run_headless(img_dir, roi_dir, out_root=None, cfg=None, eng=None, log=print)
         for line in res.get("logs", []):
             log(line)
     if rows_all and (cfg or {}).get("out_xls", True):
-        xls_dir = ensure_dir(os.path.join(out_root, "xls"))
-        common.write_rows_csv(os.path.join(xls_dir, "fluor_intensity_perROI.csv"), rows_all,
-                              columns=["stage", "time", "roi", "area_px"])
+        save_excel(rows_all, keymap, ensure_dir(os.path.join(out_root, "xls")), log=log)
     return rows_all

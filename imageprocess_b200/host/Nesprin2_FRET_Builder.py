@@ -125,9 +125,50 @@ def run_pipeline(p, eng=None, log=print, frames_per_batch=16):
                     rows_all.append(row)
     if p.get("out_png"):
         log("[SKIP-PNG] figure rendering is host matplotlib code outside the device path")
-    if rows_all and p["out_xls"]:
-        common.write_rows_csv(os.path.join(ensure_dir(os.path.join(res_root, "xls")), "nesprin2_fret_perROI.csv"), rows_all,
-                              columns=["stage", "time", "roi", "area_px", "ratio_mean", "ratio_median", "ratio_std",
-                                       "ratio_p5", "ratio_p95", "ratio_FoverD_mean", "ratio_DoverF_mean",
-                                       "donor_mean", "fret_mean", "eps"])
+    if p["out_xls"]:
+        save_xls(rows_all, ensure_dir(os.path.join(res_root, "xls")), timelapse, log=log)
     return rows_all
+
+
+KEEP_COLS = ["stage", "time", "roi", "area_px", "ratio_mode", "ratio_mean", "ratio_median", "ratio_std", "ratio_p5",
+             "ratio_p95", "ratio_FoverD_mean", "ratio_DoverF_mean", "donor_mean", "fret_mean", "eps", "p", "donor_p",
+             "fret_p", "bg_scope", "bg_mode", "clip_neg", "sat_filter_on", "sat_threshold", "clip_ratio_on",
+             "clip_ratio_max"]
+
+
+def per_roi_frame(rows_all, timelapse):
+    """The table save_xls writes (Nesprin2_FRET_Builder.py:1292-1306): the 25 kept columns in the
+    reference's order, then stage_idx, time_idx, roi_lab."""
+    import re
+    import pandas as pd
+    df = pd.DataFrame(rows_all)
+    if df.empty:
+        return None
+    df = df[[c for c in KEEP_COLS if c in df.columns]].copy()
+    df["stage_idx"] = [int(re.search(r"S(\d+)", s).group(1)) for s in df["stage"]]
+    df["time_idx"] = [int(re.search(r"t(\d+)", tt).group(1)) for tt in df["time"]] if timelapse else 0
+    df["roi_lab"] = ["s%dc%d" % (si, r) for si, r in zip(df["stage_idx"], df["roi"])]
+    return df
+
+
+def save_xls(rows_all, xls_dir, timelapse, log=print):
+    """nesprin2_fret_perROI.csv first, then the .xlsx with the two time matrices when openpyxl is
+    installed (Nesprin2_FRET_Builder.py:1287-1326)."""
+    df = per_roi_frame(rows_all, timelapse)
+    if df is None:
+        log("[warn] no ROI: no metric table")
+        return None
+    df.to_csv(os.path.join(xls_dir, "nesprin2_fret_perROI.csv"), index=False)
+    log("[saved] xls/nesprin2_fret_perROI.csv (CSV)")
+    try:
+        import openpyxl  # noqa: F401
+        import pandas as pd
+        with pd.ExcelWriter(os.path.join(xls_dir, "nesprin2_fret_perROI.xlsx"), engine="openpyxl") as w:
+            df.to_excel(w, index=False, sheet_name="per_ROI")
+            for what in ("mean", "median"):
+                df.pivot(index="time_idx", columns="roi_lab", values=f"ratio_{what}").sort_index() \
+                  .to_excel(w, sheet_name=f"ratio_{what}_matrix")
+        log("[saved] xls/nesprin2_fret_perROI.xlsx (XLSX)")
+    except ModuleNotFoundError:
+        log("[warn] openpyxl not installed: XLSX skipped, CSV only")
+    return df

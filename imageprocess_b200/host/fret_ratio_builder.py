@@ -109,6 +109,49 @@ def run_headless(img_dir, roi_dir, out_root=None, p=None, eng=None, log=print):
         for line in logs:
             log(line)
     if rows_all and p["out_xls"]:
-        common.write_rows_csv(os.path.join(ensure_dir(os.path.join(res_root, "xls")), "fret_ratio_perROI.csv"), rows_all,
-                              columns=["stage", "time", "roi", "area_px"])
+        save_tables(rows_all, bool(p["timelapse"]), ensure_dir(os.path.join(res_root, "xls")), log=log)
+    elif p["out_xls"]:
+        log("[Warn] No ROI \u2192 metric table not generated.")
     return rows_all
+
+
+CSV_COLS = ["stage", "time", "roi", "area_px", "ratio_mean", "ratio_median", "ratio_std", "ratio_p5", "ratio_p95",
+            "donor_mean", "donor_median", "yfret_mean", "yfret_median", "eps", "p", "ratio_mode", "bg_mode"]
+
+
+def per_roi_frame(rows_all, timelapse):
+    """The per_ROI table of _pipeline_thread (fret_ratio_builder.py:980-990): the reference's 17
+    columns in its order, then time_idx, stage_idx, roi_lab."""
+    import re
+    import pandas as pd
+    df = pd.DataFrame(rows_all)
+    df = df[[c for c in CSV_COLS if c in df.columns]].copy()
+    df["time_idx"] = [int(re.search(r"t(\d+)", tt).group(1)) for tt in df["time"]] if timelapse else 0
+    df["stage_idx"] = [int(re.search(r"S(\d+)", s).group(1)) for s in df["stage"]]
+    df["roi_lab"] = ["s%dc%d" % (si, r) for si, r in zip(df["stage_idx"], df["roi"])]
+    return df
+
+
+def save_tables(rows_all, timelapse, xls_dir, log=print):
+    """fret_ratio_perROI.csv, and the .xlsx with the two time matrices when an Excel engine is
+    installed (fret_ratio_builder.py:991-1011)."""
+    df = per_roi_frame(rows_all, timelapse)
+    engine = None
+    for name in ("xlsxwriter", "openpyxl"):
+        try:
+            __import__(name)
+            engine = name
+            break
+        except ImportError:
+            pass
+    if engine:
+        import pandas as pd
+        with pd.ExcelWriter(os.path.join(xls_dir, "fret_ratio_perROI.xlsx"), engine=engine) as w:
+            df.to_excel(w, index=False, sheet_name="per_ROI")
+            for what in ("mean", "median"):
+                df.pivot(index="time_idx", columns="roi_lab", values=f"ratio_{what}").sort_index() \
+                  .to_excel(w, sheet_name=f"ratio_{what}_matrix")
+        log("[Saved] xls/fret_ratio_perROI.xlsx")
+    df.to_csv(os.path.join(xls_dir, "fret_ratio_perROI.csv"), index=False)
+    log("[Saved] xls/fret_ratio_perROI.csv")
+    return df

@@ -60,8 +60,13 @@ def nesprin2_batch(eng, planes, shape, polys_per_frame, p, donor_ch=0, acc_ch=1,
     rim_px, ann_on, ann_in, ann_out = n2_px_params(p)
     scope = p["bg_scope"]
     use_ann = ann_on or scope == "annulus"
-    if use_ann and not ann_on:                        # scope == "annulus" with the option off: radii 0
-        ann_in, ann_out = 0, 0
+    if use_ann:
+        # the radii annulus_mask_from_poly really dilates by (Nesprin2_FRET_Builder.py:419-422): with the
+        # option off and scope == "annulus" the reference passes 0, 0, which it clamps to 1 and 2
+        if not ann_on:
+            ann_in, ann_out = 0, 0
+        ann_in = max(ann_in, 1)
+        ann_out = ann_out if ann_out > ann_in else ann_in + 1
     fd = p["ratio_mode"] == "FRET/Donor"
     spectral = bool(p["use_spectral"])
     clip_neg = bool(p["clip_neg"])
@@ -183,9 +188,9 @@ def nesprin2_batch(eng, planes, shape, polys_per_frame, p, donor_ch=0, acc_ch=1,
 
     # ---- optional annulus background per ROI -> per-ROI ratio re-derivation parameters
     ratio_params = None
+    ring = None
     if use_ann and NR:
-        inner_px = max(ann_in, 1)
-        outer_px = ann_out if ann_out > inner_px else inner_px + 1
+        inner_px, outer_px = ann_in, ann_out          # already clamped; the stored rects are padded by outer_px
         gi, Ri = ops.square_gmax(inner_px)
         go, Ro = ops.square_gmax(outer_px)
         inner = eng.region_dilate(reg, rm.pool, gi, Ri)
@@ -263,7 +268,8 @@ def nesprin2_batch(eng, planes, shape, polys_per_frame, p, donor_ch=0, acc_ch=1,
                             "fret_mean": float(np.float32(so[r, 3]["sum"] / nf)) if nf else math.nan})
             rows_per_frame[f].append(row)
     return {"rows_per_frame": rows_per_frame, "eps": fparams.host()[:, 2].copy(), "fparams": fparams.host(),
-            "images": images, "rim": rim, "union": rm, "has_rois": has_rois, "masks": rm}
+            "images": images, "rim": rim, "union": rm, "has_rois": has_rois, "masks": rm,
+            "ring": ring, "regions": reg}
 
 
 def bits_to_bool(words, H, W):

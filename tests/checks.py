@@ -664,6 +664,8 @@ N2_CASES = [
     {"annulus_on": True, "clip_neg": False, "sat_threshold": 30000.0, "clip_ratio_max": 3.0},
     {"ratio_mode": "Donor/FRET", "annulus_on": True, "ann_in_um": 0.5, "ann_out_um": 1.4, "sat_filter_on": False,
      "clip_ratio_on": False, "rim_um": 0.5},
+    # bg_scope "annulus" with the annulus option off: radii 0, 0 clamped to 1, 2 by annulus_mask_from_poly
+    {"bg_scope": "annulus", "annulus_on": False},
 ]
 
 
@@ -701,6 +703,16 @@ def check_nesprin2_batch(eng, case):
         assert np.array_equal(imgs[3, f], want["Acorr"], equal_nan=True)
         assert np.array_equal(rim[f], want["rim_mask"])
         assert len(out["rows_per_frame"][f]) == len(want["rows"])
+        if out["ring"] is not None:                # annulus masks themselves (annulus_mask_from_poly, :416-427)
+            ring_words, regs = out["ring"].host(), out["regions"]
+            rim_px, ann_on, ann_in, ann_out = nesprin2.n2_px_params(p)
+            for r in np.flatnonzero(regs["frame"] == f):
+                g = regs[r]
+                words = ring_words[g["mask_off"]: g["mask_off"] + g["h"] * g["wpr"]].reshape(g["h"], g["wpr"])
+                got_ring = np.zeros((H, W), bool)
+                got_ring[g["y0"]: g["y0"] + g["h"], g["x0"]: g["x0"] + g["w"]] = bits_to_bool(words, g["h"], g["w"])
+                P = polys[int(np.sum(regs["frame"][:r] == f))]
+                assert np.array_equal(got_ring, port.annulus_mask_from_poly(P, (H, W), ann_in, ann_out)), (f, r)
         for g, w in zip(out["rows_per_frame"][f], want["rows"]):
             assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"], (g["area_px"], w["area_px"])
             for k in ("ratio_median", "ratio_p5", "ratio_p95"):
