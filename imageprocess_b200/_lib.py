@@ -30,7 +30,8 @@ _PROTOS = {
     "ipb_fret_pixels": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ipb_fa_segment": [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
-    "ipb_region_stats": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "ipb_region_stats": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ipb_roi_stats_fused": [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp],
 }
 _PROTOS.update({
     "ipb_region_dilate": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -39,7 +40,6 @@ _PROTOS.update({
     "ipb_crop_normalize": [_vp, _i, _i64, _vp, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp],
     "ipb_eps_from_stat": [_vp, _vp, _i, _f, _vp, _vp],
     "ipb_hist_planes": [_vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
-    "ipb_region_stats_sw": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp],
     "ipb_hist_select": [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 })
 _RESTYPE = {"ipb_last_error": ctypes.c_char_p}

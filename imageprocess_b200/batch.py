@@ -29,7 +29,7 @@ from . import geometry as geo
 from . import ops
 from .ops import (COMP, CROP, FP_BA, FP_BD, FP_STRIDE, FRET_CFG, HIST_JOB, PAT_FULL, PAT_MASKED,
                   PAT_MASKED_STRIDE, PAT_STRIDE1D, PAT_STRIDE2D, Q_JOB, Q_OUT, QK_MEDIAN, QK_PCT,
-                  REGION, SRC_F32, SRC_U16, STAT_JOB, STAT_OUT, q32_of)
+                  REGION, ROI_JOB, SRC_F32, SRC_U16, STAT_JOB, STAT_OUT, q32_of)
 
 _ALIGN = 256
 
@@ -111,12 +111,11 @@ class FrameBatchJob:
         # percentiles by sampled windows (ipb_hist_select) instead of full histograms wherever the
         # plane passes allow it (ops.pq_servable): exact either way
         self.hist_select = bool(int(os.environ.get("IPB_HIST_SELECT", "1"))) if hist_select is None else bool(hist_select)
-        # per-ROI statistics by sampled windows (ipb_region_stats_sw) where the regions allow it; exact
-        # either way (a miss repeats the step with the full-histogram kernels).  Measured 3.4x SLOWER
-        # than the histogram kernels on the C4 workload (2.24 vs 0.65 ms per step: ~400 instructions per
-        # pixel in its three passes, profiles/README.md), so it is an option, off by default.
-        self.stats_sw = bool(int(os.environ.get("IPB_STATS_SW", "0")))
-        self.rs_ctas = 148 * 4
+        # per-ROI statistics: ONE walk of each ROI for both channels and the ratio (ipb_roi_stats_fused,
+        # sampled value windows); the regions it cannot serve are repeated by the full-histogram kernels
+        self.fused_roi = bool(int(os.environ.get("IPB_FUSED_ROI", "1")))
+        self.rf_ctas = ops.RF_CTAS_PER_SM * eng.n_sms()
+        self.roi_fallbacks = 0       # regions repeated by the full-histogram kernels so far
         self.pq_min_px = 1 << 18     # smaller planes take the full histograms (the sample would be most of the plane)
         self._pin = None
         self.n_roi_px = 0
@@ -276,7 +275,6 @@ class FrameBatchJob:
         NH = pl.NH = hist_jobs.shape[0]
         pl.has_ms = bool((hist_jobs["pattern"] == PAT_MASKED_STRIDE).any())
         pl.pq_ok = False             # set once the plane passes are known
-        pl.rs_sw_ok, pl.rs_stride = False, 0
 
         # params layout (float32): [fret F*4 | int F*Ci | fa F*4]
         Ci = pl.Ci = len(self.int_ch)
@@ -342,6 +340,7 @@ class FrameBatchJob:
             for ci, ch in enumerate(self.int_ch):
                 views.setdefault(ch, []).append((P_INT + frame * Ci + ci, clipn, pl.int_col0 + ci, q3))
         rr = np.arange(NR)
+        views_all = {ch: list(vl) for ch, vl in views.items()}
         u16_tmpl = []
         for ch, vl in views.items():
             while vl:
@@ -377,6 +376,48 @@ class FrameBatchJob:
         NS = pl.NS = sj.shape[0]
         pl.n_out = NR * rpr
 
+        # ---- fused ROI jobs (ipb_roi_stats_fused): per region, channel pairs -- the FRET pair with
+        #      its ratio first -- each channel with its views; same output rows as the jobs above,
+        #      which stay as the rerun list for the regions the fused kernel flags
+        fj = []
+        if NR and need_mpl and W % 8 == 0:
+            pairs = []
+            if "fret" in st:
+                pairs.append((self.donor_ch, self.acc_ch, True))
+            rest = [ch for ch in views_all if not ("fret" in st and ch in (self.donor_ch, self.acc_ch))]
+            for i in range(0, len(rest), 2):
+                pairs.append((rest[i], rest[i + 1] if i + 1 < len(rest) else None, False))
+            for c0, c1, ratio in pairs:
+                j = np.zeros(NR, dtype=ROI_JOB)
+                j["region"] = rr
+                j["plane"][:, 0] = frame * C + c0
+                j["plane"][:, 1] = frame * C + c1 if c1 is not None else -1
+                j["bidx"] = -1
+                for slot, ch in enumerate((c0, c1)):
+                    vl = views_all.get(ch, []) if ch is not None else []
+                    if len(vl) > 2:
+                        raise ValueError("more than two views of one channel")
+                    j["n_views"][:, slot] = len(vl)
+                    qs = q3 if any(v[3] is q3 for v in vl) else qmed
+                    j["qkind"][:, slot], j["q32"][:, slot] = qs
+                    for v, (bidx, clipn, out_slot, _) in enumerate(vl):
+                        j["bidx"][:, slot, v] = bidx
+                        j["clip"][:, slot, v] = clipn
+                        j["out"][:, slot, v] = rr * rpr + out_slot
+                if ratio:
+                    j["ratio_on"], j["ratio_out"] = 1, rr * rpr
+                    j["fp_idx"] = P_FRET + frame * FP_STRIDE
+                    j["numer_slot"] = 1 if pl.numer_is_acc else 0
+                    j["ratio_clip_neg"] = int(bool(self.fret_p["clip_neg"]))
+                    j["rqkind"], j["rq32"] = q3
+                fj.append(j[big_first])
+        fj = np.concatenate(fj) if fj else np.zeros(0, dtype=ROI_JOB)
+        NF = pl.NF = fj.shape[0]
+        if NF:
+            mr = m_rect[uidx]
+            rw, rh = (mr[:, 2] - mr[:, 0]).astype(np.int64), (mr[:, 3] - mr[:, 1]).astype(np.int64)
+            pl.rf_stride = int(min(((rw + 16) * rh).max() + 8192, 1 << 18))
+
         passes = ops.plane_passes(hist_jobs)
         pl.n_passes = passes.shape[0]
         pl.pq_ok = bool(pl.n_passes) and self.W % 8 == 0 and self.H * self.W >= self.pq_min_px and \
@@ -386,6 +427,7 @@ class FrameBatchJob:
         T.add("qjobs", Q_JOB, max(NQ, 1))
         T.add("qdst", np.int32, max(NQ, 1))
         T.add("stat_jobs", STAT_JOB, max(NS, 1))
+        T.add("roi_jobs", ROI_JOB, max(NF, 1))
         T.add("fa_stat_idx", np.int32, F)
 
         # ---- fill the pinned table buffer (uploaded with one H2D copy every step)
@@ -407,10 +449,6 @@ class FrameBatchJob:
                 r["x0"], r["y0"] = mr[:, 0], mr[:, 1]
                 r["w"], r["h"] = mr[:, 2] - mr[:, 0], mr[:, 3] - mr[:, 1]
                 r["wpr"], r["frame"], r["use_and"], r["and_plane"] = m_wpr[uidx], frame, 0, 0
-                # per-ROI statistics by sampled windows (ipb_region_stats_sw): every region must fit a
-                # CTA's scratch slice (rect area bounds the pixel count) and the row-offset table
-                pl.rs_stride = int((r["w"].astype(np.int64) * r["h"]).max())
-                pl.rs_sw_ok = int(r["h"].max()) <= 2048 and pl.rs_stride <= (1 << 18)
         if "fa" in st:
             V("f_verts")[: verts.shape[0]] = fa["local_verts"]
             V("f_erect")[:NU] = fa["erect"]
@@ -445,6 +483,8 @@ class FrameBatchJob:
             V("qdst")[:NQ] = qdst
         if NS:
             V("stat_jobs")[:NS] = sj
+        if NF:
+            V("roi_jobs")[:NF] = fj
         if "fa" in st:
             V("fa_stat_idx")[:] = hidx["fa"] + np.arange(F)
 
@@ -456,6 +496,7 @@ class FrameBatchJob:
         O.add("stat_out", STAT_OUT, max(pl.n_out, 1))
         O.add("comp_off", np.int32, NR + 1)
         O.add("miss", np.uint32, 1)
+        O.add("rf_flags", np.uint8, max(NR, 1))
         return pl
 
     # ------------------------------------------------------------------ the step
@@ -478,7 +519,7 @@ class FrameBatchJob:
             mem.wait_event(self._gather_ev[slot])
             self._gather_ev[slot] = None
         # everything the enqueued work depends on besides the (fixed) job parameters
-        key = (pl.serial, int(planes.ptr), slot, bool(full_hist), bool(self.hist_select), bool(self.stats_sw),
+        key = (pl.serial, int(planes.ptr), slot, bool(full_hist), bool(self.hist_select), bool(self.fused_roi),
                bool(self.overlap), int(self.fa_path), int(self.pq_min_px), self.dist is not None)
         graphable = self.use_graphs and hasattr(mem, "graph") and self.eng.prof is None and not pl.host_bg
         ent = self._graphs.get(key) if graphable else None
@@ -590,7 +631,7 @@ class FrameBatchJob:
                      F, H * W, float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, mem.stream)
 
         mem.join()                                   # masks and per-frame scalars are ready from here on
-        use_sw = self.stats_sw and pl.rs_sw_ok and not full_hist
+        use_fused = self.fused_roi and pl.NF > 0
 
         # ---- focal adhesions
         if "fa" in st and NR and pl.total_px > 0:
@@ -619,16 +660,18 @@ class FrameBatchJob:
             fa_ran = False
             if "fa" in st:
                 mem.zero_bytes(d_out, O.sections["comp_off"][3], O.sections["comp_off"][0])
-        # ---- uint16 per-ROI statistics (side stream)
+        # ---- per-ROI statistics (side stream): one walk of each ROI for both channels and the ratio;
+        #      else the uint16 jobs of the full-histogram kernel
         with branch(1):
-            if pl.n_u16 and use_sw:
-                d_sc = self._dev("rs_scratch_u16", 4 * pl.rs_stride * self.rs_ctas)
-                lib_call("ipb_region_stats_sw", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, H, W,
-                         planes.ptr, None, op("params"), op("stat_out"), d_sc.ptr, pl.rs_stride, self.rs_ctas,
-                         op("miss"), mem.stream)
+            if use_fused:
+                d_sc = self._dev("rf_scratch", 4 * pl.rf_stride * self.rf_ctas)
+                d_ctr = self._dev("rf_counter", 256)
+                lib_call("ipb_roi_stats_fused", tp("regions"), NR, tp("roi_jobs"), pl.NF, m_pool.ptr, H, W, planes.ptr,
+                         op("params"), op("stat_out"), d_sc.ptr, pl.rf_stride, self.rf_ctas, d_ctr.ptr, op("rf_flags"),
+                         mem.stream)
             elif pl.n_u16:
                 lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, None, 0,
-                         H, W, planes.ptr, None, op("params"), op("stat_out"), mem.stream)
+                         H, W, planes.ptr, None, op("params"), op("stat_out"), None, mem.stream)
 
         # ---- fused FRET pass
         d_R = None
@@ -642,15 +685,20 @@ class FrameBatchJob:
             res.R = ops_view(d_R, np.float32, (F, H, W), mem)
             res.R_roi = ops_view(d_Rroi, np.float32, (F, H, W), mem) if d_Rroi is not None else None
 
-        # ---- per-ROI statistics: the float (ratio) jobs first, they are the long ones
-        if pl.n_f32 and use_sw:
-            d_sc = self._dev("rs_scratch_f32", 4 * pl.rs_stride * self.rs_ctas)
-            lib_call("ipb_region_stats_sw", tp("regions"), tp("stat_jobs") + STAT_JOB.itemsize * pl.n_u16, pl.n_f32,
-                     SRC_F32, m_pool.ptr, H, W, None, d_R.ptr, op("params"), op("stat_out"), d_sc.ptr, pl.rs_stride,
-                     self.rs_ctas, op("miss"), mem.stream)
+        # ---- per-ROI statistics of the ratio image (full-histogram kernel), or -- after the fused ROI
+        #      kernel -- the rerun of the regions it flagged (usually none: a few CTAs scan the flags)
+        if use_fused:
+            mem.join()
+            if pl.n_u16:
+                lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, None, 0,
+                         H, W, planes.ptr, None, op("params"), op("stat_out"), op("rf_flags"), mem.stream)
+            if pl.n_f32:
+                lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs") + STAT_JOB.itemsize * pl.n_u16, pl.n_f32,
+                         SRC_F32, m_pool.ptr, None, 0, H, W, planes.ptr, d_R.ptr, op("params"), op("stat_out"),
+                         op("rf_flags"), mem.stream)
         elif pl.n_f32:
             lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs") + STAT_JOB.itemsize * pl.n_u16, pl.n_f32,
-                     SRC_F32, m_pool.ptr, None, 0, H, W, planes.ptr, d_R.ptr, op("params"), op("stat_out"), mem.stream)
+                     SRC_F32, m_pool.ptr, None, 0, H, W, planes.ptr, d_R.ptr, op("params"), op("stat_out"), None, mem.stream)
         mem.join()
         if "fa" in st:
             res.fa_rect, res.fa_crops = pl.fa_rect, pl.fa_crops
@@ -732,6 +780,8 @@ class FrameBatchJob:
             return self.run(tk.planes, tk.polys, full_hist=True)
         params = OV("params")[:NP].copy()
         res.d2h_bytes = O.size
+        res.roi_fallbacks = int(np.count_nonzero(OV("rf_flags")[:NR])) if (self.fused_roi and pl.NF) else 0
+        self.roi_fallbacks += res.roi_fallbacks
         if "fret" in st:
             res.fret_params = params[P_FRET: P_FRET + F * FP_STRIDE].reshape(F, FP_STRIDE)
         if "int" in st:
@@ -827,12 +877,16 @@ class FrameBatchJob:
         roi_px = self.n_roi_px or 0
         n_hist = (2 if "fret" in self.stages else 0) + (len(self.int_ch) if "int" in self.stages else 0) + \
                  (1 if "fa" in self.stages else 0)
-        entry = {"ipb_region_stats_sw": "ipb_region_stats", "ipb_hist_select": "ipb_hist_planes"}.get(entry, entry)
+        entry = {"ipb_hist_select": "ipb_hist_planes"}.get(entry, entry)
         return {
             "ipb_hist_planes": 2 * px * self._n_hist_planes(),   # every sampled plane read once per launch
             "ipb_fret_pixels": 8 * px,                   # 2 x uint16 in, float32 ratio out
             # ratio job: float32 under the mask; one uint16 job per measured channel
             "ipb_region_stats": (4 * roi_px if "fret" in self.stages else 0) + 2 * roi_px * len(
+                set(([self.donor_ch, self.acc_ch] if "fret" in self.stages else []) +
+                    (list(self.int_ch) if "int" in self.stages else []))),
+            # one read of both uint16 channels under the mask (the ratio is recomputed, not read)
+            "ipb_roi_stats_fused": 2 * roi_px * len(
                 set(([self.donor_ch, self.acc_ch] if "fret" in self.stages else []) +
                     (list(self.int_ch) if "int" in self.stages else []))),
             "ipb_rasterize_rois": roi_px // 8 + 1,       # bit masks written

@@ -13,6 +13,7 @@
 #include "ipb_raster.cuh"
 #include "ipb_hist.cuh"
 #include "ipb_roistats.cuh"
+#include "ipb_roifused.cuh"
 #include "ipb_fret.cuh"
 #include "ipb_fa.cuh"
 #include "ipb_morph.cuh"
@@ -47,13 +48,14 @@ int ipb_check_launch(const char* what) {
 template <int SRC>
 static int ipb_launch_region_stats(const void* regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
                                    const uint32_t* and_bits, int and_wpr, int H, int W, const uint16_t* planes,
-                                   const float* images, const float* bvals, void* out, void* stream)
+                                   const float* images, const float* bvals, void* out, const uint8_t* only, void* stream)
 {
     const int smem = IPB_RS_SMEM_BYTES;
     IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_region_stats<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "region_stats smem");
-    IPB_LAUNCH(ipb_k_region_stats<SRC>, dim3(n_jobs), dim3(IPB_RS_THREADS), (size_t)smem, stream,
-               (const IpbRegion*)regions, (const IpbStatJob*)jobs, mask_pool, and_bits, and_wpr, H, W,
-               planes, images, bvals, (IpbStatOut*)out, smem);
+    const int grid = (only && n_jobs > 148) ? 148 : n_jobs;       // a rerun of flagged regions: few CTAs scan the list
+    IPB_LAUNCH(ipb_k_region_stats<SRC>, dim3(grid), dim3(IPB_RS_THREADS), (size_t)smem, stream,
+               (const IpbRegion*)regions, (const IpbStatJob*)jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
+               planes, images, bvals, (IpbStatOut*)out, smem, (const unsigned char*)only);
     return ipb_check_launch("ipb_k_region_stats");
 }
 
@@ -297,31 +299,10 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const vo
 }
 
 // ---------------------------------------------------------------- region statistics
-int ipb_region_stats_sw(const void* regions, const void* jobs, int n_jobs, int src, const uint32_t* mask_pool,
-                        int H, int W, const uint16_t* planes, const float* images, const float* bvals, void* out,
-                        uint32_t* scratch, int64_t stride, int n_ctas, uint32_t* miss, void* stream)
-{
-    if (n_jobs <= 0) return IPB_OK;
-    IPB_REQUIRE(src == IPB_SRC_U16 || src == IPB_SRC_F32, "ipb_region_stats_sw: source %d not served", src);
-    IPB_REQUIRE(regions && jobs && mask_pool && out && scratch && miss && stride > 0 && n_ctas > 0 && H > 0 && W > 0,
-                "ipb_region_stats_sw: bad argument");
-    IPB_REQUIRE(src == IPB_SRC_U16 ? planes != nullptr : images != nullptr, "ipb_region_stats_sw: no pixel source");
-    const int grid = n_ctas < n_jobs ? n_ctas : n_jobs;
-    if (src == IPB_SRC_U16)
-        IPB_LAUNCH(ipb_k_region_stats_sw<IPB_SRC_U16>, dim3(grid), dim3(IPB_SW_THREADS), 0, stream, (const IpbRegion*)regions,
-                   (const IpbStatJob*)jobs, n_jobs, mask_pool, H, W, planes, images, bvals, (IpbStatOut*)out, scratch,
-                   (unsigned long long)stride, miss);
-    else
-        IPB_LAUNCH(ipb_k_region_stats_sw<IPB_SRC_F32>, dim3(grid), dim3(IPB_SW_THREADS), 0, stream, (const IpbRegion*)regions,
-                   (const IpbStatJob*)jobs, n_jobs, mask_pool, H, W, planes, images, bvals, (IpbStatOut*)out, scratch,
-                   (unsigned long long)stride, miss);
-    return ipb_check_launch("ipb_k_region_stats_sw");
-}
-
 int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int uniform_src,
                      const uint32_t* mask_pool, const uint32_t* and_bits, int and_wpr, int H, int W,
                      const uint16_t* planes, const float* images, const float* bvals, void* out,
-                     void* stream)
+                     const uint8_t* only, void* stream)
 {
     if (n_jobs <= 0) return IPB_OK;
     IPB_REQUIRE(regions && jobs && mask_pool && out && H > 0 && W > 0, "ipb_region_stats: bad argument");
@@ -332,21 +313,41 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int unif
     if (uniform_src == IPB_SRC_U16 || (uniform_src < 0 && planes)) {
         IPB_REQUIRE(planes, "ipb_region_stats: uint16 jobs need planes");
         rc = ipb_launch_region_stats<IPB_SRC_U16>(regions, jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
-                                                  planes, images, bvals, out, stream);
+                                                  planes, images, bvals, out, only, stream);
         if (rc) return rc;
     }
     if (uniform_src == IPB_SRC_F32 || (uniform_src < 0 && images)) {
         IPB_REQUIRE(images, "ipb_region_stats: float32 jobs need images");
         rc = ipb_launch_region_stats<IPB_SRC_F32>(regions, jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
-                                                  planes, images, bvals, out, stream);
+                                                  planes, images, bvals, out, only, stream);
         if (rc) return rc;
     }
     if (uniform_src == IPB_SRC_RATIO || (uniform_src < 0 && images && bvals)) {
         IPB_REQUIRE(images && bvals, "ipb_region_stats: ratio jobs need images and parameters");
         rc = ipb_launch_region_stats<IPB_SRC_RATIO>(regions, jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
-                                                    planes, images, bvals, out, stream);
+                                                    planes, images, bvals, out, only, stream);
     }
     return rc;
+}
+
+int ipb_roi_stats_fused(const void* regions, int n_regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
+                        int H, int W, const uint16_t* planes, const float* bvals, void* out, uint32_t* scratch,
+                        int64_t stride_words, int n_ctas, uint32_t* counter, uint8_t* flags, void* stream)
+{
+    IPB_REQUIRE(n_regions >= 0 && n_jobs >= 0, "ipb_roi_stats_fused: negative count");
+    IPB_REQUIRE(flags && counter, "ipb_roi_stats_fused: null flags / counter");
+    IPB_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), (cudaStream_t)stream), "memset counter");
+    if (n_regions > 0) IPB_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_regions, (cudaStream_t)stream), "memset flags");
+    if (n_jobs == 0) return IPB_OK;
+    IPB_REQUIRE(regions && jobs && mask_pool && planes && bvals && out && scratch && stride_words > 0 && n_ctas > 0 &&
+                H > 0 && W > 0, "ipb_roi_stats_fused: bad argument");
+    const int smem = IPB_RF_SMEM_BYTES;
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_roi_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "roi_fused smem");
+    const int grid = n_ctas < n_jobs ? n_ctas : n_jobs;
+    IPB_LAUNCH(ipb_k_roi_fused, dim3(grid), dim3(IPB_RF_THREADS), (size_t)smem, stream, (const IpbRegion*)regions,
+               (const IpbRoiJob*)jobs, n_jobs, mask_pool, H, W, planes, bvals, (IpbStatOut*)out, scratch,
+               (unsigned long long)stride_words, counter, (unsigned char*)flags);
+    return ipb_check_launch("ipb_k_roi_fused");
 }
 
 // ---------------------------------------------------------------- focal-adhesion chain
@@ -524,6 +525,7 @@ int ipb_sizeof(int what)
         case 9: return (int)sizeof(IpbCropJob);
         case 10: return (int)sizeof(IpbPlanePass);
         case 11: return (int)sizeof(IpbHistWin);
+        case 12: return (int)sizeof(IpbRoiJob);
         default: return -1;
     }
 }

@@ -322,13 +322,14 @@ __device__ __forceinline__ void ipb_rs_regroup(IpbRsSel& s, int nr) {
     s.gn = m > 0 ? m : 1;
 }
 
+// one job by the whole CTA (every thread of the block calls it)
 template <int SRC>
-__global__ void __launch_bounds__(IPB_RS_THREADS, 1)
-ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __restrict__ jobs,
+__device__ __forceinline__ void ipb_rs_job(unsigned jidx, const IpbRegion* __restrict__ regions, const IpbStatJob* __restrict__ jobs,
                    const unsigned* __restrict__ mask_pool, const unsigned* __restrict__ and_bits,
                    int and_wpr, int H, int W,
                    const unsigned short* __restrict__ planes, const float* __restrict__ images,
-                   const float* __restrict__ bvals, IpbStatOut* __restrict__ out, int smem_bytes)
+                   const float* __restrict__ bvals, IpbStatOut* __restrict__ out, int smem_bytes,
+                   const unsigned char* __restrict__ only)
 {
     IPB_DYN_SMEM(unsigned, keystore);
     __shared__ IpbRsWalkSh wsh;
@@ -339,8 +340,9 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     __shared__ unsigned list_n;
     __shared__ unsigned char gtab[64];
 
-    const IpbStatJob job = jobs[blockIdx.x];
+    const IpbStatJob job = jobs[jidx];
     if (job.src != SRC) return;                          // mixed job lists: the other instantiation takes it
+    if (only && !only[job.region]) return;               // rerun of the regions the fused ROI kernel could not serve
     const IpbRegion rg = regions[job.region];
     IpbRsCtx c;
     c.mask = mask_pool + rg.mask_off;
@@ -710,4 +712,19 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
     }
 }
 
-#include "ipb_roistats_sw.cuh"
+// grid = n_jobs (one job per CTA), or -- with `only` -- a small grid whose CTAs stride over the job
+// list and measure only the regions flagged by the fused ROI kernel (ipb_roifused.cuh)
+template <int SRC>
+__global__ void __launch_bounds__(IPB_RS_THREADS, 1)
+ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __restrict__ jobs, int n_jobs,
+                   const unsigned* __restrict__ mask_pool, const unsigned* __restrict__ and_bits,
+                   int and_wpr, int H, int W,
+                   const unsigned short* __restrict__ planes, const float* __restrict__ images,
+                   const float* __restrict__ bvals, IpbStatOut* __restrict__ out, int smem_bytes,
+                   const unsigned char* __restrict__ only /* null, or per region: != 0 -> measure it */)
+{
+    for (unsigned j = blockIdx.x; j < (unsigned)n_jobs; j += gridDim.x) {
+        __syncthreads();                                   // the previous job's shared state is dead
+        ipb_rs_job<SRC>(j, regions, jobs, mask_pool, and_bits, and_wpr, H, W, planes, images, bvals, out, smem_bytes, only);
+    }
+}

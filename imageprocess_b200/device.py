@@ -64,6 +64,9 @@ class TorchMem:
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
 
+    def n_sms(self):
+        return int(self.torch.cuda.get_device_properties(self.device).multi_processor_count)
+
     # -- allocation
     def empty(self, shape, dtype):
         shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))

@@ -41,7 +41,7 @@ class RoiMasks:
 KERNELS_PER_CALL = {"ipb_fa_segment": 6,   # per-crop shared-memory path (14 on the one-kernel-per-phase path)
                      "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
                     "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
-                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_region_stats_sw": 1, "ipb_region_dilate": 2, "ipb_hist_select": 3, "ipb_hist_planes": 1}
+                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_roi_stats_fused": 1, "ipb_region_dilate": 2, "ipb_hist_select": 3, "ipb_hist_planes": 1}
 
 
 class Engine:
@@ -62,6 +62,11 @@ class Engine:
         e1.record()
         self.prof.setdefault(name, []).append((e0, e1))
         return rc
+
+    def n_sms(self):
+        """Streaming multiprocessors of the device (sizes the persistent grids)."""
+        f = getattr(self.mem, "n_sms", None)
+        return int(f()) if f else 148
 
     def profile_start(self):
         self.prof = {}
@@ -128,7 +133,13 @@ CROP_JOB = np.dtype([("plane", "i4"), ("x0", "i4"), ("y0", "i4"), ("w", "i4"), (
                      ("out_off", "i8")])
 PLANE_PASS = np.dtype([("plane", "i4"), ("excl_plane1", "i4"), ("sat_min", "i4"), ("n_jobs", "i4"), ("job", "i4", 4)])
 HIST_WIN = np.dtype([("wlo", "i4"), ("whi", "i4"), ("mode", "i4"), ("pad", "i4")])
-_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG, CROP, COMP, CROP_JOB, PLANE_PASS, HIST_WIN]
+ROI_JOB = np.dtype([("region", "i4"), ("plane", "i4", 2), ("n_views", "i4", 2), ("bidx", "i4", (2, 2)),
+                    ("clip", "i4", (2, 2)), ("out", "i4", (2, 2)), ("qkind", "i4", (2, 3)), ("q32", "f4", (2, 3)),
+                    ("ratio_on", "i4"), ("ratio_out", "i4"), ("fp_idx", "i4"), ("numer_slot", "i4"),
+                    ("ratio_clip_neg", "i4"), ("rqkind", "i4", 3), ("rq32", "f4", 3)])
+_SIZEOF = [HIST_JOB, Q_JOB, Q_OUT, REGION, STAT_JOB, STAT_OUT, FRET_CFG, CROP, COMP, CROP_JOB, PLANE_PASS, HIST_WIN,
+           ROI_JOB]
+RF_CTAS_PER_SM = 2
 
 
 def plane_passes(hist_jobs):
@@ -267,7 +278,7 @@ def _engine_region_stats(self, regions, jobs, mask_pool, H, W, planes=None, imag
     out = mem.empty(max(n_out, 1), STAT_OUT)
     p = lambda b: b.ptr if b is not None else None
     self.call("ipb_region_stats", d_r.ptr, d_j.ptr, n, uniform, mask_pool.ptr, p(and_bits), int(and_wpr),
-                  int(H), int(W), p(planes), p(images), p(bvals), out.ptr, mem.stream)
+                  int(H), int(W), p(planes), p(images), p(bvals), out.ptr, None, mem.stream)
     out._keep = (d_r, d_j)
     return out
 

@@ -35,7 +35,7 @@ extern "C" {
 const char* ipb_last_error(void);
 int ipb_version(void);
 int ipb_is_emulated(void);      /* 1 only in the CPU test build of the same sources */
-int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg 7 Crop 8 Comp 9 CropJob 10 PlanePass 11 HistWin */
+int ipb_sizeof(int which);      /* 0 HistJob 1 QJob 2 QOut 3 Region 4 StatJob 5 StatOut 6 FretCfg 7 Crop 8 Comp 9 CropJob 10 PlanePass 11 HistWin 12 RoiJob */
 
 /* ------------------------------------------------------------------ ROI rasterisation
  * Replaces rasterize_polygon (INT/Fluor_INT.py:398-403; copies FRET/fret_ratio_builder.py:292,
@@ -203,20 +203,46 @@ typedef struct {
 int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int uniform_src,
                      const uint32_t* mask_pool, const uint32_t* and_bits, int and_wpr, int H, int W,
                      const uint16_t* planes, const float* images, const float* bvals, void* out,
+                     const uint8_t* only /* NULL, or [n_regions]: measure only regions with only[region] != 0 */,
                      void* stream);
 
-/* The same jobs and outputs as ipb_region_stats for IPB_SRC_U16 / IPB_SRC_F32 regions without an
- * AND plane, by sampled windows instead of full histograms: persistent 256-thread CTAs (n_ctas of
- * them, 4 per SM) compact a region's keys into their slice of `scratch` (uint32 [n_ctas][stride],
- * stride >= the largest region's pixel count), sort a <= 2048-key sample in shared memory, derive
- * a key window per wanted quantile and resolve the exact ranks with two passes over the keys.
- * Exact in every case: a job that does not fit (AND plane, > 2048 rows, more pixels than stride, a
- * rank outside its window) adds to *miss (zeroed by the caller), and the caller repeats the jobs
- * with ipb_region_stats.  Replaces the per-ROI np.mean / median / std / percentile / min / max
- * of quantify_stats (Fluor_INT.py:494-507) and quantify_per_roi (fret_ratio_builder.py:342-362). */
-int ipb_region_stats_sw(const void* regions, const void* jobs, int n_jobs, int src, const uint32_t* mask_pool,
-                        int H, int W, const uint16_t* planes, const float* images, const float* bvals,
-                        void* out, uint32_t* scratch, int64_t stride, int n_ctas, uint32_t* miss, void* stream);
+/* Per-ROI statistics of the FRET + intensity stages in ONE walk of each ROI: up to two uint16
+ * channels of a region (each with up to two (B, clip) views) and the epsilon-regularised ratio of the
+ * two, recomputed per pixel with the arithmetic of ipb_fret_pixels' plain configuration
+ * (fret_ratio_builder.py:466-474), so the ratio image is not read back and the mask is decoded once.
+ * Order statistics by sampled value windows: a sample of the ROI fixes, per source and wanted
+ * quantile, a window of values; pixels outside the windows only feed integer moments and "below
+ * the window" counters, pixels inside go to a fine histogram.  Output rows are ipb_stat_out rows,
+ * bit-identical in n / area / min / max / q to ipb_region_stats on the equivalent jobs.
+ * Exact in every case: a region the scheme cannot serve (AND plane, tiny or huge region, windows
+ * wider than the fine histogram, a rank outside its window) gets flags[region] = 1 and no output;
+ * the caller then runs ipb_region_stats on the equivalent job list with only = flags.
+ * Replaces quantify_stats / quantify_per_roi_multi (INT/Fluor_INT.py:494-538) and quantify_per_roi
+ * (FRET/fret_ratio_builder.py:342-362).
+ *   scratch   uint32 [n_ctas][stride_words]: per-CTA list of the ratio's in-window keys;
+ *             ipb_roi_stats_fused_stride() gives a sufficient stride for a region rect
+ *   counter   uint32 [1] job counter, flags uint8 [n_regions]: both cleared by the call
+ *   n_ctas    persistent CTAs (ipb_roi_stats_fused_ctas(): two per SM)                            */
+typedef struct {
+    int32_t region;
+    int32_t plane[2];             /* uint16 plane of channel slot 0 / 1; < 0: slot unused */
+    int32_t n_views[2];
+    int32_t bidx[2][2];           /* view's background at bvals[bidx]; < 0: B = 0 */
+    int32_t clip[2][2];
+    int32_t out[2][2];            /* output row of the view */
+    int32_t qkind[2][3];
+    float q32[2][3];
+    int32_t ratio_on, ratio_out;
+    int32_t fp_idx;               /* bvals[fp_idx + {0,1,2}] = {B of slot 0, B of slot 1, eps} */
+    int32_t numer_slot;           /* slot of the numerator */
+    int32_t ratio_clip_neg;
+    int32_t rqkind[3];
+    float rq32[3];
+} ipb_roi_job;
+int ipb_roi_stats_fused(const void* regions, int n_regions, const void* jobs /* ipb_roi_job[] dev */, int n_jobs,
+                        const uint32_t* mask_pool, int H, int W, const uint16_t* planes, const float* bvals,
+                        void* out /* ipb_stat_out[] */, uint32_t* scratch, int64_t stride_words, int n_ctas,
+                        uint32_t* counter, uint8_t* flags, void* stream);
 
 /* ------------------------------------------------------------------ focal-adhesion chain
  * Replaces analyze_fa_crop (INT/FA_Analyzer.py:123-195) for a ragged batch of crops in one

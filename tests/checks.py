@@ -300,53 +300,77 @@ def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168, fa_path=0, frames=
     return straddles
 
 
-def check_region_stats_sw(eng):
-    """Per-ROI statistics by sampled windows (ipb_region_stats_sw) against the full-histogram
-    kernels on regions far larger than the sorted sample (2048 keys): n, area, min, max and all
-    order statistics bit-identical, sums within 1e-12; no window miss on ordinary data.  Heavy
-    ties (Poisson counts, a constant patch, saturated pixels) and a wide uniform image."""
+def check_roi_fused_vs_hist(eng):
+    """Per-ROI statistics by ONE fused walk with sampled value windows (ipb_roi_stats_fused) against
+    the full-histogram kernels: n, area, min, max and all order statistics bit-identical, sums within
+    1e-9.  Heavy ties (Poisson counts, a constant patch, saturated pixels), a wide uniform image
+    (windows wider than the fine histogram: those regions must come back through the rerun), a small
+    ROI, dark ROIs below the clip level."""
     from imageprocess_b200 import batch
     rng = np.random.default_rng(41)
     H, W = 384, 512
     polys = [np.array([[10.5, 8.5], [300.5, 12.5], [310.5, 280.5], [150.0, 370.5], [8.5, 300.5]]),
              np.array([[330.0, 20.0], [500.0, 30.0], [490.0, 200.0], [340.0, 180.0]]),
              np.array([[340.5, 220.5], [420.5, 225.5], [415.5, 300.5], [338.5, 290.5]]),
-             np.array([[440.0, 300.0], [470.0, 300.0], [470.0, 330.0], [440.0, 330.0]])]
+             np.array([[440.0, 300.0], [470.0, 300.0], [470.0, 330.0], [440.0, 330.0]]),
+             np.array([[445.0, 340.0], [452.0, 340.0], [452.0, 346.0]])]
     d0 = rng.poisson(900, (H, W)).astype(np.uint16)
     d0[40:120, 40:200] = 1234                                         # constant patch: thousands of equal keys
     d0[rng.random((H, W)) < 0.002] = 65535
     a0 = rng.poisson(400, (H, W)).astype(np.uint16)
     d1 = rng.integers(0, 60000, (H, W)).astype(np.uint16)
     a1 = rng.integers(200, 50000, (H, W)).astype(np.uint16)
-    planes = np.stack([np.stack([d0, a0]), np.stack([d1, a1])])
+    d2 = rng.poisson(2500, (H, W)).astype(np.uint16) + (np.arange(W) * 2)[None, :].astype(np.uint16)   # a gradient
+    a2 = (0.8 * d2 + rng.poisson(300, (H, W))).astype(np.uint16)
+    d2[:, 320:] = rng.poisson(30, (H, W - 320)).astype(np.uint16)     # dark ROIs: most pixels below the background level
+    planes = np.stack([np.stack([d0, a0]), np.stack([d1, a1]), np.stack([d2, a2])])
     F = planes.shape[0]
     fret_p = {"bg_scope": "full", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False,
               "donor_p": 1.0, "fret_p": 1.0, "clip_neg": True, "eps_percentile": 1.0, "ratio_mode": "FRET/Donor"}
     task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4,
-            "percentile": 2.0, "per_channel_p": False, "ch_p_map": {}}
-    res = {}
-    for sw in (True, False):
-        job = batch.FrameBatchJob(eng, planes.shape, stages=("fret", "int"), fret_p=fret_p, int_task=task)
-        job.stats_sw = sw
-        res[sw] = job.run(eng.mem.from_host(planes), [polys] * F)
-        pl = job._plans[next(iter(job._plans))]
-        assert pl.rs_sw_ok and job.window_misses == 0, (sw, job.window_misses)
-    for name in ("fret_stat", "int_stat"):
-        g, w = getattr(res[True], name), getattr(res[False], name)
-        assert g.shape == w.shape
-        assert int(w["n"].max()) > 60000                              # far beyond the sorted sample
-        for k in ("n", "area", "vmin", "vmax"):
-            assert np.array_equal(g[k], w[k]), (name, k)
-        assert np.array_equal(g["q"], w["q"], equal_nan=True), (name, g["q"], w["q"])
-        assert np.allclose(g["sum"], w["sum"], rtol=1e-12, atol=0) and np.allclose(g["ssd"], w["ssd"], rtol=1e-9, atol=1e-6)
+            "percentile": 40.0, "per_channel_p": False, "ch_p_map": {}}
+    out = {}
+    for stages in (("fret", "int"), ("fret",), ("int",)):
+        for ratio_mode, clip in (("FRET/Donor", True), ("Donor/FRET", False)):
+            res = {}
+            fp = dict(fret_p, ratio_mode=ratio_mode, clip_neg=clip)
+            tk = dict(task, clip_neg=clip)
+            for fused in (True, False):
+                job = batch.FrameBatchJob(eng, planes.shape, stages=stages, fret_p=fp, int_task=tk)
+                job.fused_roi = fused
+                res[fused] = job.run(eng.mem.from_host(planes), [polys] * F)
+                if fused:
+                    out[(stages, ratio_mode)] = job.roi_fallbacks
+                    # the uniform frame and the tiny ROI cannot be served; the Poisson frames must be
+                    assert 0 < job.roi_fallbacks < 3 * len(polys), job.roi_fallbacks
+            for name in ("fret_stat", "int_stat"):
+                if not hasattr(res[True], name):
+                    continue
+                g, w = getattr(res[True], name), getattr(res[False], name)
+                assert g.shape == w.shape
+                for k in ("n", "area", "vmin", "vmax"):
+                    assert np.array_equal(g[k], w[k], equal_nan=True), (stages, name, k, g[k], w[k])
+                assert np.array_equal(g["q"], w["q"], equal_nan=True), (stages, name, g["q"], w["q"])
+                assert np.allclose(g["sum"], w["sum"], rtol=1e-9, atol=1e-6), (stages, name)
+                assert np.allclose(g["ssd"], w["ssd"], rtol=1e-7, atol=1e-3), (stages, name, g["ssd"], w["ssd"])
     # and against the oracle for one frame
-    rows_i = batch.rows_intensity(res[True], F, [1, 2])
-    D, A = d0.astype(np.float32), a0.astype(np.float32)
-    wrows, _, _ = port.int_process_key({1: D.copy(), 2: A.copy()}, polys, None, task)
-    check_int_rows(rows_i[0], wrows, (1, 2))
+    job = batch.FrameBatchJob(eng, planes.shape, stages=("fret", "int"), fret_p=fret_p, int_task=task)
+    res = job.run(eng.mem.from_host(planes), [polys] * F)
+    rows_i = batch.rows_intensity(res, F, [1, 2])
+    for f, (dd, aa) in enumerate(((d0, a0), (d2, a2))):
+        ff = (0, 2)[f]
+        wrows, _, _ = port.int_process_key({1: dd.astype(np.float32), 2: aa.astype(np.float32)}, polys, None, task)
+        check_int_rows(rows_i[ff], wrows, (1, 2))
+        want = port.fret_process_pair(dd.astype(np.float32), aa.astype(np.float32), polys, fret_p)
+        for g, w in zip(batch.rows_fret(res, F)[ff], want["rows"]):
+            for k in ("ratio_median", "ratio_p5", "ratio_p95", "donor_median", "yfret_median", "area_px"):
+                assert g[k] == w[k], (ff, k, g[k], w[k])
+            for k in ("ratio_mean", "ratio_std", "donor_mean", "yfret_mean"):
+                assert close(g[k], w[k]), (ff, k, g[k], w[k])
+    return out
 
 
-RASTER_CHECKS.append(check_region_stats_sw)
+RASTER_CHECKS.append(check_roi_fused_vs_hist)
 
 
 def check_graph_replay(eng):

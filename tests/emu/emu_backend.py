@@ -36,6 +36,9 @@ class NumpyMem:
 
     stream = 0
 
+    def n_sms(self):
+        return 2                     # persistent grids of a few CTAs: job loops get exercised
+
     def pinned(self, shape, dtype):
         n = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
         t = np.zeros(n, dtype=np.uint8)
