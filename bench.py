@@ -41,6 +41,10 @@ INT_TASK = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_s
 FA_PARAMS = {"alpha": 2.0, "min_area_um": 1.5, "max_area_um": 30.0, "close_radius": 1,
              "subtract_bg": True}                           # FA_Analyzer.py:298-304
 FA_PX = 0.112
+# "spread": the adhesion blobs of a cell are kept apart all over the cell (~770 separate adhesions per
+# frame); "centre" is round 1's layout (they overlap into 1-2 large adhesions per cell)
+BLOB_LAYOUT = os.environ.get("IPB_BENCH_BLOBS", "spread")
+FRAME_INFO = {}
 
 
 def make_frames(n_frames, seed=1234, n_unique=2):
@@ -51,7 +55,8 @@ def make_frames(n_frames, seed=1234, n_unique=2):
     polys = None
     for u in range(n_unique):
         d, a, polys_u = synth.fret_frame(seed=seed, H=H, W=W, n_cells=N_CELLS, r_min=80, r_max=160,
-                                         blobs_per_cell=BLOBS, drift=1.0 + 0.2 * (u / max(1, n_unique - 1) - 0.5))
+                                         blobs_per_cell=BLOBS, drift=1.0 + 0.2 * (u / max(1, n_unique - 1) - 0.5),
+                                         blob_layout=BLOB_LAYOUT, info=FRAME_INFO)
         polys = polys_u
         base.append(np.stack([d, a]))
     rng = np.random.default_rng(seed + 17)
@@ -147,63 +152,76 @@ def _ref_item(args):
 
 
 def run_reference(args):
-    """The reference's CPU path (oracle port of it) with the reference's own pool size, on a bounded
-    sample per step: one frame per worker, all in parallel.  When K steps of whole frames (~27 s
-    each) do not fit in a few minutes, the frames are the same scene at 1/2 or 1/4 of the linear
-    size (same 24 cells and blobs per cell, radii, blob areas and pixel size scaled with it), which
-    keeps the cost per pixel: every stage of the reference is linear in pixels x ROIs.  The sample
-    is named in the line."""
+    """The reference's CPU path (oracle port of it) on WHOLE 2048 x 2048 frames of the same workload
+    (same generator, seed, ROIs and blob layout as our arm), with every host thread the reference
+    would use: its own pool size min(cpu_count, 8) (Fluor_INT.py:2211-2216).
+
+    A step is a bounded sample: `workers` whole frames, one per worker, all in parallel (~30 s).
+    When K such steps would not end within the budget (IPB_REF_BUDGET_S, default 780 s) a step is
+    ONE whole frame whose ROIs are dealt to the workers (each repeats the cheap whole-frame parts).
+    The frame is never scaled down: config equals our arm's."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     import oracle
     oracle.build()
     from imageprocess_b200 import synth
     cores = os.cpu_count() or 1
-    workers = min(cores, 8)         # the reference's own pool size: Fluor_INT.py:2211-2216
-    budget_s, frame_s = 170.0, 27.0
-    div = 1
-    while div < 4 and (args.steps + 1) * frame_s / (div * div) > budget_s:
-        div *= 2
-    h, w = H // div, W // div
-    items = []
-    for u in range(2):
-        d, a, polys = synth.fret_frame(seed=1234, H=h, W=w, n_cells=N_CELLS, r_min=80 // div, r_max=160 // div,
-                                       blobs_per_cell=BLOBS, drift=0.9 + 0.2 * u,
-                                       blob_area=(max(4, 120 // (div * div)), max(8, 800 // (div * div))))
-        items.append((np.stack([d, a]), polys, FA_PX * div))
-    items = [items[i % 2] for i in range(workers)]
-    px_per_step = workers * h * w
+    workers = min(cores, 8)
+    budget_s = float(os.environ.get("IPB_REF_BUDGET_S", "780"))
+    frames, polys = make_frames(2, seed=1234)                 # the two base frames of our arm's rank 0
+    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
 
-    def step(its, nproc):
-        import multiprocessing as mp
+    def run(items):
         t0 = time.perf_counter()
-        if nproc <= 1:
-            for it in its:
+        if pool is None:
+            for it in items:
                 _ref_item(it)
         else:
-            with mp.get_context("fork").Pool(nproc) as pool:
-                pool.map(_ref_item, its)
+            pool.map(_ref_item, items, chunksize=1)
         return time.perf_counter() - t0
 
-    if args.warmup > 0:             # imports, page faults; a quarter-size frame is enough for that
-        d, a, polys = synth.fret_frame(seed=7, H=H // 4, W=W // 4, n_cells=N_CELLS, r_min=20, r_max=40, blobs_per_cell=4,
-                                       blob_area=(8, 50))
-        step([(np.stack([d, a]), polys, FA_PX * 4)], 1)
-    t_all = sum(step(items, workers) for _ in range(args.steps))
-    value = px_per_step * args.steps / t_all / 1e6
-    what = f"{h}x{w} frames" + ("" if div == 1 else f" (the C4 scene at 1/{div} linear size)")
+    if args.warmup > 0:             # imports, page faults, pool start-up: a quarter-size scene is enough for that
+        d, a, wp = synth.fret_frame(seed=7, H=H // 4, W=W // 4, n_cells=N_CELLS, r_min=20, r_max=40, blobs_per_cell=4,
+                                    blob_area=(8, 50))
+        run([(np.stack([d, a]), wp, FA_PX)] * workers)
+    by_frame = [(frames[i % 2], polys, FA_PX) for i in range(workers)]
+    by_roi = lambda k: [(frames[k % 2], polys[i::workers], FA_PX) for i in range(workers)]
+    t_first = run(by_frame)                                   # the first timed step, in the reference's own mode
+    whole = t_first * args.steps <= budget_s
+    t_all, px = t_first, workers * H * W
+    for k in range(1, args.steps):
+        if whole:
+            t_all += run(by_frame)
+            px += workers * H * W
+        else:
+            t_all += run(by_roi(k))
+            px += H * W
+    if pool is not None:
+        pool.close()
+    value = px / t_all / 1e6
+    mode = (f"{workers} whole 2048x2048 frames per step, one per worker" if whole else
+            f"step 1: {workers} whole 2048x2048 frames, one per worker; later steps: one whole 2048x2048 frame, its "
+            f"{len(polys)} ROIs dealt to the {workers} workers")
     line = {"impl": "reference", "metric": "Mpix/s (2048x2048 uint16 2ch FRET+FA+ROI-intensity time-lapse)",
             "value": value, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "C4-synth 2048x2048x2ch uint16, 24 ROIs, FA blobs",
-                                            "frames_per_step": workers, "frame": what},
+            "data": "synthetic", "config": workload_config(args.frames),
             "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": workers, "kind": "port",
-                             "sample": f"{workers} {what} per step through the oracle port (FRET+INT+FA, find_contours "
-                                       f"skipped), multiprocessing pool of {workers} (the reference's own pool size)"},
+                             "sample": f"{mode}; oracle port (FRET+INT+FA, find_contours skipped), multiprocessing "
+                                       f"pool of {workers} (the reference's own pool size), {t_all:.0f} s in all"},
             "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def workload_config(frames_per_step):
+    """The `config` object both arms print (same workload, same keys)."""
+    placed = FRAME_INFO.get("blobs_placed", 0) // 2            # make_frames paints two base frames
+    return {"workload": f"C4-synth 2048x2048x2ch uint16 time-lapse, {N_CELLS} cell ROIs, {BLOBS} FA blobs drawn per cell "
+                        f"({BLOB_LAYOUT} layout: {placed} separate blobs per frame)", "frames_per_step_per_gpu": frames_per_step,
+            "l2": "inputs larger than L2 (no flush needed)", "stages": ["fret", "int", "fa"]}
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -238,10 +256,15 @@ def run_ours(args):
 
     job.dist = dist                     # N > 1: every step all-gathers its packed row tables (NCCL)
 
+    seen = {"adhesions": 0, "roi_fallbacks": 0, "steps": 0}
+
     def consume(res):
         """Host side of one step: per-adhesion table with the reference's dtypes; on rank 0 of an
         N-rank job also the other ranks' gathered tables (their adhesion counts are read here)."""
-        batch.fa_table(res, job.fa_cfg)
+        t = batch.fa_table(res, job.fa_cfg)
+        seen["adhesions"] += int(t["label"].shape[0])
+        seen["roi_fallbacks"] += int(getattr(res, "roi_fallbacks", 0))
+        seen["steps"] += 1
         if res.gathered is not None:
             for comp_off in res.gathered_comp_off:          # every rank has its own ROI set / arena layout
                 int(comp_off[-1])
@@ -344,9 +367,7 @@ def run_ours(args):
             "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16/f32", "data": "synthetic",
-            "config": {"workload": "C4-synth 2048x2048x2ch uint16, 24 ROIs, 60 FA blobs/cell",
-                       "frames_per_step_per_gpu": F, "l2": "inputs larger than L2 (no flush needed)",
-                       "stages": list(job.stages)},
+            "config": workload_config(F),
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(frames.nbytes),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk.summary()}
@@ -384,6 +405,8 @@ def run_ours(args):
         line["ms_per_step_serialized"] = ms_ser / args.steps
         line["host_submit_ms_per_step"] = host_submit_ms
         line["window_misses"] = int(job.window_misses)       # steps repeated with full histograms (exact either way)
+        line["adhesions_per_frame"] = seen["adhesions"] / max(1, seen["steps"] * F)
+        line["roi_fallbacks_per_step"] = seen["roi_fallbacks"] / max(1, seen["steps"])   # ROIs repeated by the full-histogram kernels
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             oracle.build()

@@ -416,7 +416,7 @@ class FrameBatchJob:
         if NF:
             mr = m_rect[uidx]
             rw, rh = (mr[:, 2] - mr[:, 0]).astype(np.int64), (mr[:, 3] - mr[:, 1]).astype(np.int64)
-            pl.rf_stride = int(min(((rw + 16) * rh).max() + 8192, 1 << 18))
+            pl.rf_stride = int(min(2 * ((rw + 16) * rh).max() + 16384, 1 << 19))   # words per CTA: see ipb_roi_stats_fused
 
         passes = ops.plane_passes(hist_jobs)
         pl.n_passes = passes.shape[0]
@@ -780,7 +780,10 @@ class FrameBatchJob:
             return self.run(tk.planes, tk.polys, full_hist=True)
         params = OV("params")[:NP].copy()
         res.d2h_bytes = O.size
-        res.roi_fallbacks = int(np.count_nonzero(OV("rf_flags")[:NR])) if (self.fused_roi and pl.NF) else 0
+        # regions the fused ROI kernel left to the full-histogram kernels, by reason (ipb_roifused.cuh)
+        why = np.bincount(OV("rf_flags")[:NR], minlength=6) if (self.fused_roi and pl.NF) else np.zeros(6, np.int64)
+        res.roi_fallbacks = int(why[1:].sum())
+        res.roi_fallback_why = {n: int(why[k]) for k, n in enumerate(("geometry", "windows", "empty", "rank", "list"), 1) if why[k]}
         self.roi_fallbacks += res.roi_fallbacks
         if "fret" in st:
             res.fret_params = params[P_FRET: P_FRET + F * FP_STRIDE].reshape(F, FP_STRIDE)

@@ -303,9 +303,10 @@ def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168, fa_path=0, frames=
 def check_roi_fused_vs_hist(eng):
     """Per-ROI statistics by ONE fused walk with sampled value windows (ipb_roi_stats_fused) against
     the full-histogram kernels: n, area, min, max and all order statistics bit-identical, sums within
-    1e-9.  Heavy ties (Poisson counts, a constant patch, saturated pixels), a wide uniform image
-    (windows wider than the fine histogram: those regions must come back through the rerun), a small
-    ROI, dark ROIs below the clip level."""
+    1e-7 (the fused kernel sums v - B exactly, the histogram kernel the float32-rounded differences).
+    Heavy ties (Poisson counts, a constant patch, saturated pixels), a wide uniform image (fine bins
+    wider than one value: key lists + digit passes for the uint16 sources too), a tiny ROI (must come
+    back through the rerun), dark ROIs below the clip level."""
     from imageprocess_b200 import batch
     rng = np.random.default_rng(41)
     H, W = 384, 512
@@ -341,8 +342,8 @@ def check_roi_fused_vs_hist(eng):
                 res[fused] = job.run(eng.mem.from_host(planes), [polys] * F)
                 if fused:
                     out[(stages, ratio_mode)] = job.roi_fallbacks
-                    # the uniform frame and the tiny ROI cannot be served; the Poisson frames must be
-                    assert 0 < job.roi_fallbacks < 3 * len(polys), job.roi_fallbacks
+                    # only the tiny ROI (too few pixels for a sample) is left to the full-histogram kernels
+                    assert job.roi_fallbacks == F and res[True].roi_fallback_why == {"windows": F}, res[True].roi_fallback_why
             for name in ("fret_stat", "int_stat"):
                 if not hasattr(res[True], name):
                     continue
@@ -351,8 +352,8 @@ def check_roi_fused_vs_hist(eng):
                 for k in ("n", "area", "vmin", "vmax"):
                     assert np.array_equal(g[k], w[k], equal_nan=True), (stages, name, k, g[k], w[k])
                 assert np.array_equal(g["q"], w["q"], equal_nan=True), (stages, name, g["q"], w["q"])
-                assert np.allclose(g["sum"], w["sum"], rtol=1e-9, atol=1e-6), (stages, name)
-                assert np.allclose(g["ssd"], w["ssd"], rtol=1e-7, atol=1e-3), (stages, name, g["ssd"], w["ssd"])
+                assert np.allclose(g["sum"], w["sum"], rtol=1e-7, atol=1e-6), (stages, name)
+                assert np.allclose(g["ssd"], w["ssd"], rtol=1e-6, atol=1e-3), (stages, name, g["ssd"], w["ssd"])
     # and against the oracle for one frame
     job = batch.FrameBatchJob(eng, planes.shape, stages=("fret", "int"), fret_p=fret_p, int_task=task)
     res = job.run(eng.mem.from_host(planes), [polys] * F)

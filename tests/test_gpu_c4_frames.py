@@ -46,7 +46,7 @@ def test_c4_frames(eng):
     dev = eng.mem.from_host(frames)
     res = job.run(dev, [polys] * F)
     pl = job._plans[next(iter(job._plans))]
-    assert pl.pq_ok and job.window_misses == 0
+    assert pl.pq_ok and job.window_misses == 0 and pl.NF == len(polys) * F and res.roi_fallbacks == 0, res.roi_fallback_why
     first = _snap(res)
     R0 = res.R.host()[0].copy()
     labels = res.fa_labels.host().copy()
@@ -85,7 +85,7 @@ def test_c4_frames(eng):
         assert np.array_equal(view.labels_host(i), wlab), i
         n_fa += int(wlab.max())
     wfa = port.fa_batch_rows(D, polys, bench.FA_PARAMS, bench.FA_PX, save_ok_only=False, with_contours=False, stats=stats)
-    assert len(rows_a[0]) == len(wfa) == n_fa and n_fa >= len(polys)      # the 60 blobs of a cell overlap into a few large adhesions
+    assert len(rows_a[0]) == len(wfa) == n_fa and n_fa >= 500             # spread layout: the blobs of a cell stay separate adhesions
     for g, w in zip(rows_a[0], wfa):
         assert g["Cell_ID"] == w["Cell_ID"] and g["Category"] == w["Category"] and g["Area_px"] == w["Area_px"]
         assert checks.close(float(g["Mean_Intensity_Raw"]), float(w["Mean_Intensity_Raw"]))
