@@ -254,7 +254,8 @@ def run_ours(args):
 
     tab_dev = torch.device(f"cuda:{local}")
 
-    job.dist = dist                     # N > 1: every step all-gathers its packed row tables (NCCL)
+    job.dist = dist                     # N > 1: the packed row tables go to rank 0, ONE NCCL all-gather per 8 steps
+    LAG = max(1, args.lag)              # tickets in flight: step k is collected after step k + LAG was submitted
 
     seen = {"adhesions": 0, "roi_fallbacks": 0, "steps": 0}
 
@@ -265,10 +266,14 @@ def run_ours(args):
         seen["adhesions"] += int(t["label"].shape[0])
         seen["roi_fallbacks"] += int(getattr(res, "roi_fallbacks", 0))
         seen["steps"] += 1
-        if res.gathered is not None:
-            for comp_off in res.gathered_comp_off:          # every rank has its own ROI set / arena layout
-                int(comp_off[-1])
         return res.d2h_bytes
+
+    def consume_gathered(groups):
+        """Rank 0: the other ranks' tables as they arrive (their adhesion counts are read here)."""
+        for g in groups:
+            for ents in g["per_rank"]:
+                for arena, comps, comp_off in ents:          # every rank has its own ROI set / arena layout
+                    seen["gathered_adhesions"] = seen.get("gathered_adhesions", 0) + int(comp_off[-1])
 
     def barrier():
         torch.cuda.synchronize()
@@ -294,18 +299,21 @@ def run_ours(args):
     host = {"submit_s": 0.0, "n": 0}
 
     def loop_resident(steps):
-        """Steps over HBM-resident frames; step k+1 is submitted before step k's tables are
+        """Steps over HBM-resident frames; up to LAG steps are in flight before a step's tables are
         unpacked, as consecutive batches of a time-lapse are in the product."""
-        prev, d2h = None, 0
+        pend, d2h = [], 0
         for _ in range(steps):
             t0 = time.perf_counter()
-            tk = job.submit(planes, polys_pf)
+            pend.append(job.submit(planes, polys_pf))
             host["submit_s"] += time.perf_counter() - t0
             host["n"] += 1
-            if prev is not None:
-                d2h = consume(job.collect(prev))
-            prev = tk
-        return consume(job.collect(prev))
+            if len(pend) > LAG:
+                d2h = consume(job.collect(pend.pop(0)))
+                consume_gathered(job.gathered())
+        while pend:
+            d2h = consume(job.collect(pend.pop(0)))
+        consume_gathered(job.finish())                      # the partial last group; waits for every gather
+        return d2h
 
     # end-to-end: host frames in pinned memory, H2D of step k+1 on a copy stream while step k computes
     planes_b = [planes, eng.mem.empty(shape, np.uint16)]
@@ -324,19 +332,22 @@ def run_ours(args):
                 up[b] = torch.cuda.Event()
                 up[b].record(copy_stream)
         upload(0)
-        prev, d2h = None, 0
+        pend, d2h = [], 0
         for k in range(steps):
             if k + 1 < steps:
                 upload(k + 1)
             b = k & 1
             main.wait_event(up[b])
-            tk = job.submit(planes_b[b], polys_pf)
+            pend.append(job.submit(planes_b[b], polys_pf))
             done[b] = torch.cuda.Event()
             done[b].record(main)
-            if prev is not None:
-                d2h = consume(job.collect(prev))
-            prev = tk
-        return consume(job.collect(prev))
+            if len(pend) > LAG:
+                d2h = consume(job.collect(pend.pop(0)))
+                consume_gathered(job.gathered())
+        while pend:
+            d2h = consume(job.collect(pend.pop(0)))
+        consume_gathered(job.finish())
+        return d2h
 
     eng.mem.copy_bytes(planes_b[1], 0, planes, 0, planes.nbytes)
     for b in planes_b:                  # setup: buffers, plan tables and the CUDA graphs of both input buffers
@@ -432,6 +443,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--lag", type=int, default=2, help="steps in flight before a step's tables are unpacked")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

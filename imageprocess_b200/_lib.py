@@ -31,7 +31,7 @@ _PROTOS = {
     "ipb_fa_segment": [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "ipb_region_stats": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
-    "ipb_roi_stats_fused": [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp],
+    "ipb_roi_stats_fused": [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp],
 }
 _PROTOS.update({
     "ipb_region_dilate": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp],

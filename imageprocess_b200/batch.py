@@ -98,8 +98,17 @@ class FrameBatchJob:
         self._bufs = {}
         self._plans = {}
         self._plan_serial = 0
-        self._gather_ev = [None, None]   # per output slot: event of the last all-gather that read its staging buffer
-        self._graphs = {}           # (plan, input buffer, output slot, full_hist) -> (CUDA graph, ticket template) | (None, times seen)
+        # N ranks: every step stages its packed tables in a device ring; ONE all-gather per
+        # `gather_every` collected steps (see _issue_gather), never one per step
+        self.n_slots = 3                 # output slots: a ticket may be collected two submits later
+        self.gather_every = int(os.environ.get("IPB_GATHER_EVERY", "8"))
+        self._g_pos = 0                  # steps staged so far
+        self._g_open = {}                # group -> [entries collected, their ring-copy events]
+        self._g_issued = []              # issued gathers not yet handed out: dicts
+        self._g_last = [None, None]      # per ring buffer: event of the last gather that read it
+        self._g_total, self._g_count = None, 0
+        self._priming = False
+        self._graphs = {}           # (plan, input buffer, output slot, full_hist, ...) -> (CUDA graph, ticket template) | (None, times seen)
         self.use_graphs = bool(int(os.environ.get("IPB_GRAPHS", "1")))
         self.window_misses = 0
         self._slot = 0
@@ -500,24 +509,22 @@ class FrameBatchJob:
         return pl
 
     # ------------------------------------------------------------------ the step
-    def submit(self, planes, polys_per_frame, full_hist=False):
+    def submit(self, planes, polys_per_frame, full_hist=False, _pos=None):
         """Enqueues one step on the current stream and returns a ticket for collect(); nothing
         here waits for the device, so consecutive steps of a time-lapse overlap the host's table
-        unpacking with the device's next batch (outputs are double-buffered: collect a ticket
-        before submitting the step after next).  full_hist = True forces exact full-range
-        histograms instead of sample-selected windows (automatic after a window miss).
+        unpacking with the device's next batches (three output slots: collect a ticket before
+        the third submit after it).  full_hist = True forces exact full-range histograms instead
+        of sample-selected windows (automatic after a window miss).
 
         A step whose plan, input buffer and output slot were already seen twice is captured into
         a CUDA graph (table upload, ~25 launches on four streams, result downloads) and replayed
-        from then on: one launch instead of ~60 driver calls from Python.  The NCCL all-gather of
-        an N-rank job follows eagerly."""
+        from then on: one launch instead of ~60 driver calls from Python.  In an N-rank job the
+        step's staged tables are copied into the gather ring; the all-gather itself is issued by
+        collect() once per `gather_every` steps."""
         mem = self.mem
         pl = self._plan_for(polys_per_frame)
         slot = self._slot
-        self._slot ^= 1
-        if self._gather_ev[slot] is not None:                # this slot's staging buffer is free again
-            mem.wait_event(self._gather_ev[slot])
-            self._gather_ev[slot] = None
+        self._slot = (self._slot + 1) % self.n_slots
         # everything the enqueued work depends on besides the (fixed) job parameters
         key = (pl.serial, int(planes.ptr), slot, bool(full_hist), bool(self.hist_select), bool(self.fused_roi),
                bool(self.overlap), int(self.fa_path), int(self.pq_min_px), self.dist is not None)
@@ -548,7 +555,7 @@ class FrameBatchJob:
             if graphable:
                 self._graphs[key] = (None, (ent[1] if ent else 0) + 1)
             tk = self._enqueue(planes, polys_per_frame, full_hist, pl, slot)
-        self._gather(tk, slot)
+        self._stage_for_gather(tk, _pos)
         tk.event = mem.event()
         tk.event.record()
         return tk
@@ -557,8 +564,12 @@ class FrameBatchJob:
         """Setup for a long run over `planes`' buffer: steps it until both output slots have their
         CUDA graphs (buffers allocated, kernels loaded, graphs captured), so that the first real
         step already is one graph launch."""
-        for _ in range(6):
-            self.run(planes, polys_per_frame)
+        self._priming = True             # setup steps stage their tables (same graphs) but take no part in the gathers
+        try:
+            for _ in range(3 * self.n_slots):
+                self.run(planes, polys_per_frame)
+        finally:
+            self._priming = False
 
     def _enqueue(self, planes, polys_per_frame, full_hist, pl, slot):
         """The stream work of one step (see submit)."""
@@ -666,9 +677,10 @@ class FrameBatchJob:
             if use_fused:
                 d_sc = self._dev("rf_scratch", 4 * pl.rf_stride * self.rf_ctas)
                 d_ctr = self._dev("rf_counter", 256)
+                d_wide = self._dev("rf_wide", pl.NF)
                 lib_call("ipb_roi_stats_fused", tp("regions"), NR, tp("roi_jobs"), pl.NF, m_pool.ptr, H, W, planes.ptr,
                          op("params"), op("stat_out"), d_sc.ptr, pl.rf_stride, self.rf_ctas, d_ctr.ptr, op("rf_flags"),
-                         mem.stream)
+                         d_wide.ptr, mem.stream)
             elif pl.n_u16:
                 lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, None, 0,
                          H, W, planes.ptr, None, op("params"), op("stat_out"), None, mem.stream)
@@ -716,9 +728,9 @@ class FrameBatchJob:
             tk.pc_rows = min(pl.comp_cap, max(4096, 96 * NR))        # usual batches fit; collect() fetches the rest
             tk.pc_np, pc_t = self._pinned(f"pin_comps{slot}", COMP.itemsize * tk.pc_rows)
             mem.download_async(pc_t, d_comps, COMP.itemsize * tk.pc_rows)
-        # N > 1 ranks: the packed tables of every rank go to all ranks with ONE NCCL all-gather per
-        # step (KBs..MBs over NVLink); rank `gather_dst` also brings the gathered blob to the host
-        tk.gather_np, tk.g_stage, tk.gather_event = None, None, None
+        # N > 1 ranks: the step stages its packed tables (inside the step's graph); submit() copies
+        # the stage into the gather ring and collect() issues ONE all-gather per `gather_every` steps
+        tk.g_stage = None
         if self.dist is not None and self.dist.get_world_size() > 1:
             # every rank sends the same number of bytes: a capacity agreed once per job (max over
             # ranks of 1.25x the first step's need + 64 KiB).  Segment = 32-byte header {arena bytes,
@@ -742,28 +754,135 @@ class FrameBatchJob:
             mem.copy_bytes(d_stage, 32, d_out, 0, O.size)
             if rows_sent:
                 mem.copy_bytes(d_stage, 32 + _al(O.size), d_comps, 0, COMP.itemsize * rows_sent)
-            tk.g_stage = (d_stage, cap, world)               # the collective itself is issued by _gather()
+            tk.g_stage = (d_stage, cap, world)               # the collective itself is issued by _issue_gather()
         return tk
 
-    def _gather(self, tk, slot):
-        """The NCCL all-gather of a step's staged tables and the destination rank's download:
-        always issued eagerly after the step's stream work (a collective inside a replayed CUDA
-        graph left the process group unable to shut down)."""
-        if getattr(tk, "g_stage", None) is None:
+    # ------------------------------------------------------------------ N ranks: table gathers
+    def begin_distributed(self, n_local_steps):
+        """Agrees on the number of gathers of the job (ranks may own a different number of steps:
+        shards differ by one frame block); call it on every rank before the first step.  Without
+        it every rank must run the same number of steps."""
+        if self.dist is None or self.dist.get_world_size() == 1:
             return
-        mem = self.mem
+        groups = -(-int(n_local_steps) // self.gather_every)
+        self._g_total = self.mem.all_reduce_max(groups, self.dist)
+
+    def _stage_for_gather(self, tk, pos):
+        """Copies the step's staged tables (header + table arena + first adhesion rows, written by
+        the step itself) into entry `pos` of the gather ring and records when that is done."""
+        tk.g_pos = None
+        if getattr(tk, "g_stage", None) is None or self._priming:
+            return
+        mem, K = self.mem, self.gather_every
         d_stage, cap, world = tk.g_stage
-        d_all = self._dev(f"gather_all{slot}", cap * world)
-        # on its own stream: the next step's kernels do not queue behind the collective (which
-        # waits for the slowest rank); staging and receive buffers are per output slot
-        with mem.branch(4, detach=True) as br:
-            mem.all_gather_bytes(d_all, d_stage, cap, self.dist)
+        if pos is None:
+            pos = self._g_pos
+            self._g_pos += 1
+        g, i = divmod(pos, K)
+        if (g - 2) in self._g_open:
+            raise RuntimeError("collect() earlier tickets first: the gather ring still holds their group")
+        ring = self._dev(f"gather_ring{g & 1}", cap * K)
+        if self._g_last[g & 1] is not None and g not in self._g_open:
+            mem.wait_event(self._g_last[g & 1])          # the gather of group g - 2 has read this ring
+            self._g_last[g & 1] = None
+        self._g_open.setdefault(g, [0, []])
+        mem.copy_bytes(ring, i * cap, d_stage, 0, cap)
+        ev = mem.event()
+        ev.record()
+        tk.g_pos, tk.g_ev = pos, ev
+
+    def _entry_done(self, tk):
+        """collect() has accepted the step's tables: its ring entry is final.  The K-th accepted
+        entry of a group issues the group's all-gather."""
+        if tk.g_pos is None:
+            return
+        g = tk.g_pos // self.gather_every
+        ent = self._g_open[g]
+        ent[0] += 1
+        ent[1].append(tk.g_ev)
+        if ent[0] == self.gather_every:
+            self._issue_gather(g, self.gather_every)
+
+    def _issue_gather(self, g, n_valid):
+        """ONE NCCL all-gather (NVLink 5 / NVSwitch) of a group of `gather_every` staged steps, on
+        its own stream behind the ring copies only, so no kernel of a later step queues behind
+        the collective (which waits for the slowest rank).  The destination rank brings the
+        gathered blob to the host; gathered() hands it out.  Always issued from the host in
+        program order (a collective inside a replayed CUDA graph left the process group unable
+        to shut down)."""
+        mem, K = self.mem, self.gather_every
+        cap, world = self._gather_cap, self.dist.get_world_size()
+        ring = self._dev(f"gather_ring{g & 1}", cap * K)
+        events = self._g_open.pop(g, [0, []])[1]
+        for i in range(n_valid, K):                           # entries of a partial (or empty) last group
+            mem.zero_bytes(ring, 32, i * cap)
+        if n_valid < K:
+            ev = mem.event()
+            ev.record()
+            events = events + [ev]
+        d_all = self._dev(f"gather_all{g & 1}", cap * K * world)
+        rec = {"group": g, "n": n_valid, "np": None, "cap": cap, "world": world}
+        with mem.side(4, events) as br:
+            mem.all_gather_bytes(d_all, ring, cap * K, self.dist)
             if self.dist.get_rank() == self.gather_dst:
-                g_np, g_t = self._pinned(f"pin_gather{slot}", cap * world)
-                mem.download_async(g_t, d_all, cap * world)
-                tk.gather_np, tk.gather_pack = g_np, cap
-        tk.gather_event = br.event if br is not None else None
-        self._gather_ev[slot] = tk.gather_event
+                g_np, g_t = self._pinned(f"pin_gather{g & 1}", cap * K * world)
+                mem.download_async(g_t, d_all, cap * K * world)
+                rec["np"] = g_np
+        rec["event"] = br.event
+        self._g_last[g & 1] = br.event
+        self._g_issued.append(rec)
+        self._g_count += 1
+
+    def gathered(self, block=False):
+        """Finished gathers since the last call, oldest first: on the destination rank a list of
+        {"group", "per_rank": [rank][entry] -> (table arena, adhesion rows, comp_off)}; [] elsewhere
+        (the collectives are still waited for when block is set)."""
+        out = []
+        while self._g_issued:
+            rec = self._g_issued[0]
+            if block:
+                rec["event"].synchronize()
+            elif not rec["event"].query():
+                break
+            self._g_issued.pop(0)
+            if rec["np"] is None:
+                continue
+            K, cap, world = self.gather_every, rec["cap"], rec["world"]
+            blobs = rec["np"][: world * K * cap].reshape(world, K, cap)
+            per_rank = []
+            for r in range(world):
+                ents = []
+                for i in range(K):
+                    arena_b, rows, co_off, co_n = (int(v) for v in blobs[r, i, :32].view(np.int64))
+                    if arena_b <= 0:
+                        continue
+                    a0 = 32 + _al(arena_b)
+                    arena = blobs[r, i, 32: 32 + arena_b].copy()
+                    ents.append((arena, blobs[r, i, a0: a0 + COMP.itemsize * rows].view(COMP).copy(),
+                                 arena[co_off: co_off + 4 * co_n].view(np.int32)))
+                per_rank.append(ents)
+            out.append({"group": rec["group"], "per_rank": per_rank})
+        return out
+
+    def finish(self):
+        """End of the job (or of a timed run): gathers the partial last group, issues the empty
+        gathers a rank with fewer steps still owes (begin_distributed), waits for every gather
+        and returns what gathered() has not handed out yet.  Every rank must call it."""
+        if self.dist is None or self.dist.get_world_size() == 1 or self._gather_cap is None:
+            return []
+        for g in sorted(self._g_open):
+            self._issue_gather(g, self._g_open[g][0])
+        while self._g_total is not None and self._g_count < self._g_total:
+            g = self._g_pos // self.gather_every + 1 + self._g_count          # any unused group id
+            self._g_open[g] = [0, []]
+            if self._g_last[g & 1] is not None:
+                self.mem.wait_event(self._g_last[g & 1])
+            self._issue_gather(g, 0)
+        out = self.gathered(block=True)
+        # a later run starts on fresh groups
+        self._g_pos = (self._g_pos + self.gather_every - 1) // self.gather_every * self.gather_every
+        self._g_total, self._g_count = None, 0
+        return out
 
     def collect(self, tk):
         """Waits for a submitted step and unpacks its host tables."""
@@ -772,12 +891,14 @@ class FrameBatchJob:
         NR, NU, NP, Ci = pl.NR, pl.NU, pl.NP, pl.Ci
         P_FRET, P_INT, P_FA = pl.P_FRET, pl.P_INT, pl.P_FA
         tk.event.synchronize()
-        if getattr(tk, "gather_event", None) is not None:
-            tk.gather_event.synchronize()
         OV = lambda name: O.view(tk.pout_np, name)
-        if int(OV("miss")[0]) != 0:                        # a sampled window missed a wanted rank: exact rerun
+        if int(OV("miss")[0]) != 0:
+            # a sampled window missed a wanted rank: exact rerun with full histograms.  The rerun is
+            # rank-local (it re-stages the SAME entry of the gather ring and issues no collective),
+            # so ranks that miss and ranks that do not keep the same sequence of collectives
             self.window_misses += 1
-            return self.run(tk.planes, tk.polys, full_hist=True)
+            return self.collect(self.submit(tk.planes, tk.polys, full_hist=True, _pos=tk.g_pos))
+        self._entry_done(tk)
         params = OV("params")[:NP].copy()
         res.d2h_bytes = O.size
         # regions the fused ROI kernel left to the full-histogram kernels, by reason (ipb_roifused.cuh)
@@ -818,23 +939,11 @@ class FrameBatchJob:
                 res.d2h_bytes += COMP.itemsize * total
             else:
                 res.fa_comps = np.zeros(0, dtype=COMP)
-        # gathered[r] = (packed table arena, adhesion rows) of rank r, on the destination rank only
-        res.gathered = None
-        if tk.gather_np is not None:
-            world = self.dist.get_world_size()
-            blobs = tk.gather_np[: world * tk.gather_pack].reshape(world, tk.gather_pack)
-            res.gathered, res.gathered_comp_off = [], []
-            for r in range(world):
-                arena_b, rows, co_off, co_n = (int(v) for v in blobs[r, :32].view(np.int64))
-                a0 = 32 + _al(arena_b)
-                arena = blobs[r, 32: 32 + arena_b]
-                res.gathered.append((arena, blobs[r, a0: a0 + COMP.itemsize * rows].view(COMP)))
-                res.gathered_comp_off.append(arena[co_off: co_off + 4 * co_n].view(np.int32))
         return res
 
-    def run(self, planes, polys_per_frame, full_hist=False):
+    def run(self, planes, polys_per_frame, full_hist=False, _pos=None):
         """One synchronous step: submit + collect."""
-        return self.collect(self.submit(planes, polys_per_frame, full_hist))
+        return self.collect(self.submit(planes, polys_per_frame, full_hist, _pos))
 
     def _n_hist_planes(self):
         """Distinct uint16 planes per frame that the histogram stage reads."""

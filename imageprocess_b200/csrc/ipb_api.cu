@@ -332,22 +332,31 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int unif
 
 int ipb_roi_stats_fused(const void* regions, int n_regions, const void* jobs, int n_jobs, const uint32_t* mask_pool,
                         int H, int W, const uint16_t* planes, const float* bvals, void* out, uint32_t* scratch,
-                        int64_t stride_words, int n_ctas, uint32_t* counter, uint8_t* flags, void* stream)
+                        int64_t stride_words, int n_ctas, uint32_t* counter, uint8_t* flags, uint8_t* wide_flags,
+                        void* stream)
 {
     IPB_REQUIRE(n_regions >= 0 && n_jobs >= 0, "ipb_roi_stats_fused: negative count");
-    IPB_REQUIRE(flags && counter, "ipb_roi_stats_fused: null flags / counter");
-    IPB_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(uint32_t), (cudaStream_t)stream), "memset counter");
+    IPB_REQUIRE(flags && counter && wide_flags, "ipb_roi_stats_fused: null flags / counter");
+    IPB_CUDA_TRY(cudaMemsetAsync(counter, 0, 2 * sizeof(uint32_t), (cudaStream_t)stream), "memset counter");
     if (n_regions > 0) IPB_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_regions, (cudaStream_t)stream), "memset flags");
     if (n_jobs == 0) return IPB_OK;
-    IPB_REQUIRE(regions && jobs && mask_pool && planes && bvals && out && scratch && stride_words > 0 && n_ctas > 0 &&
-                H > 0 && W > 0, "ipb_roi_stats_fused: bad argument");
+    IPB_CUDA_TRY(cudaMemsetAsync(wide_flags, 0, (size_t)n_jobs, (cudaStream_t)stream), "memset wide flags");
+    IPB_REQUIRE(regions && jobs && mask_pool && planes && bvals && out && scratch && stride_words > 0 &&
+                stride_words <= (1ll << 30) && n_ctas > 0 && H > 0 && W > 0, "ipb_roi_stats_fused: bad argument");
     const int smem = IPB_RF_SMEM_BYTES;
-    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_roi_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "roi_fused smem");
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_roi_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "roi_fused smem");
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_roi_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "roi_fused smem");
     const int grid = n_ctas < n_jobs ? n_ctas : n_jobs;
-    IPB_LAUNCH(ipb_k_roi_fused, dim3(grid), dim3(IPB_RF_THREADS), (size_t)smem, stream, (const IpbRegion*)regions,
+    IPB_LAUNCH(ipb_k_roi_fused<false>, dim3(grid), dim3(IPB_RF_THREADS), (size_t)smem, stream, (const IpbRegion*)regions,
                (const IpbRoiJob*)jobs, n_jobs, mask_pool, H, W, planes, bvals, (IpbStatOut*)out, scratch,
-               (unsigned long long)stride_words, counter, (unsigned char*)flags);
-    return ipb_check_launch("ipb_k_roi_fused");
+               (unsigned long long)stride_words, counter, (unsigned char*)flags, (unsigned char*)wide_flags);
+    int rc = ipb_check_launch("ipb_k_roi_fused");
+    if (rc) return rc;
+    // the jobs handed on by the first launch (usually none: every CTA scans its share of the flags and leaves)
+    IPB_LAUNCH(ipb_k_roi_fused<true>, dim3(grid), dim3(IPB_RF_THREADS), (size_t)smem, stream, (const IpbRegion*)regions,
+               (const IpbRoiJob*)jobs, n_jobs, mask_pool, H, W, planes, bvals, (IpbStatOut*)out, scratch,
+               (unsigned long long)stride_words, counter + 1, (unsigned char*)flags, (unsigned char*)wide_flags);
+    return ipb_check_launch("ipb_k_roi_fused<wide>");
 }
 
 // ---------------------------------------------------------------- focal-adhesion chain

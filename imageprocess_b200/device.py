@@ -54,6 +54,29 @@ class _Branch:
         return self.ctx.__exit__(*a)
 
 
+class _Side:
+    def __init__(self, mem, idx, events):
+        self.mem, self.idx, self.events, self.event = mem, idx, list(events), None
+
+    def __enter__(self):
+        mem, torch = self.mem, self.mem.torch
+        side = mem.__dict__.setdefault("_side", {})
+        if self.idx not in side:
+            side[self.idx] = torch.cuda.Stream(device=mem.device)
+        self.s = side[self.idx]
+        for ev in self.events:
+            self.s.wait_event(ev)
+        self.ctx = torch.cuda.stream(self.s)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        ev = self.mem.torch.cuda.Event()
+        ev.record(self.s)
+        self.event = ev
+        return self.ctx.__exit__(*a)
+
+
 class TorchMem:
     """CUDA memory through torch (caching allocator, current stream)."""
 
@@ -146,6 +169,11 @@ class TorchMem:
 
     def wait_event(self, ev):
         self.torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def side(self, idx, events):
+        """Context manager: work enqueued inside goes to side stream `idx`, ordered after `events`
+        only (NOT after the rest of the current stream); never joined -- its .event is the caller's."""
+        return _Side(self, idx, events)
 
     def graph(self):
         """(CUDA graph, capture context): work enqueued inside the context on the current stream

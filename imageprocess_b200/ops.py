@@ -41,7 +41,7 @@ class RoiMasks:
 KERNELS_PER_CALL = {"ipb_fa_segment": 6,   # per-crop shared-memory path (14 on the one-kernel-per-phase path)
                      "ipb_rasterize_rois": 1, "ipb_hist_u16": 1, "ipb_hist_quantiles": 1,
                     "ipb_scatter_qvalues": 1, "ipb_fret_eps": 1, "ipb_fa_params": 1,
-                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_roi_stats_fused": 1, "ipb_region_dilate": 2, "ipb_hist_select": 3, "ipb_hist_planes": 1}
+                    "ipb_fret_pixels": 1, "ipb_region_stats": 1, "ipb_roi_stats_fused": 2, "ipb_region_dilate": 2, "ipb_hist_select": 3, "ipb_hist_planes": 1}
 
 
 class Engine:

@@ -221,7 +221,9 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int unif
  * (FRET/fret_ratio_builder.py:342-362).
  *   scratch   uint32 [n_ctas][stride_words]: per-CTA list of the ratio's in-window keys;
  *             ipb_roi_stats_fused_stride() gives a sufficient stride for a region rect
- *   counter   uint32 [1] job counter, flags uint8 [n_regions]: both cleared by the call
+ *   counter   uint32 [2] job counters, flags uint8 [n_regions] (0, or why the region was left to
+ *             ipb_region_stats), wide_flags uint8 [n_jobs] (jobs with a very broad uint16 distribution,
+ *             handed from the first launch to the second): all cleared by the call
  *   n_ctas    persistent CTAs (ipb_roi_stats_fused_ctas(): two per SM)                            */
 typedef struct {
     int32_t region;
@@ -242,7 +244,7 @@ typedef struct {
 int ipb_roi_stats_fused(const void* regions, int n_regions, const void* jobs /* ipb_roi_job[] dev */, int n_jobs,
                         const uint32_t* mask_pool, int H, int W, const uint16_t* planes, const float* bvals,
                         void* out /* ipb_stat_out[] */, uint32_t* scratch, int64_t stride_words, int n_ctas,
-                        uint32_t* counter, uint8_t* flags, void* stream);
+                        uint32_t* counter, uint8_t* flags, uint8_t* wide_flags, void* stream);
 
 /* ------------------------------------------------------------------ focal-adhesion chain
  * Replaces analyze_fa_crop (INT/FA_Analyzer.py:123-195) for a ragged batch of crops in one

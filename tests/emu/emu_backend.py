@@ -67,6 +67,22 @@ class NumpyMem:
         def elapsed_time(self, other):
             return 0.0
 
+        def query(self):
+            return True
+
+    class _SideCtx:
+        def __init__(self):
+            self.event = NumpyMem._Event()
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    def side(self, idx, events):
+        return NumpyMem._SideCtx()
+
     def event(self):
         return NumpyMem._Event()
 

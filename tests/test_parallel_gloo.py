@@ -79,7 +79,11 @@ def _job_worker(rank, world, port, q):
 
 def _job_worker_body(rank, world, port, q):
     """Each rank runs the product's FrameBatchJob (kernels in the emulated build) on its block of
-    frames; every step all-gathers the packed tables; rank 0 checks what it received."""
+    frames for several steps; the staged tables go out with ONE all-gather per `gather_every`
+    steps (+ the partial last group at finish()); rank 0 checks what it received.  Rank 1's second
+    step carries a bright plane: its sampled percentile window misses deterministically and the
+    step is repeated with full histograms -- the rerun must stay rank-local (a
+    rerun that issued its own collective desynchronised the ranks)."""
     import torch.distributed as dist
     from imageprocess_b200 import batch
     from imageprocess_b200.ops import Engine
@@ -93,32 +97,57 @@ def _job_worker_body(rank, world, port, q):
     fa_params = {"alpha": 2.0, "min_area_um": 0.05, "max_area_um": 5.0, "close_radius": 1, "subtract_bg": True}
     task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4, "percentile": 1.0,
             "per_channel_p": False, "ch_p_map": {}}
+    n_steps = {0: 3, 1: 2}                                    # ranks own a different number of steps
 
-    def run_block(r, with_dist):
+    def planes_of(r, step):
         lo, hi = parallel.shard_range(len(scenes), r, world)
         planes = np.stack([np.stack([d, a]) for d, a, _ in scenes[lo:hi]])
-        job = batch.FrameBatchJob(eng, planes.shape, stages=("int", "fa"), int_task=task, fa_params=fa_params, fa_px=0.112)
-        job.dist = dist if with_dist else None
-        return job, job.run(eng.mem.from_host(planes), [sc[2] for sc in scenes[lo:hi]])
+        planes = np.roll(planes, 3 * step, axis=-1).copy()    # a different batch every step
+        if r == 1 and step == 1:
+            planes[0, 0] = 40000 + planes[0, 0] % 512          # above the 15-bit sample histogram: deterministic window miss
+        return planes, [sc[2] for sc in scenes[lo:hi]]
 
-    job, res = run_block(rank, True)
+    def make_job(r, with_dist):
+        planes, _ = planes_of(r, 0)
+        job = batch.FrameBatchJob(eng, planes.shape, stages=("int", "fa"), int_task=task, fa_params=fa_params, fa_px=0.112)
+        job.pq_min_px = 0                                     # sampled windows even on these small frames
+        job.gather_every = 2
+        job.dist = dist if with_dist else None
+        return job
+
+    job = make_job(rank, True)
+    job.begin_distributed(n_steps[rank])
+    got = []
+    for step in range(n_steps[rank]):
+        planes, polys = planes_of(rank, step)
+        job.run(eng.mem.from_host(planes), polys)
+        got += job.gathered()
+    got += job.finish()
+    misses = job.window_misses
     ok = True
     if rank == 0:
-        assert res.gathered is not None and len(res.gathered) == world
+        assert [g["group"] for g in got] == sorted(g["group"] for g in got) and len(got) == 2, [g["group"] for g in got]
+        per_rank = [[e for g in got for e in g["per_rank"][r]] for r in range(world)]
+        assert [len(x) for x in per_rank] == [n_steps[0], n_steps[1]], [len(x) for x in per_rank]
         for r in range(world):
-            jr, want = run_block(r, False)                    # what rank r must have produced
-            O = jr._plans[next(iter(jr._plans))].O
-            arena, comps = res.gathered[r]
-            ok &= np.array_equal(O.view(arena, "comp_off")[: want.n_rois + 1], want.fa_comp_off)
-            # the header names the section, so a receiver with a different layout can read it too
-            ok &= np.array_equal(res.gathered_comp_off[r], want.fa_comp_off)
-            n = int(want.fa_comp_off[-1])
-            ok &= np.array_equal(comps[:n], want.fa_comps)
-            so = O.view(arena, "stat_out")[: want.int_stat.size].reshape(want.int_stat.shape)
-            ok &= bool((so["n"] == want.int_stat["n"]).all() and (so["q"] == want.int_stat["q"]).all())
-        q.put(bool(ok))
+            jr = make_job(r, False)
+            for step in range(n_steps[r]):
+                planes, polys = planes_of(r, step)
+                want = jr.run(eng.mem.from_host(planes), polys)          # what rank r must have produced
+                O = jr._plans[next(iter(jr._plans))].O
+                arena, comps, comp_off = per_rank[r][step]
+                ok &= np.array_equal(O.view(arena, "comp_off")[: want.n_rois + 1], want.fa_comp_off)
+                # the header names the section, so a receiver with a different layout can read it too
+                ok &= np.array_equal(comp_off, want.fa_comp_off)
+                n = int(want.fa_comp_off[-1])
+                ok &= np.array_equal(comps[:n], want.fa_comps)
+                so = O.view(arena, "stat_out")[: want.int_stat.size].reshape(want.int_stat.shape)
+                ok &= bool((so["n"] == want.int_stat["n"]).all() and (so["q"] == want.int_stat["q"]).all())
+                bg = O.view(arena, "params")[jr._plans[next(iter(jr._plans))].P_INT:][: want.int_bg.size]
+                ok &= np.array_equal(bg.reshape(want.int_bg.shape), want.int_bg)
+        q.put((bool(ok), misses))
     else:
-        assert res.gathered is None
+        assert got == [] and misses >= 1, misses               # the bright plane did miss, and was repeated locally
     dist.barrier()
     dist.destroy_process_group()
 
@@ -132,7 +161,7 @@ def test_job_all_gather_gloo():
     for p in procs:
         p.start()
     got = q.get(timeout=300)
-    assert got is True, got
+    assert got == (True, 0), got
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
