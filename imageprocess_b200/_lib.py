@@ -41,6 +41,12 @@ _PROTOS.update({
     "ipb_eps_from_stat": [_vp, _vp, _i, _f, _vp, _vp],
     "ipb_hist_planes": [_vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "ipb_hist_select": [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ipb_selftest_fdiv": [_vp, _vp, _i64, _vp, _vp],
+    "ipb_hist_sizes": [_i, _i, _i, _vp],
+    "ipb_hist_select_sizes": [_i, _i, _vp],
+    "ipb_roi_stats_fused_sizes": [_i, _i, _i, _i, _i, _vp],
+    "ipb_fa_segment_sizes": [_i, _vp, _i, _vp],
+    "ipb_region_dilate_sizes": [_i, _vp, _vp],
 })
 _RESTYPE = {"ipb_last_error": ctypes.c_char_p}
 
@@ -72,6 +78,12 @@ class Lib:
             msg = self.c.ipb_last_error()
             raise IpbError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
         return rc
+
+    def sizes(self, name, n_out, *args):
+        """Calls a workspace-size query (ipb_*_sizes): returns its int64 results as a list."""
+        out = (ctypes.c_longlong * n_out)()
+        self.call(name, *args, ctypes.cast(out, ctypes.c_void_p))
+        return [int(v) for v in out]
 
     def exported(self):
         return list(_PROTOS) + list(_RESTYPE)

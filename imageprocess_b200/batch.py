@@ -590,6 +590,7 @@ class FrameBatchJob:
         d_out = self._dev("d_out", O.size)
         op = lambda name: O.ptr(d_out.ptr, name)
 
+        mem.nvtx_mark("ipb:tables+raster")
         # ---- rasterise every unique ROI once
         if pl.need_mpl:
             m_pool = self._dev("m_pool", 4 * pl.m_words)
@@ -610,6 +611,7 @@ class FrameBatchJob:
                          tp("f_srect"), tp("f_org"), tp("uset"), tp("f_moff"), pl.f_max_rows, pl.f_max_wpr,
                          f_pool.ptr, op("f_area"), None, self.union_wpr, H, mem.stream)
 
+        mem.nvtx_mark("ipb:percentiles")
         # ---- histograms -> percentiles -> per-frame scalars
         d_hist = self._dev("hist", 4 * 65536 * max(NH, 1))
         d_hstat = self._dev("hstat", 8 * 4 * max(NH, 1))
@@ -644,6 +646,7 @@ class FrameBatchJob:
         mem.join()                                   # masks and per-frame scalars are ready from here on
         use_fused = self.fused_roi and pl.NF > 0
 
+        mem.nvtx_mark("ipb:fa_chain")
         # ---- focal adhesions
         if "fa" in st and NR and pl.total_px > 0:
             words = pl.fa_words
@@ -671,6 +674,7 @@ class FrameBatchJob:
             fa_ran = False
             if "fa" in st:
                 mem.zero_bytes(d_out, O.sections["comp_off"][3], O.sections["comp_off"][0])
+        mem.nvtx_mark("ipb:roi_stats")
         # ---- per-ROI statistics (side stream): one walk of each ROI for both channels and the ratio;
         #      else the uint16 jobs of the full-histogram kernel
         with branch(1):
@@ -685,6 +689,7 @@ class FrameBatchJob:
                 lib_call("ipb_region_stats", tp("regions"), tp("stat_jobs"), pl.n_u16, SRC_U16, m_pool.ptr, None, 0,
                          H, W, planes.ptr, None, op("params"), op("stat_out"), None, mem.stream)
 
+        mem.nvtx_mark("ipb:fret_pixels")
         # ---- fused FRET pass
         d_R = None
         if "fret" in st:
@@ -697,6 +702,7 @@ class FrameBatchJob:
             res.R = ops_view(d_R, np.float32, (F, H, W), mem)
             res.R_roi = ops_view(d_Rroi, np.float32, (F, H, W), mem) if d_Rroi is not None else None
 
+        mem.nvtx_mark("ipb:roi_stats_rerun")
         # ---- per-ROI statistics of the ratio image (full-histogram kernel), or -- after the fused ROI
         #      kernel -- the rerun of the regions it flagged (usually none: a few CTAs scan the flags)
         if use_fused:
@@ -715,6 +721,7 @@ class FrameBatchJob:
         if "fa" in st:
             res.fa_rect, res.fa_crops = pl.fa_rect, pl.fa_crops
 
+        mem.nvtx_mark("ipb:results_d2h")
         # ---- results: one packed D2H (+ a first slice of the adhesion table), then an event;
         #      the host reads them in collect() while the device may already run the next step
         pout_np, pout_t = self._pinned(f"pin_out{slot}", O.size)
@@ -755,6 +762,7 @@ class FrameBatchJob:
             if rows_sent:
                 mem.copy_bytes(d_stage, 32 + _al(O.size), d_comps, 0, COMP.itemsize * rows_sent)
             tk.g_stage = (d_stage, cap, world)               # the collective itself is issued by _issue_gather()
+        mem.nvtx_mark(None)
         return tk
 
     # ------------------------------------------------------------------ N ranks: table gathers

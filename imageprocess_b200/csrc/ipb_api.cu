@@ -52,7 +52,8 @@ static int ipb_launch_region_stats(const void* regions, const void* jobs, int n_
 {
     const int smem = IPB_RS_SMEM_BYTES;
     IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_region_stats<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "region_stats smem");
-    const int grid = (only && n_jobs > 148) ? 148 : n_jobs;       // a rerun of flagged regions: few CTAs scan the list
+    // a rerun of flagged regions: every CTA scans 32 jobs of the list at a time
+    const int grid = only ? (((n_jobs + 31) / 32) < 148 ? ((n_jobs + 31) / 32) : 148) : n_jobs;
     IPB_LAUNCH(ipb_k_region_stats<SRC>, dim3(grid), dim3(IPB_RS_THREADS), (size_t)smem, stream,
                (const IpbRegion*)regions, (const IpbStatJob*)jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
                planes, images, bvals, (IpbStatOut*)out, smem, (const unsigned char*)only);
@@ -342,7 +343,7 @@ int ipb_roi_stats_fused(const void* regions, int n_regions, const void* jobs, in
     if (n_jobs == 0) return IPB_OK;
     IPB_CUDA_TRY(cudaMemsetAsync(wide_flags, 0, (size_t)n_jobs, (cudaStream_t)stream), "memset wide flags");
     IPB_REQUIRE(regions && jobs && mask_pool && planes && bvals && out && scratch && stride_words > 0 &&
-                stride_words <= (1ll << 30) && n_ctas > 0 && H > 0 && W > 0, "ipb_roi_stats_fused: bad argument");
+                stride_words * (int64_t)n_ctas < (1ll << 32) && n_ctas > 0 && H > 0 && W > 0, "ipb_roi_stats_fused: bad argument");
     const int smem = IPB_RF_SMEM_BYTES;
     IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_roi_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "roi_fused smem");
     IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_roi_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "roi_fused smem");
@@ -517,6 +518,90 @@ int ipb_eps_from_stat(const void* stat_out, const int32_t* row_of_frame, int n_f
     IPB_LAUNCH(ipb_k_eps_from_stat, dim3(ipb_div_up(n_frames, 128)), dim3(128), 0, stream,
                (const IpbStatOut*)stat_out, row_of_frame, n_frames, eps_abs, fparams);
     return ipb_check_launch("ipb_k_eps_from_stat");
+}
+
+int ipb_selftest_fdiv(const float* a, const float* b, int64_t n, uint32_t* mismatches, void* stream)
+{
+    IPB_REQUIRE(a && b && mismatches && n >= 0, "ipb_selftest_fdiv: bad argument");
+    if (n == 0) return IPB_OK;
+    IPB_LAUNCH(ipb_k_selftest_fdiv, dim3(592), dim3(256), 0, stream, a, b, (long long)n, mismatches);
+    return ipb_check_launch("ipb_k_selftest_fdiv");
+}
+
+// ---------------------------------------------------------------- workspace sizes (host-side, no device work)
+int ipb_hist_sizes(int n_jobs, int frame_h, int has_masked_stride, int64_t* bytes)
+{
+    IPB_REQUIRE(bytes && n_jobs >= 0 && frame_h >= 0, "ipb_hist_sizes: bad argument");
+    const int64_t n = n_jobs > 0 ? n_jobs : 1;
+    bytes[0] = n * 65536 * (int64_t)sizeof(uint32_t);                 // hist
+    bytes[1] = n * 4 * (int64_t)sizeof(uint64_t);                     // stats
+    bytes[2] = has_masked_stride ? n * frame_h * (int64_t)sizeof(uint64_t) : 0;   // row_rank_scratch
+    return IPB_OK;
+}
+
+int ipb_hist_select_sizes(int n_jobs, int n_q, int64_t* bytes)
+{
+    IPB_REQUIRE(bytes && n_jobs >= 0 && n_q >= 0, "ipb_hist_select_sizes: bad argument");
+    const int64_t n = n_jobs > 0 ? n_jobs : 1, q = n_q > 0 ? n_q : 1;
+    bytes[0] = n * IPB_PQ_WIN * (int64_t)sizeof(uint32_t);            // hist_win
+    bytes[1] = n * (int64_t)sizeof(IpbHistWin);                       // win
+    bytes[2] = n * (int64_t)sizeof(uint64_t);                         // cnt
+    bytes[3] = n * 4 * (int64_t)sizeof(uint64_t);                     // stats
+    bytes[4] = q * (int64_t)sizeof(IpbQOut);                          // qout
+    return IPB_OK;
+}
+
+int ipb_roi_stats_fused_sizes(int n_regions, int n_jobs, int max_rect_w, int max_rect_h, int n_sms, int64_t* out)
+{
+    IPB_REQUIRE(out && n_regions >= 0 && n_jobs >= 0 && max_rect_w >= 0 && max_rect_h >= 0 && n_sms > 0,
+                "ipb_roi_stats_fused_sizes: bad argument");
+    // list slots of a CTA: every in-window key of the largest region even when half of its pixels are
+    // in a window, for three sources (half of the slice for the ratio, a quarter per uint16 slot)
+    int64_t stride = 2 * ((int64_t)max_rect_w + 16) * max_rect_h + 16384;
+    if (stride > (1ll << 19)) stride = 1ll << 19;
+    const int n_ctas = 2 * n_sms;                                     // __launch_bounds__(256, 2)
+    out[0] = stride;                                                  // stride_words
+    out[1] = n_ctas;                                                  // n_ctas
+    out[2] = stride * n_ctas * (int64_t)sizeof(uint32_t);             // scratch bytes
+    out[3] = 2 * (int64_t)sizeof(uint32_t);                           // counter bytes
+    out[4] = n_regions > 0 ? n_regions : 1;                           // flags bytes
+    out[5] = n_jobs > 0 ? n_jobs : 1;                                 // wide_flags bytes
+    return IPB_OK;
+}
+
+int ipb_fa_segment_sizes(int n_crops, const int32_t* crop_wh /* [host] w, h per crop */, int want_labels, int64_t* out)
+{
+    IPB_REQUIRE(out && n_crops >= 0 && (n_crops == 0 || crop_wh), "ipb_fa_segment_sizes: bad argument");
+    int64_t words = 0, px = 0, rows = 0, cap = 0;
+    for (int i = 0; i < n_crops; ++i) {
+        const int64_t w = crop_wh[2 * i], h = crop_wh[2 * i + 1];
+        IPB_REQUIRE(w >= 0 && h >= 0, "ipb_fa_segment_sizes: negative crop size");
+        words += ((w + 31) / 32) * h; px += w * h; rows += h;
+        cap += ((h + 1) / 2) * ((w + 1) / 2);                         // bound on 8-connected components of an h x w image
+    }
+    if (words < 1) words = 1;
+    if (px < 1) px = 1;
+    if (rows < 1) rows = 1;
+    if (cap < 1) cap = 1;
+    out[0] = words * 4;                                               // bw_a, bw_b, rootbits, bw_final: each
+    out[1] = px * 4;                                                  // L, csize: each
+    out[2] = rows * 4;                                                // row_roots, row_base: each
+    out[3] = (int64_t)(n_crops > 0 ? n_crops : 1) * 4;                // crop_count
+    out[4] = ((int64_t)n_crops + 1) * 4;                              // comp_off
+    out[5] = cap;                                                     // comp_cap (rows)
+    out[6] = cap * (int64_t)sizeof(IpbComp);                          // comps
+    out[7] = want_labels ? px * 4 : 0;                                // labels
+    out[8] = rows;                                                    // total_rows
+    return IPB_OK;
+}
+
+int ipb_region_dilate_sizes(int n_regions, const int32_t* region_wh /* [host] w, h per region */, int64_t* out)
+{
+    IPB_REQUIRE(out && n_regions >= 0 && (n_regions == 0 || region_wh), "ipb_region_dilate_sizes: bad argument");
+    int64_t g = 0;
+    for (int i = 0; i < n_regions; ++i) g += (int64_t)region_wh[2 * i] * region_wh[2 * i + 1];
+    out[0] = g > 0 ? g : 1;                                           // g_scratch bytes (g_off[i] = bytes before region i)
+    return IPB_OK;
 }
 
 int ipb_sizeof(int what)

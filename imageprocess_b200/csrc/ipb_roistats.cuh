@@ -712,8 +712,8 @@ __device__ __forceinline__ void ipb_rs_job(unsigned jidx, const IpbRegion* __res
     }
 }
 
-// grid = n_jobs (one job per CTA), or -- with `only` -- a small grid whose CTAs stride over the job
-// list and measure only the regions flagged by the fused ROI kernel (ipb_roifused.cuh)
+// grid = n_jobs (one job per CTA), or -- with `only` -- a small grid whose CTAs scan the job list
+// 32 jobs at a time and measure only the regions flagged by the fused ROI kernel (ipb_roifused.cuh)
 template <int SRC>
 __global__ void __launch_bounds__(IPB_RS_THREADS, 1)
 ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __restrict__ jobs, int n_jobs,
@@ -723,8 +723,29 @@ ipb_k_region_stats(const IpbRegion* __restrict__ regions, const IpbStatJob* __re
                    const float* __restrict__ bvals, IpbStatOut* __restrict__ out, int smem_bytes,
                    const unsigned char* __restrict__ only /* null, or per region: != 0 -> measure it */)
 {
-    for (unsigned j = blockIdx.x; j < (unsigned)n_jobs; j += gridDim.x) {
-        __syncthreads();                                   // the previous job's shared state is dead
-        ipb_rs_job<SRC>(j, regions, jobs, mask_pool, and_bits, and_wpr, H, W, planes, images, bvals, out, smem_bytes, only);
+    if (!only) {
+        for (unsigned j = blockIdx.x; j < (unsigned)n_jobs; j += gridDim.x) {
+            __syncthreads();                               // the previous job's shared state is dead
+            ipb_rs_job<SRC>(j, regions, jobs, mask_pool, and_bits, and_wpr, H, W, planes, images, bvals, out, smem_bytes, only);
+        }
+        return;
+    }
+    __shared__ unsigned s_pick;
+    for (unsigned c0 = 32u * blockIdx.x; c0 < (unsigned)n_jobs; c0 += 32u * gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const unsigned j = c0 + threadIdx.x;
+            const bool f = j < (unsigned)n_jobs && jobs[j].src == SRC && only[jobs[j].region] != 0;
+            const unsigned b = __ballot_sync(IPB_FULL, f);
+            if (threadIdx.x == 0) s_pick = b;
+        }
+        __syncthreads();
+        unsigned pick = s_pick;
+        while (pick) {                                     // block-uniform
+            const unsigned k = (unsigned)__ffs((int)pick) - 1u;
+            pick &= pick - 1u;
+            __syncthreads();
+            ipb_rs_job<SRC>(c0 + k, regions, jobs, mask_pool, and_bits, and_wpr, H, W, planes, images, bvals, out, smem_bytes, only);
+        }
     }
 }

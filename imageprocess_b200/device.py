@@ -90,6 +90,17 @@ class TorchMem:
     def n_sms(self):
         return int(self.torch.cuda.get_device_properties(self.device).multi_processor_count)
 
+    def nvtx_mark(self, name=None):
+        """Closes the open NVTX range of this backend and opens `name` (None: just close): one range
+        per stage of a step, visible in nsys / ncu timelines, free otherwise."""
+        nv = self.torch.cuda.nvtx
+        if getattr(self, "_nvtx_open", False):
+            nv.range_pop()
+            self._nvtx_open = False
+        if name is not None:
+            nv.range_push(name)
+            self._nvtx_open = True
+
     # -- allocation
     def empty(self, shape, dtype):
         shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))

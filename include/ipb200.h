@@ -219,12 +219,12 @@ int ipb_region_stats(const void* regions, const void* jobs, int n_jobs, int unif
  * the caller then runs ipb_region_stats on the equivalent job list with only = flags.
  * Replaces quantify_stats / quantify_per_roi_multi (INT/Fluor_INT.py:494-538) and quantify_per_roi
  * (FRET/fret_ratio_builder.py:342-362).
- *   scratch   uint32 [n_ctas][stride_words]: per-CTA list of the ratio's in-window keys;
- *             ipb_roi_stats_fused_stride() gives a sufficient stride for a region rect
+ *   scratch   uint32 [n_ctas][stride_words]: per-CTA lists of in-window keys; ipb_roi_stats_fused_sizes()
+ *             gives a sufficient stride, the CTA count and every buffer size
  *   counter   uint32 [2] job counters, flags uint8 [n_regions] (0, or why the region was left to
  *             ipb_region_stats), wide_flags uint8 [n_jobs] (jobs with a very broad uint16 distribution,
  *             handed from the first launch to the second): all cleared by the call
- *   n_ctas    persistent CTAs (ipb_roi_stats_fused_ctas(): two per SM)                            */
+ *   n_ctas    persistent CTAs (two per SM)                                                         */
 typedef struct {
     int32_t region;
     int32_t plane[2];             /* uint16 plane of channel slot 0 / 1; < 0: slot unused */
@@ -315,6 +315,32 @@ int ipb_crop_normalize(const void* jobs, int n_jobs, int64_t max_px, const uint1
  * on a spectrally corrected denominator, Nesprin2_FRET_Builder.py:470-476,1484-1486).       */
 int ipb_eps_from_stat(const void* stat_out, const int32_t* row_of_frame, int n_frames, float eps_abs,
                       float* fparams, void* stream);
+
+/* Self-test of the branch-free division ipb_roi_stats_fused uses for ratios whose operands are known to
+ * lie in [5, 65536 + eps]: *mismatches (zeroed by the caller) += number of pairs (a[i], b[i]) whose
+ * quotient differs from the IEEE-rounded one (the reference's numpy division).  Must stay 0.        */
+int ipb_selftest_fdiv(const float* a, const float* b, int64_t n, uint32_t* mismatches, void* stream);
+
+/* ------------------------------------------------------------------ workspace sizes
+ * Host-side helpers (no device work, no stream): the byte size of every caller-owned buffer whose
+ * size depends on the batch, so a binding in any language can allocate from this header alone.
+ * The reference has no counterpart (numpy allocates inside every call it makes on this path, e.g. the
+ * H*W x 2 float64 point list of rasterize_polygon, INT/Fluor_INT.py:398-402).  Buffers not listed
+ * here have the sizes stated at their entry point (one struct per job / region / frame).
+ *   ipb_hist_sizes            bytes[3] = {hist, stats, row_rank_scratch}      (ipb_hist_u16 / ipb_hist_planes)
+ *   ipb_hist_select_sizes     bytes[5] = {hist_win, win, cnt, stats, qout}    (ipb_hist_select)
+ *   ipb_roi_stats_fused_sizes out[6]   = {stride_words, n_ctas, scratch bytes, counter bytes, flags bytes,
+ *                                         wide_flags bytes} for regions whose rects are at most max_rect_w x max_rect_h
+ *   ipb_fa_segment_sizes      out[9]   = {bw_a = bw_b = rootbits = bw_final bytes (each), L = csize bytes (each),
+ *                                         row_roots = row_base bytes (each), crop_count bytes, comp_off bytes,
+ *                                         comp_cap (rows), comps bytes, labels bytes (0 unless wanted), total_rows}
+ *                             for crops of crop_wh[2i] x crop_wh[2i+1] pixels
+ *   ipb_region_dilate_sizes   out[1]   = {g_scratch bytes}                                              */
+int ipb_hist_sizes(int n_jobs, int frame_h, int has_masked_stride, int64_t* bytes);
+int ipb_hist_select_sizes(int n_jobs, int n_q, int64_t* bytes);
+int ipb_roi_stats_fused_sizes(int n_regions, int n_jobs, int max_rect_w, int max_rect_h, int n_sms, int64_t* out);
+int ipb_fa_segment_sizes(int n_crops, const int32_t* crop_wh, int want_labels, int64_t* out);
+int ipb_region_dilate_sizes(int n_regions, const int32_t* region_wh, int64_t* out);
 
 #ifdef __cplusplus
 }

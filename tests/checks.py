@@ -374,6 +374,28 @@ def check_roi_fused_vs_hist(eng):
 RASTER_CHECKS.append(check_roi_fused_vs_hist)
 
 
+def check_fdiv_inrange(eng):
+    """The branch-free division of the fused ROI kernel against the IEEE-rounded one (numpy's, the
+    reference's) on operands of the shape the kernel feeds it: max(v - B, 0) + eps with v a uint16
+    sample, B a background level, eps >= 5 -- plus adversarial neighbours of exact quotients."""
+    rng = np.random.default_rng(2)
+    n = 1 << 22
+    mism = eng.mem.zeros(1, np.uint32)
+    for B, eps in ((0.0, 5.0), (361.5, 5.0), (24.0, 76.30000305175781), (1234.56787109375, 2890.25), (99.9000015258789, 65000.0)):
+        v = rng.integers(0, 65536, (2, n)).astype(np.float32)
+        a = np.maximum(v[0] - np.float32(B), np.float32(0)) + np.float32(eps)
+        b = np.maximum(v[1] - np.float32(B), np.float32(0)) + np.float32(eps)
+        # quotients that sit next to a rounding boundary: b * k and its float neighbours over b
+        k = rng.integers(1, 4096, n // 4).astype(np.float32)
+        a[: n // 4] = np.nextafter(b[: n // 4] * k, np.float32(np.inf) * rng.choice([-1, 1], n // 4).astype(np.float32))
+        da, db = eng.mem.from_host(a), eng.mem.from_host(b)
+        eng.call("ipb_selftest_fdiv", da.ptr, db.ptr, n, mism.ptr, eng.mem.stream)
+    assert int(mism.host()[0]) == 0, int(mism.host()[0])
+
+
+RASTER_CHECKS.append(check_fdiv_inrange)
+
+
 def check_graph_replay(eng):
     """The same job stepped ten times over two input buffers: from the fifth step on a step is a
     replayed CUDA graph (on the GPU; eager under the emulator).  Every step's tables must equal
