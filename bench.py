@@ -437,6 +437,121 @@ def run_ours(args):
         os._exit(0)
 
 
+# ----------------------------------------------------------------------------- other BASELINE configs
+N2_PARAMS = {"px_um": 0.223, "rim_um": 1.12, "annulus_on": False, "ann_in_um": 1.2, "ann_out_um": 2.5,
+             "bg_scope": "full", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False,
+             "donor_p": 1.0, "fret_p": 1.0, "clip_neg": True, "eps_percentile": 1.0, "ratio_mode": "FRET/Donor",
+             "use_spectral": True, "alpha": 0.12, "beta": 0.05, "g_factor": 1.1,
+             "sat_filter_on": True, "sat_threshold": 65535.0, "clip_ratio_on": True, "clip_ratio_max": 20.0}
+C5_FA = {"alpha": 1.0, "min_area_um": 1.5, "max_area_um": 30.0, "close_radius": 1, "subtract_bg": True}
+
+
+def run_other(args):
+    """`--config c5`: one 8192 x 8192 uint16 stitched FA mosaic (~1e5 adhesions, label map returned) per
+    step through the one-kernel-per-phase FA path; `--config c3s`: the Nesprin2 builder with spectral
+    bleed-through correction on 2048 x 2048 donor / FRET / acceptor-only triples.  Same JSON line as the
+    headline (C4) run; these are single-GPU figures kept under profiles/, not the driver's metric."""
+    import torch
+    import imageprocess_b200 as ipb
+    from imageprocess_b200 import batch, nesprin2, synth
+    torch.cuda.set_device(0)
+    eng = ipb.engine("cuda:0")
+    mem = eng.mem
+    if args.config == "c5":
+        size = 8192
+        img, polys = synth.fa_mosaic(seed=99, H=size, W=size, n_blobs=100000)
+        shape = (1, 1, size, size)
+        pinned_np, pinned_t = mem.pinned(shape, np.uint16)
+        pinned_np[...] = img[None, None]
+        planes = mem.empty(shape, np.uint16)
+        mem.upload_async(planes, pinned_t)
+        job = batch.FrameBatchJob(eng, shape, stages=("fa",), fa_params=C5_FA, fa_px=FA_PX, want_labels=True)
+        seen = {}
+
+        def step():
+            res = job.run(planes, [polys])
+            seen["adhesions"] = int(res.fa_comp_off[-1])
+            return res.d2h_bytes
+
+        def step_e2e():
+            mem.upload_async(planes, pinned_t)
+            return step()
+        px, h2d, bpp = size * size, int(img.nbytes), 6.0           # SURVEY 8(d): 2 B read + 4 B label map written
+        workload = f"C5-synth 8192x8192 uint16 FA mosaic, one ROI over the field, label map returned"
+        metric = "Mpix/s (8192x8192 uint16 stitched FA mosaic: CCL + regionprops)"
+        dtype, stages = "u16", ["fa"]
+    else:
+        F = max(1, min(args.frames, 8))
+        d, a, polys = synth.fret_frame(seed=1234, H=H, W=W, n_cells=N_CELLS, r_min=80, r_max=160)
+        ao = (0.3 * a + np.random.default_rng(5).poisson(50, d.shape)).astype(np.uint16)
+        frames = np.stack([np.stack([d, a, ao])] * F)
+        rng = np.random.default_rng(3)
+        for f in range(1, F):                                      # every frame holds different pixel data
+            frames[f] = np.minimum(frames[f].astype(np.uint32) + rng.integers(0, 7, frames[f].shape), 65535).astype(np.uint16)
+        shape = frames.shape
+        pinned_np, pinned_t = mem.pinned(shape, np.uint16)
+        pinned_np[...] = frames
+        planes = mem.empty(shape, np.uint16)
+        mem.upload_async(planes, pinned_t)
+        seen = {}
+
+        def step():
+            out = nesprin2.nesprin2_batch(eng, planes, shape, [polys] * F, N2_PARAMS, donor_ch=0, acc_ch=1, aonly_ch=2)
+            seen["rows"] = sum(len(r) for r in out["rows_per_frame"])
+            return 8 * F + 200 * seen["rows"]
+
+        def step_e2e():
+            mem.upload_async(planes, pinned_t)
+            return step()
+        px, h2d, bpp = F * H * W, int(frames.nbytes), 22.0         # 3 x uint16 read + R, Ralt, Dcorr, Acorr float32 written
+        workload = (f"C3-synth 2048x2048 donor/FRET/acceptor-only uint16 triples, {N_CELLS} ROIs, Nesprin2 builder with "
+                    f"use_spectral alpha=0.12 beta=0.05 g=1.1, inner rim, {F} frames per step")
+        metric = "Mpix/s (2048x2048 uint16 3ch Nesprin2 FRET with spectral correction)"
+        dtype, stages = "u16/f32", ["nesprin2"]
+    mem.sync()
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d2h = 0
+        for _ in range(steps):
+            d2h = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), d2h
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    l0 = eng.launches
+    with ClockSampler(0) as clk:
+        ms, d2h = timed(step, args.steps)
+        launches = eng.launches - l0
+        eng.profile_start()
+        ms_prof, _ = timed(step, args.steps)
+        prof = eng.profile_stop()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    value = args.steps * px / 1e6 / (ms / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    line = {"metric": metric, "value": value, "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic", "config": {"workload": workload, "l2": "inputs larger than L2 (no flush needed)", "stages": stages},
+            "e2e": {"value": args.steps * px / 1e6 / (ms_e2e / 1e3), "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+            "pipeline_roofline": {"bytes_per_px": bpp, "achieved_gbs": value * 1e6 * bpp / 1e9,
+                                  "frac_of_peak": value * 1e6 * bpp / 1e9 / peak, "peak": peak},
+            "kernels": {k: {"calls": v[0], "ms": round(v[1], 4), "share": round(v[1] / max(ms_prof, 1e-9), 4)}
+                        for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+            "seen": seen}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -446,9 +561,13 @@ def main():
     ap.add_argument("--lag", type=int, default=2, help="steps in flight before a step's tables are unpacked")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c4", choices=["c4", "c5", "c3s"],
+                    help="c4: the BASELINE metric (default); c5: 8192^2 FA mosaic; c3s: Nesprin2 with spectral correction")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "c4":
+        run_other(args)
     else:
         run_ours(args)
 

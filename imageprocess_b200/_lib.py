@@ -27,7 +27,7 @@ _PROTOS = {
     "ipb_scatter_qvalues": [_vp, _vp, _i, _vp, _vp],
     "ipb_fret_eps": [_vp, _i, _i, _i, _f, _vp, _vp],
     "ipb_fa_params": [_vp, _vp, _vp, _i, _i64, _f, _vp, _vp],
-    "ipb_fret_pixels": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ipb_fret_pixels": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "ipb_fa_segment": [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "ipb_region_stats": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -123,6 +123,7 @@ class FrameBatchJob:
         # per-ROI statistics: ONE walk of each ROI for both channels and the ratio (ipb_roi_stats_fused,
         # sampled value windows); the regions it cannot serve are repeated by the full-histogram kernels
         self.fused_roi = bool(int(os.environ.get("IPB_FUSED_ROI", "1")))
+        self.fret_moments = bool(int(os.environ.get("IPB_FRET_MOMENTS", "1")))
         self.rf_ctas = ops.RF_CTAS_PER_SM * eng.n_sms()
         self.roi_fallbacks = 0       # regions repeated by the full-histogram kernels so far
         self.pq_min_px = 1 << 18     # smaller planes take the full histograms (the sample would be most of the plane)
@@ -274,10 +275,14 @@ class FrameBatchJob:
                     j["pattern"] = np.where(masked & has_rois, PAT_MASKED, PAT_FULL)
                 hidx[("int", ci)] = sum(x.shape[0] for x in hist_jobs)
                 hist_jobs.append(j)
+        # the FA channel's integer moments (mean / std of the frame) ride on the fused FRET pass when it
+        # reads that channel anyway; else on the percentile pass over the plane
+        pl.fa_mom_from_fret = ("fa" in st and "fret" in st and self.fa_ch in (self.donor_ch, self.acc_ch) and
+                               self.fret_moments)
         if "fa" in st:
             j = np.zeros(F, dtype=HIST_JOB)
             j["plane"] = np.arange(F) * C + self.fa_ch
-            j["pattern"], j["k"], j["moments"] = PAT_STRIDE2D, 10, 1
+            j["pattern"], j["k"], j["moments"] = PAT_STRIDE2D, 10, 0 if pl.fa_mom_from_fret else 1
             hidx["fa"] = sum(x.shape[0] for x in hist_jobs)
             hist_jobs.append(j)
         hist_jobs = np.concatenate(hist_jobs) if hist_jobs else np.zeros(0, dtype=HIST_JOB)
@@ -526,7 +531,7 @@ class FrameBatchJob:
         slot = self._slot
         self._slot = (self._slot + 1) % self.n_slots
         # everything the enqueued work depends on besides the (fixed) job parameters
-        key = (pl.serial, int(planes.ptr), slot, bool(full_hist), bool(self.hist_select), bool(self.fused_roi),
+        key = (pl.serial, int(planes.ptr), slot, bool(full_hist), bool(self.hist_select), bool(self.fused_roi), bool(self.fret_moments),
                bool(self.overlap), int(self.fa_path), int(self.pq_min_px), self.dist is not None)
         graphable = self.use_graphs and hasattr(mem, "graph") and self.eng.prof is None and not pl.host_bg
         ent = self._graphs.get(key) if graphable else None
@@ -639,9 +644,12 @@ class FrameBatchJob:
             den_slot = FP_BD if pl.numer_is_acc else FP_BA
             lib_call("ipb_fret_eps", d_qout.ptr + Q_OUT.itemsize * pl.qidx["fret_eps"], F, den_slot,
                      int(bool(self.fret_p["clip_neg"])), 5.0, op("params") + 4 * P_FRET, mem.stream)
-        if "fa" in st:
-            lib_call("ipb_fa_params", d_hstat.ptr, tp("fa_stat_idx"), d_qout.ptr + Q_OUT.itemsize * pl.qidx["fa"],
-                     F, H * W, float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, mem.stream)
+        fa_params_call = lambda: lib_call("ipb_fa_params", d_hstat.ptr, tp("fa_stat_idx"),
+                                          d_qout.ptr + Q_OUT.itemsize * pl.qidx["fa"], F, H * W,
+                                          float(np.float32(self.fa_cfg["alpha"])), op("params") + 4 * P_FA, mem.stream)
+        late_fa = "fa" in st and pl.fa_mom_from_fret         # mean / std arrive with the FRET pass
+        if "fa" in st and not late_fa:
+            fa_params_call()
 
         mem.join()                                   # masks and per-frame scalars are ready from here on
         use_fused = self.fused_roi and pl.NF > 0
@@ -659,14 +667,18 @@ class FrameBatchJob:
             d_comps = self._dev("comps", COMP.itemsize * pl.comp_cap)
             d_lab = self._dev("labels", 4 * pl.total_px) if self.want_labels else None
             cfgf = self.fa_cfg
-            with branch(2):
-                lib_call("ipb_fa_segment", tp("crops"), NR, pl.fa_max_h, pl.total_rows, planes.ptr, H, W,
-                         op("params") + 4 * P_FA, f_pool.ptr,
-                         float(cfgf["min_px"]) if cfgf["min_px"] > 0 else 0.0,
-                         int(cfgf["close_radius"]) if cfgf["close_radius"] > 0 else 0,
-                         bwA.ptr, bwB.ptr, d_L.ptr, d_cs.ptr, rootb.ptr, d_rr.ptr, d_rb.ptr, d_cc.ptr,
-                         bwF.ptr, op("comp_off"), d_comps.ptr, pl.comp_cap,
-                         d_lab.ptr if d_lab is not None else None, int(self.fa_path), tp("crop_order"), mem.stream)
+
+            def run_fa():
+                with branch(2):
+                    lib_call("ipb_fa_segment", tp("crops"), NR, pl.fa_max_h, pl.total_rows, planes.ptr, H, W,
+                             op("params") + 4 * P_FA, f_pool.ptr,
+                             float(cfgf["min_px"]) if cfgf["min_px"] > 0 else 0.0,
+                             int(cfgf["close_radius"]) if cfgf["close_radius"] > 0 else 0,
+                             bwA.ptr, bwB.ptr, d_L.ptr, d_cs.ptr, rootb.ptr, d_rr.ptr, d_rb.ptr, d_cc.ptr,
+                             bwF.ptr, op("comp_off"), d_comps.ptr, pl.comp_cap,
+                             d_lab.ptr if d_lab is not None else None, int(self.fa_path), tp("crop_order"), mem.stream)
+            if not late_fa:
+                run_fa()
             res.fa_bw = ops_view(bwF, np.uint32, (words,), mem)
             res.fa_labels = ops_view(d_lab, np.int32, (pl.total_px,), mem) if d_lab is not None else None
             fa_ran = True
@@ -698,7 +710,13 @@ class FrameBatchJob:
             cfg = fret_cfg(self.fret_p, C, self.donor_ch, self.acc_ch)
             lib_call("ipb_fret_pixels", planes.ptr, F, H, W, cfg.ctypes.data, op("params") + 4 * P_FRET,
                      union_ptr, self.union_wpr, tp("union_idx"), d_R.ptr, None,
-                     d_Rroi.ptr if d_Rroi is not None else None, None, None, mem.stream)
+                     d_Rroi.ptr if d_Rroi is not None else None, None, None,
+                     d_hstat.ptr if late_fa else None, tp("fa_stat_idx") if late_fa else None,
+                     int(self.fa_ch == self.acc_ch and self.fa_ch != self.donor_ch), mem.stream)
+            if late_fa:                                      # the frame's mean / std are complete now
+                fa_params_call()
+                if fa_ran:
+                    run_fa()
             res.R = ops_view(d_R, np.float32, (F, H, W), mem)
             res.R_roi = ops_view(d_Rroi, np.float32, (F, H, W), mem) if d_Rroi is not None else None
 

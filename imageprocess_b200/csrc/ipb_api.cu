@@ -274,10 +274,11 @@ int ipb_fa_params(const uint64_t* stats, const int32_t* stat_idx, const void* qo
 int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const void* cfg_host,
                     const float* fparams, const uint32_t* union_bits, int union_wpr,
                     const int32_t* union_idx, float* R, float* Ralt, float* Rroi, float* Dcorr,
-                    float* Acorr, void* stream)
+                    float* Acorr, uint64_t* mom_stats, const int32_t* mom_idx, int mom_acceptor, void* stream)
 {
     if (n_frames <= 0) return IPB_OK;
     IPB_REQUIRE(planes && cfg_host && fparams && H > 0 && W > 0, "ipb_fret_pixels: bad argument");
+    IPB_REQUIRE(!mom_stats || mom_idx, "ipb_fret_pixels: moments need mom_idx");
     IpbFretCfg cfg;
     memcpy(&cfg, cfg_host, sizeof(cfg));
     IPB_REQUIRE(cfg.n_ch > 0 && cfg.donor_ch >= 0 && cfg.donor_ch < cfg.n_ch && cfg.acc_ch >= 0 &&
@@ -292,7 +293,8 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W, const vo
     const bool plain = !cfg.sat_on && !cfg.use_spectral && !cfg.clip_on;
 #define IPB_FRET_LAUNCH(ALT, PLAIN)                                                                                    \
     IPB_LAUNCH((ipb_k_fret_pixels<ALT, PLAIN>), dim3((unsigned)blocks, (unsigned)n_frames), dim3(256), 0, stream, planes, \
-               n_frames, H, W, cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr)
+               n_frames, H, W, cfg, fparams, union_bits, union_wpr, union_idx, R, Ralt, Rroi, Dcorr, Acorr,                \
+               (unsigned long long*)mom_stats, mom_idx, mom_acceptor)
     if (Ralt) { if (plain) IPB_FRET_LAUNCH(true, true); else IPB_FRET_LAUNCH(true, false); }
     else      { if (plain) IPB_FRET_LAUNCH(false, true); else IPB_FRET_LAUNCH(false, false); }
 #undef IPB_FRET_LAUNCH

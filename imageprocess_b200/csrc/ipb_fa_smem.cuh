@@ -22,6 +22,8 @@
 #define IPB_FAS_MAXRUNS 8192
 #define IPB_FAS_MAXCOMP 512
 #define IPB_FAS_MARK (-7)          // row_base[c.row_off]: this crop was finished by the shared-memory kernel
+#define IPB_FAS_STAGES 4           // row buffers per warp of the threshold phase's TMA pipeline
+#define IPB_FAS_ROWBUF 1024        // bytes per row buffer: crop rows of up to 504 + 7 pixels (16 warps x 4 x 1 KB = the union-find area)
 #define IPB_FAS_SMEM_BYTES (IPB_FAS_MAXWORDS * 4 * 2 + IPB_FAS_MAXWORDS * 2 + IPB_FAS_MAXRUNS * 4 * 2)
 
 __device__ __forceinline__ unsigned ipb_fas_find(unsigned* parent, unsigned i) {
@@ -119,7 +121,9 @@ __device__ __forceinline__ unsigned ipb_fas_unit_bits(const uint4& q, int ithr) 
     return b;
 }
 __device__ __forceinline__ void ipb_fas_threshold(const IpbCrop& c, const unsigned short* __restrict__ planes, int H, int W,
-                                                  const float* __restrict__ fa_params, const unsigned* __restrict__ roi_mask, unsigned* A)
+                                                  const float* __restrict__ fa_params, const unsigned* __restrict__ roi_mask, unsigned* A,
+                                                  unsigned char* ring /* nwarps x STAGES x ROWBUF bytes, 16-byte aligned; null: no TMA */,
+                                                  IpbMbar* bars /* nwarps x STAGES */)
 {
     const unsigned short* img = planes + (size_t)c.plane * H * W;
     if ((W & 7) != 0 || (((size_t)img) & 15) != 0) {               // block-uniform: unaligned frames take the scalar phase
@@ -138,16 +142,47 @@ __device__ __forceinline__ void ipb_fas_threshold(const IpbCrop& c, const unsign
     const int k0 = c.ox >> 3, s = c.ox & 7;
     const int nunits = ((c.ox + c.w + 7) >> 3) - k0;
     const int src = 2 * (lane < 15 ? lane : 0);
-    for (int y = warp; y < c.h; y += nwarps) {
+    // Rows arrive by TMA: every warp owns IPB_FAS_STAGES row buffers in the (still unused) union-find
+    // area and one mbarrier per buffer; lane 0 starts the bulk copy of row y + STAGES * nwarps as
+    // soon as the warp has read row y, so the loads cost no issue slots and their latency hides
+    // behind the comparisons of the rows in between.  Rows wider than a buffer take the LDG loop.
+    const unsigned row_bytes = 16u * (unsigned)nunits;
+    const bool tma = ring != nullptr && row_bytes <= (unsigned)IPB_FAS_ROWBUF;          // block-uniform
+    unsigned char* mybuf = tma ? ring + (size_t)warp * IPB_FAS_STAGES * IPB_FAS_ROWBUF : nullptr;
+    IpbMbar* mybar = bars + warp * IPB_FAS_STAGES;
+    if (tma) {
+        if (lane == 0) {
+#pragma unroll
+            for (int st = 0; st < IPB_FAS_STAGES; ++st) ipb_mbar_init(mybar + st, 1u);
+            ipb_mbar_fence_init();
+#pragma unroll
+            for (int st = 0; st < IPB_FAS_STAGES; ++st) {
+                const int y = warp + st * nwarps;
+                if (y < c.h) ipb_bulk_load(mybuf + st * IPB_FAS_ROWBUF,
+                                           reinterpret_cast<const uint4*>(img + (size_t)(c.oy + y) * W) + k0, row_bytes, mybar + st);
+            }
+        }
+        __syncwarp();
+    }
+    int it = 0;
+    for (int y = warp; y < c.h; y += nwarps, ++it) {
         const uint4* row = reinterpret_cast<const uint4*>(img + (size_t)(c.oy + y) * W) + k0;
+        const int st = it % IPB_FAS_STAGES;
+        const uint4* srow = reinterpret_cast<const uint4*>(mybuf + st * IPB_FAS_ROWBUF);
+        if (tma) ipb_mbar_wait(mybar + st, (unsigned)(it / IPB_FAS_STAGES) & 1u);
         const unsigned* mrow = roi_mask + c.mask_off + (size_t)y * c.wpr;
         // a lane takes two adjacent units (16 pixels): one pass of the warp covers 15 crop words
         for (int j0 = 0; j0 < c.wpr; j0 += 15) {
             const int unit = 4 * j0 + 2 * lane;
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
             const bool in0 = unit < nunits, in1 = unit + 1 < nunits;
-            if (in0) q0 = __ldg(row + unit);
-            if (in1) q1 = __ldg(row + unit + 1);
+            if (tma) {
+                if (in0) q0 = srow[unit];
+                if (in1) q1 = srow[unit + 1];
+            } else {
+                if (in0) q0 = __ldg(row + unit);
+                if (in1) q1 = __ldg(row + unit + 1);
+            }
             const unsigned half = (in0 ? ipb_fas_unit_bits(q0, ithr) : 0u) | ((in1 ? ipb_fas_unit_bits(q1, ithr) : 0u) << 8);
             unsigned long long v = 0;
 #pragma unroll
@@ -159,6 +194,13 @@ __device__ __forceinline__ void ipb_fas_threshold(const IpbCrop& c, const unsign
                 if (rem < 32) word &= (1u << rem) - 1u;
                 A[(size_t)y * c.wpr + j] = word & mrow[j];
             }
+        }
+        if (tma) {
+            __syncwarp();                                          // every lane has read the buffer
+            const int yn = y + IPB_FAS_STAGES * nwarps;
+            if (lane == 0 && yn < c.h)
+                ipb_bulk_load(mybuf + st * IPB_FAS_ROWBUF, reinterpret_cast<const uint4*>(img + (size_t)(c.oy + yn) * W) + k0,
+                              row_bytes, mybar + st);
         }
     }
 }
@@ -197,6 +239,7 @@ ipb_k_fa_fused_smem(const IpbCrop* __restrict__ crops, const unsigned short* __r
     unsigned* size = parent + IPB_FAS_MAXRUNS;
     unsigned short* base = reinterpret_cast<unsigned short*>(size + IPB_FAS_MAXRUNS);
     __shared__ unsigned wsum[IPB_FAS_THREADS / 32];
+    __shared__ IpbMbar bars[(IPB_FAS_THREADS / 32) * IPB_FAS_STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int ci = order ? order[blockIdx.x] : (int)blockIdx.x;
     const IpbCrop c = crops[ci];
@@ -210,7 +253,7 @@ ipb_k_fa_fused_smem(const IpbCrop* __restrict__ crops, const unsigned short* __r
     cs.bit_off = 0;                                         // bit rows live in shared memory from here on
 
     // ---- 1. threshold & ROI mask -> A
-    ipb_fas_threshold(c, planes, H, W, fa_params, roi_mask, A);
+    ipb_fas_threshold(c, planes, H, W, fa_params, roi_mask, A, reinterpret_cast<unsigned char*>(parent), bars);
     __syncthreads();
     unsigned* cur = A;
     unsigned* other = B;

@@ -83,10 +83,16 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
                   const float* __restrict__ fparams, const unsigned* __restrict__ union_bits, int union_wpr,
                   const int* __restrict__ union_idx /* frame -> union plane; null: identity */,
                   float* __restrict__ R, float* __restrict__ Ralt, float* __restrict__ Rroi,
-                  float* __restrict__ Dcorr, float* __restrict__ Acorr)
+                  float* __restrict__ Dcorr, float* __restrict__ Acorr,
+                  unsigned long long* __restrict__ mom_stats /* nullable: [.][4] = {n, sum, sumsq, 0} rows */,
+                  const int* __restrict__ mom_idx /* [F] row of frame f */, int mom_acceptor)
 {
     const long long plane_px = (long long)H * W;
     const float fnan = __uint_as_float(0x7fc00000u);
+    // integer moments of one channel ride along (FA global statistics, FA_Analyzer.py:984-987): the pass
+    // is bound by HBM, the two integer multiply-adds per pixel find free issue slots
+    unsigned m1 = 0;
+    unsigned long long m2 = 0;
     if ((W & 7) == 0) {
         // grid = (chunks, frames): indices inside a frame are walked without 64-bit divisions;
         // two 8-pixel groups per trip, all of their 128-bit loads issued before the arithmetic
@@ -119,6 +125,16 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
                 const long long p0 = (iv0 + g * stride) << 3;
                 const unsigned dw[4] = {dq[g].x, dq[g].y, dq[g].z, dq[g].w}, aw[4] = {aq[g].x, aq[g].y, aq[g].z, aq[g].w},
                                ow[4] = {oq[g].x, oq[g].y, oq[g].z, oq[g].w};
+                if (mom_stats) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned w = mom_acceptor ? aw[j] : dw[j];
+                        const unsigned a = w & 0xffffu, b = w >> 16;
+                        m1 += a + b;
+                        m2 += (unsigned long long)a * a;
+                        m2 += (unsigned long long)b * b;
+                    }
+                }
                 unsigned ub = 0xffu;
                 if (Rroi) {
                     const int y = (int)((unsigned long long)p0 / (unsigned)W), x0 = (int)(p0 - (long long)y * W);
@@ -153,6 +169,7 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
             const unsigned av = base[(size_t)cfg.acc_ch * plane_px + p];
             const unsigned ov = (cfg.use_spectral && cfg.aonly_ch >= 0) ? base[(size_t)cfg.aonly_ch * plane_px + p] : 0u;
             const IpbFretPx o = ipb_fret_px<WANT_ALT, PLAIN>(cfg, fparams + (size_t)f * IPB_FP_STRIDE, dv, av, ov);
+            if (mom_stats) { const unsigned v = mom_acceptor ? av : dv; m1 += v; m2 += (unsigned long long)v * v; }
             if (R) R[i] = o.R;
             if (WANT_ALT && Ralt) Ralt[i] = o.Ralt;
             if (Dcorr) Dcorr[i] = o.dcorr;
@@ -164,6 +181,17 @@ ipb_k_fret_pixels(const unsigned short* __restrict__ planes, int F, int H, int W
                 Rroi[i] = in ? o.R : fnan;
             }
         }
+    }
+    if (mom_stats) {                                               // block-uniform
+        // (a thread sums at most 2^16 pixels of a frame: m1 < 2^32)
+        __shared__ unsigned long long msum[2];
+        if (threadIdx.x < 2) msum[threadIdx.x] = 0ull;
+        __syncthreads();
+        const unsigned long long w1 = ipb_warp_sum((unsigned long long)m1), w2 = ipb_warp_sum(m2);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&msum[0], w1); atomicAdd(&msum[1], w2); }
+        __syncthreads();
+        if (threadIdx.x < 2 && msum[threadIdx.x])
+            atomicAdd(&mom_stats[(size_t)mom_idx[blockIdx.y] * 4 + 1 + threadIdx.x], msum[threadIdx.x]);
     }
 }
 

@@ -67,3 +67,49 @@ __device__ __forceinline__ T ipb_warp_max(T v) {
     for (int o = 16; o > 0; o >>= 1) { T u = __shfl_xor_sync(IPB_FULL, v, o); v = u > v ? u : v; }
     return v;
 }
+
+// ---- TMA bulk copies (cp.async.bulk, 1-D) tracked by an mbarrier: global -> shared rows without a
+// register round trip or an issue slot per 16 bytes.  Product build: inline PTX for sm_100a (SASS:
+// UBLKCP + SYNCS).  Emulated build: the copy happens at once, the wait is a no-op.
+struct IpbMbar { unsigned long long v; };
+
+__device__ __forceinline__ void ipb_mbar_init(IpbMbar* bar, unsigned count) {
+#ifdef IPB_EMULATE
+    bar->v = 0; (void)count;
+#else
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+#endif
+}
+// makes freshly initialised barriers visible to the async proxy (call once after the inits)
+__device__ __forceinline__ void ipb_mbar_fence_init() {
+#ifndef IPB_EMULATE
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+// one thread: announces `bytes` of incoming data and starts the copy src -> dst (both 16-byte
+// aligned, bytes a multiple of 16); the barrier completes its phase when the bytes have landed
+__device__ __forceinline__ void ipb_bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, IpbMbar* bar) {
+#ifdef IPB_EMULATE
+    memcpy(dst_smem, src_gmem, bytes); (void)bar;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(d), "l"(src_gmem), "r"(bytes), "r"(b) : "memory");
+#endif
+}
+// every consumer thread: blocks until the barrier's phase with parity `parity` has completed
+__device__ __forceinline__ void ipb_mbar_wait(IpbMbar* bar, unsigned parity) {
+#ifdef IPB_EMULATE
+    (void)bar; (void)parity;
+#else
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{ .reg .pred p;\n\t"
+                 "IPB_WAIT_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra IPB_DONE_%=;\n\t"
+                 "bra IPB_WAIT_%=;\n\t"
+                 "IPB_DONE_%=: }" :: "r"(b), "r"(parity) : "memory");
+#endif
+}

@@ -156,6 +156,23 @@ class TorchMem:
         n = pinned_tensor.numel() if nbytes is None else int(nbytes)
         buf.raw[:n].copy_(pinned_tensor[:n], non_blocking=True)
 
+    def upload_on_copy_stream(self, buf, pinned_tensor, after=None, nbytes=None):
+        """H2D copy on the backend's copy stream, ordered after event `after` (the last reader of
+        `buf`); returns the event that marks its end.  Lets the next batch's upload run beside the
+        current batch's kernels."""
+        torch = self.torch
+        cs = self.__dict__.get("_copy_stream")
+        if cs is None:
+            cs = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
+        if after is not None:
+            cs.wait_event(after)
+        n = pinned_tensor.numel() if nbytes is None else int(nbytes)
+        with torch.cuda.stream(cs):
+            buf.raw[:n].copy_(pinned_tensor[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        return ev
+
     def download_async(self, pinned_tensor, buf, nbytes):
         """D2H copy into a pinned tensor on the current stream (caller syncs)."""
         n = int(nbytes)

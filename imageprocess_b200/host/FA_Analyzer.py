@@ -137,28 +137,42 @@ def run_batch(file_list, params, px_size, out_root, save_ok_only=True, eng=None,
     """_run_batch_process body: one <Sxx>_results.csv per image under individual_results/."""
     eng = eng or _engine()
     indiv = ensure_dir(os.path.join(out_root, "individual_results"))
-    items = []
+    from .stream import FrameStream
+    by_shape = {}
     for img_path, json_path, s_tag in file_list:
         log(f"Processing {s_tag}...")
-        img = load_image_safe(img_path)
-        if img is None:
+        try:
+            shape = common.image_shape(img_path)
+        except Exception:
             log(f"  [Error] Failed to load image: {s_tag}")
             continue
-        items.append((s_tag, common.as_u16_plane(img, s_tag), load_rois(json_path)))
-    by_shape = {}
-    for it in items:
-        by_shape.setdefault(it[1].shape, []).append(it)
+        by_shape.setdefault(shape, []).append((s_tag, img_path, load_rois(json_path)))
     count = 0
-    for shape, group in by_shape.items():
-        for b0 in range(0, len(group), frames_per_batch):
-            chunk = group[b0: b0 + frames_per_batch]
-            planes = np.stack([it[1] for it in chunk])[:, None]
-            out = pipeline.fa_batch(eng, eng.mem.from_host(planes), planes.shape, [it[2] for it in chunk], params,
-                                    px_size, channel=0, save_ok_only=save_ok_only)
-            for f, (s_tag, _, _) in enumerate(chunk):
-                rows = [{"File": s_tag, **r} for r in out["rows_per_frame"][f]]
-                if rows:
-                    common.write_rows_csv(os.path.join(indiv, f"{s_tag}_results.csv"), rows)
-                    count += 1
+
+    def load(it):
+        img = load_image_safe(it[1])
+        if img is None:
+            raise IOError("unreadable image")
+        return common.as_u16_plane(img, it[0])[None]
+
+    cfg = convert_um_to_px_config(params, px_size)
+    for (H, W), group in by_shape.items():
+        make_job = lambda shape: batch.FrameBatchJob(eng, shape, stages=("fa",), fa_params=params, fa_px=px_size, fa_ch=0,
+                                                     fa_config=cfg)
+        stream = FrameStream(eng, (1, H, W), make_job, frames_per_batch=min(frames_per_batch, len(group)))
+        try:
+            for pos, res in stream.run(group, load, lambda it: it[2]):
+                rows_pf = batch.rows_fa(res, cfg, params, px_size, stream.F, save_ok_only)
+                for f, k in enumerate(pos):
+                    s_tag = group[k][0]
+                    if k in stream.errors:
+                        log(f"  [Error] Failed to load image: {s_tag}")
+                        continue
+                    rows = [{"File": s_tag, **r} for r in rows_pf[f]]
+                    if rows:
+                        common.write_rows_csv(os.path.join(indiv, f"{s_tag}_results.csv"), rows)
+                        count += 1
+        finally:
+            stream.close()
     log(f"Done. Processed {count} files.")
     return count

@@ -211,7 +211,7 @@ def _bg_corrected_images(eng, planes_dev, shape, bgs, clip_neg):
         fp = np.zeros((1, FP_STRIDE), dtype=np.float32)
         fp[0, 0] = fp[0, 1] = np.float32(bgs[ci])
         eng.call("ipb_fret_pixels", planes_dev.ptr, 1, H, W, cfg.ctypes.data, mem.from_host(fp).ptr, None, 0,
-                 None, None, None, None, out.ptr + 4 * ci * H * W, None, mem.stream)
+                 None, None, None, None, out.ptr + 4 * ci * H * W, None, None, None, 0, mem.stream)
     return out
 
 
@@ -291,10 +291,29 @@ def _process_key_task(task, eng=None):
         return {"rows": [], "steps": 1, "logs": [f"[ERROR][WORKER] {task.get('stid', '?')}: {e}"]}
 
 
-def process_key_tasks(tasks, eng=None, frames_per_batch=32):
-    """Batched form: keys with ROI polygons, equal image shape and channel set share one
-    FrameBatchJob (many frames per launch sequence); everything else goes through
-    _process_key_task.  Returns the per-task results in task order."""
+def _rows_of_frame(task, rows, chs, res, f):
+    out = []
+    for r in rows:
+        r.update({"stage": task["s"], "time": task["t"] if task["timelapse"] else None,
+                  "bg_scope": task["bg_scope"], "bg_mode": task["bg_mode"],
+                  "clip_neg": bool(task["clip_neg"]), "bg_stride": int(task["bg_stride"])})
+        for ch in task["chs_to_quant"]:
+            if ch in chs:
+                r[f"ch{ch}_bg"] = float(res.int_bg[f, chs.index(ch)])
+                r[f"ch{ch}_p"] = float(res.int_p[chs.index(ch)])
+            r[f"ch{ch}_color"] = task["ch_color_map"].get(ch, "Grayscale")
+        out.append(r)
+    return out
+
+
+def process_key_tasks(tasks, eng=None, frames_per_batch=32, decode_threads=8, timing=None):
+    """Batched form of the reference's pool over (stage, time) keys (Fluor_INT.py:2211-2229): keys
+    with ROI polygons, equal image shape, channel set and settings share ONE FrameBatchJob for the
+    whole run, fed by stream.FrameStream (threaded decode -> pinned ring -> async upload, results
+    two batches behind); everything else goes through _process_key_task.  Keys are grouped on
+    metadata only (paths, shape from the TIFF header) and decoded per batch.  Returns the per-task
+    results in task order."""
+    from .stream import FrameStream
     eng = eng or _engine()
     results = [None] * len(tasks)
     groups = {}
@@ -306,43 +325,47 @@ def process_key_tasks(tasks, eng=None, frames_per_batch=32):
             polys = common.load_roi_json(roi_base + ".json") if os.path.exists(roi_base + ".json") else None
             if not chs or not polys or task.get("do_tif") or task.get("do_png"):
                 raise LookupError
-            raws = [common.as_u16_plane(common.read_image_raw(task["chmap"][ch])) for ch in chs]
-            key = (raws[0].shape, tuple(chs), task["bg_scope"], task["bg_mode"], int(task["bg_stride"]),
+            shape = common.image_shape(task["chmap"][chs[0]])
+            key = (shape, tuple(chs), task["bg_scope"], task["bg_mode"], int(task["bg_stride"]),
                    float(task["percentile"]), bool(task["per_channel_p"]), tuple(sorted(task["ch_p_map"].items())),
                    bool(task["clip_neg"]))
-            groups.setdefault(key, []).append((i, np.stack(raws), polys))
+            groups.setdefault(key, []).append((i, [task["chmap"][ch] for ch in chs], polys))
         except Exception:
             results[i] = _process_key_task(task, eng)
     for key, items in groups.items():
         (H, W), chs = key[0], list(key[1])
-        for b0 in range(0, len(items), frames_per_batch):
-            chunk = items[b0: b0 + frames_per_batch]
-            planes = np.stack([it[1] for it in chunk])
-            task0 = tasks[chunk[0][0]]
-            try:
-                job = batch.FrameBatchJob(eng, planes.shape, stages=("int",), int_task=task0,
-                                          int_channels=list(range(len(chs))))
-                job.ch_names = chs
-                res = job.run(eng.mem.from_host(planes), [it[2] for it in chunk])
-                rows_pf = batch.rows_intensity(res, len(chunk), chs)
-                for f, (i, _, _) in enumerate(chunk):
+        task0 = tasks[items[0][0]]
+
+        def make_job(shape):
+            job = batch.FrameBatchJob(eng, shape, stages=("int",), int_task=task0, int_channels=list(range(len(chs))))
+            job.ch_names = chs
+            return job
+
+        def load(it):
+            return np.stack([common.as_u16_plane(common.read_image_raw(p)) for p in it[1]])
+        stream = FrameStream(eng, (len(chs), H, W), make_job, frames_per_batch=min(frames_per_batch, len(items)),
+                             decode_threads=decode_threads)
+        try:
+            for pos, res in stream.run(items, load, lambda it: it[2]):
+                rows_pf = batch.rows_intensity(res, stream.F, chs)
+                for f, k in enumerate(pos):
+                    i = items[k][0]
                     task = tasks[i]
-                    rows = []
-                    for r in rows_pf[f]:
-                        r.update({"stage": task["s"], "time": task["t"] if task["timelapse"] else None,
-                                  "bg_scope": task["bg_scope"], "bg_mode": task["bg_mode"],
-                                  "clip_neg": bool(task["clip_neg"]), "bg_stride": int(task["bg_stride"])})
-                        for ch in task["chs_to_quant"]:
-                            if ch in chs:
-                                r[f"ch{ch}_bg"] = float(res.int_bg[f, chs.index(ch)])
-                                r[f"ch{ch}_p"] = float(res.int_p[chs.index(ch)])
-                            r[f"ch{ch}_color"] = task["ch_color_map"].get(ch, "Grayscale")
-                        rows.append(r)
+                    if k in stream.errors:
+                        results[i] = {"rows": [], "steps": 1, "logs": [f"[ERROR][WORKER] {task.get('stid', '?')}: {stream.errors[k]}"]}
+                        continue
+                    rows = _rows_of_frame(task, rows_pf[f], chs, res, f)
                     results[i] = {"rows": rows, "steps": max(1, len(rows)),
                                   "logs": [t("log_done_quant").format(stid=task["stid"], roi_count=len(rows))]}
-            except Exception as e:
-                for i, _, _ in chunk:
+        except Exception as e:
+            for i, _, _ in items:
+                if results[i] is None:
                     results[i] = {"rows": [], "steps": 1, "logs": [f"[ERROR][WORKER] {tasks[i].get('stid', '?')}: {e}"]}
+        finally:
+            stream.close()
+            if timing is not None:
+                for k, v in stream.timing.items():
+                    timing[k] = timing.get(k, 0) + v
     return results
 
 

@@ -53,6 +53,14 @@ def read_image_raw(path, page=0):
     return a
 
 
+def image_shape(path):
+    """(H, W) of an image file from its header, without decoding the pixels."""
+    from PIL import Image
+    with Image.open(path) as im:
+        w, h = im.size
+    return int(h), int(w)
+
+
 def read_2d(path):
     """float32 view of read_image_raw -- what the reference's read_2d returns (Fluor_INT.py:364-368)."""
     return read_image_raw(path).astype(np.float32, copy=False)

@@ -29,7 +29,7 @@ def _engine():
     return ipb.engine()
 
 
-def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per_batch=32):
+def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per_batch=32, timing=None):
     eng = eng or _engine()
     logs = [f"[Stage {stage_key}] start"]
     RES_ROOT, RAT32, RAT16, RROI32, RROI16, PNG_FULL, PNG_CROP = paths
@@ -39,58 +39,77 @@ def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per
     per_ch = bool(p["per_channel_p"])
     d_p = float(p["donor_p"]) if per_ch else float(p["percentile"])
     a_p = float(p["fret_p"]) if per_ch else float(p["percentile"])
-    items = []
+    from .stream import FrameStream
+    # (stage, time) pairs are grouped on metadata only (paths, shape from the TIFF header) and decoded
+    # per batch by the stream's thread pool; one FrameBatchJob serves every batch of a group
+    items, by_shape = [], {}
     for (s, t_code), dpath, apath in pairs_for_stage:
         stid = f"{s}_{t_code}" if (timelapse and t_code is not None) else s
         logs.append(f"  - Processing: {stid}")
-        D = common.as_u16_plane(common.read_image_raw(dpath), f"{stid} donor")
-        A = common.as_u16_plane(common.read_image_raw(apath), f"{stid} fret")
         polys = load_roi_polys(p["roi_dir"], s, t_code, timelapse=timelapse)
         if not polys:
             logs.append(f"    [Warn] ROI missing: {stid}.json ? skip ROI-based outputs")
-        items.append((s, t_code, stid, np.stack([D, A]), polys))
+        try:
+            shape = common.image_shape(dpath)
+        except Exception as e:
+            logs.append(f"    [Error] {stid}: {e}")
+            continue
+        by_shape.setdefault(shape, []).append((s, t_code, stid, dpath, apath, polys))
     rows_stage = []
-    by_shape = {}
-    for it in items:
-        by_shape.setdefault(it[3].shape, []).append(it)
-    for shape, group in by_shape.items():
-        for b0 in range(0, len(group), frames_per_batch):
-            chunk = group[b0: b0 + frames_per_batch]
-            planes = np.stack([it[3] for it in chunk])
-            F = planes.shape[0]
-            job = batch.FrameBatchJob(eng, planes.shape, stages=("fret",), fret_p=p, want_roi_image=out_tif)
-            res = job.run(eng.mem.from_host(planes), [it[4] or [] for it in chunk])
-            rows_pf = batch.rows_fret(res, F)
-            if out_tif:
-                R = res.R.host()
-                prev = roi_ops.preview_u16_batch(eng, res.R, 1.0, 99.0)
-                Rroi = res.R_roi.host()
-                prev_roi = roi_ops.preview_u16_batch(eng, res.R_roi, 1.0, 99.0)
-            for f, (s, t_code, stid, _, polys) in enumerate(chunk):
+
+    def load(it):
+        return np.stack([common.as_u16_plane(common.read_image_raw(it[3]), f"{it[2]} donor"),
+                         common.as_u16_plane(common.read_image_raw(it[4]), f"{it[2]} fret")])
+
+    for (H, W), group in by_shape.items():
+        make_job = lambda shape: batch.FrameBatchJob(eng, shape, stages=("fret",), fret_p=p, want_roi_image=out_tif)
+        # ratio images of a result live in the job's (single) device buffers: with TIFF output every
+        # batch is collected before the next one is submitted
+        stream = FrameStream(eng, (2, H, W), make_job, frames_per_batch=min(frames_per_batch, len(group)),
+                             decode_threads=int(p.get("n_workers", 8) or 8), lag=0 if out_tif else 2)
+        try:
+            for pos, res in stream.run(group, load, lambda it: it[5] or []):
+                F = stream.F
+                rows_pf = batch.rows_fret(res, F)
                 if out_tif:
-                    common.write_tiff(os.path.join(RAT32, f"{stid}_ratio_{suffix}.tif"), R[f])
-                    pv = prev[f] if prev[f] is not None else np.zeros(R[f].shape, np.uint16)
-                    common.write_tiff(os.path.join(RAT16, f"{stid}_ratio_{suffix}_preview.tif"), pv)
-                if not polys:
-                    continue
-                if out_tif:
-                    common.write_tiff(os.path.join(RROI32, f"{stid}_ratio_{suffix}.tif"), Rroi[f])
-                    pv = prev_roi[f] if prev_roi[f] is not None else np.zeros(R[f].shape, np.uint16)
-                    common.write_tiff(os.path.join(RROI16, f"{stid}_ratio_{suffix}_preview.tif"), pv)
-                eps = float(res.fret_params[f, 2])
-                for r in rows_pf[f]:
-                    r.update({"stage": s, "time": (t_code if timelapse else None), "eps": eps, "p": p["percentile"],
-                              "donor_p": d_p, "fret_p": a_p, "ratio_mode": p["ratio_mode"],
-                              "bg_scope": p["bg_scope"], "bg_mode": p["bg_mode"], "clip_neg": p["clip_neg"],
-                              "eps_p": p["eps_percentile"]})
-                rows_stage.extend(rows_pf[f])
+                    R = res.R.host()
+                    prev = roi_ops.preview_u16_batch(eng, res.R, 1.0, 99.0)
+                    Rroi = res.R_roi.host()
+                    prev_roi = roi_ops.preview_u16_batch(eng, res.R_roi, 1.0, 99.0)
+                for f, k in enumerate(pos):
+                    s, t_code, stid, _, _, polys = group[k]
+                    if k in stream.errors:
+                        logs.append(f"    [Error] {stid}: {stream.errors[k]}")
+                        continue
+                    if out_tif:
+                        common.write_tiff(os.path.join(RAT32, f"{stid}_ratio_{suffix}.tif"), R[f])
+                        pv = prev[f] if prev[f] is not None else np.zeros(R[f].shape, np.uint16)
+                        common.write_tiff(os.path.join(RAT16, f"{stid}_ratio_{suffix}_preview.tif"), pv)
+                    if not polys:
+                        continue
+                    if out_tif:
+                        common.write_tiff(os.path.join(RROI32, f"{stid}_ratio_{suffix}.tif"), Rroi[f])
+                        pv = prev_roi[f] if prev_roi[f] is not None else np.zeros(R[f].shape, np.uint16)
+                        common.write_tiff(os.path.join(RROI16, f"{stid}_ratio_{suffix}_preview.tif"), pv)
+                    eps = float(res.fret_params[f, 2])
+                    for r in rows_pf[f]:
+                        r.update({"stage": s, "time": (t_code if timelapse else None), "eps": eps, "p": p["percentile"],
+                                  "donor_p": d_p, "fret_p": a_p, "ratio_mode": p["ratio_mode"],
+                                  "bg_scope": p["bg_scope"], "bg_mode": p["bg_mode"], "clip_neg": p["clip_neg"],
+                                  "eps_p": p["eps_percentile"]})
+                    rows_stage.extend(rows_pf[f])
+        finally:
+            stream.close()
+            if timing is not None:
+                for k, v in stream.timing.items():
+                    timing[k] = timing.get(k, 0) + v
     if p.get("out_png"):
         logs.append("  [SKIP-PNG] figure rendering is host matplotlib code outside the device path")
     logs.append(f"[Stage {stage_key}] end (total {len(pairs_for_stage)} time/files)")
     return stage_key, rows_stage, logs
 
 
-def run_headless(img_dir, roi_dir, out_root=None, p=None, eng=None, log=print):
+def run_headless(img_dir, roi_dir, out_root=None, p=None, eng=None, log=print, frames_per_batch=32, timing=None):
     """_pipeline_thread without Tk (fret_ratio_builder.py:892-1011): pair files, group by stage,
     process, write RES/xls/fret_ratio_perROI.csv."""
     p = {**DEFAULT_P, **(p or {}), "img_dir": img_dir, "roi_dir": roi_dir}
@@ -104,7 +123,7 @@ def run_headless(img_dir, roi_dir, out_root=None, p=None, eng=None, log=print):
         stages.setdefault(pr[0][0], []).append(pr)
     rows_all = []
     for stage_key, prs in stages.items():
-        _, rows, logs = process_one_stage(stage_key, prs, p, paths, eng=eng)
+        _, rows, logs = process_one_stage(stage_key, prs, p, paths, eng=eng, frames_per_batch=frames_per_batch, timing=timing)
         rows_all.extend(rows)
         for line in logs:
             log(line)

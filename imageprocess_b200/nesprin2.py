@@ -158,7 +158,7 @@ def nesprin2_batch(eng, planes, shape, polys_per_frame, p, donor_ch=0, acc_ch=1,
     def run_pixels(only_corr):
         eng.call("ipb_fret_pixels", planes.ptr, F, H, W, cfg.ctypes.data, fparams.ptr, None, wpr, None,
                  None if only_corr else img_ptr(IMG_R), None if only_corr else img_ptr(IMG_RALT), None,
-                 img_ptr(IMG_D), img_ptr(IMG_A), mem.stream)
+                 img_ptr(IMG_D), img_ptr(IMG_A), None, None, 0, mem.stream)
 
     # ---- epsilon
     ureg = np.zeros(F, dtype=REGION)                       # the union plane of every frame as a region

@@ -254,7 +254,7 @@ def _engine_fret_pixels(self, planes, F, H, W, cfg, fparams, union=None, union_w
     p = lambda b: b.ptr if b is not None else None
     self.call("ipb_fret_pixels", planes.ptr, int(F), int(H), int(W), cfg.ctypes.data, fparams.ptr,
                   p(union), int(union_wpr), p(union_idx), p(R), p(Ralt), p(Rroi), p(Dcorr), p(Acorr),
-                  self.mem.stream)
+                  None, None, 0, self.mem.stream)
 
 
 def _engine_region_stats(self, regions, jobs, mask_pool, H, W, planes=None, images=None, bvals=None,

@@ -144,7 +144,11 @@ int ipb_fa_params(const uint64_t* stats, const int32_t* stat_idx, const void* qo
  * epsilon-regularised ratio and its inverse (fret_ratio_builder.py:474; Nesprin2 1499-1500),
  * ratio clipping (Nesprin2 1502-1504) and the ROI-masked copy (fret_ratio_builder.py:494-495).
  * planes: uint16 [F][n_ch][H][W]; fparams: float32 [F][4] = {Bd, Ba, eps, Bao};
- * outputs float32 [F][H][W], any of them may be NULL.                                      */
+ * outputs float32 [F][H][W], any of them may be NULL.
+ * mom_stats (optional): the integer moments of the donor (mom_acceptor = 0) or acceptor channel ride
+ * along for the FA global statistics (INT/FA_Analyzer.py:984-987): sum and sum of squares of frame f
+ * are ADDED to mom_stats[mom_idx[f]][1] and [2] (rows {n, sum, sumsq, 0} as ipb_hist_u16 writes
+ * them; the caller clears those two words or lets ipb_hist_select do it).                     */
 typedef struct {
     int32_t numer_is_acceptor;    /* 1: "FRET/Donor", 0: "Donor/FRET" */
     int32_t clip_neg;
@@ -157,7 +161,8 @@ int ipb_fret_pixels(const uint16_t* planes, int n_frames, int H, int W,
                     const void* cfg_host /* ipb_fret_cfg, [host] */, const float* fparams,
                     const uint32_t* union_bits, int union_wpr,
                     const int32_t* union_idx /* [F] frame -> union plane, NULL: identity */,
-                    float* R, float* Ralt, float* Rroi, float* Dcorr, float* Acorr, void* stream);
+                    float* R, float* Ralt, float* Rroi, float* Dcorr, float* Acorr,
+                    uint64_t* mom_stats, const int32_t* mom_idx, int mom_acceptor, void* stream);
 
 /* ------------------------------------------------------------------ per-region statistics
  * Replaces quantify_stats / quantify_per_roi_multi (INT/Fluor_INT.py:494-538),

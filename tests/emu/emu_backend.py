@@ -51,6 +51,10 @@ class NumpyMem:
         n = pinned_tensor.size if nbytes is None else int(nbytes)
         buf.raw[:n] = pinned_tensor[:n]
 
+    def upload_on_copy_stream(self, buf, pinned_tensor, after=None, nbytes=None):
+        self.upload_async(buf, pinned_tensor, nbytes)
+        return NumpyMem._Event()
+
     def download_async(self, pinned_tensor, buf, nbytes):
         pinned_tensor[: int(nbytes)] = buf.raw[: int(nbytes)]
 
