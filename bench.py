@@ -552,6 +552,63 @@ def run_other(args):
     print(json.dumps(line))
 
 
+def run_folder(args):
+    """`--config folder`: the `.bat`-level entry points on a folder of TIFFs: a
+    synthetic C4 time-lapse is written to disk (uncompressed uint16 TIFF pairs + one ROI JSON per
+    frame), then fret_ratio_builder.run_headless (3FRET.bat) and Fluor_INT.run_headless
+    (1Intensity.bat) process it: threaded decode -> pinned ring -> async upload -> ONE persistent
+    FrameBatchJob -> CSV.  Wall-clock Mpix/s, decode and file output included."""
+    import shutil
+    import tempfile
+    import torch
+    import imageprocess_b200 as ipb
+    from imageprocess_b200.host import Fluor_INT, common, fret_ratio_builder
+    torch.cuda.set_device(0)
+    eng = ipb.engine("cuda:0")
+    n = int(args.folder_frames)
+    root = tempfile.mkdtemp(prefix="ipb_folder_", dir=os.environ.get("IPB_TMP", None))
+    try:
+        frames, polys = make_frames(min(n, 8), seed=1234, n_unique=2)
+        roi_dir = os.path.join(root, "roi")
+        os.makedirs(roi_dir)
+        t0 = time.perf_counter()
+        roi_json = json.dumps({"name": "S01", "image_shape": {"height": H, "width": W},
+                               "rois": [np.asarray(P).tolist() for P in polys]})
+        for t in range(n):
+            f = frames[t % frames.shape[0]]
+            common.write_tiff(os.path.join(root, f"S01_t{t:03d}_1.tif"), f[0])
+            common.write_tiff(os.path.join(root, f"S01_t{t:03d}_2.tif"), f[1])
+            with open(os.path.join(roi_dir, f"S01_t{t:02d}.json"), "w") as fh:      # the mirrors' own name: S01_t07, S01_t123
+                fh.write(roi_json)
+        t_write = time.perf_counter() - t0
+        out = {}
+        for name, fn in (("fret_ratio_builder", lambda tm: fret_ratio_builder.run_headless(
+                              root, roi_dir, out_root=os.path.join(root, "RES_FRET"), eng=eng, log=lambda s: None,
+                              p={"timelapse": True, "out_tif": False, "ratio_mode": "Donor/FRET"},
+                              frames_per_batch=args.frames if args.frames < 64 else 32, timing=tm)),
+                         ("Fluor_INT", lambda tm: Fluor_INT.run_headless(
+                              root, roi_dir, out_root=os.path.join(root, "RES_INT"), eng=eng, log=lambda s: None,
+                              cfg={"timelapse": True, "channels_to_quant": [1, 2]}, timing=tm))):
+            tm = {}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rows = fn(tm)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out[name] = {"seconds": round(dt, 3), "frames_per_s": round(n / dt, 2), "mpix_per_s": round(n * H * W / dt / 1e6, 1),
+                         "rows": len(rows), "decode_thread_seconds": round(tm.get("decode_s", 0.0), 3),
+                         "host_waited_for_decode_s": round(tm.get("wait_decode_s", 0.0), 3), "batches": tm.get("batches", 0)}
+        line = {"metric": "Mpix/s (folder of 2048x2048 uint16 2ch TIFF pairs through the headless entry points, wall clock)",
+                "value": out["fret_ratio_builder"]["mpix_per_s"], "unit": "Mpix/s", "n_gpus": 1, "steps": 1, "warmup": 0,
+                "higher_is_better": True, "data": "synthetic", "dtype": "u16/f32",
+                "config": {"workload": f"{n} frames of the C4 scene as uncompressed TIFF pairs on disk + ROI JSON per frame",
+                           "tiff_write_seconds": round(t_write, 1), "cpu_count": os.cpu_count()},
+                "entry_points": out}
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -561,11 +618,15 @@ def main():
     ap.add_argument("--lag", type=int, default=2, help="steps in flight before a step's tables are unpacked")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c4", choices=["c4", "c5", "c3s"],
-                    help="c4: the BASELINE metric (default); c5: 8192^2 FA mosaic; c3s: Nesprin2 with spectral correction")
+    ap.add_argument("--config", default="c4", choices=["c4", "c5", "c3s", "folder"],
+                    help="c4: the BASELINE metric (default); c5: 8192^2 FA mosaic; c3s: Nesprin2 with spectral correction; "
+                         "folder: the headless entry points on a folder of TIFFs")
+    ap.add_argument("--folder-frames", type=int, default=256, help="--config folder: frames written to disk")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "folder":
+        run_folder(args)
     elif args.config != "c4":
         run_other(args)
     else:

@@ -42,6 +42,7 @@ _PROTOS.update({
     "ipb_hist_planes": [_vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "ipb_hist_select": [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ipb_selftest_fdiv": [_vp, _vp, _i64, _vp, _vp],
+    "ipb_fa_contour_cells": [_vp, _i, _i64, _vp, _vp, _vp, _vp],
     "ipb_hist_sizes": [_i, _i, _i, _vp],
     "ipb_hist_select_sizes": [_i, _i, _vp],
     "ipb_roi_stats_fused_sizes": [_i, _i, _i, _i, _i, _vp],

@@ -17,6 +17,7 @@
 #include "ipb_fret.cuh"
 #include "ipb_fa.cuh"
 #include "ipb_morph.cuh"
+#include "ipb_contour.cuh"
 
 static thread_local char g_ipb_err[512] = "";
 
@@ -520,6 +521,21 @@ int ipb_eps_from_stat(const void* stat_out, const int32_t* row_of_frame, int n_f
     IPB_LAUNCH(ipb_k_eps_from_stat, dim3(ipb_div_up(n_frames, 128)), dim3(128), 0, stream,
                (const IpbStatOut*)stat_out, row_of_frame, n_frames, eps_abs, fparams);
     return ipb_check_launch("ipb_k_eps_from_stat");
+}
+
+int ipb_fa_contour_cells(const void* crops, int n_crops, int64_t max_px, const int32_t* labels, void* rec,
+                         uint32_t* rec_count, void* stream)
+{
+    if (n_crops <= 0) return IPB_OK;
+    IPB_REQUIRE(crops && labels && rec && rec_count && max_px >= 0, "ipb_fa_contour_cells: bad argument");
+    IPB_REQUIRE(n_crops <= 65535, "ipb_fa_contour_cells: n_crops %d out of range", n_crops);
+    IPB_CUDA_TRY(cudaMemsetAsync(rec_count, 0, sizeof(uint32_t) * (size_t)n_crops, (cudaStream_t)stream), "memset rec_count");
+    if (max_px == 0) return IPB_OK;
+    unsigned gx = ipb_div_up(max_px, 256 * 4);
+    if (gx > 2048u) gx = 2048u;
+    IPB_LAUNCH(ipb_k_fa_contour_cells, dim3(gx, (unsigned)n_crops), dim3(256), 0, stream, (const IpbCrop*)crops, labels,
+               (uint2*)rec, rec_count);
+    return ipb_check_launch("ipb_k_fa_contour_cells");
 }
 
 int ipb_selftest_fdiv(const float* a, const float* b, int64_t n, uint32_t* mismatches, void* stream)

@@ -65,7 +65,11 @@ def convert_um_to_px_config(params, px_size):
     return batch.fa_um_to_px_config(params, px_size)
 
 
-def analyze_fa_crop(image_crop, roi_mask_crop, config, global_stats, eng=None):
+def analyze_fa_crop(image_crop, roi_mask_crop, config, global_stats, eng=None, with_contours=True):
+    """analyze_fa_crop (FA_Analyzer.py:123-195) on the device.  'contour' of every adhesion is
+    find_contours(labeled_img == k, 0.5)[0] as in the reference (FA_Analyzer.py:168-170), produced
+    from one pass over the label map (ipb_fa_contour_cells) instead of one scan per adhesion; an
+    adhesion without any contour is dropped like the reference does (`if not contours: continue`)."""
     empty = {"OK": [], "Large": [], "Small": []}
     image_crop = np.asarray(image_crop)
     if image_crop.size == 0:                                     # FA_Analyzer.py:125-126
@@ -103,7 +107,14 @@ def analyze_fa_crop(image_crop, roi_mask_crop, config, global_stats, eng=None):
     res.fa_comp_off = off
     res.fa_comps = comps.host()[: int(off[1])]
     res.fa_stats = np.array([[m, s, bg, thr]], dtype=np.float32)
-    items = batch.fa_items(res, config)[0]
+    contours = None
+    if with_contours and h >= 2 and w >= 2:
+        from .. import contours as ct
+        rec = mem.empty((h * w, 2), np.uint32)
+        rec_n = mem.empty(1, np.uint32)
+        eng.call("ipb_fa_contour_cells", d_crops.ptr, 1, h * w, labels.ptr, rec.ptr, rec_n.ptr, mem.stream)
+        contours = [ct.contours_of_crop(rec.host(), int(rec_n.host()[0]), w)]
+    items = batch.fa_items(res, config, contours=contours)[0]
     bits = np.unpackbits(bufs[3].host().reshape(h, wpr).view(np.uint8), axis=1, bitorder="little")[:, :w].astype(bool)
     return items, thr, bits, labels.host().reshape(h, w)
 

@@ -455,12 +455,12 @@ def save_excel(rows_all, keymap, xls_dir, log=print):
     return csv_path
 
 
-def run_headless(img_dir, roi_dir, out_root=None, cfg=None, eng=None, log=print):
+def run_headless(img_dir, roi_dir, out_root=None, cfg=None, eng=None, log=print, frames_per_batch=32, timing=None):
     """_run_pipeline without Tk: tasks -> device batches -> RES/xls/fluor_intensity_perROI.csv."""
     out_root = out_root or os.path.join(img_dir, "RES")
     tasks, keymap = build_tasks(img_dir, roi_dir, out_root, cfg or {})
     rows_all = []
-    for res in process_key_tasks(tasks, eng=eng):
+    for res in process_key_tasks(tasks, eng=eng, frames_per_batch=frames_per_batch, timing=timing):
         rows_all.extend(res["rows"])
         for line in res.get("logs", []):
             log(line)

@@ -49,16 +49,18 @@ class _FaView:
 
 
 def fa_batch(eng, planes, shape, polys_per_frame, params, px_size, channel=0, save_ok_only=True,
-             want_labels=False, config=None, fa_path=0):
+             want_labels=False, config=None, fa_path=0, want_contours=False):
     """FA_Analyzer batch body for F frames (reference src/INT/FA_Analyzer.py:984-1039)."""
     F = shape[0]
     cfg = config or fa_um_to_px_config(params, px_size)
     job = batch.FrameBatchJob(eng, shape, stages=("fa",), fa_params=params, fa_px=px_size, fa_ch=channel,
-                              want_labels=want_labels, fa_config=cfg)
+                              want_labels=want_labels, fa_config=cfg, want_contours=want_contours)
     job.fa_path = fa_path
     res = job.run(planes, polys_per_frame)
+    contours = batch.fa_contours(res) if want_contours else None
     owner = [(int(f), int(r)) for f, r in zip(res.frame, res.roi)]
     rects = [tuple(int(v) for v in rc) for rc in res.fa_rect]
     return {"rows_per_frame": batch.rows_fa(res, cfg, params, px_size, F, save_ok_only),
             "stats": res.fa_stats, "result": _FaView(res), "items_per_crop": batch.fa_items(res, cfg),
+            "contours": contours,
             "owner": owner, "rects": rects, "d2h_bytes": res.d2h_bytes, "raw": res}

@@ -289,6 +289,18 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    int32_t* labels, int path /* 0 auto, 1 one CTA per crop, 2 one kernel per phase */,
                    const int32_t* crop_order /* [dev] optional: crops by decreasing size */, void* stream);
 
+/* Outlines of every labelled adhesion of every crop in ONE pass over the label maps: replaces the
+ * reference's per-adhesion skimage.measure.find_contours(labeled_img == k, 0.5) loop
+ * (INT/FA_Analyzer.py:166-170, O(adhesions x crop pixels)).  For each 2 x 2 cell of a crop's label map
+ * and each label k cut by it, one record {cell = r0 * w + c0, k << 4 | case} with the marching-squares
+ * case (bit 0 ul, 1 ur, 2 ll, 3 lr of the mask label == k; cases 1..14).  The host links a label's
+ * cells in raster order into skimage's contour polylines (imageprocess_b200/contours.py).
+ *   labels     int32 [total_px]: the label maps ipb_fa_segment wrote (crop c at ipb_crop.pix_off)
+ *   rec        uint32 [total_px][2]: record slice of crop c at pix_off (at most w*h records are kept)
+ *   rec_count  uint32 [n_crops]: records emitted per crop (cleared by the call)                     */
+int ipb_fa_contour_cells(const void* crops, int n_crops, int64_t max_px, const int32_t* labels, void* rec,
+                         uint32_t* rec_count, void* stream);
+
 /* ------------------------------------------------------------------ morphology, moments, previews
  * ipb_region_dilate: dilation of region masks (ipb_region layout, all pools share mask_off)
  * by a symmetric row-convex structuring element  gmax[|dx|] = largest |dy| covered at

@@ -158,12 +158,118 @@ def regionprops(label_image, intensity_image=None, **_):
     return [RegionProperties(l, label_image, intensity_image) for l in labs if l != 0]
 
 
-def find_contours(image, level=0.5, **_):
-    """Placeholder for skimage.measure.find_contours: FA_Analyzer.py:168 uses the
-    result only for drawing and as an emptiness check (never empty for a non-empty
-    region).  Returns the outer boundary pixels as one (N, 2) float array."""
-    m = np.asarray(image) > level
-    if not m.any():
-        return []
-    er = ndi.binary_erosion(m)
-    return [np.argwhere(m & ~er).astype(np.float64)]
+def _mc_fraction(a, b, level):
+    return 0.0 if b == a else (level - a) / (b - a)
+
+
+def _contour_segments(array, level, vertex_connect_high=False):
+    """skimage/measure/_find_contours_cy.pyx _get_contour_segments (scikit-image is unpinned in
+    requirements.txt:8; restated from the published source): marching squares over every 2 x 2
+    cell in raster order, 0-2 oriented segments per cell, points interpolated linearly."""
+    segs = []
+    H, W = array.shape
+    for r0 in range(H - 1):
+        r1 = r0 + 1
+        for c0 in range(W - 1):
+            c1 = c0 + 1
+            ul, ur, ll, lr = array[r0, c0], array[r0, c1], array[r1, c0], array[r1, c1]
+            if np.isnan(ul) or np.isnan(ur) or np.isnan(ll) or np.isnan(lr):
+                continue
+            case = (1 if ul > level else 0) + (2 if ur > level else 0) + (4 if ll > level else 0) + (8 if lr > level else 0)
+            if case in (0, 15):
+                continue
+            top = (float(r0), c0 + _mc_fraction(ul, ur, level))
+            bottom = (float(r1), c0 + _mc_fraction(ll, lr, level))
+            left = (r0 + _mc_fraction(ul, ll, level), float(c0))
+            right = (r0 + _mc_fraction(ur, lr, level), float(c1))
+            if case == 1:
+                segs.append((top, left))
+            elif case == 2:
+                segs.append((right, top))
+            elif case == 3:
+                segs.append((right, left))
+            elif case == 4:
+                segs.append((left, bottom))
+            elif case == 5:
+                segs.append((top, bottom))
+            elif case == 6:
+                if vertex_connect_high:
+                    segs.append((left, top)); segs.append((right, bottom))
+                else:
+                    segs.append((right, top)); segs.append((left, bottom))
+            elif case == 7:
+                segs.append((right, bottom))
+            elif case == 8:
+                segs.append((bottom, right))
+            elif case == 9:
+                if vertex_connect_high:
+                    segs.append((top, right)); segs.append((bottom, left))
+                else:
+                    segs.append((top, left)); segs.append((bottom, right))
+            elif case == 10:
+                segs.append((bottom, top))
+            elif case == 11:
+                segs.append((bottom, left))
+            elif case == 12:
+                segs.append((left, right))
+            elif case == 13:
+                segs.append((top, right))
+            elif case == 14:
+                segs.append((left, top))
+    return segs
+
+
+def _assemble_contours(segments):
+    """skimage/measure/_find_contours.py _assemble_contours: links oriented segments into
+    polylines; contours are returned in the order in which their first segment appeared."""
+    from collections import deque
+    current_index = 0
+    contours, starts, ends = {}, {}, {}
+    for from_point, to_point in segments:
+        if from_point == to_point:
+            continue
+        tail, tail_num = starts.pop(to_point, (None, None))
+        head, head_num = ends.pop(from_point, (None, None))
+        if tail is not None and head is not None:
+            if tail is head:
+                head.append(to_point)
+            elif tail_num > head_num:
+                head.extend(tail)
+                contours.pop(tail_num, None)
+                starts[head[0]] = (head, head_num)
+                ends[head[-1]] = (head, head_num)
+            else:
+                tail.extendleft(reversed(head))
+                starts.pop(head[0], None)
+                contours.pop(head_num, None)
+                starts[tail[0]] = (tail, tail_num)
+                ends[tail[-1]] = (tail, tail_num)
+        elif tail is None and head is None:
+            new_contour = deque((from_point, to_point))
+            contours[current_index] = new_contour
+            starts[from_point] = (new_contour, current_index)
+            ends[to_point] = (new_contour, current_index)
+            current_index += 1
+        elif head is None:
+            tail.appendleft(from_point)
+            starts[from_point] = (tail, tail_num)
+        else:
+            head.append(to_point)
+            ends[to_point] = (head, head_num)
+    return [np.array(c) for _, c in sorted(contours.items())]
+
+
+def find_contours(image, level=0.5, fully_connected="low", positive_orientation="low", **_):
+    """skimage.measure.find_contours (FA_Analyzer.py:168: find_contours(labeled_img == k, 0.5)):
+    marching squares + assembly, float64 (row, col) points; no padding, so outlines of regions that
+    touch the array border stay open.  Parity unpinned by a reference artefact (scikit-image absent)."""
+    arr = np.asarray(image)
+    if arr.dtype == bool or arr.dtype.kind in "iu":
+        arr = arr.astype(np.float64)
+    if arr.ndim != 2 or arr.shape[0] < 2 or arr.shape[1] < 2:
+        raise ValueError("Input array must be at least 2x2.")
+    segs = _contour_segments(arr.astype(np.float64), float(level), fully_connected == "high")
+    contours = _assemble_contours(segs)
+    if positive_orientation == "high":
+        contours = [c[::-1] for c in contours]
+    return contours

@@ -259,8 +259,9 @@ def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168, fa_path=0, frames=
     F, C = planes.shape[:2]
     H, W = planes.shape[2:]
     out = pipeline.fa_batch(eng, eng.mem.from_host(planes), (F, C, H, W), [fr[2] for fr in frames],
-                            params, px, channel=0, save_ok_only=False, want_labels=True, fa_path=fa_path)
+                            params, px, channel=0, save_ok_only=False, want_labels=True, fa_path=fa_path, want_contours=True)
     cfg = pipeline.fa_um_to_px_config(params, px)
+    contours = out["contours"]
     straddles = 0
     k = 0
     for f, (d, a, polys) in enumerate(frames):
@@ -284,6 +285,13 @@ def check_fa_batch(eng, params, seeds=(21, 22), H=120, W=168, fa_path=0, frames=
             res, thr, bw, lab = port.analyze_fa_crop(crop, mask, cfg, stats, with_contours=False)
             assert np.array_equal(out["result"].bw_host(k), bw), (f, i)
             assert np.array_equal(out["result"].labels_host(k), lab), (f, i)
+            # outlines: every contour of every adhesion equals find_contours(labeled_img == label, 0.5)
+            for label in range(1, int(lab.max()) + 1):
+                want_c = shims.find_contours(lab == label, 0.5)
+                got_c = contours[k].get(label, [])
+                assert len(got_c) == len(want_c), (f, i, label, len(got_c), len(want_c))
+                for gc, wc in zip(got_c, want_c):
+                    assert gc.dtype == wc.dtype and np.array_equal(gc, wc), (f, i, label)
             for cat in ("OK", "Large", "Small"):
                 g_items, w_items = out["items_per_crop"][k][cat], res[cat]
                 assert len(g_items) == len(w_items), (f, i, cat)

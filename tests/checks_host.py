@@ -157,7 +157,7 @@ def check_fa_mirror(eng, tmp):
     # single-crop entry point, the GUI's call shape
     for P in polys:
         crop, mask, _ = port.fa_crop_and_mask(img, P.copy())
-        wres, wthr, wbw, wlab = port.analyze_fa_crop(crop, mask, cfg, stats, with_contours=False)
+        wres, wthr, wbw, wlab = port.analyze_fa_crop(crop, mask, cfg, stats, with_contours=True)
         gres, gthr, gbw, glab = FA_Analyzer.analyze_fa_crop(crop, mask, cfg, stats, eng=eng)
         assert gthr == wthr and type(gthr) is type(wthr)
         assert np.array_equal(gbw, wbw) and np.array_equal(glab, wlab)
@@ -166,6 +166,7 @@ def check_fa_mirror(eng, tmp):
             for g, w in zip(gres[cat], wres[cat]):
                 assert g["label"] == w["label"] and g["area"] == w["area"] and g["centroid"] == w["centroid"]
                 assert close(float(g["mean_int_raw"]), float(w["mean_int_raw"]))
+                assert g["contour"].dtype == np.float64 and np.array_equal(g["contour"], w["contour"])     # FA_Analyzer.py:168-170
     e = FA_Analyzer.analyze_fa_crop(np.array([]), np.zeros((0,), bool), cfg, stats, eng=eng)
     assert e[0] == {"OK": [], "Large": [], "Small": []} and e[1] == 0
     # batch body on a folder
