@@ -29,7 +29,7 @@ _PROTOS = {
     "ipb_fa_params": [_vp, _vp, _vp, _i, _i64, _f, _vp, _vp],
     "ipb_fret_pixels": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "ipb_fa_segment": [_vp, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                       _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
+                       _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp],
     "ipb_region_stats": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "ipb_roi_stats_fused": [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp],
 }
@@ -42,6 +42,11 @@ _PROTOS.update({
     "ipb_hist_planes": [_vp, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "ipb_hist_select": [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ipb_selftest_fdiv": [_vp, _vp, _i64, _vp, _vp],
+    "ipb_gaussian_f32": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    "ipb_gauss_combine": [_vp, _vp, _vp, _i64, _i, _f, _vp],
+    "ipb_graymorph_u16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "ipb_sub_u16": [_vp, _vp, _vp, _i64, _vp],
+    "ipb_convert_planes": [_vp, _vp, _i64, _i, _vp],
     "ipb_fa_contour_cells": [_vp, _i, _i64, _vp, _vp, _vp, _vp],
     "ipb_hist_sizes": [_i, _i, _i, _vp],
     "ipb_hist_select_sizes": [_i, _i, _vp],

@@ -18,6 +18,8 @@
 #include "ipb_fa.cuh"
 #include "ipb_morph.cuh"
 #include "ipb_contour.cuh"
+#include "ipb_gauss.cuh"
+#include "ipb_graymorph.cuh"
 
 static thread_local char g_ipb_err[512] = "";
 
@@ -59,6 +61,25 @@ static int ipb_launch_region_stats(const void* regions, const void* jobs, int n_
                (const IpbRegion*)regions, (const IpbStatJob*)jobs, n_jobs, mask_pool, and_bits, and_wpr, H, W,
                planes, images, bvals, (IpbStatOut*)out, smem, (const unsigned char*)only);
     return ipb_check_launch("ipb_k_region_stats");
+}
+
+template <bool MAX>
+static int ipb_launch_graymorph(const uint16_t* in, uint16_t* tmp, uint16_t* out, int n, int H, int W, int radius, void* stream)
+{
+    const int use_tma = (W % 8 == 0) && (((size_t)in | (size_t)tmp) % 16 == 0) && ((size_t)H * W % 8 == 0);
+    const dim3 block(IPB_GS_THREADS);
+    const size_t smem0 = (size_t)(IPB_GM_TILE_H0 + 2 * radius) * IPB_GM_TILE_W * sizeof(uint16_t);
+    const size_t smem1 = (size_t)IPB_GM_TILE_H1 * (IPB_GM_TILE_W + 2 * ((radius + 7) & ~7)) * sizeof(uint16_t);
+    auto k0 = ipb_k_graymorph_pass<0, MAX>;
+    auto k1 = ipb_k_graymorph_pass<1, MAX>;
+    IPB_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0), "graymorph smem");
+    IPB_LAUNCH(k0, dim3(ipb_div_up(W, IPB_GM_TILE_W), ipb_div_up(H, IPB_GM_TILE_H0), (unsigned)n), block, smem0, stream,
+               in, tmp, H, W, radius, use_tma);
+    int rc = ipb_check_launch("ipb_k_graymorph_pass<0>");
+    if (rc) return rc;
+    IPB_LAUNCH(k1, dim3(ipb_div_up(W, IPB_GM_TILE_W), ipb_div_up(H, IPB_GM_TILE_H1), (unsigned)n), block, smem1, stream,
+               tmp, out, H, W, radius, use_tma);
+    return ipb_check_launch("ipb_k_graymorph_pass<1>");
 }
 
 extern "C" {
@@ -370,10 +391,11 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    uint32_t* bw_a, uint32_t* bw_b, int32_t* L, uint32_t* csize, uint32_t* rootbits,
                    int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
                    uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
-                   int32_t* labels, int path, const int32_t* crop_order, void* stream)
+                   int32_t* labels, int path, const int32_t* crop_order, int label_conn, void* stream)
 {
     if (n_crops <= 0) return IPB_OK;
     IPB_REQUIRE(path >= 0 && path <= 3, "ipb_fa_segment: path %d not in 0..3", path);
+    IPB_REQUIRE(label_conn == 8 || label_conn == 4, "ipb_fa_segment: label_conn %d not 4 or 8", label_conn);
     IPB_REQUIRE(n_crops <= 65535, "ipb_fa_segment: n_crops %d out of range", n_crops);
     IPB_REQUIRE(crops && planes && fa_params && roi_mask && bw_a && bw_b && L && csize && rootbits &&
                 row_roots && row_base && crop_count && bw_final && comp_off && comps,
@@ -397,7 +419,9 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
     // that do not fit are flagged and taken by the global-memory variant right after); few / huge
     // crops (the mosaic): one kernel per phase, each crop spread over the chip.  path 3 = the
     // global-memory per-crop kernel for every crop.
-    const bool fused = path == 1 || path == 3 || (path == 0 && n_crops >= 64 && max_rows <= 1024);
+    // (4-connected final labels -- scipy.ndimage.label's default, used by the ROI drawer's assist -- are
+    // served by the one-kernel-per-phase path only)
+    const bool fused = label_conn == 8 && (path == 1 || path == 3 || (path == 0 && n_crops >= 64 && max_rows <= 1024));
     if (fused) {
         if (path != 3) {
             IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_fa_fused_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -433,7 +457,8 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
         if ((rc = ipb_check_launch("ipb_k_bits_morph"))) return rc;
         IPB_CUDA_TRY(cudaMemsetAsync(row_roots, 0, sizeof(int32_t) * (size_t)total_rows, (cudaStream_t)stream), "memset row_roots");
         IPB_LAUNCH(ipb_k_ccl_init, grid, block, 0, stream, cr, (const unsigned*)bw_final, L, (unsigned*)nullptr);
-        IPB_LAUNCH(ipb_k_ccl_merge<8>, grid, block, 0, stream, cr, (const unsigned*)bw_final, L);
+        if (label_conn == 4) IPB_LAUNCH(ipb_k_ccl_merge<4>, grid, block, 0, stream, cr, (const unsigned*)bw_final, L);
+        else IPB_LAUNCH(ipb_k_ccl_merge<8>, grid, block, 0, stream, cr, (const unsigned*)bw_final, L);
         IPB_LAUNCH(ipb_k_ccl_flatten_roots, grid, block, 0, stream, cr, (const unsigned*)bw_final, L, rootbits, row_roots);
         IPB_LAUNCH(ipb_k_fa_row_scan, dim3(n_crops), dim3(256), 0, stream, cr, (const int*)row_roots, row_base, crop_count);
         if ((rc = ipb_check_launch("ipb_fa labelling"))) return rc;
@@ -536,6 +561,67 @@ int ipb_fa_contour_cells(const void* crops, int n_crops, int64_t max_px, const i
     IPB_LAUNCH(ipb_k_fa_contour_cells, dim3(gx, (unsigned)n_crops), dim3(256), 0, stream, (const IpbCrop*)crops, labels,
                (uint2*)rec, rec_count);
     return ipb_check_launch("ipb_k_fa_contour_cells");
+}
+
+int ipb_gaussian_f32(const float* in, float* tmp, float* out, int n_images, int H, int W,
+                     const double* weights, int radius, void* stream)
+{
+    if (n_images <= 0) return IPB_OK;
+    IPB_REQUIRE(in && tmp && out && weights && H > 0 && W > 0, "ipb_gaussian_f32: bad argument");
+    IPB_REQUIRE(radius >= 0 && radius <= IPB_GS_MAXR, "ipb_gaussian_f32: radius %d not in 0..%d", radius, IPB_GS_MAXR);
+    IPB_REQUIRE(n_images <= 65535, "ipb_gaussian_f32: n_images %d out of range", n_images);
+    // TMA needs 16-byte aligned row segments; other shapes take the plain loads of the same kernels
+    const int use_tma = (W % 4 == 0) && (((size_t)in | (size_t)tmp) % 16 == 0) && ((size_t)H * W % 4 == 0);
+    const dim3 block(IPB_GS_THREADS);
+    const size_t smem0 = (size_t)(IPB_GS_TILE_H0 + 2 * radius) * IPB_GS_TILE_W * sizeof(float);
+    const size_t smem1 = (size_t)IPB_GS_TILE_H1 * (IPB_GS_TILE_W + 2 * ((radius + 3) & ~3)) * sizeof(float);
+    IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_gauss_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0), "gauss smem");
+    IPB_LAUNCH(ipb_k_gauss_pass<0>, dim3(ipb_div_up(W, IPB_GS_TILE_W), ipb_div_up(H, IPB_GS_TILE_H0), (unsigned)n_images), block,
+               smem0, stream, in, tmp, H, W, weights, radius, use_tma);
+    int rc = ipb_check_launch("ipb_k_gauss_pass<0>");
+    if (rc) return rc;
+    IPB_LAUNCH(ipb_k_gauss_pass<1>, dim3(ipb_div_up(W, IPB_GS_TILE_W), ipb_div_up(H, IPB_GS_TILE_H1), (unsigned)n_images), block,
+               smem1, stream, tmp, out, H, W, weights, radius, use_tma);
+    return ipb_check_launch("ipb_k_gauss_pass<1>");
+}
+
+int ipb_gauss_combine(const float* a, const float* b, float* out, int64_t n, int unsharp, float amount, void* stream)
+{
+    if (n <= 0) return IPB_OK;
+    IPB_REQUIRE(a && b && out, "ipb_gauss_combine: null pointer");
+    IPB_LAUNCH(ipb_k_gauss_combine, dim3(ipb_div_up(n, 256 * 8) > 4736u ? 4736u : ipb_div_up(n, 256 * 8)), dim3(256), 0, stream,
+               a, b, out, (long long)n, unsharp, amount);
+    return ipb_check_launch("ipb_k_gauss_combine");
+}
+
+int ipb_graymorph_u16(const uint16_t* in, uint16_t* tmp, uint16_t* out, int n_images, int H, int W, int radius, int dilate,
+                      void* stream)
+{
+    if (n_images <= 0) return IPB_OK;
+    IPB_REQUIRE(in && tmp && out && H > 0 && W > 0, "ipb_graymorph_u16: bad argument");
+    IPB_REQUIRE(radius >= 0 && radius <= IPB_GM_MAXR, "ipb_graymorph_u16: radius %d not in 0..%d", radius, IPB_GM_MAXR);
+    IPB_REQUIRE(n_images <= 65535, "ipb_graymorph_u16: n_images %d out of range", n_images);
+    return dilate ? ipb_launch_graymorph<true>(in, tmp, out, n_images, H, W, radius, stream)
+                  : ipb_launch_graymorph<false>(in, tmp, out, n_images, H, W, radius, stream);
+}
+
+int ipb_sub_u16(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n, void* stream)
+{
+    if (n <= 0) return IPB_OK;
+    IPB_REQUIRE(a && b && out, "ipb_sub_u16: null pointer");
+    IPB_LAUNCH(ipb_k_sub_u16, dim3(ipb_div_up(n, 256 * 8) > 4736u ? 4736u : ipb_div_up(n, 256 * 8)), dim3(256), 0, stream, a, b, out,
+               (long long)n);
+    return ipb_check_launch("ipb_k_sub_u16");
+}
+
+int ipb_convert_planes(const void* in, void* out, int64_t n, int to_u16, void* stream)
+{
+    if (n <= 0) return IPB_OK;
+    IPB_REQUIRE(in && out, "ipb_convert_planes: null pointer");
+    const unsigned g = ipb_div_up(n, 256 * 8) > 4736u ? 4736u : ipb_div_up(n, 256 * 8);
+    if (to_u16) IPB_LAUNCH(ipb_k_f32_to_u16, dim3(g), dim3(256), 0, stream, (const float*)in, (unsigned short*)out, (long long)n);
+    else IPB_LAUNCH(ipb_k_u16_to_f32, dim3(g), dim3(256), 0, stream, (const unsigned short*)in, (float*)out, (long long)n);
+    return ipb_check_launch("ipb_convert_planes");
 }
 
 int ipb_selftest_fdiv(const float* a, const float* b, int64_t n, uint32_t* mismatches, void* stream)

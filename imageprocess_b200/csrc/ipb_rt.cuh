@@ -70,8 +70,9 @@ __device__ __forceinline__ T ipb_warp_max(T v) {
 
 // ---- TMA bulk copies (cp.async.bulk, 1-D) tracked by an mbarrier: global -> shared rows without a
 // register round trip or an issue slot per 16 bytes.  Product build: inline PTX for sm_100a (SASS:
-// UBLKCP + SYNCS).  Emulated build: the copy happens at once, the wait is a no-op.
-struct IpbMbar { unsigned long long v; };
+// UBLKCP + SYNCS).  Emulated build: the copy happens at once and completes the phase when the announced
+// bytes are in; the wait yields until the phase of the given parity is complete (the hardware's rule).
+struct IpbMbar { unsigned long long v; };          // emulated: low word = completed phases, high word = bytes pending
 
 __device__ __forceinline__ void ipb_mbar_init(IpbMbar* bar, unsigned count) {
 #ifdef IPB_EMULATE
@@ -92,7 +93,8 @@ __device__ __forceinline__ void ipb_mbar_fence_init() {
 // aligned, bytes a multiple of 16); the barrier completes its phase when the bytes have landed
 __device__ __forceinline__ void ipb_bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, IpbMbar* bar) {
 #ifdef IPB_EMULATE
-    memcpy(dst_smem, src_gmem, bytes); (void)bar;
+    memcpy(dst_smem, src_gmem, bytes);
+    bar->v = (bar->v & 0xffffffffull) + 1ull;
 #else
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
@@ -100,10 +102,31 @@ __device__ __forceinline__ void ipb_bulk_load(void* dst_smem, const void* src_gm
                  :: "r"(d), "l"(src_gmem), "r"(bytes), "r"(b) : "memory");
 #endif
 }
+// several copies on one barrier phase: ONE thread announces the total first, then starts the copies
+__device__ __forceinline__ void ipb_mbar_expect(IpbMbar* bar, unsigned total_bytes) {
+#ifdef IPB_EMULATE
+    bar->v = (bar->v & 0xffffffffull) | ((unsigned long long)total_bytes << 32);
+    if (total_bytes == 0) bar->v = (bar->v & 0xffffffffull) + 1ull;
+#else
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(total_bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void ipb_bulk_copy(void* dst_smem, const void* src_gmem, unsigned bytes, IpbMbar* bar) {
+#ifdef IPB_EMULATE
+    memcpy(dst_smem, src_gmem, bytes);
+    const unsigned long long left = (bar->v >> 32) - bytes;
+    bar->v = left ? ((bar->v & 0xffffffffull) | (left << 32)) : ((bar->v & 0xffffffffull) + 1ull);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(d), "l"(src_gmem), "r"(bytes), "r"(b) : "memory");
+#endif
+}
 // every consumer thread: blocks until the barrier's phase with parity `parity` has completed
 __device__ __forceinline__ void ipb_mbar_wait(IpbMbar* bar, unsigned parity) {
 #ifdef IPB_EMULATE
-    (void)bar; (void)parity;
+    while (((unsigned)(bar->v & 1ull)) == parity) emu::yield();
 #else
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("{ .reg .pred p;\n\t"

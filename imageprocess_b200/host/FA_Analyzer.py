@@ -100,7 +100,7 @@ def analyze_fa_crop(image_crop, roi_mask_crop, config, global_stats, eng=None, w
     eng.call("ipb_fa_segment", d_crops.ptr, 1, h, h, mem.from_host(plane.reshape(1, h, w)).ptr, h, w, fa_params.ptr,
              pool.ptr, float(min_px) if min_px > 0 else 0.0, int(rad) if rad > 0 else 0, bufs[0].ptr, bufs[1].ptr,
              L.ptr, cs.ptr, bufs[2].ptr, rr.ptr, rb.ptr, cc.ptr, bufs[3].ptr, comp_off.ptr, comps.ptr, cap,
-             labels.ptr, 0, None, mem.stream)
+             labels.ptr, 0, None, 8, mem.stream)
     off = comp_off.host()
     res = batch.BatchResult()
     res.n_rois, res.frame, res.roi = 1, np.array([0]), np.array([1])

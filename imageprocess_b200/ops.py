@@ -363,7 +363,7 @@ def _engine_fa_segment(self, rm, crops, total_px, total_rows, planes, H, W, fa_p
               planes.ptr, int(H), int(W), fa_params.ptr, rm.pool.ptr, float(min_size), int(close_radius),
               bw_a.ptr, bw_b.ptr, L.ptr, csize.ptr, rootbits.ptr, row_roots.ptr, row_base.ptr,
               crop_count.ptr, bw_f.ptr, comp_off.ptr, comps.ptr, int(comp_cap),
-              labels.ptr if labels is not None else None, 0, None, mem.stream)
+              labels.ptr if labels is not None else None, 0, None, 8, mem.stream)
     return FaResult(crops, bw_f, comp_off, comps, labels, comp_cap,
                     (d_crops, bw_a, bw_b, rootbits, L, csize, row_roots, row_base, crop_count))
 

@@ -49,12 +49,22 @@ class _FaView:
 
 
 def fa_batch(eng, planes, shape, polys_per_frame, params, px_size, channel=0, save_ok_only=True,
-             want_labels=False, config=None, fa_path=0, want_contours=False):
-    """FA_Analyzer batch body for F frames (reference src/INT/FA_Analyzer.py:984-1039)."""
+             want_labels=False, config=None, fa_path=0, want_contours=False, prefilter=None, threshold=None):
+    """FA_Analyzer batch body for F frames (reference src/INT/FA_Analyzer.py:984-1039).
+
+    Optional stages, OFF by default (the reference has none of them; BASELINE.json's north_star names
+    them; their oracle is scipy.ndimage / the restated skimage rule): prefilter = ("tophat", size) or
+    ("gaussian", sigma) filters the FA channel first (filters.prefilter_planes); threshold = "otsu"
+    replaces mean + alpha * std by Otsu's threshold of the (filtered) frame."""
     F = shape[0]
     cfg = config or fa_um_to_px_config(params, px_size)
+    if prefilter is not None:
+        from . import filters
+        planes = filters.prefilter_planes(eng, planes, shape, channel, prefilter)
+        shape, channel = (F, 1, shape[2], shape[3]), 0
     job = batch.FrameBatchJob(eng, shape, stages=("fa",), fa_params=params, fa_px=px_size, fa_ch=channel,
                               want_labels=want_labels, fa_config=cfg, want_contours=want_contours)
+    job.fa_threshold = threshold
     job.fa_path = fa_path
     res = job.run(planes, polys_per_frame)
     contours = batch.fa_contours(res) if want_contours else None

@@ -287,7 +287,9 @@ int ipb_fa_segment(const void* crops, int n_crops, int max_rows, int64_t total_r
                    int32_t* row_roots, int32_t* row_base, int32_t* crop_count,
                    uint32_t* bw_final, int32_t* comp_off, void* comps, int comp_cap,
                    int32_t* labels, int path /* 0 auto, 1 one CTA per crop, 2 one kernel per phase */,
-                   const int32_t* crop_order /* [dev] optional: crops by decreasing size */, void* stream);
+                   const int32_t* crop_order /* [dev] optional: crops by decreasing size */,
+                   int label_conn /* 8: skimage.measure.label (the FA chain); 4: scipy.ndimage.label's default */,
+                   void* stream);
 
 /* Outlines of every labelled adhesion of every crop in ONE pass over the label maps: replaces the
  * reference's per-adhesion skimage.measure.find_contours(labeled_img == k, 0.5) loop
@@ -332,6 +334,36 @@ int ipb_crop_normalize(const void* jobs, int n_jobs, int64_t max_px, const uint1
  * on a spectrally corrected denominator, Nesprin2_FRET_Builder.py:470-476,1484-1486).       */
 int ipb_eps_from_stat(const void* stat_out, const int32_t* row_of_frame, int n_frames, float eps_abs,
                       float* fparams, void* stream);
+
+/* ------------------------------------------------------------------ Gaussian filter
+ * scipy.ndimage.gaussian_filter(img, sigma) on float32 images, bit for bit: axis 0 then axis 1, mode
+ * 'reflect', float64 accumulation in scipy's order, float32 stored after each pass.  Replaces the
+ * display filters of the interactive ROI drawer (roi_manual_drawer.py:870-876: band-pass =
+ * gaussian(sigma_small) - gaussian(sigma_large); unsharp = im + amount * (im - gaussian(radius))) and
+ * serves the optional, default-OFF Gaussian pre-filter stage.  Shared-memory halo tiles are filled by
+ * TMA bulk copies (cp.async.bulk + mbarrier) when W % 4 == 0 and the images are 16-byte aligned.
+ *   weights  float64 [radius + 1] [dev]: centre weight, then offsets 1..radius; the caller computes them
+ *            as scipy does: x = arange(-r, r + 1); w = exp(-0.5 / sigma^2 * x^2); w /= w.sum();
+ *            radius = int(4 * sigma + 0.5) (truncate = 4.0), at most 160
+ *   tmp      float32 scratch of the input's size; in, tmp, out: [n_images][H][W]
+ * ipb_gauss_combine: out = a - b (unsharp = 0) or a + amount * (a - b), float32 ops rounded one by one. */
+int ipb_gaussian_f32(const float* in, float* tmp, float* out, int n_images, int H, int W,
+                     const double* weights, int radius, void* stream);
+int ipb_gauss_combine(const float* a, const float* b, float* out, int64_t n, int unsharp, float amount, void* stream);
+
+/* ------------------------------------------------------------------ grey-scale morphology (optional stage)
+ * scipy.ndimage.grey_erosion / grey_dilation(input, size = 2 * radius + 1) on uint16 planes, mode
+ * 'reflect', separable min / max on TMA-filled shared-memory halo tiles (W % 8 == 0, else plain loads).
+ * white_tophat(input, size) = input - grey_dilation(grey_erosion(input)) = ipb_graymorph_u16 twice +
+ * ipb_sub_u16.  The reference has no such stage (north_star names a top-hat filter): optional, OFF by
+ * default; the oracle is scipy.ndimage itself.  tmp: scratch of the input's size; radius <= 64.      */
+int ipb_graymorph_u16(const uint16_t* in, uint16_t* tmp, uint16_t* out, int n_images, int H, int W, int radius, int dilate,
+                      void* stream);
+int ipb_sub_u16(const uint16_t* a, const uint16_t* b, uint16_t* out, int64_t n, void* stream);
+
+/* uint16 <-> float32 planes around the optional Gaussian pre-filter of an integer channel:
+ * to_u16 = 0: out float32 = float32(in uint16);  to_u16 = 1: out uint16 = clip(rint(in float32), 0, 65535).  */
+int ipb_convert_planes(const void* in, void* out, int64_t n, int to_u16, void* stream);
 
 /* Self-test of the branch-free division ipb_roi_stats_fused uses for ratios whose operands are known to
  * lie in [5, 65536 + eps]: *mismatches (zeroed by the caller) += number of pairs (a[i], b[i]) whose

@@ -698,3 +698,53 @@ def cropper_normalize(img, raw_full, P, low_cut, high_cut, gamma, mask_outside=T
         raw_out[~local_mask] = 0
     return {"norm_gamma": norm_gamma, "out16": out16, "raw_out": raw_out,
             "rect": (x0, x1, y0, y1), "mask": local_mask, "lo": lo, "hi": hi}
+
+
+# ---------------------------------------------------------------- ROI drawer assist (roi_manual_drawer.py:337-418)
+def segment_inside_polygon(img, poly, thr_param=90.0, min_area=40, tolerance=1.0, mode="percentile"):
+    """roi_manual_drawer.segment_inside_polygon: bounding-box slice, matplotlib mask, percentile or
+    mean + k * std threshold, largest 4-connected component, hole fill, contours, polygon area,
+    Douglas-Peucker; returns (thr, None, best polygon)."""
+    from scipy import ndimage as ndi
+    H, W = img.shape[:2]
+    poly_arr = np.asarray(poly)
+    min_x = int(np.floor(np.min(poly_arr[:, 0]))); max_x = int(np.ceil(np.max(poly_arr[:, 0])))
+    min_y = int(np.floor(np.min(poly_arr[:, 1]))); max_y = int(np.ceil(np.max(poly_arr[:, 1])))
+    min_x = max(0, min_x); max_x = min(W, max_x)
+    min_y = max(0, min_y); max_y = min(H, max_y)
+    if max_x <= min_x or max_y <= min_y:
+        return None, None, None
+    sub_img = img[min_y:max_y, min_x:max_x]
+    sh, sw = sub_img.shape
+    inside_sub = rasterize_polygon(poly_arr - [min_x, min_y], (sh, sw))
+    vals = sub_img[inside_sub]
+    if vals.size == 0:
+        return None, None, None
+    thr_param = float(thr_param)
+    if mode.lower() == "bnd":
+        m = float(np.nanmean(vals)); s = float(np.nanstd(vals))
+        thr = float(np.percentile(vals, 90.0)) if (s <= 0) or (not np.isfinite(s)) else m + thr_param * s
+    else:
+        thr = float(np.percentile(vals, thr_param))
+    cand_sub = (sub_img >= thr) & inside_sub
+    lab, n = ndi.label(cand_sub)
+    if n == 0:
+        return thr, None, None
+    sizes = ndi.sum(cand_sub, lab, index=np.arange(1, n + 1))
+    k = int(np.argmax(sizes)) + 1
+    mask_sub = ndi.binary_fill_holes(lab == k)
+    contours = shims.find_contours(mask_sub.astype(float), 0.5)
+    if not contours:
+        return thr, None, None
+    polys = []
+    for c in contours:
+        xy = np.c_[c[:, 1] + min_x, c[:, 0] + min_y]
+        x, y = xy[:, 0], xy[:, 1]
+        area = 0.5 * np.abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+        if area >= float(min_area):
+            xy_s = shims.approximate_polygon(xy, tolerance=float(tolerance))
+            if len(xy_s) >= 3:
+                polys.append((area, xy_s))
+    if not polys:
+        return thr, None, None
+    return thr, None, max(polys, key=lambda t: t[0])[1]

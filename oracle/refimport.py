@@ -60,6 +60,7 @@ def install_stubs():
                 sys.modules[name] = _Anything(name)
     mpl_names = ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.figure",
                  "matplotlib.patches", "matplotlib.backends", "matplotlib.backends.backend_tkagg",
+                 "matplotlib.widgets", "matplotlib.patheffects",
                  "mpl_toolkits", "mpl_toolkits.axes_grid1", "mpl_toolkits.axes_grid1.inset_locator",
                  "pptx", "pptx.util")
     for name in mpl_names:
@@ -70,6 +71,7 @@ def install_stubs():
     sys.modules["matplotlib.path"] = mpath
     sys.modules["matplotlib"].path = mpath
     sys.modules["matplotlib"].use = lambda *a, **k: None
+    sys.modules["matplotlib"].rcParams = {}                       # roi_manual_drawer.py:22 assigns key maps at import
     tf = types.ModuleType("tifffile")
     tf.imread, tf.imwrite = _tif_imread, _tif_imwrite
     sys.modules.setdefault("tifffile", tf)
@@ -80,9 +82,13 @@ def install_stubs():
     for n in ("remove_small_objects", "disk", "binary_closing", "binary_dilation", "binary_erosion"):
         setattr(sk_morph, n, getattr(shims, n))
     sk_meas = types.ModuleType("skimage.measure")
-    for n in ("label", "regionprops", "find_contours"):
+    for n in ("label", "regionprops", "find_contours", "approximate_polygon"):
         setattr(sk_meas, n, getattr(shims, n))
     sk.draw, sk.morphology, sk.measure = sk_draw, sk_morph, sk_meas
+    for extra in ("transform", "exposure", "filters"):            # display-only imports of the ROI drawer
+        mod = _Anything(f"skimage.{extra}")
+        setattr(sk, extra, mod)
+        sys.modules.setdefault(f"skimage.{extra}", mod)
     sys.modules.setdefault("skimage", sk)
     sys.modules.setdefault("skimage.draw", sk_draw)
     sys.modules.setdefault("skimage.morphology", sk_morph)
@@ -98,6 +104,7 @@ _FILES = {
     "Nesprin2_FRET_Builder": "FRET/Nesprin2_FRET_Builder.py",
     "MOR_by_ROI": "MOR_by_ROI.py",
     "roi_channel_cropper": "roi_channel_cropper.py",
+    "roi_manual_drawer": "roi_manual_drawer.py",
 }
 
 

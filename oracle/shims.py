@@ -273,3 +273,69 @@ def find_contours(image, level=0.5, fully_connected="low", positive_orientation=
     if positive_orientation == "high":
         contours = [c[::-1] for c in contours]
     return contours
+
+
+def threshold_otsu(image):
+    """skimage.filters.threshold_otsu(image) for an integer image (scikit-image unpinned and absent;
+    restated from skimage/filters/thresholding.py + exposure.histogram): integer images get one
+    bin per value from image.min() to image.max() (np.bincount), then
+        weight1 = cumsum(counts); weight2 = cumsum(counts[::-1])[::-1]
+        mean1 = cumsum(counts * centers) / weight1; mean2 = (cumsum((counts * centers)[::-1]) / weight2[::-1])[::-1]
+        variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+        threshold = centers[argmax(variance12)]
+    A single-valued image returns that value.  The reference does NOT call this (optional stage)."""
+    a = np.asarray(image)
+    if a.min() == a.max():
+        return a.flat[0]
+    off = int(a.min())
+    counts = np.bincount((a.ravel().astype(np.int64) - off)).astype(np.float64)
+    centers = np.arange(off, off + counts.shape[0], dtype=np.float64)
+    weight1 = np.cumsum(counts)
+    weight2 = np.cumsum(counts[::-1])[::-1]
+    mean1 = np.cumsum(counts * centers) / weight1
+    mean2 = (np.cumsum((counts * centers)[::-1]) / weight2[::-1])[::-1]
+    variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+    return centers[int(np.argmax(variance12))]
+
+
+def approximate_polygon(coords, tolerance):
+    """skimage.measure.approximate_polygon (skimage/measure/_polygon.py, Douglas-Peucker with an
+    explicit stack); roi_manual_drawer.py:407.  Restated from the published source."""
+    if tolerance <= 0:
+        return coords
+    chain = np.zeros(coords.shape[0], 'bool')
+    dists = np.zeros(coords.shape[0])
+    chain[0] = True
+    chain[-1] = True
+    pos_stack = [(0, chain.shape[0] - 1)]
+    end_of_chain = False
+    while not end_of_chain:
+        start, end = pos_stack.pop()
+        r0, c0 = coords[start, :]
+        r1, c1 = coords[end, :]
+        dr = r1 - r0
+        dc = c1 - c0
+        segment_angle = -np.arctan2(dr, dc)
+        segment_dist = c0 * np.sin(segment_angle) + r0 * np.cos(segment_angle)
+        segment_coords = coords[start + 1:end, :]
+        segment_dists = dists[start + 1:end]
+        dr0 = segment_coords[:, 0] - r0
+        dc0 = segment_coords[:, 1] - c0
+        dr1 = segment_coords[:, 0] - r1
+        dc1 = segment_coords[:, 1] - c1
+        projected_lengths0 = dr0 * dr + dc0 * dc
+        projected_lengths1 = -dr1 * dr - dc1 * dc
+        perp = np.logical_and(projected_lengths0 > 0, projected_lengths1 > 0)
+        eucl = np.logical_not(perp)
+        segment_dists[perp] = np.abs(segment_coords[perp, 0] * np.cos(segment_angle)
+                                     + segment_coords[perp, 1] * np.sin(segment_angle) - segment_dist)
+        segment_dists[eucl] = np.minimum(np.sqrt(dc0[eucl] ** 2 + dr0[eucl] ** 2),
+                                         np.sqrt(dc1[eucl] ** 2 + dr1[eucl] ** 2))
+        if np.any(segment_dists > tolerance):
+            new_end = start + np.argmax(segment_dists) + 1
+            pos_stack.append((new_end, end))
+            pos_stack.append((start, new_end))
+            chain[new_end] = True
+        if len(pos_stack) == 0:
+            end_of_chain = True
+    return coords[chain, :]

@@ -984,3 +984,132 @@ def check_edge_cases(eng):
 
 
 RASTER_CHECKS.append(check_edge_cases)
+
+
+def check_gaussian_filters(eng):
+    """Gaussian / band-pass / unsharp of the ROI drawer's display pipeline (roi_manual_drawer.py:870-876)
+    against scipy.ndimage on float32 images: bit for bit, TMA-tiled shapes (W % 4 == 0), odd shapes
+    (plain loads), a radius larger than a tile, a radius larger than the image (repeated reflection)."""
+    from scipy import ndimage as ndi
+    from imageprocess_b200 import filters
+    rng = np.random.default_rng(8)
+    for (H, W), sigmas in (((96, 256), (1.2, 9.0)), ((75, 203), (2.0, 0.4)), ((40, 520), (33.0,)), ((9, 12), (3.0,))):
+        img = (rng.poisson(400, (H, W)) + 50 * np.sin(np.arange(W) / 7.0)[None, :]).astype(np.float32)
+        d = eng.mem.from_host(img)
+        for sg in sigmas:
+            got = filters.gaussian_filter(eng, d, sg).host()
+            want = ndi.gaussian_filter(img, sg)
+            assert got.dtype == want.dtype == np.float32 and np.array_equal(got, want), (H, W, sg, np.abs(got - want).max())
+    img = rng.poisson(900, (2, 64, 128)).astype(np.float32)
+    d = eng.mem.from_host(img)
+    got = filters.render_pipeline(eng, d, use_bandpass=True, use_unsharp=True).host()
+    for k in range(2):
+        im = ndi.gaussian_filter(img[k], 1.2) - ndi.gaussian_filter(img[k], 9.0)
+        im = im + 0.7 * (im - ndi.gaussian_filter(im, 2.0))
+        assert np.array_equal(got[k], im), np.abs(got[k] - im).max()
+
+
+RASTER_CHECKS.append(check_gaussian_filters)
+
+
+def check_tophat_and_otsu(eng):
+    """Optional (default OFF) pre-filter stages north_star names and the reference lacks: white
+    top-hat against scipy.ndimage.white_tophat (bit for bit, uint16; TMA-tiled and odd shapes) and
+    Otsu's threshold against the restated skimage rule."""
+    from scipy import ndimage as ndi
+    from imageprocess_b200 import filters
+    rng = np.random.default_rng(9)
+    for (H, W), sizes in (((96, 256), (3, 15)), ((70, 203), (5,)), ((24, 520), (9, 129))):
+        img = rng.poisson(500, (2, H, W)).astype(np.uint16)
+        img[:, 10:14, 20:26] += 3000
+        d = eng.mem.from_host(img)
+        for size in sizes:
+            er = filters.grey_morph(eng, d, size, False).host()
+            assert np.array_equal(er[0], ndi.grey_erosion(img[0], size=(size, size))), (H, W, size)
+            di = filters.grey_morph(eng, d, size, True).host()
+            assert np.array_equal(di[1], ndi.grey_dilation(img[1], size=(size, size))), (H, W, size)
+            th = filters.white_tophat(eng, d, size).host()
+            for k in range(2):
+                want = ndi.white_tophat(img[k], size=(size, size))
+                assert th.dtype == want.dtype == np.uint16 and np.array_equal(th[k], want), (H, W, size, k)
+    d0, a0, _ = small_scene(3, H=96, W=128, n_cells=2, blobs=6)
+    flat = np.full((96, 128), 777, np.uint16)
+    planes = np.stack([d0, a0, flat])
+    got = filters.threshold_otsu(eng, eng.mem.from_host(planes), 96, 128, [0, 1, 2])
+    assert got == [int(shims.threshold_otsu(p)) for p in planes], got
+    assert d0.min() < got[0] < d0.max()
+
+
+RASTER_CHECKS.append(check_tophat_and_otsu)
+
+
+def check_fa_optional_stages(eng):
+    """The FA chain behind the optional (default OFF) stages: white top-hat pre-filter + Otsu threshold.
+    Oracle: scipy.ndimage.white_tophat, the restated skimage Otsu rule, then the reference's own
+    analyze_fa_crop control flow with that threshold (its mean / std are chosen to reproduce it)."""
+    from scipy import ndimage as ndi
+    d, a, polys = small_scene(23, H=120, W=168, n_cells=2, blobs=10)
+    planes = np.stack([d, a])[None]
+    px = 0.112
+    params = {"alpha": 2.0, "min_area_um": 12.5 * px ** 2, "max_area_um": 300.0 * px ** 2, "close_radius": 1, "subtract_bg": True}
+    cfg = pipeline.fa_um_to_px_config(params, px)
+    out = pipeline.fa_batch(eng, eng.mem.from_host(planes), planes.shape, [polys], params, px, channel=0, save_ok_only=False,
+                            want_labels=True, prefilter=("tophat", 15), threshold="otsu")
+    filt = ndi.white_tophat(d, size=(15, 15))
+    thr = float(shims.threshold_otsu(filt))
+    assert float(out["stats"][0][3]) == thr, (out["stats"][0], thr)
+    img = filt.astype(np.float32)
+    stats = (np.float32(thr), np.float32(0.0), port.fa_global_stats(img)[2])       # m + alpha * 0 = Otsu's threshold
+    n_fa = 0
+    for i, P in enumerate(polys):
+        crop, mask, rect = port.fa_crop_and_mask(img, P.copy())
+        _, _, bw, lab = port.analyze_fa_crop(crop, mask, cfg, stats, with_contours=False)
+        assert np.array_equal(out["result"].bw_host(i), bw) and np.array_equal(out["result"].labels_host(i), lab), i
+        n_fa += int(lab.max())
+    assert n_fa > 0
+    g = pipeline.fa_batch(eng, eng.mem.from_host(planes), planes.shape, [polys], params, px, channel=0, save_ok_only=False,
+                          want_labels=True, prefilter=("gaussian", 1.5))
+    gf = np.clip(np.rint(ndi.gaussian_filter(d.astype(np.float32), 1.5)), 0, 65535).astype(np.uint16)
+    gstats = port.fa_global_stats(gf.astype(np.float32))
+    assert g["stats"][0][2] == gstats[2] and close(float(g["stats"][0][0]), float(gstats[0]), 1e-6)
+
+
+RASTER_CHECKS.append(check_fa_optional_stages)
+
+
+def check_segment_inside_polygon(eng):
+    """ROI drawer assist (roi_manual_drawer.py:337-418): threshold inside a hand-drawn polygon, largest
+    4-connected component, hole fill, outline, Douglas-Peucker -- threshold and polygon equal the
+    oracle's, in both threshold modes; a polygon off the image and an all-equal slice."""
+    from imageprocess_b200.host import roi_manual_drawer as rmd
+    rng = np.random.default_rng(31)
+    H, W = 160, 200
+    img = rng.poisson(300, (H, W)).astype(np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    cell = ((xx - 95) / 50.0) ** 2 + ((yy - 80) / 35.0) ** 2 <= 1.0
+    img[cell] += rng.poisson(1500, int(cell.sum())).astype(np.float32)
+    img[70:78, 88:99] = 310.0                                          # a dark hole inside the bright cell
+    img[20:26, 150:160] += 2500.0                                      # a second, smaller bright object
+    poly = np.array([[30.0, 25.5], [170.5, 18.0], [185.0, 120.0], [100.0, 150.5], [25.5, 110.0]])
+    for mode, par in (("percentile", 60.0), ("percentile", 90.0), ("bnd", 0.5)):
+        wthr, _, wpoly = port.segment_inside_polygon(img, poly, thr_param=par, min_area=40, tolerance=1.0, mode=mode)
+        gthr, gmask, gpoly = rmd.segment_inside_polygon(img, poly, thr_param=par, min_area=40, tolerance=1.0, mode=mode, eng=eng)
+        assert gmask is None and close(gthr, wthr, 1e-6), (mode, gthr, wthr)
+        assert (gpoly is None) == (wpoly is None)
+        if wpoly is not None:
+            assert gpoly.shape == wpoly.shape and np.array_equal(gpoly, wpoly), (mode, par, gpoly[:3], wpoly[:3])
+            assert wpoly.shape[0] >= 4
+    assert rmd.segment_inside_polygon(img, poly + [500, 0], eng=eng) == (None, None, None)
+    flat = np.full((H, W), 7.0, np.float32)
+    g = rmd.segment_inside_polygon(flat, poly, thr_param=90.0, eng=eng)
+    w = port.segment_inside_polygon(flat, poly, thr_param=90.0)
+    assert g[0] == w[0] and np.array_equal(g[2], w[2])
+    # the drawer's display filters with its default settings
+    got = rmd.render_pipeline(img, use_bandpass=True, use_unsharp=True, eng=eng)
+    from scipy import ndimage as ndi
+    im = ndi.gaussian_filter(img, 1.2) - ndi.gaussian_filter(img, 9.0)
+    im = im + 0.7 * (im - ndi.gaussian_filter(im, 2.0))
+    assert np.array_equal(got, im)
+
+
+RASTER_CHECKS.append(check_segment_inside_polygon)

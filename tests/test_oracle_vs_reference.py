@@ -175,3 +175,23 @@ def test_label_numbering_is_raster_order():
         assert firsts == sorted(firsts)
         # 8-connectivity: diagonal neighbours share a label
         assert (lab[:-1, :-1][bw[:-1, :-1] & bw[1:, 1:]] == lab[1:, 1:][bw[:-1, :-1] & bw[1:, 1:]]).all()
+
+
+@needs_ref
+def test_segment_inside_polygon_matches_reference():
+    """oracle/port.segment_inside_polygon against the unmodified roi_manual_drawer.segment_inside_polygon
+    (run on the restated matplotlib / skimage shims)."""
+    ref = refimport.load("roi_manual_drawer")
+    rng = np.random.default_rng(31)
+    H, W = 120, 150
+    img = rng.poisson(300, (H, W)).astype(np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    cell = ((xx - 70) / 40.0) ** 2 + ((yy - 60) / 28.0) ** 2 <= 1.0
+    img[cell] += rng.poisson(1500, int(cell.sum())).astype(np.float32)
+    img[55:60, 66:74] = 300.0
+    poly = np.array([[20.0, 15.5], [130.5, 12.0], [140.0, 95.0], [75.0, 112.5], [15.5, 85.0]])
+    for mode, par in (("percentile", 70.0), ("bnd", 0.5)):
+        w = ref.segment_inside_polygon(img, poly, thr_param=par, min_area=40, tolerance=1.0, mode=mode)
+        g = port.segment_inside_polygon(img, poly, thr_param=par, min_area=40, tolerance=1.0, mode=mode)
+        assert g[0] == w[0] and g[1] is None and w[1] is None
+        assert np.array_equal(g[2], w[2]) and g[2].shape[0] >= 6
