@@ -402,13 +402,16 @@ def run_ours(args):
             achieved = alg_bytes / (per_step_ms / 1e3) / 1e9
             traffic = None
             try:                   # dram bytes per step from the committed ncu --set full capture
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(name)
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(name)
             except Exception:
                 pass
             line["roofline"] = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak,
                                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                                "launch_ms": per_step_ms, "calls_per_step": ncalls / max(1, args.steps)}
+                                "launch_ms": per_step_ms, "calls_per_step": ncalls / max(1, args.steps),
+                                # the same work in the domain's unit: ROI pixels measured per second (three value
+                                # sources per pixel: donor, acceptor, ratio)
+                                "roi_px_per_s": (job.n_roi_px or 0) / (per_step_ms / 1e3)}
         line["pipeline_roofline"] = {"bytes_per_px": BYTES_PER_PX,
                                      "achieved_gbs": value / world * 1e6 * BYTES_PER_PX / 1e9,
                                      "frac_of_peak": value / world * 1e6 * BYTES_PER_PX / 1e9 / peak}

@@ -7,15 +7,23 @@ only for device memory, streams and torch.distributed.  There is no CPU fallback
 """
 __version__ = "0.1.0"
 
-_engine = None
+_engine = None          # the engine handed out for device=None (tests install an emulated one here)
+_engines = {}           # device string -> Engine
 
 
 def engine(device=None):
-    """Process-wide Engine bound to libipb200.so and torch CUDA memory."""
+    """Engine bound to libipb200.so and torch CUDA memory: one per device per process
+    (device=None: the first one created, else the current CUDA device's)."""
     global _engine
-    if _engine is None:
-        from . import _lib, device as _device, ops
+    if device is None and _engine is not None:
+        return _engine
+    from . import _lib, device as _device, ops
+    mem = _device.TorchMem(device)
+    key = str(mem.device)
+    if key not in _engines:
         lib = _lib.load()
         ops.check_struct_sizes(lib)
-        _engine = ops.Engine(lib, _device.TorchMem(device))
-    return _engine
+        _engines[key] = ops.Engine(lib, mem)
+    if _engine is None:
+        _engine = _engines[key]
+    return _engines[key]

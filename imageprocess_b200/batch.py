@@ -113,6 +113,8 @@ class FrameBatchJob:
         self._graphs = {}           # (plan, input buffer, output slot, full_hist, ...) -> (CUDA graph, ticket template) | (None, times seen)
         self.use_graphs = bool(int(os.environ.get("IPB_GRAPHS", "1")))
         self.window_misses = 0
+        self._miss_streak = 0        # consecutive steps whose sampled windows missed: two in a row make the
+        self._sticky_full = False    # full histograms sticky (bright or constant planes miss every time)
         self._slot = 0
         self.dist = None            # torch.distributed module when the job is one rank of N (see parallel.py)
         self.gather_dst = 0
@@ -533,6 +535,7 @@ class FrameBatchJob:
         collect() once per `gather_every` steps."""
         mem = self.mem
         pl = self._plan_for(polys_per_frame)
+        full_hist = bool(full_hist) or self._sticky_full
         slot = self._slot
         self._slot = (self._slot + 1) % self.n_slots
         # everything the enqueued work depends on besides the (fixed) job parameters
@@ -940,7 +943,12 @@ class FrameBatchJob:
             # rank-local (it re-stages the SAME entry of the gather ring and issues no collective),
             # so ranks that miss and ranks that do not keep the same sequence of collectives
             self.window_misses += 1
+            self._miss_streak += 1
+            if self._miss_streak >= 2:                     # data that misses deterministically: stop sampling
+                self._sticky_full = True
             return self.collect(self.submit(tk.planes, tk.polys, full_hist=True, _pos=tk.g_pos))
+        if not tk.full_hist:
+            self._miss_streak = 0
         self._entry_done(tk)
         params = OV("params")[:NP].copy()
         res.d2h_bytes = O.size

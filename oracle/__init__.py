@@ -26,6 +26,13 @@ Parity pinning (see DESIGN.md "Oracle"):
     Nesprin2, MOR, cropper: NO reference artefact with inputs exists ("parity
     unpinned by a shipped golden"); they are pinned only through the reference's own
     control flow run on the shims here.
+  * shims.find_contours / approximate_polygon (skimage.measure) and port.segment_inside_polygon
+    (ROI drawer assist): restated from the published scikit-image sources; the port equals the
+    UNMODIFIED roi_manual_drawer.segment_inside_polygon run on these shims, but no reference
+    artefact pins the shims themselves: PARITY UNPINNED.
+  * shims.threshold_otsu and the optional Gaussian / top-hat stages: not in the reference at
+    all; their oracle is scipy.ndimage / the restated skimage rule: PARITY
+    UNPINNED BY REFERENCE.
 """
 import ctypes
 import os

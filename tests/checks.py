@@ -1113,3 +1113,25 @@ def check_segment_inside_polygon(eng):
 
 
 RASTER_CHECKS.append(check_segment_inside_polygon)
+
+
+def check_sticky_full_histograms(eng):
+    """Planes whose percentiles lie above the 15-bit sample histogram miss their sampled window every
+    time: after two misses in a row the job stops sampling (the rerun was paid on
+    every step); the values stay exact throughout."""
+    from imageprocess_b200 import batch
+    rng = np.random.default_rng(4)
+    planes = (rng.poisson(300, (1, 2, 256, 1024)) + 40000).astype(np.uint16)
+    task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4, "percentile": 1.0,
+            "per_channel_p": False, "ch_p_map": {}}
+    job = batch.FrameBatchJob(eng, planes.shape, stages=("int",), int_task=task, hist_select=True)
+    job.pq_min_px = 0
+    dev = eng.mem.from_host(planes)
+    want = [port.int_bg_value(planes[0, ci].astype(np.float32), "percentile", 1.0, None, 4) for ci in range(2)]
+    for step in range(5):
+        res = job.run(dev, [[]])
+        assert [float(res.int_bg[0, ci]) for ci in range(2)] == want, step
+    assert job.window_misses == 2 and job._sticky_full, job.window_misses
+
+
+RASTER_CHECKS.append(check_sticky_full_histograms)

@@ -330,5 +330,54 @@ def check_mor_and_cropper_mirrors(eng, tmp):
         assert np.array_equal(traw, wv["raw_out"])
 
 
+def check_stream_batches(eng, tmp):
+    """Folder streaming (host/stream.py) over several batches: 5 (stage, time) keys with 2 frames per
+    batch (three batches, the last one padded), one unreadable TIFF in the middle: every readable key
+    gets exactly the oracle's rows, in task order; the broken key becomes a log line only."""
+    frames = [small_scene(s, H=96, W=128, n_cells=2) for s in (61, 62, 63, 64, 65)]
+    img_dir = os.path.join(tmp, "stream")
+    roi_dir = os.path.join(img_dir, "roi")
+    os.makedirs(roi_dir)
+    for k, (d, a, polys) in enumerate(frames):
+        common.write_tiff(os.path.join(img_dir, f"S01_t{k:02d}_1.tif"), d)
+        common.write_tiff(os.path.join(img_dir, f"S01_t{k:02d}_2.tif"), a)
+        _write_rois(os.path.join(roi_dir, f"S01_t{k:02d}.json"), polys, d.shape)
+    with open(os.path.join(img_dir, "S01_t02_2.tif"), "r+b") as f:          # same header (shape), pixel data cut off
+        f.truncate(4000)
+    cfg = {"timelapse": True, "channels_to_quant": [1, 2], "bg_stride": 4, "percentile": 1.0}
+    tasks, _ = Fluor_INT.build_tasks(img_dir, roi_dir, os.path.join(img_dir, "RES"), cfg)
+    timing = {}
+    res = Fluor_INT.process_key_tasks(tasks, eng=eng, frames_per_batch=2, decode_threads=3, timing=timing)
+    assert len(res) == 5 and timing["batches"] == 3 and timing["frames"] == 5
+    task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4, "percentile": 1.0,
+            "per_channel_p": False, "ch_p_map": {}}
+    for k, (d, a, polys) in enumerate(frames):
+        if k == 2:
+            assert res[k]["rows"] == [] and res[k]["logs"][0].startswith("[ERROR][WORKER] S01_t02")
+            continue
+        want, wbg, _ = port.int_process_key({1: d.astype(np.float32), 2: a.astype(np.float32)}, polys, None, task)
+        got = res[k]["rows"]
+        assert len(got) == len(want) and all(r["time"] == f"t{k:02d}" for r in got)
+        for g, w in zip(got, want):
+            assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"] and g["ch1_bg"] == wbg[1]["bg"]
+            for key in ("ch1_median", "ch1_p5", "ch2_p95", "ch2_vmax", "ch2_npx"):
+                assert g[key] == w[key], (k, key)
+            assert close(g["ch2_mean"], w["ch2_mean"]) and close(g["ch1_std"], w["ch1_std"])
+    # the FRET entry point over the same folder (out_tif off: tickets lag two batches)
+    rows = fret_ratio_builder.run_headless(img_dir, roi_dir, p={"timelapse": True, "out_tif": False}, eng=eng,
+                                           log=lambda s: None, frames_per_batch=2)
+    pp = {**fret_ratio_builder.DEFAULT_P, "timelapse": True}
+    k0 = 0
+    for k, (d, a, polys) in enumerate(frames):
+        if k == 2:
+            continue
+        want = port.fret_process_pair(d.astype(np.float32), a.astype(np.float32), polys, pp)
+        for g, w in zip(rows[k0: k0 + len(want["rows"])], want["rows"]):
+            assert g["time"] == f"t{k:02d}" and g["roi"] == w["roi"] and g["ratio_median"] == w["ratio_median"]
+            assert close(g["ratio_mean"], w["ratio_mean"])
+        k0 += len(want["rows"])
+    assert k0 == len(rows)
+
+
 HOST_CHECKS = [check_tiff_roundtrip, check_fluor_int_golden, check_fluor_int_tifs_and_masks, check_fa_mirror,
-               check_fret_mirror, check_nesprin2_mirror, check_mor_and_cropper_mirrors]
+               check_fret_mirror, check_nesprin2_mirror, check_mor_and_cropper_mirrors, check_stream_batches]
