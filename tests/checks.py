@@ -479,6 +479,10 @@ def check_hist_select_distributions(eng):
                 want = port.int_bg_value(planes[0, ci].astype(np.float32), "percentile", p, None, stride)
                 assert float(res.int_bg[0, ci]) == want, (k, p, stride, ci, float(res.int_bg[0, ci]), want)
             misses += job.window_misses
+    # 15 jobs on awkward planes; the deterministic misses are the constant plane (the 16-bit sample
+    # counter wraps), the saturated and the bright plane (above the 15-bit sample histogram) and p = 100
+    print(f"hist_select on awkward distributions: {misses} of 15 jobs repeated with full histograms")
+    assert 1 <= misses <= 15, misses
     return misses
 
 
@@ -1135,3 +1139,38 @@ def check_sticky_full_histograms(eng):
 
 
 RASTER_CHECKS.append(check_sticky_full_histograms)
+
+
+def check_fa_threshold_straddles(eng, n_seeds=24, H=192, W=256):
+    """'keep a test that counts threshold mismatches over many seeds'.  The FA threshold
+    m + alpha * s comes from exact integer moments rounded to float32; numpy's pairwise float32
+    mean / std may differ in the last bit.  Over `n_seeds` frames: background percentile exact on every
+    frame, mean / std within 1e-6, and the number of frames whose float32 threshold differs from
+    numpy's -- and of those, the frames where an INTEGER lies between the two thresholds (the only case
+    in which a mask pixel can flip) -- is counted, printed and bounded."""
+    from imageprocess_b200 import batch
+    params = {"alpha": 2.0, "min_area_um": 12.5 * 0.112 ** 2, "max_area_um": 300.0 * 0.112 ** 2, "close_radius": 1, "subtract_bg": True}
+    frames = [small_scene(1000 + s, H=H, W=W, n_cells=3, blobs=8) for s in range(n_seeds)]
+    planes = np.stack([np.stack([d, a]) for d, a, _ in frames])
+    job = batch.FrameBatchJob(eng, planes.shape, stages=("fa",), fa_params=params, fa_px=0.112)
+    res = job.run(eng.mem.from_host(planes), [fr[2] for fr in frames])
+    differ = straddle = 0
+    for f, (d, _, _) in enumerate(frames):
+        ref = port.fa_global_stats(d.astype(np.float32))
+        got = res.fa_stats[f]
+        assert got[2] == ref[2], f
+        assert close(float(got[0]), float(ref[0]), 1e-6) and close(float(got[1]), float(ref[1]), 1e-6), f
+        thr_ref = ref[0] + params["alpha"] * ref[1]
+        if np.float32(got[3]) != thr_ref:
+            differ += 1
+            lo, hi = sorted((float(got[3]), float(thr_ref)))
+            assert hi - lo <= 4 * np.spacing(np.float32(hi)), (f, lo, hi)          # a few ulps at most
+            if math.floor(hi) > math.floor(lo) or lo == math.floor(lo):
+                straddle += 1
+    print(f"FA thresholds over {n_seeds} seeds: {differ} differ from numpy's float32 value in the last bits, "
+          f"{straddle} straddle an integer (window misses of the job: {job.window_misses})")
+    assert straddle <= max(1, n_seeds // 8), (differ, straddle)
+    return differ, straddle
+
+
+RASTER_CHECKS.append(check_fa_threshold_straddles)
