@@ -296,7 +296,24 @@ def run_ours(args):
         barrier()
         return ms, d2h
 
-    host = {"submit_s": 0.0, "n": 0}
+    host = {"submit_s": 0.0, "collect_s": 0.0, "gathered_s": 0.0, "n": 0}
+
+    def collect_one(pend):
+        t0 = time.perf_counter()
+        tk = pend.pop(0)
+        tk.event.synchronize()
+        host.setdefault("waits", []).append(round(1e3 * (time.perf_counter() - t0), 3))
+        d = consume(job.collect(tk))
+        t1 = time.perf_counter()
+        consume_gathered(job.gathered())
+        host["collect_s"] += t1 - t0
+        host["gathered_s"] += time.perf_counter() - t1
+        return d
+
+    def finish_gathers():
+        t0 = time.perf_counter()
+        consume_gathered(job.finish())                      # the partial last group; waits for every gather
+        host["gathered_s"] += time.perf_counter() - t0
 
     def loop_resident(steps):
         """Steps over HBM-resident frames; up to LAG steps are in flight before a step's tables are
@@ -308,11 +325,10 @@ def run_ours(args):
             host["submit_s"] += time.perf_counter() - t0
             host["n"] += 1
             if len(pend) > LAG:
-                d2h = consume(job.collect(pend.pop(0)))
-                consume_gathered(job.gathered())
+                d2h = collect_one(pend)
         while pend:
-            d2h = consume(job.collect(pend.pop(0)))
-        consume_gathered(job.finish())                      # the partial last group; waits for every gather
+            d2h = collect_one(pend)
+        finish_gathers()
         return d2h
 
     # end-to-end: host frames in pinned memory, H2D of step k+1 on a copy stream while step k computes
@@ -342,11 +358,10 @@ def run_ours(args):
             done[b] = torch.cuda.Event()
             done[b].record(main)
             if len(pend) > LAG:
-                d2h = consume(job.collect(pend.pop(0)))
-                consume_gathered(job.gathered())
+                d2h = collect_one(pend)
         while pend:
-            d2h = consume(job.collect(pend.pop(0)))
-        consume_gathered(job.finish())
+            d2h = collect_one(pend)
+        finish_gathers()
         return d2h
 
     eng.mem.copy_bytes(planes_b[1], 0, planes, 0, planes.nbytes)
@@ -356,9 +371,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches0 = eng.launches
     with ClockSampler(local if rank == 0 else None) as clk:      # one sampler per job, on rank 0's GPU
-        host["submit_s"], host["n"] = 0.0, 0
+        for k in host:
+            host[k] = [] if k == "waits" else 0
         ms, d2h = timed(loop_resident, args.steps)
         host_submit_ms = 1e3 * host["submit_s"] / max(1, host["n"])
+        host_ms = {k[:-2]: round(1e3 * host[k] / max(1, host["n"]), 4) for k in ("submit_s", "collect_s", "gathered_s")}
+        if os.environ.get("IPB_BENCH_TRACE"):
+            host_ms["waits"] = list(host.get("waits", []))
         launches = eng.launches - launches0
         # per-kernel CUDA-event times: the same steps once more with the branches of a step
         # serialised on one stream (overlapped kernels cannot be timed one by one)
@@ -418,6 +437,7 @@ def run_ours(args):
         line["kernels"] = kern
         line["ms_per_step_serialized"] = ms_ser / args.steps
         line["host_submit_ms_per_step"] = host_submit_ms
+        line["host_ms_per_step"] = host_ms          # rank 0: submit / collect (waits for the step) / gathered tables of all ranks
         line["window_misses"] = int(job.window_misses)       # steps repeated with full histograms (exact either way)
         line["adhesions_per_frame"] = seen["adhesions"] / max(1, seen["steps"] * F)
         line["roi_fallbacks_per_step"] = seen["roi_fallbacks"] / max(1, seen["steps"])   # ROIs repeated by the full-histogram kernels

@@ -110,6 +110,7 @@ class FrameBatchJob:
         self._g_last = [None, None]      # per ring buffer: event of the last gather that read it
         self._g_total, self._g_count = None, 0
         self._priming = False
+        self._pc_hint = None         # adhesion rows fetched with the step's tables: 1.25x the largest step seen so far
         self._graphs = {}           # (plan, input buffer, output slot, full_hist, ...) -> (CUDA graph, ticket template) | (None, times seen)
         self.use_graphs = bool(int(os.environ.get("IPB_GRAPHS", "1")))
         self.window_misses = 0
@@ -540,7 +541,7 @@ class FrameBatchJob:
         self._slot = (self._slot + 1) % self.n_slots
         # everything the enqueued work depends on besides the (fixed) job parameters
         key = (pl.serial, int(planes.ptr), slot, bool(full_hist), bool(self.hist_select), bool(self.fused_roi), bool(self.fret_moments),
-               bool(self.overlap), int(self.fa_path), int(self.pq_min_px), self.dist is not None)
+               bool(self.overlap), int(self.fa_path), int(self.pq_min_px), self._staged(), self._pc_rows(pl))
         graphable = self.use_graphs and hasattr(mem, "graph") and self.eng.prof is None and not pl.host_bg and \
             self.fa_threshold is None
         ent = self._graphs.get(key) if graphable else None
@@ -573,6 +574,18 @@ class FrameBatchJob:
         tk.event = mem.event()
         tk.event.record()
         return tk
+
+    def _pc_rows(self, pl):
+        """Adhesion rows downloaded (and staged for the gather) with a step's tables; collect()
+        fetches the rest when a step has more.  Before the job has seen a step: 96 per ROI."""
+        return min(pl.comp_cap, self._pc_hint or max(4096, 96 * pl.NR))
+
+    def _staged(self):
+        """N > 1 ranks: does the step stage its tables for the gather?  Not on the very first setup
+        step of prime(): the capacity all ranks agree on is sized from that step's adhesion count."""
+        if self.dist is None or self.dist.get_world_size() == 1:
+            return False
+        return not (self._priming and self._pc_hint is None and "fa" in self.stages)
 
     def prime(self, planes, polys_per_frame):
         """Setup for a long run over `planes`' buffer: steps it until both output slots have their
@@ -770,13 +783,13 @@ class FrameBatchJob:
         tk.d_comps, tk.pc_np, tk.pc_rows = None, None, 0
         if fa_ran:
             tk.d_comps = d_comps
-            tk.pc_rows = min(pl.comp_cap, max(4096, 96 * NR))        # usual batches fit; collect() fetches the rest
+            tk.pc_rows = self._pc_rows(pl)                           # usual batches fit; collect() fetches the rest
             tk.pc_np, pc_t = self._pinned(f"pin_comps{slot}", COMP.itemsize * tk.pc_rows)
             mem.download_async(pc_t, d_comps, COMP.itemsize * tk.pc_rows)
         # N > 1 ranks: the step stages its packed tables (inside the step's graph); submit() copies
         # the stage into the gather ring and collect() issues ONE all-gather per `gather_every` steps
         tk.g_stage = None
-        if self.dist is not None and self.dist.get_world_size() > 1:
+        if self._staged():
             # every rank sends the same number of bytes: a capacity agreed once per job (max over
             # ranks of 1.25x the first step's need + 64 KiB).  Segment = 32-byte header {arena bytes,
             # adhesion rows sent}, the table arena, the first adhesion rows.  Rows that do not fit
@@ -785,7 +798,17 @@ class FrameBatchJob:
             comps_b = COMP.itemsize * tk.pc_rows if fa_ran else 0
             need = 32 + _al(O.size) + _al(comps_b)
             if self._gather_cap is None:
-                self._gather_cap = _al(mem.all_reduce_max(need + need // 4 + (1 << 16), self.dist))
+                # (the adhesion-row count in `need` already carries 25% head room once a step was seen)
+                self._gather_cap = _al(mem.all_reduce_max(need + (need // 4 if self._pc_hint is None else 0) + (1 << 16), self.dist))
+                # every buffer of the gather path now, not inside the run: pinning the destination
+                # rank's host buffers alone takes ~25 ms each (measured: it showed up as 1 ms per step
+                # of a 24-step run when the second ring's buffers were first used inside it)
+                K = self.gather_every
+                for b in (0, 1):
+                    self._dev(f"gather_ring{b}", self._gather_cap * K)
+                    self._dev(f"gather_all{b}", self._gather_cap * K * world)
+                    if self.dist.get_rank() == self.gather_dst:
+                        self._pinned(f"pin_gather{b}", self._gather_cap * K * world)
             cap = self._gather_cap
             if 32 + _al(O.size) > cap:
                 raise RuntimeError("table arena larger than the agreed gather capacity; pass gather_cap_bytes")
@@ -869,8 +892,9 @@ class FrameBatchJob:
         d_all = self._dev(f"gather_all{g & 1}", cap * K * world)
         rec = {"group": g, "n": n_valid, "np": None, "cap": cap, "world": world}
         with mem.side(4, events) as br:
-            mem.all_gather_bytes(d_all, ring, cap * K, self.dist)
-            if self.dist.get_rank() == self.gather_dst:
+            if not os.environ.get("IPB_DEBUG_NO_GATHER"):
+                mem.all_gather_bytes(d_all, ring, cap * K, self.dist)
+            if self.dist.get_rank() == self.gather_dst and not os.environ.get("IPB_DEBUG_NO_GATHER_D2H"):
                 g_np, g_t = self._pinned(f"pin_gather{g & 1}", cap * K * world)
                 mem.download_async(g_t, d_all, cap * K * world)
                 rec["np"] = g_np
@@ -879,11 +903,18 @@ class FrameBatchJob:
         self._g_issued.append(rec)
         self._g_count += 1
 
-    def gathered(self, block=False):
+    def gathered(self, block=False, copy=False):
         """Finished gathers since the last call, oldest first: on the destination rank a list of
         {"group", "per_rank": [rank][entry] -> (table arena, adhesion rows, comp_off)}; [] elsewhere
-        (the collectives are still waited for when block is set)."""
+        (the collectives are still waited for when block is set).
+
+        The arrays are VIEWS of the pinned buffer the gather was downloaded into (two buffers,
+        alternating by group): they stay valid until the gather of group + 2 is issued, i.e. for at
+        least `gather_every` further steps.  copy = True hands out private copies instead (measured:
+        copying 8 steps x N ranks of tables in one go stalls the destination rank's submit loop for
+        ~6 ms per rank and group, which is what made N ranks slower than one -- profiles/README.md)."""
         out = []
+        keep = (lambda a: a.copy()) if copy else (lambda a: a)
         while self._g_issued:
             rec = self._g_issued[0]
             if block:
@@ -895,22 +926,24 @@ class FrameBatchJob:
                 continue
             K, cap, world = self.gather_every, rec["cap"], rec["world"]
             blobs = rec["np"][: world * K * cap].reshape(world, K, cap)
+            hdr = blobs[:, :, :32].copy().view(np.int64).reshape(world, K, 4)
             per_rank = []
             for r in range(world):
                 ents = []
                 for i in range(K):
-                    arena_b, rows, co_off, co_n = (int(v) for v in blobs[r, i, :32].view(np.int64))
+                    arena_b, rows, co_off, co_n = (int(v) for v in hdr[r, i])
                     if arena_b <= 0:
                         continue
                     a0 = 32 + _al(arena_b)
-                    arena = blobs[r, i, 32: 32 + arena_b].copy()
-                    ents.append((arena, blobs[r, i, a0: a0 + COMP.itemsize * rows].view(COMP).copy(),
-                                 arena[co_off: co_off + 4 * co_n].view(np.int32)))
+                    arena = keep(blobs[r, i, 32: 32 + arena_b])
+                    comp_off = arena[co_off: co_off + 4 * co_n].view(np.int32)
+                    rows = min(rows, int(comp_off[-1]) if co_n else 0)      # rows staged vs rows the step produced
+                    ents.append((arena, keep(blobs[r, i, a0: a0 + COMP.itemsize * rows]).view(COMP), comp_off))
                 per_rank.append(ents)
             out.append({"group": rec["group"], "per_rank": per_rank})
         return out
 
-    def finish(self):
+    def finish(self, copy=False):
         """End of the job (or of a timed run): gathers the partial last group, issues the empty
         gathers a rank with fewer steps still owes (begin_distributed), waits for every gather
         and returns what gathered() has not handed out yet.  Every rank must call it."""
@@ -924,7 +957,7 @@ class FrameBatchJob:
             if self._g_last[g & 1] is not None:
                 self.mem.wait_event(self._g_last[g & 1])
             self._issue_gather(g, 0)
-        out = self.gathered(block=True)
+        out = self.gathered(block=True, copy=copy)
         # a later run starts on fresh groups
         self._g_pos = (self._g_pos + self.gather_every - 1) // self.gather_every * self.gather_every
         self._g_total, self._g_count = None, 0
@@ -978,6 +1011,10 @@ class FrameBatchJob:
             total = int(comp_off[-1]) if tk.fa_ran else 0
             if tk.fa_ran and total > pl.comp_cap:
                 raise RuntimeError("fa_segment: component table overflow")
+            if tk.fa_ran:
+                want = -(-(total + total // 4 + 1024) // 4096) * 4096
+                if self._pc_hint is None or want > self._pc_hint:     # grows only: a new size means new graphs
+                    self._pc_hint = want
             if total:
                 if total <= tk.pc_rows:
                     res.fa_comps = tk.pc_np[: COMP.itemsize * total].view(COMP).copy()

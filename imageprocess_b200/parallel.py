@@ -9,6 +9,44 @@ tables are KBs per frame, so the fabric is never the limit), gloo in the CPU tes
 import numpy as np
 
 
+def bind_near_gpu(device_index, apply=True):
+    """Pins the calling process to the CPU cores of the GPU's NUMA node (sysfs: the PCI device's
+    numa_node and the node's cpulist, intersected with the cores the process may use), so that the
+    pinned staging buffers it allocates afterwards are first-touched on that node and its H2D copies
+    do not cross the socket link.  On an 8-GPU box every rank's default placement is node 0, whose
+    DRAM then feeds all eight PCIe links (profiles/r2_h2d_matrix.json).  Returns what it found and
+    did; never raises (containers may hide sysfs or forbid the affinity call)."""
+    import os
+    info = {"device": int(device_index), "numa_node": None, "cpus": None, "bound": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(int(device_index))
+        if hasattr(pr, "pci_bus_id"):
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:                                                # older torch: ask the runtime
+            from cuda import cudart
+            _, raw = cudart.cudaDeviceGetPCIBusId(32, int(device_index))
+            bdf = raw.decode().rstrip("\x00").lower()
+            bdf = bdf[-12:] if len(bdf) > 12 else bdf          # sysfs uses a 4-digit domain
+        info["pci"] = bdf
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus |= set(range(int(a), int(b or a) + 1))
+        mine = cpus & set(os.sched_getaffinity(0))
+        info["cpus"] = len(mine)
+        if mine and apply:
+            os.sched_setaffinity(0, mine)
+            info["bound"] = True
+    except Exception as e:
+        info["error"] = f"{type(e).__name__}: {e}"[:160]
+    return info
+
+
 def shard_range(n_items, rank, world):
     """Contiguous block [lo, hi) of rank `rank`: sizes differ by at most one, order preserved."""
     base, extra = divmod(int(n_items), int(world))

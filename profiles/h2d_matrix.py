@@ -3,6 +3,8 @@
 end-to-end number scales 1.00 / 0.99 / 0.54 / 0.43 while the device-timed one scales 0.92: is it the
 host?).  Every rank pins a 1 GiB buffer (plain pinned and write-combined) and copies it to its GPU
 back to back for ~1.5 s, all ranks at the same time; rank 0 prints per-rank and aggregate GB/s.
+Third variant: the rank first moves to the cores of its GPU's NUMA node (parallel.bind_near_gpu),
+so the buffer is first-touched there.
 
     torchrun --nproc-per-node N --master-addr 127.0.0.1 profiles/h2d_matrix.py          (under gpurun --gpus 8)
 """
@@ -23,8 +25,15 @@ def main():
     n = 1 << 30
     dev = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local}")
     out = {}
-    for kind in ("pinned", "write_combined"):
-        if kind == "pinned":
+    numa = None
+    for kind in ("pinned", "write_combined", "pinned_near_gpu"):
+        if kind == "pinned_near_gpu":
+            # the process moves to the cores of its GPU's NUMA node, then allocates and first-touches
+            import sys
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+            from imageprocess_b200.parallel import bind_near_gpu
+            numa = bind_near_gpu(local)
+        if kind in ("pinned", "pinned_near_gpu"):
             host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
             host.fill_(1)
             copy = lambda: dev.copy_(host, non_blocking=True)
@@ -65,8 +74,13 @@ def main():
         else:
             vals = [gbs]
         out[kind] = {"per_rank_gbs": [round(v, 1) for v in vals], "aggregate_gbs": round(sum(vals), 1)}
+    if world > 1:
+        infos = [None] * world
+        dist.all_gather_object(infos, numa)
+    else:
+        infos = [numa]
     if rank == 0:
-        print(json.dumps({"n_gpus": world, "bytes_per_copy": n, "h2d": out, "cpu_count": os.cpu_count()}))
+        print(json.dumps({"n_gpus": world, "bytes_per_copy": n, "h2d": out, "cpu_count": os.cpu_count(), "numa": infos}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -116,13 +116,17 @@ def _job_worker_body(rank, world, port, q):
         return job
 
     job = make_job(rank, True)
+    p0, polys0 = planes_of(rank, 0)
+    job.n_slots = 1                                           # prime() runs 3 setup steps per slot: keep the emulated test short
+    job.prime(eng.mem.from_host(p0), polys0)                  # setup steps take no part in the gathers; the first one
+    assert job._pc_hint is not None and job._gather_cap is not None      # sizes the gather capacity (agreed on the second)
     job.begin_distributed(n_steps[rank])
     got = []
     for step in range(n_steps[rank]):
         planes, polys = planes_of(rank, step)
         job.run(eng.mem.from_host(planes), polys)
-        got += job.gathered()
-    got += job.finish()
+        got += job.gathered(copy=True)          # kept until the end of the test: private copies
+    got += job.finish(copy=True)
     misses = job.window_misses
     ok = True
     if rank == 0:
