@@ -291,8 +291,10 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            every = torch.zeros(world, device=f"cuda:{local}")
+            dist.all_gather_into_tensor(every, t)
+            timed.per_rank = [round(float(v) / steps, 4) for v in every.tolist()]      # ms per step of every rank
+            ms = float(every.max().item())                                              # the job's time: the slowest rank
         barrier()
         return ms, d2h
 
@@ -374,6 +376,7 @@ def run_ours(args):
         for k in host:
             host[k] = [] if k == "waits" else 0
         ms, d2h = timed(loop_resident, args.steps)
+        ms_ranks = getattr(timed, "per_rank", None)
         host_submit_ms = 1e3 * host["submit_s"] / max(1, host["n"])
         host_ms = {k[:-2]: round(1e3 * host[k] / max(1, host["n"]), 4) for k in ("submit_s", "collect_s", "gathered_s")}
         if os.environ.get("IPB_BENCH_TRACE"):
@@ -437,6 +440,8 @@ def run_ours(args):
         line["kernels"] = kern
         line["ms_per_step_serialized"] = ms_ser / args.steps
         line["host_submit_ms_per_step"] = host_submit_ms
+        if ms_ranks is not None:
+            line["ms_per_step_ranks"] = ms_ranks      # device-timed, per rank; the job's ms_per_step is their max
         line["host_ms_per_step"] = host_ms          # rank 0: submit / collect (waits for the step) / gathered tables of all ranks
         line["window_misses"] = int(job.window_misses)       # steps repeated with full histograms (exact either way)
         line["adhesions_per_frame"] = seen["adhesions"] / max(1, seen["steps"] * F)

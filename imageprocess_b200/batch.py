@@ -103,17 +103,24 @@ class FrameBatchJob:
         # N ranks: every step stages its packed tables in a device ring; ONE all-gather per
         # `gather_every` collected steps (see _issue_gather), never one per step
         self.n_slots = 3                 # output slots: a ticket may be collected two submits later
-        self.gather_every = int(os.environ.get("IPB_GATHER_EVERY", "8"))
+        self.gather_every = int(os.environ.get("IPB_GATHER_EVERY", "2"))
+        # buffers of the gather path (ring of staged steps, gathered blob, the destination's pinned copy):
+        # a rank may run gather_rings x gather_every steps ahead of the slowest one.  Small groups keep the
+        # tail short (the last group's tables reach the destination after the last step: all-gather + D2H
+        # of N x gather_every steps); the gathers run on their own stream, so their count costs nothing
+        self.gather_rings = int(os.environ.get("IPB_GATHER_RINGS", "4"))
         self._g_pos = 0                  # steps staged so far
         self._g_open = {}                # group -> [entries collected, their ring-copy events]
         self._g_issued = []              # issued gathers not yet handed out: dicts
-        self._g_last = [None, None]      # per ring buffer: event of the last gather that read it
+        self._g_last = {}                # ring buffer index -> event of the last gather that read it
         self._g_total, self._g_count = None, 0
         self._priming = False
+        self._slot_busy = {}         # output slot -> event of its last table download
         self._pc_hint = None         # adhesion rows fetched with the step's tables: 1.25x the largest step seen so far
         self._graphs = {}           # (plan, input buffer, output slot, full_hist, ...) -> (CUDA graph, ticket template) | (None, times seen)
         self.use_graphs = bool(int(os.environ.get("IPB_GRAPHS", "1")))
         self.window_misses = 0
+        self.comp_refetches = 0      # steps repeated because they had more adhesions than rows staged
         self._miss_streak = 0        # consecutive steps whose sampled windows missed: two in a row make the
         self._sticky_full = False    # full histograms sticky (bright or constant planes miss every time)
         self._slot = 0
@@ -545,6 +552,8 @@ class FrameBatchJob:
         graphable = self.use_graphs and hasattr(mem, "graph") and self.eng.prof is None and not pl.host_bg and \
             self.fa_threshold is None
         ent = self._graphs.get(key) if graphable else None
+        if self._slot_busy.get(slot) is not None:
+            mem.wait_event(self._slot_busy[slot])            # the slot's previous download has read its stage
         if ent is not None and ent[0] is not None:
             graph, tmpl = ent
             graph.replay()
@@ -571,13 +580,18 @@ class FrameBatchJob:
                 self._graphs[key] = (None, (ent[1] if ent else 0) + 1)
             tk = self._enqueue(planes, polys_per_frame, full_hist, pl, slot)
         self._stage_for_gather(tk, _pos)
-        tk.event = mem.event()
-        tk.event.record()
+        done = mem.event()
+        done.record()
+        with mem.side(5, [done]) as dl:                      # the download stream: behind this step only
+            mem.download_async(tk.pin_t, tk.d_stage, tk.stage_bytes)
+        tk.event = self._slot_busy[slot] = dl.event
         return tk
 
     def _pc_rows(self, pl):
         """Adhesion rows downloaded (and staged for the gather) with a step's tables; collect()
         fetches the rest when a step has more.  Before the job has seen a step: 96 per ROI."""
+        if not hasattr(pl, "comp_cap"):                      # no FA stage in this job
+            return 0
         return min(pl.comp_cap, self._pc_hint or max(4096, 96 * pl.NR))
 
     def _staged(self):
@@ -772,57 +786,54 @@ class FrameBatchJob:
         if "fa" in st:
             res.fa_rect, res.fa_crops = pl.fa_rect, pl.fa_crops
 
-        mem.nvtx_mark("ipb:results_d2h")
-        # ---- results: one packed D2H (+ a first slice of the adhesion table), then an event;
-        #      the host reads them in collect() while the device may already run the next step
-        pout_np, pout_t = self._pinned(f"pin_out{slot}", O.size)
-        mem.download_async(pout_t, d_out, O.size)
+        mem.nvtx_mark("ipb:results_stage")
+        # ---- results: the step packs its tables into this slot's stage (device-to-device, inside
+        #      the step's graph): 32-byte header | table arena | first adhesion rows.  submit() then
+        #      downloads the stage with ONE D2H on the download stream, off the critical path: the next
+        #      step's kernels do not queue behind this step's PCIe copy (nor, on the destination rank of
+        #      an N-rank job, behind the gathered tables of the other ranks on the same copy engine).
         tk = _Ticket()
-        tk.pl, tk.res, tk.pout_np, tk.fa_ran = pl, res, pout_np, fa_ran
+        tk.pl, tk.res, tk.fa_ran = pl, res, fa_ran
         tk.planes, tk.polys, tk.full_hist = planes, polys_per_frame, full_hist
-        tk.d_comps, tk.pc_np, tk.pc_rows = None, None, 0
-        if fa_ran:
-            tk.d_comps = d_comps
-            tk.pc_rows = self._pc_rows(pl)                           # usual batches fit; collect() fetches the rest
-            tk.pc_np, pc_t = self._pinned(f"pin_comps{slot}", COMP.itemsize * tk.pc_rows)
-            mem.download_async(pc_t, d_comps, COMP.itemsize * tk.pc_rows)
-        # N > 1 ranks: the step stages its packed tables (inside the step's graph); submit() copies
-        # the stage into the gather ring and collect() issues ONE all-gather per `gather_every` steps
-        tk.g_stage = None
-        if self._staged():
-            # every rank sends the same number of bytes: a capacity agreed once per job (max over
-            # ranks of 1.25x the first step's need + 64 KiB).  Segment = 32-byte header {arena bytes,
-            # adhesion rows sent}, the table arena, the first adhesion rows.  Rows that do not fit
-            # are not sent; the receiver sees that from comp_off and reports it.
+        tk.pc_rows = self._pc_rows(pl) if fa_ran else 0              # usual batches fit; collect() repeats the step when not
+        a_rows = 32 + _al(O.size)
+        tk.stage_bytes = a_rows + COMP.itemsize * tk.pc_rows
+        staged = self._staged()
+        if staged and self._gather_cap is None:
+            # N > 1 ranks: every rank sends the same number of bytes per step, a capacity agreed once
+            # per job (max over ranks of the stage size + 64 KiB; + 25% while no step was seen yet).
+            # Rows that do not fit are not sent; the receiver sees that from comp_off and reports it.
             world = self.dist.get_world_size()
-            comps_b = COMP.itemsize * tk.pc_rows if fa_ran else 0
-            need = 32 + _al(O.size) + _al(comps_b)
-            if self._gather_cap is None:
-                # (the adhesion-row count in `need` already carries 25% head room once a step was seen)
-                self._gather_cap = _al(mem.all_reduce_max(need + (need // 4 if self._pc_hint is None else 0) + (1 << 16), self.dist))
-                # every buffer of the gather path now, not inside the run: pinning the destination
-                # rank's host buffers alone takes ~25 ms each (measured: it showed up as 1 ms per step
-                # of a 24-step run when the second ring's buffers were first used inside it)
-                K = self.gather_every
-                for b in (0, 1):
-                    self._dev(f"gather_ring{b}", self._gather_cap * K)
-                    self._dev(f"gather_all{b}", self._gather_cap * K * world)
-                    if self.dist.get_rank() == self.gather_dst:
-                        self._pinned(f"pin_gather{b}", self._gather_cap * K * world)
-            cap = self._gather_cap
-            if 32 + _al(O.size) > cap:
-                raise RuntimeError("table arena larger than the agreed gather capacity; pass gather_cap_bytes")
-            rows_sent = min(tk.pc_rows if fa_ran else 0, (cap - 32 - _al(O.size)) // COMP.itemsize)
-            hdr_np, hdr_t = self._pinned(f"pin_ghdr{slot}", 32)
-            # ranks may carry different ROI sets, hence different arena layouts: the header names the
-            # section every receiver needs to read the adhesion table (comp_off: offset, entries)
-            hdr_np[:32].view(np.int64)[:] = (O.size, rows_sent, O.sections["comp_off"][0], NR + 1)
-            d_stage = self._dev(f"gather_stage{slot}", cap)
-            mem.upload_async(d_stage, hdr_t, 32)
-            mem.copy_bytes(d_stage, 32, d_out, 0, O.size)
-            if rows_sent:
-                mem.copy_bytes(d_stage, 32 + _al(O.size), d_comps, 0, COMP.itemsize * rows_sent)
-            tk.g_stage = (d_stage, cap, world)               # the collective itself is issued by _issue_gather()
+            need = tk.stage_bytes
+            self._gather_cap = _al(mem.all_reduce_max(need + (need // 4 if self._pc_hint is None else 0) + (1 << 16), self.dist))
+            # every buffer of the gather path now, not inside the run: pinning the destination
+            # rank's host buffers alone takes ~25 ms each (measured: it showed up as 1 ms per step
+            # of a 24-step run when the second ring's buffers were first used inside it)
+            K = self.gather_every
+            for b in range(self.gather_rings):
+                self._dev(f"gather_ring{b}", self._gather_cap * K)
+                self._dev(f"gather_all{b}", self._gather_cap * K * world)
+                if self.dist.get_rank() == self.gather_dst:
+                    self._pinned(f"pin_gather{b}", self._gather_cap * K * world)
+        cap = self._gather_cap if staged else 0
+        if staged and a_rows > cap:
+            raise RuntimeError("table arena larger than the agreed gather capacity; pass gather_cap_bytes")
+        rows_sent = min(tk.pc_rows, (cap - a_rows) // COMP.itemsize) if staged else tk.pc_rows
+        d_stage = self._dev(f"stage{slot}", max(tk.stage_bytes, cap))
+        # ranks may carry different ROI sets, hence different arena layouts: the header names the
+        # section every receiver needs to read the adhesion table (comp_off: offset, entries).  One
+        # pinned header per (slot, plan): a replayed graph reads it at replay time
+        hdr_np, hdr_t = self._pinned(f"pin_hdr{slot}_{pl.serial}", 32)
+        hdr_np[:32].view(np.int64)[:] = (O.size, rows_sent, O.sections["comp_off"][0], NR + 1)
+        mem.upload_async(d_stage, hdr_t, 32)
+        mem.copy_bytes(d_stage, 32, d_out, 0, O.size)
+        if tk.pc_rows:
+            mem.copy_bytes(d_stage, a_rows, d_comps, 0, COMP.itemsize * tk.pc_rows)
+        pin_np, pin_t = self._pinned(f"pin_stage{slot}", tk.stage_bytes)
+        tk.d_stage, tk.pin_t = d_stage, pin_t
+        tk.pout_np = pin_np[32: 32 + O.size]
+        tk.pc_np = pin_np[a_rows: a_rows + COMP.itemsize * tk.pc_rows]
+        tk.g_stage = (d_stage, cap, self.dist.get_world_size()) if staged else None   # the collective: _issue_gather()
         mem.nvtx_mark(None)
         return tk
 
@@ -848,12 +859,13 @@ class FrameBatchJob:
             pos = self._g_pos
             self._g_pos += 1
         g, i = divmod(pos, K)
-        if (g - 2) in self._g_open:
+        if (g - self.gather_rings) in self._g_open:
             raise RuntimeError("collect() earlier tickets first: the gather ring still holds their group")
-        ring = self._dev(f"gather_ring{g & 1}", cap * K)
-        if self._g_last[g & 1] is not None and g not in self._g_open:
-            mem.wait_event(self._g_last[g & 1])          # the gather of group g - 2 has read this ring
-            self._g_last[g & 1] = None
+        b = g % self.gather_rings
+        ring = self._dev(f"gather_ring{b}", cap * K)
+        if self._g_last.get(b) is not None and g not in self._g_open:
+            mem.wait_event(self._g_last[b])              # the gather of group g - gather_rings has read this ring
+            self._g_last[b] = None
         self._g_open.setdefault(g, [0, []])
         mem.copy_bytes(ring, i * cap, d_stage, 0, cap)
         ev = mem.event()
@@ -881,7 +893,8 @@ class FrameBatchJob:
         to shut down)."""
         mem, K = self.mem, self.gather_every
         cap, world = self._gather_cap, self.dist.get_world_size()
-        ring = self._dev(f"gather_ring{g & 1}", cap * K)
+        b = g % self.gather_rings
+        ring = self._dev(f"gather_ring{b}", cap * K)
         events = self._g_open.pop(g, [0, []])[1]
         for i in range(n_valid, K):                           # entries of a partial (or empty) last group
             mem.zero_bytes(ring, 32, i * cap)
@@ -889,17 +902,18 @@ class FrameBatchJob:
             ev = mem.event()
             ev.record()
             events = events + [ev]
-        d_all = self._dev(f"gather_all{g & 1}", cap * K * world)
+        d_all = self._dev(f"gather_all{b}", cap * K * world)
         rec = {"group": g, "n": n_valid, "np": None, "cap": cap, "world": world}
         with mem.side(4, events) as br:
             if not os.environ.get("IPB_DEBUG_NO_GATHER"):
                 mem.all_gather_bytes(d_all, ring, cap * K, self.dist)
             if self.dist.get_rank() == self.gather_dst and not os.environ.get("IPB_DEBUG_NO_GATHER_D2H"):
-                g_np, g_t = self._pinned(f"pin_gather{g & 1}", cap * K * world)
-                mem.download_async(g_t, d_all, cap * K * world)
+                g_np, g_t = self._pinned(f"pin_gather{b}", cap * K * world)
+                for r in range(world):                        # one copy per rank: a step's own small download on the
+                    mem.download_async(g_t, d_all, cap * K, offset=r * cap * K)          # same copy engine slips in between
                 rec["np"] = g_np
         rec["event"] = br.event
-        self._g_last[g & 1] = br.event
+        self._g_last[b] = br.event
         self._g_issued.append(rec)
         self._g_count += 1
 
@@ -909,8 +923,8 @@ class FrameBatchJob:
         (the collectives are still waited for when block is set).
 
         The arrays are VIEWS of the pinned buffer the gather was downloaded into (two buffers,
-        alternating by group): they stay valid until the gather of group + 2 is issued, i.e. for at
-        least `gather_every` further steps.  copy = True hands out private copies instead (measured:
+        `gather_rings` buffers used in turn): they stay valid until the gather of group + gather_rings is
+        issued, i.e. for at least (gather_rings - 1) x gather_every further steps.  copy = True hands out private copies instead (measured:
         copying 8 steps x N ranks of tables in one go stalls the destination rank's submit loop for
         ~6 ms per rank and group, which is what made N ranks slower than one -- profiles/README.md)."""
         out = []
@@ -954,8 +968,8 @@ class FrameBatchJob:
         while self._g_total is not None and self._g_count < self._g_total:
             g = self._g_pos // self.gather_every + 1 + self._g_count          # any unused group id
             self._g_open[g] = [0, []]
-            if self._g_last[g & 1] is not None:
-                self.mem.wait_event(self._g_last[g & 1])
+            if self._g_last.get(g % self.gather_rings) is not None:
+                self.mem.wait_event(self._g_last[g % self.gather_rings])
             self._issue_gather(g, 0)
         out = self.gathered(block=True, copy=copy)
         # a later run starts on fresh groups
@@ -982,9 +996,22 @@ class FrameBatchJob:
             return self.collect(self.submit(tk.planes, tk.polys, full_hist=True, _pos=tk.g_pos))
         if not tk.full_hist:
             self._miss_streak = 0
+        if "fa" in st and tk.fa_ran:
+            total = int(OV("comp_off")[NR])
+            if total > pl.comp_cap:
+                raise RuntimeError("fa_segment: component table overflow")
+            want = -(-(total + total // 4 + 1024) // 4096) * 4096
+            if self._pc_hint is None or want > self._pc_hint:         # grows only: a new size means new graphs
+                self._pc_hint = want
+            if total > tk.pc_rows:
+                # more adhesions than the rows staged with the tables: the step is repeated with the
+                # larger fetch (rank-local, same ring entry; the device table of a step is overwritten
+                # by the steps behind it, so the missing rows cannot be fetched after the fact)
+                self.comp_refetches += 1
+                return self.collect(self.submit(tk.planes, tk.polys, full_hist=tk.full_hist, _pos=tk.g_pos))
         self._entry_done(tk)
         params = OV("params")[:NP].copy()
-        res.d2h_bytes = O.size
+        res.d2h_bytes = tk.stage_bytes                       # what the step's one D2H copied
         # regions the fused ROI kernel left to the full-histogram kernels, by reason (ipb_roifused.cuh)
         why = np.bincount(OV("rf_flags")[:NR], minlength=6) if (self.fused_roi and pl.NF) else np.zeros(6, np.int64)
         res.roi_fallbacks = int(why[1:].sum())
@@ -1009,24 +1036,7 @@ class FrameBatchJob:
             comp_off = OV("comp_off")[: NR + 1].copy()
             res.fa_comp_off = comp_off
             total = int(comp_off[-1]) if tk.fa_ran else 0
-            if tk.fa_ran and total > pl.comp_cap:
-                raise RuntimeError("fa_segment: component table overflow")
-            if tk.fa_ran:
-                want = -(-(total + total // 4 + 1024) // 4096) * 4096
-                if self._pc_hint is None or want > self._pc_hint:     # grows only: a new size means new graphs
-                    self._pc_hint = want
-            if total:
-                if total <= tk.pc_rows:
-                    res.fa_comps = tk.pc_np[: COMP.itemsize * total].view(COMP).copy()
-                else:                                       # more adhesions than the pre-fetched slice
-                    nb = COMP.itemsize * total
-                    pc_np, pc_t = self._pinned("pin_comps_all", nb)
-                    mem.download_async(pc_t, tk.d_comps, nb)
-                    mem.sync()
-                    res.fa_comps = pc_np[:nb].view(COMP).copy()
-                res.d2h_bytes += COMP.itemsize * total
-            else:
-                res.fa_comps = np.zeros(0, dtype=COMP)
+            res.fa_comps = tk.pc_np[: COMP.itemsize * total].view(COMP).copy() if total else np.zeros(0, dtype=COMP)
         return res
 
     def run(self, planes, polys_per_frame, full_hist=False, _pos=None):

@@ -173,10 +173,10 @@ class TorchMem:
         ev.record(cs)
         return ev
 
-    def download_async(self, pinned_tensor, buf, nbytes):
-        """D2H copy into a pinned tensor on the current stream (caller syncs)."""
-        n = int(nbytes)
-        pinned_tensor[:n].copy_(buf.raw[:n], non_blocking=True)
+    def download_async(self, pinned_tensor, buf, nbytes, offset=0):
+        """D2H copy into a pinned tensor on the current stream (caller syncs); `offset` applies to both sides."""
+        o, n = int(offset), int(nbytes)
+        pinned_tensor[o: o + n].copy_(buf.raw[o: o + n], non_blocking=True)
 
     def zero_bytes(self, buf, nbytes, offset=0):
         buf.raw[int(offset): int(offset) + int(nbytes)].zero_()

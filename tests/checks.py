@@ -1174,3 +1174,25 @@ def check_fa_threshold_straddles(eng, n_seeds=24, H=192, W=256):
 
 
 RASTER_CHECKS.append(check_fa_threshold_straddles)
+
+
+def check_fa_row_refetch(eng):
+    """A step with more adhesions than rows staged with its tables is repeated with a larger fetch
+    (FrameBatchJob.collect): same rows as a job that fetched enough at once, one repeat counted."""
+    from imageprocess_b200 import batch
+    params = {"alpha": 2.0, "min_area_um": 0.05, "max_area_um": 5.0, "close_radius": 1, "subtract_bg": True}
+    frames = [small_scene(70 + s, H=128, W=160, n_cells=2, blobs=6) for s in range(2)]
+    planes = np.stack([np.stack([d, a]) for d, a, _ in frames])
+    polys = [fr[2] for fr in frames]
+    want = batch.FrameBatchJob(eng, planes.shape, stages=("fa",), fa_params=params, fa_px=0.112).run(eng.mem.from_host(planes), polys)
+    assert int(want.fa_comp_off[-1]) > 1
+    job = batch.FrameBatchJob(eng, planes.shape, stages=("fa",), fa_params=params, fa_px=0.112)
+    job._pc_hint = 1                                              # as if earlier steps had found (almost) nothing
+    got = job.run(eng.mem.from_host(planes), polys)
+    assert job.comp_refetches == 1 and job._pc_hint >= int(want.fa_comp_off[-1])
+    assert np.array_equal(got.fa_comp_off, want.fa_comp_off) and np.array_equal(got.fa_comps, want.fa_comps)
+    got2 = job.run(eng.mem.from_host(planes), polys)              # and the next step fits at once
+    assert job.comp_refetches == 1 and np.array_equal(got2.fa_comps, want.fa_comps)
+
+
+RASTER_CHECKS.append(check_fa_row_refetch)

@@ -55,8 +55,9 @@ class NumpyMem:
         self.upload_async(buf, pinned_tensor, nbytes)
         return NumpyMem._Event()
 
-    def download_async(self, pinned_tensor, buf, nbytes):
-        pinned_tensor[: int(nbytes)] = buf.raw[: int(nbytes)]
+    def download_async(self, pinned_tensor, buf, nbytes, offset=0):
+        o, n = int(offset), int(nbytes)
+        pinned_tensor[o: o + n] = buf.raw[o: o + n]
 
     def zero_bytes(self, buf, nbytes, offset=0):
         buf.raw[int(offset): int(offset) + int(nbytes)] = 0
