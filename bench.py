@@ -441,6 +441,7 @@ def run_ours(args):
         line["ms_per_step_serialized"] = ms_ser / args.steps
         line["host_submit_ms_per_step"] = host_submit_ms
         if ms_ranks is not None:
+            line["gather_via"] = job.gather_via       # how the other ranks' tables reached rank 0 (shared-memory ring | NCCL all-gather)
             line["ms_per_step_ranks"] = ms_ranks      # device-timed, per rank; the job's ms_per_step is their max
         line["host_ms_per_step"] = host_ms          # rank 0: submit / collect (waits for the step) / gathered tables of all ranks
         line["window_misses"] = int(job.window_misses)       # steps repeated with full histograms (exact either way)

@@ -109,6 +109,12 @@ class FrameBatchJob:
         # tail short (the last group's tables reach the destination after the last step: all-gather + D2H
         # of N x gather_every steps); the gathers run on their own stream, so their count costs nothing
         self.gather_rings = int(os.environ.get("IPB_GATHER_RINGS", "4"))
+        # how the step tables of N ranks reach the destination rank: "shm" = every rank downloads into a
+        # shared-memory ring the destination reads in place (ranks of one host; parallel.ShmTableRing: no
+        # device work, no collective, nothing couples the ranks); "nccl" = all-gather + one download on the
+        # destination (ranks on several hosts, or when the shared segments cannot be had)
+        self.gather_via = os.environ.get("IPB_GATHER_VIA", "shm")
+        self._shm = None
         self._g_pos = 0                  # steps staged so far
         self._g_open = {}                # group -> [entries collected, their ring-copy events]
         self._g_issued = []              # issued gathers not yet handed out: dicts
@@ -582,8 +588,17 @@ class FrameBatchJob:
         self._stage_for_gather(tk, _pos)
         done = mem.event()
         done.record()
+        if self._shm is not None and tk.g_pos is not None:   # N ranks, one host: straight into the shared ring
+            pin_np, pin_t = self._shm.entry(tk.g_pos)
+        else:
+            pin_np, pin_t = self._pinned(f"pin_stage{slot}", tk.stage_bytes)
+        O, a_rows = tk.pl.O, 32 + _al(tk.pl.O.size)
+        n_dl = min(tk.stage_bytes, pin_np.nbytes)            # (a ring entry holds `cap` bytes: rows beyond it stay behind)
+        tk.pout_np = pin_np[32: 32 + O.size]
+        tk.pc_np = pin_np[a_rows: n_dl]
+        tk.pc_rows_host = (n_dl - a_rows) // COMP.itemsize
         with mem.side(5, [done]) as dl:                      # the download stream: behind this step only
-            mem.download_async(tk.pin_t, tk.d_stage, tk.stage_bytes)
+            mem.download_async(pin_t, tk.d_stage, n_dl)
         tk.event = self._slot_busy[slot] = dl.event
         return tk
 
@@ -810,7 +825,14 @@ class FrameBatchJob:
             # rank's host buffers alone takes ~25 ms each (measured: it showed up as 1 ms per step
             # of a 24-step run when the second ring's buffers were first used inside it)
             K = self.gather_every
-            for b in range(self.gather_rings):
+            if self.gather_via == "shm":
+                from . import parallel
+                ring = parallel.ShmTableRing(self.dist, mem, self._gather_cap, n_entries=16, dst=self.gather_dst)
+                if ring.ok:
+                    self._shm = ring
+                else:
+                    self.gather_via = "nccl"                  # no room for the segments (or no page-locking): collective path
+            for b in range(self.gather_rings if self._shm is None else 0):
                 self._dev(f"gather_ring{b}", self._gather_cap * K)
                 self._dev(f"gather_all{b}", self._gather_cap * K * world)
                 if self.dist.get_rank() == self.gather_dst:
@@ -829,10 +851,8 @@ class FrameBatchJob:
         mem.copy_bytes(d_stage, 32, d_out, 0, O.size)
         if tk.pc_rows:
             mem.copy_bytes(d_stage, a_rows, d_comps, 0, COMP.itemsize * tk.pc_rows)
-        pin_np, pin_t = self._pinned(f"pin_stage{slot}", tk.stage_bytes)
-        tk.d_stage, tk.pin_t = d_stage, pin_t
-        tk.pout_np = pin_np[32: 32 + O.size]
-        tk.pc_np = pin_np[a_rows: a_rows + COMP.itemsize * tk.pc_rows]
+        self._pinned(f"pin_stage{slot}", tk.stage_bytes)          # (allocated here, outside the timed steps)
+        tk.d_stage, tk.slot = d_stage, slot
         tk.g_stage = (d_stage, cap, self.dist.get_world_size()) if staged else None   # the collective: _issue_gather()
         mem.nvtx_mark(None)
         return tk
@@ -858,6 +878,9 @@ class FrameBatchJob:
         if pos is None:
             pos = self._g_pos
             self._g_pos += 1
+        if self._shm is not None:                            # the download itself goes into the ring entry (submit)
+            tk.g_pos, tk.g_ev = pos, None
+            return
         g, i = divmod(pos, K)
         if (g - self.gather_rings) in self._g_open:
             raise RuntimeError("collect() earlier tickets first: the gather ring still holds their group")
@@ -876,6 +899,9 @@ class FrameBatchJob:
         """collect() has accepted the step's tables: its ring entry is final.  The K-th accepted
         entry of a group issues the group's all-gather."""
         if tk.g_pos is None:
+            return
+        if self._shm is not None:
+            self._shm.publish(tk.g_pos)
             return
         g = tk.g_pos // self.gather_every
         ent = self._g_open[g]
@@ -929,6 +955,47 @@ class FrameBatchJob:
         ~6 ms per rank and group, which is what made N ranks slower than one -- profiles/README.md)."""
         out = []
         keep = (lambda a: a.copy()) if copy else (lambda a: a)
+        if self._shm is not None:
+            # shared-memory ring: whatever became final since the last call, read in place.  The views are
+            # valid until the NEXT call of gathered() / finish(), which releases them to their producers
+            if self.dist.get_rank() != self.gather_dst:
+                return out
+            import time
+            ring, world = self._shm, self.dist.get_world_size()
+            run = getattr(self, "_shm_wait_run", None)
+            prev = getattr(self, "_shm_prev", [0] * world)
+            for r in range(world):
+                ring.release(r, prev[r])                         # handed out by earlier calls
+            per_rank, private = [[] for _ in range(world)], [0] * world
+            t0 = time.perf_counter()
+            while True:
+                for r in range(world):
+                    for _pos, blob in ring.poll_rank(r):
+                        arena_b, rows, co_off, co_n = (int(v) for v in blob[:32].view(np.int64))
+                        a0 = 32 + _al(arena_b)
+                        arena = keep(blob[32: 32 + arena_b])
+                        comp_off = arena[co_off: co_off + 4 * co_n].view(np.int32)
+                        rows = min(rows, int(comp_off[-1]) if co_n else 0)
+                        per_rank[r].append((arena, keep(blob[a0: a0 + COMP.itemsize * rows]).view(COMP), comp_off, co_off))
+                if not block or run is None or ring.drained(run):
+                    break
+                # waiting for ranks that still have steps to run: do not sit on half of a producer's ring
+                for r in range(world):
+                    if ring.next[r] - ring.released[r] >= ring.n // 2:
+                        for k in range(private[r], len(per_rank[r])):
+                            a, c, o, co_off = per_rank[r][k]
+                            a = a.copy()
+                            per_rank[r][k] = (a, c.copy(), a[co_off: co_off + o.nbytes].view(np.int32), co_off)
+                        private[r] = len(per_rank[r])
+                        ring.release(r, ring.next[r])
+                if time.perf_counter() - t0 > 120.0:
+                    raise RuntimeError("finish(): a rank did not end its run")
+                time.sleep(50e-6)
+            self._shm_prev = list(ring.next)
+            if any(per_rank):
+                self._shm_seq = getattr(self, "_shm_seq", -1) + 1
+                out.append({"group": self._shm_seq, "per_rank": [[e[:3] for e in ents] for ents in per_rank]})
+            return out
         while self._g_issued:
             rec = self._g_issued[0]
             if block:
@@ -963,6 +1030,15 @@ class FrameBatchJob:
         and returns what gathered() has not handed out yet.  Every rank must call it."""
         if self.dist is None or self.dist.get_world_size() == 1 or self._gather_cap is None:
             return []
+        if self._shm is not None:
+            # every step of this rank is published (collect() did that): tell the destination the run is
+            # over; the destination waits until it has every rank's steps.  No collective, no barrier
+            self._shm.end_run(self._g_pos)
+            self._shm_wait_run = self._shm.run
+            try:
+                return self.gathered(block=True, copy=copy)
+            finally:
+                self._shm_wait_run = None
         for g in sorted(self._g_open):
             self._issue_gather(g, self._g_open[g][0])
         while self._g_total is not None and self._g_count < self._g_total:
@@ -1003,7 +1079,9 @@ class FrameBatchJob:
             want = -(-(total + total // 4 + 1024) // 4096) * 4096
             if self._pc_hint is None or want > self._pc_hint:         # grows only: a new size means new graphs
                 self._pc_hint = want
-            if total > tk.pc_rows:
+            if total > min(tk.pc_rows, tk.pc_rows_host):
+                if total <= tk.pc_rows:
+                    raise RuntimeError("adhesion rows beyond the agreed table capacity of the N-rank job; pass a larger gather capacity")
                 # more adhesions than the rows staged with the tables: the step is repeated with the
                 # larger fetch (rank-local, same ring entry; the device table of a step is overwritten
                 # by the steps behind it, so the missing rows cannot be fetched after the fact)

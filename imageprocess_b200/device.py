@@ -151,6 +151,15 @@ class TorchMem:
         t = self.torch.empty(n, dtype=self.torch.uint8, pin_memory=True)
         return t.numpy().view(dtype).reshape(shape), t
 
+    def register_host(self, buffer, array):
+        """Page-locks existing host memory (a shared-memory mapping) and returns the torch tensor
+        over it, so that copies into it are asynchronous like those into pinned() buffers."""
+        t = self.torch.frombuffer(buffer, dtype=self.torch.uint8)
+        rc = self.torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel(), 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed: {rc}")
+        return t
+
     def upload_async(self, buf, pinned_tensor, nbytes=None):
         """H2D copy of a pinned tensor into an existing DevBuf on the current stream."""
         n = pinned_tensor.numel() if nbytes is None else int(nbytes)

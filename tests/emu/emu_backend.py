@@ -55,6 +55,9 @@ class NumpyMem:
         self.upload_async(buf, pinned_tensor, nbytes)
         return NumpyMem._Event()
 
+    def register_host(self, buffer, array):
+        return array
+
     def download_async(self, pinned_tensor, buf, nbytes, offset=0):
         o, n = int(offset), int(nbytes)
         pinned_tensor[o: o + n] = buf.raw[o: o + n]

@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch.multiprocessing as mp
 
 from imageprocess_b200 import parallel
@@ -69,15 +70,15 @@ def test_two_rank_gather_gloo():
     assert [r[1] for r in flat] == list(range(n_frames)) and [r[0] for r in flat] == [7 * i for i in range(n_frames)]
 
 
-def _job_worker(rank, world, port, q):
+def _job_worker(rank, world, port, q, via):
     try:
-        _job_worker_body(rank, world, port, q)
+        _job_worker_body(rank, world, port, q, via)
     except Exception as e:                                   # surface the failure instead of a queue timeout
         q.put(f"rank {rank}: {type(e).__name__}: {e}")
         raise
 
 
-def _job_worker_body(rank, world, port, q):
+def _job_worker_body(rank, world, port, q, via):
     """Each rank runs the product's FrameBatchJob (kernels in the emulated build) on its block of
     frames for several steps; the staged tables go out with ONE all-gather per `gather_every`
     steps (+ the partial last group at finish()); rank 0 checks what it received.  Rank 1's second
@@ -112,6 +113,7 @@ def _job_worker_body(rank, world, port, q):
         job = batch.FrameBatchJob(eng, planes.shape, stages=("int", "fa"), int_task=task, fa_params=fa_params, fa_px=0.112)
         job.pq_min_px = 0                                     # sampled windows even on these small frames
         job.gather_every = 2
+        job.gather_via = via
         job.dist = dist if with_dist else None
         return job
 
@@ -130,7 +132,10 @@ def _job_worker_body(rank, world, port, q):
     misses = job.window_misses
     ok = True
     if rank == 0:
-        assert [g["group"] for g in got] == sorted(g["group"] for g in got) and len(got) == 2, [g["group"] for g in got]
+        assert (job._shm is not None) == (via == "shm")
+        assert [g["group"] for g in got] == sorted(g["group"] for g in got), [g["group"] for g in got]
+        if via == "nccl":
+            assert len(got) == 2, len(got)                        # 3 steps in groups of 2: one full, one partial gather
         per_rank = [[e for g in got for e in g["per_rank"][r]] for r in range(world)]
         assert [len(x) for x in per_rank] == [n_steps[0], n_steps[1]], [len(x) for x in per_rank]
         for r in range(world):
@@ -156,12 +161,15 @@ def _job_worker_body(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_job_all_gather_gloo():
+@pytest.mark.parametrize("via", ["shm", "nccl"])
+def test_job_all_gather_gloo(via):
+    """via = "shm": shared-memory table ring (ranks of one host, the default); "nccl": the
+    all-gather path (gloo stands in for NCCL here)."""
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_job_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_job_worker, args=(r, world, port, q, via)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=300)
@@ -169,3 +177,68 @@ def test_job_all_gather_gloo():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+
+
+def _ring_worker(rank, world, port, q):
+    """Producer (rank 1) publishes 50 entries into a 16-entry ring while the consumer (rank 0, also a
+    producer of 5) polls: order, content, back-pressure (the producer can never be more than a ring
+    ahead of what the consumer released) and the end-of-run handshake."""
+    try:
+        import torch.distributed as dist
+        from tests.emu.emu_backend import NumpyMem
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        ring = parallel.ShmTableRing(dist, NumpyMem(), cap=4096, n_entries=16, dst=0)
+        assert ring.ok
+        n_mine = 50 if rank == 1 else 5
+        seen = {0: [], 1: []}
+        prev = [0, 0]
+
+        def consume():
+            for r in range(world):
+                ring.release(r, prev[r])
+            for r in range(world):
+                for pos, blob in ring.poll_rank(r):
+                    assert ring.next[r] - ring.released[r] <= ring.n
+                    assert int(blob[:8].view(np.int64)[0]) == 1000 * r + pos and int(blob[-1]) == pos % 251
+                    seen[r].append(pos)
+                prev[r] = ring.next[r]
+
+        for pos in range(n_mine):
+            arr, _ = ring.entry(pos)                   # blocks while the consumer has not released pos - 16
+            arr[:8].view(np.int64)[0] = 1000 * rank + pos
+            arr[-1] = pos % 251
+            ring.publish(pos)
+            if rank == 0:
+                consume()
+        ring.end_run(n_mine)
+        if rank == 0:
+            import time
+            t0 = time.time()
+            while not ring.drained(ring.run):
+                consume()
+                assert time.time() - t0 < 60
+                time.sleep(1e-4)
+            assert seen[0] == list(range(5)) and seen[1] == list(range(50)), (seen[0], len(seen[1]))
+            q.put("ok")
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:
+        q.put(f"rank {rank}: {type(e).__name__}: {e}")
+        raise
+
+
+def test_shm_table_ring_backpressure():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=120) == "ok"
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("ipb200_tables_")] if os.path.isdir("/dev/shm") else True
