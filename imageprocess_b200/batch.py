@@ -145,7 +145,7 @@ class FrameBatchJob:
         # FA moments on the FRET pass instead of the percentile pass: measured 2.545 vs 2.468 ms per step
         # (the FRET pass loses 30 us, the percentile pass gains 25 us, the FA chain starts later): off
         self.fret_moments = bool(int(os.environ.get("IPB_FRET_MOMENTS", "0")))
-        self.rf_ctas = ops.RF_CTAS_PER_SM * eng.n_sms()
+        self.rf_ctas = int(os.environ.get("IPB_RF_CTAS", ops.RF_CTAS_PER_SM)) * eng.n_sms()      # persistent CTAs of the fused ROI kernel
         self.roi_fallbacks = 0       # regions repeated by the full-histogram kernels so far
         self.pq_min_px = 1 << 18     # smaller planes take the full histograms (the sample would be most of the plane)
         self._pin = None
