@@ -627,7 +627,9 @@ def run_folder(args):
             dt = time.perf_counter() - t0
             out[name] = {"seconds": round(dt, 3), "frames_per_s": round(n / dt, 2), "mpix_per_s": round(n * H * W / dt / 1e6, 1),
                          "rows": len(rows), "decode_thread_seconds": round(tm.get("decode_s", 0.0), 3),
-                         "host_waited_for_decode_s": round(tm.get("wait_decode_s", 0.0), 3), "batches": tm.get("batches", 0)}
+                         "host_waited_for_decode_s": round(tm.get("wait_decode_s", 0.0), 3), "batches": tm.get("batches", 0),
+                         "host_seconds": {k[:-2]: round(v, 3) for k, v in tm.items()
+                                          if k.endswith("_s") and k not in ("decode_s", "wait_decode_s")}}
         line = {"metric": "Mpix/s (folder of 2048x2048 uint16 2ch TIFF pairs through the headless entry points, wall clock)",
                 "value": out["fret_ratio_builder"]["mpix_per_s"], "unit": "Mpix/s", "n_gpus": 1, "steps": 1, "warmup": 0,
                 "higher_is_better": True, "data": "synthetic", "dtype": "u16/f32",

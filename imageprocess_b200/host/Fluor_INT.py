@@ -313,10 +313,12 @@ def process_key_tasks(tasks, eng=None, frames_per_batch=32, decode_threads=8, ti
     two batches behind); everything else goes through _process_key_task.  Keys are grouped on
     metadata only (paths, shape from the TIFF header) and decoded per batch.  Returns the per-task
     results in task order."""
+    import time
     from .stream import FrameStream
     eng = eng or _engine()
     results = [None] * len(tasks)
     groups = {}
+    t_scan, t_rows = time.perf_counter(), 0.0
     for i, task in enumerate(tasks):
         try:
             chs = sorted(ch for ch in task["chs_to_quant"] if task["chmap"].get(ch) is not None)
@@ -332,6 +334,8 @@ def process_key_tasks(tasks, eng=None, frames_per_batch=32, decode_threads=8, ti
             groups.setdefault(key, []).append((i, [task["chmap"][ch] for ch in chs], polys))
         except Exception:
             results[i] = _process_key_task(task, eng)
+    if timing is not None:
+        timing["scan_s"] = timing.get("scan_s", 0.0) + time.perf_counter() - t_scan          # ROI JSONs + TIFF headers
     for key, items in groups.items():
         (H, W), chs = key[0], list(key[1])
         task0 = tasks[items[0][0]]
@@ -347,6 +351,7 @@ def process_key_tasks(tasks, eng=None, frames_per_batch=32, decode_threads=8, ti
                              decode_threads=decode_threads)
         try:
             for pos, res in stream.run(items, load, lambda it: it[2]):
+                t_r = time.perf_counter()
                 rows_pf = batch.rows_intensity(res, stream.F, chs)
                 for f, k in enumerate(pos):
                     i = items[k][0]
@@ -357,6 +362,7 @@ def process_key_tasks(tasks, eng=None, frames_per_batch=32, decode_threads=8, ti
                     rows = _rows_of_frame(task, rows_pf[f], chs, res, f)
                     results[i] = {"rows": rows, "steps": max(1, len(rows)),
                                   "logs": [t("log_done_quant").format(stid=task["stid"], roi_count=len(rows))]}
+                t_rows += time.perf_counter() - t_r
         except Exception as e:
             for i, _, _ in items:
                 if results[i] is None:
@@ -366,6 +372,8 @@ def process_key_tasks(tasks, eng=None, frames_per_batch=32, decode_threads=8, ti
             if timing is not None:
                 for k, v in stream.timing.items():
                     timing[k] = timing.get(k, 0) + v
+                timing["rows_s"] = timing.get("rows_s", 0.0) + t_rows
+                t_rows = 0.0
     return results
 
 
@@ -465,5 +473,9 @@ def run_headless(img_dir, roi_dir, out_root=None, cfg=None, eng=None, log=print,
         for line in res.get("logs", []):
             log(line)
     if rows_all and (cfg or {}).get("out_xls", True):
+        import time
+        t0 = time.perf_counter()
         save_excel(rows_all, keymap, ensure_dir(os.path.join(out_root, "xls")), log=log)
+        if timing is not None:
+            timing["save_s"] = timing.get("save_s", 0.0) + time.perf_counter() - t0
     return rows_all

@@ -30,6 +30,8 @@ def _engine():
 
 
 def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per_batch=32, timing=None):
+    import time
+    t_scan = time.perf_counter()
     eng = eng or _engine()
     logs = [f"[Stage {stage_key}] start"]
     RES_ROOT, RAT32, RAT16, RROI32, RROI16, PNG_FULL, PNG_CROP = paths
@@ -56,6 +58,9 @@ def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per
             continue
         by_shape.setdefault(shape, []).append((s, t_code, stid, dpath, apath, polys))
     rows_stage = []
+    if timing is not None:
+        timing["scan_s"] = timing.get("scan_s", 0.0) + time.perf_counter() - t_scan      # ROI JSONs + TIFF headers
+    t_rows = 0.0
 
     def load(it):
         return np.stack([common.as_u16_plane(common.read_image_raw(it[3]), f"{it[2]} donor"),
@@ -69,6 +74,7 @@ def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per
                              decode_threads=int(p.get("n_workers", 8) or 8), lag=0 if out_tif else 2)
         try:
             for pos, res in stream.run(group, load, lambda it: it[5] or []):
+                t_r = time.perf_counter()
                 F = stream.F
                 rows_pf = batch.rows_fret(res, F)
                 if out_tif:
@@ -98,11 +104,13 @@ def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per
                                   "bg_scope": p["bg_scope"], "bg_mode": p["bg_mode"], "clip_neg": p["clip_neg"],
                                   "eps_p": p["eps_percentile"]})
                     rows_stage.extend(rows_pf[f])
+                t_rows += time.perf_counter() - t_r
         finally:
             stream.close()
             if timing is not None:
                 for k, v in stream.timing.items():
                     timing[k] = timing.get(k, 0) + v
+                timing["rows_s"] = timing.get("rows_s", 0.0) + t_rows
     if p.get("out_png"):
         logs.append("  [SKIP-PNG] figure rendering is host matplotlib code outside the device path")
     logs.append(f"[Stage {stage_key}] end (total {len(pairs_for_stage)} time/files)")
@@ -128,7 +136,11 @@ def run_headless(img_dir, roi_dir, out_root=None, p=None, eng=None, log=print, f
         for line in logs:
             log(line)
     if rows_all and p["out_xls"]:
+        import time
+        t0 = time.perf_counter()
         save_tables(rows_all, bool(p["timelapse"]), ensure_dir(os.path.join(res_root, "xls")), log=log)
+        if timing is not None:
+            timing["save_s"] = timing.get("save_s", 0.0) + time.perf_counter() - t0
     elif p["out_xls"]:
         log("[Warn] No ROI \u2192 metric table not generated.")
     return rows_all

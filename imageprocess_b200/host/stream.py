@@ -22,6 +22,7 @@ import numpy as np
 
 class FrameStream:
     def __init__(self, eng, chw, make_job, frames_per_batch=32, decode_threads=8, depth=3, lag=2):
+        t_c = time.perf_counter()
         self.eng, self.mem = eng, eng.mem
         self.C, self.H, self.W = (int(v) for v in chw)
         self.F = int(frames_per_batch)
@@ -32,10 +33,12 @@ class FrameStream:
         self.pin = [self.mem.pinned(shape, np.uint16) for _ in range(self.depth)]
         self.dev = [self.mem.empty(shape, np.uint16) for _ in range(self.depth)]
         self.pool = ThreadPoolExecutor(max_workers=max(1, int(decode_threads)))
-        self.timing = {"decode_s": 0.0, "wait_decode_s": 0.0, "batches": 0, "frames": 0}
+        self.timing = {"decode_s": 0.0, "wait_decode_s": 0.0, "batches": 0, "frames": 0,
+                       "submit_s": 0.0, "collect_s": 0.0, "construct_s": 0.0}     # host seconds by phase
         self.lag = max(0, min(int(lag), 2))  # batches in flight before one is collected (0: device images of a
                                              # result -- single-buffered per job -- are read before the next submit)
         self.errors = {}                     # item position -> exception raised by its load(); its frame is zeros
+        self.timing["construct_s"] = time.perf_counter() - t_c      # job + pinned / device rings
 
     def _decode_batch(self, slot, chunk, load):
         """Starts the decode of `chunk` into pinned slot `slot`; returns the futures."""
@@ -83,6 +86,7 @@ class FrameStream:
             n = len(pos)
             if n < F:                                            # tail: repeat the last frame, no ROIs on the padding
                 self.pin[slot][0][n:] = self.pin[slot][0][n - 1]
+            t1 = time.perf_counter()
             polys = [(polys_of(items[i]) if i not in self.errors else []) for i in pos] + [[] for _ in range(F - n)]
             up = mem.upload_on_copy_stream(self.dev[slot], self.pin[slot][1], after=computed[slot])
             uploaded[b] = up
@@ -91,15 +95,21 @@ class FrameStream:
             computed[slot] = mem.event()
             computed[slot].record()
             inflight.append((pos, tk))
+            self.timing["submit_s"] += time.perf_counter() - t1
             self.timing["batches"] += 1
             self.timing["frames"] += n
             start_decode(b + 2)
             while len(inflight) > self.lag:
-                p, t = inflight.pop(0)
-                yield p, job.collect(t)
+                yield self._collect(inflight.pop(0))
         while inflight:
-            p, t = inflight.pop(0)
-            yield p, job.collect(t)
+            yield self._collect(inflight.pop(0))
+
+    def _collect(self, entry):
+        t0 = time.perf_counter()
+        pos, tk = entry
+        res = self.job.collect(tk)
+        self.timing["collect_s"] += time.perf_counter() - t0
+        return pos, res
 
     def close(self):
         self.pool.shutdown(wait=True)
