@@ -30,8 +30,10 @@ class FrameStream:
         shape = (self.F, self.C, self.H, self.W)
         self.shape = shape
         self.job = make_job(shape)
-        self.pin = [self.mem.pinned(shape, np.uint16) for _ in range(self.depth)]
-        self.dev = [self.mem.empty(shape, np.uint16) for _ in range(self.depth)]
+        # ring buffers are allocated when their slot is first used (page-locking 0.5 GB takes ~0.2 s:
+        # slots 1 and 2 are pinned while the pool already decodes into slot 0)
+        self.pin = [None] * self.depth
+        self.dev = [None] * self.depth
         self.pool = ThreadPoolExecutor(max_workers=max(1, int(decode_threads)))
         self.timing = {"decode_s": 0.0, "wait_decode_s": 0.0, "batches": 0, "frames": 0,
                        "submit_s": 0.0, "collect_s": 0.0, "construct_s": 0.0}     # host seconds by phase
@@ -42,6 +44,11 @@ class FrameStream:
 
     def _decode_batch(self, slot, chunk, load):
         """Starts the decode of `chunk` into pinned slot `slot`; returns the futures."""
+        if self.pin[slot] is None:
+            t0 = time.perf_counter()
+            self.pin[slot] = self.mem.pinned(self.shape, np.uint16)
+            self.dev[slot] = self.mem.empty(self.shape, np.uint16)
+            self.timing["construct_s"] += time.perf_counter() - t0
         dst = self.pin[slot][0]
 
         def one(k, pos, item):
