@@ -26,6 +26,13 @@
 
 #define IPB_FULL 0xffffffffu
 
+// hint: bring the line of `p` into L2 (no register result, no fault on a bad address)
+#ifdef IPB_EMULATE
+static inline void ipb_prefetch_l2(const void*) {}
+#else
+__device__ __forceinline__ void ipb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+#endif
+
 // ---- status codes (mirrored in include/ipb200.h)
 #define IPB_OK 0
 #define IPB_ERR_ARG (-1)
