@@ -345,7 +345,9 @@ def process_key_tasks(tasks, eng=None, frames_per_batch=32, decode_threads=8, ti
             job.ch_names = chs
             return job
 
-        def load(it):
+        def load(it, out=None):
+            if out is not None and all(common.read_plane_into(p, out[ci]) for ci, p in enumerate(it[1])):
+                return None                                      # plain uint16 TIFFs: file -> pinned buffer
             return np.stack([common.as_u16_plane(common.read_image_raw(p)) for p in it[1]])
         stream = FrameStream(eng, (len(chs), H, W), make_job, frames_per_batch=min(frames_per_batch, len(items)),
                              decode_threads=decode_threads)

@@ -119,6 +119,29 @@ def read_image_raw(path, page=0):
     return a
 
 
+def read_plane_into(path, out):
+    """Reads a plain uncompressed uint16 TIFF (see _tiff_plain_layout) straight into `out`, a
+    C-contiguous uint16 [H][W] array -- the stream's page-locked ring buffer: file -> pinned memory
+    with no array in between.  Returns False (nothing usable written) when the file is anything
+    else or its shape differs; the caller then decodes it the general way."""
+    lay = _tiff_plain_layout(path)
+    if lay is None:
+        return False
+    dt, h, w, off = lay
+    if dt != np.dtype("<u2") or out.dtype != np.uint16 or out.shape != (h, w) or not out.flags.c_contiguous:
+        return False
+    with open(path, "rb", buffering=0) as f:
+        f.seek(off)
+        view = memoryview(out).cast("B")
+        got = 0
+        while got < len(view):
+            n = f.readinto(view[got:])
+            if not n:
+                return False
+            got += n
+    return True
+
+
 def image_shape(path):
     """(H, W) of an image file from its header, without decoding the pixels."""
     lay = _tiff_plain_layout(path)

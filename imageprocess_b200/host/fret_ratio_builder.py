@@ -62,7 +62,9 @@ def process_one_stage(stage_key, pairs_for_stage, p, paths, eng=None, frames_per
         timing["scan_s"] = timing.get("scan_s", 0.0) + time.perf_counter() - t_scan      # ROI JSONs + TIFF headers
     t_rows = 0.0
 
-    def load(it):
+    def load(it, out=None):
+        if out is not None and common.read_plane_into(it[3], out[0]) and common.read_plane_into(it[4], out[1]):
+            return None                                          # plain uint16 TIFFs: file -> pinned buffer
         return np.stack([common.as_u16_plane(common.read_image_raw(it[3]), f"{it[2]} donor"),
                          common.as_u16_plane(common.read_image_raw(it[4]), f"{it[2]} fret")])
 

@@ -43,7 +43,14 @@ class FrameStream:
         self.timing["construct_s"] = time.perf_counter() - t_c      # job + pinned / device rings
 
     def _decode_batch(self, slot, chunk, load):
-        """Starts the decode of `chunk` into pinned slot `slot`; returns the futures."""
+        """Starts the decode of `chunk` into pinned slot `slot`; returns the futures.  A loader that
+        takes a second argument gets the frame's slice of the pinned buffer and may fill it in place
+        (returning None): plain TIFFs go from the file into page-locked memory without a copy."""
+        import inspect
+        try:
+            self._load_into = len(inspect.signature(load).parameters) >= 2
+        except (TypeError, ValueError):
+            self._load_into = False
         if self.pin[slot] is None:
             t0 = time.perf_counter()
             self.pin[slot] = self.mem.pinned(self.shape, np.uint16)
@@ -54,10 +61,12 @@ class FrameStream:
         def one(k, pos, item):
             t0 = time.perf_counter()
             try:                                                 # one unreadable image must not lose the batch
-                a = np.asarray(load(item))                       # (the reference logs the key and goes on)
-                if a.shape != (self.C, self.H, self.W):
-                    raise ValueError(f"frame of shape {a.shape}, expected {(self.C, self.H, self.W)}")
-                dst[k] = a
+                a = load(item, dst[k]) if self._load_into else load(item)      # (the reference logs the key and goes on)
+                if a is not None:                                # None: the loader filled dst[k] itself
+                    a = np.asarray(a)
+                    if a.shape != (self.C, self.H, self.W):
+                        raise ValueError(f"frame of shape {a.shape}, expected {(self.C, self.H, self.W)}")
+                    dst[k] = a
             except Exception as e:
                 self.errors[pos] = e
                 dst[k] = 0

@@ -78,3 +78,23 @@ def test_rgb_and_truncated_go_to_pil(tmp_path):
         f.write(cut[:4] + struct.pack("<I", 8 + 1000) + cut[8:])
     with pytest.raises(Exception):
         common.read_image_raw(q)
+
+
+def test_read_plane_into_pinned_like_buffer(tmp_path):
+    """File -> caller's buffer without an array in between (the stream's pinned ring); anything that
+    is not a plain little-endian uint16 raster of the buffer's shape is refused untouched."""
+    rng = np.random.default_rng(7)
+    arr = rng.integers(0, 65535, (40, 56), dtype=np.uint16)
+    p = str(tmp_path / "a.tif")
+    Image.fromarray(arr).save(p)
+    ring = np.zeros((3, 2, 40, 56), np.uint16)
+    assert common.read_plane_into(p, ring[1, 0]) and np.array_equal(ring[1, 0], arr) and not ring[1, 1].any()
+    assert not common.read_plane_into(p, np.zeros((40, 57), np.uint16))               # shape differs
+    assert not common.read_plane_into(p, np.zeros((40, 56), np.float32))              # dtype differs
+    assert not common.read_plane_into(p, np.zeros((40, 112), np.uint16)[:, ::2])      # not contiguous
+    q = str(tmp_path / "lzw.tif")
+    Image.fromarray(arr).save(q, compression="tiff_lzw")
+    assert not common.read_plane_into(q, ring[0, 0]) and not ring[0, 0].any()
+    q8 = str(tmp_path / "u8.tif")
+    Image.fromarray(arr.astype(np.uint8)).save(q8)
+    assert not common.read_plane_into(q8, ring[0, 0])
