@@ -93,16 +93,20 @@ class ShmTableRing:
             self.mine_t = mem.register_host(self.maps[self.rank], self.mine)   # page-locked: the D2H into it is asynchronous
         except (OSError, RuntimeError):
             self.ok = False
-        self.ok = bool(mem.all_reduce_max(0 if self.ok else 1, dist) == 0)     # every rank, or none
-        dist.barrier()
+        dist.barrier()                            # every rank's segment exists (or its creation failed)
         if self.ok and self.rank == self.dst:
-            for r in range(self.world):
-                if r != self.rank:
-                    fd = os.open(f"{self.base}_{r}", os.O_RDWR)
-                    try:
-                        self.maps[r] = mmap.mmap(fd, self.size)
-                    finally:
-                        os.close(fd)
+            try:
+                for r in range(self.world):
+                    if r != self.rank:
+                        fd = os.open(f"{self.base}_{r}", os.O_RDWR)
+                        try:
+                            self.maps[r] = mmap.mmap(fd, self.size)
+                        finally:
+                            os.close(fd)
+            except OSError:                       # a rank on another host, or a segment that could not be made
+                self.ok = False
+        self.ok = bool(mem.all_reduce_max(0 if self.ok else 1, dist) == 0)     # every rank, or none
+        if self.ok and self.rank == self.dst:
             self.segs = [np.frombuffer(self.maps[r], dtype=np.uint8) for r in range(self.world)]
             self.heads = [sg[: self.DATA_OFF].view(np.int64) for sg in self.segs]
             self.next = [0] * self.world          # per producer: the next step expected
