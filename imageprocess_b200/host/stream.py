@@ -14,6 +14,7 @@ only decode (PIL releases the GIL while it reads and decompresses), the device c
 Frames are decoded per batch, never all up front (a long time-lapse does not fit host RAM:
 ADVICE round 1); batches keep the caller's item order.
 """
+import os
 import time
 from concurrent.futures import ThreadPoolExecutor
 
@@ -34,6 +35,9 @@ class FrameStream:
         # slots 1 and 2 are pinned while the pool already decodes into slot 0)
         self.pin = [None] * self.depth
         self.dev = [None] * self.depth
+        if os.environ.get("IPB_STREAM_EAGER"):               # measurement switch: the whole ring up front
+            self.pin = [self.mem.pinned(shape, np.uint16) for _ in range(self.depth)]
+            self.dev = [self.mem.empty(shape, np.uint16) for _ in range(self.depth)]
         self.pool = ThreadPoolExecutor(max_workers=max(1, int(decode_threads)))
         self.timing = {"decode_s": 0.0, "wait_decode_s": 0.0, "batches": 0, "frames": 0,
                        "submit_s": 0.0, "collect_s": 0.0, "construct_s": 0.0}     # host seconds by phase
@@ -112,6 +116,8 @@ class FrameStream:
             computed[slot].record()
             inflight.append((pos, tk))
             self.timing["submit_s"] += time.perf_counter() - t1
+            if b == 0:
+                self.timing["first_submit_s"] = time.perf_counter() - t1      # eager step: workspace allocations, module load
             self.timing["batches"] += 1
             self.timing["frames"] += n
             start_decode(b + 2)
