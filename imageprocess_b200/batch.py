@@ -58,6 +58,13 @@ class _Arena:
         return base_ptr + self.sections[name][0]
 
 
+def _copy_records(a):
+    """Private copy of a structured array by bytes (numpy copies structured dtypes field by field:
+    1 ms for the 1.5 MB adhesion table of a step against 0.1 ms for the same bytes)."""
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint8).copy().view(a.dtype).reshape(a.shape)
+
+
 class _Plan:
     """Host tables + sizes of one batch layout (see FrameBatchJob._plan_for)."""
     pass
@@ -954,7 +961,7 @@ class FrameBatchJob:
         copying 8 steps x N ranks of tables in one go stalls the destination rank's submit loop for
         ~6 ms per rank and group, which is what made N ranks slower than one -- profiles/README.md)."""
         out = []
-        keep = (lambda a: a.copy()) if copy else (lambda a: a)
+        keep = _copy_records if copy else (lambda a: a)
         if self._shm is not None:
             # shared-memory ring: whatever became final since the last call, read in place.  The views are
             # valid until the NEXT call of gathered() / finish(), which releases them to their producers
@@ -1105,7 +1112,7 @@ class FrameBatchJob:
         if pl.need_mpl:
             res.area = OV("m_area")[:NU].copy()[pl.uidx] if NR else np.zeros(0, np.uint32)
             self.n_roi_px = int(res.area.sum())
-        so = OV("stat_out")[:pl.n_out].copy().reshape(NR, pl.rpr) if pl.n_out else np.zeros((NR, 0), dtype=STAT_OUT)
+        so = _copy_records(OV("stat_out")[:pl.n_out]).reshape(NR, pl.rpr) if pl.n_out else np.zeros((NR, 0), dtype=STAT_OUT)
         if "fret" in st:
             res.fret_stat = so[:, 0:3]
         if "int" in st:
@@ -1114,7 +1121,7 @@ class FrameBatchJob:
             comp_off = OV("comp_off")[: NR + 1].copy()
             res.fa_comp_off = comp_off
             total = int(comp_off[-1]) if tk.fa_ran else 0
-            res.fa_comps = tk.pc_np[: COMP.itemsize * total].view(COMP).copy() if total else np.zeros(0, dtype=COMP)
+            res.fa_comps = tk.pc_np[: COMP.itemsize * total].copy().view(COMP) if total else np.zeros(0, dtype=COMP)
         return res
 
     def run(self, planes, polys_per_frame, full_hist=False, _pos=None):
@@ -1293,29 +1300,30 @@ FA_CATS = ("OK", "Large", "Small")
 
 def fa_table(res, cfg):
     """Vectorised per-adhesion table with the reference's dtypes (FA_Analyzer.py:166-193):
-    area float64, mean float32, integrated densities float64, centroid float64."""
+    area float64, mean float32, integrated densities float64, centroid float64.  Per-crop values are
+    spread with np.repeat (fancy indexing and boolean-mask stores cost 2-3x as much at ~50 k rows)."""
     comps, off = res.fa_comps, res.fa_comp_off
     n = comps.shape[0]
-    crop = np.repeat(np.arange(res.n_rois), np.diff(off)) if n else np.zeros(0, dtype=np.int64)
-    label = (np.arange(n) - off[crop] + 1) if n else np.zeros(0, dtype=np.int64)
+    counts = np.diff(off)
+    crop = np.repeat(np.arange(res.n_rois), counts) if n else np.zeros(0, dtype=np.int64)
+    label = (np.arange(n) - np.repeat(off[:-1], counts) + 1) if n else np.zeros(0, dtype=np.int64)
     area = comps["area"].astype(np.float64)
     with np.errstate(invalid="ignore", divide="ignore"):
         mean_raw = (comps["sum_i"].astype(np.float64) / area).astype(np.float32)
         cy = comps["sum_y"].astype(np.float64) / area
         cx = comps["sum_x"].astype(np.float64) / area
-    frame = res.frame[crop] if n else np.zeros(0, dtype=np.int32)
-    bg = res.fa_stats[frame, 2].astype(np.float32) if n else np.zeros(0, dtype=np.float32)
+    frame = np.repeat(res.frame, counts) if n else np.zeros(0, dtype=np.int32)
+    bg = np.repeat(res.fa_stats[res.frame, 2].astype(np.float32), counts) if n else np.zeros(0, dtype=np.float32)
     if cfg.get("subtract_bg", True):
         mean_corr = np.maximum(np.float32(0), mean_raw - bg)
     else:
         mean_corr = mean_raw
-    cat = np.zeros(n, dtype=np.int8)                         # 0 OK, 1 Large, 2 Small
-    cat[area > cfg["max_px"]] = 1
-    cat[area < cfg["min_px"]] = 2
-    return {"crop": crop, "frame": frame, "cell_id": res.roi[crop] if n else np.zeros(0, np.int32),
+    cat = np.where(area < cfg["min_px"], np.int8(2), (area > cfg["max_px"]).view(np.int8))      # 0 OK, 1 Large, 2 Small
+    return {"crop": crop, "frame": frame, "cell_id": np.repeat(res.roi, counts) if n else np.zeros(0, np.int32),
             "label": label, "cat": cat, "area": area, "mean_raw": mean_raw, "mean_corr": mean_corr,
             "int_den_raw": mean_raw.astype(np.float64) * area, "int_den_corr": mean_corr.astype(np.float64) * area,
-            "cy": cy, "cx": cx, "bg": bg, "thr": res.fa_stats[frame, 3].astype(np.float32) if n else bg}
+            "cy": cy, "cx": cx, "bg": bg,
+            "thr": np.repeat(res.fa_stats[res.frame, 3].astype(np.float32), counts) if n else bg}
 
 
 def fa_items(res, cfg, contours=None):
