@@ -242,7 +242,10 @@ def run_ours(args):
     eng = ipb.engine(f"cuda:{local}")
     F = args.frames
     frames, polys = make_frames(F, seed=1234 + 1000 * rank)
-    polys_pf = [polys] * F
+    polys_pf = [polys] * F              # a time-lapse stage: every frame carries the stage's ROI list (one rasterisation per step)
+    if args.per_frame_rois:             # every frame its own ROI list (vertices shifted by a frame-dependent sub-pixel offset):
+        polys_pf = [[np.asarray(P, dtype=float) + np.array([0.25 * (f % 4), 0.125 * (f // 4 % 8)]) for P in polys]
+                    for f in range(F)]  # F x 24 polygons rasterised per step instead of 24
     shape = (F, 2, H, W)
     pinned_np, pinned_t = eng.mem.pinned(shape, np.uint16)
     pinned_np[...] = frames
@@ -400,7 +403,7 @@ def run_ours(args):
             "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16/f32", "data": "synthetic",
-            "config": workload_config(F),
+            "config": dict(workload_config(F), **({"rois": "one ROI list per frame (rasterised every step)"} if args.per_frame_rois else {})),
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(frames.nbytes),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk.summary()}
@@ -647,6 +650,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU")
+    ap.add_argument("--per-frame-rois", action="store_true",
+                    help="give every frame of the step its own ROI list (default: one list per step, a time-lapse stage)")
     ap.add_argument("--lag", type=int, default=2, help="steps in flight before a step's tables are unpacked")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
