@@ -459,6 +459,7 @@ class FrameBatchJob:
             mr = m_rect[uidx]
             rw, rh = (mr[:, 2] - mr[:, 0]).astype(np.int64), (mr[:, 3] - mr[:, 1]).astype(np.int64)
             pl.rf_stride = int(min(2 * ((rw + 16) * rh).max() + 16384, 1 << 19))   # words per CTA: see ipb_roi_stats_fused
+            pl.rf_max_w, pl.rf_max_h = int(rw.max()), int(rh.max())             # what ipb_roi_stats_fused_sizes is asked with
 
         passes = ops.plane_passes(hist_jobs)
         pl.n_passes = passes.shape[0]

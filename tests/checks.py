@@ -1196,3 +1196,44 @@ def check_fa_row_refetch(eng):
 
 
 RASTER_CHECKS.append(check_fa_row_refetch)
+
+
+def check_workspace_queries(eng):
+    """SURVEY.md 8(b) `ipb_*_workspace_bytes`: the library's size queries (include/ipb200.h, "workspace
+    sizes") give exactly the buffer sizes the batch engine allocates for a real plan, so a caller in
+    another language that sizes its buffers from the header alone runs the same launches."""
+    from imageprocess_b200 import batch, ops
+    frames = [small_scene(50 + s, H=128, W=160, n_cells=3, blobs=5) for s in range(2)]
+    planes = np.stack([np.stack([d, a]) for d, a, _ in frames])
+    polys = [fr[2] for fr in frames]
+    fret_p = {"bg_scope": "full", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False, "donor_p": 1.0,
+              "fret_p": 1.0, "clip_neg": True, "eps_percentile": 1.0, "ratio_mode": "Donor/FRET"}
+    task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": True, "bg_stride": 4, "percentile": 1.0,
+            "per_channel_p": False, "ch_p_map": {}}
+    fa = {"alpha": 2.0, "min_area_um": 0.05, "max_area_um": 5.0, "close_radius": 1, "subtract_bg": True}
+    job = batch.FrameBatchJob(eng, planes.shape, stages=("fret", "int", "fa"), fret_p=fret_p, int_task=task,
+                              fa_params=fa, fa_px=0.112, want_labels=True)
+    job.run(eng.mem.from_host(planes), polys)
+    pl = job._plan_for(polys)
+    lib = eng.lib
+    c = pl.fa_crops
+    wh = np.ascontiguousarray(np.stack([c["w"], c["h"]], axis=1), dtype=np.int32)
+    got = lib.sizes("ipb_fa_segment_sizes", 9, int(pl.NR), wh.ctypes.data, 1)
+    assert got == [4 * pl.fa_words, 4 * pl.total_px, 4 * pl.total_rows, 4 * pl.NR, 4 * (pl.NR + 1), pl.comp_cap,
+                   ops.COMP.itemsize * pl.comp_cap, 4 * pl.total_px, pl.total_rows], got
+    assert lib.sizes("ipb_fa_segment_sizes", 9, int(pl.NR), wh.ctypes.data, 0)[7] == 0          # no label map wanted
+    assert pl.NF > 0
+    n_sms = eng.n_sms()
+    # the fused ROI statistics: the query for the widest and the tallest ROI rect covers the plan's per-CTA list stride
+    got = lib.sizes("ipb_roi_stats_fused_sizes", 6, int(pl.NR), int(pl.NF), pl.rf_max_w, pl.rf_max_h, n_sms)
+    assert got[1] == ops.RF_CTAS_PER_SM * n_sms and got[2] == 4 * got[0] * got[1], got
+    assert pl.rf_stride <= got[0] == min(2 * (pl.rf_max_w + 16) * pl.rf_max_h + 16384, 1 << 19), (got[0], pl.rf_stride)
+    assert got[3:] == [8, max(pl.NR, 1), max(pl.NF, 1)], got
+    got = lib.sizes("ipb_hist_select_sizes", 5, int(pl.NH), int(pl.NQ))
+    assert got == [4 * ops.PQ_WIN * pl.NH, ops.HIST_WIN.itemsize * pl.NH, 8 * pl.NH, 32 * pl.NH, ops.Q_OUT.itemsize * pl.NQ], got
+    got = lib.sizes("ipb_hist_sizes", 3, int(pl.NH), planes.shape[2], 1)
+    assert got == [4 * 65536 * pl.NH, 32 * pl.NH, 8 * planes.shape[2] * pl.NH], got
+    assert lib.sizes("ipb_hist_sizes", 3, int(pl.NH), planes.shape[2], 0)[2] == 0
+
+
+RASTER_CHECKS.append(check_workspace_queries)
