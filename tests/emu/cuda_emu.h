@@ -10,7 +10,10 @@
 // x86-64 context switch) scheduled round-robin on one OS thread.  __syncthreads() and
 // the warp collectives yield until all participants arrived, so barrier/shuffle
 // semantics are exact for converged code; atomics are plain read-modify-writes.
-// Data races are NOT detected (use compute-sanitizer on the GPU for that).
+// Data races are not detected as such (use compute-sanitizer on the GPU for that), but the order in which
+// the threads of a block (and the blocks of a grid) run is selectable -- IPB_EMU_ORDER = forward | reverse |
+// random[:seed], each optionally with ":preempt" (a thread yields after every atomic) -- and correctly
+// synchronised kernels give identical results under all of them (tests/test_emu_orders.py).
 #pragma once
 #if !defined(__x86_64__)
 #error "cuda_emu.h: x86-64 only"
@@ -91,6 +94,7 @@ extern BlockCtx* g_blk;
 extern Fiber* g_cur;
 extern uint3_ g_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
+extern int g_preempt;
 
 extern "C" void emu_switch(void** from_sp, void* to_sp);
 void yield();
@@ -212,8 +216,10 @@ static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 }
 
 // ---------------------------------------------------------------- atomics (one OS thread)
+// With IPB_EMU_ORDER=...:preempt a thread gives up its turn right after every atomic, so the sections of
+// different threads interleave at their atomics instead of running one whole section after the other.
 #define EMU_ATOMIC_RMW(name, T, expr) \
-    static inline T name(T* a, T v) { T old = *a; *a = (expr); return old; }
+    static inline T name(T* a, T v) { T old = *a; *a = (expr); if (emu::g_preempt) emu::yield(); return old; }
 EMU_ATOMIC_RMW(atomicAdd, int, old + v)
 EMU_ATOMIC_RMW(atomicAdd, unsigned, old + v)
 EMU_ATOMIC_RMW(atomicAdd, unsigned long long, old + v)
@@ -242,7 +248,7 @@ EMU_ATOMIC_RMW(atomicExch, unsigned long long, v)
 EMU_ATOMIC_RMW(atomicExch, float, v)
 #undef EMU_ATOMIC_RMW
 template <typename T>
-static inline T atomicCAS(T* a, T cmp, T v) { T old = *a; if (old == cmp) *a = v; return old; }
+static inline T atomicCAS(T* a, T cmp, T v) { T old = *a; if (old == cmp) *a = v; if (emu::g_preempt) emu::yield(); return old; }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 
