@@ -167,6 +167,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>&
                             (unsigned)(lin_b / ((unsigned long long)grid.x * grid.y))};
         for (auto& w : b.warps) { w.arrived = w.departed = 0; }
         g_spin = 0;
+        std::memset(b.dyn_smem, 0xA5, dyn_smem);      // a block never finds its dynamic shared memory zeroed (or as the last block left it)
         run_block(b);
     }
     g_blk = nullptr;

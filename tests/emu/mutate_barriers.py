@@ -53,6 +53,8 @@ def run(so, names, order):
         return "timeout"
     if r.returncode == 0:
         return None
+    if r.returncode < 0:
+        return f"signal {-r.returncode}"                     # e.g. an index built from stale shared memory
     tail = (r.stderr.strip().splitlines() or ["?"])[-1]
     return "deadlock" if "deadlock" in r.stderr else ("assert" if "Assert" in r.stderr else tail[:60])
 
