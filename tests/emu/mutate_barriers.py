@@ -6,7 +6,7 @@ IPB_EMU_ORDER.  Output: one line per barrier with the orders under which a check
 reported a deadlock).  A barrier no order notices is either redundant or guards a hazard that needs true
 concurrency to show (the emulator runs one thread at a time) -- it stays in the kernel either way.
 
-    python tests/emu/mutate_barriers.py ipb_fa_smem.cuh check_fa_overflow check_fa_wide_crop
+    python tests/emu/mutate_barriers.py [--lines=119,121] ipb_fa_smem.cuh check_fa_overflow check_fa_wide_crop
 """
 import os
 import re
@@ -60,17 +60,21 @@ def run(so, names, order):
 
 
 def main():
-    fname, names = sys.argv[1], sys.argv[2:]
+    argv = sys.argv[1:]
+    only = None
+    if argv and argv[0].startswith("--lines="):            # restrict to these source lines (e.g. the ones a first run did not see)
+        only = {int(v) for v in argv.pop(0)[8:].split(",")}
+    fname, names = argv[0], argv[1:]
     tmp = tempfile.mkdtemp(prefix="ipb_mut_")
     try:
         csrc = os.path.join(tmp, "csrc")
         shutil.copytree(CSRC, csrc)
         src = open(os.path.join(CSRC, fname)).read().split("\n")
-        lines = [i for i, ln in enumerate(src) if re.search(r"__syncthreads\(\);", ln)]
+        lines = [i for i, ln in enumerate(src) if re.search(r"__syncthreads\(\);", ln) and (only is None or i + 1 in only)]
         so = os.path.join(tmp, "emu.so")
         build(csrc, so)
         base = [run(so, names, o) for o in ORDERS]
-        print(f"{fname}: {len(lines)} barriers; unmodified: {base}", flush=True)
+        print(f"{fname}: {len(lines)} barriers; checks: {' '.join(names)}; unmodified: {base}", flush=True)
         seen = {o: 0 for o in ORDERS}
         any_seen = 0
         for i in lines:

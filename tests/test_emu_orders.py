@@ -13,7 +13,7 @@ from tests import checks
 from tests.emu.emu_backend import NumpyMem, emu_lib
 
 ORDERS = ["reverse", "random:5:preempt"]
-FAST_CHECKS = [checks.check_edge_cases, checks.check_fa_overflow, checks.check_graph_replay,
+FAST_CHECKS = [checks.check_edge_cases, checks.check_fa_overflow, checks.check_fa_wide_crop, checks.check_graph_replay,
                checks.check_hist_select_paths, checks.check_combined_batch_shared_rois,
                checks.check_region_stats_ties, checks.check_region_stats_two_views, checks.check_region_stats_streaming,
                checks.check_rim_mask, checks.check_square_dilation, checks.check_region_moments,
