@@ -313,7 +313,7 @@ class FrameBatchJob:
             j["pattern"], j["k"], j["moments"] = PAT_STRIDE2D, 10, 0 if pl.fa_mom_from_fret else 1
             hidx["fa"] = sum(x.shape[0] for x in hist_jobs)
             hist_jobs.append(j)
-        hist_jobs = np.concatenate(hist_jobs) if hist_jobs else np.zeros(0, dtype=HIST_JOB)
+        hist_jobs = ops.check_hist_jobs(np.concatenate(hist_jobs)) if hist_jobs else np.zeros(0, dtype=HIST_JOB)
         NH = pl.NH = hist_jobs.shape[0]
         pl.has_ms = bool((hist_jobs["pattern"] == PAT_MASKED_STRIDE).any())
         pl.pq_ok = False             # set once the plane passes are known
@@ -463,7 +463,7 @@ class FrameBatchJob:
 
         passes = ops.plane_passes(hist_jobs)
         pl.n_passes = passes.shape[0]
-        pl.pq_ok = bool(pl.n_passes) and self.W % 8 == 0 and self.H * self.W >= self.pq_min_px and \
+        pl.pq_ok = bool(pl.n_passes) and self.W % 8 == 0 and self.W >= 16 and self.H * self.W >= self.pq_min_px and \
             ops.pq_servable(hist_jobs, passes)
         T.add("hist_jobs", HIST_JOB, max(NH, 1))
         T.add("passes", ops.PLANE_PASS, max(pl.n_passes, 1))

@@ -185,7 +185,8 @@ int ipb_hist_select(const uint16_t* planes, int H, int W, const void* jobs, int 
     IPB_REQUIRE(planes && jobs && passes && hist_win && win && cnt && stats && miss && H > 0 && W > 0,
                 "ipb_hist_select: bad argument");
     IPB_REQUIRE(n_q == 0 || (qjobs && qout), "ipb_hist_select: quantile jobs without buffers");
-    IPB_REQUIRE((W & 7) == 0 && (((size_t)planes) & 15) == 0, "ipb_hist_select: needs W %% 8 == 0 and 16-byte aligned planes");
+    IPB_REQUIRE((W & 7) == 0 && W >= 16 && (((size_t)planes) & 15) == 0,
+                "ipb_hist_select: needs W %% 8 == 0, W >= 16 and 16-byte aligned planes");    // W == 8: one unit per row has no 32-bit multiply-high constant
     int rc;
     const size_t smem = sizeof(unsigned) * IPB_PQ_SBINS;
     IPB_CUDA_TRY(cudaFuncSetAttribute(ipb_k_pq_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pq sample smem");

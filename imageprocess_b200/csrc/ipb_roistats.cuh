@@ -214,8 +214,10 @@ __device__ __forceinline__ void ipb_rs_walk_u16x8(const IpbRsCtx& c, F f) {
     const int k0 = c.x0 >> 3, s = c.x0 & 7;
     const unsigned nunits = (unsigned)(((c.x0 + c.w + 7) >> 3) - k0);
     const unsigned total = (unsigned)c.h * nunits;
-    const bool fastdiv = (unsigned long long)total * nunits < 0xffffffffull;
-    const unsigned magic = (unsigned)((0x100000000ull + nunits - 1) / nunits);
+    // row of a unit by one multiply-high; nunits == 1 (a rect inside ONE aligned 8-pixel column) has no 32-bit
+    // magic (2^32) and takes the division, as do rects too large for the exactness bound
+    const unsigned magic = (unsigned)((0x100000000ull + nunits - 1) / nunits);     // 0 for nunits == 1
+    const bool fastdiv = magic != 0u && (unsigned long long)total * nunits < 0xffffffffull;
     for (unsigned i0 = threadIdx.x; i0 < total; i0 += 4u * blockDim.x) {
         uint4 q[4];
         unsigned bits[4];

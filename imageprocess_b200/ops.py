@@ -178,7 +178,7 @@ def pq_servable(hist_jobs, passes):
                 roles.add("F")
             elif pat == PAT_STRIDE1D and k in (2, 4, 8) and "S" not in roles:
                 roles.add("S")
-            elif pat == PAT_STRIDE2D and k >= 1 and "P" not in roles:
+            elif pat == PAT_STRIDE2D and k >= 2 and "P" not in roles:
                 roles.add("P")
             else:
                 return False
@@ -202,10 +202,19 @@ class HistResult:
         self.hist, self.stats, self.n_jobs = hist, stats, n_jobs
 
 
+def check_hist_jobs(jobs):
+    """include/ipb200.h: the stride of a strided pattern is >= 2 (a stride of 1 is the FULL / MASKED pattern:
+    the kernels' multiply-high remainder has no 32-bit constant for k = 1)."""
+    strided = np.isin(jobs["pattern"], (PAT_STRIDE1D, PAT_STRIDE2D, PAT_MASKED_STRIDE))
+    if bool((strided & (jobs["k"] < 2)).any()):
+        raise ValueError("histogram job with a strided pattern and k < 2: use the FULL / MASKED pattern for a stride of 1")
+    return jobs
+
+
 def _engine_hist(self, planes, H, W, jobs, union=None, union_wpr=0):
     """jobs: structured array HIST_JOB.  Returns HistResult (device)."""
     mem = self.mem
-    jobs = np.ascontiguousarray(jobs, dtype=HIST_JOB)
+    jobs = check_hist_jobs(np.ascontiguousarray(jobs, dtype=HIST_JOB))
     n = jobs.shape[0]
     d_jobs = mem.from_host(jobs if n else np.zeros(1, HIST_JOB))
     hist = mem.empty((max(n, 1), 65536), np.uint32)

@@ -74,7 +74,7 @@ int ipb_rasterize_rois(int rule, int n_rois, const double* verts_xy, const int32
 typedef struct {
     int32_t plane;        /* plane index into planes[][H][W] (frame * C + channel) */
     int32_t pattern;      /* IPB_PAT_* */
-    int32_t k;            /* stride of the strided patterns */
+    int32_t k;            /* stride of the strided patterns, >= 2 (a stride of 1 is IPB_PAT_FULL / IPB_PAT_MASKED) */
     int32_t mask_frame;   /* frame index into union_bits (masked patterns) */
     int32_t moments;      /* != 0: also accumulate sum / sum of squares of ALL pixels */
     int32_t excl_plane1;  /* 1 + index of a second plane for the saturation filter, 0 = none */
@@ -100,7 +100,7 @@ int ipb_hist_planes(const uint16_t* planes, int H, int W, const void* jobs, int 
  * every wanted rank with overwhelming probability; one read of the plane counts the pixels below
  * the window in registers and histograms the pixels inside it (2048 bins); the plane's integer
  * moments and a sparse [::k, ::k] job (own window from the same sample) ride along.  Served roles per pass: one FULL job, one flat-stride job vals[::k] (k in {2, 4, 8}),
- * one [::k, ::k] job; W % 8 == 0.  *miss (zeroed by the caller) counts quantiles whose rank fell
+ * one [::k, ::k] job; W % 8 == 0 and W >= 16.  *miss (zeroed by the caller) counts quantiles whose rank fell
  * outside the window or whose pass cannot be served: the caller must then repeat with
  * ipb_hist_planes + ipb_hist_quantiles.  Replaces the np.percentile calls of bg_value
  * (Fluor_INT.py:464-485, fret_ratio_builder.py:314-330), pick_epsilon (fret_ratio_builder.py:338)

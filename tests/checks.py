@@ -1295,3 +1295,48 @@ def check_raster_adversarial(eng, n_polys=240, H=24, W=40):
 
 
 RASTER_CHECKS.append(check_raster_adversarial)
+
+
+def check_narrow_rois(eng):
+    """ROIs whose stored rect lies inside ONE aligned 8-pixel column (1 - 8 px wide), slivers across the
+    left and the top border, single pixels: found by fuzzing in round 2 -- the unit walks' multiply-high row
+    index has no 32-bit constant for one unit per row and returned row 0 for every unit, so such ROIs came
+    back with n pixels of value 0.  Intensity + FRET rows against the oracle, through the fused kernel's
+    rerun (tiny ROIs) and through the full-histogram kernels alone."""
+    from imageprocess_b200 import batch
+    rng = np.random.default_rng(12)
+    H, W = 72, 96
+    planes = np.stack([np.stack([rng.poisson(500, (H, W)), rng.poisson(300, (H, W))]).astype(np.uint16) for _ in range(2)])
+    box = lambda x0, y0, w, h: np.array([[x0 - 0.5, y0 - 0.5], [x0 + w - 0.5, y0 - 0.5], [x0 + w - 0.5, y0 + h - 0.5],
+                                         [x0 - 0.5, y0 + h - 0.5]])
+    polys = [[box(20, 9, 1, 1), box(33, 9, 2, 2), box(40, 5, 3, 60), box(49, 3, 6, 66), box(8, 30, 7, 30),
+              np.array([[-3.8, 43.8], [1.9, 55.0], [-4.9, 10.5]]),                      # sliver across the left border
+              box(88, 10, 7, 50)],                                                      # the last unit column of the frame
+             [np.array([[50.2, -4.0], [53.9, -3.0], [52.0, 9.5]]),                      # sliver across the top border
+              box(0, 0, 2, 70), box(64, 40, 8, 30), box(17, 20, 6, 3)]]
+    F = planes.shape[0]
+    fret_p = {"bg_scope": "full", "bg_mode": "percentile", "percentile": 1.0, "per_channel_p": False, "donor_p": 1.0,
+              "fret_p": 1.0, "clip_neg": False, "eps_percentile": 1.0, "ratio_mode": "Donor/FRET"}
+    task = {"bg_scope": "full", "bg_mode": "percentile", "clip_neg": False, "bg_stride": 1, "percentile": 50.0,
+            "per_channel_p": False, "ch_p_map": {}}
+    for fused in (True, False):
+        job = batch.FrameBatchJob(eng, planes.shape, stages=("fret", "int"), fret_p=fret_p, int_task=task)
+        job.fused_roi = fused
+        res = job.run(eng.mem.from_host(planes), polys)
+        rows_i, rows_f = batch.rows_intensity(res, F, [1, 2]), batch.rows_fret(res, F)
+        for f in range(F):
+            D, A = planes[f, 0].astype(np.float32), planes[f, 1].astype(np.float32)
+            with np.errstate(all="ignore"):
+                want = port.fret_process_pair(D, A, polys[f], fret_p)
+            assert len(rows_f[f]) == len(want["rows"]) == len(polys[f])
+            for g, w in zip(rows_f[f], want["rows"]):
+                assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"] > 0, (fused, f, g["roi"])
+                for k in ("ratio_median", "ratio_p5", "ratio_p95", "donor_median", "yfret_median"):
+                    assert g[k] == w[k], (fused, f, g["roi"], k, g[k], w[k])
+                for k in ("ratio_mean", "donor_mean", "yfret_mean"):
+                    assert close(g[k], w[k]), (fused, f, g["roi"], k, g[k], w[k])
+            wrows, wbg, _ = port.int_process_key({1: D.copy(), 2: A.copy()}, polys[f], None, task)
+            check_int_rows(rows_i[f], wrows, (1, 2))
+
+
+RASTER_CHECKS.append(check_narrow_rois)
