@@ -681,6 +681,16 @@ def check_rim_mask(eng):
         got = bits_to_bool(rim.host().reshape(1, H, wpr), H, W)[0]
         want = port.make_inside_rim_mask(union, rim_px)
         assert np.array_equal(got, want), rim_px
+    # A union WITHOUT any background pixel: scipy's EDT then measures from the virtual point
+    # (row -1, column 0) and the reference's rim is a quarter disc in the top-left corner; the device rim is empty.
+    full = eng.rasterize(geo.RULE_MPL, [geo.mpl_spec(np.array([[-2.0, -2.0], [W + 2.0, -2.0], [W + 2.0, H + 2.0], [-2.0, H + 2.0]]),
+                                                     (W, H))], (H, W), 1, want_union=True)
+    assert full.union_host()[0].all()
+    gm, R = ops.ball_gmax(ops.rim_d2max(5))
+    got = bits_to_bool(eng.region_dilate(ureg, full.union, gm, R, invert=True, and_pool=full.union).host().reshape(1, H, wpr), H, W)[0]
+    assert not got.any()
+    yy, xx = np.mgrid[0:H, 0:W]
+    assert np.array_equal(port.make_inside_rim_mask(np.ones((H, W), bool), 5), (yy + 1) ** 2 + xx ** 2 <= 25)
 
 
 def check_square_dilation(eng):
