@@ -1,0 +1,90 @@
+"""tests/fuzz/fuzz_nesprin2.py -- TEST INFRASTRUCTURE, run by hand (not collected by pytest), emulated build only.
+
+Nesprin2 builder (saturation filter, spectral correction, rim, annulus, per-ROI rows) against oracle.port.n2_process_pair on random scenes and parameters.  Known, documented divergence: the rim of a union that covers the whole frame.
+
+    python tests/fuzz/fuzz_nesprin2.py <first seed> <number of seeds>     (prints one FAIL line per seed that differs)
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np, time, math, traceback
+from imageprocess_b200.ops import Engine
+from imageprocess_b200 import nesprin2
+from imageprocess_b200.nesprin2 import bits_to_bool
+from tests.emu.emu_backend import NumpyMem, emu_lib
+from tests import checks
+from tests.checks import close, N2_BASE
+from oracle import port
+eng = Engine(emu_lib(), NumpyMem())
+seed0 = int(sys.argv[1]); n = int(sys.argv[2])
+bad = 0; t0 = time.time(); cond = 0
+for seed in range(seed0, seed0 + n):
+    rng = np.random.default_rng(seed)
+    H = int(rng.integers(24, 110)); W = int(rng.choice([8 * int(rng.integers(4, 20)), int(rng.integers(25, 150))]))
+    F = int(rng.integers(1, 3))
+    planes = []
+    for f in range(F):
+        d = rng.poisson(float(rng.choice([200, 900, 5000])), (H, W)).astype(np.int64)
+        a = rng.poisson(float(rng.choice([150, 600, 3000])), (H, W)).astype(np.int64)
+        if rng.random() < 0.5:
+            y, x = int(rng.integers(0, H - 8)), int(rng.integers(0, W - 8))
+            d[y:y + 20, x:x + 30] += 3000; a[y:y + 20, x:x + 30] += 2000
+        d = np.minimum(d, 65535).astype(np.uint16); a = np.minimum(a, 65535).astype(np.uint16)
+        d[rng.random((H, W)) < 0.003] = 65535; a[rng.random((H, W)) < 0.003] = 65535
+        ao = (0.3 * a + rng.poisson(50, d.shape)).astype(np.uint16)
+        planes.append(np.stack([d, a, ao]))
+    planes = np.stack(planes)
+    polys = []
+    for f in range(F):
+        pl = []
+        for k in range(int(rng.integers(1, 4))):
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                nv = int(rng.integers(3, 8)); P = np.stack([rng.uniform(-6, W + 6, nv), rng.uniform(-6, H + 6, nv)], axis=1)
+            elif kind == 1:
+                x0, y0 = float(rng.integers(0, W - 3)), float(rng.integers(0, H - 3)); w, h = float(rng.integers(1, 9)), float(rng.integers(1, 30))
+                P = np.array([[x0 - .5, y0 - .5], [x0 + w - .5, y0 - .5], [x0 + w - .5, y0 + h - .5], [x0 - .5, y0 + h - .5]])
+            elif kind == 2:
+                cx, cy, r = rng.uniform(10, W - 10), rng.uniform(10, H - 10), rng.uniform(4, 30)
+                t = np.sort(rng.uniform(0, 2 * np.pi, int(rng.integers(5, 14)))); P = np.stack([cx + r * np.cos(t), cy + r * np.sin(t)], axis=1)
+            else:
+                P = np.array([[0.0, 0.0], [W - 1.0, 0.0], [W - 1.0, H - 1.0], [0.0, H - 1.0]])
+            pl.append(P)
+        polys.append(pl)
+    p = dict(N2_BASE)
+    p.update({"annulus_on": bool(rng.integers(0, 2)), "ann_in_um": float(rng.choice([0.0, 0.3, 0.5, 1.2])), "ann_out_um": float(rng.choice([0.5, 1.4, 2.5])),
+              "rim_um": float(rng.choice([0.0, 0.3, 1.12, 2.0])), "clip_neg": bool(rng.integers(0, 2)), "ratio_mode": str(rng.choice(["FRET/Donor", "Donor/FRET"])),
+              "sat_filter_on": bool(rng.integers(0, 2)), "sat_threshold": float(rng.choice([30000.0, 65535.0, 4000.0])),
+              "clip_ratio_on": bool(rng.integers(0, 2)), "clip_ratio_max": float(rng.choice([3.0, 10.0, 0.8])),
+              "bg_scope": str(rng.choice(["full", "roi_union", "annulus"])), "use_spectral": bool(rng.integers(0, 2)),
+              "alpha": float(rng.choice([0.0, 0.12, 0.5])), "beta": float(rng.choice([0.0, 0.05])), "g_factor": float(rng.choice([1.0, 1.1, 0.7])),
+              "eps_percentile": float(rng.choice([0.0, 1.0, 5.0])), "per_channel_p": bool(rng.integers(0, 2)), "donor_p": float(rng.choice([0.5, 1.0, 5.0])), "fret_p": float(rng.choice([1.0, 3.0]))})
+    aonly_ch = 2 if rng.random() < 0.5 else None
+    try:
+        with np.errstate(all="ignore"):
+            wants = [port.n2_process_pair(planes[f, 0].astype(np.float32), planes[f, 1].astype(np.float32), polys[f], p,
+                                          Aonly=planes[f, 2].astype(np.float32) if aonly_ch is not None else None) for f in range(F)]
+    except Exception as e:
+        print("oracle raises", seed, type(e).__name__, str(e)[:100]); continue
+    try:
+        out = nesprin2.nesprin2_batch(eng, eng.mem.from_host(planes), planes.shape, polys, p, donor_ch=0, acc_ch=1, aonly_ch=aonly_ch)
+        imgs = out["images"].host(); wpr = (W + 31) // 32
+        rim = bits_to_bool(out["rim"].host().reshape(F, H, wpr), H, W)
+        for f in range(F):
+            want = wants[f]
+            assert np.float32(out["eps"][f]) == np.float32(want["eps"]), ("eps", f, out["eps"][f], want["eps"])
+            for i, k in enumerate(("R_full", "R_alt", "Dcorr", "Acorr")):
+                assert np.array_equal(imgs[i, f], want[k], equal_nan=True), (k, f)
+            assert np.array_equal(rim[f], want["rim_mask"]), ("rim", f)
+            assert len(out["rows_per_frame"][f]) == len(want["rows"]), ("nrows", f)
+            for g, w in zip(out["rows_per_frame"][f], want["rows"]):
+                assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"], ("area", g["area_px"], w["area_px"])
+                for k in ("ratio_median", "ratio_p5", "ratio_p95"):
+                    assert (g[k] == w[k]) or (math.isnan(g[k]) and math.isnan(w[k])), (f, g["roi"], k, g[k], w[k])
+                for k in ("ratio_mean", "ratio_std", "ratio_FoverD_mean", "ratio_DoverF_mean", "donor_mean", "fret_mean"):
+                    ok = close(g[k], w[k]) or (math.isnan(g[k]) and math.isnan(w[k]))
+                    if not ok and close(g[k], w[k], 2e-4): cond += 1; ok = True      # conditioning of float32 sums: counted, looked at separately
+                    assert ok, (f, g["roi"], k, g[k], w[k])
+    except Exception as e:
+        bad += 1
+        print("FAIL seed", seed, (H, W, F), {k: p[k] for k in ("annulus_on", "ann_in_um", "ann_out_um", "rim_um", "clip_neg", "ratio_mode", "sat_filter_on", "sat_threshold", "clip_ratio_on", "clip_ratio_max", "bg_scope", "use_spectral")}, "aonly", aonly_ch, type(e).__name__, str(e)[:200], flush=True)
+print("done", seed0, n, "bad", bad, "loose-mean", cond, round(time.time() - t0, 1), flush=True)
