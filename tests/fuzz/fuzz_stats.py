@@ -2,7 +2,7 @@
 
 FRET + ROI-intensity in one FrameBatchJob against the oracle: adversarial value distributions (constant, two-valued, saturated, uniform, ramps), random ROIs (also off-frame), random scopes / strides / percentiles / hist-mode.  Found the narrow-ROI bug fixed in round 2 (tests/checks.py: check_narrow_rois).
 
-    python tests/fuzz/fuzz_stats.py <first seed> <number of seeds>     (prints one FAIL line per seed that differs)
+    python tests/fuzz/fuzz_stats.py <first seed> <number of seeds> [big]     (prints one FAIL line per seed that differs)
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -14,8 +14,19 @@ from tests import checks
 from tests.checks import close, check_int_rows
 from oracle import port
 eng = Engine(emu_lib(), NumpyMem())
-seed0 = int(sys.argv[1]); n = int(sys.argv[2])
+seed0 = int(sys.argv[1]); n = int(sys.argv[2]); BIG = len(sys.argv) > 3 and sys.argv[3] == "big"
 bad = 0; t0 = time.time(); stats = {"miss": 0, "fallback": 0}
+
+def soft_close(a, b, scale):
+    """1e-5 relative, or -- for sums that cancel (mean ~ 0 with clip_neg off) and for constant regions, where numpy's
+    float32 pairwise sums carry the rounding noise of the VALUES -- 1e-5 of the values' scale.  Counted in stats."""
+    if (math.isnan(a) and math.isnan(b)) or close(a, b):
+        return True
+    if abs(a - b) <= 1e-5 * scale:
+        stats["scale_tol"] = stats.get("scale_tol", 0) + 1
+        return True
+    return False
+
 
 def plane(rng, H, W):
     kind = int(rng.integers(0, 8))
@@ -30,11 +41,23 @@ def plane(rng, H, W):
         p = rng.poisson(200, (H, W)).astype(np.uint16); p[: H // 2] += 30000; return p
     return (rng.poisson(100, (H, W)) * int(rng.integers(1, 600))).clip(0, 65535).astype(np.uint16)
 
+
+def patchy(rng, H, W):
+    """Blocks of different distributions: a ROI sees mixtures with heavy ties around its quantile ranks."""
+    p = plane(rng, H, W)
+    for _ in range(int(rng.integers(0, 4))):
+        y0, x0 = int(rng.integers(0, H)), int(rng.integers(0, W)); y1, x1 = int(rng.integers(y0, H + 1)), int(rng.integers(x0, W + 1))
+        p[y0:y1, x0:x1] = plane(rng, H, W)[y0:y1, x0:x1]
+    return p
+
 for seed in range(seed0, seed0 + n):
     rng = np.random.default_rng(seed)
-    H = int(rng.integers(16, 120)); W = int(rng.choice([8 * int(rng.integers(3, 24)), int(rng.integers(17, 190))]))
+    if BIG:            # ROIs of thousands of pixels: the fused kernel's sampled-window path proper
+        H = int(rng.integers(150, 300)); W = int(rng.choice([8 * int(rng.integers(20, 48)), int(rng.integers(150, 380))]))
+    else:
+        H = int(rng.integers(16, 120)); W = int(rng.choice([8 * int(rng.integers(3, 24)), int(rng.integers(17, 190))]))
     F = int(rng.integers(1, 3))
-    planes = np.stack([np.stack([plane(rng, H, W), plane(rng, H, W)]) for _ in range(F)])
+    planes = np.stack([np.stack([patchy(rng, H, W), patchy(rng, H, W)]) for _ in range(F)])
     polys = []
     for f in range(F):
         pl = []
@@ -72,12 +95,24 @@ for seed in range(seed0, seed0 + n):
                 for k in ("ratio_median", "ratio_p5", "ratio_p95", "donor_median", "yfret_median"):
                     assert g[k] == w[k] or (math.isnan(g[k]) and math.isnan(w[k])), (f, k, g[k], w[k])
                 for k in ("ratio_mean", "ratio_std", "donor_mean", "yfret_mean"):
-                    assert close(g[k], w[k]) or (math.isnan(g[k]) and math.isnan(w[k])), (f, k, g[k], w[k])
+                    pre = k.split("_")[0]
+                    scale = abs(w[pre + "_median"]) + (abs(w["ratio_p5"]) + abs(w["ratio_p95"]) if pre == "ratio" else 0.0)
+                    assert soft_close(g[k], w[k], scale), (f, k, g[k], w[k])
             if polys[f]:
                 with np.errstate(all="ignore"):
                     wrows, wbg, _ = port.int_process_key({1: D.copy(), 2: A.copy()}, polys[f], None, task)
                 assert res.int_bg[f, 0] == wbg[1]["bg"] and res.int_bg[f, 1] == wbg[2]["bg"], ("bg", f, res.int_bg[f], wbg)
-                check_int_rows(rows_i[f], wrows, (1, 2))
+                assert len(rows_i[f]) == len(wrows)
+                for g, w in zip(rows_i[f], wrows):
+                    assert g["roi"] == w["roi"] and g["area_px"] == w["area_px"]
+                    for ch in (1, 2):
+                        for k in ("median", "p5", "p95", "vmin", "vmax", "npx"):
+                            a, b = g[f"ch{ch}_{k}"], w[f"ch{ch}_{k}"]
+                            assert a == b or (math.isnan(a) and math.isnan(b)), (f, g["roi"], ch, k, a, b)
+                        scale = max(abs(w[f"ch{ch}_vmin"]), abs(w[f"ch{ch}_vmax"])) if w[f"ch{ch}_npx"] else 0.0
+                        for k in ("mean", "std"):
+                            assert soft_close(g[f"ch{ch}_{k}"], w[f"ch{ch}_{k}"], scale), (f, g["roi"], ch, k, g[f"ch{ch}_{k}"], w[f"ch{ch}_{k}"])
+                        assert soft_close(g[f"ch{ch}_vsum"], w[f"ch{ch}_vsum"], scale * max(w[f"ch{ch}_npx"], 1)), (f, g["roi"], ch, "vsum")
             else:
                 assert rows_i[f] == []
     except Exception as e:
