@@ -2,7 +2,7 @@
 
 FA chain (threshold, size filter, closing, labelling, per-adhesion rows, outlines) on all three device paths against oracle.port.analyze_fa_crop: random crop sizes (widths at word boundaries), noise densities, ROI shapes, parameters.
 
-    python tests/fuzz/fuzz_fa.py <first seed> <number of seeds>     (prints one FAIL line per seed that differs)
+    python tests/fuzz/fuzz_fa.py <first seed> <number of seeds> [big]     (prints one FAIL line per seed that differs)
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -11,12 +11,15 @@ from imageprocess_b200.ops import Engine
 from tests.emu.emu_backend import NumpyMem, emu_lib
 from tests import checks
 eng = Engine(emu_lib(), NumpyMem())
-seed0 = int(sys.argv[1]); n = int(sys.argv[2])
+seed0 = int(sys.argv[1]); n = int(sys.argv[2]); BIG = len(sys.argv) > 3 and sys.argv[3] == "big"
 bad = 0
 t0 = time.time()
 for seed in range(seed0, seed0 + n):
     rng = np.random.default_rng(seed)
-    H = int(rng.integers(8, 90)); W = int(rng.choice([int(rng.integers(8, 140)), 32, 64, 96, 33, 65, 31, 63, 128]))
+    if BIG:        # crops beyond the shared-memory kernel's limits (4096 words, 8192 runs, 512 adhesions): flagged, finished in global memory
+        H = int(rng.integers(150, 420)); W = int(rng.choice([int(rng.integers(200, 560)), 256, 512, 257, 511]))
+    else:
+        H = int(rng.integers(8, 90)); W = int(rng.choice([int(rng.integers(8, 140)), 32, 64, 96, 33, 65, 31, 63, 128]))
     dens = float(rng.choice([0.02, 0.1, 0.3, 0.5, 0.7]))
     d = rng.poisson(500, (H, W)).astype(np.int64)
     m = rng.random((H, W)) < dens
@@ -48,7 +51,7 @@ for seed in range(seed0, seed0 + n):
               "max_area_um": float(rng.choice([40.0, 400.0])) * 0.112 ** 2, "close_radius": int(rng.integers(0, 6)), "subtract_bg": bool(rng.integers(0, 2))}
     for path in (1, 2, 3):
         try:
-            checks.check_fa_batch(eng, params, fa_path=path, frames=[(d, a, polys)], contour_stride=7)
+            checks.check_fa_batch(eng, params, fa_path=path, frames=[(d, a, polys)], contour_stride=97 if BIG else 7)
         except Exception as e:
             bad += 1
             print("FAIL seed", seed, "path", path, H, W, params, type(e).__name__, str(e)[:200], flush=True)
