@@ -32,8 +32,16 @@ def order(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("fn", FAST_CHECKS, ids=lambda f: f.__name__)
-def test_checks_under_other_thread_orders(eng, order, fn):
+# the slow checks run under ONE of the two orders each (alternating), the quick ones under both
+SLOW = {"check_combined_batch_shared_rois", "check_fa_overflow", "check_fa_wide_crop", "check_hist_select_paths",
+        "check_edge_cases", "check_segment_inside_polygon"}
+CASES = [(o, fn) for k, fn in enumerate(FAST_CHECKS) for i, o in enumerate(ORDERS)
+         if fn.__name__ not in SLOW or i == k % 2]
+
+
+@pytest.mark.parametrize("which,fn", CASES, ids=lambda v: v if isinstance(v, str) else v.__name__)
+def test_checks_under_other_thread_orders(eng, monkeypatch, which, fn):
+    monkeypatch.setenv("IPB_EMU_ORDER", which)
     fn(eng)
 
 
