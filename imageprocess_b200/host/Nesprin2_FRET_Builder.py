@@ -16,7 +16,8 @@ import numpy as np
 
 from .. import nesprin2
 from . import common
-from ._fretnames import build_pairs_by_channel, load_roi_polys, parse_tokens  # noqa: F401
+from ._fretnames import build_pairs_by_channel, load_roi_polys  # noqa: F401
+from ._fretnames import parse_tokens_delimited as parse_tokens  # noqa: F401  (this script's own grammar, :292-307)
 from .common import ensure_dir, list_tifs
 
 DEFAULT_P = {
@@ -50,7 +51,7 @@ def run_pipeline(p, eng=None, log=print, frames_per_batch=16):
     out_root = (p.get("out_root") or "").strip() or os.path.join(img_dir, "RES")
     timelapse = bool(p["timelapse"])
     donor_ch, fret_ch = int(p["donor_ch"]), int(p["fret_ch"])
-    pairs, _ = build_pairs_by_channel(list_tifs(img_dir), timelapse, donor_ch, fret_ch)
+    pairs, _ = build_pairs_by_channel(list_tifs(img_dir), timelapse, donor_ch, fret_ch, parse=parse_tokens)
     log(f"[info] pairs to process: {len(pairs)}")
     if not pairs:
         log("no matching (donor, fret) channel pairs")

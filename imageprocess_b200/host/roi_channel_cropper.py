@@ -13,7 +13,8 @@ import os
 
 from .. import roi_ops
 from . import common
-from ._fretnames import load_roi_polys, parse_tokens
+from ._fretnames import load_roi_polys
+from ._fretnames import parse_tokens_cropper as parse_tokens      # this script's own grammar (:211-252)
 from .common import ensure_dir, fmt_stage, fmt_time, list_tifs
 
 
@@ -41,7 +42,7 @@ def run_headless(img_dir, roi_dir, ch_select=1, low_cut=1.0, high_cut=1.0, gamma
         S = fmt_stage(s_num)
         t_code = fmt_time(t_num) if (timelapse and t_num is not None) else None
         keytag = f"{S}_{t_code}" if t_code is not None else S
-        polys = load_roi_polys(roi_dir, S, t_code, timelapse)
+        polys = load_roi_polys(roi_dir, S, t_code, timelapse, legacy=False)
         if not polys:
             log(f"[warn] ROI not found: {keytag}.json")
             continue

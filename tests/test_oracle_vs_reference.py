@@ -195,3 +195,58 @@ def test_segment_inside_polygon_matches_reference():
         g = port.segment_inside_polygon(img, poly, thr_param=par, min_area=40, tolerance=1.0, mode=mode)
         assert g[0] == w[0] and g[1] is None and w[1] is None
         assert np.array_equal(g[2], w[2]) and g[2].shape[0] >= 6
+
+
+# ------------------------------------------------------------------ file-name grammars
+def _adversarial_names():
+    S = ["S1", "S01", "s2", "S003", "S12", "S1234", "Stage1", "S", "S1a", "XS1", "S1S2", "S01 "]
+    T = ["", "_t0", "_t00", "_t003", "_T7", "_t12", "t3", "_time4", "_t", "_t1_t2", "_t1234", "-t5"]
+    C = ["", "_1", "_2", "_ch1", "_ch02", "_c3", "_C4", "_CH5", "_10", "_ch", "-1", "_1_2", "_DAPI", "_c1_extra", "_ch1234",
+         "_03_7"]
+    E = [".tif", ".TIF", ".tiff", ".png", ""]
+    names = [s + t + c + e for s in S for t in T for c in C for e in E]
+    return names + ["S01_t000_1.tif", "S01_t000_2.tif", "S1_t0.json", "S01.json", "image.tif", "S01_1.tif.bak", "S01__1.tif",
+                    "_S01_1.tif", "S01_t01_ch2_ch3.tif", "exp-S02-t07-c3.tif", "S02_t07_007.tif", "S02_t07_07.tif"]
+
+
+@needs_ref
+def test_name_grammars_match_reference():
+    """Every mirror parses file names with ITS script's regex set (the five sets differ): the mirrors' functions
+    against the unmodified reference functions on ~12 000 (name, time-lapse) pairs, exceptions included."""
+    from imageprocess_b200.host import Fluor_INT as mF, _fretnames as mN
+    ref = {n: refimport.load(n) for n in ("Fluor_INT", "fret_ratio_builder", "Nesprin2_FRET_Builder", "MOR_by_ROI",
+                                          "roi_channel_cropper")}
+
+    def cropper_ref(name, tl):
+        s, t = ref["roi_channel_cropper"].parse_stage_time(name, tl)
+        return s, t, ref["roi_channel_cropper"].detect_channel(name, timelapse=tl)
+
+    def cropper_ours(name, tl):
+        s, t, ch = mN.parse_tokens_cropper(name, tl)
+        return (f"S{s:02d}" if s is not None else None), (f"t{t:02d}" if t is not None else None), ch
+
+    pairs = [("Fluor_INT.parse_tokens", ref["Fluor_INT"].parse_tokens, mF.parse_tokens),
+             ("Fluor_INT.clean_base_for_save", ref["Fluor_INT"].clean_base_for_save, mF.clean_base_for_save),
+             ("fret_ratio_builder.parse_tokens", ref["fret_ratio_builder"].parse_tokens, mN.parse_tokens),
+             ("MOR_by_ROI.parse_tokens", ref["MOR_by_ROI"].parse_tokens, mN.parse_tokens),
+             ("Nesprin2_FRET_Builder.parse_tokens", ref["Nesprin2_FRET_Builder"].parse_tokens, mN.parse_tokens_delimited),
+             ("roi_channel_cropper.parse_stage_time + detect_channel", cropper_ref, cropper_ours)]
+    args = [(n, tl) for n in _adversarial_names() for tl in (False, True)]
+    for label, fr, fm in pairs:
+        diffs = []
+        for a in args:
+            try:
+                r = ("ok", fr(*a))
+            except Exception as e:          # noqa: BLE001  (the exception type is part of the behaviour)
+                r = ("raises", type(e).__name__)
+            try:
+                m = ("ok", fm(*a))
+            except Exception as e:          # noqa: BLE001
+                m = ("raises", type(e).__name__)
+            if r != m:
+                diffs.append((a, r, m))
+        assert not diffs, (label, len(diffs), diffs[:4])
+    # and the mirrors are wired to their own grammar
+    from imageprocess_b200.host import Nesprin2_FRET_Builder as mNe, roi_channel_cropper as mC, MOR_by_ROI as mM
+    assert mNe.parse_tokens is mN.parse_tokens_delimited and mC.parse_tokens is mN.parse_tokens_cropper
+    assert mM.parse_tokens is mN.parse_tokens
