@@ -250,3 +250,68 @@ def test_name_grammars_match_reference():
     from imageprocess_b200.host import Nesprin2_FRET_Builder as mNe, roi_channel_cropper as mC, MOR_by_ROI as mM
     assert mNe.parse_tokens is mN.parse_tokens_delimited and mC.parse_tokens is mN.parse_tokens_cropper
     assert mM.parse_tokens is mN.parse_tokens
+
+
+# ------------------------------------------------------------------ table writers
+class _NoExcel:
+    """Stands in for pandas.ExcelWriter where no Excel engine is installed: the reference's writers open it
+    unconditionally (Fluor_INT.py:754) -- only their CSV output is compared here."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+@needs_ref
+@pytest.mark.parametrize("timelapse", [False, True])
+def test_table_writers_match_reference(tmp_path, monkeypatch, timelapse):
+    """fluor_intensity_perROI.csv and nesprin2_fret_perROI.csv: the UNMODIFIED reference writers
+    (Fluor_INT.save_excel :728-790, Nesprin2_FRET_Builder.save_xls :1287-1326) and the mirrors' writers get the same
+    rows and must produce the same bytes (column set and order, derived columns, dtypes, float text)."""
+    import pandas as pd
+    from imageprocess_b200.host import Fluor_INT as mF, Nesprin2_FRET_Builder as mN
+    monkeypatch.setattr(pd, "ExcelWriter", _NoExcel)
+    monkeypatch.setattr(pd.DataFrame, "to_excel", lambda self, *a, **k: None)
+    rF, rN = refimport.load("Fluor_INT"), refimport.load("Nesprin2_FRET_Builder")
+    rng = np.random.default_rng(5)
+    stages = ["S01", "S02", "S10"]
+    times = ["t00", "t01", "t12"] if timelapse else [None]
+    rows_i, rows_n, keymap = [], [], {}
+    for s in stages:
+        for tm in times:
+            keymap[(s, tm)] = {1: "a.tif", 2: "b.tif", 10: "c.tif"}
+            for roi in (1, 2, 11):
+                r = {"stage": s, "time": tm, "roi": roi, "area_px": int(rng.integers(50, 5000)), "bg_mode": "percentile",
+                     "bg_scope": "full", "clip_neg": True, "bg_stride": 4}
+                for ch in (1, 2, 10):                        # natural_key order: ch1, ch2, ch10
+                    for k in ("mean", "median", "std", "p5", "p95", "vmin", "vmax", "vsum"):
+                        r[f"ch{ch}_{k}"] = float(np.float32(rng.uniform(0, 5000)))
+                    r[f"ch{ch}_npx"] = int(rng.integers(50, 5000))
+                    r[f"ch{ch}_bg"], r[f"ch{ch}_p"] = float(rng.integers(50, 500)), 1.0
+                rows_i.append(r)
+                n = {"stage": s, "time": tm, "roi": roi, "area_px": int(rng.integers(50, 5000)), "ratio_mode": "FRET/Donor"}
+                for k in ("ratio_mean", "ratio_median", "ratio_std", "ratio_p5", "ratio_p95", "ratio_FoverD_mean",
+                          "ratio_DoverF_mean", "donor_mean", "fret_mean"):
+                    n[k] = float(np.float32(rng.uniform(0, 3)))
+                n.update({"eps": 5.0, "p": 1.0, "donor_p": 1.0, "fret_p": 1.0, "bg_scope": "roi_union", "bg_mode": "percentile",
+                          "clip_neg": True, "sat_filter_on": True, "sat_threshold": 65535.0, "clip_ratio_on": False,
+                          "clip_ratio_max": 10.0, "extra_column_the_writer_drops": 1})
+                rows_n.append(n)
+    for name, ref_fn, our_fn, rows, csv in (
+            ("Fluor_INT", lambda d: rF.save_excel([dict(r) for r in rows_i], keymap, d),
+             lambda d: mF.save_excel([dict(r) for r in rows_i], keymap, d, log=lambda s: None), rows_i, "fluor_intensity_perROI.csv"),
+            ("Nesprin2", lambda d: rN.save_xls([dict(r) for r in rows_n], d, timelapse),
+             lambda d: mN.save_xls([dict(r) for r in rows_n], d, timelapse, log=lambda s: None), rows_n, "nesprin2_fret_perROI.csv")):
+        d_ref, d_our = tmp_path / f"{name}_ref", tmp_path / f"{name}_our"
+        d_ref.mkdir()
+        d_our.mkdir()
+        ref_fn(str(d_ref))
+        our_fn(str(d_our))
+        want, got = (d_ref / csv).read_bytes(), (d_our / csv).read_bytes()
+        assert want.count(b"\n") == len(rows) + 1
+        assert got == want, (name, got[:300], want[:300])
