@@ -13,7 +13,7 @@ def eng():
     return Engine(emu_lib(), NumpyMem())
 
 
-@pytest.mark.parametrize("fn", checks.RASTER_CHECKS, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("fn", checks.RASTER_CHECKS + checks.LATE_CHECKS, ids=lambda f: f.__name__)
 def test_raster(eng, fn):
     fn(eng)
 
