@@ -55,7 +55,8 @@ for seed in range(seed0, seed0 + n):
               "rim_um": float(rng.choice([0.0, 0.3, 1.12, 2.0])), "clip_neg": bool(rng.integers(0, 2)), "ratio_mode": str(rng.choice(["FRET/Donor", "Donor/FRET"])),
               "sat_filter_on": bool(rng.integers(0, 2)), "sat_threshold": float(rng.choice([30000.0, 65535.0, 4000.0])),
               "clip_ratio_on": bool(rng.integers(0, 2)), "clip_ratio_max": float(rng.choice([3.0, 10.0, 0.8])),
-              "bg_scope": str(rng.choice(["full", "roi_union", "annulus"])), "use_spectral": bool(rng.integers(0, 2)),
+              "bg_scope": str(rng.choice(["full", "roi_union", "annulus"])), "bg_mode": str(rng.choice(["percentile", "percentile", "hist-mode"])),
+              "percentile": float(rng.choice([0.5, 1.0, 5.0, 50.0])), "use_spectral": bool(rng.integers(0, 2)),
               "alpha": float(rng.choice([0.0, 0.12, 0.5])), "beta": float(rng.choice([0.0, 0.05])), "g_factor": float(rng.choice([1.0, 1.1, 0.7])),
               "eps_percentile": float(rng.choice([0.0, 1.0, 5.0])), "per_channel_p": bool(rng.integers(0, 2)), "donor_p": float(rng.choice([0.5, 1.0, 5.0])), "fret_p": float(rng.choice([1.0, 3.0]))})
     aonly_ch = 2 if rng.random() < 0.5 else None

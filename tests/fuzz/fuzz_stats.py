@@ -2,7 +2,7 @@
 
 FRET + ROI-intensity in one FrameBatchJob against the oracle: adversarial value distributions (constant, two-valued, saturated, uniform, ramps), random ROIs (also off-frame), random scopes / strides / percentiles / hist-mode.  Found the narrow-ROI bug fixed in round 2 (tests/checks.py: check_narrow_rois).
 
-    python tests/fuzz/fuzz_stats.py <first seed> <number of seeds> [big]     (prints one FAIL line per seed that differs)
+    python tests/fuzz/fuzz_stats.py <first seed> <number of seeds> [big] [hist]     (prints one FAIL line per seed that differs)
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -14,7 +14,7 @@ from tests import checks
 from tests.checks import close, check_int_rows
 from oracle import port
 eng = Engine(emu_lib(), NumpyMem())
-seed0 = int(sys.argv[1]); n = int(sys.argv[2]); BIG = len(sys.argv) > 3 and sys.argv[3] == "big"
+seed0 = int(sys.argv[1]); n = int(sys.argv[2]); BIG = "big" in sys.argv[3:]; HIST = "hist" in sys.argv[3:]      # hist: hist-mode backgrounds in the FRET stage too
 bad = 0; t0 = time.time(); stats = {"miss": 0, "fallback": 0}
 
 def soft_close(a, b, scale):
@@ -70,7 +70,7 @@ for seed in range(seed0, seed0 + n):
             pl.append(np.array([[0.0, 0.0], [W - 1.0, 0.0], [W - 1.0, H - 1.0], [0.0, H - 1.0]]))
         polys.append(pl)
     scope = str(rng.choice(["full", "roi_union"]))
-    fret_p = {"bg_scope": scope, "bg_mode": "percentile", "percentile": float(rng.choice([0.0, 1.0, 5.0, 50.0, 99.0, 100.0])),
+    fret_p = {"bg_scope": scope, "bg_mode": str(rng.choice(["percentile", "percentile", "hist-mode"])) if HIST else "percentile", "percentile": float(rng.choice([0.0, 1.0, 5.0, 50.0, 99.0, 100.0])),
               "per_channel_p": bool(rng.integers(0, 2)), "donor_p": float(rng.choice([0.5, 1.0, 10.0])), "fret_p": float(rng.choice([1.0, 3.0, 30.0])),
               "clip_neg": bool(rng.integers(0, 2)), "eps_percentile": float(rng.choice([0.0, 1.0, 3.0, 50.0])),
               "ratio_mode": str(rng.choice(["Donor/FRET", "FRET/Donor"]))}
