@@ -97,7 +97,8 @@ def analyze_fa_crop(image_crop, roi_mask_crop, config, global_stats, eng=None, w
     labels = mem.empty(h * w, np.int32)
     d_crops = mem.from_host(crops)
     min_px, rad = config["min_px"], config["close_radius"]
-    eng.call("ipb_fa_segment", d_crops.ptr, 1, h, h, mem.from_host(plane.reshape(1, h, w)).ptr, h, w, fa_params.ptr,
+    d_plane = mem.from_host(plane.reshape(1, h, w))          # named: a temporary would be freed before the call runs
+    eng.call("ipb_fa_segment", d_crops.ptr, 1, h, h, d_plane.ptr, h, w, fa_params.ptr,
              pool.ptr, float(min_px) if min_px > 0 else 0.0, int(rad) if rad > 0 else 0, bufs[0].ptr, bufs[1].ptr,
              L.ptr, cs.ptr, bufs[2].ptr, rr.ptr, rb.ptr, cc.ptr, bufs[3].ptr, comp_off.ptr, comps.ptr, cap,
              labels.ptr, 0, None, 8, mem.stream)
@@ -108,6 +109,9 @@ def analyze_fa_crop(image_crop, roi_mask_crop, config, global_stats, eng=None, w
     res.fa_comps = comps.host()[: int(off[1])]
     res.fa_stats = np.array([[m, s, bg, thr]], dtype=np.float32)
     contours = None
+    if with_contours and (h < 2 or w < 2) and int(off[1]) > 0:
+        # find_contours(labeled_img == k, 0.5) of the reference (FA_Analyzer.py:168) refuses such crops
+        raise ValueError("Input array must be at least 2x2.")
     if with_contours and h >= 2 and w >= 2:
         from .. import contours as ct
         rec = mem.empty((h * w, 2), np.uint32)

@@ -210,7 +210,8 @@ def _bg_corrected_images(eng, planes_dev, shape, bgs, clip_neg):
         cfg["donor_ch"], cfg["acc_ch"], cfg["aonly_ch"], cfg["n_ch"] = ci, ci, -1, C
         fp = np.zeros((1, FP_STRIDE), dtype=np.float32)
         fp[0, 0] = fp[0, 1] = np.float32(bgs[ci])
-        eng.call("ipb_fret_pixels", planes_dev.ptr, 1, H, W, cfg.ctypes.data, mem.from_host(fp).ptr, None, 0,
+        d_fp = mem.from_host(fp)                                 # named: a temporary would be freed before the call runs
+        eng.call("ipb_fret_pixels", planes_dev.ptr, 1, H, W, cfg.ctypes.data, d_fp.ptr, None, 0,
                  None, None, None, None, out.ptr + 4 * ci * H * W, None, None, None, 0, mem.stream)
     return out
 

@@ -165,7 +165,8 @@ def segment_inside_polygon(img, poly, thr_param=90.0, min_area=40, tolerance=1.0
     crops["w"], crops["h"], crops["wpr"] = sw, sh, (sw + 31) // 32
     d_fill = mem.from_host(filled.astype(np.int32).reshape(-1))
     rec, rec_n = mem.empty((sh * sw, 2), np.uint32), mem.empty(1, np.uint32)
-    eng.call("ipb_fa_contour_cells", mem.from_host(crops).ptr, 1, sh * sw, d_fill.ptr, rec.ptr, rec_n.ptr, mem.stream)
+    d_crops = mem.from_host(crops)                               # named: a temporary would be freed before the call runs
+    eng.call("ipb_fa_contour_cells", d_crops.ptr, 1, sh * sw, d_fill.ptr, rec.ptr, rec_n.ptr, mem.stream)
     cont = ct.contours_of_crop(rec.host(), int(rec_n.host()[0]), sw).get(1, [])
     if not cont:
         return thr, None, None

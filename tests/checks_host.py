@@ -381,3 +381,49 @@ def check_stream_batches(eng, tmp):
 
 HOST_CHECKS = [check_tiff_roundtrip, check_fluor_int_golden, check_fluor_int_tifs_and_masks, check_fa_mirror,
                check_fret_mirror, check_nesprin2_mirror, check_mor_and_cropper_mirrors, check_stream_batches]
+
+
+def check_fa_crop_arbitrary_masks(eng, tmp):
+    """FA_Analyzer.analyze_fa_crop with masks that are not rasterised polygons (random pixels, an L-shaped block, an
+    empty mask), crops one pixel high or wide (the reference's find_contours refuses those with a ValueError as soon
+    as a region exists), repeated calls giving identical results (the image plane used to be uploaded through a
+    temporary that was freed before the call ran)."""
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(17)
+    stats = port.fa_global_stats(rng.poisson(500, (64, 64)).astype(np.float32))
+    for h, w, kind in ((40, 31, 0), (29, 33, 1), (61, 35, 2), (17, 64, 3), (2, 2, 0), (3, 70, 1)):
+        img = rng.poisson(500, (h, w)).astype(np.int64)
+        img[ndi.binary_dilation(rng.random((h, w)) < 0.05)] += 2500
+        crop = img.astype(np.float32)
+        mask = [np.ones((h, w), bool), rng.random((h, w)) < 0.7, np.zeros((h, w), bool), np.zeros((h, w), bool)][kind]
+        if kind == 2:
+            mask[h // 4:, : 3 * w // 4] = True
+        cfg = {"alpha": 2.0, "min_px": float(rng.choice([0.0, 2.5, 6.0])), "max_px": 400.0, "close_radius": int(rng.integers(0, 4)),
+               "subtract_bg": True}
+        want = port.analyze_fa_crop(crop, mask, cfg, stats, with_contours=True)
+        for rep in range(3):
+            got = FA_Analyzer.analyze_fa_crop(crop, mask, cfg, stats, eng=eng)
+            assert got[1] == want[1] and np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3]), (h, w, kind, rep)
+            for cat in ("OK", "Large", "Small"):
+                assert [(g["label"], g["area"], g["centroid"]) for g in got[0][cat]] == \
+                       [(x["label"], x["area"], x["centroid"]) for x in want[0][cat]]
+                assert all(np.array_equal(g["contour"], x["contour"]) for g, x in zip(got[0][cat], want[0][cat]))
+    row = np.full((1, 40), 400.0, np.float32)
+    row[0, 10:20] = 5000.0
+    cfg = {"alpha": 2.0, "min_px": 0.0, "max_px": 400.0, "close_radius": 0, "subtract_bg": True}
+    for crop in (row, row.T.copy()):
+        m = np.ones(crop.shape, bool)
+        for fn in (lambda: port.analyze_fa_crop(crop, m, cfg, stats, with_contours=True),
+                   lambda: FA_Analyzer.analyze_fa_crop(crop, m, cfg, stats, eng=eng)):
+            try:
+                fn()
+                raise AssertionError("a 1-pixel-thin crop with a region must raise like skimage's find_contours")
+            except ValueError as e:
+                assert str(e) == "Input array must be at least 2x2."
+        # without a region above the threshold nothing is traced and nothing is raised
+        dark = np.full(crop.shape, 400.0, np.float32)
+        assert FA_Analyzer.analyze_fa_crop(dark, m, cfg, stats, eng=eng)[0] == port.analyze_fa_crop(dark, m, cfg, stats)[0]
+
+
+# added after the round's last GPU session: the GPU tier runs it from tests/test_gpu_zz_late_checks.py
+LATE_HOST_CHECKS = [check_fa_crop_arbitrary_masks]

@@ -12,7 +12,7 @@ def eng():
     return Engine(emu_lib(), NumpyMem())
 
 
-@pytest.mark.parametrize("fn", checks_host.HOST_CHECKS, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("fn", checks_host.HOST_CHECKS + checks_host.LATE_HOST_CHECKS, ids=lambda f: f.__name__)
 def test_host(eng, fn, tmp_path):
     fn(eng, str(tmp_path))
 

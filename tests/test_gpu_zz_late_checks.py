@@ -3,7 +3,7 @@
 has already run on a B200."""
 import pytest
 
-from tests import checks
+from tests import checks, checks_host
 
 pytestmark = pytest.mark.gpu
 
@@ -17,3 +17,8 @@ def eng():
 @pytest.mark.parametrize("fn", checks.LATE_CHECKS, ids=lambda f: f.__name__)
 def test_late_check(eng, fn):
     fn(eng)
+
+
+@pytest.mark.parametrize("fn", checks_host.LATE_HOST_CHECKS, ids=lambda f: f.__name__)
+def test_late_host_check(eng, fn, tmp_path):
+    fn(eng, str(tmp_path))
