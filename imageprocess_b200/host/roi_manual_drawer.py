@@ -75,7 +75,8 @@ def _label_crop(eng, plane_dev, h, w, mask_pool, thr, conn):
     wpr = (w + 31) // 32
     crops = np.zeros(1, dtype=CROP)
     crops["w"], crops["h"], crops["wpr"] = w, h, wpr
-    sizes = eng.lib.sizes("ipb_fa_segment_sizes", 9, 1, np.array([w, h], dtype=np.int32).ctypes.data, 1)
+    crop_wh = np.array([w, h], dtype=np.int32)                   # named: a temporary would be freed before the call runs
+    sizes = eng.lib.sizes("ipb_fa_segment_sizes", 9, 1, crop_wh.ctypes.data, 1)
     bufs = [mem.empty(sizes[0], np.uint8) for _ in range(4)]
     L, cs = mem.empty(sizes[1], np.uint8), mem.empty(sizes[1], np.uint8)
     rr, rb = mem.empty(sizes[2], np.uint8), mem.empty(sizes[2], np.uint8)
