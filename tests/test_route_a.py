@@ -158,3 +158,12 @@ def test_fret_stage_and_mor_rebound(emu_engine, tmp_path):
     assert set(got) == set(want) and got["area_px"] == want["area_px"]
     for k, wv in want.items():
         assert close(float(got[k]), float(wv), 1e-9), k
+
+
+@pytest.mark.parametrize("seed", [0, 3, 5])
+def test_nesprin2_run_pipeline_against_reference(emu_engine, seed):
+    """Nesprin2_FRET_Builder.run_pipeline(p) of the unmodified reference and of the mirror on the same random folder and
+    parameter dict (tests/fuzz/fuzz_route_a_nesprin2.py: 600 such folders were run by hand): the two
+    nesprin2_fret_perROI.csv agree cell for cell."""
+    from tests.fuzz import fuzz_route_a_nesprin2 as fz
+    assert fz.run_seed(seed, refimport.load("Nesprin2_FRET_Builder")) > 0
