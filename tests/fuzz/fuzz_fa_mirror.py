@@ -5,7 +5,7 @@ The FA boundary function itself, host/FA_Analyzer.analyze_fa_crop(image_crop, ro
 loader hands them over, empty / one-row / one-column crops, against oracle.port.analyze_fa_crop: threshold value, binary
 image, label map, the three lists of per-adhesion dicts incl. contours.
 
-    python tests/fuzz/fuzz_fa_mirror.py <first seed> <number of seeds>
+    python tests/fuzz/fuzz_fa_mirror.py <first seed> <number of seeds> [ref]
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -18,6 +18,13 @@ from tests.checks import close
 from oracle import port
 eng = Engine(emu_lib(), NumpyMem())
 seed0 = int(sys.argv[1]); n = int(sys.argv[2])
+if "ref" in sys.argv[3:]:            # expected side = the UNMODIFIED reference function (build container only) instead of the oracle port
+    from oracle import refimport
+    refimport.install_stubs()
+    _ref = refimport.load("FA_Analyzer")
+    expected = lambda crop, mask, cfg, stats: _ref.analyze_fa_crop(crop, mask, cfg, stats)
+else:
+    expected = lambda crop, mask, cfg, stats: port.analyze_fa_crop(crop, mask, cfg, stats, with_contours=True)
 bad = 0; t0 = time.time()
 for seed in range(seed0, seed0 + n):
     rng = np.random.default_rng(seed)
@@ -38,7 +45,7 @@ for seed in range(seed0, seed0 + n):
            "close_radius": int(rng.integers(0, 6)), "subtract_bg": bool(rng.integers(0, 2))}
     try:
         try:
-            want = port.analyze_fa_crop(crop, mask, cfg, stats, with_contours=True)
+            want = expected(crop, mask, cfg, stats)
         except ValueError as e:                  # find_contours refuses crops smaller than 2 x 2 that hold a region
             try:
                 mFA.analyze_fa_crop(crop, mask, cfg, stats, eng=eng)
