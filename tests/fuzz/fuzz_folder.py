@@ -14,12 +14,12 @@ import numpy as np
 from oracle import refimport
 import imageprocess_b200 as ipb
 from imageprocess_b200.ops import Engine
-from imageprocess_b200.host import Fluor_INT as mF, common
+from imageprocess_b200.host import Fluor_INT as mF, common, fret_ratio_builder as mR
 from tests.emu.emu_backend import NumpyMem, emu_lib
 from tests.checks import close
 ipb._engine = Engine(emu_lib(), NumpyMem())
 refimport.install_stubs()
-rF = refimport.load("Fluor_INT")
+rF, rR = refimport.load("Fluor_INT"), refimport.load("fret_ratio_builder")
 seed0 = int(sys.argv[1]); n = int(sys.argv[2])
 bad = 0; t0 = time.time(); stats = {"rows": 0, "broken_keys": 0}
 for seed in range(seed0, seed0 + n):
@@ -80,6 +80,44 @@ for seed in range(seed0, seed0 + n):
                 else:
                     assert gv == wv, (k, gv, wv)
         stats["rows"] += len(want)
+        # the same folder through fret_ratio_builder.process_one_stage, stage by stage, in small batches
+        pf = {"img_dir": root, "roi_dir": roi_dir, "out_root": "", "timelapse": True, "ratio_mode": str(rng.choice(["Donor/FRET", "FRET/Donor"])),
+              "donor_ch": 1, "acceptor_ch": 2, "fret_ch": 2, "bg_scope": str(rng.choice(["full", "roi_union"])), "bg_mode": "percentile",
+              "percentile": 1.0, "per_channel_p": False, "donor_p": 1.0, "fret_p": 1.0, "clip_neg": bool(rng.integers(0, 2)), "eps_percentile": 1.0,
+              "px_um": None, "out_xls": False, "out_tif": False, "out_png": False, "save_full": False, "save_crop": False, "mask_outside": True,
+              "apply_cmap": True, "cmap_name": "jet", "show_colorbar": False, "png_dpi": 300, "add_scalebar": False, "scale_bar_um": 20.0,
+              "cmin_txt": "", "cmax_txt": "", "fixed_crop": True, "crop_w": 500, "crop_h": 500, "subset_on": False, "subset_stage": "",
+              "subset_time": "", "subset_roi": "", "n_workers": 1, "lang": "en"}
+        pairs_all, _ = mR.build_pairs_by_channel(common.list_tifs(root), True, 1, 2)
+        for stage in ("S01", "S02", "S03"):
+            pairs = [pr for pr in pairs_all if pr[0][0] == stage]
+            paths = (root, None, None, None, None, None, None)
+            try:
+                with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+                    _, wrows, _ = rR.process_one_stage(stage, pairs, dict(pf), paths)
+            except Exception as e:                      # the reference lets an unreadable image fail the whole stage
+                try:
+                    mR.process_one_stage(stage, pairs, dict(pf), paths, frames_per_batch=int(rng.choice([1, 2, 3, 5])))
+                    stats["ref_stage_fails_ours_continues"] = stats.get("ref_stage_fails_ours_continues", 0) + 1
+                except Exception:
+                    stats["both_fail_stage"] = stats.get("both_fail_stage", 0) + 1
+                continue
+            _, grows, _ = mR.process_one_stage(stage, pairs, dict(pf), paths, frames_per_batch=int(rng.choice([1, 2, 3, 5])))
+            assert [(g["stage"], g["time"], g["roi"]) for g in grows] == [(w["stage"], w["time"], w["roi"]) for w in wrows], ("FRET order", stage, len(grows), len(wrows))
+            for g, w in zip(grows, wrows):
+                for k, wv in w.items():
+                    gv = g[k]
+                    if isinstance(wv, float) and math.isnan(wv):
+                        assert math.isnan(gv), k
+                    elif k == "eps":
+                        assert np.float32(gv) == np.float32(wv), k
+                    elif isinstance(wv, float) and k.endswith(("_mean", "_std")):
+                        pre = k.rsplit("_", 1)[0]
+                        scale = abs(w[pre + "_median"]) + (abs(w["ratio_p5"]) + abs(w["ratio_p95"]) if pre == "ratio" else 0.0)
+                        assert close(gv, wv) or abs(gv - wv) <= 1e-5 * scale, (k, gv, wv)
+                    else:
+                        assert gv == wv, (k, gv, wv)
+            stats["fret_rows"] = stats.get("fret_rows", 0) + len(wrows)
     except Exception as e:
         bad += 1
         tb = traceback.extract_tb(e.__traceback__)
